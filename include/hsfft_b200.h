@@ -1,0 +1,74 @@
+/*
+ * hsfft_b200.h -- additive API of hsfft-b200 (nothing here exists in the reference; nothing here
+ * changes a reference symbol).  Everything is plain C ABI: pointers and sizes.
+ *
+ *   1. fft_convolve / next_power_of_two / find_optimal_fft_length: the reference DEFINES these in
+ *      src/convolve.c:20,39,74 but declares them in no header; they are declared here.
+ *   2. Batched entry points with HOST pointers (fft_exec_batch ...): what a caller looping
+ *      fft_exec over a batch should call instead; copies are chunked and pipelined.
+ *   3. Batched entry points with DEVICE pointers (*_dev): the path the roofline is measured on.
+ *   4. Small device helpers so a C caller needs no CUDA headers.
+ *
+ * Layouts: complex data is interleaved {re, im} doubles (fft_data); a batch is `howmany`
+ * transforms stored back to back (row stride = transform length unless a stride is given).
+ */
+#ifndef HSFFT_B200_H_
+#define HSFFT_B200_H_
+
+#include "real.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- 1. convolution (reference src/convolve.c:20-25, :39-55, :74-214) ---- */
+int next_power_of_two(int n);
+int find_optimal_fft_length(int min_length, const char *conv_type, int length1, int length2);
+/* type: "full" | "same" | "valid"; conv_type: "linear" | "circular".  Returns the number of
+ * samples written to output, or -1 on invalid arguments. */
+int fft_convolve(const char *type, const char *conv_type, fft_type *input1, int length1,
+                 fft_type *input2, int length2, fft_type *output);
+
+/* ---- 2. batched, host pointers ---- */
+void fft_exec_batch(fft_object obj, fft_data *inp, fft_data *oup, long howmany);
+/* r2c: rows of N reals in, rows of N bins out (full mirrored spectrum, like fft_r2c_exec) */
+void fft_r2c_exec_batch(fft_real_object obj, fft_type *inp, fft_data *oup, long howmany);
+/* c2r: rows of N bins in (bins 0..N/2 are read), rows of N reals out */
+void fft_c2r_exec_batch(fft_real_object obj, fft_data *inp, fft_type *oup, long howmany);
+/* howmany independent convolutions: rows of length1 / length2 samples, output rows of out_stride */
+int fft_convolve_batch(const char *type, const char *conv_type, fft_type *input1, int length1,
+                       fft_type *input2, int length2, fft_type *output, long out_stride, long howmany);
+
+/* ---- 3. batched, device pointers (stream: a cudaStream_t passed as void*, NULL = default) ---- */
+void fft_exec_batch_dev(fft_object obj, const fft_data *d_in, fft_data *d_out, long howmany, void *stream);
+/* out_stride: complex elements between output rows (>= N/2+1); full != 0 also writes the mirror
+ * bins N/2+1..N-1 (needs out_stride >= N), full == 0 writes bins 0..N/2 only. */
+void fft_r2c_exec_batch_dev(fft_real_object obj, const fft_type *d_in, fft_data *d_out, long out_stride, int full,
+                            long howmany, void *stream);
+/* in_stride: complex elements between input rows (>= N/2+1); bins 0..N/2 are read */
+void fft_c2r_exec_batch_dev(fft_real_object obj, const fft_data *d_in, long in_stride, fft_type *d_out, long howmany,
+                            void *stream);
+int fft_convolve_batch_dev(const char *type, const char *conv_type, const fft_type *d_in1, int length1,
+                           const fft_type *d_in2, int length2, fft_type *d_out, long out_stride, long howmany,
+                           void *stream);
+
+/* ---- 4. device helpers ---- */
+int   hsfft_device_count(void);          /* 0 when no usable CUDA device */
+void  hsfft_set_device(int dev);         /* plans are bound to the device current at their first execute */
+int   hsfft_get_device(void);
+void *hsfft_malloc_device(size_t bytes);
+void  hsfft_free_device(void *d);
+void *hsfft_malloc_host(size_t bytes);   /* pinned host memory for the host-pointer batch calls */
+void  hsfft_free_host(void *h);
+void  hsfft_copy_h2d(void *d, const void *h, size_t bytes);
+void  hsfft_copy_d2h(void *h, const void *d, size_t bytes);
+void  hsfft_sync(void);
+long long hsfft_launch_count(void);      /* kernels this library has launched in this process */
+/* human-readable description of how a plan will execute (kernel family, passes); static buffer */
+const char *hsfft_plan_describe(fft_object obj);
+const char *hsfft_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HSFFT_B200_H_ */

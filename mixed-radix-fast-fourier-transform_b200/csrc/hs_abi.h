@@ -1,0 +1,102 @@
+/*
+ * hs_abi.h -- the thin C ABI between the host side (plain C: plan builder, public API,
+ * hsfft_plan.c / hsfft_real.c / hsfft_convolve.c) and the CUDA side (hs_device.cu: memory,
+ * streams, kernel launches).  Plain pointers and sizes only.  Not installed; the public
+ * headers are include/highspeedFFT.h, include/real.h and include/hsfft_b200.h.
+ *
+ * Error convention (reference SURVEY.md section 5 "Metrics / logging"): every CUDA failure
+ * prints one line to stderr and exit(EXIT_FAILURE)s, like the reference's own argument checks.
+ */
+#ifndef HS_ABI_H_
+#define HS_ABI_H_
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HS_MAX_STAGES 32
+#define HS_MAX_GENERIC_RADIX 128
+
+/* compile-time kernel families */
+enum { HS_CT_C2C = 0, HS_CT_BLUESTEIN = 1, HS_CT_COLS = 2, HS_CT_ROWS = 3 };
+
+/* one compile-time specialised shared-memory transform the CUDA side offers */
+typedef struct hs_ct_desc {
+    int id;
+    int family;     /* HS_CT_* */
+    int n;          /* transform length held in shared memory */
+    int nst;        /* stages */
+    int radix[8];   /* execution order (leaf first) */
+    int nlogical;   /* Bluestein: the logical N this instance serves (0 = any up to (n+1)/2) */
+    int threads, smem_bytes;
+} hs_ct_desc;
+
+/* parameters of one run-time planned pass (see hs_generic.cuh) */
+typedef struct hs_gen_params {
+    int n, nst, C, npad;
+    int radix[HS_MAX_STAGES];
+    int tw_off[HS_MAX_STAGES];
+    int gen_off[HS_MAX_STAGES];
+    long long n_c, n_o, n_batch;
+    long long in_b, in_o, in_c, in_e;
+    long long out_b, out_o, out_c, out_e;
+    int load_c_fast, store_c_fast;
+    long long tw_L;
+    int tw_S;
+    const void *tw, *tw_lo, *tw_hi;
+    const double *gen_cs, *gen_sn;
+} hs_gen_params;
+
+/* ---- device / memory / streams ---- */
+int   hs_cu_device_count(void);
+void  hs_cu_require_device(void);            /* exits with a message when no CUDA device is usable */
+int   hs_cu_get_device(void);
+void  hs_cu_set_device(int dev);
+void *hs_cu_malloc(size_t bytes);
+void  hs_cu_free(void *d);
+void *hs_cu_malloc_host(size_t bytes);       /* pinned */
+void  hs_cu_free_host(void *h);
+void  hs_cu_h2d(void *d, const void *h, size_t bytes, void *stream);
+void  hs_cu_d2h(void *h, const void *d, size_t bytes, void *stream);
+void  hs_cu_d2d(void *dst, const void *src, size_t bytes, void *stream);
+void  hs_cu_memset0(void *d, size_t bytes, void *stream);
+void *hs_cu_stream_create(void);
+void  hs_cu_stream_destroy(void *stream);
+void  hs_cu_stream_sync(void *stream);
+void *hs_cu_event_create(void);
+void  hs_cu_event_destroy(void *ev);
+void  hs_cu_event_record(void *ev, void *stream);
+void  hs_cu_stream_wait_event(void *stream, void *ev);
+float hs_cu_event_elapsed_ms(void *start, void *stop);
+void  hs_cu_event_sync(void *ev);
+int   hs_cu_sm_count(void);
+long long hs_cu_launch_count(void);          /* kernels launched by this library so far */
+
+/* ---- compile-time kernels ---- */
+int   hs_cu_ct_count(void);
+const hs_ct_desc *hs_cu_ct_get(int idx);
+/* batched contiguous c2c, transform b at in + b*n */
+void  hs_cu_launch_ct_c2c(int id, int sgn, const void *d_in, void *d_out, const void *d_tw, long long howmany, void *stream);
+/* fused Bluestein: d_tw_f / d_tw_i are the forward-order / inverse-order stage tables of length M */
+void  hs_cu_launch_ct_bluestein(int id, int sgn, int N, const void *d_in, void *d_out, const void *d_tw_f, const void *d_tw_i,
+                                const void *d_chirp, const void *d_hk, long long howmany, void *stream);
+
+/* ---- run-time planned pass and element-wise helpers ---- */
+void  hs_cu_launch_generic(int sgn, const void *d_in, void *d_out, const hs_gen_params *p, void *stream);
+void  hs_cu_launch_chirp_pad(int sgn, const void *x, void *a, const void *h, int N, int M, long long howmany, void *stream);
+void  hs_cu_launch_spectrum_mul(int sgn, void *A, const void *Hk, int M, long long howmany, void *stream);
+void  hs_cu_launch_chirp_crop(int sgn, const void *y, void *out, const void *h, int N, int M, long long howmany, void *stream);
+void  hs_cu_launch_r2c_post(const void *Z, void *out, const void *tw2, int H, long long out_stride, int full, long long howmany,
+                            void *stream);
+void  hs_cu_launch_c2r_pre(const void *in, void *z, const void *tw2, int H, long long in_stride, long long howmany, void *stream);
+void  hs_cu_launch_conv_mul(const void *A, const void *B, void *C, long long total, double scale, void *stream);
+/* rows of len reals -> rows of P reals, zero padded; rows of P reals -> rows [start, start+len) */
+void  hs_cu_launch_pad_rows(const void *src, int len, void *dst, int P, long long howmany, void *stream);
+void  hs_cu_launch_slice_rows(const void *src, int P, int start, int len, void *dst, long long dst_stride, long long howmany,
+                              void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,116 @@
+// hs_ct_table.cuh -- the table of compile-time specialised plans and their dispatch.
+// Included by hs_device.cu (CUDA launchers) and by tests/emu/hs_device_emu.cpp (CPU emulation of the
+// same kernels); the including file provides launch_c2c<P,SGN,MINB>() / launch_blu<PF,PI,SGN,MINB>()
+// and the hs_stream_t type before including this header.
+#pragma once
+#include <cstdio>
+#include <cstdlib>
+#include "hs_abi.h"
+#include "hs_fused.cuh"
+#include "hs_smem_fft.cuh"
+
+// ------------------------------------------------------------------------ compile-time plan table
+// Stage radices in execution order (the reference's factor list reversed; runs of power-of-two
+// factors regrouped, which only exact constants allow -- SURVEY.md section 8c).  LOGPAD values come
+// from tests/emu/bank_check.py (all stages conflict free).
+//                      N     T   X  LOGPAD  radices...
+using P4096a = HsPlan<4096, 256, 1, 4, 16, 16, 16>;       // reference factors [8,8,8,8]
+using P4096b = HsPlan<4096, 512, 1, 3, 8, 8, 8, 8>;
+using P3000  = HsPlan<3000, 200, 1, 3, 3, 5, 5, 5, 8>;    // reference factors [8,5,5,5,3], verbatim
+using P1024  = HsPlan<1024, 64, 4, 3, 16, 8, 8>;          // reference factors [8,8,8,2]
+using P2048  = HsPlan<2048, 128, 2, 3, 16, 16, 8>;        // reference factors [8,8,8,4]
+using P512   = HsPlan<512, 64, 4, 3, 8, 8, 8>;
+using P256   = HsPlan<256, 16, 16, 4, 16, 16>;
+using P8192  = HsPlan<8192, 512, 1, 4, 8, 8, 8, 16>;
+// fused Bluestein, M = 2048 (N = 513..1024, e.g. the N = 1009 config): forward / inverse pair
+using PB2048f = HsPlan<2048, 128, 2, 4, 8, 16, 16>;
+using PB2048i = HsPlan<2048, 128, 2, 4, 16, 16, 8>;
+
+template <class P>
+static void fill_desc(hs_ct_desc &d, int id, int family)
+{
+    d.id = id;
+    d.family = family;
+    d.n = P::N;
+    d.nst = P::NST;
+    for (int s = 0; s < 8; ++s) d.radix[s] = s < P::NST ? P::radix(s) : 0;
+    d.nlogical = 0;
+    d.threads = P::threads;
+    d.smem_bytes = P::smem_bytes;
+}
+
+enum { CT_4096A = 0, CT_4096B, CT_3000, CT_1024, CT_2048, CT_512, CT_256, CT_8192, CT_B2048, CT_COUNT };
+static hs_ct_desc g_ct[CT_COUNT];
+static int g_ct_order[CT_COUNT];
+static bool g_ct_ready = false;
+
+static void ct_init()
+{
+    if (g_ct_ready) return;
+    fill_desc<P4096a>(g_ct[CT_4096A], CT_4096A, HS_CT_C2C);
+    fill_desc<P4096b>(g_ct[CT_4096B], CT_4096B, HS_CT_C2C);
+    fill_desc<P3000>(g_ct[CT_3000], CT_3000, HS_CT_C2C);
+    fill_desc<P1024>(g_ct[CT_1024], CT_1024, HS_CT_C2C);
+    fill_desc<P2048>(g_ct[CT_2048], CT_2048, HS_CT_C2C);
+    fill_desc<P512>(g_ct[CT_512], CT_512, HS_CT_C2C);
+    fill_desc<P256>(g_ct[CT_256], CT_256, HS_CT_C2C);
+    fill_desc<P8192>(g_ct[CT_8192], CT_8192, HS_CT_C2C);
+    fill_desc<PB2048f>(g_ct[CT_B2048], CT_B2048, HS_CT_BLUESTEIN);
+    for (int i = 0; i < CT_COUNT; ++i) g_ct_order[i] = i;
+    // HSFFT_PREFER_CT=<id>: list that instance first (A/B runs of alternative plans for one N)
+    if (const char *e = getenv("HSFFT_PREFER_CT")) {
+        const int want = atoi(e);
+        if (want > 0 && want < CT_COUNT) { g_ct_order[0] = want; for (int i = 1; i <= want; ++i) g_ct_order[i] = i - 1; }
+    }
+    // HSFFT_NO_CT=1: hide the compile-time kernels (exercise the run-time planned engine)
+    g_ct_ready = true;
+}
+
+extern "C" int hs_cu_ct_count(void)
+{
+    ct_init();
+    if (const char *e = getenv("HSFFT_NO_CT")) if (atoi(e) != 0) return 0;
+    return CT_COUNT;
+}
+extern "C" const hs_ct_desc *hs_cu_ct_get(int idx)
+{
+    ct_init();
+    return (idx >= 0 && idx < CT_COUNT) ? &g_ct[g_ct_order[idx]] : nullptr;
+}
+
+template <class P, int MINB>
+static void launch_c2c_sgn(int sgn, const void *in, void *out, const void *tw, long long howmany, hs_stream_t st)
+{
+    if (sgn == 1) launch_c2c<P, 1, MINB>(in, out, tw, howmany, st);
+    else launch_c2c<P, -1, MINB>(in, out, tw, howmany, st);
+}
+
+extern "C" void hs_cu_launch_ct_c2c(int id, int sgn, const void *d_in, void *d_out, const void *d_tw, long long howmany, void *stream)
+{
+    hs_stream_t st = (hs_stream_t)stream;
+    switch (id) {
+    case CT_4096A: launch_c2c_sgn<P4096a, 2>(sgn, d_in, d_out, d_tw, howmany, st); break;
+    case CT_4096B: launch_c2c_sgn<P4096b, 2>(sgn, d_in, d_out, d_tw, howmany, st); break;
+    case CT_3000: launch_c2c_sgn<P3000, 3>(sgn, d_in, d_out, d_tw, howmany, st); break;
+    case CT_1024: launch_c2c_sgn<P1024, 2>(sgn, d_in, d_out, d_tw, howmany, st); break;
+    case CT_2048: launch_c2c_sgn<P2048, 2>(sgn, d_in, d_out, d_tw, howmany, st); break;
+    case CT_512: launch_c2c_sgn<P512, 3>(sgn, d_in, d_out, d_tw, howmany, st); break;
+    case CT_256: launch_c2c_sgn<P256, 3>(sgn, d_in, d_out, d_tw, howmany, st); break;
+    case CT_8192: launch_c2c_sgn<P8192, 1>(sgn, d_in, d_out, d_tw, howmany, st); break;
+    default: fprintf(stderr, "Error: unknown compile-time kernel id %d\n", id); exit(EXIT_FAILURE);
+    }
+}
+
+extern "C" void hs_cu_launch_ct_bluestein(int id, int sgn, int N, const void *d_in, void *d_out, const void *d_tw_f, const void *d_tw_i,
+                                          const void *d_chirp, const void *d_hk, long long howmany, void *stream)
+{
+    hs_stream_t st = (hs_stream_t)stream;
+    switch (id) {
+    case CT_B2048:
+        if (sgn == 1) launch_blu<PB2048f, PB2048i, 1, 2>(N, d_in, d_out, d_tw_f, d_tw_i, d_chirp, d_hk, howmany, st);
+        else launch_blu<PB2048f, PB2048i, -1, 2>(N, d_in, d_out, d_tw_f, d_tw_i, d_chirp, d_hk, howmany, st);
+        break;
+    default: fprintf(stderr, "Error: unknown fused Bluestein kernel id %d\n", id); exit(EXIT_FAILURE);
+    }
+}
+

@@ -1,0 +1,252 @@
+// hs_device.cu -- the CUDA side of the thin C ABI (hs_abi.h): device/stream/memory helpers and
+// the launchers of the sm_100a kernels.  Built only by nvcc for sm_100a; there is no other backend.
+#include <cstdio>
+#include <cstdlib>
+#include <atomic>
+
+#include "hs_abi.h"
+#include "hs_fused.cuh"
+#include "hs_generic.cuh"
+#include "hs_smem_fft.cuh"
+
+#define HS_CUDA_CHECK(expr)                                                                            \
+    do {                                                                                               \
+        cudaError_t e_ = (expr);                                                                       \
+        if (e_ != cudaSuccess) {                                                                       \
+            fprintf(stderr, "Error: CUDA failure %s at %s:%d (%s)\n", cudaGetErrorString(e_), __FILE__, \
+                    __LINE__, #expr);                                                                  \
+            exit(EXIT_FAILURE);                                                                        \
+        }                                                                                              \
+    } while (0)
+
+static std::atomic<long long> g_launches{0};
+
+typedef cudaStream_t hs_stream_t;
+
+// ----------------------------------------------------------------------------- device management
+static int g_dev_count = -2;
+
+extern "C" int hs_cu_device_count(void)
+{
+    if (g_dev_count == -2) {
+        int n = 0;
+        if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); n = 0; }
+        g_dev_count = n;
+    }
+    return g_dev_count;
+}
+extern "C" void hs_cu_require_device(void)
+{
+    if (hs_cu_device_count() <= 0) {
+        fprintf(stderr, "Error: hsfft-b200 needs a CUDA device (sm_100a); there is no CPU fallback\n");
+        exit(EXIT_FAILURE);
+    }
+}
+extern "C" int hs_cu_get_device(void) { int d = 0; HS_CUDA_CHECK(cudaGetDevice(&d)); return d; }
+extern "C" void hs_cu_set_device(int dev) { HS_CUDA_CHECK(cudaSetDevice(dev)); }
+extern "C" int hs_cu_sm_count(void)
+{
+    int dev = 0, n = 0;
+    HS_CUDA_CHECK(cudaGetDevice(&dev));
+    HS_CUDA_CHECK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    return n;
+}
+extern "C" void *hs_cu_malloc(size_t bytes)
+{
+    void *p = nullptr;
+    HS_CUDA_CHECK(cudaMalloc(&p, bytes ? bytes : 16));
+    return p;
+}
+extern "C" void hs_cu_free(void *d) { if (d) HS_CUDA_CHECK(cudaFree(d)); }
+extern "C" void *hs_cu_malloc_host(size_t bytes)
+{
+    void *p = nullptr;
+    HS_CUDA_CHECK(cudaMallocHost(&p, bytes ? bytes : 16));
+    return p;
+}
+extern "C" void hs_cu_free_host(void *h) { if (h) HS_CUDA_CHECK(cudaFreeHost(h)); }
+extern "C" void hs_cu_h2d(void *d, const void *h, size_t bytes, void *stream)
+{
+    if (!bytes) return;
+    if (stream) HS_CUDA_CHECK(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    else HS_CUDA_CHECK(cudaMemcpy(d, h, bytes, cudaMemcpyHostToDevice));
+}
+extern "C" void hs_cu_d2h(void *h, const void *d, size_t bytes, void *stream)
+{
+    if (!bytes) return;
+    if (stream) HS_CUDA_CHECK(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    else HS_CUDA_CHECK(cudaMemcpy(h, d, bytes, cudaMemcpyDeviceToHost));
+}
+extern "C" void hs_cu_d2d(void *dst, const void *src, size_t bytes, void *stream)
+{
+    if (bytes) HS_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+}
+extern "C" void hs_cu_memset0(void *d, size_t bytes, void *stream)
+{
+    if (bytes) HS_CUDA_CHECK(cudaMemsetAsync(d, 0, bytes, (cudaStream_t)stream));
+}
+extern "C" void *hs_cu_stream_create(void)
+{
+    cudaStream_t s;
+    HS_CUDA_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    return (void *)s;
+}
+extern "C" void hs_cu_stream_destroy(void *stream) { if (stream) HS_CUDA_CHECK(cudaStreamDestroy((cudaStream_t)stream)); }
+extern "C" void hs_cu_stream_sync(void *stream) { HS_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream)); }
+extern "C" void *hs_cu_event_create(void)
+{
+    cudaEvent_t e;
+    HS_CUDA_CHECK(cudaEventCreate(&e));
+    return (void *)e;
+}
+extern "C" void hs_cu_event_destroy(void *ev) { if (ev) HS_CUDA_CHECK(cudaEventDestroy((cudaEvent_t)ev)); }
+extern "C" void hs_cu_event_record(void *ev, void *stream) { HS_CUDA_CHECK(cudaEventRecord((cudaEvent_t)ev, (cudaStream_t)stream)); }
+extern "C" void hs_cu_stream_wait_event(void *stream, void *ev)
+{
+    HS_CUDA_CHECK(cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)ev, 0));
+}
+extern "C" float hs_cu_event_elapsed_ms(void *start, void *stop)
+{
+    float ms = 0.f;
+    HS_CUDA_CHECK(cudaEventElapsedTime(&ms, (cudaEvent_t)start, (cudaEvent_t)stop));
+    return ms;
+}
+extern "C" void hs_cu_event_sync(void *ev) { HS_CUDA_CHECK(cudaEventSynchronize((cudaEvent_t)ev)); }
+extern "C" long long hs_cu_launch_count(void) { return g_launches.load(); }
+
+// --------------------------------------------------------------------------------------- launchers
+static void check_grid(long long blocks)
+{
+    if (blocks <= 0 || blocks > 2147483647LL) {
+        fprintf(stderr, "Error: batch too large for one launch (%lld CTAs)\n", blocks);
+        exit(EXIT_FAILURE);
+    }
+}
+
+template <class P, int SGN, int MINB>
+static void launch_c2c(const void *in, void *out, const void *tw, long long howmany, cudaStream_t st)
+{
+    auto kern = hs_c2c_smem_kernel<P, SGN, MINB>;
+    static bool attr_done = false; // per instantiation
+    if (!attr_done) {
+        HS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P::smem_bytes));
+        attr_done = true;
+    }
+    const long long blocks = (howmany + P::X - 1) / P::X;
+    check_grid(blocks);
+    kern<<<(unsigned)blocks, P::threads, P::smem_bytes, st>>>((const cplx *)in, (cplx *)out, (const cplx *)tw, howmany);
+    HS_CUDA_CHECK(cudaGetLastError());
+    ++g_launches;
+}
+
+template <class PF, class PI, int SGN, int MINB>
+static void launch_blu(int N, const void *in, void *out, const void *twf, const void *twi, const void *chirp, const void *hk,
+                       long long howmany, cudaStream_t st)
+{
+    auto kern = hs_bluestein_kernel<PF, PI, SGN, MINB>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        HS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PF::smem_bytes));
+        attr_done = true;
+    }
+    const long long blocks = (howmany + PF::X - 1) / PF::X;
+    check_grid(blocks);
+    kern<<<(unsigned)blocks, PF::threads, PF::smem_bytes, st>>>((const cplx *)in, (cplx *)out, (const cplx *)twf, (const cplx *)twi,
+                                                                 (const cplx *)chirp, (const cplx *)hk, N, howmany);
+    HS_CUDA_CHECK(cudaGetLastError());
+    ++g_launches;
+}
+
+#include "hs_ct_table.cuh"
+
+extern "C" void hs_cu_launch_generic(int sgn, const void *d_in, void *d_out, const hs_gen_params *p, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long ntile = (p->n_c + p->C - 1) / p->C;
+    const long long blocks = ntile * p->n_o * p->n_batch;
+    check_grid(blocks);
+    const size_t smem = (size_t)2 * p->C * p->npad * sizeof(cplx);
+    static bool attr_done = false;
+    if (!attr_done) {
+        HS_CUDA_CHECK(cudaFuncSetAttribute(hs_generic_pass_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        HS_CUDA_CHECK(cudaFuncSetAttribute(hs_generic_pass_kernel<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_done = true;
+    }
+    if (smem > 227 * 1024) { fprintf(stderr, "Error: pass needs %zu bytes of shared memory\n", smem); exit(EXIT_FAILURE); }
+    if (sgn == 1) hs_generic_pass_kernel<1><<<(unsigned)blocks, 256, smem, st>>>((const cplx *)d_in, (cplx *)d_out, *p);
+    else hs_generic_pass_kernel<-1><<<(unsigned)blocks, 256, smem, st>>>((const cplx *)d_in, (cplx *)d_out, *p);
+    HS_CUDA_CHECK(cudaGetLastError());
+    ++g_launches;
+}
+
+static unsigned ew_grid(long long total)
+{
+    long long b = (total + 255) / 256;
+    const long long cap = 148LL * 32;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (unsigned)b;
+}
+
+extern "C" void hs_cu_launch_chirp_pad(int sgn, const void *x, void *a, const void *h, int N, int M, long long howmany, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned g = ew_grid(howmany * M);
+    if (sgn == 1) hs_chirp_pad_kernel<1><<<g, 256, 0, st>>>((const cplx *)x, (cplx *)a, (const cplx *)h, N, M, howmany);
+    else hs_chirp_pad_kernel<-1><<<g, 256, 0, st>>>((const cplx *)x, (cplx *)a, (const cplx *)h, N, M, howmany);
+    HS_CUDA_CHECK(cudaGetLastError());
+    ++g_launches;
+}
+extern "C" void hs_cu_launch_spectrum_mul(int sgn, void *A, const void *Hk, int M, long long howmany, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned g = ew_grid(howmany * M);
+    if (sgn == 1) hs_spectrum_mul_kernel<1><<<g, 256, 0, st>>>((cplx *)A, (const cplx *)Hk, M, howmany);
+    else hs_spectrum_mul_kernel<-1><<<g, 256, 0, st>>>((cplx *)A, (const cplx *)Hk, M, howmany);
+    HS_CUDA_CHECK(cudaGetLastError());
+    ++g_launches;
+}
+extern "C" void hs_cu_launch_chirp_crop(int sgn, const void *y, void *out, const void *h, int N, int M, long long howmany, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned g = ew_grid(howmany * N);
+    if (sgn == 1) hs_chirp_crop_kernel<1><<<g, 256, 0, st>>>((const cplx *)y, (cplx *)out, (const cplx *)h, N, M, howmany);
+    else hs_chirp_crop_kernel<-1><<<g, 256, 0, st>>>((const cplx *)y, (cplx *)out, (const cplx *)h, N, M, howmany);
+    HS_CUDA_CHECK(cudaGetLastError());
+    ++g_launches;
+}
+extern "C" void hs_cu_launch_r2c_post(const void *Z, void *out, const void *tw2, int H, long long out_stride, int full, long long howmany,
+                                      void *stream)
+{
+    hs_r2c_post_kernel<<<ew_grid(howmany * (H + 1)), 256, 0, (cudaStream_t)stream>>>((const cplx *)Z, (cplx *)out, (const cplx *)tw2, H,
+                                                                                      out_stride, full, howmany);
+    HS_CUDA_CHECK(cudaGetLastError());
+    ++g_launches;
+}
+extern "C" void hs_cu_launch_c2r_pre(const void *in, void *z, const void *tw2, int H, long long in_stride, long long howmany, void *stream)
+{
+    hs_c2r_pre_kernel<<<ew_grid(howmany * H), 256, 0, (cudaStream_t)stream>>>((const cplx *)in, (cplx *)z, (const cplx *)tw2, H, in_stride,
+                                                                               howmany);
+    HS_CUDA_CHECK(cudaGetLastError());
+    ++g_launches;
+}
+extern "C" void hs_cu_launch_conv_mul(const void *A, const void *B, void *C, long long total, double scale, void *stream)
+{
+    hs_conv_mul_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>((const cplx *)A, (const cplx *)B, (cplx *)C, total, scale);
+    HS_CUDA_CHECK(cudaGetLastError());
+    ++g_launches;
+}
+extern "C" void hs_cu_launch_pad_rows(const void *src, int len, void *dst, int P, long long howmany, void *stream)
+{
+    hs_pad_rows_kernel<<<ew_grid(howmany * P), 256, 0, (cudaStream_t)stream>>>((const double *)src, len, (double *)dst, P, howmany);
+    HS_CUDA_CHECK(cudaGetLastError());
+    ++g_launches;
+}
+extern "C" void hs_cu_launch_slice_rows(const void *src, int P, int start, int len, void *dst, long long dst_stride, long long howmany,
+                                        void *stream)
+{
+    hs_slice_rows_kernel<<<ew_grid(howmany * len), 256, 0, (cudaStream_t)stream>>>((const double *)src, P, start, len, (double *)dst,
+                                                                                    dst_stride, howmany);
+    HS_CUDA_CHECK(cudaGetLastError());
+    ++g_launches;
+}

@@ -1,0 +1,76 @@
+/*
+ * hs_engine.h -- host-side (plain C) execution planner shared by hsfft_plan.c, hsfft_real.c and
+ * hsfft_convolve.c.  Internal; the public surface is the three headers under include.
+ *
+ * A public plan (struct fft_set, a bare malloc block the caller may even free() directly --
+ * reference src/real.c:264, test/test_mixedRadixFFT.cpp:126,305) carries no GPU state.  The GPU
+ * state (HBM-resident stage twiddles, chirp tables, pass list, staging buffers, streams) lives in
+ * an hs_dev_obj kept in a registry keyed by the plan's address and validated against the plan's
+ * (N, sgn, lt) on every call; it is created on the first execute and released by free_fft.
+ */
+#ifndef HS_ENGINE_H_
+#define HS_ENGINE_H_
+
+#include "../../include/real.h"
+#include "hs_abi.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HS_MAX_PASS 6
+#define HS_NSLOT 3 /* pipeline depth of the host-pointer batch path */
+
+/* batched, contiguous, out-of-place c2c of one length and direction */
+typedef struct hs_c2c {
+    int n, sgn;
+    int ct_id;          /* >= 0: one compile-time kernel does the whole transform */
+    void *d_tw;         /* its stage twiddles in HBM */
+    int npass;          /* otherwise: run-time planned passes */
+    hs_gen_params pass[HS_MAX_PASS];
+    void *d_pass_tw[HS_MAX_PASS], *d_pass_lo[HS_MAX_PASS], *d_pass_hi[HS_MAX_PASS];
+    void *d_gen_cs, *d_gen_sn;
+} hs_c2c;
+
+typedef struct hs_dev_obj {
+    const void *key;    /* plan address */
+    int N, sgn, lt;
+    hs_c2c *direct;     /* lt == 0 */
+    /* Bluestein (lt == 1) */
+    int M;
+    hs_c2c *fwdM, *invM;
+    void *d_chirp, *d_hk;
+    int blu_ct_id;
+    void *d_blu_twf, *d_blu_twi;
+    /* pipeline slots for host-pointer calls */
+    void *stream[HS_NSLOT];
+    void *d_in[HS_NSLOT], *d_out[HS_NSLOT], *d_ws[HS_NSLOT], *d_ws2[HS_NSLOT];
+    size_t cap_in[HS_NSLOT], cap_out[HS_NSLOT], cap_ws[HS_NSLOT], cap_ws2[HS_NSLOT];
+    struct hs_dev_obj *next;
+} hs_dev_obj;
+
+/* plan tables built on the host with the reference's own expressions */
+void hs_build_stage_twiddles(fft_data *out, const int *radix_exec, int nst, int sgn); /* [i-1][k] per stage */
+int  hs_stage_twiddle_count(const int *radix_exec, int nst);
+void hs_build_chirp(fft_data *h, int N);                                              /* exp(+i pi n^2/N) */
+int  hs_bluestein_exec_pad(int N);                                                    /* 2^ceil(log2(2N-1)) */
+
+/* c2c sub-plans */
+hs_c2c *hs_c2c_create(int n, int sgn);
+void    hs_c2c_destroy(hs_c2c *p);
+size_t  hs_c2c_ws_elems(const hs_c2c *p, long long howmany); /* workspace (complex elements) exec needs */
+void    hs_c2c_exec(const hs_c2c *p, const void *d_in, void *d_out, void *d_ws, long long howmany, void *stream);
+
+/* registry */
+hs_dev_obj *hs_dev_get(fft_object plan);      /* find or build; exits when no CUDA device */
+void        hs_dev_release(const void *key);  /* no-op when absent */
+void        hs_dev_reserve(hs_dev_obj *d, int slot, size_t in_bytes, size_t out_bytes, size_t ws_bytes, size_t ws2_bytes);
+
+/* device-pointer execution of a full plan (mixed radix or Bluestein) */
+size_t hs_dev_ws_bytes(const hs_dev_obj *d, long long howmany);
+void   hs_dev_exec(hs_dev_obj *d, const void *d_in, void *d_out, void *d_ws, long long howmany, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,190 @@
+/*
+ * hsfft_convolve.c -- FFT convolution of real signals (host side, plain C).
+ *
+ * Replaces reference src/convolve.c: next_power_of_two :20-25, find_optimal_fft_length :39-55,
+ * fft_convolve :74-214.  Same argument meaning, same return values (-1 on bad arguments, exit on
+ * an unknown conv_type inside find_optimal_fft_length), same "full" / "same" / "valid" slicing.
+ *
+ * The reference builds and destroys two real plans and six P-sized buffers on every call
+ * (:104-122, :204-211) and multiplies all P mirrored bins (:147-151).  Here the pair of plans for a
+ * given P is cached, the spectra are produced half-length only (bins 0..P/2 -- all c2r reads),
+ * the product carries the 1/P scale (exact: P is a power of two), and a batch entry point runs
+ * many independent convolutions per launch.
+ */
+#include "hs_engine.h"
+#include "../../include/hsfft_b200.h"
+
+#include <pthread.h>
+
+#ifndef MIN
+#define MIN(a, b) ((a) < (b) ? (a) : (b))
+#endif
+#ifndef MAX
+#define MAX(a, b) ((a) > (b) ? (a) : (b))
+#endif
+
+int next_power_of_two(int n)
+{
+    if (n <= 0) return 1;
+    return (int)pow(2, ceil(log2(n)));
+}
+
+int find_optimal_fft_length(int min_length, const char *conv_type, int length1, int length2)
+{
+    if (strcmp(conv_type, "linear") == 0) return next_power_of_two(min_length);
+    if (strcmp(conv_type, "circular") == 0) return next_power_of_two(MAX(length1, length2));
+    fprintf(stderr, "Error: Invalid convolution type\n");
+    exit(EXIT_FAILURE);
+}
+
+/* plan cache: one forward and one inverse real plan per padded length */
+typedef struct conv_plans {
+    int P;
+    fft_real_object fwd, inv;
+    void *d_a, *d_b, *d_A, *d_B, *d_res; /* device scratch, grown on demand */
+    size_t cap_ab, cap_AB, cap_res;
+    struct conv_plans *next;
+} conv_plans;
+
+static pthread_mutex_t c_lock = PTHREAD_MUTEX_INITIALIZER;
+static conv_plans *c_head = NULL;
+
+static conv_plans *plans_for(int P)
+{
+    pthread_mutex_lock(&c_lock);
+    conv_plans *c = c_head;
+    while (c && c->P != P) c = c->next;
+    if (!c) {
+        c = (conv_plans *)calloc(1, sizeof(*c));
+        if (!c) { fprintf(stderr, "Error: Memory allocation failed\n"); exit(EXIT_FAILURE); }
+        c->P = P;
+        c->fwd = fft_real_init(P, 1);
+        c->inv = fft_real_init(P, -1);
+        c->next = c_head;
+        c_head = c;
+    }
+    pthread_mutex_unlock(&c_lock);
+    return c;
+}
+
+static void grow(void **buf, size_t *cap, size_t need)
+{
+    if (need <= *cap) return;
+    hs_cu_free(*buf);
+    *buf = hs_cu_malloc(need);
+    *cap = need;
+}
+
+/* slicing rules of reference :163-195; returns the output length (or -1), sets *start */
+static int conv_slice(const char *type, int linear, int length1, int length2, int conv_length, int P, int *start)
+{
+    *start = 0;
+    if (!linear) return P;
+    if (type == NULL || strcmp(type, "full") == 0) return conv_length;
+    if (strcmp(type, "same") == 0) {
+        const int larger = MAX(length1, length2);
+        *start = (conv_length - larger) / 2;
+        return larger;
+    }
+    if (strcmp(type, "valid") == 0) {
+        const int smaller = MIN(length1, length2);
+        *start = smaller - 1;
+        return MAX(length1, length2) - smaller + 1;
+    }
+    fprintf(stderr, "Error: Invalid output type. Use 'full', 'same', or 'valid'.\n");
+    return -1;
+}
+
+static int conv_setup(const char *type, const char *conv_type, const void *in1, int length1, const void *in2, int length2, const void *out,
+                      int *P, int *start, int *linear)
+{
+    if (type == NULL) type = "full"; /* the reference's `|| type == NULL` intent (:165) */
+    if (in1 == NULL || in2 == NULL || out == NULL || length1 <= 0 || length2 <= 0 || conv_type == NULL) {
+        fprintf(stderr, "Error: Invalid inputs for fft_convolve\n");
+        return -1;
+    }
+    int conv_length;
+    if (strcmp(conv_type, "linear") == 0) { conv_length = length1 + length2 - 1; *linear = 1; }
+    else if (strcmp(conv_type, "circular") == 0) { conv_length = MAX(length1, length2); *linear = 0; }
+    else {
+        fprintf(stderr, "Error: Invalid convolution type. Use 'linear' or 'circular'.\n");
+        return -1;
+    }
+    *P = find_optimal_fft_length(conv_length, conv_type, length1, length2);
+    if (*P < 2) { /* P == 1 is odd: the reference exits inside fft_real_init (src/real.c:28-32) */
+        fprintf(stderr, "Error: Signal length (%d) must be positive and even\n", *P);
+        exit(EXIT_FAILURE);
+    }
+    return conv_slice(type, *linear, length1, length2, conv_length, *P, start);
+}
+
+int fft_convolve_batch_dev(const char *type, const char *conv_type, const fft_type *d_in1, int length1, const fft_type *d_in2, int length2,
+                           fft_type *d_out, long out_stride, long howmany, void *stream)
+{
+    int P, start, linear;
+    const int n = conv_setup(type, conv_type, d_in1, length1, d_in2, length2, d_out, &P, &start, &linear);
+    if (n <= 0 || howmany <= 0) return n;
+    conv_plans *c = plans_for(P);
+    const size_t H1 = (size_t)P / 2 + 1;
+    if (c->cap_ab < sizeof(fft_type) * (size_t)P * howmany) {
+        hs_cu_free(c->d_a); hs_cu_free(c->d_b);
+        c->cap_ab = sizeof(fft_type) * (size_t)P * howmany;
+        c->d_a = hs_cu_malloc(c->cap_ab);
+        c->d_b = hs_cu_malloc(c->cap_ab);
+    }
+    if (c->cap_AB < sizeof(fft_data) * H1 * howmany) {
+        hs_cu_free(c->d_A); hs_cu_free(c->d_B);
+        c->cap_AB = sizeof(fft_data) * H1 * howmany;
+        c->d_A = hs_cu_malloc(c->cap_AB);
+        c->d_B = hs_cu_malloc(c->cap_AB);
+    }
+    grow(&c->d_res, &c->cap_res, sizeof(fft_type) * (size_t)P * howmany);
+    /* zero-pad -> r2c x2 (half spectra) -> product * 1/P -> c2r -> slice */
+    hs_cu_launch_pad_rows(d_in1, length1, c->d_a, P, howmany, stream);
+    hs_cu_launch_pad_rows(d_in2, length2, c->d_b, P, howmany, stream);
+    fft_r2c_exec_batch_dev(c->fwd, (const fft_type *)c->d_a, (fft_data *)c->d_A, (long)H1, 0, howmany, stream);
+    /* the real plan keeps one scratch set per stream slot; the two transforms share it in order */
+    fft_r2c_exec_batch_dev(c->fwd, (const fft_type *)c->d_b, (fft_data *)c->d_B, (long)H1, 0, howmany, stream);
+    hs_cu_launch_conv_mul(c->d_A, c->d_B, c->d_A, (long long)(H1 * howmany), 1.0 / P, stream);
+    fft_c2r_exec_batch_dev(c->inv, (const fft_data *)c->d_A, (long)H1, (fft_type *)c->d_res, howmany, stream);
+    hs_cu_launch_slice_rows(c->d_res, P, start, n, d_out, out_stride, howmany, stream);
+    return n;
+}
+
+int fft_convolve_batch(const char *type, const char *conv_type, fft_type *input1, int length1, fft_type *input2, int length2,
+                       fft_type *output, long out_stride, long howmany)
+{
+    int P, start, linear;
+    const int n = conv_setup(type, conv_type, input1, length1, input2, length2, output, &P, &start, &linear);
+    if (n <= 0 || howmany <= 0) return n;
+    hs_cu_require_device();
+    /* chunk so that the device scratch (about 5 P-sized rows per convolution) stays bounded */
+    long chunk = (long)(((size_t)256 << 20) / (sizeof(fft_type) * (size_t)P * 5));
+    if (chunk < 1) chunk = 1;
+    if (chunk > howmany) chunk = howmany;
+    void *d1 = hs_cu_malloc(sizeof(fft_type) * (size_t)length1 * chunk);
+    void *d2 = hs_cu_malloc(sizeof(fft_type) * (size_t)length2 * chunk);
+    void *dout = hs_cu_malloc(sizeof(fft_type) * (size_t)n * chunk);
+    for (long first = 0; first < howmany; first += chunk) {
+        const long cnt = (first + chunk <= howmany) ? chunk : howmany - first;
+        hs_cu_h2d(d1, input1 + first * length1, sizeof(fft_type) * (size_t)length1 * cnt, NULL);
+        hs_cu_h2d(d2, input2 + first * length2, sizeof(fft_type) * (size_t)length2 * cnt, NULL);
+        fft_convolve_batch_dev(type, conv_type, (const fft_type *)d1, length1, (const fft_type *)d2, length2, (fft_type *)dout, n, cnt,
+                               NULL);
+        if (out_stride == n) hs_cu_d2h(output + first * out_stride, dout, sizeof(fft_type) * (size_t)n * cnt, NULL);
+        else
+            for (long i = 0; i < cnt; ++i)
+                hs_cu_d2h(output + (first + i) * out_stride, (fft_type *)dout + i * n, sizeof(fft_type) * (size_t)n, NULL);
+    }
+    hs_cu_stream_sync(NULL);
+    hs_cu_free(d1); hs_cu_free(d2); hs_cu_free(dout);
+    return n;
+}
+
+int fft_convolve(const char *type, const char *conv_type, fft_type *input1, int length1, fft_type *input2, int length2, fft_type *output)
+{
+    int P, start, linear;
+    const int n = conv_setup(type, conv_type, input1, length1, input2, length2, output, &P, &start, &linear);
+    if (n <= 0) return n;
+    return fft_convolve_batch(type, conv_type, input1, length1, input2, length2, output, n, 1);
+}

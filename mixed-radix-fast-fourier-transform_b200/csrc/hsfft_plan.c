@@ -1,0 +1,668 @@
+/*
+ * hsfft_plan.c -- complex plan builder and execute/destroy entry points (host side, plain C).
+ *
+ * Public symbols and the reference interface each replaces (paths under /root/reference):
+ *   fft_init     src/highSpeedFFT.c:206-286     fft_exec   src/highSpeedFFT.c:1920-1942
+ *   free_fft     src/highSpeedFFT.c:2315-2318   divideby   src/highSpeedFFT.c:1954-1968
+ *   dividebyN    src/highSpeedFFT.c:1979-2025   factors    src/highSpeedFFT.c:2038-2163
+ *   twiddle      src/highSpeedFFT.c:2186-2224   longvectorN src/highSpeedFFT.c:2238-2313
+ *
+ * The plan builder keeps the reference's routing (mixed radix vs Bluestein), its factor order and
+ * its twiddle expression, so the public struct is field-for-field what the reference returns; the
+ * execution plan (which sm_100a kernels run, in how many passes) is derived from those fields on
+ * the first execute and cached in the registry (hs_engine.h).  No CPU fallback exists: execute
+ * calls need a CUDA device and exit otherwise.
+ */
+#include "hs_engine.h"
+#include "../../include/hsfft_b200.h"
+
+#include <pthread.h>
+
+/* ----------------------------------------------------------------- plan helpers (reference API) */
+
+int divideby(int number, int divisor)
+{
+    if (number <= 0 || divisor <= 0) {
+        fprintf(stderr, "Error: Invalid inputs for divideby - number: %d, divisor: %d\n", number, divisor);
+        exit(EXIT_FAILURE);
+    }
+    while (number % divisor == 0) number /= divisor;
+    return number == 1;
+}
+
+int dividebyN(int number)
+{
+    /* "is N a product of {2,3,4,5,7,8,11,13,17,23,29,31,37,41,43,47,53}?" -- 19 is not in the
+     * router's list (reference :13), so multiples of 19 go to Bluestein.  The reference answers
+     * from a constructor-filled table below 1024 and by trial division above; both compute this. */
+    static const int radices[13] = {53, 47, 43, 41, 37, 31, 29, 23, 17, 13, 11, 7, 5};
+    if (number < 1) return 0; /* the reference indexes its table out of bounds here */
+    for (int i = 0; i < 13; ++i)
+        while (number % radices[i] == 0) number /= radices[i];
+    while (number % 3 == 0) number /= 3;
+    while (number % 2 == 0) number /= 2;
+    return number == 1;
+}
+
+int factors(int number, int *out)
+{
+    static const int order[18] = {53, 47, 43, 41, 37, 31, 29, 23, 19, 17, 13, 11, 8, 7, 5, 4, 3, 2};
+    if (out == NULL) {
+        fprintf(stderr, "Error: Invalid inputs for factors - number: %d, factors_array: %p\n", number, (void *)out);
+        exit(EXIT_FAILURE);
+    }
+    if (number <= 0) { /* the reference never terminates on 0 (0 % 53 == 0); refuse cleanly */
+        fprintf(stderr, "Error: Invalid inputs for factors - number: %d\n", number);
+        exit(EXIT_FAILURE);
+    }
+    int cnt = 0, rest = number;
+    for (int i = 0; i < 18; ++i)
+        while (rest % order[i] == 0) { out[cnt++] = order[i]; rest /= order[i]; }
+    if (rest > 31) { /* 6k+-1 sweep for what is left (reference :2140-2160) */
+        for (int k = 2; rest > 1; ++k) {
+            const int lo = 6 * k - 1, hi = 6 * k + 1;
+            while (rest % lo == 0) { out[cnt++] = lo; rest /= lo; }
+            while (rest % hi == 0) { out[cnt++] = hi; rest /= hi; }
+        }
+    }
+    return cnt;
+}
+
+void twiddle(fft_data *sig, int N, int radix)
+{
+    /* Never called by the reference itself.  Its table branch reads the mis-indexed
+     * twiddle_tables[]; this keeps the documented meaning:
+     * sig[i] = exp(-2 pi i * i / N), i < N / radix. */
+    if (N <= 0 || radix <= 0) {
+        fprintf(stderr, "Error: Invalid inputs for twiddle - signal_length: %d, radix: %d\n", N, radix);
+        exit(EXIT_FAILURE);
+    }
+    const int cnt = N / radix;
+    for (int i = 0; i < cnt; ++i) {
+        const fft_type angle = PI2 * i / N;
+        sig[i].re = cos(angle);
+        sig[i].im = -sin(angle);
+    }
+}
+
+void longvectorN(fft_data *sig, int N, int *array, int M)
+{
+    /* Stage twiddles in the reference's layout: factors walked last to first, stage of combine
+     * length L = r*Ls writes (r-1)*Ls entries cos/sin((k+1)*j*theta), theta = -PI2/L, j-major
+     * (reference :2273-2289, the branch that is correct for every radix). */
+    if (N <= 0 || array == NULL || M <= 0) {
+        fprintf(stderr, "Error: Invalid inputs for longvectorN - signal_length: %d, prime_factors: %p, num_factors: %d\n", N,
+                (void *)array, M);
+        exit(EXIT_FAILURE);
+    }
+    int L = 1, written = 0;
+    for (int s = M - 1; s >= 0; --s) {
+        const int r = array[s], Ls = L;
+        L *= r;
+        const fft_type theta = -PI2 / L;
+        for (int j = 0; j < Ls; ++j)
+            for (int k = 0; k < r - 1; ++k)
+                if (written < N - 1) {
+                    const fft_type angle = (k + 1) * j * theta;
+                    sig[written].re = cos(angle);
+                    sig[written].im = sin(angle);
+                    ++written;
+                }
+    }
+    if (written != N - 1)
+        fprintf(stderr, "Warning: Twiddle factor count (%d) does not match expected (%d) for N=%d\n", written, N - 1, N);
+}
+
+/* -------------------------------------------------------------------- device-side table builders */
+
+int hs_stage_twiddle_count(const int *rx, int nst)
+{
+    int m = 1, cnt = 0;
+    for (int s = 0; s < nst; ++s) {
+        if (s > 0) cnt += (rx[s] - 1) * m;
+        m *= rx[s];
+    }
+    return cnt;
+}
+
+void hs_build_stage_twiddles(fft_data *out, const int *rx, int nst, int sgn)
+{
+    /* Same values as longvectorN (same expression, so bit-identical where the stage lengths
+     * coincide), laid out [i-1][k] per stage so that a warp's loads of one twiddle row coalesce. */
+    int m = 1, off = 0;
+    for (int s = 0; s < nst; ++s) {
+        const int r = rx[s];
+        if (s > 0) {
+            const fft_type theta = -PI2 / ((fft_type)m * r);
+            for (int i = 1; i < r; ++i)
+                for (int k = 0; k < m; ++k) {
+                    const fft_type angle = i * k * theta;
+                    out[off + (i - 1) * m + k].re = cos(angle);
+                    out[off + (i - 1) * m + k].im = (sgn == -1) ? -sin(angle) : sin(angle);
+                }
+            off += (r - 1) * m;
+        }
+        m *= r;
+    }
+}
+
+void hs_build_chirp(fft_data *h, int N)
+{
+    /* h[n] = exp(+i pi n^2 / N), n^2 reduced mod 2N by the running sum of reference :1676-1689 */
+    const fft_type PI = 3.1415926535897932384626433832795;
+    const fft_type theta = PI / N;
+    int l2 = 0;
+    const int len2 = 2 * N;
+    for (int n = 0; n < N; ++n) {
+        const fft_type angle = theta * l2;
+        h[n].re = cos(angle);
+        h[n].im = sin(angle);
+        l2 += 2 * n + 1;
+        while (l2 > len2) l2 -= len2;
+    }
+}
+
+int hs_bluestein_exec_pad(int N)
+{
+    int m = 1;
+    while (m < 2 * N - 1) m *= 2; /* = 2^ceil(log2(2N-1)), reference :1750-1751 */
+    return m;
+}
+
+/* ------------------------------------------------------------------------------- c2c sub-plans */
+
+#define HS_SMEM_POINTS 6400 /* complex points of one ping-pong buffer pair's half (2*6400*16 B = 200 KiB) */
+#define HS_GROUP_MAX 512
+
+static const hs_ct_desc *find_ct(int family, int n)
+{
+    const int cnt = hs_cu_ct_count();
+    for (int i = 0; i < cnt; ++i) {
+        const hs_ct_desc *d = hs_cu_ct_get(i);
+        if (d->family == family && d->n == n) return d;
+    }
+    return NULL;
+}
+
+static void *upload(const void *h, size_t bytes)
+{
+    void *d = hs_cu_malloc(bytes ? bytes : 16);
+    if (bytes) hs_cu_h2d(d, h, bytes, NULL);
+    return d;
+}
+
+static void *upload_stage_twiddles(const int *rx, int nst, int sgn)
+{
+    const int cnt = hs_stage_twiddle_count(rx, nst);
+    fft_data *t = (fft_data *)malloc(sizeof(fft_data) * (cnt > 0 ? cnt : 1));
+    if (!t) { fprintf(stderr, "Error: Memory allocation failed for twiddle table\n"); exit(EXIT_FAILURE); }
+    hs_build_stage_twiddles(t, rx, nst, sgn);
+    void *d = upload(t, sizeof(fft_data) * cnt);
+    hs_cu_stream_sync(NULL);
+    free(t);
+    return d;
+}
+
+hs_c2c *hs_c2c_create(int n, int sgn)
+{
+    hs_c2c *p = (hs_c2c *)calloc(1, sizeof(hs_c2c));
+    if (!p) { fprintf(stderr, "Error: Memory allocation failed for execution plan\n"); exit(EXIT_FAILURE); }
+    p->n = n;
+    p->sgn = sgn;
+    p->ct_id = -1;
+    const hs_ct_desc *ct = find_ct(HS_CT_C2C, n);
+    if (ct) {
+        p->ct_id = ct->id;
+        p->d_tw = upload_stage_twiddles(ct->radix, ct->nst, sgn);
+        return p;
+    }
+    /* run-time plan: the reference's factor list reversed = execution order */
+    int fac[64], rx[64];
+    const int lf = factors(n, fac);
+    if (lf <= 0 || lf > HS_MAX_STAGES) { fprintf(stderr, "Error: cannot plan N=%d\n", n); exit(EXIT_FAILURE); }
+    for (int s = 0; s < lf; ++s) {
+        rx[s] = fac[lf - 1 - s];
+        if (rx[s] > 8 && (rx[s] % 2 == 0 || rx[s] >= HS_MAX_GENERIC_RADIX)) {
+            fprintf(stderr, "Error: unsupported radix %d in the factor list of N=%d\n", rx[s], n);
+            exit(EXIT_FAILURE);
+        }
+    }
+    /* cos/sin half tables of the generic odd radices (reference :1533-1543) */
+    double *cs = (double *)calloc((size_t)lf * HS_MAX_GENERIC_RADIX, sizeof(double));
+    double *sn = (double *)calloc((size_t)lf * HS_MAX_GENERIC_RADIX, sizeof(double));
+    int gen_off[64], gen_total = 0;
+    for (int s = 0; s < lf; ++s) {
+        gen_off[s] = 0;
+        const int r = rx[s];
+        if (r > 8) {
+            const int h = (r - 1) / 2;
+            gen_off[s] = gen_total;
+            double *c = cs + gen_total, *sv = sn + gen_total;
+            for (int i = 1; i <= h; ++i) { c[i - 1] = cos(i * PI2 / r); sv[i - 1] = sin(i * PI2 / r); }
+            for (int i = 0; i < h; ++i) { sv[i + h] = -sv[h - 1 - i]; c[i + h] = c[h - 1 - i]; }
+            gen_total += r - 1;
+        }
+    }
+    if (gen_total) {
+        p->d_gen_cs = upload(cs, sizeof(double) * gen_total);
+        p->d_gen_sn = upload(sn, sizeof(double) * gen_total);
+        hs_cu_stream_sync(NULL);
+    }
+    free(cs);
+    free(sn);
+
+    /* group consecutive stages into passes whose composite radix fits shared memory */
+    int gstart[HS_MAX_PASS + 1], ng = 0;
+    if (n <= HS_SMEM_POINTS) { gstart[0] = 0; gstart[1] = lf; ng = 1; }
+    else {
+        int s = 0;
+        while (s < lf) {
+            if (ng >= HS_MAX_PASS) { fprintf(stderr, "Error: N=%d needs too many passes\n", n); exit(EXIT_FAILURE); }
+            gstart[ng] = s;
+            long prod = rx[s++];
+            if (prod > HS_SMEM_POINTS) { fprintf(stderr, "Error: radix %ld too large\n", prod); exit(EXIT_FAILURE); }
+            while (s < lf && prod * rx[s] <= HS_GROUP_MAX) prod *= rx[s++];
+            ++ng;
+        }
+        gstart[ng] = lf;
+    }
+    p->npass = ng;
+    long long m = 1;
+    for (int g = 0; g < ng; ++g) {
+        hs_gen_params *q = &p->pass[g];
+        const int *grx = rx + gstart[g];
+        const int gst = gstart[g + 1] - gstart[g];
+        long long Rg = 1;
+        for (int s = 0; s < gst; ++s) Rg *= grx[s];
+        memset(q, 0, sizeof(*q));
+        q->n = (int)Rg;
+        q->nst = gst;
+        q->npad = (int)(Rg | 1);
+        int mm = 1;
+        int off = 0;
+        for (int s = 0; s < gst; ++s) {
+            q->radix[s] = grx[s];
+            q->gen_off[s] = gen_off[gstart[g] + s];
+            q->tw_off[s] = (s > 0) ? off : 0;
+            if (s > 0) off += (grx[s] - 1) * mm;
+            mm *= grx[s];
+        }
+        p->d_pass_tw[g] = upload_stage_twiddles(grx, gst, sgn);
+        q->tw = p->d_pass_tw[g];
+        q->gen_cs = (const double *)p->d_gen_cs;
+        q->gen_sn = (const double *)p->d_gen_sn;
+        int C = HS_SMEM_POINTS / q->npad;
+        if (ng == 1) { int want = 2048 / q->n; if (want < 1) want = 1; if (C > want) C = want; }
+        else if (C > 16) C = 16;
+        if (C < 1) C = 1;
+        q->C = C;
+        if (ng == 1) {
+            /* whole transform in one pass: the batch is the tile dimension (set per launch) */
+            q->n_o = 1; q->n_batch = 1;
+            q->in_c = n; q->in_e = 1; q->out_c = n; q->out_e = 1;
+            q->load_c_fast = 0; q->store_c_fast = 0;
+        } else if (g == 0) {
+            const long long Qp = n / Rg;
+            q->n_o = 1; q->n_c = Qp;
+            q->in_b = n; q->out_b = n;
+            q->in_c = 1; q->in_e = Qp; q->out_c = Rg; q->out_e = 1;
+            q->load_c_fast = 1; q->store_c_fast = 0;
+        } else {
+            const long long Qp = n / (m * Rg);
+            q->n_o = Qp; q->n_c = m;
+            q->in_b = n; q->out_b = n;
+            q->in_o = m; q->in_c = 1; q->in_e = Qp * m;
+            q->out_o = m * Rg; q->out_c = 1; q->out_e = m;
+            q->load_c_fast = 1; q->store_c_fast = 1;
+            /* inter-pass twiddle W_L^(e*c), L = m*Rg, split in two short tables */
+            const long long L = m * Rg;
+            int S = (int)ceil(sqrt((double)L));
+            if (S < 1) S = 1;
+            const long long nhi = (L + S - 1) / S;
+            fft_data *lo = (fft_data *)malloc(sizeof(fft_data) * S), *hi = (fft_data *)malloc(sizeof(fft_data) * nhi);
+            if (!lo || !hi) { fprintf(stderr, "Error: Memory allocation failed for twiddle table\n"); exit(EXIT_FAILURE); }
+            const fft_type theta = -PI2 / (fft_type)L;
+            for (int x = 0; x < S; ++x) {
+                const fft_type a = x * theta;
+                lo[x].re = cos(a); lo[x].im = (sgn == -1) ? -sin(a) : sin(a);
+            }
+            for (long long x = 0; x < nhi; ++x) {
+                const fft_type a = (fft_type)(x * S) * theta;
+                hi[x].re = cos(a); hi[x].im = (sgn == -1) ? -sin(a) : sin(a);
+            }
+            p->d_pass_lo[g] = upload(lo, sizeof(fft_data) * S);
+            p->d_pass_hi[g] = upload(hi, sizeof(fft_data) * nhi);
+            hs_cu_stream_sync(NULL);
+            free(lo); free(hi);
+            q->tw_L = L; q->tw_S = S; q->tw_lo = p->d_pass_lo[g]; q->tw_hi = p->d_pass_hi[g];
+        }
+        m *= Rg;
+    }
+    return p;
+}
+
+void hs_c2c_destroy(hs_c2c *p)
+{
+    if (!p) return;
+    hs_cu_free(p->d_tw);
+    for (int g = 0; g < HS_MAX_PASS; ++g) { hs_cu_free(p->d_pass_tw[g]); hs_cu_free(p->d_pass_lo[g]); hs_cu_free(p->d_pass_hi[g]); }
+    hs_cu_free(p->d_gen_cs);
+    hs_cu_free(p->d_gen_sn);
+    free(p);
+}
+
+size_t hs_c2c_ws_elems(const hs_c2c *p, long long howmany)
+{
+    return (p->ct_id < 0 && p->npass > 1) ? (size_t)howmany * p->n : 0;
+}
+
+void hs_c2c_exec(const hs_c2c *p, const void *d_in, void *d_out, void *d_ws, long long howmany, void *stream)
+{
+    if (howmany <= 0) return;
+    if (p->ct_id >= 0) { hs_cu_launch_ct_c2c(p->ct_id, p->sgn, d_in, d_out, p->d_tw, howmany, stream); return; }
+    if (p->npass == 1) {
+        hs_gen_params q = p->pass[0];
+        q.n_c = howmany;
+        if (q.C > howmany) q.C = (int)howmany;
+        hs_cu_launch_generic(p->sgn, d_in, d_out, &q, stream);
+        return;
+    }
+    const void *src = d_in;
+    for (int g = 0; g < p->npass; ++g) {
+        hs_gen_params q = p->pass[g];
+        q.n_batch = howmany;
+        if (q.C > q.n_c) q.C = (int)q.n_c;
+        void *dst = ((p->npass - 1 - g) % 2 == 0) ? d_out : d_ws;
+        hs_cu_launch_generic(p->sgn, src, dst, &q, stream);
+        src = dst;
+    }
+}
+
+/* ------------------------------------------------------------------------------------ registry */
+
+static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
+static hs_dev_obj *g_head = NULL;
+
+static void dev_free_contents(hs_dev_obj *d)
+{
+    hs_c2c_destroy(d->direct);
+    hs_c2c_destroy(d->fwdM);
+    hs_c2c_destroy(d->invM);
+    hs_cu_free(d->d_chirp);
+    hs_cu_free(d->d_hk);
+    hs_cu_free(d->d_blu_twf);
+    hs_cu_free(d->d_blu_twi);
+    for (int s = 0; s < HS_NSLOT; ++s) {
+        hs_cu_free(d->d_in[s]); hs_cu_free(d->d_out[s]); hs_cu_free(d->d_ws[s]); hs_cu_free(d->d_ws2[s]);
+        if (d->stream[s]) hs_cu_stream_destroy(d->stream[s]);
+    }
+}
+
+static void dev_build(hs_dev_obj *d, fft_object plan)
+{
+    d->key = plan;
+    d->N = plan->N;
+    d->sgn = plan->sgn;
+    d->lt = plan->lt;
+    d->blu_ct_id = -1;
+    if (d->N < 2 || (d->sgn != 1 && d->sgn != -1)) {
+        fprintf(stderr, "Error: Invalid FFT object (N = %d, sgn = %d)\n", d->N, d->sgn);
+        exit(EXIT_FAILURE);
+    }
+    for (int s = 0; s < HS_NSLOT; ++s) d->stream[s] = hs_cu_stream_create();
+    if (d->lt == 0) { d->direct = hs_c2c_create(d->N, d->sgn); return; }
+
+    /* Bluestein: chirp h and Hk = FFT_M(h padded and mirrored, scaled 1/M) live in HBM */
+    const int N = d->N, M = hs_bluestein_exec_pad(N);
+    d->M = M;
+    fft_data *h = (fft_data *)malloc(sizeof(fft_data) * N), *hp = (fft_data *)calloc(M, sizeof(fft_data));
+    if (!h || !hp) { fprintf(stderr, "Error: Memory allocation failed for Bluestein's FFT arrays\n"); exit(EXIT_FAILURE); }
+    hs_build_chirp(h, N);
+    const fft_type scale = 1.0 / M;
+    for (int n = 0; n < N; ++n) { hp[n].re = h[n].re * scale; hp[n].im = h[n].im * scale; }
+    for (int n = M - N + 1; n < M; ++n) hp[n] = hp[M - n]; /* reference :1698-1703 */
+    d->d_chirp = upload(h, sizeof(fft_data) * N);
+    void *d_hp = upload(hp, sizeof(fft_data) * M);
+    d->d_hk = hs_cu_malloc(sizeof(fft_data) * M);
+    hs_c2c *f = hs_c2c_create(M, 1);
+    void *ws = NULL;
+    const size_t wse = hs_c2c_ws_elems(f, 1);
+    if (wse) ws = hs_cu_malloc(wse * sizeof(fft_data));
+    hs_c2c_exec(f, d_hp, d->d_hk, ws, 1, NULL);
+    hs_cu_stream_sync(NULL);
+    hs_cu_free(ws);
+    hs_cu_free(d_hp);
+    free(h);
+    free(hp);
+
+    const hs_ct_desc *ct = find_ct(HS_CT_BLUESTEIN, M);
+    if (ct) {
+        /* fused kernel: forward plan = ct->radix, inverse plan = the same list reversed */
+        int inv[8];
+        for (int s = 0; s < ct->nst; ++s) inv[s] = ct->radix[ct->nst - 1 - s];
+        d->blu_ct_id = ct->id;
+        d->d_blu_twf = upload_stage_twiddles(ct->radix, ct->nst, 1);
+        d->d_blu_twi = upload_stage_twiddles(inv, ct->nst, -1);
+        hs_c2c_destroy(f);
+    } else {
+        d->fwdM = f;
+        d->invM = hs_c2c_create(M, -1);
+    }
+}
+
+hs_dev_obj *hs_dev_get(fft_object plan)
+{
+    if (plan == NULL) { fprintf(stderr, "Error: Invalid FFT object or data pointers\n"); exit(EXIT_FAILURE); }
+    hs_cu_require_device();
+    pthread_mutex_lock(&g_lock);
+    hs_dev_obj *d = g_head;
+    while (d && d->key != plan) d = d->next;
+    if (d && (d->N != plan->N || d->sgn != plan->sgn || d->lt != plan->lt)) {
+        /* the block was free()d and re-used, or the caller edited the public struct: rebuild */
+        hs_dev_obj *nx = d->next;
+        dev_free_contents(d);
+        memset(d, 0, sizeof(*d));
+        d->next = nx;
+        dev_build(d, plan);
+    } else if (!d) {
+        d = (hs_dev_obj *)calloc(1, sizeof(hs_dev_obj));
+        if (!d) { fprintf(stderr, "Error: Memory allocation failed for device plan\n"); exit(EXIT_FAILURE); }
+        dev_build(d, plan);
+        d->next = g_head;
+        g_head = d;
+    }
+    pthread_mutex_unlock(&g_lock);
+    return d;
+}
+
+void hs_dev_release(const void *key)
+{
+    pthread_mutex_lock(&g_lock);
+    hs_dev_obj **pp = &g_head;
+    while (*pp && (*pp)->key != key) pp = &(*pp)->next;
+    if (*pp) {
+        hs_dev_obj *d = *pp;
+        *pp = d->next;
+        dev_free_contents(d);
+        free(d);
+    }
+    pthread_mutex_unlock(&g_lock);
+}
+
+static void grow(void **buf, size_t *cap, size_t need)
+{
+    if (need <= *cap) return;
+    hs_cu_free(*buf);
+    *buf = hs_cu_malloc(need);
+    *cap = need;
+}
+
+void hs_dev_reserve(hs_dev_obj *d, int slot, size_t in_bytes, size_t out_bytes, size_t ws_bytes, size_t ws2_bytes)
+{
+    grow(&d->d_in[slot], &d->cap_in[slot], in_bytes);
+    grow(&d->d_out[slot], &d->cap_out[slot], out_bytes);
+    grow(&d->d_ws[slot], &d->cap_ws[slot], ws_bytes);
+    grow(&d->d_ws2[slot], &d->cap_ws2[slot], ws2_bytes);
+}
+
+size_t hs_dev_ws_bytes(const hs_dev_obj *d, long long howmany)
+{
+    if (d->lt == 0) return hs_c2c_ws_elems(d->direct, howmany) * sizeof(fft_data);
+    if (d->blu_ct_id >= 0) return 0;
+    return ((size_t)2 * howmany * d->M + hs_c2c_ws_elems(d->fwdM, howmany)) * sizeof(fft_data);
+}
+
+void hs_dev_exec(hs_dev_obj *d, const void *d_in, void *d_out, void *d_ws, long long howmany, void *stream)
+{
+    if (howmany <= 0) return;
+    if (d->lt == 0) { hs_c2c_exec(d->direct, d_in, d_out, d_ws, howmany, stream); return; }
+    if (d->blu_ct_id >= 0) {
+        hs_cu_launch_ct_bluestein(d->blu_ct_id, d->sgn, d->N, d_in, d_out, d->d_blu_twf, d->d_blu_twi, d->d_chirp, d->d_hk, howmany,
+                                  stream);
+        return;
+    }
+    /* unfused chirp-z: pad*chirp -> FFT_M -> *Hk -> IFFT_M -> *chirp, crop */
+    fft_data *a = (fft_data *)d_ws, *b = a + (size_t)howmany * d->M, *c = b + (size_t)howmany * d->M;
+    hs_cu_launch_chirp_pad(d->sgn, d_in, a, d->d_chirp, d->N, d->M, howmany, stream);
+    hs_c2c_exec(d->fwdM, a, b, c, howmany, stream);
+    hs_cu_launch_spectrum_mul(d->sgn, b, d->d_hk, d->M, howmany, stream);
+    hs_c2c_exec(d->invM, b, a, c, howmany, stream);
+    hs_cu_launch_chirp_crop(d->sgn, a, d_out, d->d_chirp, d->N, d->M, howmany, stream);
+}
+
+/* ---------------------------------------------------------------------------------- public API */
+
+fft_object fft_init(int N, int sgn)
+{
+    if (N <= 0) { /* undefined behaviour in the reference (segfault) */
+        fprintf(stderr, "Error: Signal length (%d) must be positive\n", N);
+        exit(EXIT_FAILURE);
+    }
+    fft_object obj = NULL;
+    int count;
+    if (dividebyN(N)) {
+        obj = (fft_object)malloc(sizeof(struct fft_set) + sizeof(fft_data) * (N - 1));
+        if (obj == NULL) return NULL;
+        obj->lf = factors(N, obj->factors);
+        longvectorN(obj->twiddle, N, obj->factors, obj->lf); /* exits for N == 1, like the reference */
+        count = N;
+        obj->lt = 0;
+    } else {
+        /* pad length recorded in the public struct: the reference's plan-time estimate (:242-252) */
+        const int K = (int)pow(2.0, ceil(log10(N) / log10(2.0)));
+        int M = (K < 2 * N - 2) ? K * 2 : K;
+        const int Mexec = hs_bluestein_exec_pad(N);
+        if (M < Mexec) M = Mexec; /* N = 2^k+1: the reference under-allocates here (its bug 4) */
+        obj = (fft_object)malloc(sizeof(struct fft_set) + sizeof(fft_data) * (M - 1));
+        if (obj == NULL) return NULL;
+        obj->lf = factors(M, obj->factors);
+        longvectorN(obj->twiddle, M, obj->factors, obj->lf);
+        count = M;
+        obj->lt = 1;
+    }
+    obj->N = N;
+    obj->sgn = sgn;
+    if (sgn == -1)
+        for (int i = 0; i < count; ++i) obj->twiddle[i].im = -obj->twiddle[i].im;
+    /* A stale registry entry under this address (plan free()d directly by its owner) is dropped
+     * lazily: hs_dev_get compares (N, sgn, lt) on the first execute. */
+    return obj;
+}
+
+static long long chunk_len(long long howmany, size_t bytes_per_xf)
+{
+    const size_t target = (size_t)64 << 20;
+    long long c = (long long)(target / (bytes_per_xf ? bytes_per_xf : 1));
+    if (c < 1) c = 1;
+    if (c > howmany) c = howmany;
+    return c;
+}
+
+void fft_exec_batch(fft_object obj, fft_data *inp, fft_data *oup, long howmany)
+{
+    if (obj == NULL || inp == NULL || oup == NULL) {
+        fprintf(stderr, "Error: Invalid FFT object or data pointers\n");
+        exit(EXIT_FAILURE);
+    }
+    if (obj->lt != 0 && obj->lt != 1) {
+        fprintf(stderr, "Error: Invalid FFT object type (lt = %d)\n", obj->lt);
+        exit(EXIT_FAILURE);
+    }
+    if (howmany <= 0) return;
+    hs_dev_obj *d = hs_dev_get(obj);
+    const size_t row = sizeof(fft_data) * (size_t)d->N;
+    const long long chunk = chunk_len(howmany, row);
+    const long long nchunk = (howmany + chunk - 1) / chunk;
+    const int nslot = nchunk < HS_NSLOT ? (int)nchunk : HS_NSLOT;
+    for (int s = 0; s < nslot; ++s) hs_dev_reserve(d, s, row * chunk, row * chunk, hs_dev_ws_bytes(d, chunk), 0);
+    /* chunked three-deep pipeline: H2D(i+1) and D2H(i-1) overlap the kernels of chunk i */
+    for (long long i = 0; i < nchunk; ++i) {
+        const int s = (int)(i % HS_NSLOT);
+        const long long first = i * chunk, cnt = (first + chunk <= howmany) ? chunk : howmany - first;
+        hs_cu_h2d(d->d_in[s], inp + first * d->N, row * cnt, d->stream[s]);
+        hs_dev_exec(d, d->d_in[s], d->d_out[s], d->d_ws[s], cnt, d->stream[s]);
+        hs_cu_d2h(oup + first * d->N, d->d_out[s], row * cnt, d->stream[s]);
+    }
+    for (int s = 0; s < nslot; ++s) hs_cu_stream_sync(d->stream[s]);
+}
+
+void fft_exec(fft_object obj, fft_data *inp, fft_data *oup)
+{
+    fft_exec_batch(obj, inp, oup, 1);
+}
+
+void fft_exec_batch_dev(fft_object obj, const fft_data *d_in, fft_data *d_out, long howmany, void *stream)
+{
+    if (obj == NULL || d_in == NULL || d_out == NULL) {
+        fprintf(stderr, "Error: Invalid FFT object or data pointers\n");
+        exit(EXIT_FAILURE);
+    }
+    if (howmany <= 0) return;
+    hs_dev_obj *d = hs_dev_get(obj);
+    hs_dev_reserve(d, 0, 0, 0, hs_dev_ws_bytes(d, howmany), 0);
+    hs_dev_exec(d, d_in, d_out, d->d_ws[0], howmany, stream);
+}
+
+void free_fft(fft_object object)
+{
+    if (object) hs_dev_release(object);
+    free(object);
+}
+
+/* ----------------------------------------------------------------------------- device helpers */
+
+int hsfft_device_count(void) { return hs_cu_device_count(); }
+void hsfft_set_device(int dev) { hs_cu_set_device(dev); }
+int hsfft_get_device(void) { return hs_cu_get_device(); }
+void *hsfft_malloc_device(size_t bytes) { hs_cu_require_device(); return hs_cu_malloc(bytes); }
+void hsfft_free_device(void *d) { hs_cu_free(d); }
+void *hsfft_malloc_host(size_t bytes) { hs_cu_require_device(); return hs_cu_malloc_host(bytes); }
+void hsfft_free_host(void *h) { hs_cu_free_host(h); }
+void hsfft_copy_h2d(void *d, const void *h, size_t bytes) { hs_cu_h2d(d, h, bytes, NULL); hs_cu_stream_sync(NULL); }
+void hsfft_copy_d2h(void *h, const void *d, size_t bytes) { hs_cu_d2h(h, d, bytes, NULL); hs_cu_stream_sync(NULL); }
+void hsfft_sync(void) { hs_cu_stream_sync(NULL); }
+long long hsfft_launch_count(void) { return hs_cu_launch_count(); }
+const char *hsfft_version(void) { return "hsfft-b200 0.1 (sm_100a)"; }
+
+const char *hsfft_plan_describe(fft_object obj)
+{
+    static char buf[512];
+    if (!obj) return "null plan";
+    hs_dev_obj *d = hs_dev_get(obj);
+    int n = 0;
+    if (d->lt == 0) {
+        const hs_c2c *p = d->direct;
+        if (p->ct_id >= 0) n = snprintf(buf, sizeof buf, "mixed-radix N=%d: compile-time smem kernel #%d", d->N, p->ct_id);
+        else {
+            n = snprintf(buf, sizeof buf, "mixed-radix N=%d: %d run-time pass(es):", d->N, p->npass);
+            for (int g = 0; g < p->npass && n < (int)sizeof buf - 32; ++g)
+                n += snprintf(buf + n, sizeof buf - n, " [n=%d C=%d]", p->pass[g].n, p->pass[g].C);
+        }
+    } else if (d->blu_ct_id >= 0)
+        n = snprintf(buf, sizeof buf, "bluestein N=%d M=%d: fused compile-time kernel #%d", d->N, d->M, d->blu_ct_id);
+    else
+        n = snprintf(buf, sizeof buf, "bluestein N=%d M=%d: unfused (chirp, FFT_M x%d pass, mul, IFFT_M, chirp)", d->N, d->M,
+                     d->fwdM->ct_id >= 0 ? 1 : d->fwdM->npass);
+    (void)n;
+    return buf;
+}

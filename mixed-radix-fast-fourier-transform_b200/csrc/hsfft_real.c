@@ -1,0 +1,302 @@
+/*
+ * hsfft_real.c -- real-input transforms (host side, plain C).
+ *
+ * Replaces reference src/real.c: fft_real_init :26-64, fft_r2c_exec :78-136, fft_c2r_exec :150-193,
+ * free_real_fft :259-267 and the helper exports :198-257.
+ *
+ * The reference packs N reals as N/2 complex samples (a pure reinterpretation of the same bytes,
+ * :99-103), runs the half-length complex plan, and splits / merges with the table
+ * twiddle2[k] = exp(+2 pi i k / N).  Here the pack is free (the device reads the real rows as
+ * complex rows), the half-length transform runs on the GPU through the complex plan's own
+ * execution plan, and the split (r2c) / merge (c2r) arithmetic keeps the reference's expressions.
+ */
+#include "hs_engine.h"
+#include "../../include/hsfft_b200.h"
+
+#include <pthread.h>
+
+/* device state of a real plan: twiddle2 in HBM, keyed by the real plan's address */
+typedef struct hs_real_dev {
+    const void *key;
+    int H;
+    void *d_tw2;
+    void *stream[HS_NSLOT];
+    void *d_in[HS_NSLOT], *d_out[HS_NSLOT], *d_z[HS_NSLOT], *d_ws[HS_NSLOT];
+    size_t cap_in[HS_NSLOT], cap_out[HS_NSLOT], cap_z[HS_NSLOT], cap_ws[HS_NSLOT];
+    struct hs_real_dev *next;
+} hs_real_dev;
+
+static pthread_mutex_t r_lock = PTHREAD_MUTEX_INITIALIZER;
+static hs_real_dev *r_head = NULL;
+
+static void real_dev_clear(hs_real_dev *r)
+{
+    hs_cu_free(r->d_tw2);
+    for (int s = 0; s < HS_NSLOT; ++s) {
+        hs_cu_free(r->d_in[s]); hs_cu_free(r->d_out[s]); hs_cu_free(r->d_z[s]); hs_cu_free(r->d_ws[s]);
+        if (r->stream[s]) hs_cu_stream_destroy(r->stream[s]);
+    }
+}
+
+static hs_real_dev *real_dev_get(fft_real_object obj)
+{
+    hs_cu_require_device();
+    const int H = obj->cobj->N;
+    pthread_mutex_lock(&r_lock);
+    hs_real_dev *r = r_head;
+    while (r && r->key != obj) r = r->next;
+    if (r && r->H != H) { /* address re-used by a different plan */
+        hs_real_dev *nx = r->next;
+        real_dev_clear(r);
+        memset(r, 0, sizeof(*r));
+        r->next = nx;
+        r->key = NULL;
+    }
+    if (!r) {
+        r = (hs_real_dev *)calloc(1, sizeof(*r));
+        if (!r) { fprintf(stderr, "Error: Memory allocation failed for real FFT object\n"); exit(EXIT_FAILURE); }
+        r->next = r_head;
+        r_head = r;
+    }
+    if (r->key == NULL) {
+        r->key = obj;
+        r->H = H;
+        r->d_tw2 = hs_cu_malloc(sizeof(fft_data) * (size_t)H);
+        hs_cu_h2d(r->d_tw2, obj->twiddle2, sizeof(fft_data) * (size_t)H, NULL);
+        for (int s = 0; s < HS_NSLOT; ++s) r->stream[s] = hs_cu_stream_create();
+    }
+    pthread_mutex_unlock(&r_lock);
+    return r;
+}
+
+static void real_dev_release(const void *key)
+{
+    pthread_mutex_lock(&r_lock);
+    hs_real_dev **pp = &r_head;
+    while (*pp && (*pp)->key != key) pp = &(*pp)->next;
+    if (*pp) {
+        hs_real_dev *r = *pp;
+        *pp = r->next;
+        real_dev_clear(r);
+        free(r);
+    }
+    pthread_mutex_unlock(&r_lock);
+}
+
+static void grow(void **buf, size_t *cap, size_t need)
+{
+    if (need <= *cap) return;
+    hs_cu_free(*buf);
+    *buf = hs_cu_malloc(need);
+    *cap = need;
+}
+
+/* ---------------------------------------------------------------------------------- public API */
+
+fft_real_object fft_real_init(int signal_length, int transform_direction)
+{
+    if (signal_length <= 0 || signal_length % 2 != 0) {
+        fprintf(stderr, "Error: Signal length (%d) must be positive and even\n", signal_length);
+        exit(EXIT_FAILURE);
+    }
+    const int half = signal_length / 2;
+    fft_real_object obj = (fft_real_object)malloc(sizeof(struct fft_real_set) + sizeof(fft_data) * half);
+    if (obj == NULL) {
+        fprintf(stderr, "Error: Memory allocation failed for real FFT object\n");
+        exit(EXIT_FAILURE);
+    }
+    obj->cobj = fft_init(half, transform_direction);
+    if (obj->cobj == NULL) {
+        free(obj);
+        fprintf(stderr, "Error: Failed to initialize complex FFT object\n");
+        exit(EXIT_FAILURE);
+    }
+    for (int k = 0; k < half; ++k) {
+        const fft_type angle = PI2 * k / signal_length;
+        obj->twiddle2[k].re = cos(angle);
+        obj->twiddle2[k].im = sin(angle);
+    }
+    return obj;
+}
+
+static void check_real_args(fft_real_object obj, const void *a, const void *b)
+{
+    if (obj == NULL || a == NULL || b == NULL || obj->cobj == NULL) {
+        fprintf(stderr, "Error: Invalid real FFT object or data pointers\n");
+        exit(EXIT_FAILURE);
+    }
+}
+
+/* device-pointer cores; d_z holds howmany*H complex, d_ws the complex plan's workspace */
+static void r2c_dev(fft_real_object obj, hs_real_dev *r, const fft_type *d_in, fft_data *d_out, long out_stride, int full, void *d_z,
+                    void *d_ws, long howmany, void *stream)
+{
+    hs_dev_obj *c = hs_dev_get(obj->cobj);
+    hs_dev_exec(c, d_in, d_z, d_ws, howmany, stream); /* rows of N reals == rows of H complex */
+    hs_cu_launch_r2c_post(d_z, d_out, r->d_tw2, r->H, out_stride, full, howmany, stream);
+}
+
+static void c2r_dev(fft_real_object obj, hs_real_dev *r, const fft_data *d_in, long in_stride, fft_type *d_out, void *d_z, void *d_ws,
+                    long howmany, void *stream)
+{
+    hs_dev_obj *c = hs_dev_get(obj->cobj);
+    hs_cu_launch_c2r_pre(d_in, d_z, r->d_tw2, r->H, in_stride, howmany, stream);
+    hs_dev_exec(c, d_z, d_out, d_ws, howmany, stream);
+}
+
+void fft_r2c_exec_batch_dev(fft_real_object obj, const fft_type *d_in, fft_data *d_out, long out_stride, int full, long howmany,
+                            void *stream)
+{
+    check_real_args(obj, d_in, d_out);
+    if (howmany <= 0) return;
+    hs_real_dev *r = real_dev_get(obj);
+    if (out_stride < r->H + 1 || (full && out_stride < 2 * r->H)) {
+        fprintf(stderr, "Error: r2c output stride %ld too small for N = %d\n", out_stride, 2 * r->H);
+        exit(EXIT_FAILURE);
+    }
+    hs_dev_obj *c = hs_dev_get(obj->cobj);
+    grow(&r->d_z[0], &r->cap_z[0], sizeof(fft_data) * (size_t)howmany * r->H);
+    grow(&r->d_ws[0], &r->cap_ws[0], hs_dev_ws_bytes(c, howmany));
+    r2c_dev(obj, r, d_in, d_out, out_stride, full, r->d_z[0], r->d_ws[0], howmany, stream);
+}
+
+void fft_c2r_exec_batch_dev(fft_real_object obj, const fft_data *d_in, long in_stride, fft_type *d_out, long howmany, void *stream)
+{
+    check_real_args(obj, d_in, d_out);
+    if (howmany <= 0) return;
+    hs_real_dev *r = real_dev_get(obj);
+    if (in_stride < r->H + 1) {
+        fprintf(stderr, "Error: c2r input stride %ld too small for N = %d\n", in_stride, 2 * r->H);
+        exit(EXIT_FAILURE);
+    }
+    hs_dev_obj *c = hs_dev_get(obj->cobj);
+    grow(&r->d_z[0], &r->cap_z[0], sizeof(fft_data) * (size_t)howmany * r->H);
+    grow(&r->d_ws[0], &r->cap_ws[0], hs_dev_ws_bytes(c, howmany));
+    c2r_dev(obj, r, d_in, in_stride, d_out, r->d_z[0], r->d_ws[0], howmany, stream);
+}
+
+static long real_chunk(long howmany, size_t row_bytes)
+{
+    long c = (long)(((size_t)64 << 20) / row_bytes);
+    if (c < 1) c = 1;
+    return c > howmany ? howmany : c;
+}
+
+void fft_r2c_exec_batch(fft_real_object obj, fft_type *inp, fft_data *oup, long howmany)
+{
+    check_real_args(obj, inp, oup);
+    if (howmany <= 0) return;
+    hs_real_dev *r = real_dev_get(obj);
+    hs_dev_obj *c = hs_dev_get(obj->cobj);
+    const size_t N = 2 * (size_t)r->H, in_row = sizeof(fft_type) * N, out_row = sizeof(fft_data) * N;
+    const long chunk = real_chunk(howmany, out_row), nchunk = (howmany + chunk - 1) / chunk;
+    for (long i = 0; i < nchunk; ++i) {
+        const int s = (int)(i % HS_NSLOT);
+        const long first = i * chunk, cnt = (first + chunk <= howmany) ? chunk : howmany - first;
+        if (i < HS_NSLOT) {
+            grow(&r->d_in[s], &r->cap_in[s], in_row * chunk);
+            grow(&r->d_out[s], &r->cap_out[s], out_row * chunk);
+            grow(&r->d_z[s], &r->cap_z[s], sizeof(fft_data) * (size_t)chunk * r->H);
+            grow(&r->d_ws[s], &r->cap_ws[s], hs_dev_ws_bytes(c, chunk));
+        }
+        hs_cu_h2d(r->d_in[s], inp + first * N, in_row * cnt, r->stream[s]);
+        r2c_dev(obj, r, (const fft_type *)r->d_in[s], (fft_data *)r->d_out[s], (long)N, 1, r->d_z[s], r->d_ws[s], cnt, r->stream[s]);
+        hs_cu_d2h(oup + first * N, r->d_out[s], out_row * cnt, r->stream[s]);
+    }
+    for (int s = 0; s < HS_NSLOT; ++s) hs_cu_stream_sync(r->stream[s]);
+}
+
+void fft_c2r_exec_batch(fft_real_object obj, fft_data *inp, fft_type *oup, long howmany)
+{
+    check_real_args(obj, inp, oup);
+    if (howmany <= 0) return;
+    hs_real_dev *r = real_dev_get(obj);
+    hs_dev_obj *c = hs_dev_get(obj->cobj);
+    const size_t N = 2 * (size_t)r->H, in_row = sizeof(fft_data) * N, out_row = sizeof(fft_type) * N;
+    const long chunk = real_chunk(howmany, in_row), nchunk = (howmany + chunk - 1) / chunk;
+    for (long i = 0; i < nchunk; ++i) {
+        const int s = (int)(i % HS_NSLOT);
+        const long first = i * chunk, cnt = (first + chunk <= howmany) ? chunk : howmany - first;
+        if (i < HS_NSLOT) {
+            grow(&r->d_in[s], &r->cap_in[s], in_row * chunk);
+            grow(&r->d_out[s], &r->cap_out[s], out_row * chunk);
+            grow(&r->d_z[s], &r->cap_z[s], sizeof(fft_data) * (size_t)chunk * r->H);
+            grow(&r->d_ws[s], &r->cap_ws[s], hs_dev_ws_bytes(c, chunk));
+        }
+        /* a single transform is given as N/2+1 bins by reference-style callers; rows of a batch are N bins apart */
+        const size_t bytes = (howmany == 1) ? sizeof(fft_data) * (size_t)(r->H + 1) : in_row * cnt;
+        hs_cu_h2d(r->d_in[s], inp + first * N, bytes, r->stream[s]);
+        c2r_dev(obj, r, (const fft_data *)r->d_in[s], (long)N, (fft_type *)r->d_out[s], r->d_z[s], r->d_ws[s], cnt, r->stream[s]);
+        hs_cu_d2h(oup + first * N, r->d_out[s], out_row * cnt, r->stream[s]);
+    }
+    for (int s = 0; s < HS_NSLOT; ++s) hs_cu_stream_sync(r->stream[s]);
+}
+
+void fft_r2c_exec(fft_real_object real_obj, fft_type *input_data, fft_data *output_data)
+{
+    fft_r2c_exec_batch(real_obj, input_data, output_data, 1);
+}
+
+void fft_c2r_exec(fft_real_object real_obj, fft_data *input_data, fft_type *output_data)
+{
+    fft_c2r_exec_batch(real_obj, input_data, output_data, 1);
+}
+
+void free_real_fft(fft_real_object real_obj)
+{
+    if (real_obj != NULL) {
+        real_dev_release(real_obj);
+        free_fft(real_obj->cobj);
+        free(real_obj);
+    }
+}
+
+/* ------------------------------------------------- helper exports of the reference's real.c */
+#define HS_M_PI 3.14159265358979323846
+
+void generate_signal(fft_data *signal, int length, double freq, double amplitude)
+{
+    for (int i = 0; i < length; i++) {
+        signal[i].re = amplitude * sin(2.0 * HS_M_PI * freq * i / length);
+        signal[i].im = 0.0;
+    }
+}
+
+double compute_mse(fft_data *original, fft_data *reconstructed, int length)
+{
+    double acc = 0.0;
+    for (int i = 0; i < length; i++) {
+        const double dr = original[i].re - reconstructed[i].re, di = original[i].im - reconstructed[i].im;
+        acc += dr * dr + di * di;
+    }
+    return acc / length;
+}
+
+void print_complex(fft_data *data, int length, const char *label)
+{
+    printf("%s:\n", label);
+    for (int i = 0; i < length; i++) printf("  [%d] %.6f + %.6fi\n", i, data[i].re, data[i].im);
+    printf("\n");
+}
+
+void generate_real_signal(fft_type *signal, int length, double freq, double amplitude)
+{
+    for (int i = 0; i < length; i++) signal[i] = amplitude * sin(2.0 * HS_M_PI * freq * i / length);
+}
+
+double compute_mse_real(fft_type *original, fft_type *reconstructed, int length)
+{
+    double acc = 0.0;
+    for (int i = 0; i < length; i++) {
+        const double d = original[i] - reconstructed[i];
+        acc += d * d;
+    }
+    return acc / length;
+}
+
+void print_real(fft_type *data, int length, const char *label)
+{
+    printf("%s:\n", label);
+    for (int i = 0; i < length; i++) printf("  [%d] %.6f\n", i, data[i]);
+    printf("\n");
+}

@@ -1,0 +1,127 @@
+// hs_device_emu.cpp -- CPU emulation of the CUDA side of hs_abi.h.  TEST INFRASTRUCTURE ONLY.
+//
+// Linked with the product's own host C files (hsfft_plan.c, hsfft_real.c, hsfft_convolve.c) and
+// the product's own kernel headers (csrc/*.cuh compiled with HS_EMU) into
+// tests/emu/_build/libhsfft_emu.so, it runs the REAL kernel bodies with one OS thread per CUDA
+// thread.  It exists so the index arithmetic, barrier placement, planner and numerics can be
+// checked against the oracle on a box without a GPU.  It is never shipped, never imported by the
+// package, and is orders of magnitude slower than anything one would call a fallback.
+#include "hs_emu.h"
+
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "hs_abi.h"
+#include "hs_fused.cuh"
+#include "hs_generic.cuh"
+#include "hs_smem_fft.cuh"
+
+typedef void *hs_stream_t;
+static std::atomic<long long> g_launches{0};
+
+template <class P, int SGN, int MINB>
+static void launch_c2c(const void *in, void *out, const void *tw, long long howmany, hs_stream_t)
+{
+    const long long blocks = (howmany + P::X - 1) / P::X;
+    hs_emu_launch(hs_c2c_smem_kernel<P, SGN, MINB>, blocks, P::threads, P::smem_bytes, (const cplx *)in, (cplx *)out, (const cplx *)tw,
+                  howmany);
+    ++g_launches;
+}
+
+template <class PF, class PI, int SGN, int MINB>
+static void launch_blu(int N, const void *in, void *out, const void *twf, const void *twi, const void *chirp, const void *hk,
+                       long long howmany, hs_stream_t)
+{
+    const long long blocks = (howmany + PF::X - 1) / PF::X;
+    hs_emu_launch(hs_bluestein_kernel<PF, PI, SGN, MINB>, blocks, PF::threads, PF::smem_bytes, (const cplx *)in, (cplx *)out,
+                  (const cplx *)twf, (const cplx *)twi, (const cplx *)chirp, (const cplx *)hk, N, howmany);
+    ++g_launches;
+}
+
+#include "hs_ct_table.cuh"
+
+extern "C" {
+int hs_cu_device_count(void) { return 1; }
+void hs_cu_require_device(void) {}
+int hs_cu_get_device(void) { return 0; }
+void hs_cu_set_device(int) {}
+int hs_cu_sm_count(void) { return 148; }
+void *hs_cu_malloc(size_t bytes) { return malloc(bytes ? bytes : 16); }
+void hs_cu_free(void *d) { free(d); }
+void *hs_cu_malloc_host(size_t bytes) { return malloc(bytes ? bytes : 16); }
+void hs_cu_free_host(void *h) { free(h); }
+void hs_cu_h2d(void *d, const void *h, size_t bytes, void *) { if (bytes) memcpy(d, h, bytes); }
+void hs_cu_d2h(void *h, const void *d, size_t bytes, void *) { if (bytes) memcpy(h, d, bytes); }
+void hs_cu_d2d(void *dst, const void *src, size_t bytes, void *) { if (bytes) memmove(dst, src, bytes); }
+void hs_cu_memset0(void *d, size_t bytes, void *) { if (bytes) memset(d, 0, bytes); }
+void *hs_cu_stream_create(void) { return (void *)1; }
+void hs_cu_stream_destroy(void *) {}
+void hs_cu_stream_sync(void *) {}
+void *hs_cu_event_create(void) { return (void *)1; }
+void hs_cu_event_destroy(void *) {}
+void hs_cu_event_record(void *, void *) {}
+void hs_cu_stream_wait_event(void *, void *) {}
+float hs_cu_event_elapsed_ms(void *, void *) { return 0.f; }
+void hs_cu_event_sync(void *) {}
+long long hs_cu_launch_count(void) { return g_launches.load(); }
+
+void hs_cu_launch_generic(int sgn, const void *d_in, void *d_out, const hs_gen_params *p, void *)
+{
+    const long long ntile = (p->n_c + p->C - 1) / p->C;
+    const long long blocks = ntile * p->n_o * p->n_batch;
+    const size_t smem = (size_t)2 * p->C * p->npad * sizeof(cplx);
+    const int threads = 64; // the kernel strides by blockDim; fewer OS threads keep the emulation quick
+    if (sgn == 1) hs_emu_launch(hs_generic_pass_kernel<1>, blocks, threads, smem, (const cplx *)d_in, (cplx *)d_out, *p);
+    else hs_emu_launch(hs_generic_pass_kernel<-1>, blocks, threads, smem, (const cplx *)d_in, (cplx *)d_out, *p);
+    ++g_launches;
+}
+
+static long long ew_blocks(long long total) { long long b = (total + 63) / 64; return b > 4 ? 4 : (b < 1 ? 1 : b); }
+
+void hs_cu_launch_chirp_pad(int sgn, const void *x, void *a, const void *h, int N, int M, long long howmany, void *)
+{
+    if (sgn == 1) hs_emu_launch(hs_chirp_pad_kernel<1>, ew_blocks(howmany * M), 64, 0, (const cplx *)x, (cplx *)a, (const cplx *)h, N, M, howmany);
+    else hs_emu_launch(hs_chirp_pad_kernel<-1>, ew_blocks(howmany * M), 64, 0, (const cplx *)x, (cplx *)a, (const cplx *)h, N, M, howmany);
+    ++g_launches;
+}
+void hs_cu_launch_spectrum_mul(int sgn, void *A, const void *Hk, int M, long long howmany, void *)
+{
+    if (sgn == 1) hs_emu_launch(hs_spectrum_mul_kernel<1>, ew_blocks(howmany * M), 64, 0, (cplx *)A, (const cplx *)Hk, M, howmany);
+    else hs_emu_launch(hs_spectrum_mul_kernel<-1>, ew_blocks(howmany * M), 64, 0, (cplx *)A, (const cplx *)Hk, M, howmany);
+    ++g_launches;
+}
+void hs_cu_launch_chirp_crop(int sgn, const void *y, void *out, const void *h, int N, int M, long long howmany, void *)
+{
+    if (sgn == 1) hs_emu_launch(hs_chirp_crop_kernel<1>, ew_blocks(howmany * N), 64, 0, (const cplx *)y, (cplx *)out, (const cplx *)h, N, M, howmany);
+    else hs_emu_launch(hs_chirp_crop_kernel<-1>, ew_blocks(howmany * N), 64, 0, (const cplx *)y, (cplx *)out, (const cplx *)h, N, M, howmany);
+    ++g_launches;
+}
+void hs_cu_launch_r2c_post(const void *Z, void *out, const void *tw2, int H, long long out_stride, int full, long long howmany, void *)
+{
+    hs_emu_launch(hs_r2c_post_kernel, ew_blocks(howmany * (H + 1)), 64, 0, (const cplx *)Z, (cplx *)out, (const cplx *)tw2, H, out_stride, full,
+                  howmany);
+    ++g_launches;
+}
+void hs_cu_launch_c2r_pre(const void *in, void *z, const void *tw2, int H, long long in_stride, long long howmany, void *)
+{
+    hs_emu_launch(hs_c2r_pre_kernel, ew_blocks(howmany * H), 64, 0, (const cplx *)in, (cplx *)z, (const cplx *)tw2, H, in_stride, howmany);
+    ++g_launches;
+}
+void hs_cu_launch_conv_mul(const void *A, const void *B, void *C, long long total, double scale, void *)
+{
+    hs_emu_launch(hs_conv_mul_kernel, ew_blocks(total), 64, 0, (const cplx *)A, (const cplx *)B, (cplx *)C, total, scale);
+    ++g_launches;
+}
+void hs_cu_launch_pad_rows(const void *src, int len, void *dst, int P, long long howmany, void *)
+{
+    hs_emu_launch(hs_pad_rows_kernel, ew_blocks(howmany * P), 64, 0, (const double *)src, len, (double *)dst, P, howmany);
+    ++g_launches;
+}
+void hs_cu_launch_slice_rows(const void *src, int P, int start, int len, void *dst, long long dst_stride, long long howmany, void *)
+{
+    hs_emu_launch(hs_slice_rows_kernel, ew_blocks(howmany * len), 64, 0, (const double *)src, P, start, len, (double *)dst, dst_stride, howmany);
+    ++g_launches;
+}
+}
