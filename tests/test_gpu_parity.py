@@ -1,0 +1,148 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (libhsfft_b200.so), against the oracle
+on the same seeded inputs.  Tolerance = north_star's: relative RMS <= 1e-12 * log2(N), forward and
+inverse, per transform.  Run on the B200 box with `pytest -m gpu`.
+"""
+import math
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib
+from oracle_lib import rand_cplx, rel_rms, tol, xorshift_uniform
+
+pytestmark = pytest.mark.gpu
+
+
+def per_transform_worst(y, r):
+    return max(rel_rms(y[i], r[i]) for i in range(y.shape[0]))
+
+
+# BASELINE.json config sizes + the reference's own self-test sizes (src/real.c:278,360) + edge sizes
+C2C_SIZES = [2, 3, 4, 5, 7, 8, 15, 16, 20, 64, 100, 128, 256, 512, 1000, 1024, 2048, 3000, 4096, 8192,
+             11, 13, 26, 143, 1001, 53 * 8, 17 * 29, 6561, 10000, 16384, 32768]
+BLUESTEIN_SIZES = [19, 59, 257, 513, 1009, 2018, 4099, 10007]
+
+
+@pytest.mark.parametrize("n", C2C_SIZES)
+@pytest.mark.parametrize("sgn", [1, -1])
+def test_c2c_mixed_radix(hs, product_lib, oracle, n, sgn):
+    howmany = 5 if n <= 8192 else 2
+    x = rand_cplx(howmany, n, seed=1234 + n)
+    with hs.Plan(n, sgn) as p:
+        assert p.lt == 0
+        y = p.exec(x)
+        y1 = p.exec(x[0])  # the reference-style single fft_exec call
+    r = oracle.c2c(x, sgn)
+    assert per_transform_worst(y, r) <= tol(n), p.describe()
+    assert rel_rms(y1, r[0]) <= tol(n)
+
+
+@pytest.mark.parametrize("n", BLUESTEIN_SIZES)
+@pytest.mark.parametrize("sgn", [1, -1])
+def test_c2c_bluestein(hs, product_lib, oracle, n, sgn):
+    howmany = 3
+    x = rand_cplx(howmany, n, seed=99 + n)
+    with hs.Plan(n, sgn) as p:
+        assert p.lt == 1
+        y = p.exec(x)
+    r = oracle.c2c(x, sgn)
+    assert per_transform_worst(y, r) <= tol(n)
+
+
+@pytest.mark.parametrize("n", [1024, 3000, 4096, 1009])
+def test_generic_engine_matches_compile_time_kernels(hs, product_lib, oracle, n):
+    """Same sizes through the run-time planned engine (HSFFT_NO_CT=1 is read at plan build)."""
+    x = rand_cplx(3, n, seed=5 + n)
+    os.environ["HSFFT_NO_CT"] = "1"
+    try:
+        with hs.Plan(n, 1) as p:
+            desc = p.describe()
+            y = p.exec(x)
+    finally:
+        del os.environ["HSFFT_NO_CT"]
+    assert "compile-time" not in desc
+    assert per_transform_worst(y, oracle.c2c(x, 1)) <= tol(n)
+
+
+def test_config1_n1024_forward_inverse_roundtrip(hs, product_lib, oracle):
+    """BASELINE.json config 1: N=1024, forward then inverse, /N round trip."""
+    n = 1024
+    x = rand_cplx(1, n)[0]
+    with hs.Plan(n, 1) as f, hs.Plan(n, -1) as b:
+        X = f.exec(x)
+        back = b.exec(X) / n
+    assert rel_rms(X, oracle.c2c(x, 1)) <= tol(n)
+    assert rel_rms(back, x) <= tol(n)
+
+
+def test_linearity_and_parseval_full_batch(hs, product_lib):
+    """Size-independent properties at the full BASELINE batch (device resident, N=4096 x 65536)."""
+    import torch
+    n, batch = 4096, 65536
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev); g.manual_seed(1)
+    x = torch.rand((batch, n), generator=g, device=dev, dtype=torch.float64).to(torch.complex128)
+    x = x + 1j * torch.rand((batch, n), generator=g, device=dev, dtype=torch.float64)
+    y = torch.empty_like(x)
+    with hs.Plan(n, 1) as p:
+        p.exec_dev(x, y, batch)
+        torch.cuda.synchronize()
+        # Parseval per transform
+        ex = (x.abs() ** 2).sum(dim=1)
+        ey = (y.abs() ** 2).sum(dim=1) / n
+        assert float(((ex - ey).abs() / ex).max()) < 1e-12
+        # first / last / random transforms against torch's own fp64 FFT (independent cross-check)
+        idx = torch.tensor([0, 1, 777, 40000, batch - 1], device=dev)
+        ref = torch.fft.fft(x[idx], dim=1)
+        err = (y[idx] - ref).abs().pow(2).sum(dim=1).sqrt() / ref.abs().pow(2).sum(dim=1).sqrt()
+        assert float(err.max()) < 1e-12 * math.log2(n)
+        # inverse round trip of the whole batch
+        z = torch.empty_like(x)
+        with hs.Plan(n, -1) as q:
+            q.exec_dev(y, z, batch)
+        torch.cuda.synchronize()
+        rt = ((z / n - x).abs().pow(2).sum(dim=1).sqrt() / x.abs().pow(2).sum(dim=1).sqrt()).max()
+        assert float(rt) < 1e-12 * math.log2(n)
+
+
+@pytest.mark.parametrize("n", [4, 8, 16, 32, 64, 2018, 4096, 8192, 1 << 15])
+def test_real_r2c_c2r(hs, product_lib, oracle, n):
+    x = xorshift_uniform(3 * n, seed=n).reshape(3, n)
+    with hs.RealPlan(n, 1) as f, hs.RealPlan(n, -1) as g:
+        X = f.r2c(x)
+        Xr = oracle.r2c(x)
+        assert per_transform_worst(X, Xr) <= tol(n)
+        # Hermitian mirror written in full (reference src/real.c:128-132)
+        assert np.array_equal(X[:, n - 1: n // 2: -1], np.conj(X[:, 1: n // 2]))
+        y = g.c2r(X)
+        assert per_transform_worst(y, oracle.c2r(Xr, n)) <= tol(n)
+        assert rel_rms(y / n, x) <= tol(n)
+
+
+@pytest.mark.parametrize("la,lb", [(5, 3), (100, 37), (512, 512), (1000, 24), (4096, 4096)])
+@pytest.mark.parametrize("type_", ["full", "same", "valid"])
+def test_convolve_linear(hs, product_lib, oracle, la, lb, type_):
+    a = xorshift_uniform(la, seed=la)
+    b = xorshift_uniform(lb, seed=lb + 1)
+    n, y = hs.convolve(a, b, type_, "linear")
+    nr, yr = oracle.convolve(a, b, type_, "linear")
+    assert n == nr
+    assert rel_rms(y, yr) <= 1e-12 * math.log2(max(la + lb, 4))
+
+
+def test_convolve_circular_and_errors(hs, product_lib, oracle):
+    a = xorshift_uniform(100, seed=1)
+    b = xorshift_uniform(37, seed=2)
+    n, y = hs.convolve(a, b, "full", "circular")
+    nr, yr = oracle.convolve(a, b, "full", "circular")
+    assert n == nr == 128 and rel_rms(y, yr) <= 1e-11
+    assert hs.convolve(a, b, "bogus", "linear")[0] == -1
+    assert hs.convolve(a, b, "full", "nope")[0] == -1
+
+
+def test_kernels_really_launched(hs, product_lib):
+    before = hs.launch_count()
+    with hs.Plan(4096, 1) as p:
+        p.exec(rand_cplx(2, 4096))
+    assert hs.launch_count() > before
