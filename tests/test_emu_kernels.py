@@ -1,0 +1,119 @@
+"""CPU tests that run the product's KERNEL SOURCE (csrc/*.cuh) under the thread emulation of
+tests/emu (one OS thread per CUDA thread, std::barrier for __syncthreads) and compare with the
+oracle.  This checks index arithmetic, barrier placement, the planner and the numerics of every
+kernel family without a GPU; the same cases run on the B200 in test_gpu_parity.py."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle_lib import rand_cplx, rel_rms, tol, xorshift_uniform
+
+
+def run_c2c(hs, lib, oracle, n, sgn, howmany=2, seed=0):
+    x = rand_cplx(howmany, n, seed=77 + n + seed)
+    with hs.Plan(n, sgn, lib=lib) as p:
+        desc = p.describe()
+        y = p.exec(x)
+    r = oracle.c2c(x, sgn)
+    return max(rel_rms(y[i], r[i]) for i in range(howmany)), desc
+
+
+@pytest.mark.parametrize("n", [4096, 3000, 1024, 2048, 512, 256, 8192])
+def test_compile_time_plans(hs, emu_lib, oracle, n):
+    for sgn in (1, -1):
+        err, desc = run_c2c(hs, emu_lib, oracle, n, sgn, howmany=5 if n <= 1024 else 2)
+        assert "compile-time" in desc and err <= tol(n), (n, sgn, err, desc)
+
+
+def test_n3000_is_within_rounding_of_the_reference_not_just_tolerance(hs, emu_lib, oracle):
+    """Same butterflies, same truncated constants, same stage twiddles: ~1e-16, far below 1.16e-11."""
+    err, _ = run_c2c(hs, emu_lib, oracle, 3000, 1)
+    assert err <= 1e-15
+
+
+@pytest.mark.parametrize("n", [1009, 513, 600, 1000])
+def test_fused_bluestein_and_neighbours(hs, emu_lib, oracle, n):
+    for sgn in (1, -1):
+        err, desc = run_c2c(hs, emu_lib, oracle, n, sgn)
+        assert err <= tol(n), (n, sgn, err, desc)
+
+
+@pytest.mark.parametrize("n", [2, 3, 4, 5, 7, 8, 15, 20, 64, 11, 13, 26, 143, 53, 1001, 19, 59, 257])
+def test_runtime_planned_engine_small(hs, emu_lib, oracle, n):
+    for sgn in (1, -1):
+        err, desc = run_c2c(hs, emu_lib, oracle, n, sgn, howmany=3)
+        assert err <= tol(n), (n, sgn, err, desc)
+
+
+@pytest.mark.parametrize("n", [6561, 10000, 32768, 10007])
+def test_runtime_planned_engine_multipass(hs, emu_lib, oracle, n):
+    err, desc = run_c2c(hs, emu_lib, oracle, n, 1, howmany=2)
+    assert ("pass" in desc) and err <= tol(n), (n, err, desc)
+
+
+def test_three_pass_plan(hs, emu_lib, oracle):
+    n = 1 << 19
+    err, desc = run_c2c(hs, emu_lib, oracle, n, -1, howmany=1)
+    assert "3 run-time" in desc and err <= tol(n), (err, desc)
+
+
+@pytest.mark.parametrize("n", [4, 8, 16, 32, 64, 2018, 4096])
+def test_real_transforms(hs, emu_lib, oracle, n):
+    x = xorshift_uniform(3 * n, seed=5 + n).reshape(3, n)
+    with hs.RealPlan(n, 1, lib=emu_lib) as f, hs.RealPlan(n, -1, lib=emu_lib) as g:
+        X = f.r2c(x)
+        Xr = oracle.r2c(x)
+        assert rel_rms(X, Xr) <= tol(n)
+        assert np.array_equal(X[:, n - 1: n // 2: -1], np.conj(X[:, 1: n // 2]))   # mirror bins written
+        y = g.c2r(X)
+        assert rel_rms(y, oracle.c2r(Xr, n)) <= tol(n)
+        assert rel_rms(y / n, x) <= tol(n)
+        assert rel_rms(g.c2r(f.r2c(x[0])) / n, x[0]) <= tol(n)                   # single-transform entry points
+
+
+@pytest.mark.parametrize("la,lb", [(5, 3), (100, 37), (512, 512), (1000, 24)])
+def test_convolution(hs, emu_lib, oracle, la, lb):
+    a, b = xorshift_uniform(la, seed=la), xorshift_uniform(lb, seed=lb + 1)
+    for t in ("full", "same", "valid"):
+        n, y = hs.convolve(a, b, t, "linear", lib=emu_lib)
+        nr, yr = oracle.convolve(a, b, t, "linear")
+        assert n == nr and rel_rms(y, yr) <= 1e-14
+    n, y = hs.convolve(a, b, "full", "circular", lib=emu_lib)
+    nr, yr = oracle.convolve(a, b, "full", "circular")
+    assert n == nr and rel_rms(y, yr) <= 1e-14
+    assert hs.convolve(a, b, "bogus", "linear", lib=emu_lib)[0] == -1
+    assert hs.convolve(a, b, "full", "nope", lib=emu_lib)[0] == -1
+
+
+def test_convolution_batch(hs, emu_lib):
+    a = xorshift_uniform(4 * 50, 3).reshape(4, 50)
+    b = xorshift_uniform(4 * 20, 4).reshape(4, 20)
+    n, y = hs.convolve_batch(a, b, lib=emu_lib)
+    assert n == 69
+    for i in range(4):
+        assert rel_rms(y[i], np.convolve(a[i], b[i])) <= 1e-14
+
+
+def test_batch_tail_and_chunking(hs, emu_lib, oracle):
+    """Batches that do not fill the last CTA (X transforms per CTA) and single transforms."""
+    for n, howmany in ((1024, 7), (256, 19), (64, 33)):
+        x = rand_cplx(howmany, n, seed=n)
+        with hs.Plan(n, 1, lib=emu_lib) as p:
+            assert rel_rms(p.exec(x), oracle.c2c(x, 1)) <= tol(n)
+
+
+def test_plan_address_reuse_rebuilds_device_state(hs, emu_lib, oracle):
+    """Callers may free() a plan directly (reference src/real.c:264); a new plan at the same address
+    with other (N, sgn) must not inherit the old device tables."""
+    import ctypes as C
+    libc = C.CDLL(None)
+    libc.free.argtypes = [C.c_void_p]
+    seen = 0
+    for n in (64, 128, 64, 256, 128):
+        p = hs.Plan(n, 1, lib=emu_lib)
+        x = rand_cplx(1, n, seed=n + seen)[0]
+        assert rel_rms(p.exec(x), oracle.c2c(x, 1)) <= tol(n)
+        libc.free(C.cast(p.p, C.c_void_p))      # bare free: the registry entry goes stale
+        p.p = None
+        seen += 1

@@ -1,0 +1,141 @@
+"""CPU tests of the product's HOST side (plain C in libhsfft_b200.so): the library loads, exports
+every symbol include/*.h declares, and builds plans whose public fields equal the reference's.
+No compute call is made here (that needs a GPU; see test_gpu_parity.py)."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_vectors.npz"))
+
+
+def test_library_exports_every_declared_symbol(hs, product_lib):
+    for name in hs.EXPORTS:
+        assert hasattr(product_lib, name), name
+    # and every function prototype in the public headers is in that list
+    declared = set()
+    for h in ("highspeedFFT.h", "real.h", "hsfft_b200.h"):
+        src = open(os.path.join(ROOT, "include", h)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        for m in re.finditer(r"^[ \t]*(?:const\s+)?[A-Za-z_][\w \*]*?[\s\*]([A-Za-z_]\w*)\s*\([^;{]*\)\s*;", src, flags=re.M):
+            declared.add(m.group(1))
+    assert declared and declared <= set(hs.EXPORTS), declared - set(hs.EXPORTS)
+
+
+def test_struct_layout_matches_reference_abi(hs):
+    """N@0 sgn@4 factors@8 lf@264 lt@268 twiddle@272, sizeof 288."""
+    S = hs.FftSet
+    assert (S.N.offset, S.sgn.offset, S.factors.offset, S.lf.offset, S.lt.offset, S.twiddle.offset) == (0, 4, 8, 264, 268, 272)
+    assert C.sizeof(S) == 288
+    code = r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "real.h"
+int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", offsetof(struct fft_set,N), offsetof(struct fft_set,sgn),
+ offsetof(struct fft_set,factors), offsetof(struct fft_set,lf), offsetof(struct fft_set,lt), offsetof(struct fft_set,twiddle),
+ sizeof(struct fft_set), offsetof(struct fft_real_set,twiddle2)); return 0;}'''
+    exe = "/tmp/hs_layout_test"
+    subprocess.run(["/usr/bin/gcc", "-x", "c", "-", "-I", os.path.join(ROOT, "include"), "-o", exe], input=code.encode(), check=True)
+    out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()
+    assert [int(v) for v in out] == [0, 4, 8, 264, 268, 272, 288, 8]
+
+
+def test_routing_and_factors_match_oracle_sweep(hs, product_lib, oracle):
+    for n in list(range(1, 3000)) + [4096, 10007, 32768, 1 << 19, 1 << 20, 3 ** 9, 19 * 64, 53 * 53 * 4]:
+        assert hs.dividebyN(n) == oracle.dividebyN(n), n
+        assert hs.factors(n) == oracle.factors(n), n
+
+
+def test_routing_matches_reference_build(hs, product_lib, ref_repaired):
+    for n in list(range(1, 1100)) + [2048, 3000, 4096, 10007]:
+        assert hs.dividebyN(n) == ref_repaired.dividebyN(n), n
+        assert hs.factors(n) == ref_repaired.factors(n), n
+
+
+@pytest.mark.parametrize("n", [15, 17, 64, 1024, 3000, 4096, 1009])
+@pytest.mark.parametrize("sgn", [1, -1])
+def test_plan_fields_equal_reference(hs, product_lib, oracle, n, sgn):
+    with hs.Plan(n, sgn) as p:
+        assert p.p.contents.N == n and p.p.contents.sgn == sgn
+        assert p.factors == list(GOLD["plan_%d_factors" % n])
+        assert p.lt == int(GOLD["plan_%d_lt" % n][0])
+        if p.lt == 0:
+            tw = p.twiddles(n - 1)
+            ref = GOLD["plan_%d_twiddle" % n]
+            ref = ref if sgn == 1 else np.conj(ref)
+            assert np.array_equal(tw, ref)                       # same cos/sin expression -> same bits
+            assert np.array_equal(tw, oracle.stage_twiddles(n, p.factors) if sgn == 1 else np.conj(oracle.stage_twiddles(n, p.factors)))
+
+
+def test_bluestein_plan_records_padded_length(hs, product_lib):
+    with hs.Plan(1009, 1) as p:
+        assert p.lt == 1 and p.factors == [8, 8, 8, 4]            # M = 2048
+    with hs.Plan(10007, -1) as p:
+        assert p.lt == 1 and p.factors == [8] * 5                  # M = 32768
+    with hs.Plan(19, 1) as p:                                      # 19 is not in the router's list
+        assert p.lt == 1
+
+
+def test_real_plan_fields(hs, product_lib):
+    n = 64
+    with hs.RealPlan(n, 1) as r:
+        assert r.p.contents.cobj.contents.N == n // 2
+        tw2 = r.twiddle2()
+        k = np.arange(n // 2)
+        assert np.allclose(tw2, np.exp(2j * np.pi * k / n), atol=1e-15)
+
+
+def test_convolution_length_helpers(hs, product_lib):
+    L = product_lib
+    assert [L.next_power_of_two(v) for v in (0, 1, 2, 3, 1023, 1024, 1025)] == [1, 1, 2, 4, 1024, 1024, 2048]
+    assert L.find_optimal_fft_length(1047, b"linear", 1000, 48) == 2048
+    assert L.find_optimal_fft_length(1047, b"circular", 1000, 48) == 1024
+
+
+def _run_snippet(code):
+    return subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT)
+
+
+PRE = "import importlib,sys; sys.path.insert(0,'.'); hs=importlib.import_module('mixed-radix-fast-fourier-transform_b200'); L=hs.load();"
+
+
+def test_error_convention_print_and_exit():
+    """Reference convention: message on stderr + exit(EXIT_FAILURE)."""
+    r = _run_snippet(PRE + "L.fft_real_init(7, 1)")
+    assert r.returncode == 1 and "must be positive and even" in r.stderr
+    r = _run_snippet(PRE + "L.fft_init(0, 1)")
+    assert r.returncode == 1 and "must be positive" in r.stderr
+    r = _run_snippet(PRE + "L.fft_init(1, 1)")                    # reference: longvectorN rejects num_factors == 0
+    assert r.returncode == 1 and "longvectorN" in r.stderr
+    r = _run_snippet(PRE + "import ctypes; L.fft_exec(None, None, None)")
+    assert r.returncode == 1 and "Invalid FFT object or data pointers" in r.stderr
+    r = _run_snippet(PRE + "L.find_optimal_fft_length(8, b'bogus', 4, 4)")
+    assert r.returncode == 1 and "Invalid convolution type" in r.stderr
+
+
+def test_no_cpu_fallback_exec_fails_loudly_without_gpu(hs, product_lib):
+    """The product path must not silently compute on the CPU."""
+    if product_lib.hsfft_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    r = _run_snippet(PRE + "import numpy as np; p=hs.Plan(64,1); p.exec(np.zeros(64,dtype=np.complex128)); print('computed')")
+    assert r.returncode == 1 and "no CPU fallback" in r.stderr and "computed" not in r.stdout
+
+
+def test_product_does_not_link_or_import_the_oracle():
+    pkg = os.path.join(ROOT, "mixed-radix-fast-fourier-transform_b200")
+    for dirpath, _, files in os.walk(pkg):
+        if os.path.basename(dirpath) == "build":
+            continue
+        for f in files:
+            if f.endswith((".c", ".h", ".cu", ".cuh", ".py")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "hsfft_oracle" not in txt and "liboracle" not in txt and "oracle_lib" not in txt, f
+    ldd = subprocess.run(["ldd", os.path.join(pkg, "libhsfft_b200.so")], capture_output=True, text=True).stdout
+    assert "oracle" not in ldd and "cufft" not in ldd.lower()

@@ -1,0 +1,33 @@
+#!/usr/bin/env python
+"""Top stall sites of an .ncu-rep source page (SASS view): tools/ncu_source.py rep [topN]"""
+import csv, io, subprocess, sys
+rep = sys.argv[1]; top = int(sys.argv[2]) if len(sys.argv) > 2 else 25
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(out)))
+hdr = rows[1]; body = [r for r in rows[2:] if len(r) == len(hdr)]
+ix = {h: i for i, h in enumerate(hdr)}
+tot = sum(int(r[ix["# Samples"]] or 0) for r in body)
+stalls = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
+agg = {s: sum(int(r[ix[s]] or 0) for r in body) for s in stalls}
+print("total samples", tot, " instrs", len(body))
+print("by reason:", ", ".join("%s=%.1f%%" % (k[6:], 100.0 * v / tot) for k, v in sorted(agg.items(), key=lambda kv: -kv[1]) if v))
+# cumulative by opcode class
+byop = {}
+for r in body:
+    op = r[ix["Source"]].split()[0] if r[ix["Source"]].split() else "?"
+    if op.startswith("@"): op = r[ix["Source"]].split()[1]
+    op = op.split(".")[0]
+    byop[op] = byop.get(op, 0) + int(r[ix["# Samples"]] or 0)
+print("by opcode:", ", ".join("%s=%.1f%%" % (k, 100.0 * v / tot) for k, v in sorted(byop.items(), key=lambda kv: -kv[1])[:14]))
+cnt = {}
+for r in body:
+    op = r[ix["Source"]].split()[0] if r[ix["Source"]].split() else "?"
+    if op.startswith("@"): op = r[ix["Source"]].split()[1]
+    op = op.split(".")[0]
+    cnt[op] = cnt.get(op, 0) + 1
+print("static instr mix:", ", ".join("%s=%d" % kv for kv in sorted(cnt.items(), key=lambda kv: -kv[1])[:16]))
+print("top sites:")
+for n, r in sorted(enumerate(body), key=lambda nr: -int(nr[1][ix["# Samples"]] or 0))[:top]:
+    s = int(r[ix["# Samples"]] or 0)
+    why = sorted(((int(r[ix[k]] or 0), k[6:]) for k in stalls), reverse=True)[:2]
+    print("  #%4d %5.1f%%  %-60s %s" % (n, 100.0 * s / tot, r[ix["Source"]].strip()[:60], " ".join("%s:%d" % (k, v) for v, k in why if v)))
