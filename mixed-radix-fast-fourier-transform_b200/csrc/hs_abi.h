@@ -18,6 +18,31 @@ extern "C" {
 #define HS_MAX_STAGES 32
 #define HS_MAX_GENERIC_RADIX 128
 
+/* Split stage twiddles.  A stage of radix r on sub-transforms of length m needs W_L^(i k), L = r m,
+ * i < r, k < m: (r-1) m table entries, each used once per transform -- for the last stage that is a
+ * table as large as the signal itself, streamed from L2 with its latency exposed in every CTA.
+ * When (r-1) m exceeds split_min entries the compile-time plans use k = k_lo + KL k_hi and
+ * W_L^(i k) = W_L^(i k_lo) * W_L^(i KL k_hi): two tables of (r-1) KL and (r-1) m/KL entries that stay
+ * L1 resident, at the price of one extra complex multiply per twiddle.  KL = largest divisor of m
+ * not above sqrt(m).  Shared by the kernels (constexpr) and the host table builder (plain C). */
+#ifdef __cplusplus
+#define HS_RULE constexpr
+#else
+#define HS_RULE static inline
+#endif
+HS_RULE int hs_split_kl(int r, int m, int split_min)
+{
+    if (split_min <= 0 || (r - 1) * m <= split_min) return 0;
+    int best = 1;
+    for (int d = 1; d * d <= m; ++d)
+        if (m % d == 0) best = d;
+    return best > 1 ? best : 0;
+}
+HS_RULE int hs_stage_tw_entries(int r, int m, int split_min)
+{
+    return hs_split_kl(r, m, split_min) ? (r - 1) * (hs_split_kl(r, m, split_min) + m / hs_split_kl(r, m, split_min)) : (r - 1) * m;
+}
+
 /* compile-time kernel families */
 enum { HS_CT_C2C = 0, HS_CT_BLUESTEIN = 1, HS_CT_COLS = 2, HS_CT_ROWS = 3 };
 
@@ -28,7 +53,7 @@ typedef struct hs_ct_desc {
     int n;          /* transform length held in shared memory */
     int nst;        /* stages */
     int radix[8];   /* execution order (leaf first) */
-    int nlogical;   /* Bluestein: the logical N this instance serves (0 = any up to (n+1)/2) */
+    int split_min;  /* twiddle-table split threshold of this plan (0 = never split), see hs_split_kl */
     int threads, smem_bytes;
 } hs_ct_desc;
 

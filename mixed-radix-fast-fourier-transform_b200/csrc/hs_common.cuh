@@ -54,11 +54,24 @@ static inline void hs_st_stream_d(double *p, double v) { *p = v; }
     extern __shared__ __align__(16) unsigned char hs_smem_raw[]; \
     type *name = reinterpret_cast<type *>(hs_smem_raw)
 #define HS_UNROLL _Pragma("unroll")
-// Signal samples are touched exactly once per pass: stream them (evict-first) so the L2 keeps
-// the twiddle / chirp tables, which every CTA re-reads.
-HS_DEVICE double2 hs_ld_stream(const double2 *p) { return __ldcs(p); }
-HS_DEVICE void hs_st_stream(double2 *p, double2 v) { __stcs(p, v); }
-HS_DEVICE double2 hs_ld_tab(const double2 *p) { return __ldg(p); }
+// Signal samples are touched exactly once per pass: keep them out of L1 (no_allocate) so that L1
+// holds the stage-twiddle / chirp tables, which every CTA on the SM re-reads (evict_last).
+HS_DEVICE double2 hs_ld_stream(const double2 *p)
+{
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+HS_DEVICE void hs_st_stream(double2 *p, double2 v)
+{
+    asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+}
+HS_DEVICE double2 hs_ld_tab(const double2 *p)
+{
+    double2 v;
+    asm volatile("ld.global.nc.L1::evict_last.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
 HS_DEVICE double hs_ld_stream_d(const double *p) { return __ldcs(p); }
 HS_DEVICE void hs_st_stream_d(double *p, double v) { __stcs(p, v); }
 #endif

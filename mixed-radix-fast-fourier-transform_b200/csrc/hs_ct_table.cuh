@@ -13,18 +13,24 @@
 // Stage radices in execution order (the reference's factor list reversed; runs of power-of-two
 // factors regrouped, which only exact constants allow -- SURVEY.md section 8c).  LOGPAD values come
 // from tests/emu/bank_check.py (all stages conflict free).
-//                      N     T   X  LOGPAD  radices...
-using P4096a = HsPlan<4096, 256, 1, 4, 16, 16, 16>;       // reference factors [8,8,8,8]
-using P4096b = HsPlan<4096, 512, 1, 3, 8, 8, 8, 8>;
-using P3000  = HsPlan<3000, 200, 1, 3, 3, 5, 5, 5, 8>;    // reference factors [8,5,5,5,3], verbatim
-using P1024  = HsPlan<1024, 64, 4, 3, 16, 8, 8>;          // reference factors [8,8,8,2]
-using P2048  = HsPlan<2048, 128, 2, 3, 16, 16, 8>;        // reference factors [8,8,8,4]
-using P512   = HsPlan<512, 64, 4, 3, 8, 8, 8>;
-using P256   = HsPlan<256, 16, 16, 4, 16, 16>;
-using P8192  = HsPlan<8192, 512, 1, 4, 8, 8, 8, 16>;
+//                      N     T   X  LOGPAD SPLIT GROUPS radices...
+using P4096a = HsPlan<4096, 256, 1, 4, -1, 0, 16, 16, 16>;       // reference factors [8,8,8,8]
+using P4096b = HsPlan<4096, 512, 1, 3, -1, 0, 8, 8, 8, 8>;
+using P3000  = HsPlan<3000, 200, 1, 3, -1, 221, 3, 5, 5, 5, 8>; // reference factors [8,5,5,5,3] verbatim; passes {3,5}{5,5}{8}
+using P1024  = HsPlan<1024, 64, 4, 3, -1, 0, 16, 8, 8>;          // reference factors [8,8,8,2]
+using P2048  = HsPlan<2048, 128, 2, 3, -1, 0, 16, 16, 8>;        // reference factors [8,8,8,4]
+using P512   = HsPlan<512, 64, 4, 3, -1, 0, 8, 8, 8>;
+using P256   = HsPlan<256, 16, 16, 4, -1, 0, 16, 16>;
+using P8192  = HsPlan<8192, 512, 1, 4, -1, 0, 8, 8, 8, 16>;
 // fused Bluestein, M = 2048 (N = 513..1024, e.g. the N = 1009 config): forward / inverse pair
-using PB2048f = HsPlan<2048, 128, 2, 4, 8, 16, 16>;
-using PB2048i = HsPlan<2048, 128, 2, 4, 16, 16, 8>;
+using PB2048f = HsPlan<2048, 128, 2, 4, -1, 0, 8, 16, 16>;
+using PB2048i = HsPlan<2048, 128, 2, 4, -1, 0, 16, 16, 8>;
+// profiling-only ablations (never selected unless HSFFT_PREFER_CT names them)
+using P4096x = HsPlan<4096, 256, 1, 4, 0, 0, 16, 16, 16>;
+using P3000x = HsPlan<3000, 200, 1, 3, -1, 0, 3, 5, 5, 5, 8>;
+using P4096y = HsPlan<4096, 256, 1, 4, -2, 0, 16, 16, 16>;
+using P3000y = HsPlan<3000, 200, 1, 3, 0, 0, 3, 5, 5, 5, 8>;       // one stage per pass, load-all twiddles (round-1 first contact)
+using P3000z = HsPlan<3000, 200, 1, 3, -1, 2111, 3, 5, 5, 5, 8>;  // passes {3,5} {5} {5} {8}
 
 template <class P>
 static void fill_desc(hs_ct_desc &d, int id, int family)
@@ -34,12 +40,12 @@ static void fill_desc(hs_ct_desc &d, int id, int family)
     d.n = P::N;
     d.nst = P::NST;
     for (int s = 0; s < 8; ++s) d.radix[s] = s < P::NST ? P::radix(s) : 0;
-    d.nlogical = 0;
+    d.split_min = P::SPLIT;
     d.threads = P::threads;
     d.smem_bytes = P::smem_bytes;
 }
 
-enum { CT_4096A = 0, CT_4096B, CT_3000, CT_1024, CT_2048, CT_512, CT_256, CT_8192, CT_B2048, CT_COUNT };
+enum { CT_4096A = 0, CT_4096B, CT_3000, CT_1024, CT_2048, CT_512, CT_256, CT_8192, CT_B2048, CT_4096X, CT_3000X, CT_4096Y, CT_3000Y, CT_3000Z, CT_COUNT };
 static hs_ct_desc g_ct[CT_COUNT];
 static int g_ct_order[CT_COUNT];
 static bool g_ct_ready = false;
@@ -56,6 +62,11 @@ static void ct_init()
     fill_desc<P256>(g_ct[CT_256], CT_256, HS_CT_C2C);
     fill_desc<P8192>(g_ct[CT_8192], CT_8192, HS_CT_C2C);
     fill_desc<PB2048f>(g_ct[CT_B2048], CT_B2048, HS_CT_BLUESTEIN);
+    fill_desc<P4096x>(g_ct[CT_4096X], CT_4096X, HS_CT_C2C);
+    fill_desc<P3000x>(g_ct[CT_3000X], CT_3000X, HS_CT_C2C);
+    fill_desc<P4096y>(g_ct[CT_4096Y], CT_4096Y, HS_CT_C2C);
+    fill_desc<P3000y>(g_ct[CT_3000Y], CT_3000Y, HS_CT_C2C);
+    fill_desc<P3000z>(g_ct[CT_3000Z], CT_3000Z, HS_CT_C2C);
     for (int i = 0; i < CT_COUNT; ++i) g_ct_order[i] = i;
     // HSFFT_PREFER_CT=<id>: list that instance first (A/B runs of alternative plans for one N)
     if (const char *e = getenv("HSFFT_PREFER_CT")) {
@@ -91,12 +102,17 @@ extern "C" void hs_cu_launch_ct_c2c(int id, int sgn, const void *d_in, void *d_o
     switch (id) {
     case CT_4096A: launch_c2c_sgn<P4096a, 2>(sgn, d_in, d_out, d_tw, howmany, st); break;
     case CT_4096B: launch_c2c_sgn<P4096b, 2>(sgn, d_in, d_out, d_tw, howmany, st); break;
-    case CT_3000: launch_c2c_sgn<P3000, 3>(sgn, d_in, d_out, d_tw, howmany, st); break;
+    case CT_3000: launch_c2c_sgn<P3000, 2>(sgn, d_in, d_out, d_tw, howmany, st); break;
     case CT_1024: launch_c2c_sgn<P1024, 2>(sgn, d_in, d_out, d_tw, howmany, st); break;
     case CT_2048: launch_c2c_sgn<P2048, 2>(sgn, d_in, d_out, d_tw, howmany, st); break;
     case CT_512: launch_c2c_sgn<P512, 3>(sgn, d_in, d_out, d_tw, howmany, st); break;
     case CT_256: launch_c2c_sgn<P256, 3>(sgn, d_in, d_out, d_tw, howmany, st); break;
     case CT_8192: launch_c2c_sgn<P8192, 1>(sgn, d_in, d_out, d_tw, howmany, st); break;
+    case CT_4096X: launch_c2c_sgn<P4096x, 2>(sgn, d_in, d_out, d_tw, howmany, st); break;
+    case CT_3000X: launch_c2c_sgn<P3000x, 2>(sgn, d_in, d_out, d_tw, howmany, st); break;
+    case CT_4096Y: launch_c2c_sgn<P4096y, 2>(sgn, d_in, d_out, d_tw, howmany, st); break;
+    case CT_3000Y: launch_c2c_sgn<P3000y, 3>(sgn, d_in, d_out, d_tw, howmany, st); break;
+    case CT_3000Z: launch_c2c_sgn<P3000z, 3>(sgn, d_in, d_out, d_tw, howmany, st); break;
     default: fprintf(stderr, "Error: unknown compile-time kernel id %d\n", id); exit(EXIT_FAILURE);
     }
 }

@@ -123,6 +123,18 @@ static void check_grid(long long blocks)
     }
 }
 
+// Ask for just enough shared memory for the intended CTAs per SM, so that the rest of the 228 KB
+// stays L1 and keeps the twiddle / chirp tables close (HSFFT_CARVEOUT=0 leaves the driver default).
+static void set_carveout(const void *kern, int smem_per_cta, int ctas_per_sm)
+{
+    static int mode = -1;
+    if (mode < 0) { const char *e = getenv("HSFFT_CARVEOUT"); mode = e ? atoi(e) : 1; }
+    if (!mode) return;
+    int pct = (int)(((long long)(smem_per_cta + 1024) * ctas_per_sm * 100 + 228 * 1024 - 1) / (228 * 1024));
+    if (pct > 100) pct = 100;
+    HS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+}
+
 template <class P, int SGN, int MINB>
 static void launch_c2c(const void *in, void *out, const void *tw, long long howmany, cudaStream_t st)
 {
@@ -130,6 +142,7 @@ static void launch_c2c(const void *in, void *out, const void *tw, long long howm
     static bool attr_done = false; // per instantiation
     if (!attr_done) {
         HS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P::smem_bytes));
+        set_carveout((const void *)kern, P::smem_bytes, MINB);
         attr_done = true;
     }
     const long long blocks = (howmany + P::X - 1) / P::X;
@@ -147,6 +160,7 @@ static void launch_blu(int N, const void *in, void *out, const void *twf, const 
     static bool attr_done = false;
     if (!attr_done) {
         HS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PF::smem_bytes));
+        set_carveout((const void *)kern, PF::smem_bytes, MINB);
         attr_done = true;
     }
     const long long blocks = (howmany + PF::X - 1) / PF::X;

@@ -50,8 +50,8 @@ typedef struct hs_dev_obj {
 } hs_dev_obj;
 
 /* plan tables built on the host with the reference's own expressions */
-void hs_build_stage_twiddles(fft_data *out, const int *radix_exec, int nst, int sgn); /* [i-1][k] per stage */
-int  hs_stage_twiddle_count(const int *radix_exec, int nst);
+void hs_build_stage_twiddles(fft_data *out, const int *radix_exec, int nst, int sgn, int split_min); /* [i-1][k] per stage */
+int  hs_stage_twiddle_count(const int *radix_exec, int nst, int split_min);
 void hs_build_chirp(fft_data *h, int N);                                              /* exp(+i pi n^2/N) */
 int  hs_bluestein_exec_pad(int N);                                                    /* 2^ceil(log2(2N-1)) */
 

@@ -22,6 +22,7 @@
 // Bank conflicts of the strided reads of the late stages are removed by padding one 16-byte slot
 // every 2^LOGPAD points (the plans below were checked with tests/emu/bank_check.py).
 #pragma once
+#include "hs_abi.h"
 #include "hs_butterflies.cuh"
 
 // ------------------------------------------------------------------ compile-time plan descriptor
@@ -39,27 +40,86 @@ struct HsRadixList<> {
 };
 
 // N_: transform length; T_: threads cooperating on one transform; X_: transforms per CTA;
-// LOGPAD_: one pad slot per 2^LOGPAD_ points (0 = none); RS...: stage radices in EXECUTION order
+// LOGPAD_: one pad slot per 2^LOGPAD_ points (0 = none); SPLIT_: how a stage gets its r-1 twiddles --
+//   0: load all r-1 rows of the [i-1][k] table;  -1: load rows 1,2,4,8 and form the others as products
+//   (-2: load row 1 only)
+//   (fewer 16-byte loads through the L1 data pipe, which is what limits these kernels, for a few FP64
+//   multiplies);  >0: split-table threshold in entries (hs_split_kl in hs_abi.h);
+// GROUPS_: how consecutive stages are fused into register-level passes, as decimal digits from the
+//   first pass to the last (221 = {s0,s1} {s2,s3} {s4}); 0 = every stage is its own pass.  A fused
+//   pass of radices (ra, rb) keeps ra*rb points per butterfly in registers and exchanges through
+//   shared memory once instead of twice; the twiddles, butterflies and their order are unchanged.
+// RS...: stage radices in EXECUTION order
 // (= the reference's factor list reversed, runs of power-of-two factors possibly regrouped).
-template <int N_, int T_, int X_, int LOGPAD_, int... RS>
+template <int N_, int T_, int X_, int LOGPAD_, int SPLIT_, int GROUPS_, int... RS>
 struct HsPlan {
     using radices = HsRadixList<RS...>;
-    static constexpr int N = N_, T = T_, X = X_, LOGPAD = LOGPAD_;
+    static constexpr int N = N_, T = T_, X = X_, LOGPAD = LOGPAD_, SPLIT = SPLIT_;
     static constexpr int NST = radices::count;
     static constexpr int radix(int s) { return radices::at(s); }
+    // pass structure
+    static constexpr int ndigits(int g) { return g == 0 ? 0 : 1 + ndigits(g / 10); }
+    static constexpr int pow10(int e) { return e == 0 ? 1 : 10 * pow10(e - 1); }
+    static constexpr int NPASS = GROUPS_ ? ndigits(GROUPS_) : NST;
+    static constexpr int pass_size(int p) { return GROUPS_ ? (GROUPS_ / pow10(NPASS - 1 - p)) % 10 : 1; }
+    static constexpr int pass_start(int p) { return p == 0 ? 0 : pass_start(p - 1) + pass_size(p - 1); }
     static constexpr int m_before(int s) { return s == 0 ? 1 : m_before(s - 1) * radix(s - 1); }
     // offset of stage s in the device twiddle table ([i-1][k] layout per stage), stage 0 has none
-    static constexpr int tw_off(int s) { return s <= 1 ? 0 : tw_off(s - 1) + (radix(s - 1) - 1) * m_before(s - 1); }
+    static constexpr int split_kl(int s) { return s == 0 ? 0 : hs_split_kl(radix(s), m_before(s), SPLIT_); }
+    static constexpr int tw_off(int s) { return s <= 1 ? 0 : tw_off(s - 1) + hs_stage_tw_entries(radix(s - 1), m_before(s - 1), SPLIT_); }
     static constexpr int tw_count = tw_off(NST);
     static constexpr int NPAD = LOGPAD_ ? N_ + (N_ >> LOGPAD_) + 1 : N_;
     static constexpr int pad(int p) { return LOGPAD_ ? p + (p >> LOGPAD_) : p; }
-    static constexpr int smem_bytes = NST > 1 ? NPAD * X_ * 16 : 0;
+    static constexpr int smem_bytes = NPASS > 1 ? NPAD * X_ * 16 : 0;
     static constexpr int threads = T_ * X_;
+    static constexpr int ABL = 0; // ablation bits for profiling builds (1: skip twiddle loads -- wrong results)
 };
+template <class Base, int A>
+struct HsAblate : Base { static constexpr int ABL = A; };
+
+// ---------------------------------------------------------------------------- stage twiddles
+// wv[1..R) <- W_{M R}^{i k}, i = 1..R-1, for flat stage S (radix R on sub-transforms of length M).
+template <class P, int S>
+HS_DEVICE void hs_twiddles(const cplx *HS_RESTRICT tw, const int k, cplx *wv)
+{
+    constexpr int R = P::radix(S);
+    constexpr int M = P::m_before(S);
+    constexpr int KL = P::split_kl(S);
+    if (KL == 0 && P::SPLIT < 0) {
+        // load only the rows i = 1, 2, 4, 8 (or just row 1) and build the others by products (<= 3
+        // deep): fewer 16-byte loads through the L1 data pipe, a few more FP64 multiplies
+        const cplx *w = tw + P::tw_off(S) + k;
+        if (P::SPLIT == -1) {
+            HS_UNROLL
+            for (int i = 1; i < R; i *= 2) wv[i] = hs_ld_tab(w + (i - 1) * M);
+        } else {
+            wv[1] = hs_ld_tab(w);
+            HS_UNROLL
+            for (int i = 2; i < R; i *= 2) wv[i] = hs_mul(wv[i / 2], wv[i / 2]);
+        }
+        HS_UNROLL
+        for (int i = 3; i < R; ++i)
+            if (i & (i - 1)) { // not a power of two: highest set bit times the rest
+                int hb = 1;
+                while (hb * 2 <= i) hb *= 2;
+                wv[i] = hs_mul(wv[hb], wv[i - hb]);
+            }
+    } else if (KL == 0) { // one table, [i-1][k]: load every row
+        const cplx *w = tw + P::tw_off(S) + k;
+        HS_UNROLL
+        for (int i = 1; i < R; ++i) wv[i] = (P::ABL & 1) ? hs_c(1.0, 1e-300 * i) : hs_ld_tab(w + (i - 1) * M);
+    } else { // split tables: W^(i k) = lo[i-1][k % KL] * hi[i-1][k / KL]
+        constexpr int KH = M / (KL ? KL : 1);
+        const cplx *wl = tw + P::tw_off(S) + k % (KL ? KL : 1);
+        const cplx *wh = tw + P::tw_off(S) + (R - 1) * KL + k / (KL ? KL : 1);
+        HS_UNROLL
+        for (int i = 1; i < R; ++i) wv[i] = hs_mul(hs_ld_tab(wl + (i - 1) * KL), hs_ld_tab(wh + (i - 1) * KH));
+    }
+}
 
 // ------------------------------------------------------------------------------- one stage
-// LD(u, i, n)       -> cplx   : element n of the input signal   (first stage only)
-// ST(u, j, k, v)              : element k of the output spectrum (last stage only)
+// LD(u, i, n)       -> cplx   : element n of the input signal   (first pass only)
+// ST(u, j, k, v)              : element k of the output spectrum (last pass only)
 // u (butterfly slot of this thread) and i/j are compile-time constants after unrolling, so
 // register-to-register hand-over between two transforms (fused Bluestein) stays in registers.
 template <class P, int SGN, int S, class LD, class ST>
@@ -73,6 +133,7 @@ HS_DEVICE void hs_stage(LD &ld, ST &st, cplx *sm, const cplx *HS_RESTRICT tw, co
     constexpr bool FIRST = (S == 0), LAST = (S == P::NST - 1);
     cplx v[B][R];
 
+    // phase 1: issue every load of this thread's butterflies back to back (memory-level parallelism)
     HS_UNROLL
     for (int u = 0; u < B; ++u) {
         const int b = t + P::T * u;
@@ -83,10 +144,18 @@ HS_DEVICE void hs_stage(LD &ld, ST &st, cplx *sm, const cplx *HS_RESTRICT tw, co
                 if (FIRST) v[u][i] = ld(u, i, b + NB * i);
                 else       v[u][i] = sm[P::pad(q + QP * i + (QP * R) * k)];
             }
+        }
+    }
+    // phase 2: twiddle (reference combine loops) and butterfly, in registers
+    HS_UNROLL
+    for (int u = 0; u < B; ++u) {
+        const int b = t + P::T * u;
+        if (active && (NB % P::T == 0 || b < NB)) {
             if (!FIRST) {
-                const cplx *w = tw + P::tw_off(S) + k;
+                cplx wv[R];
+                hs_twiddles<P, S>(tw, b / QP, wv);
                 HS_UNROLL
-                for (int i = 1; i < R; ++i) v[u][i] = hs_mul(v[u][i], hs_ld_tab(w + (i - 1) * M));
+                for (int i = 1; i < R; ++i) v[u][i] = hs_mul(v[u][i], wv[i]);
             }
             hs_bfly<R, SGN>(v[u]);
         }
@@ -106,11 +175,101 @@ HS_DEVICE void hs_stage(LD &ld, ST &st, cplx *sm, const cplx *HS_RESTRICT tw, co
     if (!LAST) HS_SYNC();
 }
 
-template <class P, int SGN, int S, class LD, class ST>
-HS_DEVICE void hs_stages_from(LD &ld, ST &st, cplx *sm, const cplx *tw, int t, bool active)
+// ------------------------------------------------------------- two consecutive stages, fused
+// Stages F (radix RA) and F+1 (radix RB) run back to back on RA*RB points held in registers:
+//   in  : A_m0[q' + QB (ib + RB ia)][k0]                      (element e = ib + RB ia)
+//   a   : y[ib][ja] = radix-RA over ia of ( W_{m0 RA}^{ia k0} * in )
+//   b   : out[jb][ja] = radix-RB over ib of ( W_{m0 RA RB}^{ib (k0 + m0 ja)} * y[ib][ja] )
+//   out : A_{m0 RA RB}[q'][k0 + m0 ja + m0 RA jb]              (element o = ja + RA jb)
+// i.e. exactly the reference's two combine loops, with the intermediate state never leaving the
+// thread.  To shared memory it looks like one stage of radix RA*RB (bank_check.py models it so).
+template <class P, int SGN, int F, class LD, class ST>
+HS_DEVICE void hs_stage2(LD &ld, ST &st, cplx *sm, const cplx *HS_RESTRICT tw, const int t, const bool active)
 {
-    hs_stage<P, SGN, S>(ld, st, sm, tw, t, active);
-    if constexpr (S + 1 < P::NST) hs_stages_from<P, SGN, S + 1>(ld, st, sm, tw, t, active);
+    constexpr int RA = P::radix(F), RB = P::radix(F + 1), RC = RA * RB;
+    constexpr int M0 = P::m_before(F);
+    constexpr int QB = P::N / (M0 * RC);
+    constexpr int NB = P::N / RC;
+    constexpr int B = (NB + P::T - 1) / P::T;
+    constexpr bool FIRST = (F == 0), LAST = (F + 2 == P::NST);
+    cplx v[B][RB][RA];
+
+    HS_UNROLL
+    for (int u = 0; u < B; ++u) {
+        const int b = t + P::T * u;
+        if (active && (NB % P::T == 0 || b < NB)) {
+            const int q = b % QB, k0 = b / QB;
+            HS_UNROLL
+            for (int ia = 0; ia < RA; ++ia) {
+                HS_UNROLL
+                for (int ib = 0; ib < RB; ++ib) {
+                    const int e = ib + RB * ia;
+                    if (FIRST) v[u][ib][ia] = ld(u, e, b + NB * e);
+                    else       v[u][ib][ia] = sm[P::pad(q + QB * e + (QB * RC) * k0)];
+                }
+            }
+        }
+    }
+    HS_UNROLL
+    for (int u = 0; u < B; ++u) {
+        const int b = t + P::T * u;
+        if (active && (NB % P::T == 0 || b < NB)) {
+            const int k0 = b / QB;
+            if (!FIRST) {
+                cplx wa[RA];
+                hs_twiddles<P, F>(tw, k0, wa);
+                HS_UNROLL
+                for (int ib = 0; ib < RB; ++ib) {
+                    HS_UNROLL
+                    for (int ia = 1; ia < RA; ++ia) v[u][ib][ia] = hs_mul(v[u][ib][ia], wa[ia]);
+                }
+            }
+            HS_UNROLL
+            for (int ib = 0; ib < RB; ++ib) hs_bfly<RA, SGN>(v[u][ib]);
+            HS_UNROLL
+            for (int ja = 0; ja < RA; ++ja) {
+                cplx tt[RB];
+                HS_UNROLL
+                for (int ib = 0; ib < RB; ++ib) tt[ib] = v[u][ib][ja];
+                if (!(FIRST && ja == 0)) { // k1 = 0 in the first pass: W^0 = 1, as in the reference's k = 0 column
+                    cplx wb[RB];
+                    hs_twiddles<P, F + 1>(tw, k0 + M0 * ja, wb);
+                    HS_UNROLL
+                    for (int ib = 1; ib < RB; ++ib) tt[ib] = hs_mul(tt[ib], wb[ib]);
+                }
+                hs_bfly<RB, SGN>(tt);
+                HS_UNROLL
+                for (int jb = 0; jb < RB; ++jb) v[u][jb][ja] = tt[jb];
+            }
+        }
+    }
+    if (!FIRST && !LAST) HS_SYNC();
+    HS_UNROLL
+    for (int u = 0; u < B; ++u) {
+        const int b = t + P::T * u;
+        if (active && (NB % P::T == 0 || b < NB)) {
+            HS_UNROLL
+            for (int jb = 0; jb < RB; ++jb) {
+                HS_UNROLL
+                for (int ja = 0; ja < RA; ++ja) {
+                    const int o = ja + RA * jb;
+                    if (LAST) st(u, o, b + NB * o, v[u][jb][ja]);
+                    else      sm[P::pad(b + NB * o)] = v[u][jb][ja];
+                }
+            }
+        }
+    }
+    if (!LAST) HS_SYNC();
+}
+
+template <class P, int SGN, int PASS, class LD, class ST>
+HS_DEVICE void hs_passes_from(LD &ld, ST &st, cplx *sm, const cplx *tw, int t, bool active)
+{
+    constexpr int F = P::pass_start(PASS);
+    static_assert(P::pass_size(PASS) == 1 || P::pass_size(PASS) == 2, "a pass fuses one or two stages");
+    if constexpr (P::pass_size(PASS) == 2) hs_stage2<P, SGN, F>(ld, st, sm, tw, t, active);
+    else hs_stage<P, SGN, F>(ld, st, sm, tw, t, active);
+    if constexpr (PASS + 1 < P::NPASS) hs_passes_from<P, SGN, PASS + 1>(ld, st, sm, tw, t, active);
 }
 
 // Whole transform for one thread team.  sm: this team's NPAD-point buffer; tw: the plan's device
@@ -119,7 +278,8 @@ HS_DEVICE void hs_stages_from(LD &ld, ST &st, cplx *sm, const cplx *tw, int t, b
 template <class P, int SGN, class LD, class ST>
 HS_DEVICE void hs_fft_team(LD &ld, ST &st, cplx *sm, const cplx *tw, int t, bool active)
 {
-    hs_stages_from<P, SGN, 0>(ld, st, sm, tw, t, active);
+    static_assert(P::pass_start(P::NPASS - 1) + P::pass_size(P::NPASS - 1) == P::NST, "GROUPS must cover every stage");
+    hs_passes_from<P, SGN, 0>(ld, st, sm, tw, t, active);
 }
 
 // ------------------------------------------------------------------------- plain c2c kernel

@@ -115,32 +115,47 @@ void longvectorN(fft_data *sig, int N, int *array, int M)
 
 /* -------------------------------------------------------------------- device-side table builders */
 
-int hs_stage_twiddle_count(const int *rx, int nst)
+int hs_stage_twiddle_count(const int *rx, int nst, int split_min)
 {
     int m = 1, cnt = 0;
     for (int s = 0; s < nst; ++s) {
-        if (s > 0) cnt += (rx[s] - 1) * m;
+        if (s > 0) cnt += hs_stage_tw_entries(rx[s], m, split_min);
         m *= rx[s];
     }
     return cnt;
 }
 
-void hs_build_stage_twiddles(fft_data *out, const int *rx, int nst, int sgn)
+static void put_twiddle(fft_data *dst, int exponent, fft_type theta, int sgn)
+{
+    const fft_type angle = exponent * theta; /* same expression as longvectorN: (int product) * theta */
+    dst->re = cos(angle);
+    dst->im = (sgn == -1) ? -sin(angle) : sin(angle);
+}
+
+void hs_build_stage_twiddles(fft_data *out, const int *rx, int nst, int sgn, int split_min)
 {
     /* Same values as longvectorN (same expression, so bit-identical where the stage lengths
-     * coincide), laid out [i-1][k] per stage so that a warp's loads of one twiddle row coalesce. */
+     * coincide), laid out [i-1][k] per stage so that a warp's loads of one twiddle row coalesce.
+     * Stages whose table would exceed split_min entries are stored split (hs_split_kl, hs_abi.h):
+     * lo[i-1][k_lo] = W_L^(i k_lo) followed by hi[i-1][k_hi] = W_L^(i KL k_hi). */
     int m = 1, off = 0;
     for (int s = 0; s < nst; ++s) {
         const int r = rx[s];
         if (s > 0) {
             const fft_type theta = -PI2 / ((fft_type)m * r);
-            for (int i = 1; i < r; ++i)
-                for (int k = 0; k < m; ++k) {
-                    const fft_type angle = i * k * theta;
-                    out[off + (i - 1) * m + k].re = cos(angle);
-                    out[off + (i - 1) * m + k].im = (sgn == -1) ? -sin(angle) : sin(angle);
+            const int KL = hs_split_kl(r, m, split_min);
+            if (KL == 0) {
+                for (int i = 1; i < r; ++i)
+                    for (int k = 0; k < m; ++k) put_twiddle(&out[off + (i - 1) * m + k], i * k, theta, sgn);
+            } else {
+                const int KH = m / KL;
+                fft_data *lo = out + off, *hi = out + off + (r - 1) * KL;
+                for (int i = 1; i < r; ++i) {
+                    for (int k = 0; k < KL; ++k) put_twiddle(&lo[(i - 1) * KL + k], i * k, theta, sgn);
+                    for (int k = 0; k < KH; ++k) put_twiddle(&hi[(i - 1) * KH + k], i * KL * k, theta, sgn);
                 }
-            off += (r - 1) * m;
+            }
+            off += hs_stage_tw_entries(r, m, split_min);
         }
         m *= r;
     }
@@ -191,12 +206,12 @@ static void *upload(const void *h, size_t bytes)
     return d;
 }
 
-static void *upload_stage_twiddles(const int *rx, int nst, int sgn)
+static void *upload_stage_twiddles(const int *rx, int nst, int sgn, int split_min)
 {
-    const int cnt = hs_stage_twiddle_count(rx, nst);
+    const int cnt = hs_stage_twiddle_count(rx, nst, split_min);
     fft_data *t = (fft_data *)malloc(sizeof(fft_data) * (cnt > 0 ? cnt : 1));
     if (!t) { fprintf(stderr, "Error: Memory allocation failed for twiddle table\n"); exit(EXIT_FAILURE); }
-    hs_build_stage_twiddles(t, rx, nst, sgn);
+    hs_build_stage_twiddles(t, rx, nst, sgn, split_min);
     void *d = upload(t, sizeof(fft_data) * cnt);
     hs_cu_stream_sync(NULL);
     free(t);
@@ -213,7 +228,7 @@ hs_c2c *hs_c2c_create(int n, int sgn)
     const hs_ct_desc *ct = find_ct(HS_CT_C2C, n);
     if (ct) {
         p->ct_id = ct->id;
-        p->d_tw = upload_stage_twiddles(ct->radix, ct->nst, sgn);
+        p->d_tw = upload_stage_twiddles(ct->radix, ct->nst, sgn, ct->split_min);
         return p;
     }
     /* run-time plan: the reference's factor list reversed = execution order */
@@ -287,7 +302,7 @@ hs_c2c *hs_c2c_create(int n, int sgn)
             if (s > 0) off += (grx[s] - 1) * mm;
             mm *= grx[s];
         }
-        p->d_pass_tw[g] = upload_stage_twiddles(grx, gst, sgn);
+        p->d_pass_tw[g] = upload_stage_twiddles(grx, gst, sgn, 0);
         q->tw = p->d_pass_tw[g];
         q->gen_cs = (const double *)p->d_gen_cs;
         q->gen_sn = (const double *)p->d_gen_sn;
@@ -441,8 +456,8 @@ static void dev_build(hs_dev_obj *d, fft_object plan)
         int inv[8];
         for (int s = 0; s < ct->nst; ++s) inv[s] = ct->radix[ct->nst - 1 - s];
         d->blu_ct_id = ct->id;
-        d->d_blu_twf = upload_stage_twiddles(ct->radix, ct->nst, 1);
-        d->d_blu_twi = upload_stage_twiddles(inv, ct->nst, -1);
+        d->d_blu_twf = upload_stage_twiddles(ct->radix, ct->nst, 1, ct->split_min);
+        d->d_blu_twi = upload_stage_twiddles(inv, ct->nst, -1, ct->split_min);
         hs_c2c_destroy(f);
     } else {
         d->fwdM = f;
