@@ -44,7 +44,7 @@ HS_RULE int hs_stage_tw_entries(int r, int m, int split_min)
 }
 
 /* compile-time kernel families */
-enum { HS_CT_C2C = 0, HS_CT_BLUESTEIN = 1, HS_CT_COLS = 2, HS_CT_ROWS = 3 };
+enum { HS_CT_C2C = 0, HS_CT_BLUESTEIN = 1, HS_CT_TWOPASS = 2 };
 
 /* one compile-time specialised shared-memory transform the CUDA side offers */
 typedef struct hs_ct_desc {
@@ -55,6 +55,9 @@ typedef struct hs_ct_desc {
     int radix[8];   /* execution order (leaf first) */
     int split_min;  /* twiddle-table split threshold of this plan (0 = never split), see hs_split_kl */
     int threads, smem_bytes;
+    /* HS_CT_TWOPASS: n = n1 * n2; radix[]/nst/split_min describe the pass-1 sub-plan of length n1
+     * (columns of stride n2), the fields below the pass-2 sub-plan of length n2 (columns of stride n1) */
+    int n1, n2, nst2, radix2[8], split_min2;
 } hs_ct_desc;
 
 /* parameters of one run-time planned pass (see hs_generic.cuh) */
@@ -103,6 +106,10 @@ int   hs_cu_ct_count(void);
 const hs_ct_desc *hs_cu_ct_get(int idx);
 /* batched contiguous c2c, transform b at in + b*n */
 void  hs_cu_launch_ct_c2c(int id, int sgn, const void *d_in, void *d_out, const void *d_tw, long long howmany, void *stream);
+/* one pass (1 or 2) of a two-pass transform; d_tw: that pass's sub-plan twiddles; d_twb/d_tws: the
+ * inter-pass twiddle tables (pass 2 only) */
+void  hs_cu_launch_ct_twopass(int id, int pass, int sgn, const void *d_in, void *d_out, const void *d_tw, const void *d_twb,
+                              const void *d_tws, long long howmany, void *stream);
 /* fused Bluestein: d_tw_f / d_tw_i are the forward-order / inverse-order stage tables of length M */
 void  hs_cu_launch_ct_bluestein(int id, int sgn, int N, const void *d_in, void *d_out, const void *d_tw_f, const void *d_tw_i,
                                 const void *d_chirp, const void *d_hk, long long howmany, void *stream);

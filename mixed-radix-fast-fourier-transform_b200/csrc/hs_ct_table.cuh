@@ -8,6 +8,7 @@
 #include "hs_abi.h"
 #include "hs_fused.cuh"
 #include "hs_smem_fft.cuh"
+#include "hs_tiled.cuh"
 
 // ------------------------------------------------------------------------ compile-time plan table
 // Stage radices in execution order (the reference's factor list reversed; runs of power-of-two
@@ -25,6 +26,11 @@ using P8192  = HsPlan<8192, 512, 1, 4, -1, 0, 8, 8, 8, 16>;
 // fused Bluestein, M = 2048 (N = 513..1024, e.g. the N = 1009 config): forward / inverse pair
 using PB2048f = HsPlan<2048, 128, 2, 4, -1, 0, 8, 16, 16>;
 using PB2048i = HsPlan<2048, 128, 2, 4, -1, 0, 16, 16, 8>;
+// sub-plans of the two-pass transforms (N = n1 * n2 > 8192); X is unused there
+using S128  = HsPlan<128, 8, 1, 4, -1, 0, 8, 16>;
+using S256  = HsPlan<256, 16, 1, 4, -1, 0, 16, 16>;
+using S512  = HsPlan<512, 64, 1, 3, -1, 0, 8, 8, 8>;
+using S1024 = HsPlan<1024, 64, 1, 3, -1, 0, 16, 8, 8>;
 // profiling-only ablations (never selected unless HSFFT_PREFER_CT names them)
 using P4096x = HsPlan<4096, 256, 1, 4, 0, 0, 16, 16, 16>;
 using P3000x = HsPlan<3000, 200, 1, 3, -1, 0, 3, 5, 5, 5, 8>;
@@ -45,7 +51,20 @@ static void fill_desc(hs_ct_desc &d, int id, int family)
     d.smem_bytes = P::smem_bytes;
 }
 
-enum { CT_4096A = 0, CT_4096B, CT_3000, CT_1024, CT_2048, CT_512, CT_256, CT_8192, CT_B2048, CT_4096X, CT_3000X, CT_4096Y, CT_3000Y, CT_3000Z, CT_COUNT };
+template <class P1, class P2>
+static void fill_desc2(hs_ct_desc &d, int id)
+{
+    fill_desc<P1>(d, id, HS_CT_TWOPASS);
+    d.n = P1::N * P2::N;
+    d.n1 = P1::N;
+    d.n2 = P2::N;
+    d.nst2 = P2::NST;
+    for (int s = 0; s < 8; ++s) d.radix2[s] = s < P2::NST ? P2::radix(s) : 0;
+    d.split_min2 = P2::SPLIT;
+}
+
+enum { CT_4096A = 0, CT_4096B, CT_3000, CT_1024, CT_2048, CT_512, CT_256, CT_8192, CT_B2048, CT_4096X, CT_3000X, CT_4096Y, CT_3000Y, CT_3000Z,
+       CT_T14, CT_T15, CT_T16, CT_T17, CT_T18, CT_T19, CT_T20, CT_COUNT };
 static hs_ct_desc g_ct[CT_COUNT];
 static int g_ct_order[CT_COUNT];
 static bool g_ct_ready = false;
@@ -67,6 +86,13 @@ static void ct_init()
     fill_desc<P4096y>(g_ct[CT_4096Y], CT_4096Y, HS_CT_C2C);
     fill_desc<P3000y>(g_ct[CT_3000Y], CT_3000Y, HS_CT_C2C);
     fill_desc<P3000z>(g_ct[CT_3000Z], CT_3000Z, HS_CT_C2C);
+    fill_desc2<S128, S128>(g_ct[CT_T14], CT_T14);
+    fill_desc2<S128, S256>(g_ct[CT_T15], CT_T15);
+    fill_desc2<S256, S256>(g_ct[CT_T16], CT_T16);
+    fill_desc2<S256, S512>(g_ct[CT_T17], CT_T17);
+    fill_desc2<S512, S512>(g_ct[CT_T18], CT_T18);
+    fill_desc2<S512, S1024>(g_ct[CT_T19], CT_T19);
+    fill_desc2<S1024, S1024>(g_ct[CT_T20], CT_T20);
     for (int i = 0; i < CT_COUNT; ++i) g_ct_order[i] = i;
     // HSFFT_PREFER_CT=<id>: list that instance first (A/B runs of alternative plans for one N)
     if (const char *e = getenv("HSFFT_PREFER_CT")) {
@@ -130,3 +156,40 @@ extern "C" void hs_cu_launch_ct_bluestein(int id, int sgn, int N, const void *d_
     }
 }
 
+
+// ---- two-pass transforms: C columns per CTA, chosen so that a CTA has 128..512 threads
+template <class P> struct HsTileCols { static constexpr int C = P::T >= 64 ? 8 : 16; };
+
+template <class P1, class P2>
+static void launch_twopass(int pass, int sgn, const void *in, void *out, const void *tw, const void *twb, const void *tws,
+                           long long howmany, hs_stream_t st)
+{
+    constexpr int N = P1::N * P2::N;
+    HsTileGeom g;
+    g.in_xf = g.out_xf = N;
+    if (pass == 1) {
+        g.ncols = P2::N; g.in_c = 1; g.in_e = P2::N; g.out_c = P1::N; g.out_e = 1; g.twb = nullptr; g.tws = nullptr;
+        if (sgn == 1) launch_tiled<P1, 1, HsTileCols<P1>::C, false, false>(in, out, tw, g, howmany, st);
+        else launch_tiled<P1, -1, HsTileCols<P1>::C, false, false>(in, out, tw, g, howmany, st);
+    } else {
+        g.ncols = P1::N; g.in_c = 1; g.in_e = P1::N; g.out_c = 1; g.out_e = P1::N; g.twb = (const cplx *)twb; g.tws = (const cplx *)tws;
+        if (sgn == 1) launch_tiled<P2, 1, HsTileCols<P2>::C, true, true>(in, out, tw, g, howmany, st);
+        else launch_tiled<P2, -1, HsTileCols<P2>::C, true, true>(in, out, tw, g, howmany, st);
+    }
+}
+
+extern "C" void hs_cu_launch_ct_twopass(int id, int pass, int sgn, const void *d_in, void *d_out, const void *d_tw, const void *d_twb,
+                                        const void *d_tws, long long howmany, void *stream)
+{
+    hs_stream_t st = (hs_stream_t)stream;
+    switch (id) {
+    case CT_T14: launch_twopass<S128, S128>(pass, sgn, d_in, d_out, d_tw, d_twb, d_tws, howmany, st); break;
+    case CT_T15: launch_twopass<S128, S256>(pass, sgn, d_in, d_out, d_tw, d_twb, d_tws, howmany, st); break;
+    case CT_T16: launch_twopass<S256, S256>(pass, sgn, d_in, d_out, d_tw, d_twb, d_tws, howmany, st); break;
+    case CT_T17: launch_twopass<S256, S512>(pass, sgn, d_in, d_out, d_tw, d_twb, d_tws, howmany, st); break;
+    case CT_T18: launch_twopass<S512, S512>(pass, sgn, d_in, d_out, d_tw, d_twb, d_tws, howmany, st); break;
+    case CT_T19: launch_twopass<S512, S1024>(pass, sgn, d_in, d_out, d_tw, d_twb, d_tws, howmany, st); break;
+    case CT_T20: launch_twopass<S1024, S1024>(pass, sgn, d_in, d_out, d_tw, d_twb, d_tws, howmany, st); break;
+    default: fprintf(stderr, "Error: unknown two-pass kernel id %d\n", id); exit(EXIT_FAILURE);
+    }
+}

@@ -8,6 +8,7 @@
 #include "hs_fused.cuh"
 #include "hs_generic.cuh"
 #include "hs_smem_fft.cuh"
+#include "hs_tiled.cuh"
 
 #define HS_CUDA_CHECK(expr)                                                                            \
     do {                                                                                               \
@@ -167,6 +168,24 @@ static void launch_blu(int N, const void *in, void *out, const void *twf, const 
     check_grid(blocks);
     kern<<<(unsigned)blocks, PF::threads, PF::smem_bytes, st>>>((const cplx *)in, (cplx *)out, (const cplx *)twf, (const cplx *)twi,
                                                                  (const cplx *)chirp, (const cplx *)hk, N, howmany);
+    HS_CUDA_CHECK(cudaGetLastError());
+    ++g_launches;
+}
+
+template <class P, int SGN, int C, bool TW, bool STCOL>
+static void launch_tiled(const void *in, void *out, const void *tw, const HsTileGeom &g, long long howmany, cudaStream_t st)
+{
+    constexpr int MINB = (P::T * C <= 256) ? 2 : 1;
+    constexpr int smem = C * (P::NPAD | 1) * (int)sizeof(cplx);
+    auto kern = hs_tiled_kernel<P, SGN, C, TW, STCOL, MINB>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        HS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_done = true;
+    }
+    const long long blocks = howmany * (g.ncols / C);
+    check_grid(blocks);
+    kern<<<(unsigned)blocks, P::T * C, smem, st>>>((const cplx *)in, (cplx *)out, (const cplx *)tw, g, howmany);
     HS_CUDA_CHECK(cudaGetLastError());
     ++g_launches;
 }

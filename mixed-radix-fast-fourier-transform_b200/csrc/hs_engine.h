@@ -26,6 +26,8 @@ typedef struct hs_c2c {
     int n, sgn;
     int ct_id;          /* >= 0: one compile-time kernel does the whole transform */
     void *d_tw;         /* its stage twiddles in HBM */
+    int tp_id;          /* >= 0: compile-time two-pass transform (n = n1 * n2) */
+    void *d_tw2, *d_twb, *d_tws; /* pass-2 stage twiddles and the inter-pass tables W_n^{k b}, W_n^{k NB} */
     int npass;          /* otherwise: run-time planned passes */
     hs_gen_params pass[HS_MAX_PASS];
     void *d_pass_tw[HS_MAX_PASS], *d_pass_lo[HS_MAX_PASS], *d_pass_hi[HS_MAX_PASS];

@@ -17,6 +17,7 @@
 
 template <int SGN>
 struct HsLoadChirp {
+    static constexpr bool kPost = false;
     const cplx *HS_RESTRICT x;
     const cplx *HS_RESTRICT h;
     int N;
@@ -52,6 +53,7 @@ struct HsStoreRegsMul {
 };
 template <int RL>
 struct HsLoadRegs {
+    static constexpr bool kPost = false;
     cplx (*y)[RL];
     HS_DEVICE cplx operator()(int u, int i, int) const { return y[u][i]; }
 };

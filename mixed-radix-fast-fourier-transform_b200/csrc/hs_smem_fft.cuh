@@ -77,6 +77,17 @@ struct HsPlan {
 template <class Base, int A>
 struct HsAblate : Base { static constexpr int ABL = A; };
 
+// Where a thread sits in its team for one pass: team buffer, index inside the team, and whether the
+// team has work (padding teams of the last CTA still take part in the barriers).  Tiled kernels use
+// one mapping for the first pass (teams across lanes: coalesced strided loads) and another for the
+// rest (threads of a team across lanes: coalesced contiguous stores); the shared-memory exchange
+// between passes makes the switch free.
+struct HsLane {
+    cplx *sm;
+    int t;
+    bool active;
+};
+
 // ---------------------------------------------------------------------------- stage twiddles
 // wv[1..R) <- W_{M R}^{i k}, i = 1..R-1, for flat stage S (radix R on sub-transforms of length M).
 template <class P, int S>
@@ -123,8 +134,11 @@ HS_DEVICE void hs_twiddles(const cplx *HS_RESTRICT tw, const int k, cplx *wv)
 // u (butterfly slot of this thread) and i/j are compile-time constants after unrolling, so
 // register-to-register hand-over between two transforms (fused Bluestein) stays in registers.
 template <class P, int SGN, int S, class LD, class ST>
-HS_DEVICE void hs_stage(LD &ld, ST &st, cplx *sm, const cplx *HS_RESTRICT tw, const int t, const bool active)
+HS_DEVICE void hs_stage(LD &ld, ST &st, const HsLane &ln, const cplx *HS_RESTRICT tw)
 {
+    cplx *const sm = ln.sm;
+    const int t = ln.t;
+    const bool active = ln.active;
     constexpr int R = P::radix(S);
     constexpr int M = P::m_before(S);   // sub-transform length already done
     constexpr int QP = P::N / (M * R);  // q' range after this stage
@@ -156,6 +170,8 @@ HS_DEVICE void hs_stage(LD &ld, ST &st, cplx *sm, const cplx *HS_RESTRICT tw, co
                 hs_twiddles<P, S>(tw, b / QP, wv);
                 HS_UNROLL
                 for (int i = 1; i < R; ++i) v[u][i] = hs_mul(v[u][i], wv[i]);
+            } else if constexpr (LD::kPost) {
+                ld.template post<R>(b, v[u]); // inter-pass twiddle of a multi-pass transform
             }
             hs_bfly<R, SGN>(v[u]);
         }
@@ -184,8 +200,12 @@ HS_DEVICE void hs_stage(LD &ld, ST &st, cplx *sm, const cplx *HS_RESTRICT tw, co
 // i.e. exactly the reference's two combine loops, with the intermediate state never leaving the
 // thread.  To shared memory it looks like one stage of radix RA*RB (bank_check.py models it so).
 template <class P, int SGN, int F, class LD, class ST>
-HS_DEVICE void hs_stage2(LD &ld, ST &st, cplx *sm, const cplx *HS_RESTRICT tw, const int t, const bool active)
+HS_DEVICE void hs_stage2(LD &ld, ST &st, const HsLane &ln, const cplx *HS_RESTRICT tw)
 {
+    static_assert(!(F == 0 && LD::kPost), "a loader with an inter-pass twiddle hook needs an unfused first pass");
+    cplx *const sm = ln.sm;
+    const int t = ln.t;
+    const bool active = ln.active;
     constexpr int RA = P::radix(F), RB = P::radix(F + 1), RC = RA * RB;
     constexpr int M0 = P::m_before(F);
     constexpr int QB = P::N / (M0 * RC);
@@ -263,13 +283,14 @@ HS_DEVICE void hs_stage2(LD &ld, ST &st, cplx *sm, const cplx *HS_RESTRICT tw, c
 }
 
 template <class P, int SGN, int PASS, class LD, class ST>
-HS_DEVICE void hs_passes_from(LD &ld, ST &st, cplx *sm, const cplx *tw, int t, bool active)
+HS_DEVICE void hs_passes_from(LD &ld, ST &st, const HsLane &first, const HsLane &rest, const cplx *tw)
 {
     constexpr int F = P::pass_start(PASS);
     static_assert(P::pass_size(PASS) == 1 || P::pass_size(PASS) == 2, "a pass fuses one or two stages");
-    if constexpr (P::pass_size(PASS) == 2) hs_stage2<P, SGN, F>(ld, st, sm, tw, t, active);
-    else hs_stage<P, SGN, F>(ld, st, sm, tw, t, active);
-    if constexpr (PASS + 1 < P::NPASS) hs_passes_from<P, SGN, PASS + 1>(ld, st, sm, tw, t, active);
+    const HsLane &ln = (PASS == 0) ? first : rest;
+    if constexpr (P::pass_size(PASS) == 2) hs_stage2<P, SGN, F>(ld, st, ln, tw);
+    else hs_stage<P, SGN, F>(ld, st, ln, tw);
+    if constexpr (PASS + 1 < P::NPASS) hs_passes_from<P, SGN, PASS + 1>(ld, st, first, rest, tw);
 }
 
 // Whole transform for one thread team.  sm: this team's NPAD-point buffer; tw: the plan's device
@@ -279,11 +300,21 @@ template <class P, int SGN, class LD, class ST>
 HS_DEVICE void hs_fft_team(LD &ld, ST &st, cplx *sm, const cplx *tw, int t, bool active)
 {
     static_assert(P::pass_start(P::NPASS - 1) + P::pass_size(P::NPASS - 1) == P::NST, "GROUPS must cover every stage");
-    hs_passes_from<P, SGN, 0>(ld, st, sm, tw, t, active);
+    const HsLane ln{sm, t, active};
+    hs_passes_from<P, SGN, 0>(ld, st, ln, ln, tw);
+}
+// Same, with a different thread-to-team mapping for the first pass than for the others.
+template <class P, int SGN, class LD, class ST>
+HS_DEVICE void hs_fft_team2(LD &ld, ST &st, const HsLane &first, const HsLane &rest, const cplx *tw)
+{
+    static_assert(P::pass_start(P::NPASS - 1) + P::pass_size(P::NPASS - 1) == P::NST, "GROUPS must cover every stage");
+    static_assert(P::NPASS >= 2, "switching the mapping needs a shared-memory exchange");
+    hs_passes_from<P, SGN, 0>(ld, st, first, rest, tw);
 }
 
 // ------------------------------------------------------------------------- plain c2c kernel
 struct HsLoadGlobal {
+    static constexpr bool kPost = false;
     const cplx *HS_RESTRICT base;
     HS_DEVICE cplx operator()(int, int, int n) const { return hs_ld_stream(base + n); }
 };

@@ -225,10 +225,31 @@ hs_c2c *hs_c2c_create(int n, int sgn)
     p->n = n;
     p->sgn = sgn;
     p->ct_id = -1;
+    p->tp_id = -1;
     const hs_ct_desc *ct = find_ct(HS_CT_C2C, n);
     if (ct) {
         p->ct_id = ct->id;
         p->d_tw = upload_stage_twiddles(ct->radix, ct->nst, sgn, ct->split_min);
+        return p;
+    }
+    ct = find_ct(HS_CT_TWOPASS, n);
+    if (ct) {
+        /* n = n1 * n2: pass 1 = n2 strided transforms of length n1, pass 2 = n1 of length n2 with the
+         * inter-pass twiddle W_n^{i k} applied on load as W_n^{k b} * (W_n^{k NB})^ii, i = b + NB ii */
+        p->tp_id = ct->id;
+        p->d_tw = upload_stage_twiddles(ct->radix, ct->nst, sgn, ct->split_min);
+        p->d_tw2 = upload_stage_twiddles(ct->radix2, ct->nst2, sgn, ct->split_min2);
+        const int NB = ct->n2 / ct->radix2[0], K = ct->n1;
+        fft_data *tb = (fft_data *)malloc(sizeof(fft_data) * (size_t)NB * K), *ts = (fft_data *)malloc(sizeof(fft_data) * K);
+        if (!tb || !ts) { fprintf(stderr, "Error: Memory allocation failed for twiddle table\n"); exit(EXIT_FAILURE); }
+        const fft_type theta = -PI2 / (fft_type)n;
+        for (int b = 0; b < NB; ++b)
+            for (int k = 0; k < K; ++k) put_twiddle(&tb[(size_t)b * K + k], k * b, theta, sgn);
+        for (int k = 0; k < K; ++k) put_twiddle(&ts[k], k * NB, theta, sgn);
+        p->d_twb = upload(tb, sizeof(fft_data) * (size_t)NB * K);
+        p->d_tws = upload(ts, sizeof(fft_data) * K);
+        hs_cu_stream_sync(NULL);
+        free(tb); free(ts);
         return p;
     }
     /* run-time plan: the reference's factor list reversed = execution order */
@@ -360,6 +381,7 @@ void hs_c2c_destroy(hs_c2c *p)
 {
     if (!p) return;
     hs_cu_free(p->d_tw);
+    hs_cu_free(p->d_tw2); hs_cu_free(p->d_twb); hs_cu_free(p->d_tws);
     for (int g = 0; g < HS_MAX_PASS; ++g) { hs_cu_free(p->d_pass_tw[g]); hs_cu_free(p->d_pass_lo[g]); hs_cu_free(p->d_pass_hi[g]); }
     hs_cu_free(p->d_gen_cs);
     hs_cu_free(p->d_gen_sn);
@@ -368,6 +390,7 @@ void hs_c2c_destroy(hs_c2c *p)
 
 size_t hs_c2c_ws_elems(const hs_c2c *p, long long howmany)
 {
+    if (p->tp_id >= 0) return (size_t)howmany * p->n;
     return (p->ct_id < 0 && p->npass > 1) ? (size_t)howmany * p->n : 0;
 }
 
@@ -375,6 +398,11 @@ void hs_c2c_exec(const hs_c2c *p, const void *d_in, void *d_out, void *d_ws, lon
 {
     if (howmany <= 0) return;
     if (p->ct_id >= 0) { hs_cu_launch_ct_c2c(p->ct_id, p->sgn, d_in, d_out, p->d_tw, howmany, stream); return; }
+    if (p->tp_id >= 0) {
+        hs_cu_launch_ct_twopass(p->tp_id, 1, p->sgn, d_in, d_ws, p->d_tw, NULL, NULL, howmany, stream);
+        hs_cu_launch_ct_twopass(p->tp_id, 2, p->sgn, d_ws, d_out, p->d_tw2, p->d_twb, p->d_tws, howmany, stream);
+        return;
+    }
     if (p->npass == 1) {
         hs_gen_params q = p->pass[0];
         q.n_c = howmany;
@@ -668,6 +696,7 @@ const char *hsfft_plan_describe(fft_object obj)
     if (d->lt == 0) {
         const hs_c2c *p = d->direct;
         if (p->ct_id >= 0) n = snprintf(buf, sizeof buf, "mixed-radix N=%d: compile-time smem kernel #%d", d->N, p->ct_id);
+        else if (p->tp_id >= 0) n = snprintf(buf, sizeof buf, "mixed-radix N=%d: compile-time two-pass kernels #%d", d->N, p->tp_id);
         else {
             n = snprintf(buf, sizeof buf, "mixed-radix N=%d: %d run-time pass(es):", d->N, p->npass);
             for (int g = 0; g < p->npass && n < (int)sizeof buf - 32; ++g)
@@ -677,7 +706,7 @@ const char *hsfft_plan_describe(fft_object obj)
         n = snprintf(buf, sizeof buf, "bluestein N=%d M=%d: fused compile-time kernel #%d", d->N, d->M, d->blu_ct_id);
     else
         n = snprintf(buf, sizeof buf, "bluestein N=%d M=%d: unfused (chirp, FFT_M x%d pass, mul, IFFT_M, chirp)", d->N, d->M,
-                     d->fwdM->ct_id >= 0 ? 1 : d->fwdM->npass);
+                     d->fwdM->ct_id >= 0 ? 1 : (d->fwdM->tp_id >= 0 ? 2 : d->fwdM->npass));
     (void)n;
     return buf;
 }

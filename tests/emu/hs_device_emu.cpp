@@ -17,6 +17,7 @@
 #include "hs_fused.cuh"
 #include "hs_generic.cuh"
 #include "hs_smem_fft.cuh"
+#include "hs_tiled.cuh"
 
 typedef void *hs_stream_t;
 static std::atomic<long long> g_launches{0};
@@ -37,6 +38,15 @@ static void launch_blu(int N, const void *in, void *out, const void *twf, const 
     const long long blocks = (howmany + PF::X - 1) / PF::X;
     hs_emu_launch(hs_bluestein_kernel<PF, PI, SGN, MINB>, blocks, PF::threads, PF::smem_bytes, (const cplx *)in, (cplx *)out,
                   (const cplx *)twf, (const cplx *)twi, (const cplx *)chirp, (const cplx *)hk, N, howmany);
+    ++g_launches;
+}
+
+template <class P, int SGN, int C, bool TW, bool STCOL>
+static void launch_tiled(const void *in, void *out, const void *tw, const HsTileGeom &g, long long howmany, hs_stream_t)
+{
+    constexpr int smem = C * (P::NPAD | 1) * (int)sizeof(cplx);
+    hs_emu_launch(hs_tiled_kernel<P, SGN, C, TW, STCOL, 1>, howmany * (g.ncols / C), P::T * C, smem, (const cplx *)in, (cplx *)out,
+                  (const cplx *)tw, g, howmany);
     ++g_launches;
 }
 

@@ -20,7 +20,7 @@ def per_transform_worst(y, r):
 
 # BASELINE.json config sizes + the reference's own self-test sizes (src/real.c:278,360) + edge sizes
 C2C_SIZES = [2, 3, 4, 5, 7, 8, 15, 16, 20, 64, 100, 128, 256, 512, 1000, 1024, 2048, 3000, 4096, 8192,
-             11, 13, 26, 143, 1001, 53 * 8, 17 * 29, 6561, 10000, 16384, 32768]
+             11, 13, 26, 143, 1001, 53 * 8, 17 * 29, 6561, 10000, 16384, 32768, 1 << 17, 1 << 19, 1 << 20, 3 << 14]
 BLUESTEIN_SIZES = [19, 59, 257, 513, 1009, 2018, 4099, 10007]
 
 
@@ -106,7 +106,7 @@ def test_linearity_and_parseval_full_batch(hs, product_lib):
         assert float(rt) < 1e-12 * math.log2(n)
 
 
-@pytest.mark.parametrize("n", [4, 8, 16, 32, 64, 2018, 4096, 8192, 1 << 15])
+@pytest.mark.parametrize("n", [4, 8, 16, 32, 64, 2018, 4096, 8192, 1 << 15, 1 << 20])
 def test_real_r2c_c2r(hs, product_lib, oracle, n):
     x = xorshift_uniform(3 * n, seed=n).reshape(3, n)
     with hs.RealPlan(n, 1) as f, hs.RealPlan(n, -1) as g:

@@ -27,33 +27,69 @@ def main():
         if a == "--steps":
             steps = int(args.pop(0))
         else:
-            n, b = a.split(":")
-            cases.append((int(n), int(b)))
+            f = a.split(":")
+            if len(f) == 2:
+                cases.append(("c2c", int(f[0]), int(f[1])))
+            else:
+                cases.append((f[0], int(f[1]), int(f[2])))
     try:
         peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
     except Exception:
         peak = 6650.0
     dev = torch.device("cuda", 0)
-    for n, batch in cases:
-        x = torch.rand((batch, n, 2), device=dev, dtype=torch.float64) * 2 - 1
-        y = torch.empty_like(x)
-        for sgn in (1,):
-            with hs.Plan(n, sgn) as p:
-                desc = p.describe()
-                for _ in range(3):
-                    p.exec_dev(x, y, batch)
-                torch.cuda.synchronize()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                for _ in range(steps):
-                    p.exec_dev(x, y, batch)
-                e1.record()
-                torch.cuda.synchronize()
-                ms = e0.elapsed_time(e1) / steps
-            gbs = 32.0 * n * batch / (ms * 1e-3) / 1e9
-            gfl = 5.0 * n * math.log2(n) * batch / (ms * 1e-3) / 1e9
-            print("N=%-7d batch=%-7d %8.3f ms  %8.1f GB/s  %5.1f%% of %.0f  %9.1f GFLOP/s  [%s]" %
-                  (n, batch, ms, gbs, 100 * gbs / peak, peak, gfl, desc), flush=True)
+    for kind, n, batch in cases:
+        if kind == "c2c":
+            x = torch.rand((batch, n, 2), device=dev, dtype=torch.float64) * 2 - 1
+            y = torch.empty_like(x)
+            p = hs.Plan(n, 1)
+            run = lambda: p.exec_dev(x, y, batch)
+            nbytes, flops = 32.0 * n * batch, 5.0 * n * math.log2(n) * batch
+        elif kind == "r2c":      # full mirrored spectrum, like the reference
+            x = torch.rand((batch, n), device=dev, dtype=torch.float64) * 2 - 1
+            y = torch.empty((batch, n, 2), device=dev, dtype=torch.float64)
+            p = hs.RealPlan(n, 1)
+            run = lambda: p.r2c_dev(x, y, n, 1, batch)
+            nbytes, flops = 24.0 * n * batch, 2.5 * n * math.log2(n) * batch
+        elif kind == "r2ch":     # half spectrum (bins 0..N/2)
+            x = torch.rand((batch, n), device=dev, dtype=torch.float64) * 2 - 1
+            y = torch.empty((batch, n // 2 + 1, 2), device=dev, dtype=torch.float64)
+            p = hs.RealPlan(n, 1)
+            run = lambda: p.r2c_dev(x, y, n // 2 + 1, 0, batch)
+            nbytes, flops = (8.0 * n + 16.0 * (n // 2 + 1)) * batch, 2.5 * n * math.log2(n) * batch
+        elif kind == "c2r":
+            x = torch.rand((batch, n // 2 + 1, 2), device=dev, dtype=torch.float64) * 2 - 1
+            y = torch.empty((batch, n), device=dev, dtype=torch.float64)
+            p = hs.RealPlan(n, -1)
+            run = lambda: p.c2r_dev(x, n // 2 + 1, y, batch)
+            nbytes, flops = (8.0 * n + 16.0 * (n // 2 + 1)) * batch, 2.5 * n * math.log2(n) * batch
+        elif kind == "conv":     # n-sample rows convolved pairwise, linear / full
+            import ctypes as C
+            x = torch.rand((batch, n), device=dev, dtype=torch.float64) * 2 - 1
+            x2 = torch.rand((batch, n), device=dev, dtype=torch.float64) * 2 - 1
+            y = torch.empty((batch, 2 * n), device=dev, dtype=torch.float64)
+            L = hs.load()
+            p = None
+            run = lambda: L.fft_convolve_batch_dev(b"full", b"linear", C.c_void_p(x.data_ptr()), n, C.c_void_p(x2.data_ptr()), n,
+                                                   C.c_void_p(y.data_ptr()), 2 * n, batch, None)
+            P = 2 * n
+            nbytes, flops = (16.0 * n + 8.0 * (2 * n - 1)) * batch, 3 * 2.5 * P * math.log2(P) * batch
+        desc = p.describe() if kind == "c2c" else kind
+        for _ in range(3):
+            run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        gfl = flops / (ms * 1e-3) / 1e9
+        print("%-4s N=%-8d batch=%-7d %8.3f ms  %8.1f GB/s  %5.1f%% of %.0f  %9.1f GFLOP/s  [%s]" %
+              (kind, n, batch, ms, gbs, 100 * gbs / peak, peak, gfl, desc), flush=True)
+        if p is not None:
+            p.close()
         del x, y
         torch.cuda.empty_cache()
 
