@@ -125,11 +125,21 @@ def cpu_reference_lib():
         return oracle_lib.Oracle(), "port"
 
 
+def host_cores():
+    """Cores this process may use (torchrun exports OMP_NUM_THREADS=1, so ask the affinity mask, not OpenMP)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def time_cpu(kind, n, transforms, repeats, nthreads=0, warm=1, mean=False):
     """Seconds per call of the CPU path on `transforms` transforms (best of `repeats`, or their mean), threads used."""
     import numpy as np
     import oracle_lib
     lib, tag = cpu_reference_lib()
+    if nthreads <= 0:
+        nthreads = host_cores()
     rng = np.random.default_rng(88172645463325252 % (2 ** 63))
     if kind == "c2c":
         x = rng.uniform(-1, 1, (transforms, 2 * n)).view(np.complex128)
@@ -154,7 +164,7 @@ def time_cpu(kind, n, transforms, repeats, nthreads=0, warm=1, mean=False):
         call()
         dt = time.perf_counter() - t0
         best, total = min(best, dt), total + dt
-    threads = lib.num_threads() if nthreads <= 0 else nthreads
+    threads = nthreads
     return (total / repeats if mean else best), threads, tag
 
 

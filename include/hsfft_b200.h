@@ -52,6 +52,18 @@ int fft_convolve_batch_dev(const char *type, const char *conv_type, const fft_ty
                            const fft_type *d_in2, int length2, fft_type *d_out, long out_stride, long howmany,
                            void *stream);
 
+/* ---- 3b. distributed four-step transform: local phases (the exchange between them is the caller's
+ *          all-to-all, e.g. torch.distributed / NCCL; see csrc/hsfft_dist.c for the data layout) ----
+ * N = N1*N2 (powers of two), `nranks` devices; rank g holds a[N1][N2/nranks] = x[N2 n1 + g N2/nranks + c]. */
+typedef struct hsfft_dist_set *hsfft_dist_object;
+hsfft_dist_object hsfft_dist_init(int N1, int N2, int nranks, int rank, int sgn);
+/* phase A: b[k1][c] = W_N^(n2 k1) * FFT_N1 over n1 of a[n1][c]; ws holds N1 * N2/nranks elements */
+void hsfft_dist_cols_dev(hsfft_dist_object d, const fft_data *d_a, fft_data *d_b, fft_data *d_ws, void *stream);
+/* phase B: out[k1l][k2] = FFT_N2 over n2 of r[n2 / Cw][k1l][n2 % Cw] (r as received from the all-to-all) */
+void hsfft_dist_rows_dev(hsfft_dist_object d, const fft_data *d_r, fft_data *d_out, fft_data *d_ws, void *stream);
+long long hsfft_dist_slab_elems(hsfft_dist_object d);
+void hsfft_dist_free(hsfft_dist_object d);
+
 /* ---- 4. device helpers ---- */
 int   hsfft_device_count(void);          /* 0 when no usable CUDA device */
 void  hsfft_set_device(int dev);         /* plans are bound to the device current at their first execute */

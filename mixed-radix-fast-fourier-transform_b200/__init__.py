@@ -49,6 +49,7 @@ EXPORTS = [
     "hsfft_device_count", "hsfft_set_device", "hsfft_get_device", "hsfft_malloc_device", "hsfft_free_device",
     "hsfft_malloc_host", "hsfft_free_host", "hsfft_copy_h2d", "hsfft_copy_d2h", "hsfft_sync", "hsfft_launch_count",
     "hsfft_plan_describe", "hsfft_version",
+    "hsfft_dist_init", "hsfft_dist_cols_dev", "hsfft_dist_rows_dev", "hsfft_dist_slab_elems", "hsfft_dist_free",
 ]
 
 
@@ -75,6 +76,8 @@ def _bind(L):
         "hsfft_malloc_host": (vp, [sz]), "hsfft_free_host": (None, [vp]),
         "hsfft_copy_h2d": (None, [vp, vp, sz]), "hsfft_copy_d2h": (None, [vp, vp, sz]), "hsfft_sync": (None, []),
         "hsfft_launch_count": (ll, []), "hsfft_plan_describe": (cp, [P]), "hsfft_version": (cp, []),
+        "hsfft_dist_init": (vp, [i, i, i, i, i]), "hsfft_dist_cols_dev": (None, [vp, vp, vp, vp, vp]),
+        "hsfft_dist_rows_dev": (None, [vp, vp, vp, vp, vp]), "hsfft_dist_slab_elems": (ll, [vp]), "hsfft_dist_free": (None, [vp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)

@@ -24,7 +24,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 C_FLAGS = ["-O2", "-std=gnu11", "-fPIC", "-Wall", "-Wextra", "-Wno-unused-parameter"]
 
 CU_SOURCES = ["hs_device.cu"]
-C_SOURCES = ["hsfft_plan.c", "hsfft_real.c", "hsfft_convolve.c"]
+C_SOURCES = ["hsfft_plan.c", "hsfft_real.c", "hsfft_convolve.c", "hsfft_dist.c"]
 
 
 def _newer(target, deps):

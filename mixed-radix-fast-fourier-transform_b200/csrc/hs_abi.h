@@ -44,7 +44,7 @@ HS_RULE int hs_stage_tw_entries(int r, int m, int split_min)
 }
 
 /* compile-time kernel families */
-enum { HS_CT_C2C = 0, HS_CT_BLUESTEIN = 1, HS_CT_TWOPASS = 2 };
+enum { HS_CT_C2C = 0, HS_CT_BLUESTEIN = 1, HS_CT_TWOPASS = 2, HS_CT_SUB = 3 };
 
 /* one compile-time specialised shared-memory transform the CUDA side offers */
 typedef struct hs_ct_desc {
@@ -75,6 +75,22 @@ typedef struct hs_gen_params {
     const void *tw, *tw_lo, *tw_hi;
     const double *gen_cs, *gen_sn;
 } hs_gen_params;
+
+/* geometry of one tiled pass (hs_tiled.cuh): `howmany` outer items x `ncols` columns, each column a
+ * strided sub-transform; element e of column c of outer item x sits at
+ *     x*in_xf + c*in_c + remap(e*in_e)          remap(o) = (o >> blk_log)*blk_stride + (o & (2^blk_log-1))
+ * (blk_log == 0: remap is the identity; it un-blocks the layout an all-to-all leaves behind), outputs
+ * likewise without the remap.
+ * tw_mode: 0 none; 1 inter-pass twiddle W^(k b) * (W^(k NB))^ii with k = column; 2 same with k = outer item. */
+typedef struct hs_tile_geom {
+    long long in_xf, out_xf;
+    long long in_c, in_e, out_c, out_e;
+    int ncols;
+    int blk_log;
+    long long blk_stride;
+    const void *twb, *tws;
+    int tw_ld; /* row length of twb: entries per b */
+} hs_tile_geom;
 
 /* ---- device / memory / streams ---- */
 int   hs_cu_device_count(void);
@@ -110,6 +126,13 @@ void  hs_cu_launch_ct_c2c(int id, int sgn, const void *d_in, void *d_out, const 
  * inter-pass twiddle tables (pass 2 only) */
 void  hs_cu_launch_ct_twopass(int id, int pass, int sgn, const void *d_in, void *d_out, const void *d_tw, const void *d_twb,
                               const void *d_tws, long long howmany, void *stream);
+/* building blocks for strided / distributed transforms: sub-plans (family HS_CT_SUB, n <= 1024) run by
+ * the tiled kernel with explicit geometry */
+void  hs_cu_launch_tiled(int sub_id, int sgn, int tw_mode, int stcol, const void *d_in, void *d_out, const void *d_tw,
+                         const hs_tile_geom *g, long long howmany, void *stream);
+/* b[k1][c] *= W_N^((c0 + c) * k1), N = 2^logN, via the split tables hi[e >> logS], lo[e & (2^logS - 1)] */
+void  hs_cu_launch_dist_twiddle(void *b, const void *hi, const void *lo, long long rows, long long cols, long long c0, int logN,
+                                int logS, void *stream);
 /* fused Bluestein: d_tw_f / d_tw_i are the forward-order / inverse-order stage tables of length M */
 void  hs_cu_launch_ct_bluestein(int id, int sgn, int N, const void *d_in, void *d_out, const void *d_tw_f, const void *d_tw_i,
                                 const void *d_chirp, const void *d_hk, long long howmany, void *stream);

@@ -49,6 +49,8 @@ static void fill_desc(hs_ct_desc &d, int id, int family)
     d.split_min = P::SPLIT;
     d.threads = P::threads;
     d.smem_bytes = P::smem_bytes;
+    d.n1 = d.n2 = d.nst2 = d.split_min2 = 0;
+    for (int s = 0; s < 8; ++s) d.radix2[s] = 0;
 }
 
 template <class P1, class P2>
@@ -64,7 +66,8 @@ static void fill_desc2(hs_ct_desc &d, int id)
 }
 
 enum { CT_4096A = 0, CT_4096B, CT_3000, CT_1024, CT_2048, CT_512, CT_256, CT_8192, CT_B2048, CT_4096X, CT_3000X, CT_4096Y, CT_3000Y, CT_3000Z,
-       CT_T14, CT_T15, CT_T16, CT_T17, CT_T18, CT_T19, CT_T20, CT_COUNT };
+       CT_T14, CT_T15, CT_T16, CT_T17, CT_T18, CT_T19, CT_T20,
+       CT_S128, CT_S256, CT_S512, CT_S1024, CT_COUNT };
 static hs_ct_desc g_ct[CT_COUNT];
 static int g_ct_order[CT_COUNT];
 static bool g_ct_ready = false;
@@ -93,6 +96,10 @@ static void ct_init()
     fill_desc2<S512, S512>(g_ct[CT_T18], CT_T18);
     fill_desc2<S512, S1024>(g_ct[CT_T19], CT_T19);
     fill_desc2<S1024, S1024>(g_ct[CT_T20], CT_T20);
+    fill_desc<S128>(g_ct[CT_S128], CT_S128, HS_CT_SUB);
+    fill_desc<S256>(g_ct[CT_S256], CT_S256, HS_CT_SUB);
+    fill_desc<S512>(g_ct[CT_S512], CT_S512, HS_CT_SUB);
+    fill_desc<S1024>(g_ct[CT_S1024], CT_S1024, HS_CT_SUB);
     for (int i = 0; i < CT_COUNT; ++i) g_ct_order[i] = i;
     // HSFFT_PREFER_CT=<id>: list that instance first (A/B runs of alternative plans for one N)
     if (const char *e = getenv("HSFFT_PREFER_CT")) {
@@ -167,14 +174,15 @@ static void launch_twopass(int pass, int sgn, const void *in, void *out, const v
     constexpr int N = P1::N * P2::N;
     HsTileGeom g;
     g.in_xf = g.out_xf = N;
+    g.blk_log = 0; g.blk_stride = 0; g.tw_ld = 0;
     if (pass == 1) {
         g.ncols = P2::N; g.in_c = 1; g.in_e = P2::N; g.out_c = P1::N; g.out_e = 1; g.twb = nullptr; g.tws = nullptr;
-        if (sgn == 1) launch_tiled<P1, 1, HsTileCols<P1>::C, false, false>(in, out, tw, g, howmany, st);
-        else launch_tiled<P1, -1, HsTileCols<P1>::C, false, false>(in, out, tw, g, howmany, st);
+        if (sgn == 1) launch_tiled<P1, 1, HsTileCols<P1>::C, 0, false>(in, out, tw, g, howmany, st);
+        else launch_tiled<P1, -1, HsTileCols<P1>::C, 0, false>(in, out, tw, g, howmany, st);
     } else {
-        g.ncols = P1::N; g.in_c = 1; g.in_e = P1::N; g.out_c = 1; g.out_e = P1::N; g.twb = (const cplx *)twb; g.tws = (const cplx *)tws;
-        if (sgn == 1) launch_tiled<P2, 1, HsTileCols<P2>::C, true, true>(in, out, tw, g, howmany, st);
-        else launch_tiled<P2, -1, HsTileCols<P2>::C, true, true>(in, out, tw, g, howmany, st);
+        g.ncols = P1::N; g.in_c = 1; g.in_e = P1::N; g.out_c = 1; g.out_e = P1::N; g.twb = twb; g.tws = tws; g.tw_ld = P1::N;
+        if (sgn == 1) launch_tiled<P2, 1, HsTileCols<P2>::C, 1, true>(in, out, tw, g, howmany, st);
+        else launch_tiled<P2, -1, HsTileCols<P2>::C, 1, true>(in, out, tw, g, howmany, st);
     }
 }
 
@@ -191,5 +199,31 @@ extern "C" void hs_cu_launch_ct_twopass(int id, int pass, int sgn, const void *d
     case CT_T19: launch_twopass<S512, S1024>(pass, sgn, d_in, d_out, d_tw, d_twb, d_tws, howmany, st); break;
     case CT_T20: launch_twopass<S1024, S1024>(pass, sgn, d_in, d_out, d_tw, d_twb, d_tws, howmany, st); break;
     default: fprintf(stderr, "Error: unknown two-pass kernel id %d\n", id); exit(EXIT_FAILURE);
+    }
+}
+
+// ---- sub-plans with explicit geometry (strided batches, distributed four-step)
+template <class P>
+static void launch_sub(int sgn, int tw_mode, int stcol, const void *in, void *out, const void *tw, const hs_tile_geom &g, long long howmany,
+                       hs_stream_t st)
+{
+    constexpr int C = HsTileCols<P>::C;
+    if (g.ncols % C != 0) { fprintf(stderr, "Error: tiled pass needs a multiple of %d columns (got %d)\n", C, g.ncols); exit(EXIT_FAILURE); }
+    if (tw_mode == 0 && !stcol) { if (sgn == 1) launch_tiled<P, 1, C, 0, false>(in, out, tw, g, howmany, st); else launch_tiled<P, -1, C, 0, false>(in, out, tw, g, howmany, st); }
+    else if (tw_mode == 0)      { if (sgn == 1) launch_tiled<P, 1, C, 0, true>(in, out, tw, g, howmany, st); else launch_tiled<P, -1, C, 0, true>(in, out, tw, g, howmany, st); }
+    else if (tw_mode == 1)      { if (sgn == 1) launch_tiled<P, 1, C, 1, true>(in, out, tw, g, howmany, st); else launch_tiled<P, -1, C, 1, true>(in, out, tw, g, howmany, st); }
+    else                        { if (sgn == 1) launch_tiled<P, 1, C, 2, true>(in, out, tw, g, howmany, st); else launch_tiled<P, -1, C, 2, true>(in, out, tw, g, howmany, st); }
+}
+
+extern "C" void hs_cu_launch_tiled(int sub_id, int sgn, int tw_mode, int stcol, const void *d_in, void *d_out, const void *d_tw,
+                                   const hs_tile_geom *g, long long howmany, void *stream)
+{
+    hs_stream_t st = (hs_stream_t)stream;
+    switch (sub_id) {
+    case CT_S128: launch_sub<S128>(sgn, tw_mode, stcol, d_in, d_out, d_tw, *g, howmany, st); break;
+    case CT_S256: launch_sub<S256>(sgn, tw_mode, stcol, d_in, d_out, d_tw, *g, howmany, st); break;
+    case CT_S512: launch_sub<S512>(sgn, tw_mode, stcol, d_in, d_out, d_tw, *g, howmany, st); break;
+    case CT_S1024: launch_sub<S1024>(sgn, tw_mode, stcol, d_in, d_out, d_tw, *g, howmany, st); break;
+    default: fprintf(stderr, "Error: unknown sub-plan id %d\n", sub_id); exit(EXIT_FAILURE);
     }
 }

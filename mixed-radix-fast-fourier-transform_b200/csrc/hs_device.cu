@@ -172,7 +172,7 @@ static void launch_blu(int N, const void *in, void *out, const void *twf, const 
     ++g_launches;
 }
 
-template <class P, int SGN, int C, bool TW, bool STCOL>
+template <class P, int SGN, int C, int TW, bool STCOL>
 static void launch_tiled(const void *in, void *out, const void *tw, const HsTileGeom &g, long long howmany, cudaStream_t st)
 {
     constexpr int MINB = (P::T * C <= 256) ? 2 : 1;
@@ -280,6 +280,14 @@ extern "C" void hs_cu_launch_slice_rows(const void *src, int P, int start, int l
 {
     hs_slice_rows_kernel<<<ew_grid(howmany * len), 256, 0, (cudaStream_t)stream>>>((const double *)src, P, start, len, (double *)dst,
                                                                                     dst_stride, howmany);
+    HS_CUDA_CHECK(cudaGetLastError());
+    ++g_launches;
+}
+extern "C" void hs_cu_launch_dist_twiddle(void *b, const void *hi, const void *lo, long long rows, long long cols, long long c0, int logN,
+                                          int logS, void *stream)
+{
+    hs_dist_twiddle_kernel<0><<<ew_grid(rows * cols), 256, 0, (cudaStream_t)stream>>>((cplx *)b, (const cplx *)hi, (const cplx *)lo, rows, cols,
+                                                                                       c0, logN, logS);
     HS_CUDA_CHECK(cudaGetLastError());
     ++g_launches;
 }

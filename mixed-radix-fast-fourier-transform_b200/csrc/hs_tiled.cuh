@@ -17,33 +17,30 @@
 #pragma once
 #include "hs_smem_fft.cuh"
 
-struct HsTileGeom {
-    long long in_xf, out_xf; // elements between consecutive transforms
-    long long in_c, in_e;    // input: column stride, element stride
-    long long out_c, out_e;  // output: column stride, element stride
-    int ncols;               // columns per transform (a multiple of C)
-    const cplx *twb;         // [b][k] = W_N^{k b}, b < NB of the plan's first stage, k < ncols; null = no twiddle
-    const cplx *tws;         // [k]    = W_N^{k NB}
-};
+typedef hs_tile_geom HsTileGeom; // see hs_abi.h
 
 struct HsLoadCol {
     static constexpr bool kPost = false;
-    const cplx *HS_RESTRICT base;
-    long long es;
-    HS_DEVICE cplx operator()(int, int, int n) const { return hs_ld_stream(base + n * es); }
+    const cplx *HS_RESTRICT base; // outer item's base
+    long long off0, es;           // column offset, element stride
+    int blk_log;
+    long long blk_stride;
+    HS_DEVICE long long addr(int n) const
+    {
+        const long long e = n * es;
+        return off0 + (blk_log ? (e >> blk_log) * blk_stride + (e & ((1LL << blk_log) - 1)) : e);
+    }
+    HS_DEVICE cplx operator()(int, int, int n) const { return hs_ld_stream(base + addr(n)); }
 };
-struct HsLoadColTw {
+struct HsLoadColTw : HsLoadCol {
     static constexpr bool kPost = true;
-    const cplx *HS_RESTRICT base;
-    long long es;
-    const cplx *HS_RESTRICT twb; // already offset by the column
-    int ncols;
+    const cplx *HS_RESTRICT twb; // already offset by k
+    int tw_ld;
     cplx step;
-    HS_DEVICE cplx operator()(int, int, int n) const { return hs_ld_stream(base + n * es); }
     template <int R>
     HS_DEVICE void post(int b, cplx *v) const
     {
-        const cplx w0 = hs_ld_tab(twb + (long long)b * ncols);
+        const cplx w0 = hs_ld_tab(twb + (long long)b * tw_ld);
         cplx s[R];
         s[1] = step;
         HS_UNROLL
@@ -66,9 +63,10 @@ struct HsStoreCol {
     HS_DEVICE void operator()(int, int, int k, cplx v) const { hs_st_stream(base + k * es, v); }
 };
 
-// P: plan of the sub-transform (P::X is ignored); C: columns per CTA; TW: apply the inter-pass twiddle
-// on load; STCOL: stores keep lane = column (pass 2) instead of switching to lane = thread (pass 1).
-template <class P, int SGN, int C, bool TW, bool STCOL, int MINB>
+// P: plan of the sub-transform (P::X is ignored); C: columns per CTA; TW: inter-pass twiddle on load
+// (0 none, 1 keyed by the column, 2 keyed by the outer item); STCOL: stores keep lane = column
+// instead of switching to lane = thread of a team (contiguous output rows).
+template <class P, int SGN, int C, int TW, bool STCOL, int MINB>
 HS_GLOBAL void HS_LAUNCH_BOUNDS(P::T *C, MINB)
 hs_tiled_kernel(const cplx *HS_RESTRICT in, cplx *HS_RESTRICT out, const cplx *HS_RESTRICT tw, const HsTileGeom g, long long howmany)
 {
@@ -83,12 +81,33 @@ hs_tiled_kernel(const cplx *HS_RESTRICT in, cplx *HS_RESTRICT out, const cplx *H
     const HsLane rest = STCOL ? first : HsLane{smem + colB * NPADC, tB, true};
     const int colS = STCOL ? colA : colB;
     HsStoreCol st{out + xf * g.out_xf + (long long)(c0 + colS) * g.out_c, g.out_e};
-    if constexpr (TW) {
-        HsLoadColTw ld{in + xf * g.in_xf + (long long)(c0 + colA) * g.in_c, g.in_e, g.twb + (c0 + colA), g.ncols,
-                       hs_ld_tab(g.tws + (c0 + colA))};
+    if constexpr (TW != 0) {
+        const long long k = (TW == 1) ? (long long)(c0 + colA) : xf;
+        HsLoadColTw ld;
+        ld.base = in + xf * g.in_xf; ld.off0 = (long long)(c0 + colA) * g.in_c; ld.es = g.in_e;
+        ld.blk_log = g.blk_log; ld.blk_stride = g.blk_stride;
+        ld.twb = (const cplx *)g.twb + k; ld.tw_ld = g.tw_ld; ld.step = hs_ld_tab((const cplx *)g.tws + k);
         hs_fft_team2<P, SGN>(ld, st, first, rest, tw);
     } else {
-        HsLoadCol ld{in + xf * g.in_xf + (long long)(c0 + colA) * g.in_c, g.in_e};
+        HsLoadCol ld;
+        ld.base = in + xf * g.in_xf; ld.off0 = (long long)(c0 + colA) * g.in_c; ld.es = g.in_e;
+        ld.blk_log = g.blk_log; ld.blk_stride = g.blk_stride;
         hs_fft_team2<P, SGN>(ld, st, first, rest, tw);
+    }
+}
+
+// Four-step exchange twiddle (north_star config 5): b[k1][c] *= W_N^{(c0 + c) k1}, N = 2^logN, from two
+// short tables (W_N^e = hi[e >> logS] * lo[e mod 2^logS]) instead of an N-entry one.
+template <int SGN_UNUSED>
+HS_GLOBAL void hs_dist_twiddle_kernel(cplx *HS_RESTRICT b, const cplx *HS_RESTRICT hi, const cplx *HS_RESTRICT lo, long long rows, long long cols,
+                                      long long c0, int logN, int logS)
+{
+    const long long total = rows * cols;
+    const unsigned long long maskN = (1ULL << logN) - 1, maskS = (1ULL << logS) - 1;
+    for (long long idx = HS_BID * HS_NTHREADS + HS_TID; idx < total; idx += HS_NBLOCKS * HS_NTHREADS) {
+        const unsigned long long k1 = (unsigned long long)(idx / cols), n2 = (unsigned long long)(c0 + idx % cols);
+        const unsigned long long e = (k1 * n2) & maskN;
+        const cplx w = hs_mul(hs_ld_tab(hi + (e >> logS)), hs_ld_tab(lo + (e & maskS)));
+        b[idx] = hs_mul(b[idx], w);
     }
 }

@@ -1,0 +1,212 @@
+/*
+ * hsfft_dist.c -- local phases of the distributed four-step transform (host side, plain C).
+ *
+ * No counterpart in the reference (it recurses on one core: N = 2^27 takes 19 s there, SURVEY.md
+ * section 5 "long-context" row); this is north_star's "single very large 1D transform ... four-step
+ * decomposition whose transpose is an NCCL all-to-all".
+ *
+ *   N = N1 * N2,  n = N2 n1 + n2,  k = k1 + N1 k2,  G ranks, Cw = N2 / G columns and Kw = N1 / G rows per rank
+ *   X[k1 + N1 k2] = sum_n2 W_N2^(n2 k2) * [ W_N^(n2 k1) * sum_n1 x[N2 n1 + n2] W_N1^(n1 k1) ]
+ *
+ *   rank g holds   a[n1][c]      = x[N2 n1 + g Cw + c]              (its column slab of the N1 x N2 matrix)
+ *   phase A (hsfft_dist_cols_dev):  b[k1][c] = W_N^((g Cw + c) k1) * FFT_N1 over n1          -- local
+ *   exchange (caller, NCCL all-to-all): rows [g' Kw, (g'+1) Kw) of b go to rank g'; a rank receives
+ *                                   r[g][k1l][c] -- contiguous blocks on both sides, no pack kernel
+ *   phase B (hsfft_dist_rows_dev):  out[k1l][k2] = FFT_N2 over n2 of r[n2 / Cw][k1l][n2 % Cw]  -- local,
+ *                                   the un-blocking of the received layout is fused into the loads
+ *   rank g ends with out[k1l][k2] = X[(g Kw + k1l) + N1 k2]         (its row slab, transposed order)
+ *
+ * The length-N1 / length-N2 transforms are the same compile-time sub-plans as everywhere else, run
+ * by the tiled kernel (hs_tiled.cuh) in one pass (128..1024) or two (2^14..2^20, e.g. 2^15 = 128 x 256
+ * for N = 2^30).
+ */
+#include "hs_engine.h"
+#include "../../include/hsfft_b200.h"
+
+typedef struct hs_axis { /* transform of length L along one axis, as one or two tiled passes */
+    int L, two, sub1, sub2, n1, n2, nb2;
+    void *d_tw1, *d_tw2, *d_twb, *d_tws;
+} hs_axis;
+
+struct hsfft_dist_set {
+    int N1, N2, nranks, rank, sgn;
+    long long Cw, Kw;
+    int logN, logS, logCw;
+    hs_axis ax1, ax2;
+    void *d_hi, *d_lo;
+};
+
+static int ilog2_exact(long long v)
+{
+    int l = 0;
+    while ((1LL << l) < v) ++l;
+    return ((1LL << l) == v) ? l : -1;
+}
+
+static const hs_ct_desc *find_family(int family, int n)
+{
+    const int cnt = hs_cu_ct_count();
+    for (int i = 0; i < cnt; ++i) {
+        const hs_ct_desc *d = hs_cu_ct_get(i);
+        if (d->family == family && d->n == n) return d;
+    }
+    return NULL;
+}
+
+static void *upload_tw(const int *rx, int nst, int sgn, int split_min)
+{
+    const int cnt = hs_stage_twiddle_count(rx, nst, split_min);
+    fft_data *t = (fft_data *)malloc(sizeof(fft_data) * (cnt > 0 ? cnt : 1));
+    if (!t) { fprintf(stderr, "Error: Memory allocation failed for twiddle table\n"); exit(EXIT_FAILURE); }
+    hs_build_stage_twiddles(t, rx, nst, sgn, split_min);
+    void *d = hs_cu_malloc(sizeof(fft_data) * (cnt > 0 ? cnt : 1));
+    hs_cu_h2d(d, t, sizeof(fft_data) * cnt, NULL);
+    free(t);
+    return d;
+}
+
+static void put_tw(fft_data *dst, double e, double theta, int sgn)
+{
+    const double a = e * theta;
+    dst->re = cos(a);
+    dst->im = (sgn == -1) ? -sin(a) : sin(a);
+}
+
+static void axis_init(hs_axis *ax, int L, int sgn)
+{
+    memset(ax, 0, sizeof(*ax));
+    ax->L = L;
+    const hs_ct_desc *s = find_family(HS_CT_SUB, L);
+    if (s) {
+        ax->sub1 = s->id;
+        ax->d_tw1 = upload_tw(s->radix, s->nst, sgn, s->split_min);
+        return;
+    }
+    const hs_ct_desc *t = find_family(HS_CT_TWOPASS, L);
+    if (!t) {
+        fprintf(stderr, "Error: distributed transform needs axis lengths in {128,256,512,1024} or 2^14..2^20 (got %d)\n", L);
+        exit(EXIT_FAILURE);
+    }
+    const hs_ct_desc *s1 = find_family(HS_CT_SUB, t->n1), *s2 = find_family(HS_CT_SUB, t->n2);
+    ax->two = 1;
+    ax->n1 = t->n1; ax->n2 = t->n2;
+    ax->sub1 = s1->id; ax->sub2 = s2->id;
+    ax->d_tw1 = upload_tw(s1->radix, s1->nst, sgn, s1->split_min);
+    ax->d_tw2 = upload_tw(s2->radix, s2->nst, sgn, s2->split_min);
+    ax->nb2 = t->n2 / s2->radix[0];
+    fft_data *tb = (fft_data *)malloc(sizeof(fft_data) * (size_t)ax->nb2 * t->n1), *ts = (fft_data *)malloc(sizeof(fft_data) * t->n1);
+    if (!tb || !ts) { fprintf(stderr, "Error: Memory allocation failed for twiddle table\n"); exit(EXIT_FAILURE); }
+    const double theta = -PI2 / (double)L;
+    for (int b = 0; b < ax->nb2; ++b)
+        for (int k = 0; k < t->n1; ++k) put_tw(&tb[(size_t)b * t->n1 + k], (double)(k * b), theta, sgn);
+    for (int k = 0; k < t->n1; ++k) put_tw(&ts[k], (double)(k * ax->nb2), theta, sgn);
+    ax->d_twb = hs_cu_malloc(sizeof(fft_data) * (size_t)ax->nb2 * t->n1);
+    ax->d_tws = hs_cu_malloc(sizeof(fft_data) * t->n1);
+    hs_cu_h2d(ax->d_twb, tb, sizeof(fft_data) * (size_t)ax->nb2 * t->n1, NULL);
+    hs_cu_h2d(ax->d_tws, ts, sizeof(fft_data) * t->n1, NULL);
+    hs_cu_stream_sync(NULL);
+    free(tb); free(ts);
+}
+
+static void axis_free(hs_axis *ax)
+{
+    hs_cu_free(ax->d_tw1); hs_cu_free(ax->d_tw2); hs_cu_free(ax->d_twb); hs_cu_free(ax->d_tws);
+}
+
+hsfft_dist_object hsfft_dist_init(int N1, int N2, int nranks, int rank, int sgn)
+{
+    hs_cu_require_device();
+    const int l1 = ilog2_exact(N1), l2 = ilog2_exact(N2), lg = ilog2_exact(nranks);
+    if (l1 < 0 || l2 < 0 || lg < 0 || rank < 0 || rank >= nranks || N1 % nranks || N2 % nranks || (sgn != 1 && sgn != -1)) {
+        fprintf(stderr, "Error: Invalid inputs for hsfft_dist_init - N1: %d, N2: %d, ranks: %d, rank: %d, sgn: %d\n", N1, N2, nranks, rank, sgn);
+        exit(EXIT_FAILURE);
+    }
+    hsfft_dist_object d = (hsfft_dist_object)calloc(1, sizeof(*d));
+    if (!d) { fprintf(stderr, "Error: Memory allocation failed for distributed plan\n"); exit(EXIT_FAILURE); }
+    d->N1 = N1; d->N2 = N2; d->nranks = nranks; d->rank = rank; d->sgn = sgn;
+    d->Cw = N2 / nranks; d->Kw = N1 / nranks;
+    d->logN = l1 + l2; d->logS = (d->logN + 1) / 2; d->logCw = ilog2_exact(d->Cw);
+    if (d->Cw < 16 || d->Kw < 16) { fprintf(stderr, "Error: distributed transform needs at least 16 columns and rows per rank\n"); exit(EXIT_FAILURE); }
+    axis_init(&d->ax1, N1, sgn);
+    axis_init(&d->ax2, N2, sgn);
+    if (d->ax2.two && d->ax2.n2 > d->Cw) {
+        fprintf(stderr, "Error: N2 = %d over %d ranks leaves slabs narrower than its second factor %d\n", N2, nranks, d->ax2.n2);
+        exit(EXIT_FAILURE);
+    }
+    /* exchange twiddle W_N^e, e = n2 k1 mod N, as hi[e >> logS] * lo[e mod 2^logS] */
+    const long long S = 1LL << d->logS, H = 1LL << (d->logN - d->logS);
+    fft_data *hi = (fft_data *)malloc(sizeof(fft_data) * H), *lo = (fft_data *)malloc(sizeof(fft_data) * S);
+    if (!hi || !lo) { fprintf(stderr, "Error: Memory allocation failed for twiddle table\n"); exit(EXIT_FAILURE); }
+    const double theta = -PI2 / ldexp(1.0, d->logN);
+    for (long long e = 0; e < S; ++e) put_tw(&lo[e], (double)e, theta, sgn);
+    for (long long e = 0; e < H; ++e) put_tw(&hi[e], ldexp((double)e, d->logS), theta, sgn);
+    d->d_hi = hs_cu_malloc(sizeof(fft_data) * H);
+    d->d_lo = hs_cu_malloc(sizeof(fft_data) * S);
+    hs_cu_h2d(d->d_hi, hi, sizeof(fft_data) * H, NULL);
+    hs_cu_h2d(d->d_lo, lo, sizeof(fft_data) * S, NULL);
+    hs_cu_stream_sync(NULL);
+    free(hi); free(lo);
+    return d;
+}
+
+void hsfft_dist_free(hsfft_dist_object d)
+{
+    if (!d) return;
+    axis_free(&d->ax1); axis_free(&d->ax2);
+    hs_cu_free(d->d_hi); hs_cu_free(d->d_lo);
+    free(d);
+}
+
+long long hsfft_dist_slab_elems(hsfft_dist_object d) { return (long long)d->N1 * d->Cw; }
+
+/* transform of length ax->L along the rows of src[L][W] (column stride 1), result dst[L][W]; ws: L*W */
+static void axis_cols(const hs_axis *ax, int sgn, const void *src, void *dst, void *ws, long long W, void *stream)
+{
+    hs_tile_geom g;
+    memset(&g, 0, sizeof g);
+    g.ncols = (int)W;
+    g.in_c = 1; g.out_c = 1;
+    if (!ax->two) {
+        g.in_e = W; g.out_e = W;
+        hs_cu_launch_tiled(ax->sub1, sgn, 0, 1, src, dst, ax->d_tw1, &g, 1, stream);
+        return;
+    }
+    const long long L1 = ax->n1, L2 = ax->n2;
+    g.in_xf = W; g.in_e = W * L2; g.out_xf = L1 * W; g.out_e = W;
+    hs_cu_launch_tiled(ax->sub1, sgn, 0, 1, src, ws, ax->d_tw1, &g, L2, stream);
+    g.in_xf = W; g.in_e = L1 * W; g.out_xf = W; g.out_e = L1 * W;
+    g.twb = ax->d_twb; g.tws = ax->d_tws; g.tw_ld = (int)L1;
+    hs_cu_launch_tiled(ax->sub2, sgn, 2, 1, ws, dst, ax->d_tw2, &g, L1, stream);
+}
+
+void hsfft_dist_cols_dev(hsfft_dist_object d, const fft_data *d_a, fft_data *d_b, fft_data *d_ws, void *stream)
+{
+    if (!d || !d_a || !d_b || !d_ws) { fprintf(stderr, "Error: Invalid distributed plan or data pointers\n"); exit(EXIT_FAILURE); }
+    axis_cols(&d->ax1, d->sgn, d_a, d_b, d_ws, d->Cw, stream);
+    hs_cu_launch_dist_twiddle(d_b, d->d_hi, d->d_lo, d->N1, d->Cw, (long long)d->rank * d->Cw, d->logN, d->logS, stream);
+}
+
+void hsfft_dist_rows_dev(hsfft_dist_object d, const fft_data *d_r, fft_data *d_out, fft_data *d_ws, void *stream)
+{
+    if (!d || !d_r || !d_out || !d_ws) { fprintf(stderr, "Error: Invalid distributed plan or data pointers\n"); exit(EXIT_FAILURE); }
+    const hs_axis *ax = &d->ax2;
+    const long long Cw = d->Cw, Kw = d->Kw, N2 = d->N2;
+    hs_tile_geom g;
+    memset(&g, 0, sizeof g);
+    g.blk_log = d->logCw; g.blk_stride = Kw * Cw; /* element n2 of row r: r*Cw + (n2 / Cw) * Kw*Cw + n2 % Cw */
+    if (!ax->two) {
+        /* lanes = rows (strided loads; only the small test sizes come here), contiguous stores */
+        g.ncols = (int)Kw; g.in_c = Cw; g.in_e = 1; g.out_c = N2; g.out_e = 1;
+        hs_cu_launch_tiled(ax->sub1, d->sgn, 0, 0, d_r, d_out, ax->d_tw1, &g, 1, stream);
+        return;
+    }
+    const long long L1 = ax->n1, L2 = ax->n2;
+    /* pass 1: per row r, columns q < L2: FFT_L1 over i of row[q + L2 i]  ->  ws[r][q*L1 + j] */
+    g.ncols = (int)L2; g.in_xf = Cw; g.in_c = 1; g.in_e = L2; g.out_xf = N2; g.out_c = L1; g.out_e = 1;
+    hs_cu_launch_tiled(ax->sub1, d->sgn, 0, 0, d_r, d_ws, ax->d_tw1, &g, Kw, stream);
+    /* pass 2: per row r, columns k < L1: FFT_L2 over i of W^(i k) ws[r][i*L1 + k]  ->  out[r][k + L1 j] */
+    memset(&g, 0, sizeof g);
+    g.ncols = (int)L1; g.in_xf = N2; g.in_c = 1; g.in_e = L1; g.out_xf = N2; g.out_c = 1; g.out_e = L1;
+    g.twb = ax->d_twb; g.tws = ax->d_tws; g.tw_ld = (int)L1;
+    hs_cu_launch_tiled(ax->sub2, d->sgn, 1, 1, d_ws, d_out, ax->d_tw2, &g, Kw, stream);
+}

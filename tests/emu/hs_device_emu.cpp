@@ -41,7 +41,7 @@ static void launch_blu(int N, const void *in, void *out, const void *twf, const 
     ++g_launches;
 }
 
-template <class P, int SGN, int C, bool TW, bool STCOL>
+template <class P, int SGN, int C, int TW, bool STCOL>
 static void launch_tiled(const void *in, void *out, const void *tw, const HsTileGeom &g, long long howmany, hs_stream_t)
 {
     constexpr int smem = C * (P::NPAD | 1) * (int)sizeof(cplx);
@@ -127,6 +127,13 @@ void hs_cu_launch_conv_mul(const void *A, const void *B, void *C, long long tota
 void hs_cu_launch_pad_rows(const void *src, int len, void *dst, int P, long long howmany, void *)
 {
     hs_emu_launch(hs_pad_rows_kernel, ew_blocks(howmany * P), 64, 0, (const double *)src, len, (double *)dst, P, howmany);
+    ++g_launches;
+}
+void hs_cu_launch_dist_twiddle(void *b, const void *hi, const void *lo, long long rows, long long cols, long long c0, int logN, int logS,
+                               void *)
+{
+    hs_emu_launch(hs_dist_twiddle_kernel<0>, ew_blocks(rows * cols), 64, 0, (cplx *)b, (const cplx *)hi, (const cplx *)lo, rows, cols, c0, logN,
+                  logS);
     ++g_launches;
 }
 void hs_cu_launch_slice_rows(const void *src, int P, int start, int len, void *dst, long long dst_stride, long long howmany, void *)
