@@ -90,6 +90,9 @@ typedef struct hs_tile_geom {
     long long blk_stride;
     const void *twb, *tws;
     int tw_ld; /* row length of twb: entries per b */
+    /* Bluestein fusions (io_mode of hs_cu_launch_tiled_io): the chirp h[n] and the logical length */
+    const void *chirp;
+    int nlog;
 } hs_tile_geom;
 
 /* ---- device / memory / streams ---- */
@@ -130,6 +133,15 @@ void  hs_cu_launch_ct_twopass(int id, int pass, int sgn, const void *d_in, void 
  * the tiled kernel with explicit geometry */
 void  hs_cu_launch_tiled(int sub_id, int sgn, int tw_mode, int stcol, const void *d_in, void *d_out, const void *d_tw,
                          const hs_tile_geom *g, long long howmany, void *stream);
+/* same with a fused Bluestein end: io_mode 1 = load x[n]*conj(h[n]) (chirp_sgn=+1; *h[n] for -1) for n < nlog
+ * and zero beyond (input rows are nlog long); io_mode 2 = store y[n]*conj(h[n]) (resp. *h[n]) for n < nlog only */
+void  hs_cu_launch_tiled_io(int sub_id, int sgn, int tw_mode, int stcol, int io_mode, int chirp_sgn, const void *d_in, void *d_out,
+                            const void *d_tw, const hs_tile_geom *g, long long howmany, void *stream);
+/* middle kernel of the long Bluestein: per column k of the padded length M = n1*n2 (n2 = the sub-plan's
+ * length): FFT_n2 (inter-pass twiddle on load) -> *Hk (conj for chirp_sgn=-1) -> inverse FFT_n2, written as
+ * contiguous rows ws2[k][j'].  g describes the loads like pass 2 of a two-pass transform. */
+void  hs_cu_launch_blu_mid(int sub_id, int chirp_sgn, const void *d_in, void *d_out, const void *d_twf, const void *d_twi,
+                           const hs_tile_geom *g, const void *d_hk, long long howmany, void *stream);
 /* b[k1][c] *= W_N^((c0 + c) * k1), N = 2^logN, via the split tables hi[e >> logS], lo[e & (2^logS - 1)] */
 void  hs_cu_launch_dist_twiddle(void *b, const void *hi, const void *lo, long long rows, long long cols, long long c0, int logN,
                                 int logS, void *stream);

@@ -30,7 +30,7 @@ using PB2048i = HsPlan<2048, 128, 2, 4, -1, 0, 16, 16, 8>;
 using S128  = HsPlan<128, 8, 1, 4, -1, 0, 8, 16>;
 using S256  = HsPlan<256, 16, 1, 4, -1, 0, 16, 16>;
 using S512  = HsPlan<512, 64, 1, 3, -1, 0, 8, 8, 8>;
-using S1024 = HsPlan<1024, 64, 1, 3, -1, 0, 16, 8, 8>;
+using S1024 = HsPlan<1024, 64, 1, 3, -1, 0, 16, 8, 8>;      // (T=128, 8.8.8.2 measured slower: 29% vs 36% at 2^20)
 // profiling-only ablations (never selected unless HSFFT_PREFER_CT names them)
 using P4096x = HsPlan<4096, 256, 1, 4, 0, 0, 16, 16, 16>;
 using P3000x = HsPlan<3000, 200, 1, 3, -1, 0, 3, 5, 5, 5, 8>;
@@ -165,7 +165,7 @@ extern "C" void hs_cu_launch_ct_bluestein(int id, int sgn, int N, const void *d_
 
 
 // ---- two-pass transforms: C columns per CTA, chosen so that a CTA has 128..512 threads
-template <class P> struct HsTileCols { static constexpr int C = P::T >= 64 ? 8 : 16; };
+template <class P> struct HsTileCols { static constexpr int C = P::T >= 64 ? 4 : 16; }; // 256..512 threads per CTA
 
 template <class P1, class P2>
 static void launch_twopass(int pass, int sgn, const void *in, void *out, const void *tw, const void *twb, const void *tws,
@@ -224,6 +224,57 @@ extern "C" void hs_cu_launch_tiled(int sub_id, int sgn, int tw_mode, int stcol, 
     case CT_S256: launch_sub<S256>(sgn, tw_mode, stcol, d_in, d_out, d_tw, *g, howmany, st); break;
     case CT_S512: launch_sub<S512>(sgn, tw_mode, stcol, d_in, d_out, d_tw, *g, howmany, st); break;
     case CT_S1024: launch_sub<S1024>(sgn, tw_mode, stcol, d_in, d_out, d_tw, *g, howmany, st); break;
+    default: fprintf(stderr, "Error: unknown sub-plan id %d\n", sub_id); exit(EXIT_FAILURE);
+    }
+}
+
+// ---- long Bluestein (padded length 2^14..2^20): fused ends and the middle kernel
+template <class P>
+static void launch_sub_io(int sgn, int tw_mode, int stcol, int io_mode, int cs, const void *in, void *out, const void *tw,
+                          const hs_tile_geom &g, long long howmany, hs_stream_t st)
+{
+    constexpr int C = HsTileCols<P>::C;
+    if (g.ncols % C != 0) { fprintf(stderr, "Error: tiled pass needs a multiple of %d columns (got %d)\n", C, g.ncols); exit(EXIT_FAILURE); }
+    if (io_mode == 1 && sgn == 1 && tw_mode == 0 && !stcol) {
+        if (cs == 1) launch_tiled<P, 1, C, 0, false, 1, 1>(in, out, tw, g, howmany, st);
+        else launch_tiled<P, 1, C, 0, false, 1, -1>(in, out, tw, g, howmany, st);
+    } else if (io_mode == 2 && sgn == -1 && tw_mode == 1 && stcol) {
+        if (cs == 1) launch_tiled<P, -1, C, 1, true, 2, 1>(in, out, tw, g, howmany, st);
+        else launch_tiled<P, -1, C, 1, true, 2, -1>(in, out, tw, g, howmany, st);
+    } else if (io_mode == 3 && tw_mode == 0 && !stcol) {
+        if (sgn == 1) launch_tiled<P, 1, C, 0, false, 3, 1>(in, out, tw, g, howmany, st);
+        else launch_tiled<P, -1, C, 0, false, 3, 1>(in, out, tw, g, howmany, st);
+    } else { fprintf(stderr, "Error: unsupported fused tiled pass\n"); exit(EXIT_FAILURE); }
+}
+
+extern "C" void hs_cu_launch_tiled_io(int sub_id, int sgn, int tw_mode, int stcol, int io_mode, int chirp_sgn, const void *d_in, void *d_out,
+                                      const void *d_tw, const hs_tile_geom *g, long long howmany, void *stream)
+{
+    hs_stream_t st = (hs_stream_t)stream;
+    switch (sub_id) {
+    case CT_S128: launch_sub_io<S128>(sgn, tw_mode, stcol, io_mode, chirp_sgn, d_in, d_out, d_tw, *g, howmany, st); break;
+    case CT_S256: launch_sub_io<S256>(sgn, tw_mode, stcol, io_mode, chirp_sgn, d_in, d_out, d_tw, *g, howmany, st); break;
+    case CT_S512: launch_sub_io<S512>(sgn, tw_mode, stcol, io_mode, chirp_sgn, d_in, d_out, d_tw, *g, howmany, st); break;
+    case CT_S1024: launch_sub_io<S1024>(sgn, tw_mode, stcol, io_mode, chirp_sgn, d_in, d_out, d_tw, *g, howmany, st); break;
+    default: fprintf(stderr, "Error: unknown sub-plan id %d\n", sub_id); exit(EXIT_FAILURE);
+    }
+}
+
+// inverse-order partners of the sub-plans (first radix = the forward plan's last radix)
+using S128i  = HsPlan<128, 8, 1, 4, -1, 0, 16, 8>;
+using S256i  = S256;
+using S512i  = S512;
+using S1024i = HsPlan<1024, 64, 1, 3, -1, 0, 8, 8, 16>;
+
+extern "C" void hs_cu_launch_blu_mid(int sub_id, int chirp_sgn, const void *d_in, void *d_out, const void *d_twf, const void *d_twi,
+                                     const hs_tile_geom *g, const void *d_hk, long long howmany, void *stream)
+{
+    hs_stream_t st = (hs_stream_t)stream;
+    switch (sub_id) {
+    case CT_S128: if (chirp_sgn == 1) launch_blu_mid<S128, S128i, 1>(d_in, d_out, d_twf, d_twi, *g, d_hk, howmany, st); else launch_blu_mid<S128, S128i, -1>(d_in, d_out, d_twf, d_twi, *g, d_hk, howmany, st); break;
+    case CT_S256: if (chirp_sgn == 1) launch_blu_mid<S256, S256i, 1>(d_in, d_out, d_twf, d_twi, *g, d_hk, howmany, st); else launch_blu_mid<S256, S256i, -1>(d_in, d_out, d_twf, d_twi, *g, d_hk, howmany, st); break;
+    case CT_S512: if (chirp_sgn == 1) launch_blu_mid<S512, S512i, 1>(d_in, d_out, d_twf, d_twi, *g, d_hk, howmany, st); else launch_blu_mid<S512, S512i, -1>(d_in, d_out, d_twf, d_twi, *g, d_hk, howmany, st); break;
+    case CT_S1024: if (chirp_sgn == 1) launch_blu_mid<S1024, S1024i, 1>(d_in, d_out, d_twf, d_twi, *g, d_hk, howmany, st); else launch_blu_mid<S1024, S1024i, -1>(d_in, d_out, d_twf, d_twi, *g, d_hk, howmany, st); break;
     default: fprintf(stderr, "Error: unknown sub-plan id %d\n", sub_id); exit(EXIT_FAILURE);
     }
 }

@@ -172,12 +172,12 @@ static void launch_blu(int N, const void *in, void *out, const void *twf, const 
     ++g_launches;
 }
 
-template <class P, int SGN, int C, int TW, bool STCOL>
+template <class P, int SGN, int C, int TW, bool STCOL, int IO = 0, int CS = 1>
 static void launch_tiled(const void *in, void *out, const void *tw, const HsTileGeom &g, long long howmany, cudaStream_t st)
 {
-    constexpr int MINB = (P::T * C <= 256) ? 2 : 1;
+    constexpr int MINB = (P::T * C <= 256 || P::N / P::T <= 8) ? 2 : 1;
     constexpr int smem = C * (P::NPAD | 1) * (int)sizeof(cplx);
-    auto kern = hs_tiled_kernel<P, SGN, C, TW, STCOL, MINB>;
+    auto kern = hs_tiled_kernel<P, SGN, C, TW, STCOL, MINB, IO, CS>;
     static bool attr_done = false;
     if (!attr_done) {
         HS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -186,6 +186,28 @@ static void launch_tiled(const void *in, void *out, const void *tw, const HsTile
     const long long blocks = howmany * (g.ncols / C);
     check_grid(blocks);
     kern<<<(unsigned)blocks, P::T * C, smem, st>>>((const cplx *)in, (cplx *)out, (const cplx *)tw, g, howmany);
+    HS_CUDA_CHECK(cudaGetLastError());
+    ++g_launches;
+}
+
+template <class PF, class PI, int CS>
+static void launch_blu_mid(const void *in, void *out, const void *twf, const void *twi, const HsTileGeom &g, const void *hk,
+                           long long howmany, cudaStream_t st)
+{
+    constexpr int C = PF::T >= 64 ? 4 : 16;
+    constexpr int MINB = (PF::T * C <= 256 || PF::N / PF::T <= 8) ? 2 : 1;
+    constexpr int smem = C * (PF::NPAD | 1) * (int)sizeof(cplx);
+    auto kern = hs_blu_mid_kernel<PF, PI, CS, C, MINB>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        HS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_done = true;
+    }
+    if (g.ncols % C != 0) { fprintf(stderr, "Error: tiled pass needs a multiple of %d columns\n", C); exit(EXIT_FAILURE); }
+    const long long blocks = howmany * (g.ncols / C);
+    check_grid(blocks);
+    kern<<<(unsigned)blocks, PF::T * C, smem, st>>>((const cplx *)in, (cplx *)out, (const cplx *)twf, (const cplx *)twi, g, (const cplx *)hk,
+                                                    howmany);
     HS_CUDA_CHECK(cudaGetLastError());
     ++g_launches;
 }

@@ -44,6 +44,10 @@ typedef struct hs_dev_obj {
     void *d_chirp, *d_hk;
     int blu_ct_id;
     void *d_blu_twf, *d_blu_twi;
+    /* long Bluestein (M = n1*n2 two-pass): three fused kernels, see hs_tiled.cuh */
+    int big, big_n1, big_n2, big_sub1, big_sub2;
+    void *d_big_f1, *d_big_f2, *d_big_i1, *d_big_i2, *d_big_fb, *d_big_fs, *d_big_ib, *d_big_is;
+    long long big_chunk;
     /* pipeline slots for host-pointer calls */
     void *stream[HS_NSLOT];
     void *d_in[HS_NSLOT], *d_out[HS_NSLOT], *d_ws[HS_NSLOT], *d_ws2[HS_NSLOT];
@@ -62,6 +66,11 @@ hs_c2c *hs_c2c_create(int n, int sgn);
 void    hs_c2c_destroy(hs_c2c *p);
 size_t  hs_c2c_ws_elems(const hs_c2c *p, long long howmany); /* workspace (complex elements) exec needs */
 void    hs_c2c_exec(const hs_c2c *p, const void *d_in, void *d_out, void *d_ws, long long howmany, void *stream);
+
+/* c2r with the merge pass fused into the first pass of the half-length transform; returns 0 when this plan
+ * has no such fusion (the caller then runs the separate merge kernel) */
+int     hs_dev_exec_c2r_fused(hs_dev_obj *d, const void *d_spec, long long in_stride, const void *d_tw2, void *d_out, void *d_ws,
+                              long long howmany, void *stream);
 
 /* registry */
 hs_dev_obj *hs_dev_get(fft_object plan);      /* find or build; exits when no CUDA device */

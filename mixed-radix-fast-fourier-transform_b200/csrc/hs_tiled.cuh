@@ -63,10 +63,63 @@ struct HsStoreCol {
     HS_DEVICE void operator()(int, int, int k, cplx v) const { hs_st_stream(base + k * es, v); }
 };
 
+// Bluestein ends fused into the tiled passes (reference src/highSpeedFFT.c:1803-1827 and :1871-1886):
+// pass 1 of the forward transform loads x[n]*conj(h[n]) (or *h[n]) and the zero padding directly,
+// the last pass of the inverse transform multiplies by the chirp and stores only the N logical outputs.
+template <int CS>
+struct HsLoadColChirp {
+    static constexpr bool kPost = false;
+    const cplx *HS_RESTRICT x; // this transform's N logical samples
+    const cplx *HS_RESTRICT h;
+    int N;
+    long long off0, es;
+    HS_DEVICE cplx operator()(int, int, int n_) const
+    {
+        const long long n = off0 + n_ * es;
+        if (n >= N) return hs_c(0.0, 0.0);
+        const cplx xv = hs_ld_stream(x + n), hv = hs_ld_tab(h + n);
+        return (CS == 1) ? hs_mulc(xv, hv) : hs_mul(xv, hv);
+    }
+};
+template <int CS>
+struct HsStoreColChirpCrop {
+    cplx *HS_RESTRICT out;
+    const cplx *HS_RESTRICT h;
+    int N;
+    long long off0, es;
+    HS_DEVICE void operator()(int, int, int k, cplx v) const
+    {
+        const long long n = off0 + k * es;
+        if (n < N) {
+            const cplx hv = hs_ld_tab(h + n);
+            hs_st_stream(out + n, (CS == 1) ? hs_mulc(v, hv) : hs_mul(v, hv));
+        }
+    }
+};
+
+// c2r merge (reference src/real.c:171-179) fused into pass 1 of the half-length transform: element k of the
+// packed signal is built from bins k and H-k of the Hermitian input on the fly, so the merged signal is
+// never written to HBM.
+struct HsLoadColC2RPre {
+    static constexpr bool kPost = false;
+    const cplx *HS_RESTRICT x;   // this transform's bins 0..H
+    const cplx *HS_RESTRICT tw2; // exp(+2 pi i k / N)
+    int H;
+    long long off0, es;
+    HS_DEVICE cplx operator()(int, int, int n_) const
+    {
+        const long long k = off0 + n_ * es;
+        const cplx a = hs_ld_stream(x + k), c = hs_ld_stream(x + (H - k)), w = hs_ld_tab(tw2 + k);
+        const double t1 = -a.y - c.y, t2 = -c.x + a.x;
+        return hs_c(a.x + c.x + (t1 * w.x) - (t2 * w.y), a.y - c.y + (t2 * w.x) + (t1 * w.y));
+    }
+};
+
 // P: plan of the sub-transform (P::X is ignored); C: columns per CTA; TW: inter-pass twiddle on load
 // (0 none, 1 keyed by the column, 2 keyed by the outer item); STCOL: stores keep lane = column
 // instead of switching to lane = thread of a team (contiguous output rows).
-template <class P, int SGN, int C, int TW, bool STCOL, int MINB>
+// IO: 0 plain; 1 chirp-and-pad load (CS = chirp direction); 2 chirp-and-crop store; 3 c2r merge on load.
+template <class P, int SGN, int C, int TW, bool STCOL, int MINB, int IO = 0, int CS = 1>
 HS_GLOBAL void HS_LAUNCH_BOUNDS(P::T *C, MINB)
 hs_tiled_kernel(const cplx *HS_RESTRICT in, cplx *HS_RESTRICT out, const cplx *HS_RESTRICT tw, const HsTileGeom g, long long howmany)
 {
@@ -80,6 +133,27 @@ hs_tiled_kernel(const cplx *HS_RESTRICT in, cplx *HS_RESTRICT out, const cplx *H
     const HsLane first{smem + colA * NPADC, tA, true};
     const HsLane rest = STCOL ? first : HsLane{smem + colB * NPADC, tB, true};
     const int colS = STCOL ? colA : colB;
+    if constexpr (IO == 1) { // forward pass 1 of the long Bluestein
+        HsStoreCol st{out + xf * g.out_xf + (long long)(c0 + colS) * g.out_c, g.out_e};
+        HsLoadColChirp<CS> ld{in + xf * g.in_xf, (const cplx *)g.chirp, g.nlog, (long long)(c0 + colA) * g.in_c, g.in_e};
+        hs_fft_team2<P, SGN>(ld, st, first, rest, tw);
+        return;
+    } else if constexpr (IO == 3) { // c2r: merge fused into pass 1 (g.chirp = twiddle2, g.nlog = H)
+        HsStoreCol st{out + xf * g.out_xf + (long long)(c0 + colS) * g.out_c, g.out_e};
+        HsLoadColC2RPre ld{in + xf * g.in_xf, (const cplx *)g.chirp, g.nlog, (long long)(c0 + colA) * g.in_c, g.in_e};
+        hs_fft_team2<P, SGN>(ld, st, first, rest, tw);
+        return;
+    } else if constexpr (IO == 2) { // inverse last pass of the long Bluestein
+        static_assert(TW != 0, "the chirp-and-crop store belongs to a second pass");
+        HsStoreColChirpCrop<CS> st{out + xf * g.out_xf, (const cplx *)g.chirp, g.nlog, (long long)(c0 + colS) * g.out_c, g.out_e};
+        const long long k = (TW == 1) ? (long long)(c0 + colA) : xf;
+        HsLoadColTw ld;
+        ld.base = in + xf * g.in_xf; ld.off0 = (long long)(c0 + colA) * g.in_c; ld.es = g.in_e;
+        ld.blk_log = g.blk_log; ld.blk_stride = g.blk_stride;
+        ld.twb = (const cplx *)g.twb + k; ld.tw_ld = g.tw_ld; ld.step = hs_ld_tab((const cplx *)g.tws + k);
+        hs_fft_team2<P, SGN>(ld, st, first, rest, tw);
+        return;
+    }
     HsStoreCol st{out + xf * g.out_xf + (long long)(c0 + colS) * g.out_c, g.out_e};
     if constexpr (TW != 0) {
         const long long k = (TW == 1) ? (long long)(c0 + colA) : xf;
@@ -94,6 +168,60 @@ hs_tiled_kernel(const cplx *HS_RESTRICT in, cplx *HS_RESTRICT out, const cplx *H
         ld.blk_log = g.blk_log; ld.blk_stride = g.blk_stride;
         hs_fft_team2<P, SGN>(ld, st, first, rest, tw);
     }
+}
+
+// Middle kernel of the long Bluestein (padded length M = n1 * P::N): for column k < n1
+//   Y[k + n1 j] = FFT_{P::N} over i of ( W_M^{i k} ws1[i n1 + k] )      forward pass 2
+//   Y *= Hk (conj(Hk) for the inverse plan direction)                   reference :1838-1855
+//   ws2[k][j'] = inverse FFT_{P::N} over j of Y[k + n1 j]               inverse pass 1 (decomposition n2 x n1)
+// The spectrum Y never leaves the registers between the two transforms (same radix, same map).
+template <int CS, int RL>
+struct HsStoreRegsMulCol {
+    cplx (*y)[RL];
+    const cplx *HS_RESTRICT hk; // already offset by the column
+    long long es;
+    HS_DEVICE void operator()(int u, int j, int k, cplx v) const
+    {
+        const cplx hv = hs_ld_tab(hk + k * es);
+        y[u][j] = (CS == 1) ? hs_mul(v, hv) : hs_mulc(v, hv);
+    }
+};
+template <int RL>
+struct HsLoadRegsCol {
+    static constexpr bool kPost = false;
+    cplx (*y)[RL];
+    HS_DEVICE cplx operator()(int u, int i, int) const { return y[u][i]; }
+};
+
+template <class PF, class PI, int CS, int C, int MINB>
+HS_GLOBAL void HS_LAUNCH_BOUNDS(PF::T *C, MINB)
+hs_blu_mid_kernel(const cplx *HS_RESTRICT in, cplx *HS_RESTRICT out, const cplx *HS_RESTRICT twf, const cplx *HS_RESTRICT twi,
+                  const HsTileGeom g, const cplx *HS_RESTRICT hk, long long howmany)
+{
+    static_assert(PF::N == PI::N && PF::T == PI::T && PF::NPAD == PI::NPAD, "plans must pair");
+    constexpr int RL = PF::radix(PF::NST - 1);
+    static_assert(PI::radix(0) == RL && PF::pass_size(PF::NPASS - 1) == 1 && PI::pass_size(0) == 1, "register hand-over needs matching radices");
+    constexpr int NB = PF::N / RL, B = (NB + PF::T - 1) / PF::T;
+    constexpr int NPADC = PF::NPAD | 1;
+    HS_DYN_SMEM(cplx, smem);
+    const int tiles = g.ncols / C;
+    const long long xf = HS_BID / tiles;
+    const int c0 = (int)(HS_BID % tiles) * C;
+    const int colA = HS_TID % C, tA = HS_TID / C;         // lane = column
+    const int colB = HS_TID / PF::T, tB = HS_TID % PF::T; // lane = thread of a team
+    const HsLane laneA{smem + colA * NPADC, tA, true}, laneB{smem + colB * NPADC, tB, true};
+    cplx y[B][RL];
+
+    const long long k = c0 + colA;
+    HsLoadColTw ld;
+    ld.base = in + xf * g.in_xf; ld.off0 = k * g.in_c; ld.es = g.in_e; ld.blk_log = 0; ld.blk_stride = 0;
+    ld.twb = (const cplx *)g.twb + k; ld.tw_ld = g.tw_ld; ld.step = hs_ld_tab((const cplx *)g.tws + k);
+    HsStoreRegsMulCol<CS, RL> st{y, hk + k, (long long)g.ncols}; // Hk[k + n1 j]
+    hs_fft_team2<PF, 1>(ld, st, laneA, laneA, twf);
+    HS_SYNC();
+    HsLoadRegsCol<RL> ld2{y};
+    HsStoreCol st2{out + xf * g.out_xf + (long long)(c0 + colB) * g.out_c, g.out_e};
+    hs_fft_team2<PI, -1>(ld2, st2, laneA, laneB, twi);
 }
 
 // Four-step exchange twiddle (north_star config 5): b[k1][c] *= W_N^{(c0 + c) k1}, N = 2^logN, from two

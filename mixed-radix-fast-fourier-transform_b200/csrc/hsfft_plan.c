@@ -435,6 +435,8 @@ static void dev_free_contents(hs_dev_obj *d)
     hs_cu_free(d->d_hk);
     hs_cu_free(d->d_blu_twf);
     hs_cu_free(d->d_blu_twi);
+    hs_cu_free(d->d_big_f1); hs_cu_free(d->d_big_f2); hs_cu_free(d->d_big_i1); hs_cu_free(d->d_big_i2);
+    hs_cu_free(d->d_big_fb); hs_cu_free(d->d_big_fs); hs_cu_free(d->d_big_ib); hs_cu_free(d->d_big_is);
     for (int s = 0; s < HS_NSLOT; ++s) {
         hs_cu_free(d->d_in[s]); hs_cu_free(d->d_out[s]); hs_cu_free(d->d_ws[s]); hs_cu_free(d->d_ws2[s]);
         if (d->stream[s]) hs_cu_stream_destroy(d->stream[s]);
@@ -478,6 +480,44 @@ static void dev_build(hs_dev_obj *d, fft_object plan)
     free(h);
     free(hp);
 
+    const hs_ct_desc *tp = find_ct(HS_CT_TWOPASS, M);
+    const hs_ct_desc *s1 = tp ? find_ct(HS_CT_SUB, tp->n1) : NULL, *s2 = tp ? find_ct(HS_CT_SUB, tp->n2) : NULL;
+    if (tp && s1 && s2 && !getenv("HSFFT_NO_BIGBLU")) {
+        /* long Bluestein: A = chirp/pad + forward pass 1, B = forward pass 2 * Hk + inverse pass 1, C = inverse
+         * pass 2 + chirp/crop.  Forward decomposition n1 x n2, inverse n2 x n1, so B works column by column. */
+        const int n1 = tp->n1, n2 = tp->n2;
+        int inv2[8];
+        for (int s = 0; s < s2->nst; ++s) inv2[s] = s2->radix[s2->nst - 1 - s];
+        d->big = 1; d->big_n1 = n1; d->big_n2 = n2; d->big_sub1 = s1->id; d->big_sub2 = s2->id;
+        d->d_big_f1 = upload_stage_twiddles(s1->radix, s1->nst, 1, s1->split_min);
+        d->d_big_f2 = upload_stage_twiddles(s2->radix, s2->nst, 1, s2->split_min);
+        d->d_big_i1 = upload_stage_twiddles(inv2, s2->nst, -1, s2->split_min);
+        d->d_big_i2 = upload_stage_twiddles(s1->radix, s1->nst, -1, s1->split_min);
+        const int NBf = n2 / s2->radix[0], NBi = n1 / s1->radix[0];
+        fft_data *fb = (fft_data *)malloc(sizeof(fft_data) * (size_t)NBf * n1), *fs = (fft_data *)malloc(sizeof(fft_data) * n1);
+        fft_data *ib = (fft_data *)malloc(sizeof(fft_data) * (size_t)NBi * n2), *is = (fft_data *)malloc(sizeof(fft_data) * n2);
+        if (!fb || !fs || !ib || !is) { fprintf(stderr, "Error: Memory allocation failed for twiddle table\n"); exit(EXIT_FAILURE); }
+        const fft_type theta = -PI2 / (fft_type)M;
+        for (int b = 0; b < NBf; ++b)
+            for (int k = 0; k < n1; ++k) put_twiddle(&fb[(size_t)b * n1 + k], k * b, theta, 1);
+        for (int k = 0; k < n1; ++k) put_twiddle(&fs[k], k * NBf, theta, 1);
+        for (int b = 0; b < NBi; ++b)
+            for (int k = 0; k < n2; ++k) put_twiddle(&ib[(size_t)b * n2 + k], k * b, theta, -1);
+        for (int k = 0; k < n2; ++k) put_twiddle(&is[k], k * NBi, theta, -1);
+        d->d_big_fb = upload(fb, sizeof(fft_data) * (size_t)NBf * n1);
+        d->d_big_fs = upload(fs, sizeof(fft_data) * n1);
+        d->d_big_ib = upload(ib, sizeof(fft_data) * (size_t)NBi * n2);
+        d->d_big_is = upload(is, sizeof(fft_data) * n2);
+        hs_cu_stream_sync(NULL);
+        free(fb); free(fs); free(ib); free(is);
+        /* chunk the batch so that both M-sized workspaces of a chunk stay resident in the 126 MB L2 */
+        long long mb = 1 << 20; /* measured: chunks small enough for L2 (48 MB) underfill the GPU; default = no chunking */
+        if (getenv("HSFFT_BLU_CHUNK_MB")) mb = atoll(getenv("HSFFT_BLU_CHUNK_MB"));
+        d->big_chunk = (mb << 20) / ((long long)2 * M * (long long)sizeof(fft_data));
+        if (d->big_chunk < 1) d->big_chunk = 1;
+        hs_c2c_destroy(f);
+        return;
+    }
     const hs_ct_desc *ct = find_ct(HS_CT_BLUESTEIN, M);
     if (ct) {
         /* fused kernel: forward plan = ct->radix, inverse plan = the same list reversed */
@@ -552,6 +592,7 @@ size_t hs_dev_ws_bytes(const hs_dev_obj *d, long long howmany)
 {
     if (d->lt == 0) return hs_c2c_ws_elems(d->direct, howmany) * sizeof(fft_data);
     if (d->blu_ct_id >= 0) return 0;
+    if (d->big) return (size_t)2 * (howmany < d->big_chunk ? howmany : d->big_chunk) * d->M * sizeof(fft_data);
     return ((size_t)2 * howmany * d->M + hs_c2c_ws_elems(d->fwdM, howmany)) * sizeof(fft_data);
 }
 
@@ -564,6 +605,28 @@ void hs_dev_exec(hs_dev_obj *d, const void *d_in, void *d_out, void *d_ws, long 
                                   stream);
         return;
     }
+    if (d->big) {
+        const long long M = d->M, N = d->N, n1 = d->big_n1, n2 = d->big_n2;
+        const long long chunk = howmany < d->big_chunk ? howmany : d->big_chunk;
+        fft_data *ws1 = (fft_data *)d_ws, *ws2 = ws1 + (size_t)chunk * M;
+        hs_tile_geom ga, gb, gc;
+        memset(&ga, 0, sizeof ga); memset(&gb, 0, sizeof gb); memset(&gc, 0, sizeof gc);
+        ga.ncols = (int)n2; ga.in_xf = N; ga.in_c = 1; ga.in_e = n2; ga.out_xf = M; ga.out_c = n1; ga.out_e = 1;
+        ga.chirp = d->d_chirp; ga.nlog = (int)N;
+        gb.ncols = (int)n1; gb.in_xf = M; gb.in_c = 1; gb.in_e = n1; gb.out_xf = M; gb.out_c = n2; gb.out_e = 1;
+        gb.twb = d->d_big_fb; gb.tws = d->d_big_fs; gb.tw_ld = (int)n1;
+        gc.ncols = (int)n2; gc.in_xf = M; gc.in_c = 1; gc.in_e = n2; gc.out_xf = N; gc.out_c = 1; gc.out_e = n2;
+        gc.twb = d->d_big_ib; gc.tws = d->d_big_is; gc.tw_ld = (int)n2; gc.chirp = d->d_chirp; gc.nlog = (int)N;
+        for (long long first = 0; first < howmany; first += chunk) {
+            const long long cnt = (first + chunk <= howmany) ? chunk : howmany - first;
+            const fft_data *x = (const fft_data *)d_in + first * N;
+            fft_data *o = (fft_data *)d_out + first * N;
+            hs_cu_launch_tiled_io(d->big_sub1, 1, 0, 0, 1, d->sgn, x, ws1, d->d_big_f1, &ga, cnt, stream);
+            hs_cu_launch_blu_mid(d->big_sub2, d->sgn, ws1, ws2, d->d_big_f2, d->d_big_i1, &gb, d->d_hk, cnt, stream);
+            hs_cu_launch_tiled_io(d->big_sub1, -1, 1, 1, 2, d->sgn, ws2, o, d->d_big_i2, &gc, cnt, stream);
+        }
+        return;
+    }
     /* unfused chirp-z: pad*chirp -> FFT_M -> *Hk -> IFFT_M -> *chirp, crop */
     fft_data *a = (fft_data *)d_ws, *b = a + (size_t)howmany * d->M, *c = b + (size_t)howmany * d->M;
     hs_cu_launch_chirp_pad(d->sgn, d_in, a, d->d_chirp, d->N, d->M, howmany, stream);
@@ -571,6 +634,24 @@ void hs_dev_exec(hs_dev_obj *d, const void *d_in, void *d_out, void *d_ws, long 
     hs_cu_launch_spectrum_mul(d->sgn, b, d->d_hk, d->M, howmany, stream);
     hs_c2c_exec(d->invM, b, a, c, howmany, stream);
     hs_cu_launch_chirp_crop(d->sgn, a, d_out, d->d_chirp, d->N, d->M, howmany, stream);
+}
+
+int hs_dev_exec_c2r_fused(hs_dev_obj *d, const void *d_spec, long long in_stride, const void *d_tw2, void *d_out, void *d_ws,
+                          long long howmany, void *stream)
+{
+    if (d->lt != 0 || !d->direct || d->direct->tp_id < 0 || getenv("HSFFT_NO_C2R_FUSE")) return 0;
+    const hs_c2c *p = d->direct;
+    const hs_ct_desc *tp = NULL;
+    for (int i = 0; i < hs_cu_ct_count(); ++i) if (hs_cu_ct_get(i)->id == p->tp_id) tp = hs_cu_ct_get(i);
+    const hs_ct_desc *s1 = tp ? find_ct(HS_CT_SUB, tp->n1) : NULL;
+    if (!tp || !s1) return 0;
+    hs_tile_geom g;
+    memset(&g, 0, sizeof g);
+    g.ncols = tp->n2; g.in_xf = in_stride; g.in_c = 1; g.in_e = tp->n2; g.out_xf = p->n; g.out_c = tp->n1; g.out_e = 1;
+    g.chirp = d_tw2; g.nlog = p->n;
+    hs_cu_launch_tiled_io(s1->id, p->sgn, 0, 0, 3, 1, d_spec, d_ws, p->d_tw, &g, howmany, stream);
+    hs_cu_launch_ct_twopass(p->tp_id, 2, p->sgn, d_ws, d_out, p->d_tw2, p->d_twb, p->d_tws, howmany, stream);
+    return 1;
 }
 
 /* ---------------------------------------------------------------------------------- public API */
@@ -702,7 +783,10 @@ const char *hsfft_plan_describe(fft_object obj)
             for (int g = 0; g < p->npass && n < (int)sizeof buf - 32; ++g)
                 n += snprintf(buf + n, sizeof buf - n, " [n=%d C=%d]", p->pass[g].n, p->pass[g].C);
         }
-    } else if (d->blu_ct_id >= 0)
+    } else if (d->big)
+        n = snprintf(buf, sizeof buf, "bluestein N=%d M=%d=%dx%d: 3 fused tiled kernels, %lld transforms per L2-resident chunk", d->N, d->M,
+                     d->big_n1, d->big_n2, d->big_chunk);
+    else if (d->blu_ct_id >= 0)
         n = snprintf(buf, sizeof buf, "bluestein N=%d M=%d: fused compile-time kernel #%d", d->N, d->M, d->blu_ct_id);
     else
         n = snprintf(buf, sizeof buf, "bluestein N=%d M=%d: unfused (chirp, FFT_M x%d pass, mul, IFFT_M, chirp)", d->N, d->M,

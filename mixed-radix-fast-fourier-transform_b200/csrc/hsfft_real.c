@@ -140,6 +140,8 @@ static void c2r_dev(fft_real_object obj, hs_real_dev *r, const fft_data *d_in, l
                     long howmany, void *stream)
 {
     hs_dev_obj *c = hs_dev_get(obj->cobj);
+    /* long transforms: the merge is fused into the first pass (d_z then serves as the pass workspace) */
+    if (hs_dev_exec_c2r_fused(c, d_in, in_stride, r->d_tw2, d_out, d_z, howmany, stream)) return;
     hs_cu_launch_c2r_pre(d_in, d_z, r->d_tw2, r->H, in_stride, howmany, stream);
     hs_dev_exec(c, d_z, d_out, d_ws, howmany, stream);
 }

@@ -41,11 +41,22 @@ static void launch_blu(int N, const void *in, void *out, const void *twf, const 
     ++g_launches;
 }
 
-template <class P, int SGN, int C, int TW, bool STCOL>
+template <class PF, class PI, int CS>
+static void launch_blu_mid(const void *in, void *out, const void *twf, const void *twi, const HsTileGeom &g, const void *hk,
+                           long long howmany, hs_stream_t)
+{
+    constexpr int C = PF::T >= 64 ? 4 : 16;
+    constexpr int smem = C * (PF::NPAD | 1) * (int)sizeof(cplx);
+    hs_emu_launch(hs_blu_mid_kernel<PF, PI, CS, C, 1>, howmany * (g.ncols / C), PF::T * C, smem, (const cplx *)in, (cplx *)out,
+                  (const cplx *)twf, (const cplx *)twi, g, (const cplx *)hk, howmany);
+    ++g_launches;
+}
+
+template <class P, int SGN, int C, int TW, bool STCOL, int IO = 0, int CS = 1>
 static void launch_tiled(const void *in, void *out, const void *tw, const HsTileGeom &g, long long howmany, hs_stream_t)
 {
     constexpr int smem = C * (P::NPAD | 1) * (int)sizeof(cplx);
-    hs_emu_launch(hs_tiled_kernel<P, SGN, C, TW, STCOL, 1>, howmany * (g.ncols / C), P::T * C, smem, (const cplx *)in, (cplx *)out,
+    hs_emu_launch(hs_tiled_kernel<P, SGN, C, TW, STCOL, 1, IO, CS>, howmany * (g.ncols / C), P::T * C, smem, (const cplx *)in, (cplx *)out,
                   (const cplx *)tw, g, howmany);
     ++g_launches;
 }

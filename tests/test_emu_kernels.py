@@ -46,14 +46,27 @@ def test_runtime_planned_engine_small(hs, emu_lib, oracle, n):
         assert err <= tol(n), (n, sgn, err, desc)
 
 
-@pytest.mark.parametrize("n", [6561, 10000, 32768, 10007])
+@pytest.mark.parametrize("n", [6561, 10000, 24576])
 def test_runtime_planned_engine_multipass(hs, emu_lib, oracle, n):
     err, desc = run_c2c(hs, emu_lib, oracle, n, 1, howmany=2)
     assert ("pass" in desc) and err <= tol(n), (n, err, desc)
 
 
+@pytest.mark.parametrize("n", [16384, 65536])
+def test_compile_time_two_pass(hs, emu_lib, oracle, n):
+    err, desc = run_c2c(hs, emu_lib, oracle, n, -1, howmany=1)
+    assert "two-pass" in desc and err <= tol(n), (err, desc)
+
+
+@pytest.mark.parametrize("n", [4099, 10007])
+def test_long_bluestein_three_fused_kernels(hs, emu_lib, oracle, n):
+    for sgn in (1, -1):
+        err, desc = run_c2c(hs, emu_lib, oracle, n, sgn, howmany=2)
+        assert "3 fused tiled kernels" in desc and err <= tol(n), (n, sgn, err, desc)
+
+
 def test_three_pass_plan(hs, emu_lib, oracle):
-    n = 1 << 19
+    n = 3 << 17   # 393216 = [8]*5 + [4, 3]: no compile-time plan, three run-time passes
     err, desc = run_c2c(hs, emu_lib, oracle, n, -1, howmany=1)
     assert "3 run-time" in desc and err <= tol(n), (err, desc)
 

@@ -3,7 +3,13 @@
 import csv, io, subprocess, sys
 rep = sys.argv[1]; top = int(sys.argv[2]) if len(sys.argv) > 2 else 25
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
-rows = list(csv.reader(io.StringIO(out)))
+allrows = list(csv.reader(io.StringIO(out)))
+# a report with several kernels repeats the two header lines; pick kernel number sys.argv[3] (default 0)
+starts = [i for i, r in enumerate(allrows) if r and r[0] == "Kernel Name"]
+which = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+lo = starts[which]; hi = starts[which + 1] if which + 1 < len(starts) else len(allrows)
+rows = allrows[lo:hi]
+print("kernel:", rows[0][1][:140])
 hdr = rows[1]; body = [r for r in rows[2:] if len(r) == len(hdr)]
 ix = {h: i for i, h in enumerate(hdr)}
 tot = sum(int(r[ix["# Samples"]] or 0) for r in body)
