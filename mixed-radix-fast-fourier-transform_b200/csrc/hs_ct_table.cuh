@@ -165,7 +165,6 @@ extern "C" void hs_cu_launch_ct_bluestein(int id, int sgn, int N, const void *d_
 
 
 // ---- two-pass transforms: C columns per CTA, chosen so that a CTA has 128..512 threads
-template <class P> struct HsTileCols { static constexpr int C = P::T >= 64 ? 4 : 16; }; // 256..512 threads per CTA
 
 template <class P1, class P2>
 static void launch_twopass(int pass, int sgn, const void *in, void *out, const void *tw, const void *twb, const void *tws,

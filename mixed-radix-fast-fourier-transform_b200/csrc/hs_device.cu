@@ -175,7 +175,7 @@ static void launch_blu(int N, const void *in, void *out, const void *twf, const 
 template <class P, int SGN, int C, int TW, bool STCOL, int IO = 0, int CS = 1>
 static void launch_tiled(const void *in, void *out, const void *tw, const HsTileGeom &g, long long howmany, cudaStream_t st)
 {
-    constexpr int MINB = (P::T * C <= 256 || P::N / P::T <= 8) ? 2 : 1;
+    constexpr int MINB = (P::T * C <= 256) ? 2 : 1;
     constexpr int smem = C * (P::NPAD | 1) * (int)sizeof(cplx);
     auto kern = hs_tiled_kernel<P, SGN, C, TW, STCOL, MINB, IO, CS>;
     static bool attr_done = false;
@@ -194,8 +194,8 @@ template <class PF, class PI, int CS>
 static void launch_blu_mid(const void *in, void *out, const void *twf, const void *twi, const HsTileGeom &g, const void *hk,
                            long long howmany, cudaStream_t st)
 {
-    constexpr int C = PF::T >= 64 ? 4 : 16;
-    constexpr int MINB = (PF::T * C <= 256 || PF::N / PF::T <= 8) ? 2 : 1;
+    constexpr int C = HsTileCols<PF>::C;
+    constexpr int MINB = (PF::T * C <= 256) ? 2 : 1;
     constexpr int smem = C * (PF::NPAD | 1) * (int)sizeof(cplx);
     auto kern = hs_blu_mid_kernel<PF, PI, CS, C, MINB>;
     static bool attr_done = false;

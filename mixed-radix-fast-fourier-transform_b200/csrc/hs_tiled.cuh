@@ -19,6 +19,10 @@
 
 typedef hs_tile_geom HsTileGeom; // see hs_abi.h
 
+// columns per CTA: as many as shared memory and the register file allow (longer contiguous runs on the
+// strided side), 128..512 threads per CTA
+template <class P> struct HsTileCols { static constexpr int C = P::T >= 64 ? (P::N <= 512 ? 8 : 4) : 16; }; // measured: 512-pt 4/8/16 -> 35/40/31 %, 1024-pt 4/8 -> 36/30 % (two-pass, 2^18 / 2^20)
+
 struct HsLoadCol {
     static constexpr bool kPost = false;
     const cplx *HS_RESTRICT base; // outer item's base

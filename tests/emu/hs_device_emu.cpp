@@ -45,7 +45,7 @@ template <class PF, class PI, int CS>
 static void launch_blu_mid(const void *in, void *out, const void *twf, const void *twi, const HsTileGeom &g, const void *hk,
                            long long howmany, hs_stream_t)
 {
-    constexpr int C = PF::T >= 64 ? 4 : 16;
+    constexpr int C = HsTileCols<PF>::C;
     constexpr int smem = C * (PF::NPAD | 1) * (int)sizeof(cplx);
     hs_emu_launch(hs_blu_mid_kernel<PF, PI, CS, C, 1>, howmany * (g.ncols / C), PF::T * C, smem, (const cplx *)in, (cplx *)out,
                   (const cplx *)twf, (const cplx *)twi, g, (const cplx *)hk, howmany);
