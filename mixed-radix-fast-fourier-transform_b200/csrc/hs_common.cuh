@@ -36,6 +36,27 @@ static inline void hs_st_stream(double2 *p, double2 v) { *p = v; }
 static inline double2 hs_ld_tab(const double2 *p) { return *p; }
 static inline double hs_ld_stream_d(const double *p) { return *p; }
 static inline void hs_st_stream_d(double *p, double v) { *p = v; }
+// bulk-copy engine (TMA) stand-ins: the copy is done by the issuing thread, the barrier counts bytes
+#include <atomic>
+struct HsMbar { std::atomic<long long> done; };
+static inline void hs_mbar_init(HsMbar *m) { m->done.store(0); }
+static inline void hs_mbar_expect(HsMbar *, unsigned) {}
+static inline void hs_bulk_g2s(void *dst, const void *src, unsigned bytes, HsMbar *m) { memcpy(dst, src, bytes); m->done.fetch_add(bytes); }
+static inline void hs_mbar_wait(HsMbar *m, unsigned /*parity*/, long long seq, long long bytes_per_phase)
+{
+    while (m->done.load() < (seq + 1) * bytes_per_phase) { }
+}
+static inline void hs_fence_async_proxy() {}
+// 3-D tensor-map stand-in: [z][row][x doubles], strides in bytes
+struct HsTmap { const unsigned char *base; long long row_stride, z_stride; };
+static inline void hs_tma_load_3d(void *dst, const HsTmap *t, int x_dbl, int row0, long long z, int rows, int row_bytes, HsMbar *m)
+{
+    for (int r = 0; r < rows; ++r)
+        memcpy((unsigned char *)dst + (size_t)r * row_bytes, t->base + z * t->z_stride + (long long)(row0 + r) * t->row_stride + (long long)x_dbl * 8,
+               row_bytes);
+    m->done.fetch_add((long long)rows * row_bytes);
+}
+#define HS_GRID_CONSTANT
 #else
 // ---------------------------------------------------------------------------- CUDA (product)
 #include <cuda_runtime.h>
@@ -74,6 +95,54 @@ HS_DEVICE double2 hs_ld_tab(const double2 *p)
 }
 HS_DEVICE double hs_ld_stream_d(const double *p) { return __ldcs(p); }
 HS_DEVICE void hs_st_stream_d(double *p, double v) { __stcs(p, v); }
+
+// ---- bulk asynchronous copies (the TMA engine, cp.async.bulk -> UBLKCP in SASS) and their mbarrier
+struct HsMbar { unsigned long long word; };
+HS_DEVICE unsigned hs_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+HS_DEVICE void hs_mbar_init(HsMbar *m)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(hs_smem_u32(m)) : "memory");
+}
+// one arrival (of the single expected one) announcing `bytes` of asynchronous writes for this phase
+HS_DEVICE void hs_mbar_expect(HsMbar *m, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(hs_smem_u32(m)), "r"(bytes) : "memory");
+}
+// global -> shared, 16-byte aligned, size a multiple of 16; completion is credited to the mbarrier
+HS_DEVICE void hs_bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, HsMbar *m)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(hs_smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(hs_smem_u32(m))
+                 : "memory");
+}
+// wait for the phase of the given parity; a copy that never lands traps instead of hanging the GPU
+HS_DEVICE void hs_mbar_wait(HsMbar *m, unsigned parity, long long, long long)
+{
+    const unsigned a = hs_smem_u32(m);
+    for (unsigned spin = 0;; ++spin) {
+        unsigned ok;
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok)
+                     : "r"(a), "r"(parity)
+                     : "memory");
+        if (ok) return;
+        if (spin > (1u << 24)) __trap();
+    }
+}
+// 2-D tile of a 3-D tensor [z][row][x] described by a CUtensorMap (cuTensorMapEncodeTiled on the host): one
+// instruction moves box_rows x box_x elements, the TMA engine walks the strides (UTMALDG in SASS)
+#include <cuda.h>
+typedef CUtensorMap HsTmap;
+#define HS_GRID_CONSTANT __grid_constant__
+HS_DEVICE void hs_tma_load_3d(void *dst_smem, const HsTmap *t, int x_dbl, int row0, long long z, int /*rows*/, int /*row_bytes*/, HsMbar *m)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                     hs_smem_u32(dst_smem)),
+                 "l"(t), "r"(x_dbl), "r"(row0), "r"((int)z), "r"(hs_smem_u32(m))
+                 : "memory");
+}
+// order this thread's generic-proxy accesses to shared memory before later asynchronous-proxy ones
+HS_DEVICE void hs_fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 #endif
 
 typedef double2 cplx; // x = re, y = im; 16-byte interleaved, same bytes as the API's fft_data

@@ -172,9 +172,80 @@ static void launch_blu(int N, const void *in, void *out, const void *twf, const 
     ++g_launches;
 }
 
+// persistent, TMA-staged variant (hs_tiled_tma_kernel).  Measured on B200 (two-pass c2c, same box, TMA vs plain):
+// 2^17 43.8 vs 38.8 %, 2^18 40.5 vs 29.6 %, 2^19 36.4 vs 32.3 %, 2^20 35.9 vs 35.6 % of the HBM peak, but
+// 2^14..2^16 (128/256-point sub-plans, already at the two-pass cap) 45-49 vs 52-54 %.  So it is the default for
+// sub-plans of 512 points and more; HSFFT_TMA=0 / 1 forces it off / on everywhere.
+static bool tma_enabled(int sub_len)
+{
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("HSFFT_TMA"); v = e ? atoi(e) : 2; }
+    return v == 1 || (v == 2 && sub_len >= 512);
+}
+
+typedef CUresult (*hs_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                 CUtensorMapFloatOOBfill);
+static hs_encode_fn hs_encode()
+{
+    static hs_encode_fn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        HS_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+        if (!p || q != cudaDriverEntryPointSuccess) { fprintf(stderr, "Error: cuTensorMapEncodeTiled is not available\n"); exit(EXIT_FAILURE); }
+        fn = (hs_encode_fn)p;
+    }
+    return fn;
+}
+
+// tensor map of one pass's input: [howmany][rows][2*ncols doubles], row stride in_e, item stride in_xf
+static CUtensorMap make_tmap(const void *in, const HsTileGeom &g, int rows, int C, long long howmany)
+{
+    CUtensorMap m;
+    const int boxr = rows < 256 ? rows : 256;
+    cuuint64_t dims[3] = {(cuuint64_t)2 * g.ncols, (cuuint64_t)rows, (cuuint64_t)howmany};
+    cuuint64_t strides[2] = {(cuuint64_t)g.in_e * 16, (cuuint64_t)g.in_xf * 16};
+    cuuint32_t box[3] = {(cuuint32_t)2 * C, (cuuint32_t)boxr, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = hs_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void *>(in), dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { fprintf(stderr, "Error: cuTensorMapEncodeTiled failed (%d)\n", (int)r); exit(EXIT_FAILURE); }
+    return m;
+}
+
+template <class P, int SGN, int C, int TW, bool STCOL>
+static void launch_tiled_tma(const void *in, void *out, const void *tw, const HsTileGeom &g, long long howmany, cudaStream_t st)
+{
+    constexpr int smem = HsTmaTileSmem<P, C>::bytes;
+    static_assert(smem <= 227 * 1024, "staging buffers do not fit");
+    auto kern = hs_tiled_tma_kernel<P, SGN, C, TW, STCOL>;
+    static bool attr_done = false;
+    static int per_sm = 1;
+    if (!attr_done) {
+        HS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        per_sm = (227 * 1024) / smem;
+        if (per_sm * P::T * C > 1024) per_sm = 1024 / (P::T * C);
+        if (per_sm < 1) per_sm = 1;
+        attr_done = true;
+    }
+    const long long total = howmany * (g.ncols / C);
+    long long blocks = (long long)hs_cu_sm_count() * per_sm;
+    if (blocks > total) blocks = total;
+    check_grid(blocks);
+    const CUtensorMap tm = make_tmap(in, g, P::N, C, howmany);
+    kern<<<(unsigned)blocks, P::T * C, smem, st>>>(tm, (cplx *)out, (const cplx *)tw, g, howmany);
+    HS_CUDA_CHECK(cudaGetLastError());
+    ++g_launches;
+}
+
 template <class P, int SGN, int C, int TW, bool STCOL, int IO = 0, int CS = 1>
 static void launch_tiled(const void *in, void *out, const void *tw, const HsTileGeom &g, long long howmany, cudaStream_t st)
 {
+    if constexpr (IO == 0) {
+        if (tma_enabled(P::N) && g.in_c == 1 && g.blk_log == 0) { launch_tiled_tma<P, SGN, C, TW, STCOL>(in, out, tw, g, howmany, st); return; }
+    }
     constexpr int MINB = (P::T * C <= 256) ? 2 : 1;
     constexpr int smem = C * (P::NPAD | 1) * (int)sizeof(cplx);
     auto kern = hs_tiled_kernel<P, SGN, C, TW, STCOL, MINB, IO, CS>;
