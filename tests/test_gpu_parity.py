@@ -146,3 +146,46 @@ def test_kernels_really_launched(hs, product_lib):
     with hs.Plan(4096, 1) as p:
         p.exec(rand_cplx(2, 4096))
     assert hs.launch_count() > before
+
+
+def test_four_step_distributed_phases_single_gpu(hs, product_lib, oracle):
+    """hsfft_dist_* local phases on one GPU (world = 1: the exchange is a copy); N = N1*N2 = 2^17 and 2^28-style split."""
+    import importlib
+    import torch
+    dmod = importlib.import_module("mixed-radix-fast-fourier-transform_b200.dist")
+    dev = torch.device("cuda", 0)
+    for N1, N2, sgn in ((256, 512, 1), (16384, 128, -1), (128, 16384, 1)):
+        N = N1 * N2
+        x = rand_cplx(1, N, seed=N1 + N2)[0]
+        plan = dmod.DistPlan(hs, N1, N2, sgn, rank=0, world=1, device=dev)
+        a = torch.view_as_real(torch.from_numpy(dmod.scatter_input(x, N1, N2, 0, 1))).reshape(-1, 2).contiguous().to(dev)
+        out = torch.empty((N1 * N2, 2), dtype=torch.float64, device=dev)
+        plan.forward(a, out)
+        torch.cuda.synchronize()
+        X = dmod.gather_output([torch.view_as_complex(out).reshape(N1, N2).cpu().numpy()], N1, N2)
+        assert rel_rms(X, oracle.c2c(x, sgn)) <= tol(N), (N1, N2)
+        plan.close()
+
+
+@pytest.mark.parametrize("tma", ["0", "1"])
+def test_tiled_passes_with_and_without_tma(tma):
+    """The plain and the TMA-staged tiled kernels must agree with the oracle on every two-pass size class."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import importlib, sys
+sys.path.insert(0, %r); sys.path.insert(0, %r + "/tests")
+import oracle_lib as ol
+hs = importlib.import_module("mixed-radix-fast-fourier-transform_b200")
+orc = ol.Oracle()
+for n in (1 << 14, 1 << 15, 1 << 17, 1 << 19, 1 << 20):
+    x = ol.rand_cplx(2, n, seed=n)
+    with hs.Plan(n, -1) as p:
+        y = p.exec(x)
+    e = ol.rel_rms(y, orc.c2c(x, -1))
+    assert e <= ol.tol(n), (n, e)
+print("TILED_OK")
+''' % (root, root)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, HSFFT_TMA=tma), timeout=600)
+    assert "TILED_OK" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
