@@ -24,6 +24,8 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 C_FLAGS = ["-O2", "-std=gnu11", "-fPIC", "-Wall", "-Wextra", "-Wno-unused-parameter"]
 
 CU_SOURCES = ["hs_device.cu"]
+# the persistent pipeline kernels: one object per two-pass size 2^14..2^20 (same source, -DHS_PIPE_ID), built in parallel
+PIPE_SIZES = [14, 15, 16, 17, 18, 19, 20]
 C_SOURCES = ["hsfft_plan.c", "hsfft_real.c", "hsfft_convolve.c", "hsfft_dist.c"]
 
 
@@ -35,28 +37,34 @@ def _newer(target, deps):
 
 
 def build(force=False, verbose=False, extra_nvcc=()):
+    from concurrent.futures import ThreadPoolExecutor
     os.makedirs(BUILD, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
     headers += [os.path.join(HERE, "..", "include", f) for f in ("highspeedFFT.h", "real.h", "hsfft_b200.h")]
-    objs = []
+    jobs = []  # (object, command)
     for src in CU_SOURCES:
         s = os.path.join(CSRC, src)
         o = os.path.join(BUILD, src + ".o")
-        if force or _newer(o, [s] + headers):
-            cmd = [NVCC] + NVCC_FLAGS + list(extra_nvcc) + ["-c", s, "-o", o]
-            if verbose:
-                print(" ".join(cmd), flush=True)
-            subprocess.run(cmd, check=True)
-        objs.append(o)
+        jobs.append((o, [s], [NVCC] + NVCC_FLAGS + list(extra_nvcc) + ["-c", s, "-o", o]))
+    for k in PIPE_SIZES:
+        s = os.path.join(CSRC, "hs_pipe_inst.cu")
+        o = os.path.join(BUILD, "hs_pipe_%d.o" % k)
+        jobs.append((o, [s], [NVCC] + NVCC_FLAGS + list(extra_nvcc) + ["-DHS_PIPE_ID=CT_T%d" % k, "-DHS_PIPE_NAME=%d" % k, "-c", s, "-o", o]))
     for src in C_SOURCES:
         s = os.path.join(CSRC, src)
         o = os.path.join(BUILD, src + ".o")
-        if force or _newer(o, [s] + headers):
-            cmd = [GCC] + C_FLAGS + ["-c", s, "-o", o]
+        jobs.append((o, [s], [GCC] + C_FLAGS + ["-c", s, "-o", o]))
+
+    def run(job):
+        o, deps, cmd = job
+        if force or _newer(o, deps + headers):
             if verbose:
                 print(" ".join(cmd), flush=True)
             subprocess.run(cmd, check=True)
-        objs.append(o)
+        return o
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 2)) as ex:
+        objs = list(ex.map(run, jobs))
     if force or _newer(OUT, objs):
         cmd = [NVCC, "-shared", "-o", OUT] + objs + ["-ccbin", GXX, "-Xlinker", "-Bsymbolic", "-lpthread", "-lm"]
         if verbose:

@@ -95,6 +95,37 @@ typedef struct hs_tile_geom {
     int nlog;
 } hs_tile_geom;
 
+/* ---- persistent pipeline kernels (hs_pipe.cuh): a chain of up to HS_PIPE_MAX_PHASE tile phases whose
+ * intermediates live in rings of workspace slots small enough to stay in L2 ---- */
+#define HS_PIPE_MAX_PHASE 3
+typedef struct hs_phase_args {
+    hs_tile_geom g;       /* in_xf / out_xf: per-transform stride of this phase's source / destination */
+    const void *tw;       /* stage twiddles of the phase's sub-plan */
+    const void *tw_b;     /* second sub-plan of a fused phase (Bluestein middle: inverse pass 1) */
+    const void *aux;      /* Bluestein middle: Hk */
+    int tiles;            /* tiles per transform */
+    int flags;            /* r2c split: 1 = write the mirrored upper half too */
+} hs_phase_args;
+typedef struct hs_pipe_args {
+    int nphase;
+    hs_phase_args ph[HS_PIPE_MAX_PHASE];
+    const void *in;       /* phase 0 reads transform x at in + x*ph[0].g.in_xf */
+    void *out;            /* the last phase writes transform x at out + x*ph[last].g.out_xf */
+    void *ring[HS_PIPE_MAX_PHASE - 1]; /* ring[j]: nslot*G transforms, written by phase j, read by phase j+1 */
+    long long howmany;
+    int G;                /* transforms per group (the unit of dependency tracking) */
+    int lag;              /* phase j+1 of group g is issued `lag` rounds after phase j of group g */
+    int nslot;            /* ring slots (groups); >= lag + 1 */
+    void *ctl;            /* zeroed by the launcher: u64 ticket, then u32 done[phase][group] from byte 128 */
+    /* derived by the launcher (hs_pipe_finalize) */
+    long long ngroups;
+    unsigned items[HS_PIPE_MAX_PHASE]; /* tickets per group of each phase = G * tiles */
+    unsigned round_items;              /* sum of items[] */
+    unsigned long long total;          /* tickets of the whole launch = (ngroups + (nphase-1)*lag) * round_items */
+} hs_pipe_args;
+/* bytes of control words hs_cu_launch_pipe needs behind hs_pipe_args.ctl */
+#define HS_PIPE_CTL_BYTES(ngroups) ((size_t)128 + (size_t)HS_PIPE_MAX_PHASE * (size_t)(ngroups) * 4)
+
 /* ---- device / memory / streams ---- */
 int   hs_cu_device_count(void);
 void  hs_cu_require_device(void);            /* exits with a message when no CUDA device is usable */
@@ -148,6 +179,12 @@ void  hs_cu_launch_dist_twiddle(void *b, const void *hi, const void *lo, long lo
 /* fused Bluestein: d_tw_f / d_tw_i are the forward-order / inverse-order stage tables of length M */
 void  hs_cu_launch_ct_bluestein(int id, int sgn, int N, const void *d_in, void *d_out, const void *d_tw_f, const void *d_tw_i,
                                 const void *d_chirp, const void *d_hk, long long howmany, void *stream);
+
+/* persistent pipeline of the two-pass size tp_id.  variant: 0 c2c, 1 c2r (merge on load), 2 r2c (split as third phase),
+ * 3 long Bluestein (sgn = chirp direction).  The caller fills geometry, tables, in/out/ring/ctl, howmany, G, lag, nslot;
+ * the callee fills ph[].tiles.  query != 0: only fill tiles and report availability.  Returns 0 when this
+ * (size, variant, sgn) has no pipeline (the caller then runs the multi-launch path). */
+int   hs_cu_launch_pipe(int tp_id, int variant, int sgn, hs_pipe_args *a, void *stream, int query);
 
 /* ---- run-time planned pass and element-wise helpers ---- */
 void  hs_cu_launch_generic(int sgn, const void *d_in, void *d_out, const hs_gen_params *p, void *stream);

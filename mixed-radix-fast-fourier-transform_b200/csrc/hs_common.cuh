@@ -10,6 +10,8 @@
 // ---------------------------------------------------------------- host emulation (tests only)
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 struct double2 { double x, y; };
 static inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
@@ -21,6 +23,7 @@ extern thread_local unsigned char *hs_emu_smem;
 void hs_emu_barrier();
 #define HS_GLOBAL
 #define HS_DEVICE inline
+#define HS_NOINLINE
 #define HS_HD inline
 #define HS_LAUNCH_BOUNDS(t, b)
 #define HS_RESTRICT
@@ -36,6 +39,17 @@ static inline void hs_st_stream(double2 *p, double2 v) { *p = v; }
 static inline double2 hs_ld_tab(const double2 *p) { return *p; }
 static inline double hs_ld_stream_d(const double *p) { return *p; }
 static inline void hs_st_stream_d(double *p, double v) { *p = v; }
+template <int MP> static inline double2 hs_ld_mp(const double2 *p) { return *p; }
+template <int MP> static inline void hs_st_mp(double2 *p, double2 v) { *p = v; }
+// grid-level dataflow (persistent pipeline kernels): tickets and completion counters
+static inline unsigned long long hs_ticket_take(unsigned long long *p) { return __atomic_fetch_add(p, 1ULL, __ATOMIC_ACQ_REL); }
+static inline void hs_signal_add(unsigned *p) { __atomic_fetch_add(p, 1u, __ATOMIC_RELEASE); }
+static inline unsigned hs_peek(const unsigned *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+static inline void hs_wait_geq(const unsigned *p, unsigned need)
+{
+    // CTAs run one after another in the emulation: a dependency that is not already met never will be
+    if (__atomic_load_n(p, __ATOMIC_ACQUIRE) < need) { fprintf(stderr, "hs_emu: pipeline dependency not met (ticket order bug)\n"); abort(); }
+}
 // bulk-copy engine (TMA) stand-ins: the copy is done by the issuing thread, the barrier counts bytes
 #include <atomic>
 struct HsMbar { std::atomic<long long> done; };
@@ -63,6 +77,7 @@ static inline void hs_tma_load_3d(void *dst, const HsTmap *t, int x_dbl, int row
 #include <cstdint>
 #define HS_GLOBAL __global__
 #define HS_DEVICE __device__ __forceinline__
+#define HS_NOINLINE __device__ __noinline__
 #define HS_HD __host__ __device__ __forceinline__
 #define HS_LAUNCH_BOUNDS(t, b) __launch_bounds__(t, b)
 #define HS_RESTRICT __restrict__
@@ -95,6 +110,78 @@ HS_DEVICE double2 hs_ld_tab(const double2 *p)
 }
 HS_DEVICE double hs_ld_stream_d(const double *p) { return __ldcs(p); }
 HS_DEVICE void hs_st_stream_d(double *p, double v) { __stcs(p, v); }
+
+// ---- L2 residency classes for the persistent pipeline kernels (hs_pipe.cuh).  Intermediates that one
+// phase writes and the next phase reads are tagged evict_last so that they live and die in the 126 MB L2
+// (the ring of workspace slots is overwritten in place, its dirty lines never reach HBM); the signal
+// streaming in and the spectrum streaming out are tagged evict_first so they do not push the ring out.
+//   MP 0: stream, read-only path (as hs_ld_stream / hs_st_stream)
+//   MP 1: keep  -- loads are coherent (ld.relaxed.gpu: another CTA of this launch wrote the data)
+//   MP 2: stream + L2 evict_first
+HS_DEVICE unsigned long long hs_pol_keep()
+{
+    unsigned long long p;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+HS_DEVICE unsigned long long hs_pol_first()
+{
+    unsigned long long p;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+template <int MP>
+HS_DEVICE double2 hs_ld_mp(const double2 *p)
+{
+    double2 v;
+    if (MP == 1)
+        asm volatile("ld.relaxed.gpu.global.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;"
+                     : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(hs_pol_keep()) : "memory");
+    else if (MP == 2)
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(hs_pol_first()));
+    else
+        v = hs_ld_stream(p);
+    return v;
+}
+template <int MP>
+HS_DEVICE void hs_st_mp(double2 *p, double2 v)
+{
+    if (MP == 1)
+        asm volatile("st.global.L1::no_allocate.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(hs_pol_keep()) : "memory");
+    else if (MP == 2)
+        asm volatile("st.global.L1::no_allocate.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(hs_pol_first()) : "memory");
+    else
+        hs_st_stream(p, v);
+}
+// ---- grid-level dataflow: work tickets and completion counters in global memory
+HS_DEVICE unsigned long long hs_ticket_take(unsigned long long *p) { return atomicAdd(p, 1ULL); }
+// after a CTA barrier: publish this CTA's global writes (the fence is cumulative over what the barrier ordered
+// before it), then count the tile as done
+HS_DEVICE void hs_signal_add(unsigned *p)
+{
+    __threadfence();
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
+}
+// Completion counters are read with ld.relaxed.gpu, not ld.acquire: an acquire at gpu scope makes ptxas
+// invalidate the SM's whole L1 (CCTL.IVALL), which would throw out the twiddle tables on every poll.  The data
+// the counter guards is only ever read with ld.relaxed.gpu as well (hs_ld_mp<1>: served by the L2, the point
+// of coherence), after a CTA barrier that follows the poll, and was published by hs_signal_add's fence.
+HS_DEVICE unsigned hs_peek(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// spin until *p >= need; a dependency that never completes traps instead of hanging the GPU
+HS_DEVICE void hs_wait_geq(const unsigned *p, unsigned need)
+{
+    for (unsigned spin = 0;; ++spin) {
+        const unsigned v = hs_peek(p);
+        if (v >= need) return;
+        if (spin > 64) __nanosleep(spin > 4096 ? 1000 : 100);
+        if (spin > (1u << 22)) __trap();
+    }
+}
 
 // ---- bulk asynchronous copies (the TMA engine, cp.async.bulk -> UBLKCP in SASS) and their mbarrier
 struct HsMbar { unsigned long long word; };

@@ -5,20 +5,11 @@
 #include <atomic>
 
 #include "hs_abi.h"
+#include "hs_cuda_util.h"
 #include "hs_fused.cuh"
 #include "hs_generic.cuh"
 #include "hs_smem_fft.cuh"
 #include "hs_tiled.cuh"
-
-#define HS_CUDA_CHECK(expr)                                                                            \
-    do {                                                                                               \
-        cudaError_t e_ = (expr);                                                                       \
-        if (e_ != cudaSuccess) {                                                                       \
-            fprintf(stderr, "Error: CUDA failure %s at %s:%d (%s)\n", cudaGetErrorString(e_), __FILE__, \
-                    __LINE__, #expr);                                                                  \
-            exit(EXIT_FAILURE);                                                                        \
-        }                                                                                              \
-    } while (0)
 
 static std::atomic<long long> g_launches{0};
 
@@ -114,6 +105,7 @@ extern "C" float hs_cu_event_elapsed_ms(void *start, void *stop)
 }
 extern "C" void hs_cu_event_sync(void *ev) { HS_CUDA_CHECK(cudaEventSynchronize((cudaEvent_t)ev)); }
 extern "C" long long hs_cu_launch_count(void) { return g_launches.load(); }
+extern "C" void hs_cu_count_launch(void) { ++g_launches; }
 
 // --------------------------------------------------------------------------------------- launchers
 static void check_grid(long long blocks)
@@ -247,7 +239,7 @@ static void launch_tiled(const void *in, void *out, const void *tw, const HsTile
         if (tma_enabled(P::N) && g.in_c == 1 && g.blk_log == 0) { launch_tiled_tma<P, SGN, C, TW, STCOL>(in, out, tw, g, howmany, st); return; }
     }
     constexpr int MINB = (P::T * C <= 256) ? 2 : 1;
-    constexpr int smem = C * (P::NPAD | 1) * (int)sizeof(cplx);
+    constexpr int smem = C * hs_col_stride(P::NPAD, C) * (int)sizeof(cplx);
     auto kern = hs_tiled_kernel<P, SGN, C, TW, STCOL, MINB, IO, CS>;
     static bool attr_done = false;
     if (!attr_done) {
@@ -267,7 +259,7 @@ static void launch_blu_mid(const void *in, void *out, const void *twf, const voi
 {
     constexpr int C = HsTileCols<PF>::C;
     constexpr int MINB = (PF::T * C <= 256) ? 2 : 1;
-    constexpr int smem = C * (PF::NPAD | 1) * (int)sizeof(cplx);
+    constexpr int smem = C * hs_col_stride(PF::NPAD, C) * (int)sizeof(cplx);
     auto kern = hs_blu_mid_kernel<PF, PI, CS, C, MINB>;
     static bool attr_done = false;
     if (!attr_done) {
@@ -383,4 +375,28 @@ extern "C" void hs_cu_launch_dist_twiddle(void *b, const void *hi, const void *l
                                                                                        c0, logN, logS);
     HS_CUDA_CHECK(cudaGetLastError());
     ++g_launches;
+}
+
+// ---- persistent pipelines (hs_pipe.cuh): one translation unit per two-pass size, see hs_pipe_inst.cu
+extern "C" {
+int hs_cu_pipe_14(int, int, hs_pipe_args *, void *, int);
+int hs_cu_pipe_15(int, int, hs_pipe_args *, void *, int);
+int hs_cu_pipe_16(int, int, hs_pipe_args *, void *, int);
+int hs_cu_pipe_17(int, int, hs_pipe_args *, void *, int);
+int hs_cu_pipe_18(int, int, hs_pipe_args *, void *, int);
+int hs_cu_pipe_19(int, int, hs_pipe_args *, void *, int);
+int hs_cu_pipe_20(int, int, hs_pipe_args *, void *, int);
+}
+extern "C" int hs_cu_launch_pipe(int tp_id, int variant, int sgn, hs_pipe_args *a, void *stream, int query)
+{
+    switch (tp_id) {
+    case CT_T14: return hs_cu_pipe_14(variant, sgn, a, stream, query);
+    case CT_T15: return hs_cu_pipe_15(variant, sgn, a, stream, query);
+    case CT_T16: return hs_cu_pipe_16(variant, sgn, a, stream, query);
+    case CT_T17: return hs_cu_pipe_17(variant, sgn, a, stream, query);
+    case CT_T18: return hs_cu_pipe_18(variant, sgn, a, stream, query);
+    case CT_T19: return hs_cu_pipe_19(variant, sgn, a, stream, query);
+    case CT_T20: return hs_cu_pipe_20(variant, sgn, a, stream, query);
+    }
+    return 0;
 }

@@ -1,0 +1,43 @@
+// hs_plans.cuh -- the compile-time plans (stage radices, team sizes, padding) and their ids, shared by the
+// dispatch tables hs_ct_table.cuh (one-launch kernels and stand-alone passes) and hs_pipe_table.cuh
+// (persistent pipelines).
+#pragma once
+#include "hs_smem_fft.cuh"
+
+// ------------------------------------------------------------------------ compile-time plan table
+// Stage radices in execution order (the reference's factor list reversed; runs of power-of-two
+// factors regrouped, which only exact constants allow -- SURVEY.md section 8c).  LOGPAD values come
+// from tests/emu/bank_check.py (all stages conflict free).
+//                      N     T   X  LOGPAD SPLIT GROUPS radices...
+using P4096a = HsPlan<4096, 256, 1, 4, -1, 0, 16, 16, 16>;       // reference factors [8,8,8,8]
+using P4096b = HsPlan<4096, 512, 1, 3, -1, 0, 8, 8, 8, 8>;
+using P3000  = HsPlan<3000, 200, 1, 3, -1, 221, 3, 5, 5, 5, 8>; // reference factors [8,5,5,5,3] verbatim; passes {3,5}{5,5}{8}
+using P1024  = HsPlan<1024, 64, 4, 3, -1, 0, 16, 8, 8>;          // reference factors [8,8,8,2]
+using P2048  = HsPlan<2048, 128, 2, 3, -1, 0, 16, 16, 8>;        // reference factors [8,8,8,4]
+using P512   = HsPlan<512, 64, 4, 3, -1, 0, 8, 8, 8>;
+using P256   = HsPlan<256, 16, 16, 4, -1, 0, 16, 16>;
+using P8192  = HsPlan<8192, 512, 1, 4, -1, 0, 8, 8, 8, 16>;
+// fused Bluestein, M = 2048 (N = 513..1024, e.g. the N = 1009 config): forward / inverse pair
+using PB2048f = HsPlan<2048, 128, 2, 4, -1, 0, 8, 16, 16>;
+using PB2048i = HsPlan<2048, 128, 2, 4, -1, 0, 16, 16, 8>;
+// sub-plans of the two-pass transforms (N = n1 * n2 > 8192); X is unused there
+using S128  = HsPlan<128, 8, 1, 4, -1, 0, 8, 16>;
+using S256  = HsPlan<256, 16, 1, 4, -1, 0, 16, 16>;
+using S512  = HsPlan<512, 64, 1, 3, -1, 0, 8, 8, 8>;
+using S1024 = HsPlan<1024, 64, 1, 3, -1, 0, 16, 8, 8>;      // (T=128, 8.8.8.2 measured slower: 29% vs 36% at 2^20)
+// profiling-only ablations (never selected unless HSFFT_PREFER_CT names them)
+using P4096x = HsPlan<4096, 256, 1, 4, 0, 0, 16, 16, 16>;
+using P3000x = HsPlan<3000, 200, 1, 3, -1, 0, 3, 5, 5, 5, 8>;
+using P4096y = HsPlan<4096, 256, 1, 4, -2, 0, 16, 16, 16>;
+using P3000y = HsPlan<3000, 200, 1, 3, 0, 0, 3, 5, 5, 5, 8>;       // one stage per pass, load-all twiddles (round-1 first contact)
+using P3000z = HsPlan<3000, 200, 1, 3, -1, 2111, 3, 5, 5, 5, 8>;  // passes {3,5} {5} {5} {8}
+
+// inverse-order partners of the sub-plans (first radix = the forward plan's last radix)
+using S128i  = HsPlan<128, 8, 1, 4, -1, 0, 16, 8>;
+using S256i  = S256;
+using S512i  = S512;
+using S1024i = HsPlan<1024, 64, 1, 3, -1, 0, 8, 8, 16>;
+
+enum { CT_4096A = 0, CT_4096B, CT_3000, CT_1024, CT_2048, CT_512, CT_256, CT_8192, CT_B2048, CT_4096X, CT_3000X, CT_4096Y, CT_3000Y, CT_3000Z,
+       CT_T14, CT_T15, CT_T16, CT_T17, CT_T18, CT_T19, CT_T20,
+       CT_S128, CT_S256, CT_S512, CT_S1024, CT_COUNT };

@@ -88,6 +88,14 @@ struct HsLane {
     bool active;
 };
 
+// Hooks a caller may hang into a transform: after the first pass has issued its global loads (their latency
+// hides whatever the hook does) and before the last pass (one shared-memory exchange and the global stores
+// still to come).  The persistent pipeline kernels (hs_pipe.cuh) run their dataflow protocol there.
+struct HsNoHooks {
+    HS_DEVICE void after_first_loads() const {}
+    HS_DEVICE void before_last_pass() const {}
+};
+
 // ---------------------------------------------------------------------------- stage twiddles
 // wv[1..R) <- W_{M R}^{i k}, i = 1..R-1, for flat stage S (radix R on sub-transforms of length M).
 template <class P, int S>
@@ -133,8 +141,8 @@ HS_DEVICE void hs_twiddles(const cplx *HS_RESTRICT tw, const int k, cplx *wv)
 // ST(u, j, k, v)              : element k of the output spectrum (last pass only)
 // u (butterfly slot of this thread) and i/j are compile-time constants after unrolling, so
 // register-to-register hand-over between two transforms (fused Bluestein) stays in registers.
-template <class P, int SGN, int S, class LD, class ST>
-HS_DEVICE void hs_stage(LD &ld, ST &st, const HsLane &ln, const cplx *HS_RESTRICT tw)
+template <class P, int SGN, int S, class LD, class ST, class HK>
+HS_DEVICE void hs_stage(LD &ld, ST &st, const HsLane &ln, const cplx *HS_RESTRICT tw, HK &hk)
 {
     cplx *const sm = ln.sm;
     const int t = ln.t;
@@ -160,6 +168,7 @@ HS_DEVICE void hs_stage(LD &ld, ST &st, const HsLane &ln, const cplx *HS_RESTRIC
             }
         }
     }
+    if constexpr (FIRST) hk.after_first_loads();
     // phase 2: twiddle (reference combine loops) and butterfly, in registers
     HS_UNROLL
     for (int u = 0; u < B; ++u) {
@@ -199,8 +208,8 @@ HS_DEVICE void hs_stage(LD &ld, ST &st, const HsLane &ln, const cplx *HS_RESTRIC
 //   out : A_{m0 RA RB}[q'][k0 + m0 ja + m0 RA jb]              (element o = ja + RA jb)
 // i.e. exactly the reference's two combine loops, with the intermediate state never leaving the
 // thread.  To shared memory it looks like one stage of radix RA*RB (bank_check.py models it so).
-template <class P, int SGN, int F, class LD, class ST>
-HS_DEVICE void hs_stage2(LD &ld, ST &st, const HsLane &ln, const cplx *HS_RESTRICT tw)
+template <class P, int SGN, int F, class LD, class ST, class HK>
+HS_DEVICE void hs_stage2(LD &ld, ST &st, const HsLane &ln, const cplx *HS_RESTRICT tw, HK &hk)
 {
     static_assert(!(F == 0 && LD::kPost), "a loader with an inter-pass twiddle hook needs an unfused first pass");
     cplx *const sm = ln.sm;
@@ -230,6 +239,7 @@ HS_DEVICE void hs_stage2(LD &ld, ST &st, const HsLane &ln, const cplx *HS_RESTRI
             }
         }
     }
+    if constexpr (FIRST) hk.after_first_loads();
     HS_UNROLL
     for (int u = 0; u < B; ++u) {
         const int b = t + P::T * u;
@@ -282,15 +292,16 @@ HS_DEVICE void hs_stage2(LD &ld, ST &st, const HsLane &ln, const cplx *HS_RESTRI
     if (!LAST) HS_SYNC();
 }
 
-template <class P, int SGN, int PASS, class LD, class ST>
-HS_DEVICE void hs_passes_from(LD &ld, ST &st, const HsLane &first, const HsLane &rest, const cplx *tw)
+template <class P, int SGN, int PASS, class LD, class ST, class HK>
+HS_DEVICE void hs_passes_from(LD &ld, ST &st, const HsLane &first, const HsLane &rest, const cplx *tw, HK &hk)
 {
     constexpr int F = P::pass_start(PASS);
     static_assert(P::pass_size(PASS) == 1 || P::pass_size(PASS) == 2, "a pass fuses one or two stages");
     const HsLane &ln = (PASS == 0) ? first : rest;
-    if constexpr (P::pass_size(PASS) == 2) hs_stage2<P, SGN, F>(ld, st, ln, tw);
-    else hs_stage<P, SGN, F>(ld, st, ln, tw);
-    if constexpr (PASS + 1 < P::NPASS) hs_passes_from<P, SGN, PASS + 1>(ld, st, first, rest, tw);
+    if constexpr (PASS > 0 && PASS + 1 == P::NPASS) hk.before_last_pass();
+    if constexpr (P::pass_size(PASS) == 2) hs_stage2<P, SGN, F>(ld, st, ln, tw, hk);
+    else hs_stage<P, SGN, F>(ld, st, ln, tw, hk);
+    if constexpr (PASS + 1 < P::NPASS) hs_passes_from<P, SGN, PASS + 1>(ld, st, first, rest, tw, hk);
 }
 
 // Whole transform for one thread team.  sm: this team's NPAD-point buffer; tw: the plan's device
@@ -301,15 +312,22 @@ HS_DEVICE void hs_fft_team(LD &ld, ST &st, cplx *sm, const cplx *tw, int t, bool
 {
     static_assert(P::pass_start(P::NPASS - 1) + P::pass_size(P::NPASS - 1) == P::NST, "GROUPS must cover every stage");
     const HsLane ln{sm, t, active};
-    hs_passes_from<P, SGN, 0>(ld, st, ln, ln, tw);
+    HsNoHooks hk;
+    hs_passes_from<P, SGN, 0>(ld, st, ln, ln, tw, hk);
 }
 // Same, with a different thread-to-team mapping for the first pass than for the others.
-template <class P, int SGN, class LD, class ST>
-HS_DEVICE void hs_fft_team2(LD &ld, ST &st, const HsLane &first, const HsLane &rest, const cplx *tw)
+template <class P, int SGN, class LD, class ST, class HK>
+HS_DEVICE void hs_fft_team2(LD &ld, ST &st, const HsLane &first, const HsLane &rest, const cplx *tw, HK &hk)
 {
     static_assert(P::pass_start(P::NPASS - 1) + P::pass_size(P::NPASS - 1) == P::NST, "GROUPS must cover every stage");
     static_assert(P::NPASS >= 2, "switching the mapping needs a shared-memory exchange");
-    hs_passes_from<P, SGN, 0>(ld, st, first, rest, tw);
+    hs_passes_from<P, SGN, 0>(ld, st, first, rest, tw, hk);
+}
+template <class P, int SGN, class LD, class ST>
+HS_DEVICE void hs_fft_team2(LD &ld, ST &st, const HsLane &first, const HsLane &rest, const cplx *tw)
+{
+    HsNoHooks hk;
+    hs_fft_team2<P, SGN>(ld, st, first, rest, tw, hk);
 }
 
 // ------------------------------------------------------------------------- plain c2c kernel

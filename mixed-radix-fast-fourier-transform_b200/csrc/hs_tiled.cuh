@@ -19,10 +19,26 @@
 
 typedef hs_tile_geom HsTileGeom; // see hs_abi.h
 
+// Distance (in 16-byte slots) between the buffers of adjacent columns of a tile.  In the passes that map
+// lane -> column, a quarter-warp (one LDS.128 / STS.128 wavefront) holds min(C, 8) columns x 8/min(C, 8)
+// consecutive threads of a team, i.e. slots  col*stride + t  (mod 8 they must all differ): the stride has to be
+// odd for C >= 8, 2 mod 4 for C = 4, 4 mod 8 for C = 2.  (ncu on the first pipeline build, C = 4 with an odd
+// stride: 44 M bank conflicts against 0.5 M, shared-memory wavefronts x 1.7.)
+constexpr int hs_col_stride(int npad, int C)
+{
+    const int want = C >= 8 ? 1 : (C == 4 ? 2 : (C == 2 ? 4 : 0));
+    int s = npad;
+    while (C >= 8 ? (s % 2 == 0) : (want ? (s % (2 * want) != want) : false)) ++s;
+    return s;
+}
+
 // columns per CTA: as many as shared memory and the register file allow (longer contiguous runs on the
 // strided side), 128..512 threads per CTA
 template <class P> struct HsTileCols { static constexpr int C = P::T >= 64 ? (P::N <= 512 ? 8 : 4) : 16; }; // measured: 512-pt 4/8/16 -> 35/40/31 %, 1024-pt 4/8 -> 36/30 % (two-pass, 2^18 / 2^20)
 
+// LDP / STP: residency class of the loads / stores (hs_ld_mp / hs_st_mp in hs_common.cuh): 0 for the stand-alone
+// passes, 1 / 2 inside the persistent pipeline kernels of hs_pipe.cuh.
+template <int LDP = 0>
 struct HsLoadCol {
     static constexpr bool kPost = false;
     const cplx *HS_RESTRICT base; // outer item's base
@@ -34,9 +50,29 @@ struct HsLoadCol {
         const long long e = n * es;
         return off0 + (blk_log ? (e >> blk_log) * blk_stride + (e & ((1LL << blk_log) - 1)) : e);
     }
-    HS_DEVICE cplx operator()(int, int, int n) const { return hs_ld_stream(base + addr(n)); }
+    HS_DEVICE cplx operator()(int, int, int n) const { return hs_ld_mp<LDP>(base + addr(n)); }
 };
-struct HsLoadColTw : HsLoadCol {
+// inter-pass twiddle of element i = b + NB*ii of column k: W^(k b) * (W^(k NB))^ii
+template <int R>
+HS_DEVICE void hs_interpass_twiddle(const cplx w0, const cplx step, cplx *v)
+{
+    cplx s[R];
+    s[1] = step;
+    HS_UNROLL
+    for (int i = 2; i < R; i *= 2) s[i] = hs_mul(s[i / 2], s[i / 2]);
+    HS_UNROLL
+    for (int i = 3; i < R; ++i)
+        if (i & (i - 1)) {
+            int hb = 1;
+            while (hb * 2 <= i) hb *= 2;
+            s[i] = hs_mul(s[hb], s[i - hb]);
+        }
+    v[0] = hs_mul(v[0], w0);
+    HS_UNROLL
+    for (int i = 1; i < R; ++i) v[i] = hs_mul(v[i], hs_mul(w0, s[i]));
+}
+template <int LDP = 0>
+struct HsLoadColTw : HsLoadCol<LDP> {
     static constexpr bool kPost = true;
     const cplx *HS_RESTRICT twb; // already offset by k
     int tw_ld;
@@ -44,33 +80,20 @@ struct HsLoadColTw : HsLoadCol {
     template <int R>
     HS_DEVICE void post(int b, cplx *v) const
     {
-        const cplx w0 = hs_ld_tab(twb + (long long)b * tw_ld);
-        cplx s[R];
-        s[1] = step;
-        HS_UNROLL
-        for (int i = 2; i < R; i *= 2) s[i] = hs_mul(s[i / 2], s[i / 2]);
-        HS_UNROLL
-        for (int i = 3; i < R; ++i)
-            if (i & (i - 1)) {
-                int hb = 1;
-                while (hb * 2 <= i) hb *= 2;
-                s[i] = hs_mul(s[hb], s[i - hb]);
-            }
-        v[0] = hs_mul(v[0], w0);
-        HS_UNROLL
-        for (int i = 1; i < R; ++i) v[i] = hs_mul(v[i], hs_mul(w0, s[i]));
+        hs_interpass_twiddle<R>(hs_ld_tab(twb + (long long)b * tw_ld), step, v);
     }
 };
+template <int STP = 0>
 struct HsStoreCol {
     cplx *HS_RESTRICT base;
     long long es;
-    HS_DEVICE void operator()(int, int, int k, cplx v) const { hs_st_stream(base + k * es, v); }
+    HS_DEVICE void operator()(int, int, int k, cplx v) const { hs_st_mp<STP>(base + k * es, v); }
 };
 
 // Bluestein ends fused into the tiled passes (reference src/highSpeedFFT.c:1803-1827 and :1871-1886):
 // pass 1 of the forward transform loads x[n]*conj(h[n]) (or *h[n]) and the zero padding directly,
 // the last pass of the inverse transform multiplies by the chirp and stores only the N logical outputs.
-template <int CS>
+template <int CS, int LDP = 0>
 struct HsLoadColChirp {
     static constexpr bool kPost = false;
     const cplx *HS_RESTRICT x; // this transform's N logical samples
@@ -81,11 +104,11 @@ struct HsLoadColChirp {
     {
         const long long n = off0 + n_ * es;
         if (n >= N) return hs_c(0.0, 0.0);
-        const cplx xv = hs_ld_stream(x + n), hv = hs_ld_tab(h + n);
+        const cplx xv = hs_ld_mp<LDP>(x + n), hv = hs_ld_tab(h + n);
         return (CS == 1) ? hs_mulc(xv, hv) : hs_mul(xv, hv);
     }
 };
-template <int CS>
+template <int CS, int STP = 0>
 struct HsStoreColChirpCrop {
     cplx *HS_RESTRICT out;
     const cplx *HS_RESTRICT h;
@@ -96,7 +119,7 @@ struct HsStoreColChirpCrop {
         const long long n = off0 + k * es;
         if (n < N) {
             const cplx hv = hs_ld_tab(h + n);
-            hs_st_stream(out + n, (CS == 1) ? hs_mulc(v, hv) : hs_mul(v, hv));
+            hs_st_mp<STP>(out + n, (CS == 1) ? hs_mulc(v, hv) : hs_mul(v, hv));
         }
     }
 };
@@ -104,6 +127,7 @@ struct HsStoreColChirpCrop {
 // c2r merge (reference src/real.c:171-179) fused into pass 1 of the half-length transform: element k of the
 // packed signal is built from bins k and H-k of the Hermitian input on the fly, so the merged signal is
 // never written to HBM.
+template <int LDP = 0>
 struct HsLoadColC2RPre {
     static constexpr bool kPost = false;
     const cplx *HS_RESTRICT x;   // this transform's bins 0..H
@@ -113,65 +137,74 @@ struct HsLoadColC2RPre {
     HS_DEVICE cplx operator()(int, int, int n_) const
     {
         const long long k = off0 + n_ * es;
-        const cplx a = hs_ld_stream(x + k), c = hs_ld_stream(x + (H - k)), w = hs_ld_tab(tw2 + k);
+        const cplx a = hs_ld_mp<LDP>(x + k), c = hs_ld_mp<LDP>(x + (H - k)), w = hs_ld_tab(tw2 + k);
         const double t1 = -a.y - c.y, t2 = -c.x + a.x;
         return hs_c(a.x + c.x + (t1 * w.x) - (t2 * w.y), a.y - c.y + (t2 * w.x) + (t1 * w.y));
     }
 };
 
+// One tile: C adjacent columns c0..c0+C-1 of one outer item, whose input / output start at in_x / out_x.
 // P: plan of the sub-transform (P::X is ignored); C: columns per CTA; TW: inter-pass twiddle on load
-// (0 none, 1 keyed by the column, 2 keyed by the outer item); STCOL: stores keep lane = column
+// (0 none, 1 keyed by the column, 2 keyed by the outer item xf); STCOL: stores keep lane = column
 // instead of switching to lane = thread of a team (contiguous output rows).
 // IO: 0 plain; 1 chirp-and-pad load (CS = chirp direction); 2 chirp-and-crop store; 3 c2r merge on load.
+// tid: thread index in the tile's team of P::T*C threads; on: false for threads (or whole CTAs) that only
+// take part in the barriers.
+template <class P, int SGN, int C, int TW, bool STCOL, int IO, int CS, int LDP, int STP, class HK>
+HS_DEVICE void hs_tile_run(const cplx *HS_RESTRICT in_x, cplx *HS_RESTRICT out_x, const cplx *HS_RESTRICT tw, const HsTileGeom &g,
+                           const long long xf, const int c0, cplx *smem, const int tid, const bool on, HK &hk)
+{
+    constexpr int NPADC = hs_col_stride(P::NPAD, C);
+    const int colA = tid % C, tA = tid / C;       // lane = column
+    const int colB = tid / P::T, tB = tid % P::T; // lane = thread of a team
+    const HsLane first{smem + colA * NPADC, tA, on};
+    const HsLane rest = STCOL ? first : HsLane{smem + colB * NPADC, tB, on};
+    const int colS = STCOL ? colA : colB;
+    if constexpr (IO == 1) { // forward pass 1 of the long Bluestein
+        HsStoreCol<STP> st{out_x + (long long)(c0 + colS) * g.out_c, g.out_e};
+        HsLoadColChirp<CS, LDP> ld{in_x, (const cplx *)g.chirp, g.nlog, (long long)(c0 + colA) * g.in_c, g.in_e};
+        hs_fft_team2<P, SGN>(ld, st, first, rest, tw, hk);
+    } else if constexpr (IO == 3) { // c2r: merge fused into pass 1 (g.chirp = twiddle2, g.nlog = H)
+        HsStoreCol<STP> st{out_x + (long long)(c0 + colS) * g.out_c, g.out_e};
+        HsLoadColC2RPre<LDP> ld{in_x, (const cplx *)g.chirp, g.nlog, (long long)(c0 + colA) * g.in_c, g.in_e};
+        hs_fft_team2<P, SGN>(ld, st, first, rest, tw, hk);
+    } else if constexpr (IO == 2) { // inverse last pass of the long Bluestein
+        static_assert(TW != 0, "the chirp-and-crop store belongs to a second pass");
+        HsStoreColChirpCrop<CS, STP> st{out_x, (const cplx *)g.chirp, g.nlog, (long long)(c0 + colS) * g.out_c, g.out_e};
+        const long long k = (TW == 1) ? (long long)(c0 + colA) : xf;
+        HsLoadColTw<LDP> ld;
+        ld.base = in_x; ld.off0 = (long long)(c0 + colA) * g.in_c; ld.es = g.in_e;
+        ld.blk_log = g.blk_log; ld.blk_stride = g.blk_stride;
+        ld.twb = (const cplx *)g.twb + k; ld.tw_ld = g.tw_ld; ld.step = on ? hs_ld_tab((const cplx *)g.tws + k) : hs_c(0.0, 0.0);
+        hs_fft_team2<P, SGN>(ld, st, first, rest, tw, hk);
+    } else if constexpr (TW != 0) {
+        HsStoreCol<STP> st{out_x + (long long)(c0 + colS) * g.out_c, g.out_e};
+        const long long k = (TW == 1) ? (long long)(c0 + colA) : xf;
+        HsLoadColTw<LDP> ld;
+        ld.base = in_x; ld.off0 = (long long)(c0 + colA) * g.in_c; ld.es = g.in_e;
+        ld.blk_log = g.blk_log; ld.blk_stride = g.blk_stride;
+        ld.twb = (const cplx *)g.twb + k; ld.tw_ld = g.tw_ld; ld.step = on ? hs_ld_tab((const cplx *)g.tws + k) : hs_c(0.0, 0.0);
+        hs_fft_team2<P, SGN>(ld, st, first, rest, tw, hk);
+    } else {
+        HsStoreCol<STP> st{out_x + (long long)(c0 + colS) * g.out_c, g.out_e};
+        HsLoadCol<LDP> ld;
+        ld.base = in_x; ld.off0 = (long long)(c0 + colA) * g.in_c; ld.es = g.in_e;
+        ld.blk_log = g.blk_log; ld.blk_stride = g.blk_stride;
+        hs_fft_team2<P, SGN>(ld, st, first, rest, tw, hk);
+    }
+}
+
+// Stand-alone pass: one CTA per tile.
 template <class P, int SGN, int C, int TW, bool STCOL, int MINB, int IO = 0, int CS = 1>
 HS_GLOBAL void HS_LAUNCH_BOUNDS(P::T *C, MINB)
 hs_tiled_kernel(const cplx *HS_RESTRICT in, cplx *HS_RESTRICT out, const cplx *HS_RESTRICT tw, const HsTileGeom g, long long howmany)
 {
-    constexpr int NPADC = P::NPAD | 1; // odd: columns side by side in lanes hit different banks
     HS_DYN_SMEM(cplx, smem);
     const int tiles = g.ncols / C;
     const long long xf = HS_BID / tiles;
     const int c0 = (int)(HS_BID % tiles) * C;
-    const int colA = HS_TID % C, tA = HS_TID / C; // lane = column
-    const int colB = HS_TID / P::T, tB = HS_TID % P::T; // lane = thread of a team
-    const HsLane first{smem + colA * NPADC, tA, true};
-    const HsLane rest = STCOL ? first : HsLane{smem + colB * NPADC, tB, true};
-    const int colS = STCOL ? colA : colB;
-    if constexpr (IO == 1) { // forward pass 1 of the long Bluestein
-        HsStoreCol st{out + xf * g.out_xf + (long long)(c0 + colS) * g.out_c, g.out_e};
-        HsLoadColChirp<CS> ld{in + xf * g.in_xf, (const cplx *)g.chirp, g.nlog, (long long)(c0 + colA) * g.in_c, g.in_e};
-        hs_fft_team2<P, SGN>(ld, st, first, rest, tw);
-        return;
-    } else if constexpr (IO == 3) { // c2r: merge fused into pass 1 (g.chirp = twiddle2, g.nlog = H)
-        HsStoreCol st{out + xf * g.out_xf + (long long)(c0 + colS) * g.out_c, g.out_e};
-        HsLoadColC2RPre ld{in + xf * g.in_xf, (const cplx *)g.chirp, g.nlog, (long long)(c0 + colA) * g.in_c, g.in_e};
-        hs_fft_team2<P, SGN>(ld, st, first, rest, tw);
-        return;
-    } else if constexpr (IO == 2) { // inverse last pass of the long Bluestein
-        static_assert(TW != 0, "the chirp-and-crop store belongs to a second pass");
-        HsStoreColChirpCrop<CS> st{out + xf * g.out_xf, (const cplx *)g.chirp, g.nlog, (long long)(c0 + colS) * g.out_c, g.out_e};
-        const long long k = (TW == 1) ? (long long)(c0 + colA) : xf;
-        HsLoadColTw ld;
-        ld.base = in + xf * g.in_xf; ld.off0 = (long long)(c0 + colA) * g.in_c; ld.es = g.in_e;
-        ld.blk_log = g.blk_log; ld.blk_stride = g.blk_stride;
-        ld.twb = (const cplx *)g.twb + k; ld.tw_ld = g.tw_ld; ld.step = hs_ld_tab((const cplx *)g.tws + k);
-        hs_fft_team2<P, SGN>(ld, st, first, rest, tw);
-        return;
-    }
-    HsStoreCol st{out + xf * g.out_xf + (long long)(c0 + colS) * g.out_c, g.out_e};
-    if constexpr (TW != 0) {
-        const long long k = (TW == 1) ? (long long)(c0 + colA) : xf;
-        HsLoadColTw ld;
-        ld.base = in + xf * g.in_xf; ld.off0 = (long long)(c0 + colA) * g.in_c; ld.es = g.in_e;
-        ld.blk_log = g.blk_log; ld.blk_stride = g.blk_stride;
-        ld.twb = (const cplx *)g.twb + k; ld.tw_ld = g.tw_ld; ld.step = hs_ld_tab((const cplx *)g.tws + k);
-        hs_fft_team2<P, SGN>(ld, st, first, rest, tw);
-    } else {
-        HsLoadCol ld;
-        ld.base = in + xf * g.in_xf; ld.off0 = (long long)(c0 + colA) * g.in_c; ld.es = g.in_e;
-        ld.blk_log = g.blk_log; ld.blk_stride = g.blk_stride;
-        hs_fft_team2<P, SGN>(ld, st, first, rest, tw);
-    }
+    HsNoHooks hk;
+    hs_tile_run<P, SGN, C, TW, STCOL, IO, CS, 0, 0>(in + xf * g.in_xf, out + xf * g.out_xf, tw, g, xf, c0, smem, HS_TID, true, hk);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -196,27 +229,13 @@ struct HsLoadTileTw : HsLoadTile {
     template <int R>
     HS_DEVICE void post(int b, cplx *v) const
     {
-        const cplx w0 = hs_ld_tab(twb + (long long)b * tw_ld);
-        cplx s[R];
-        s[1] = step;
-        HS_UNROLL
-        for (int i = 2; i < R; i *= 2) s[i] = hs_mul(s[i / 2], s[i / 2]);
-        HS_UNROLL
-        for (int i = 3; i < R; ++i)
-            if (i & (i - 1)) {
-                int hb = 1;
-                while (hb * 2 <= i) hb *= 2;
-                s[i] = hs_mul(s[hb], s[i - hb]);
-            }
-        v[0] = hs_mul(v[0], w0);
-        HS_UNROLL
-        for (int i = 1; i < R; ++i) v[i] = hs_mul(v[i], hs_mul(w0, s[i]));
+        hs_interpass_twiddle<R>(hs_ld_tab(twb + (long long)b * tw_ld), step, v);
     }
 };
 
 template <class P, int C>
 struct HsTmaTileSmem {
-    static constexpr int NPADC = P::NPAD | 1;
+    static constexpr int NPADC = hs_col_stride(P::NPAD, C);
     static constexpr int tile_elems = P::N * C;
     static constexpr int bytes = (2 * tile_elems + C * NPADC) * 16 + 64;
 };
@@ -226,7 +245,7 @@ HS_GLOBAL void HS_LAUNCH_BOUNDS(P::T *C, 1)
 hs_tiled_tma_kernel(const HS_GRID_CONSTANT HsTmap tmap, cplx *HS_RESTRICT out, const cplx *HS_RESTRICT tw, const HsTileGeom g, long long howmany)
 {
     constexpr int BOXR = P::N < 256 ? P::N : 256; // rows per TMA box (hardware limit 256 per dimension)
-    constexpr int NPADC = P::NPAD | 1;
+    constexpr int NPADC = hs_col_stride(P::NPAD, C);
     constexpr int TE = P::N * C;             // elements of one staged tile
     constexpr unsigned ROWB = C * 16;        // bytes of one row
     HS_DYN_SMEM(cplx, smem);
@@ -263,7 +282,7 @@ hs_tiled_tma_kernel(const HS_GRID_CONSTANT HsTmap tmap, cplx *HS_RESTRICT out, c
         const long long xf = tile_id / tiles;
         const int c0 = (int)(tile_id % tiles) * C;
         const cplx *stage = buf ? stage1 : stage0;
-        HsStoreCol st{out + xf * g.out_xf + (long long)(c0 + colS) * g.out_c, g.out_e};
+        HsStoreCol<0> st{out + xf * g.out_xf + (long long)(c0 + colS) * g.out_c, g.out_e};
         if constexpr (TW != 0) {
             const long long k = (TW == 1) ? (long long)(c0 + colA) : xf;
             HsLoadTileTw ld;
@@ -296,6 +315,19 @@ struct HsStoreRegsMulCol {
         y[u][j] = (CS == 1) ? hs_mul(v, hv) : hs_mulc(v, hv);
     }
 };
+// hook adapters for two transforms back to back: only the first one's loads and the second one's last pass count
+template <class HK>
+struct HsFirstHook {
+    HK &h;
+    HS_DEVICE void after_first_loads() { h.after_first_loads(); }
+    HS_DEVICE void before_last_pass() {}
+};
+template <class HK>
+struct HsLastHook {
+    HK &h;
+    HS_DEVICE void after_first_loads() {}
+    HS_DEVICE void before_last_pass() { h.before_last_pass(); }
+};
 template <int RL>
 struct HsLoadRegsCol {
     static constexpr bool kPost = false;
@@ -303,35 +335,45 @@ struct HsLoadRegsCol {
     HS_DEVICE cplx operator()(int u, int i, int) const { return y[u][i]; }
 };
 
-template <class PF, class PI, int CS, int C, int MINB>
-HS_GLOBAL void HS_LAUNCH_BOUNDS(PF::T *C, MINB)
-hs_blu_mid_kernel(const cplx *HS_RESTRICT in, cplx *HS_RESTRICT out, const cplx *HS_RESTRICT twf, const cplx *HS_RESTRICT twi,
-                  const HsTileGeom g, const cplx *HS_RESTRICT hk, long long howmany)
+template <class PF, class PI, int CS, int C, int LDP, int STP, class HK>
+HS_DEVICE void hs_blu_mid_run(const cplx *HS_RESTRICT in_x, cplx *HS_RESTRICT out_x, const cplx *HS_RESTRICT twf, const cplx *HS_RESTRICT twi,
+                              const HsTileGeom &g, const cplx *HS_RESTRICT hk, const int c0, cplx *smem, const int tid, const bool on, HK &hooks)
 {
     static_assert(PF::N == PI::N && PF::T == PI::T && PF::NPAD == PI::NPAD, "plans must pair");
     constexpr int RL = PF::radix(PF::NST - 1);
     static_assert(PI::radix(0) == RL && PF::pass_size(PF::NPASS - 1) == 1 && PI::pass_size(0) == 1, "register hand-over needs matching radices");
     constexpr int NB = PF::N / RL, B = (NB + PF::T - 1) / PF::T;
-    constexpr int NPADC = PF::NPAD | 1;
+    constexpr int NPADC = hs_col_stride(PF::NPAD, C);
+    const int colA = tid % C, tA = tid / C;         // lane = column
+    const int colB = tid / PF::T, tB = tid % PF::T; // lane = thread of a team
+    const HsLane laneA{smem + colA * NPADC, tA, on}, laneB{smem + colB * NPADC, tB, on};
+    cplx y[B][RL];
+
+    const long long k = c0 + colA;
+    HsLoadColTw<LDP> ld;
+    ld.base = in_x; ld.off0 = k * g.in_c; ld.es = g.in_e; ld.blk_log = 0; ld.blk_stride = 0;
+    ld.twb = (const cplx *)g.twb + k; ld.tw_ld = g.tw_ld; ld.step = on ? hs_ld_tab((const cplx *)g.tws + k) : hs_c(0.0, 0.0);
+    HsStoreRegsMulCol<CS, RL> st{y, hk + k, (long long)g.ncols}; // Hk[k + n1 j]
+    HsFirstHook<HK> h1{hooks}; // the forward transform loads from memory, the inverse one stores to it
+    hs_fft_team2<PF, 1>(ld, st, laneA, laneA, twf, h1);
+    HS_SYNC();
+    HsLoadRegsCol<RL> ld2{y};
+    HsStoreCol<STP> st2{out_x + (long long)(c0 + colB) * g.out_c, g.out_e};
+    HsLastHook<HK> h2{hooks};
+    hs_fft_team2<PI, -1>(ld2, st2, laneA, laneB, twi, h2);
+}
+
+template <class PF, class PI, int CS, int C, int MINB>
+HS_GLOBAL void HS_LAUNCH_BOUNDS(PF::T *C, MINB)
+hs_blu_mid_kernel(const cplx *HS_RESTRICT in, cplx *HS_RESTRICT out, const cplx *HS_RESTRICT twf, const cplx *HS_RESTRICT twi,
+                  const HsTileGeom g, const cplx *HS_RESTRICT hk, long long howmany)
+{
     HS_DYN_SMEM(cplx, smem);
     const int tiles = g.ncols / C;
     const long long xf = HS_BID / tiles;
     const int c0 = (int)(HS_BID % tiles) * C;
-    const int colA = HS_TID % C, tA = HS_TID / C;         // lane = column
-    const int colB = HS_TID / PF::T, tB = HS_TID % PF::T; // lane = thread of a team
-    const HsLane laneA{smem + colA * NPADC, tA, true}, laneB{smem + colB * NPADC, tB, true};
-    cplx y[B][RL];
-
-    const long long k = c0 + colA;
-    HsLoadColTw ld;
-    ld.base = in + xf * g.in_xf; ld.off0 = k * g.in_c; ld.es = g.in_e; ld.blk_log = 0; ld.blk_stride = 0;
-    ld.twb = (const cplx *)g.twb + k; ld.tw_ld = g.tw_ld; ld.step = hs_ld_tab((const cplx *)g.tws + k);
-    HsStoreRegsMulCol<CS, RL> st{y, hk + k, (long long)g.ncols}; // Hk[k + n1 j]
-    hs_fft_team2<PF, 1>(ld, st, laneA, laneA, twf);
-    HS_SYNC();
-    HsLoadRegsCol<RL> ld2{y};
-    HsStoreCol st2{out + xf * g.out_xf + (long long)(c0 + colB) * g.out_c, g.out_e};
-    hs_fft_team2<PI, -1>(ld2, st2, laneA, laneB, twi);
+    HsNoHooks hooks;
+    hs_blu_mid_run<PF, PI, CS, C, 0, 0>(in + xf * g.in_xf, out + xf * g.out_xf, twf, twi, g, hk, c0, smem, HS_TID, true, hooks);
 }
 
 // Four-step exchange twiddle (north_star config 5): b[k1][c] *= W_N^{(c0 + c) k1}, N = 2^logN, from two

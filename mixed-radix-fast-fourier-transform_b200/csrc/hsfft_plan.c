@@ -218,6 +218,81 @@ static void *upload_stage_twiddles(const int *rx, int nst, int sgn, int split_mi
     return d;
 }
 
+/* ------------------------------------------------------------------------- persistent pipelines */
+
+enum { HS_PIPE_V_C2C = 0, HS_PIPE_V_C2R = 1, HS_PIPE_V_R2C = 2, HS_PIPE_V_BLU = 3 };
+
+static int pipe_enabled(void)
+{
+    const char *e = getenv("HSFFT_PIPE");
+    return !e || atoi(e) != 0;
+}
+
+static int pipe_available(int tp_id, int variant, int sgn)
+{
+    hs_pipe_args a;
+    memset(&a, 0, sizeof a);
+    a.nphase = (variant == HS_PIPE_V_C2C || variant == HS_PIPE_V_C2R) ? 2 : 3;
+    for (int j = 0; j < HS_PIPE_MAX_PHASE; ++j) a.ph[j].g.ncols = 1 << 20;
+    return hs_cu_launch_pipe(tp_id, variant, sgn, &a, NULL, 1);
+}
+
+static int env_int(const char *name, int dflt)
+{
+    const char *e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
+void hs_pipe_shape(long long len, long long howmany, int *G, int *lag, int *nslot)
+{
+    /* A slot holds the tiles that are in flight between two phases (resident CTAs x 64 KiB tiles, about 16 MiB);
+     * lag 1 and three slots keep every dependency one full round (two slots' worth of tickets) behind the
+     * tile that needs it, so the acquire polls of hs_pipe_kernel find their counters already full. */
+    const long long slot_bytes = (long long)env_int("HSFFT_PIPE_SLOT_KB", 16384) << 10;
+    long long g = slot_bytes / (len * (long long)sizeof(fft_data));
+    if (g < 1) g = 1;
+    if (g > howmany) g = howmany;
+    *G = (int)g;
+    *lag = env_int("HSFFT_PIPE_LAG", 1);
+    if (*lag < 1) *lag = 1;
+    *nslot = env_int("HSFFT_PIPE_NSLOT", *lag + 2);
+    if (*nslot < *lag + 1) *nslot = *lag + 1;
+}
+
+static size_t pipe_ctl_bytes(long long howmany, int G)
+{
+    const long long ngroups = (howmany + G - 1) / G;
+    return (HS_PIPE_CTL_BYTES(ngroups) + 255) & ~(size_t)255;
+}
+
+size_t hs_pipe_ws_bytes(long long len, int nrings, long long howmany)
+{
+    int G, lag, nslot;
+    hs_pipe_shape(len, howmany, &G, &lag, &nslot);
+    return pipe_ctl_bytes(howmany, G) + (size_t)nrings * nslot * G * len * sizeof(fft_data);
+}
+
+/* ctl words and rings carved out of the workspace */
+static void pipe_layout(hs_pipe_args *a, void *ws, long long len, int nrings, long long howmany)
+{
+    hs_pipe_shape(len, howmany, &a->G, &a->lag, &a->nslot);
+    a->howmany = howmany;
+    a->ctl = ws;
+    char *ring = (char *)ws + pipe_ctl_bytes(howmany, a->G);
+    for (int r = 0; r < nrings; ++r) a->ring[r] = ring + (size_t)r * a->nslot * a->G * len * sizeof(fft_data);
+}
+
+/* the two passes of a compile-time two-pass plan as phases 0 and 1 */
+static void pipe_twopass_phases(const hs_c2c *p, hs_pipe_args *a)
+{
+    hs_tile_geom *g0 = &a->ph[0].g, *g1 = &a->ph[1].g;
+    g0->ncols = p->n2; g0->in_c = 1; g0->in_e = p->n2; g0->out_c = p->n1; g0->out_e = 1; g0->in_xf = p->n; g0->out_xf = p->n;
+    a->ph[0].tw = p->d_tw;
+    g1->ncols = p->n1; g1->in_c = 1; g1->in_e = p->n1; g1->out_c = 1; g1->out_e = p->n1; g1->in_xf = p->n; g1->out_xf = p->n;
+    g1->twb = p->d_twb; g1->tws = p->d_tws; g1->tw_ld = p->n1;
+    a->ph[1].tw = p->d_tw2;
+}
+
 hs_c2c *hs_c2c_create(int n, int sgn)
 {
     hs_c2c *p = (hs_c2c *)calloc(1, sizeof(hs_c2c));
@@ -237,6 +312,9 @@ hs_c2c *hs_c2c_create(int n, int sgn)
         /* n = n1 * n2: pass 1 = n2 strided transforms of length n1, pass 2 = n1 of length n2 with the
          * inter-pass twiddle W_n^{i k} applied on load as W_n^{k b} * (W_n^{k NB})^ii, i = b + NB ii */
         p->tp_id = ct->id;
+        p->n1 = ct->n1;
+        p->n2 = ct->n2;
+        p->pipe = pipe_enabled() && pipe_available(ct->id, HS_PIPE_V_C2C, sgn);
         p->d_tw = upload_stage_twiddles(ct->radix, ct->nst, sgn, ct->split_min);
         p->d_tw2 = upload_stage_twiddles(ct->radix2, ct->nst2, sgn, ct->split_min2);
         const int NB = ct->n2 / ct->radix2[0], K = ct->n1;
@@ -390,6 +468,7 @@ void hs_c2c_destroy(hs_c2c *p)
 
 size_t hs_c2c_ws_elems(const hs_c2c *p, long long howmany)
 {
+    if (p->tp_id >= 0 && p->pipe) return (hs_pipe_ws_bytes(p->n, 2, howmany) + sizeof(fft_data) - 1) / sizeof(fft_data);
     if (p->tp_id >= 0) return (size_t)howmany * p->n;
     return (p->ct_id < 0 && p->npass > 1) ? (size_t)howmany * p->n : 0;
 }
@@ -398,6 +477,16 @@ void hs_c2c_exec(const hs_c2c *p, const void *d_in, void *d_out, void *d_ws, lon
 {
     if (howmany <= 0) return;
     if (p->ct_id >= 0) { hs_cu_launch_ct_c2c(p->ct_id, p->sgn, d_in, d_out, p->d_tw, howmany, stream); return; }
+    if (p->tp_id >= 0 && p->pipe) {
+        hs_pipe_args a;
+        memset(&a, 0, sizeof a);
+        a.nphase = 2;
+        pipe_twopass_phases(p, &a);
+        pipe_layout(&a, d_ws, p->n, 1, howmany);
+        a.in = d_in; a.out = d_out;
+        hs_cu_launch_pipe(p->tp_id, HS_PIPE_V_C2C, p->sgn, &a, stream, 0);
+        return;
+    }
     if (p->tp_id >= 0) {
         hs_cu_launch_ct_twopass(p->tp_id, 1, p->sgn, d_in, d_ws, p->d_tw, NULL, NULL, howmany, stream);
         hs_cu_launch_ct_twopass(p->tp_id, 2, p->sgn, d_ws, d_out, p->d_tw2, p->d_twb, p->d_tws, howmany, stream);
@@ -489,6 +578,8 @@ static void dev_build(hs_dev_obj *d, fft_object plan)
         int inv2[8];
         for (int s = 0; s < s2->nst; ++s) inv2[s] = s2->radix[s2->nst - 1 - s];
         d->big = 1; d->big_n1 = n1; d->big_n2 = n2; d->big_sub1 = s1->id; d->big_sub2 = s2->id;
+        d->big_tp_id = tp->id;
+        d->big_pipe = pipe_enabled() && pipe_available(tp->id, HS_PIPE_V_BLU, d->sgn);
         d->d_big_f1 = upload_stage_twiddles(s1->radix, s1->nst, 1, s1->split_min);
         d->d_big_f2 = upload_stage_twiddles(s2->radix, s2->nst, 1, s2->split_min);
         d->d_big_i1 = upload_stage_twiddles(inv2, s2->nst, -1, s2->split_min);
@@ -592,6 +683,7 @@ size_t hs_dev_ws_bytes(const hs_dev_obj *d, long long howmany)
 {
     if (d->lt == 0) return hs_c2c_ws_elems(d->direct, howmany) * sizeof(fft_data);
     if (d->blu_ct_id >= 0) return 0;
+    if (d->big && d->big_pipe) return hs_pipe_ws_bytes(d->M, 2, howmany);
     if (d->big) return (size_t)2 * (howmany < d->big_chunk ? howmany : d->big_chunk) * d->M * sizeof(fft_data);
     return ((size_t)2 * howmany * d->M + hs_c2c_ws_elems(d->fwdM, howmany)) * sizeof(fft_data);
 }
@@ -617,6 +709,18 @@ void hs_dev_exec(hs_dev_obj *d, const void *d_in, void *d_out, void *d_ws, long 
         gb.twb = d->d_big_fb; gb.tws = d->d_big_fs; gb.tw_ld = (int)n1;
         gc.ncols = (int)n2; gc.in_xf = M; gc.in_c = 1; gc.in_e = n2; gc.out_xf = N; gc.out_c = 1; gc.out_e = n2;
         gc.twb = d->d_big_ib; gc.tws = d->d_big_is; gc.tw_ld = (int)n2; gc.chirp = d->d_chirp; gc.nlog = (int)N;
+        if (d->big_pipe) { /* one persistent kernel, both M-point intermediates stay in L2 */
+            hs_pipe_args a;
+            memset(&a, 0, sizeof a);
+            a.nphase = 3;
+            a.ph[0].g = ga; a.ph[0].tw = d->d_big_f1;
+            a.ph[1].g = gb; a.ph[1].tw = d->d_big_f2; a.ph[1].tw_b = d->d_big_i1; a.ph[1].aux = d->d_hk;
+            a.ph[2].g = gc; a.ph[2].tw = d->d_big_i2;
+            pipe_layout(&a, d_ws, M, 2, howmany);
+            a.in = d_in; a.out = d_out;
+            hs_cu_launch_pipe(d->big_tp_id, HS_PIPE_V_BLU, d->sgn, &a, stream, 0);
+            return;
+        }
         for (long long first = 0; first < howmany; first += chunk) {
             const long long cnt = (first + chunk <= howmany) ? chunk : howmany - first;
             const fft_data *x = (const fft_data *)d_in + first * N;
@@ -634,6 +738,43 @@ void hs_dev_exec(hs_dev_obj *d, const void *d_in, void *d_out, void *d_ws, long 
     hs_cu_launch_spectrum_mul(d->sgn, b, d->d_hk, d->M, howmany, stream);
     hs_c2c_exec(d->invM, b, a, c, howmany, stream);
     hs_cu_launch_chirp_crop(d->sgn, a, d_out, d->d_chirp, d->N, d->M, howmany, stream);
+}
+
+int hs_dev_has_pipe(const hs_dev_obj *d, int variant)
+{
+    if (d->lt != 0 || !d->direct || d->direct->tp_id < 0 || !d->direct->pipe) return 0;
+    return pipe_available(d->direct->tp_id, variant, d->direct->sgn);
+}
+
+int hs_dev_exec_r2c_pipe(hs_dev_obj *d, const void *d_in, void *d_out, long long out_stride, int full, const void *d_tw2, void *d_ws,
+                         long long howmany, void *stream)
+{
+    if (!hs_dev_has_pipe(d, HS_PIPE_V_R2C)) return 0;
+    const hs_c2c *p = d->direct;
+    hs_pipe_args a;
+    memset(&a, 0, sizeof a);
+    a.nphase = 3;
+    pipe_twopass_phases(p, &a);
+    a.ph[2].g.ncols = 1; a.ph[2].g.in_xf = p->n; a.ph[2].g.out_xf = out_stride; a.ph[2].g.chirp = d_tw2; a.ph[2].g.nlog = p->n;
+    a.ph[2].flags = full ? 1 : 0;
+    pipe_layout(&a, d_ws, p->n, 2, howmany);
+    a.in = d_in; a.out = d_out;
+    return hs_cu_launch_pipe(p->tp_id, HS_PIPE_V_R2C, p->sgn, &a, stream, 0);
+}
+
+int hs_dev_exec_c2r_pipe(hs_dev_obj *d, const void *d_spec, long long in_stride, const void *d_tw2, void *d_out, void *d_ws,
+                         long long howmany, void *stream)
+{
+    if (!hs_dev_has_pipe(d, HS_PIPE_V_C2R)) return 0;
+    const hs_c2c *p = d->direct;
+    hs_pipe_args a;
+    memset(&a, 0, sizeof a);
+    a.nphase = 2;
+    pipe_twopass_phases(p, &a);
+    a.ph[0].g.in_xf = in_stride; a.ph[0].g.chirp = d_tw2; a.ph[0].g.nlog = p->n;
+    pipe_layout(&a, d_ws, p->n, 1, howmany);
+    a.in = d_spec; a.out = d_out;
+    return hs_cu_launch_pipe(p->tp_id, HS_PIPE_V_C2R, p->sgn, &a, stream, 0);
 }
 
 int hs_dev_exec_c2r_fused(hs_dev_obj *d, const void *d_spec, long long in_stride, const void *d_tw2, void *d_out, void *d_ws,
@@ -777,15 +918,17 @@ const char *hsfft_plan_describe(fft_object obj)
     if (d->lt == 0) {
         const hs_c2c *p = d->direct;
         if (p->ct_id >= 0) n = snprintf(buf, sizeof buf, "mixed-radix N=%d: compile-time smem kernel #%d", d->N, p->ct_id);
-        else if (p->tp_id >= 0) n = snprintf(buf, sizeof buf, "mixed-radix N=%d: compile-time two-pass kernels #%d", d->N, p->tp_id);
+        else if (p->tp_id >= 0)
+            n = snprintf(buf, sizeof buf, "mixed-radix N=%d: compile-time two-pass kernels #%d%s", d->N, p->tp_id,
+                         p->pipe ? " as one persistent L2-resident pipeline" : "");
         else {
             n = snprintf(buf, sizeof buf, "mixed-radix N=%d: %d run-time pass(es):", d->N, p->npass);
             for (int g = 0; g < p->npass && n < (int)sizeof buf - 32; ++g)
                 n += snprintf(buf + n, sizeof buf - n, " [n=%d C=%d]", p->pass[g].n, p->pass[g].C);
         }
     } else if (d->big)
-        n = snprintf(buf, sizeof buf, "bluestein N=%d M=%d=%dx%d: 3 fused tiled kernels, %lld transforms per L2-resident chunk", d->N, d->M,
-                     d->big_n1, d->big_n2, d->big_chunk);
+        n = snprintf(buf, sizeof buf, "bluestein N=%d M=%d=%dx%d: 3 fused tiled kernels%s", d->N, d->M, d->big_n1, d->big_n2,
+                     d->big_pipe ? " as one persistent L2-resident pipeline" : "");
     else if (d->blu_ct_id >= 0)
         n = snprintf(buf, sizeof buf, "bluestein N=%d M=%d: fused compile-time kernel #%d", d->N, d->M, d->blu_ct_id);
     else

@@ -18,6 +18,7 @@
 #include "hs_generic.cuh"
 #include "hs_smem_fft.cuh"
 #include "hs_tiled.cuh"
+#include "hs_pipe.cuh"
 
 typedef void *hs_stream_t;
 static std::atomic<long long> g_launches{0};
@@ -46,7 +47,7 @@ static void launch_blu_mid(const void *in, void *out, const void *twf, const voi
                            long long howmany, hs_stream_t)
 {
     constexpr int C = HsTileCols<PF>::C;
-    constexpr int smem = C * (PF::NPAD | 1) * (int)sizeof(cplx);
+    constexpr int smem = C * hs_col_stride(PF::NPAD, C) * (int)sizeof(cplx);
     hs_emu_launch(hs_blu_mid_kernel<PF, PI, CS, C, 1>, howmany * (g.ncols / C), PF::T * C, smem, (const cplx *)in, (cplx *)out,
                   (const cplx *)twf, (const cplx *)twi, g, (const cplx *)hk, howmany);
     ++g_launches;
@@ -66,13 +67,26 @@ static void launch_tiled(const void *in, void *out, const void *tw, const HsTile
             return;
         }
     }
-    constexpr int smem = C * (P::NPAD | 1) * (int)sizeof(cplx);
+    constexpr int smem = C * hs_col_stride(P::NPAD, C) * (int)sizeof(cplx);
     hs_emu_launch(hs_tiled_kernel<P, SGN, C, TW, STCOL, 1, IO, CS>, howmany * (g.ncols / C), P::T * C, smem, (const cplx *)in, (cplx *)out,
                   (const cplx *)tw, g, howmany);
     ++g_launches;
 }
 
 #include "hs_ct_table.cuh"
+
+// persistent pipelines: CTAs run one after another here, so the first one drains the ticket counter; the
+// emulation checks the ticket order (a dependency that is not met aborts), the geometry and the numerics
+template <class PH0, class PH1, class PH2, int MINB>
+static void launch_pipe(hs_pipe_args &a, hs_stream_t)
+{
+    using SH = HsPipeShape<PH0, PH1, PH2>;
+    const long long ngroups = (a.howmany + a.G - 1) / a.G;
+    memset(a.ctl, 0, HS_PIPE_CTL_BYTES(ngroups));
+    hs_emu_launch(hs_pipe_kernel<PH0, PH1, PH2, MINB>, 2, SH::NT, SH::SMEM, a);
+    ++g_launches;
+}
+#include "hs_pipe_table.cuh"
 
 extern "C" {
 int hs_cu_device_count(void) { return 1; }
@@ -98,6 +112,20 @@ void hs_cu_stream_wait_event(void *, void *) {}
 float hs_cu_event_elapsed_ms(void *, void *) { return 0.f; }
 void hs_cu_event_sync(void *) {}
 long long hs_cu_launch_count(void) { return g_launches.load(); }
+
+int hs_cu_launch_pipe(int tp_id, int variant, int sgn, hs_pipe_args *a, void *stream, int query)
+{
+    switch (tp_id) {
+    case CT_T14: return pipe_dispatch<CT_T14>(variant, sgn, *a, stream, query != 0);
+    case CT_T15: return pipe_dispatch<CT_T15>(variant, sgn, *a, stream, query != 0);
+    case CT_T16: return pipe_dispatch<CT_T16>(variant, sgn, *a, stream, query != 0);
+    case CT_T17: return pipe_dispatch<CT_T17>(variant, sgn, *a, stream, query != 0);
+    case CT_T18: return pipe_dispatch<CT_T18>(variant, sgn, *a, stream, query != 0);
+    case CT_T19: return pipe_dispatch<CT_T19>(variant, sgn, *a, stream, query != 0);
+    case CT_T20: return pipe_dispatch<CT_T20>(variant, sgn, *a, stream, query != 0);
+    }
+    return 0;
+}
 
 void hs_cu_launch_generic(int sgn, const void *d_in, void *d_out, const hs_gen_params *p, void *)
 {

@@ -65,6 +65,42 @@ def test_long_bluestein_three_fused_kernels(hs, emu_lib, oracle, n):
         assert "3 fused tiled kernels" in desc and err <= tol(n), (n, sgn, err, desc)
 
 
+def test_persistent_pipeline_groups_rings_and_tail(hs, emu_lib, oracle, monkeypatch):
+    """Two-pass transforms as one persistent kernel (hs_pipe.cuh): several groups, a partial last group, ring
+    slots re-used (more groups than slots), lag 1 and 2.  The emulation aborts if a ticket's dependency is not
+    produced by a smaller ticket."""
+    n = 16384
+    for slot_kb, lag, howmany in ((512, 1, 7), (256, 2, 6), (1 << 14, 1, 3)):
+        monkeypatch.setenv("HSFFT_PIPE_SLOT_KB", str(slot_kb))
+        monkeypatch.setenv("HSFFT_PIPE_LAG", str(lag))
+        err, desc = run_c2c(hs, emu_lib, oracle, n, 1, howmany=howmany, seed=slot_kb)
+        assert "persistent" in desc and err <= tol(n), (slot_kb, lag, err, desc)
+    monkeypatch.setenv("HSFFT_PIPE", "0")
+    err, desc = run_c2c(hs, emu_lib, oracle, n, 1, howmany=2)
+    assert "persistent" not in desc and err <= tol(n)
+
+
+def test_persistent_pipeline_real_transforms(hs, emu_lib, oracle, monkeypatch):
+    """r2c (split as third phase) and c2r (merge on pass 1's loads) over a pipelined half-length plan."""
+    n = 32768
+    monkeypatch.setenv("HSFFT_PIPE_SLOT_KB", "512")
+    x = xorshift_uniform(5 * n, seed=11).reshape(5, n)
+    with hs.RealPlan(n, 1, lib=emu_lib) as f, hs.RealPlan(n, -1, lib=emu_lib) as g:
+        X = f.r2c(x)
+        Xr = oracle.r2c(x)
+        assert rel_rms(X, Xr) <= tol(n)
+        assert np.array_equal(X[:, n - 1: n // 2: -1], np.conj(X[:, 1: n // 2]))
+        y = g.c2r(X)
+        assert rel_rms(y, oracle.c2r(Xr, n)) <= tol(n)
+        assert rel_rms(y / n, x) <= tol(n)
+
+
+def test_persistent_pipeline_long_bluestein_groups(hs, emu_lib, oracle, monkeypatch):
+    monkeypatch.setenv("HSFFT_PIPE_SLOT_KB", "512")
+    err, desc = run_c2c(hs, emu_lib, oracle, 10007, 1, howmany=5)
+    assert "persistent" in desc and err <= tol(10007), (err, desc)
+
+
 def test_three_pass_plan(hs, emu_lib, oracle):
     n = 3 << 17   # 393216 = [8]*5 + [4, 3]: no compile-time plan, three run-time passes
     err, desc = run_c2c(hs, emu_lib, oracle, n, -1, howmany=1)

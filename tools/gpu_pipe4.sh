@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+CASES="16384:16384 32768:8192 65536:4096 131072:2048 262144:1024 524288:512 1048576:256 r2c:1048576:256 c2r:1048576:256 10007:16384"
+for s in 0 1; do echo "== SHAPE=$s"; HSFFT_PIPE_SHAPE=$s timeout 600 python tools/sweep.py $CASES 2>&1 | tee gpurun_out/sweep_pipe4_shape$s.log; done
+echo "== HSFFT_PIPE=0"; HSFFT_PIPE=0 timeout 600 python tools/sweep.py $CASES 2>&1 | tee gpurun_out/sweep_pipe4_nopipe.log
+echo "== HSFFT_PIPE=0 HSFFT_TMA=0"; HSFFT_TMA=0 HSFFT_PIPE=0 timeout 600 python tools/sweep.py $CASES 2>&1 | tee gpurun_out/sweep_pipe4_nopipe_notma.log
