@@ -91,7 +91,7 @@ _LIBS = {}
 
 def load(path=None):
     """Load (once) and return the bound C library.  Raises if it has not been built."""
-    path = os.path.abspath(path or LIB_PATH)
+    path = os.path.abspath(path or os.environ.get("HSFFT_LIB") or LIB_PATH)  # HSFFT_LIB: A/B runs of build variants
     if path not in _LIBS:
         if not os.path.exists(path):
             raise ImportError(

@@ -12,15 +12,17 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OUT = os.path.join(HERE, "libhsfft_b200.so")
-BUILD = os.path.join(HERE, "build")
+# HSFFT_VARIANT=<name> HSFFT_DEFS="-DX=1 ..." builds an experiment into libhsfft_b200_<name>.so (A/B runs: HSFFT_LIB=<path>)
+VARIANT = os.environ.get("HSFFT_VARIANT", "")
+OUT = os.path.join(HERE, "libhsfft_b200%s.so" % ("_" + VARIANT if VARIANT else ""))
+BUILD = os.path.join(HERE, "build" + ("_" + VARIANT if VARIANT else ""))
 
 NVCC = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 GCC = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
 GXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
-              "--expt-relaxed-constexpr", "-ccbin", GXX]
+              "--expt-relaxed-constexpr", "-ccbin", GXX] + os.environ.get("HSFFT_DEFS", "").split()
 C_FLAGS = ["-O2", "-std=gnu11", "-fPIC", "-Wall", "-Wextra", "-Wno-unused-parameter"]
 
 CU_SOURCES = ["hs_device.cu"]

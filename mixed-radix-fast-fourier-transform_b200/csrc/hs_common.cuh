@@ -61,6 +61,7 @@ static inline void hs_mbar_wait(HsMbar *m, unsigned /*parity*/, long long seq, l
     while (m->done.load() < (seq + 1) * bytes_per_phase) { }
 }
 static inline void hs_fence_async_proxy() {}
+static inline void hs_prefetch_l2(const void *, unsigned) {}
 // 3-D tensor-map stand-in: [z][row][x doubles], strides in bytes
 struct HsTmap { const unsigned char *base; long long row_stride, z_stride; };
 static inline void hs_tma_load_3d(void *dst, const HsTmap *t, int x_dbl, int row0, long long z, int rows, int row_bytes, HsMbar *m)
@@ -202,6 +203,11 @@ HS_DEVICE void hs_bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes,
                  "l"(src_gmem), "r"(bytes), "r"(hs_smem_u32(m))
                  : "memory");
 }
+// ask the copy engine to bring [p, p + bytes) into the L2 (16-byte aligned, a multiple of 16 bytes)
+HS_DEVICE void hs_prefetch_l2(const void *p, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 // wait for the phase of the given parity; a copy that never lands traps instead of hanging the GPU
 HS_DEVICE void hs_mbar_wait(HsMbar *m, unsigned parity, long long, long long)
 {
@@ -246,3 +252,10 @@ HS_HD cplx hs_scale(cplx a, double s) { return make_double2(a.x * s, a.y * s); }
 // multiply by -i (forward quarter turn) when SGN=+1, by +i when SGN=-1
 template <int SGN>
 HS_HD cplx hs_rot(cplx a) { return SGN == 1 ? make_double2(a.y, -a.x) : make_double2(-a.y, a.x); }
+
+// r2c split (reference src/real.c:109-125): bin k of the real transform from Z[k], Z[H-k] and twiddle2[k]
+HS_DEVICE cplx hs_r2c_bin(cplx a, cplx c, cplx w) // the reference's expression for bin k from (Z[k], Z[H-k], twiddle2[k])
+{
+    const double t1 = a.y + c.y, t2 = c.x - a.x;
+    return hs_c((a.x + c.x + (t1 * w.x) + (t2 * w.y)) / 2.0, (a.y - c.y + (t2 * w.x) - (t1 * w.y)) / 2.0);
+}

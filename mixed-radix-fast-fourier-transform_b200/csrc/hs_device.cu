@@ -128,7 +128,18 @@ static void set_carveout(const void *kern, int smem_per_cta, int ctas_per_sm)
     HS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
 }
 
-template <class P, int SGN, int MINB>
+// L2 prefetch distance of the one-shot kernels, in CTAs: the number of CTAs resident at once (HSFFT_PREFETCH=0 turns it off,
+// HSFFT_PREFETCH=<n> sets it in units of resident waves).  Measured on B200 (fraction of the HBM peak, prefetch off -> on):
+// N=8192 56 -> 65 %, N=256 90 -> 104 %, N=512 104 -> 107 %, Bluestein N=1009 25.0 -> 26.2 %; N=4096 / 1024 / 2048 / 3000 lose
+// 1-3 points, so only the first group asks for it.
+static int prefetch_dist(int ctas_per_sm)
+{
+    static int waves = -1;
+    if (waves < 0) { const char *e = getenv("HSFFT_PREFETCH"); waves = e ? atoi(e) : 1; }
+    return waves * ctas_per_sm * hs_cu_sm_count();
+}
+
+template <class P, int SGN, int MINB, int PFW = 0> // PFW: L2 prefetch distance in resident waves (0 = none)
 static void launch_c2c(const void *in, void *out, const void *tw, long long howmany, cudaStream_t st)
 {
     auto kern = hs_c2c_smem_kernel<P, SGN, MINB>;
@@ -140,7 +151,38 @@ static void launch_c2c(const void *in, void *out, const void *tw, long long howm
     }
     const long long blocks = (howmany + P::X - 1) / P::X;
     check_grid(blocks);
-    kern<<<(unsigned)blocks, P::threads, P::smem_bytes, st>>>((const cplx *)in, (cplx *)out, (const cplx *)tw, howmany);
+    kern<<<(unsigned)blocks, P::threads, P::smem_bytes, st>>>((const cplx *)in, (cplx *)out, (const cplx *)tw, howmany, PFW ? prefetch_dist(MINB) : 0);
+    HS_CUDA_CHECK(cudaGetLastError());
+    ++g_launches;
+}
+
+// persistent, prefetching variant (hs_c2c_persist_kernel): HSFFT_PERSIST=0 falls back to one CTA per X transforms
+static bool persist_enabled()
+{
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("HSFFT_PERSIST"); v = e ? atoi(e) : 0; }
+    return v != 0;
+}
+
+template <class P, int SGN, int MINB>
+static void launch_c2c_persist(const void *in, void *out, const void *tw, long long howmany, cudaStream_t st)
+{
+    if (!persist_enabled()) { launch_c2c<P, SGN, MINB>(in, out, tw, howmany, st); return; }
+    constexpr int smem = HsPersistSmem<P>::bytes;
+    static_assert(smem * MINB <= 227 * 1024, "staging + exchange buffers of MINB CTAs do not fit one SM");
+    auto kern = hs_c2c_persist_kernel<P, SGN, MINB>;
+    static int per_sm = 0;
+    if (!per_sm) {
+        HS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        HS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        HS_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, P::threads, smem));
+        if (getenv("HSFFT_VERBOSE")) fprintf(stderr, "hsfft: persistent c2c N=%d: %d CTAs/SM, %d bytes smem\n", P::N, per_sm, smem);
+        if (per_sm < 1) per_sm = 1;
+    }
+    const long long nstep = (howmany + P::X - 1) / P::X;
+    long long blocks = (long long)hs_cu_sm_count() * per_sm;
+    if (blocks > nstep) blocks = nstep;
+    kern<<<(unsigned)blocks, P::threads, smem, st>>>((const cplx *)in, (cplx *)out, (const cplx *)tw, howmany);
     HS_CUDA_CHECK(cudaGetLastError());
     ++g_launches;
 }
@@ -159,7 +201,32 @@ static void launch_blu(int N, const void *in, void *out, const void *twf, const 
     const long long blocks = (howmany + PF::X - 1) / PF::X;
     check_grid(blocks);
     kern<<<(unsigned)blocks, PF::threads, PF::smem_bytes, st>>>((const cplx *)in, (cplx *)out, (const cplx *)twf, (const cplx *)twi,
-                                                                 (const cplx *)chirp, (const cplx *)hk, N, howmany);
+                                                                 (const cplx *)chirp, (const cplx *)hk, N, howmany, prefetch_dist(MINB));
+    HS_CUDA_CHECK(cudaGetLastError());
+    ++g_launches;
+}
+
+template <class PF, class PI, int SGN, int MINB>
+static void launch_blu_persist(int N, const void *in, void *out, const void *twf, const void *twi, const void *chirp, const void *hk,
+                               long long howmany, cudaStream_t st)
+{
+    if (!persist_enabled() || N > PF::N / 2 + 1) { launch_blu<PF, PI, SGN, MINB>(N, in, out, twf, twi, chirp, hk, howmany, st); return; }
+    constexpr int smem = HsBluPersistSmem<PF>::bytes;
+    static_assert(smem * MINB <= 227 * 1024, "staging + exchange buffers of MINB CTAs do not fit one SM");
+    auto kern = hs_bluestein_persist_kernel<PF, PI, SGN, MINB>;
+    static int per_sm = 0;
+    if (!per_sm) {
+        HS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        HS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        HS_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PF::threads, smem));
+        if (getenv("HSFFT_VERBOSE")) fprintf(stderr, "hsfft: persistent Bluestein M=%d: %d CTAs/SM, %d bytes smem\n", PF::N, per_sm, smem);
+        if (per_sm < 1) per_sm = 1;
+    }
+    const long long nstep = (howmany + PF::X - 1) / PF::X;
+    long long blocks = (long long)hs_cu_sm_count() * per_sm;
+    if (blocks > nstep) blocks = nstep;
+    kern<<<(unsigned)blocks, PF::threads, smem, st>>>((const cplx *)in, (cplx *)out, (const cplx *)twf, (const cplx *)twi, (const cplx *)chirp,
+                                                      (const cplx *)hk, N, howmany);
     HS_CUDA_CHECK(cudaGetLastError());
     ++g_launches;
 }
@@ -336,7 +403,7 @@ extern "C" void hs_cu_launch_chirp_crop(int sgn, const void *y, void *out, const
 extern "C" void hs_cu_launch_r2c_post(const void *Z, void *out, const void *tw2, int H, long long out_stride, int full, long long howmany,
                                       void *stream)
 {
-    hs_r2c_post_kernel<<<ew_grid(howmany * (H + 1)), 256, 0, (cudaStream_t)stream>>>((const cplx *)Z, (cplx *)out, (const cplx *)tw2, H,
+    hs_r2c_post_kernel<<<ew_grid(howmany * (H / 2 + 1)), 256, 0, (cudaStream_t)stream>>>((const cplx *)Z, (cplx *)out, (const cplx *)tw2, H,
                                                                                       out_stride, full, howmany);
     HS_CUDA_CHECK(cudaGetLastError());
     ++g_launches;

@@ -170,27 +170,32 @@ HS_GLOBAL void hs_chirp_crop_kernel(const cplx *HS_RESTRICT y, cplx *HS_RESTRICT
 
 // r2c split (reference src/real.c:109-132).  Z: half-length spectrum (H = N/2 per row);
 // out row stride out_stride, bins 0..H always written, mirror bins H+1..N-1 when full != 0.
+// One thread per pair (k, H-k), k = 0..H/2: bins k and H-k need the same two inputs Z[k] and Z[H-k], so every
+// input is read once (the first version read it twice: 32 N bytes of traffic for 24 N algorithmic).
 HS_GLOBAL void hs_r2c_post_kernel(const cplx *HS_RESTRICT Z, cplx *HS_RESTRICT out, const cplx *HS_RESTRICT tw2, int H, long long out_stride,
                                   int full, long long howmany)
 {
-    const long long total = howmany * (H + 1);
+    const int P = H / 2 + 1; // pairs per row
+    const long long total = howmany * P;
     for (long long idx = HS_BID * HS_NTHREADS + HS_TID; idx < total; idx += HS_NBLOCKS * HS_NTHREADS) {
-        const long long b = idx / (H + 1);
-        const int k = (int)(idx % (H + 1));
+        const long long b = idx / P;
+        const int k = (int)(idx % P);
         const cplx *z = Z + b * H;
         cplx *o = out + b * out_stride;
         if (k == 0) {
-            const cplx z0 = z[0];
-            o[0] = hs_c(z0.x + z0.y, 0.0);
-        } else if (k == H) {
-            const cplx z0 = z[0];
-            o[H] = hs_c(z0.x - z0.y, 0.0);
+            const cplx z0 = hs_ld_stream(z);
+            hs_st_stream(o, hs_c(z0.x + z0.y, 0.0));
+            hs_st_stream(o + H, hs_c(z0.x - z0.y, 0.0));
         } else {
-            const cplx a = z[k], c = z[H - k], w = hs_ld_tab(tw2 + k);
-            const double t1 = a.y + c.y, t2 = c.x - a.x;
-            const cplx r = hs_c((a.x + c.x + (t1 * w.x) + (t2 * w.y)) / 2.0, (a.y - c.y + (t2 * w.x) - (t1 * w.y)) / 2.0);
-            o[k] = r;
-            if (full) o[2 * H - k] = hs_c(r.x, -r.y);
+            const cplx a = hs_ld_stream(z + k), c = (2 * k == H) ? a : hs_ld_stream(z + (H - k));
+            const cplx r = hs_r2c_bin(a, c, hs_ld_tab(tw2 + k));
+            hs_st_stream(o + k, r);
+            if (full) hs_st_stream(o + (2 * H - k), hs_c(r.x, -r.y));
+            if (2 * k != H) {
+                const cplx r2 = hs_r2c_bin(c, a, hs_ld_tab(tw2 + (H - k)));
+                hs_st_stream(o + (H - k), r2);
+                if (full) hs_st_stream(o + (H + k), hs_c(r2.x, -r2.y));
+            }
         }
     }
 }

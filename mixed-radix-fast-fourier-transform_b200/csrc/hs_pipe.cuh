@@ -71,11 +71,7 @@ template <int NT_, int KPT, int LDP, int STP>
 struct HsPhR2CSplit {
     static constexpr int NT = NT_, C = 1, SMEM = 0;
     static constexpr int KT = NT_ * KPT; // k values per tile
-    static HS_DEVICE cplx bin(cplx a, cplx c, cplx w) // the reference's expression for bin k from (Z[k], Z[H-k], twiddle2[k])
-    {
-        const double t1 = a.y + c.y, t2 = c.x - a.x;
-        return hs_c((a.x + c.x + (t1 * w.x) + (t2 * w.y)) / 2.0, (a.y - c.y + (t2 * w.x) - (t1 * w.y)) / 2.0);
-    }
+    static HS_DEVICE cplx bin(cplx a, cplx c, cplx w) { return hs_r2c_bin(a, c, w); }
     template <int KNT, class HK>
     static HS_DEVICE void run(const hs_phase_args &pa, const cplx *z, cplx *o, long long, int tile, cplx *, HK &)
     {
@@ -172,6 +168,7 @@ struct HsPipeHooks {
         if (HS_TID == SIG && sigp) hs_signal_add(sigp);
         sigp = nullptr;
     }
+    HS_DEVICE void after_first_pass() const {}
     HS_DEVICE void before_last_pass()
     {
         fired2 = true;

@@ -21,10 +21,13 @@ using P8192  = HsPlan<8192, 512, 1, 4, -1, 0, 8, 8, 8, 16>;
 using PB2048f = HsPlan<2048, 128, 2, 4, -1, 0, 8, 16, 16>;
 using PB2048i = HsPlan<2048, 128, 2, 4, -1, 0, 16, 16, 8>;
 // sub-plans of the two-pass transforms (N = n1 * n2 > 8192); X is unused there
-using S128  = HsPlan<128, 8, 1, 4, -1, 0, 8, 16>;
-using S256  = HsPlan<256, 16, 1, 4, -1, 0, 16, 16>;
-using S512  = HsPlan<512, 64, 1, 3, -1, 0, 8, 8, 8>;
-using S1024 = HsPlan<1024, 64, 1, 3, -1, 0, 16, 8, 8>;      // (T=128, 8.8.8.2 measured slower: 29% vs 36% at 2^20)
+#ifndef HS_SUB_SPLIT
+#define HS_SUB_SPLIT -1
+#endif
+using S128  = HsPlan<128, 8, 1, 4, HS_SUB_SPLIT, 0, 8, 16>;
+using S256  = HsPlan<256, 16, 1, 4, HS_SUB_SPLIT, 0, 16, 16>;
+using S512  = HsPlan<512, 64, 1, 3, HS_SUB_SPLIT, 0, 8, 8, 8>;
+using S1024 = HsPlan<1024, 64, 1, 3, HS_SUB_SPLIT, 0, 16, 8, 8>;      // (T=128, 8.8.8.2 measured slower: 29% vs 36% at 2^20)
 // profiling-only ablations (never selected unless HSFFT_PREFER_CT names them)
 using P4096x = HsPlan<4096, 256, 1, 4, 0, 0, 16, 16, 16>;
 using P3000x = HsPlan<3000, 200, 1, 3, -1, 0, 3, 5, 5, 5, 8>;
@@ -33,10 +36,10 @@ using P3000y = HsPlan<3000, 200, 1, 3, 0, 0, 3, 5, 5, 5, 8>;       // one stage 
 using P3000z = HsPlan<3000, 200, 1, 3, -1, 2111, 3, 5, 5, 5, 8>;  // passes {3,5} {5} {5} {8}
 
 // inverse-order partners of the sub-plans (first radix = the forward plan's last radix)
-using S128i  = HsPlan<128, 8, 1, 4, -1, 0, 16, 8>;
+using S128i  = HsPlan<128, 8, 1, 4, HS_SUB_SPLIT, 0, 16, 8>;
 using S256i  = S256;
 using S512i  = S512;
-using S1024i = HsPlan<1024, 64, 1, 3, -1, 0, 8, 8, 16>;
+using S1024i = HsPlan<1024, 64, 1, 3, HS_SUB_SPLIT, 0, 8, 8, 16>;
 
 enum { CT_4096A = 0, CT_4096B, CT_3000, CT_1024, CT_2048, CT_512, CT_256, CT_8192, CT_B2048, CT_4096X, CT_3000X, CT_4096Y, CT_3000Y, CT_3000Z,
        CT_T14, CT_T15, CT_T16, CT_T17, CT_T18, CT_T19, CT_T20,

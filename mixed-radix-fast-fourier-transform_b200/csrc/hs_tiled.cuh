@@ -52,24 +52,29 @@ struct HsLoadCol {
     }
     HS_DEVICE cplx operator()(int, int, int n) const { return hs_ld_mp<LDP>(base + addr(n)); }
 };
-// inter-pass twiddle of element i = b + NB*ii of column k: W^(k b) * (W^(k NB))^ii
+// inter-pass twiddle of element i = b + NB*ii of column k: v[ii] *= t[ii], t[ii] = W^(k b) * (W^(k NB))^ii.
+// t[] costs R + 1 complex products for R = 16 (the first version took 30): the step's powers 2 and 4 by squaring,
+// t[1], t[2], t[4] from w0, t[8] = t[4]*s[4], and every other t[ii] from the entry without its lowest set bit,
+// t[ii] = t[ii - low] * s[low].  The longest chain is 5 products (ii = 15), the same depth as before.
 template <int R>
 HS_DEVICE void hs_interpass_twiddle(const cplx w0, const cplx step, cplx *v)
 {
-    cplx s[R];
+    constexpr int SMAX = R >= 4 ? R / 4 : 1; // largest power of the step that is needed
+    cplx s[SMAX + 1], t[R];
     s[1] = step;
     HS_UNROLL
-    for (int i = 2; i < R; i *= 2) s[i] = hs_mul(s[i / 2], s[i / 2]);
+    for (int p = 2; p <= SMAX; p *= 2) s[p] = hs_mul(s[p / 2], s[p / 2]);
+    t[0] = w0;
+    HS_UNROLL
+    for (int p = 1; p < R; p *= 2) t[p] = (p <= SMAX) ? hs_mul(w0, s[p]) : hs_mul(t[p / 2], s[p / 2]);
     HS_UNROLL
     for (int i = 3; i < R; ++i)
         if (i & (i - 1)) {
-            int hb = 1;
-            while (hb * 2 <= i) hb *= 2;
-            s[i] = hs_mul(s[hb], s[i - hb]);
+            const int low = i & -i;
+            t[i] = hs_mul(t[i - low], s[low]);
         }
-    v[0] = hs_mul(v[0], w0);
     HS_UNROLL
-    for (int i = 1; i < R; ++i) v[i] = hs_mul(v[i], hs_mul(w0, s[i]));
+    for (int i = 0; i < R; ++i) v[i] = hs_mul(v[i], t[i]);
 }
 template <int LDP = 0>
 struct HsLoadColTw : HsLoadCol<LDP> {
@@ -320,12 +325,14 @@ template <class HK>
 struct HsFirstHook {
     HK &h;
     HS_DEVICE void after_first_loads() { h.after_first_loads(); }
+    HS_DEVICE void after_first_pass() {}
     HS_DEVICE void before_last_pass() {}
 };
 template <class HK>
 struct HsLastHook {
     HK &h;
     HS_DEVICE void after_first_loads() {}
+    HS_DEVICE void after_first_pass() {}
     HS_DEVICE void before_last_pass() { h.before_last_pass(); }
 };
 template <int RL>

@@ -23,12 +23,21 @@
 typedef void *hs_stream_t;
 static std::atomic<long long> g_launches{0};
 
-template <class P, int SGN, int MINB>
+template <class P, int SGN, int MINB, int PFW = 0>
 static void launch_c2c(const void *in, void *out, const void *tw, long long howmany, hs_stream_t)
 {
     const long long blocks = (howmany + P::X - 1) / P::X;
     hs_emu_launch(hs_c2c_smem_kernel<P, SGN, MINB>, blocks, P::threads, P::smem_bytes, (const cplx *)in, (cplx *)out, (const cplx *)tw,
-                  howmany);
+                  howmany, 2);
+    ++g_launches;
+}
+
+template <class P, int SGN, int MINB>
+static void launch_c2c_persist(const void *in, void *out, const void *tw, long long howmany, hs_stream_t)
+{
+    const long long nstep = (howmany + P::X - 1) / P::X; // two "SMs": the second CTA's steps interleave with the first's
+    hs_emu_launch(hs_c2c_persist_kernel<P, SGN, MINB>, nstep < 2 ? nstep : 2, P::threads, HsPersistSmem<P>::bytes, (const cplx *)in, (cplx *)out,
+                  (const cplx *)tw, howmany);
     ++g_launches;
 }
 
@@ -38,7 +47,17 @@ static void launch_blu(int N, const void *in, void *out, const void *twf, const 
 {
     const long long blocks = (howmany + PF::X - 1) / PF::X;
     hs_emu_launch(hs_bluestein_kernel<PF, PI, SGN, MINB>, blocks, PF::threads, PF::smem_bytes, (const cplx *)in, (cplx *)out,
-                  (const cplx *)twf, (const cplx *)twi, (const cplx *)chirp, (const cplx *)hk, N, howmany);
+                  (const cplx *)twf, (const cplx *)twi, (const cplx *)chirp, (const cplx *)hk, N, howmany, 2);
+    ++g_launches;
+}
+
+template <class PF, class PI, int SGN, int MINB>
+static void launch_blu_persist(int N, const void *in, void *out, const void *twf, const void *twi, const void *chirp, const void *hk,
+                               long long howmany, hs_stream_t)
+{
+    const long long nstep = (howmany + PF::X - 1) / PF::X;
+    hs_emu_launch(hs_bluestein_persist_kernel<PF, PI, SGN, MINB>, nstep < 2 ? nstep : 2, PF::threads, HsBluPersistSmem<PF>::bytes, (const cplx *)in,
+                  (cplx *)out, (const cplx *)twf, (const cplx *)twi, (const cplx *)chirp, (const cplx *)hk, N, howmany);
     ++g_launches;
 }
 
@@ -160,7 +179,7 @@ void hs_cu_launch_chirp_crop(int sgn, const void *y, void *out, const void *h, i
 }
 void hs_cu_launch_r2c_post(const void *Z, void *out, const void *tw2, int H, long long out_stride, int full, long long howmany, void *)
 {
-    hs_emu_launch(hs_r2c_post_kernel, ew_blocks(howmany * (H + 1)), 64, 0, (const cplx *)Z, (cplx *)out, (const cplx *)tw2, H, out_stride, full,
+    hs_emu_launch(hs_r2c_post_kernel, ew_blocks(howmany * (H / 2 + 1)), 64, 0, (const cplx *)Z, (cplx *)out, (const cplx *)tw2, H, out_stride, full,
                   howmany);
     ++g_launches;
 }

@@ -65,11 +65,21 @@ def test_long_bluestein_three_fused_kernels(hs, emu_lib, oracle, n):
         assert "3 fused tiled kernels" in desc and err <= tol(n), (n, sgn, err, desc)
 
 
+@pytest.mark.parametrize("n,howmany", [(3000, 5), (1009, 7), (600, 3)])
+def test_persistent_prefetching_kernels_walk_several_steps(hs, emu_lib, oracle, n, howmany):
+    """hs_c2c_persist_kernel / hs_bluestein_persist_kernel: each CTA takes several steps (two CTAs in the
+    emulation), the staging buffer is refilled behind the first pass, the last step is partial."""
+    for sgn in (1, -1):
+        err, desc = run_c2c(hs, emu_lib, oracle, n, sgn, howmany=howmany, seed=howmany)
+        assert err <= tol(n), (n, sgn, err, desc)
+
+
 def test_persistent_pipeline_groups_rings_and_tail(hs, emu_lib, oracle, monkeypatch):
     """Two-pass transforms as one persistent kernel (hs_pipe.cuh): several groups, a partial last group, ring
     slots re-used (more groups than slots), lag 1 and 2.  The emulation aborts if a ticket's dependency is not
     produced by a smaller ticket."""
     n = 16384
+    monkeypatch.setenv("HSFFT_PIPE", "1")
     for slot_kb, lag, howmany in ((512, 1, 7), (256, 2, 6), (1 << 14, 1, 3)):
         monkeypatch.setenv("HSFFT_PIPE_SLOT_KB", str(slot_kb))
         monkeypatch.setenv("HSFFT_PIPE_LAG", str(lag))
@@ -83,6 +93,7 @@ def test_persistent_pipeline_groups_rings_and_tail(hs, emu_lib, oracle, monkeypa
 def test_persistent_pipeline_real_transforms(hs, emu_lib, oracle, monkeypatch):
     """r2c (split as third phase) and c2r (merge on pass 1's loads) over a pipelined half-length plan."""
     n = 32768
+    monkeypatch.setenv("HSFFT_PIPE", "1")
     monkeypatch.setenv("HSFFT_PIPE_SLOT_KB", "512")
     x = xorshift_uniform(5 * n, seed=11).reshape(5, n)
     with hs.RealPlan(n, 1, lib=emu_lib) as f, hs.RealPlan(n, -1, lib=emu_lib) as g:
@@ -96,6 +107,7 @@ def test_persistent_pipeline_real_transforms(hs, emu_lib, oracle, monkeypatch):
 
 
 def test_persistent_pipeline_long_bluestein_groups(hs, emu_lib, oracle, monkeypatch):
+    monkeypatch.setenv("HSFFT_PIPE", "1")
     monkeypatch.setenv("HSFFT_PIPE_SLOT_KB", "512")
     err, desc = run_c2c(hs, emu_lib, oracle, 10007, 1, howmany=5)
     assert "persistent" in desc and err <= tol(10007), (err, desc)
