@@ -58,6 +58,9 @@ typedef struct hs_ct_desc {
     /* HS_CT_TWOPASS: n = n1 * n2; radix[]/nst/split_min describe the pass-1 sub-plan of length n1
      * (columns of stride n2), the fields below the pass-2 sub-plan of length n2 (columns of stride n1) */
     int n1, n2, nst2, radix2[8], split_min2;
+    /* 1: the radix-3/5/7 stages use full-precision constants -- usable inside Bluestein only (a transform the
+     * reference runs itself must reproduce its 11-digit literals) */
+    int exact;
 } hs_ct_desc;
 
 /* parameters of one run-time planned pass (see hs_generic.cuh) */

@@ -209,15 +209,16 @@ HS_DEVICE void hs_bfly_generic(cplx *v, int r, const double *cs, const double *s
     }
 }
 
-// compile-time radix dispatch
-template <int R, int SGN>
+// compile-time radix dispatch; EXACT selects the full-precision radix-3/5/7 constants (Bluestein-internal
+// transforms only -- a transform the reference itself runs must keep the reference's literals)
+template <int R, int SGN, bool EXACT = false>
 HS_HD void hs_bfly(cplx *v)
 {
     if (R == 2) hs_bfly2<SGN>(v);
-    else if (R == 3) hs_bfly3<SGN>(v);
+    else if (R == 3) { if (EXACT) hs_bfly3_exact<SGN>(v); else hs_bfly3<SGN>(v); }
     else if (R == 4) hs_bfly4<SGN>(v);
-    else if (R == 5) hs_bfly5<SGN>(v);
-    else if (R == 7) hs_bfly7<SGN>(v);
+    else if (R == 5) { if (EXACT) hs_bfly5_exact<SGN>(v); else hs_bfly5<SGN>(v); }
+    else if (R == 7) { if (EXACT) hs_bfly7_exact<SGN>(v); else hs_bfly7<SGN>(v); }
     else if (R == 8) hs_bfly8<SGN>(v);
     else if (R == 16) hs_bfly16<SGN>(v);
 }

@@ -24,6 +24,7 @@ static void fill_desc(hs_ct_desc &d, int id, int family)
     d.threads = P::threads;
     d.smem_bytes = P::smem_bytes;
     d.n1 = d.n2 = d.nst2 = d.split_min2 = 0;
+    d.exact = P::EXACT ? 1 : 0;
     for (int s = 0; s < 8; ++s) d.radix2[s] = 0;
 }
 
@@ -37,6 +38,7 @@ static void fill_desc2(hs_ct_desc &d, int id)
     d.nst2 = P2::NST;
     for (int s = 0; s < 8; ++s) d.radix2[s] = s < P2::NST ? P2::radix(s) : 0;
     d.split_min2 = P2::SPLIT;
+    d.exact = (P1::EXACT || P2::EXACT) ? 1 : 0;
 }
 
 static hs_ct_desc g_ct[CT_COUNT];
@@ -71,6 +73,8 @@ static void ct_init()
     fill_desc<S256>(g_ct[CT_S256], CT_S256, HS_CT_SUB);
     fill_desc<S512>(g_ct[CT_S512], CT_S512, HS_CT_SUB);
     fill_desc<S1024>(g_ct[CT_S1024], CT_S1024, HS_CT_SUB);
+    fill_desc2<S160x, S128>(g_ct[CT_TX20480], CT_TX20480);
+    fill_desc<S160x>(g_ct[CT_S160X], CT_S160X, HS_CT_SUB);
     for (int i = 0; i < CT_COUNT; ++i) g_ct_order[i] = i;
     // HSFFT_PREFER_CT=<id>: list that instance first (A/B runs of alternative plans for one N)
     if (const char *e = getenv("HSFFT_PREFER_CT")) {
@@ -175,6 +179,7 @@ extern "C" void hs_cu_launch_ct_twopass(int id, int pass, int sgn, const void *d
     case CT_T18: launch_twopass<S512, S512>(pass, sgn, d_in, d_out, d_tw, d_twb, d_tws, howmany, st); break;
     case CT_T19: launch_twopass<S512, S1024>(pass, sgn, d_in, d_out, d_tw, d_twb, d_tws, howmany, st); break;
     case CT_T20: launch_twopass<S1024, S1024>(pass, sgn, d_in, d_out, d_tw, d_twb, d_tws, howmany, st); break;
+    case CT_TX20480: launch_twopass<S160x, S128>(pass, sgn, d_in, d_out, d_tw, d_twb, d_tws, howmany, st); break;
     default: fprintf(stderr, "Error: unknown two-pass kernel id %d\n", id); exit(EXIT_FAILURE);
     }
 }
@@ -201,6 +206,7 @@ extern "C" void hs_cu_launch_tiled(int sub_id, int sgn, int tw_mode, int stcol, 
     case CT_S256: launch_sub<S256>(sgn, tw_mode, stcol, d_in, d_out, d_tw, *g, howmany, st); break;
     case CT_S512: launch_sub<S512>(sgn, tw_mode, stcol, d_in, d_out, d_tw, *g, howmany, st); break;
     case CT_S1024: launch_sub<S1024>(sgn, tw_mode, stcol, d_in, d_out, d_tw, *g, howmany, st); break;
+    case CT_S160X: launch_sub<S160x>(sgn, tw_mode, stcol, d_in, d_out, d_tw, *g, howmany, st); break;
     default: fprintf(stderr, "Error: unknown sub-plan id %d\n", sub_id); exit(EXIT_FAILURE);
     }
 }
@@ -233,6 +239,7 @@ extern "C" void hs_cu_launch_tiled_io(int sub_id, int sgn, int tw_mode, int stco
     case CT_S256: launch_sub_io<S256>(sgn, tw_mode, stcol, io_mode, chirp_sgn, d_in, d_out, d_tw, *g, howmany, st); break;
     case CT_S512: launch_sub_io<S512>(sgn, tw_mode, stcol, io_mode, chirp_sgn, d_in, d_out, d_tw, *g, howmany, st); break;
     case CT_S1024: launch_sub_io<S1024>(sgn, tw_mode, stcol, io_mode, chirp_sgn, d_in, d_out, d_tw, *g, howmany, st); break;
+    case CT_S160X: launch_sub_io<S160x>(sgn, tw_mode, stcol, io_mode, chirp_sgn, d_in, d_out, d_tw, *g, howmany, st); break;
     default: fprintf(stderr, "Error: unknown sub-plan id %d\n", sub_id); exit(EXIT_FAILURE);
     }
 }
@@ -245,6 +252,7 @@ extern "C" void hs_cu_launch_blu_mid(int sub_id, int chirp_sgn, const void *d_in
     case CT_S128: if (chirp_sgn == 1) launch_blu_mid<S128, S128i, 1>(d_in, d_out, d_twf, d_twi, *g, d_hk, howmany, st); else launch_blu_mid<S128, S128i, -1>(d_in, d_out, d_twf, d_twi, *g, d_hk, howmany, st); break;
     case CT_S256: if (chirp_sgn == 1) launch_blu_mid<S256, S256i, 1>(d_in, d_out, d_twf, d_twi, *g, d_hk, howmany, st); else launch_blu_mid<S256, S256i, -1>(d_in, d_out, d_twf, d_twi, *g, d_hk, howmany, st); break;
     case CT_S512: if (chirp_sgn == 1) launch_blu_mid<S512, S512i, 1>(d_in, d_out, d_twf, d_twi, *g, d_hk, howmany, st); else launch_blu_mid<S512, S512i, -1>(d_in, d_out, d_twf, d_twi, *g, d_hk, howmany, st); break;
+    case CT_S160X: if (chirp_sgn == 1) launch_blu_mid<S160x, S160xi, 1>(d_in, d_out, d_twf, d_twi, *g, d_hk, howmany, st); else launch_blu_mid<S160x, S160xi, -1>(d_in, d_out, d_twf, d_twi, *g, d_hk, howmany, st); break;
     case CT_S1024: if (chirp_sgn == 1) launch_blu_mid<S1024, S1024i, 1>(d_in, d_out, d_twf, d_twi, *g, d_hk, howmany, st); else launch_blu_mid<S1024, S1024i, -1>(d_in, d_out, d_twf, d_twi, *g, d_hk, howmany, st); break;
     default: fprintf(stderr, "Error: unknown sub-plan id %d\n", sub_id); exit(EXIT_FAILURE);
     }

@@ -73,9 +73,14 @@ struct HsPlan {
     static constexpr int smem_bytes = NPASS > 1 ? NPAD * X_ * 16 : 0;
     static constexpr int threads = T_ * X_;
     static constexpr int ABL = 0; // ablation bits for profiling builds (1: skip twiddle loads -- wrong results)
+    static constexpr bool EXACT = false; // radix-3/5/7 butterflies with the reference's 11-digit literals
 };
 template <class Base, int A>
 struct HsAblate : Base { static constexpr int ABL = A; };
+// the same plan with full-precision radix-3/5/7 constants: for the padded convolution inside Bluestein, which
+// the reference runs with power-of-two stages only (so its result carries no truncation error to reproduce)
+template <class Base>
+struct HsExact : Base { static constexpr bool EXACT = true; };
 
 // Where a thread sits in its team for one pass: team buffer, index inside the team, and whether the
 // team has work (padding teams of the last CTA still take part in the barriers).  Tiled kernels use
@@ -184,7 +189,7 @@ HS_DEVICE void hs_stage(LD &ld, ST &st, const HsLane &ln, const cplx *HS_RESTRIC
             } else if constexpr (LD::kPost) {
                 ld.template post<R>(b, v[u]); // inter-pass twiddle of a multi-pass transform
             }
-            hs_bfly<R, SGN>(v[u]);
+            hs_bfly<R, SGN, P::EXACT>(v[u]);
         }
     }
     if (!FIRST && !LAST) HS_SYNC(); // every thread has read its inputs; the buffer may be overwritten
@@ -257,7 +262,7 @@ HS_DEVICE void hs_stage2(LD &ld, ST &st, const HsLane &ln, const cplx *HS_RESTRI
                 }
             }
             HS_UNROLL
-            for (int ib = 0; ib < RB; ++ib) hs_bfly<RA, SGN>(v[u][ib]);
+            for (int ib = 0; ib < RB; ++ib) hs_bfly<RA, SGN, P::EXACT>(v[u][ib]);
             HS_UNROLL
             for (int ja = 0; ja < RA; ++ja) {
                 cplx tt[RB];
@@ -269,7 +274,7 @@ HS_DEVICE void hs_stage2(LD &ld, ST &st, const HsLane &ln, const cplx *HS_RESTRI
                     HS_UNROLL
                     for (int ib = 1; ib < RB; ++ib) tt[ib] = hs_mul(tt[ib], wb[ib]);
                 }
-                hs_bfly<RB, SGN>(tt);
+                hs_bfly<RB, SGN, P::EXACT>(tt);
                 HS_UNROLL
                 for (int jb = 0; jb < RB; ++jb) v[u][jb][ja] = tt[jb];
             }

@@ -56,10 +56,11 @@ struct HsLoadCol {
 // t[] costs R + 1 complex products for R = 16 (the first version took 30): the step's powers 2 and 4 by squaring,
 // t[1], t[2], t[4] from w0, t[8] = t[4]*s[4], and every other t[ii] from the entry without its lowest set bit,
 // t[ii] = t[ii - low] * s[low].  The longest chain is 5 products (ii = 15), the same depth as before.
+constexpr int hs_pow2_floor(int x) { return x < 2 ? 1 : 2 * hs_pow2_floor(x / 2); }
 template <int R>
 HS_DEVICE void hs_interpass_twiddle(const cplx w0, const cplx step, cplx *v)
 {
-    constexpr int SMAX = R >= 4 ? R / 4 : 1; // largest power of the step that is needed
+    constexpr int SMAX = hs_pow2_floor((R - 1) / 2); // largest power of the step that is needed (any radix, not only 2^k)
     cplx s[SMAX + 1], t[R];
     s[1] = step;
     HS_UNROLL

@@ -184,20 +184,37 @@ int hs_bluestein_exec_pad(int N)
     return m;
 }
 
+static const hs_ct_desc *find_ct_ex(int family, int n, int allow_exact);
+
+/* The pad length the device runs with.  Any M >= 2N-1 gives the same convolution (SURVEY.md section 8c "may
+ * differ"); between two powers of two the engine also offers 5/8 of the upper one where a compile-time plan with
+ * full-precision radix-5 stages exists (N = 10007: 20480 instead of 32768).  HSFFT_BLU_POW2=1 keeps the power of two. */
+static int bluestein_device_pad(int N)
+{
+    const int m = hs_bluestein_exec_pad(N);
+    const int alt = m / 8 * 5;
+    if (m >= 8 && alt >= 2 * N - 1 && !getenv("HSFFT_BLU_POW2") && find_ct_ex(HS_CT_TWOPASS, alt, 1) &&
+        find_ct_ex(HS_CT_TWOPASS, alt, 1)->exact)
+        return alt;
+    return m;
+}
+
 /* ------------------------------------------------------------------------------- c2c sub-plans */
 
 #define HS_SMEM_POINTS 6400 /* complex points of one ping-pong buffer pair's half (2*6400*16 B = 200 KiB) */
 #define HS_GROUP_MAX 512
 
-static const hs_ct_desc *find_ct(int family, int n)
+/* allow_exact: also accept plans whose radix-3/5/7 stages use full-precision constants (Bluestein-internal use) */
+static const hs_ct_desc *find_ct_ex(int family, int n, int allow_exact)
 {
     const int cnt = hs_cu_ct_count();
     for (int i = 0; i < cnt; ++i) {
         const hs_ct_desc *d = hs_cu_ct_get(i);
-        if (d->family == family && d->n == n) return d;
+        if (d->family == family && d->n == n && (allow_exact || !d->exact)) return d;
     }
     return NULL;
 }
+static const hs_ct_desc *find_ct(int family, int n) { return find_ct_ex(family, n, 0); }
 
 static void *upload(const void *h, size_t bytes)
 {
@@ -295,7 +312,10 @@ static void pipe_twopass_phases(const hs_c2c *p, hs_pipe_args *a)
     a->ph[1].tw = p->d_tw2;
 }
 
-hs_c2c *hs_c2c_create(int n, int sgn)
+static hs_c2c *c2c_create(int n, int sgn, int allow_exact);
+hs_c2c *hs_c2c_create(int n, int sgn) { return c2c_create(n, sgn, 0); }
+
+static hs_c2c *c2c_create(int n, int sgn, int allow_exact)
 {
     hs_c2c *p = (hs_c2c *)calloc(1, sizeof(hs_c2c));
     if (!p) { fprintf(stderr, "Error: Memory allocation failed for execution plan\n"); exit(EXIT_FAILURE); }
@@ -309,7 +329,7 @@ hs_c2c *hs_c2c_create(int n, int sgn)
         p->d_tw = upload_stage_twiddles(ct->radix, ct->nst, sgn, ct->split_min);
         return p;
     }
-    ct = find_ct(HS_CT_TWOPASS, n);
+    ct = find_ct_ex(HS_CT_TWOPASS, n, allow_exact);
     if (ct) {
         /* n = n1 * n2: pass 1 = n2 strided transforms of length n1, pass 2 = n1 of length n2 with the
          * inter-pass twiddle W_n^{i k} applied on load as W_n^{k b} * (W_n^{k NB})^ii, i = b + NB ii */
@@ -549,7 +569,7 @@ static void dev_build(hs_dev_obj *d, fft_object plan)
     if (d->lt == 0) { d->direct = hs_c2c_create(d->N, d->sgn); return; }
 
     /* Bluestein: chirp h and Hk = FFT_M(h padded and mirrored, scaled 1/M) live in HBM */
-    const int N = d->N, M = hs_bluestein_exec_pad(N);
+    const int N = d->N, M = bluestein_device_pad(N);
     d->M = M;
     fft_data *h = (fft_data *)malloc(sizeof(fft_data) * N), *hp = (fft_data *)calloc(M, sizeof(fft_data));
     if (!h || !hp) { fprintf(stderr, "Error: Memory allocation failed for Bluestein's FFT arrays\n"); exit(EXIT_FAILURE); }
@@ -560,7 +580,7 @@ static void dev_build(hs_dev_obj *d, fft_object plan)
     d->d_chirp = upload(h, sizeof(fft_data) * N);
     void *d_hp = upload(hp, sizeof(fft_data) * M);
     d->d_hk = hs_cu_malloc(sizeof(fft_data) * M);
-    hs_c2c *f = hs_c2c_create(M, 1);
+    hs_c2c *f = c2c_create(M, 1, 1);
     void *ws = NULL;
     const size_t wse = hs_c2c_ws_elems(f, 1);
     if (wse) ws = hs_cu_malloc(wse * sizeof(fft_data));
@@ -571,8 +591,8 @@ static void dev_build(hs_dev_obj *d, fft_object plan)
     free(h);
     free(hp);
 
-    const hs_ct_desc *tp = find_ct(HS_CT_TWOPASS, M);
-    const hs_ct_desc *s1 = tp ? find_ct(HS_CT_SUB, tp->n1) : NULL, *s2 = tp ? find_ct(HS_CT_SUB, tp->n2) : NULL;
+    const hs_ct_desc *tp = find_ct_ex(HS_CT_TWOPASS, M, 1);
+    const hs_ct_desc *s1 = tp ? find_ct_ex(HS_CT_SUB, tp->n1, 1) : NULL, *s2 = tp ? find_ct_ex(HS_CT_SUB, tp->n2, 1) : NULL;
     if (tp && s1 && s2 && !getenv("HSFFT_NO_BIGBLU")) {
         /* long Bluestein: A = chirp/pad + forward pass 1, B = forward pass 2 * Hk + inverse pass 1, C = inverse
          * pass 2 + chirp/crop.  Forward decomposition n1 x n2, inverse n2 x n1, so B works column by column. */
@@ -622,7 +642,7 @@ static void dev_build(hs_dev_obj *d, fft_object plan)
         hs_c2c_destroy(f);
     } else {
         d->fwdM = f;
-        d->invM = hs_c2c_create(M, -1);
+        d->invM = c2c_create(M, -1, 1);
     }
 }
 

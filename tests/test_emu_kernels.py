@@ -108,9 +108,23 @@ def test_persistent_pipeline_real_transforms(hs, emu_lib, oracle, monkeypatch):
 
 def test_persistent_pipeline_long_bluestein_groups(hs, emu_lib, oracle, monkeypatch):
     monkeypatch.setenv("HSFFT_PIPE", "1")
+    monkeypatch.setenv("HSFFT_BLU_POW2", "1")   # the pipelines exist for the power-of-two pad lengths
     monkeypatch.setenv("HSFFT_PIPE_SLOT_KB", "512")
     err, desc = run_c2c(hs, emu_lib, oracle, 10007, 1, howmany=5)
     assert "persistent" in desc and err <= tol(10007), (err, desc)
+
+
+def test_smooth_bluestein_pad_uses_exact_radix5_and_stays_bluestein_only(hs, emu_lib, oracle, monkeypatch):
+    """N in 8193..10240: the device pads to 20480 = 128 x 160 (full-precision radix-5 stages) instead of 32768.
+    A user-facing N = 20480 transform must NOT take that plan: the reference's own radix-5 literals apply there."""
+    for n in (8209, 10239):
+        err, desc = run_c2c(hs, emu_lib, oracle, n, 1, howmany=2)
+        assert "M=20480=160x128" in desc and err <= 1e-14, (n, err, desc)
+    err, desc = run_c2c(hs, emu_lib, oracle, 20480, 1, howmany=1)
+    assert "run-time" in desc and err <= 1e-14, (err, desc)   # within rounding of the reference's truncated constants
+    monkeypatch.setenv("HSFFT_BLU_POW2", "1")
+    err, desc = run_c2c(hs, emu_lib, oracle, 8209, -1, howmany=1)
+    assert "M=32768" in desc and err <= tol(8209)
 
 
 def test_three_pass_plan(hs, emu_lib, oracle):
