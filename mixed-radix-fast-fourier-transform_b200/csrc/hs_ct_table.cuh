@@ -74,6 +74,9 @@ static void ct_init()
     fill_desc<S512>(g_ct[CT_S512], CT_S512, HS_CT_SUB);
     fill_desc<S1024>(g_ct[CT_S1024], CT_S1024, HS_CT_SUB);
     fill_desc2<S160x, S128>(g_ct[CT_TX20480], CT_TX20480);
+    fill_desc2<S160x, S256>(g_ct[CT_TX40960], CT_TX40960);
+    fill_desc2<S160x, S512>(g_ct[CT_TX81920], CT_TX81920);
+    fill_desc2<S160x, S1024>(g_ct[CT_TX163840], CT_TX163840);
     fill_desc<S160x>(g_ct[CT_S160X], CT_S160X, HS_CT_SUB);
     for (int i = 0; i < CT_COUNT; ++i) g_ct_order[i] = i;
     // HSFFT_PREFER_CT=<id>: list that instance first (A/B runs of alternative plans for one N)
@@ -180,6 +183,9 @@ extern "C" void hs_cu_launch_ct_twopass(int id, int pass, int sgn, const void *d
     case CT_T19: launch_twopass<S512, S1024>(pass, sgn, d_in, d_out, d_tw, d_twb, d_tws, howmany, st); break;
     case CT_T20: launch_twopass<S1024, S1024>(pass, sgn, d_in, d_out, d_tw, d_twb, d_tws, howmany, st); break;
     case CT_TX20480: launch_twopass<S160x, S128>(pass, sgn, d_in, d_out, d_tw, d_twb, d_tws, howmany, st); break;
+    case CT_TX40960: launch_twopass<S160x, S256>(pass, sgn, d_in, d_out, d_tw, d_twb, d_tws, howmany, st); break;
+    case CT_TX81920: launch_twopass<S160x, S512>(pass, sgn, d_in, d_out, d_tw, d_twb, d_tws, howmany, st); break;
+    case CT_TX163840: launch_twopass<S160x, S1024>(pass, sgn, d_in, d_out, d_tw, d_twb, d_tws, howmany, st); break;
     default: fprintf(stderr, "Error: unknown two-pass kernel id %d\n", id); exit(EXIT_FAILURE);
     }
 }

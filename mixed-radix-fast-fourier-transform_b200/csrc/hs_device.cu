@@ -305,7 +305,7 @@ static void launch_tiled(const void *in, void *out, const void *tw, const HsTile
     if constexpr (IO == 0) {
         if (tma_enabled(P::N) && g.in_c == 1 && g.blk_log == 0) { launch_tiled_tma<P, SGN, C, TW, STCOL>(in, out, tw, g, howmany, st); return; }
     }
-    constexpr int MINB = (P::T * C <= 256 || P::N * 16 / P::T <= 160) ? 2 : 1; // 8-10 points per thread fit 100 registers
+    constexpr int MINB = (P::T * C <= 256 || (P::T * C <= 320 && P::N / P::T <= 10)) ? 2 : 1; // 320 threads of 8-10 points fit 100 registers
     constexpr int smem = C * hs_col_stride(P::NPAD, C) * (int)sizeof(cplx);
     auto kern = hs_tiled_kernel<P, SGN, C, TW, STCOL, MINB, IO, CS>;
     static bool attr_done = false;

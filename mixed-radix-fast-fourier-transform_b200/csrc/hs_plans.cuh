@@ -49,4 +49,4 @@ using S160xi = HsExact<HsPlan<160, 20, 1, 3, HS_SUB_SPLIT, 0, 8, 4, 5>>;
 enum { CT_4096A = 0, CT_4096B, CT_3000, CT_1024, CT_2048, CT_512, CT_256, CT_8192, CT_B2048, CT_4096X, CT_3000X, CT_4096Y, CT_3000Y, CT_3000Z,
        CT_T14, CT_T15, CT_T16, CT_T17, CT_T18, CT_T19, CT_T20,
        CT_S128, CT_S256, CT_S512, CT_S1024,
-       CT_TX20480, CT_S160X, CT_COUNT };
+       CT_TX20480, CT_TX40960, CT_TX81920, CT_TX163840, CT_S160X, CT_COUNT };
