@@ -50,17 +50,23 @@ static inline void hs_wait_geq(const unsigned *p, unsigned need)
     // CTAs run one after another in the emulation: a dependency that is not already met never will be
     if (__atomic_load_n(p, __ATOMIC_ACQUIRE) < need) { fprintf(stderr, "hs_emu: pipeline dependency not met (ticket order bug)\n"); abort(); }
 }
-// bulk-copy engine (TMA) stand-ins: the copy is done by the issuing thread, the barrier counts bytes
-#include <atomic>
-struct HsMbar { std::atomic<long long> done; };
-static inline void hs_mbar_init(HsMbar *m) { m->done.store(0); }
-static inline void hs_mbar_expect(HsMbar *, unsigned) {}
-static inline void hs_bulk_g2s(void *dst, const void *src, unsigned bytes, HsMbar *m) { memcpy(dst, src, bytes); m->done.fetch_add(bytes); }
-static inline void hs_mbar_wait(HsMbar *m, unsigned /*parity*/, long long seq, long long bytes_per_phase)
-{
-    while (m->done.load() < (seq + 1) * bytes_per_phase) { }
-}
+// bulk-copy engine (TMA) and mbarrier stand-ins with the hardware's phase semantics: a phase completes when the
+// expected arrivals have arrived and the pending transaction bytes are back to zero; copies are done by the
+// issuing thread at issue time
+#include <mutex>
+struct HsMbar { unsigned phase; int count, arrivals; long long tx; };
+extern std::mutex hs_emu_mbar_mu;
+static inline void hs_emu_mbar_check(HsMbar *m) { if (m->arrivals >= m->count && m->tx == 0) { m->phase++; m->arrivals = 0; } }
+static inline void hs_mbar_init_n(HsMbar *m, int count) { m->phase = 0; m->count = count; m->arrivals = 0; m->tx = 0; }
+static inline void hs_mbar_init(HsMbar *m) { hs_mbar_init_n(m, 1); }
+static inline void hs_mbar_expect(HsMbar *m, unsigned bytes) { std::lock_guard<std::mutex> g(hs_emu_mbar_mu); m->tx += bytes; m->arrivals++; hs_emu_mbar_check(m); }
+static inline void hs_mbar_arrive(HsMbar *m) { std::lock_guard<std::mutex> g(hs_emu_mbar_mu); m->arrivals++; hs_emu_mbar_check(m); }
+static inline void hs_emu_mbar_complete_tx(HsMbar *m, long long bytes) { std::lock_guard<std::mutex> g(hs_emu_mbar_mu); m->tx -= bytes; hs_emu_mbar_check(m); }
+static inline bool hs_mbar_test(HsMbar *m, unsigned parity) { std::lock_guard<std::mutex> g(hs_emu_mbar_mu); return (m->phase & 1u) != parity; }
+static inline void hs_mbar_wait(HsMbar *m, unsigned parity) { while (!hs_mbar_test(m, parity)) { } }
+static inline void hs_bulk_g2s(void *dst, const void *src, unsigned bytes, HsMbar *m) { memcpy(dst, src, bytes); hs_emu_mbar_complete_tx(m, bytes); }
 static inline void hs_fence_async_proxy() {}
+static inline void hs_fence_proxy_async_all() {}
 static inline void hs_prefetch_l2(const void *, unsigned) {}
 // 3-D tensor-map stand-in: [z][row][x doubles], strides in bytes
 struct HsTmap { const unsigned char *base; long long row_stride, z_stride; };
@@ -69,8 +75,22 @@ static inline void hs_tma_load_3d(void *dst, const HsTmap *t, int x_dbl, int row
     for (int r = 0; r < rows; ++r)
         memcpy((unsigned char *)dst + (size_t)r * row_bytes, t->base + z * t->z_stride + (long long)(row0 + r) * t->row_stride + (long long)x_dbl * 8,
                row_bytes);
-    m->done.fetch_add((long long)rows * row_bytes);
+    hs_emu_mbar_complete_tx(m, (long long)rows * row_bytes);
 }
+template <int MP>
+static inline void hs_tma_load_3d_mp(void *dst, const HsTmap *t, int x_dbl, int row0, long long z, int rows, int row_bytes, HsMbar *m)
+{
+    hs_tma_load_3d(dst, t, x_dbl, row0, z, rows, row_bytes, m);
+}
+// CTA-scope flags in shared memory between warp roles
+static inline void hs_flag_add(unsigned *p) { __atomic_fetch_add(p, 1u, __ATOMIC_RELEASE); }
+static inline unsigned hs_flag_read(const unsigned *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+static inline void hs_flag_set(unsigned *p, unsigned v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+#include <thread>
+static inline void hs_backoff() { std::this_thread::yield(); }
+void hs_emu_barrier2();
+#define HS_SYNC_COMPUTE(n) hs_emu_barrier2()
+#define HS_TRAP() ((void)0) /* spin counts mean nothing with OS threads; a real deadlock shows as a test timeout */
 #define HS_GRID_CONSTANT
 #else
 // ---------------------------------------------------------------------------- CUDA (product)
@@ -88,7 +108,7 @@ static inline void hs_tma_load_3d(void *dst, const HsTmap *t, int x_dbl, int row
 #define HS_NBLOCKS ((long long)gridDim.x)
 #define HS_SYNC() __syncthreads()
 #define HS_DYN_SMEM(type, name)                                  \
-    extern __shared__ __align__(16) unsigned char hs_smem_raw[]; \
+    extern __shared__ __align__(128) unsigned char hs_smem_raw[]; \
     type *name = reinterpret_cast<type *>(hs_smem_raw)
 #define HS_UNROLL _Pragma("unroll")
 // Signal samples are touched exactly once per pass: keep them out of L1 (no_allocate) so that L1
@@ -156,12 +176,13 @@ HS_DEVICE void hs_st_mp(double2 *p, double2 v)
 }
 // ---- grid-level dataflow: work tickets and completion counters in global memory
 HS_DEVICE unsigned long long hs_ticket_take(unsigned long long *p) { return atomicAdd(p, 1ULL); }
-// after a CTA barrier: publish this CTA's global writes (the fence is cumulative over what the barrier ordered
-// before it), then count the tile as done
+// publish this CTA's global writes, then count the tile as done: a RELEASE reduction (cumulative over what the
+// CTA-scope synchronisation ordered before it).  Not __threadfence() + relaxed: that fence is acq_rel, and its
+// acquire half makes ptxas invalidate the SM's whole L1 (MEMBAR.SC.GPU + CCTL.IVALL) -- once per tile, that threw
+// the stage-twiddle tables out of L1 and put their L2 latency on every tile's critical path (ncu, round 1).
 HS_DEVICE void hs_signal_add(unsigned *p)
 {
-    __threadfence();
-    asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
 }
 // Completion counters are read with ld.relaxed.gpu, not ld.acquire: an acquire at gpu scope makes ptxas
 // invalidate the SM's whole L1 (CCTL.IVALL), which would throw out the twiddle tables on every poll.  The data
@@ -191,6 +212,24 @@ HS_DEVICE void hs_mbar_init(HsMbar *m)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(hs_smem_u32(m)) : "memory");
 }
+HS_DEVICE void hs_mbar_init_n(HsMbar *m, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(hs_smem_u32(m)), "r"(count) : "memory");
+}
+HS_DEVICE void hs_mbar_arrive(HsMbar *m)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(hs_smem_u32(m)) : "memory");
+}
+// non-blocking: has the phase of the given parity completed?
+HS_DEVICE bool hs_mbar_test(HsMbar *m, unsigned parity)
+{
+    unsigned ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok)
+                 : "r"(hs_smem_u32(m)), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
 // one arrival (of the single expected one) announcing `bytes` of asynchronous writes for this phase
 HS_DEVICE void hs_mbar_expect(HsMbar *m, unsigned bytes)
 {
@@ -209,7 +248,7 @@ HS_DEVICE void hs_prefetch_l2(const void *p, unsigned bytes)
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 // wait for the phase of the given parity; a copy that never lands traps instead of hanging the GPU
-HS_DEVICE void hs_mbar_wait(HsMbar *m, unsigned parity, long long, long long)
+HS_DEVICE void hs_mbar_wait(HsMbar *m, unsigned parity)
 {
     const unsigned a = hs_smem_u32(m);
     for (unsigned spin = 0;; ++spin) {
@@ -234,8 +273,41 @@ HS_DEVICE void hs_tma_load_3d(void *dst_smem, const HsTmap *t, int x_dbl, int ro
                  "l"(t), "r"(x_dbl), "r"(row0), "r"((int)z), "r"(hs_smem_u32(m))
                  : "memory");
 }
+// same with an L2 residency class for the tile's lines: MP 1 keep (evict_last), MP 2 stream (evict_first)
+template <int MP>
+HS_DEVICE void hs_tma_load_3d_mp(void *dst_smem, const HsTmap *t, int x_dbl, int row0, long long z, int rows, int row_bytes, HsMbar *m)
+{
+    if (MP == 0) { hs_tma_load_3d(dst_smem, t, x_dbl, row0, z, rows, row_bytes, m); return; }
+    const unsigned long long pol = MP == 1 ? hs_pol_keep() : hs_pol_first();
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;" ::"r"(
+            hs_smem_u32(dst_smem)),
+        "l"(t), "r"(x_dbl), "r"(row0), "r"((int)z), "r"(hs_smem_u32(m)), "l"(pol)
+        : "memory");
+}
 // order this thread's generic-proxy accesses to shared memory before later asynchronous-proxy ones
 HS_DEVICE void hs_fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// same for every state space: a counter read through the generic proxy gates a TMA load of global data
+HS_DEVICE void hs_fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// CTA-scope counters in shared memory between warp roles (producer warp <-> compute warps)
+HS_DEVICE void hs_flag_add(unsigned *p)
+{
+    asm volatile("red.release.cta.shared::cta.add.u32 [%0], 1;" ::"r"(hs_smem_u32(p)) : "memory");
+}
+HS_DEVICE unsigned hs_flag_read(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(hs_smem_u32(p)) : "memory");
+    return v;
+}
+HS_DEVICE void hs_flag_set(unsigned *p, unsigned v)
+{
+    asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(hs_smem_u32(p)), "r"(v) : "memory");
+}
+HS_DEVICE void hs_backoff() { __nanosleep(64); }
+// barrier among the first n threads of the CTA only (the compute warps of a warp-specialised kernel)
+#define HS_SYNC_COMPUTE(n) asm volatile("bar.sync 1, %0;" ::"r"(n) : "memory")
+#define HS_TRAP() __trap()
 #endif
 
 typedef double2 cplx; // x = re, y = im; 16-byte interleaved, same bytes as the API's fft_data

@@ -134,11 +134,9 @@ hs_bluestein_persist_kernel(const cplx *HS_RESTRICT in, cplx *HS_RESTRICT out, c
         hs_mbar_expect(bar, step_bytes(HS_BID));
         hs_bulk_g2s(stage, in + HS_BID * PF::X * N, step_bytes(HS_BID), bar);
     }
-    long long arrived = 0;
     unsigned j = 0;
     for (long long s = HS_BID; s < nstep; s += HS_NBLOCKS, ++j) {
-        arrived += step_bytes(s);
-        hs_mbar_wait(bar, j & 1u, 0, arrived);
+        hs_mbar_wait(bar, j & 1u);
         const long long xf = s * PF::X + team, next = s + HS_NBLOCKS;
         const bool active = xf < howmany;
         cplx *sm = exch + team * PF::NPAD;

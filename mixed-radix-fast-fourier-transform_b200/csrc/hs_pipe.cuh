@@ -1,66 +1,70 @@
-// hs_pipe.cuh -- persistent dataflow pipeline: the passes of a long transform as ONE kernel whose
-// intermediates never leave the L2.
+// hs_pipe.cuh -- persistent, warp-specialised dataflow pipeline: the passes of a long transform as ONE kernel
+// whose intermediates never leave the L2.
 //
 // A transform of 2^14..2^20 points needs two tiled passes (hs_tiled.cuh); run as two launches over the whole
-// batch the intermediate makes a round trip through HBM, which caps the pair at 50 % of the one-pass roofline
-// (r2c: 43 %, long Bluestein: 13 %).  Here the passes are *phases* of one persistent kernel:
+// batch the intermediate makes a round trip through HBM (r2c: 56 N bytes of traffic for 24 N algorithmic, long
+// Bluestein: 4 M + 2 N points for 2 N).  Here the passes are *phases* of one persistent kernel:
 //   * work is cut into tiles (C columns of one transform in one phase) and handed out through a global
 //     ticket counter in an order in which every tile's inputs are produced by tiles with smaller tickets:
 //     round s = [phase 0 of group s | phase 1 of group s-lag | phase 2 of group s-2 lag], a group being G
 //     consecutive transforms;
-//   * a tile of phase j+1 needs the completion counter of phase j of its group to be full; tiles of phase j need
-//     phase j+1 to have drained the ring slot they overwrite.  Both conditions were met long ago when lag and
-//     the slot count are chosen as in hsfft_plan.c -- and because dependencies only point to smaller tickets,
-//     which are held by CTAs that are already running, the scheme cannot deadlock whatever the number of
-//     resident CTAs;
-//   * none of the protocol's latencies is exposed: the next ticket is taken when a tile starts, its two
-//     counters are peeked before the tile's last pass, and the tile's own completion is published (fence +
-//     atomic) by one thread after the NEXT tile has issued its loads (hooks of hs_smem_fft.cuh); a tile whose
-//     counters were full at the peek starts without any extra barrier;
 //   * phase j writes its tiles into slot (group mod nslot) of a small ring; with nslot*G*N*16 bytes well below
 //     the 126 MB L2 and the accesses tagged evict_last (hs_ld_mp / hs_st_mp), the ring is overwritten in place
-//     and its dirty lines never reach HBM.  HBM sees the signal once on the way in and once on the way out.
+//     and its dirty lines never reach HBM.  HBM sees the signal once on the way in and once on the way out;
+//   * a tile of phase j+1 needs the completion counter of phase j of its group to be full; tiles of phase j need
+//     phase j+1 to have drained the ring slot they overwrite.  Dependencies only point to smaller tickets and
+//     nobody blocks while it holds unpublished work, so the scheme cannot deadlock whatever the number of
+//     resident CTAs;
+//   * every CTA has two PRODUCER warps next to its compute warps.  The issuer takes the tickets, peeks the two
+//     counters of the next tile, and -- when they are full -- has the TMA engine stage the tile's C x n strided
+//     input (cp.async.bulk.tensor, UTMALDG) into one of two staging buffers while the compute warps still work
+//     on the previous tile; the publisher makes finished tiles public (fence + atomic).  None of the protocol's
+//     latencies is paid by the warps that do the arithmetic.  Compute warps wait on the staging buffer's
+//     mbarrier, transform, store, bump two shared-memory counters; they synchronise among themselves with a
+//     named barrier (hooks of hs_smem_fft.cuh).
 // The tile bodies are the same device functions the stand-alone pass kernels use (hs_tile_run,
 // hs_blu_mid_run), so results are bit-identical to the multi-launch path.
 #pragma once
 #include "hs_tiled.cuh"
 
-#ifndef HS_PIPE_TILE_FN
-#define HS_PIPE_TILE_FN HS_DEVICE
-#endif
 
 // ----------------------------------------------------------------------------------------- phases
+// NT: compute threads; SMEM: exchange buffer bytes; STAGED: the input tile is ROWS x C and the producer stages it
 struct HsPhNone {
-    static constexpr int NT = 0, SMEM = 0, C = 1;
-    template <int KNT, class HK>
+    static constexpr int NT = 0, SMEM = 0, C = 1, ROWS = 0, STAGE_ELEMS = 0;
+    static constexpr bool STAGED = false;
+    template <class HK>
     static HS_DEVICE void run(const hs_phase_args &, const cplx *, cplx *, long long, int, cplx *, HK &) {}
 };
 
 // one tiled pass; NT_ threads = P::T threads per column x C columns per tile
 template <class P, int SGN, int NT_, int TW, bool STCOL, int IO, int CS, int LDP, int STP>
 struct HsPhTiled {
-    static constexpr int NT = NT_, C = NT_ / P::T;
+    static constexpr int NT = NT_, C = NT_ / P::T, ROWS = P::N;
     static_assert(C * P::T == NT_ && C >= 1, "thread count must be a multiple of the team size");
     static constexpr int SMEM = C * hs_col_stride(P::NPAD, C) * 16;
-    template <int KNT, class HK> // KNT: threads of the kernel's CTA (>= NT; the surplus only takes part in the barriers)
-    static HS_DEVICE void run(const hs_phase_args &pa, const cplx *in_x, cplx *out_x, long long x, int tile, cplx *smem, HK &hk)
+    static constexpr bool STAGED = (IO == 0 || IO == 2); // plain strided loads; the fused loads (chirp, c2r merge) read global memory themselves
+    static constexpr int STAGE_ELEMS = STAGED ? P::N * C : 0;
+    template <class HK>
+    static HS_DEVICE void run(const hs_phase_args &pa, const cplx *src, cplx *out_x, long long x, int tile, cplx *exch, HK &hk)
     {
-        hs_tile_run<P, SGN, C, TW, STCOL, IO, CS, LDP, STP>(in_x, out_x, (const cplx *)pa.tw, pa.g, x, tile * C, smem, HS_TID,
-                                                            KNT == NT ? true : HS_TID < NT, hk);
+        hs_tile_run<P, SGN, C, TW, STCOL, IO, CS, LDP, STP, STAGED>(src, out_x, (const cplx *)pa.tw, pa.g, x, tile * C, exch, HS_TID, true, hk);
     }
 };
 
 // middle of the long Bluestein: forward pass 2, spectrum product, inverse pass 1
 template <class PF, class PI, int CS, int NT_, int LDP, int STP>
 struct HsPhBluMid {
-    static constexpr int NT = NT_, C = NT_ / PF::T;
+    static constexpr int NT = NT_, C = NT_ / PF::T, ROWS = PF::N;
     static_assert(C * PF::T == NT_ && C >= 1, "thread count must be a multiple of the team size");
     static constexpr int SMEM = C * hs_col_stride(PF::NPAD, C) * 16;
-    template <int KNT, class HK>
-    static HS_DEVICE void run(const hs_phase_args &pa, const cplx *in_x, cplx *out_x, long long, int tile, cplx *smem, HK &hk)
+    static constexpr bool STAGED = true;
+    static constexpr int STAGE_ELEMS = PF::N * C;
+    template <class HK>
+    static HS_DEVICE void run(const hs_phase_args &pa, const cplx *src, cplx *out_x, long long, int tile, cplx *exch, HK &hk)
     {
-        hs_blu_mid_run<PF, PI, CS, C, LDP, STP>(in_x, out_x, (const cplx *)pa.tw, (const cplx *)pa.tw_b, pa.g, (const cplx *)pa.aux, tile * C, smem,
-                                                HS_TID, KNT == NT ? true : HS_TID < NT, hk);
+        hs_blu_mid_run<PF, PI, CS, C, LDP, STP, true>(src, out_x, (const cplx *)pa.tw, (const cplx *)pa.tw_b, pa.g, (const cplx *)pa.aux, tile * C, exch,
+                                                      HS_TID, true, hk);
     }
 };
 
@@ -69,10 +73,10 @@ struct HsPhBluMid {
 // pa.g: chirp = twiddle2, nlog = H; pa.flags & 1: write the mirrored upper half.
 template <int NT_, int KPT, int LDP, int STP>
 struct HsPhR2CSplit {
-    static constexpr int NT = NT_, C = 1, SMEM = 0;
+    static constexpr int NT = NT_, C = 1, SMEM = 0, ROWS = 0, STAGE_ELEMS = 0;
+    static constexpr bool STAGED = false;
     static constexpr int KT = NT_ * KPT; // k values per tile
-    static HS_DEVICE cplx bin(cplx a, cplx c, cplx w) { return hs_r2c_bin(a, c, w); }
-    template <int KNT, class HK>
+    template <class HK>
     static HS_DEVICE void run(const hs_phase_args &pa, const cplx *z, cplx *o, long long, int tile, cplx *, HK &)
     {
         const int H = pa.g.nlog;
@@ -81,18 +85,18 @@ struct HsPhR2CSplit {
         HS_UNROLL
         for (int u = 0; u < KPT; ++u) {
             const int k = tile * KT + u * NT + HS_TID;
-            if (HS_TID >= NT || 2 * k > H) continue;
+            if (2 * k > H) continue;
             if (k == 0) {
                 const cplx z0 = hs_ld_mp<LDP>(z);
                 hs_st_mp<STP>(o, hs_c(z0.x + z0.y, 0.0));
                 hs_st_mp<STP>(o + H, hs_c(z0.x - z0.y, 0.0));
             } else {
                 const cplx a = hs_ld_mp<LDP>(z + k), c = (2 * k == H) ? a : hs_ld_mp<LDP>(z + (H - k));
-                const cplx r = bin(a, c, hs_ld_tab(tw2 + k));
+                const cplx r = hs_r2c_bin(a, c, hs_ld_tab(tw2 + k));
                 hs_st_mp<STP>(o + k, r);
                 if (full) hs_st_mp<STP>(o + (2 * H - k), hs_c(r.x, -r.y));
                 if (2 * k != H) {
-                    const cplx r2 = bin(c, a, hs_ld_tab(tw2 + (H - k)));
+                    const cplx r2 = hs_r2c_bin(c, a, hs_ld_tab(tw2 + (H - k)));
                     hs_st_mp<STP>(o + (H - k), r2);
                     if (full) hs_st_mp<STP>(o + (H + k), hs_c(r2.x, -r2.y));
                 }
@@ -102,21 +106,29 @@ struct HsPhR2CSplit {
 };
 
 // ----------------------------------------------------------------------------------------- kernel
+// per-CTA queue between the producer warp and the compute warps
+struct HsPipeQ {
+    HsMbar full[2];            // producer -> compute: the slot's ticket is valid and its staged tile has landed
+    unsigned long long tk[2];  // ticket in the slot (>= total: no more work)
+    unsigned consumed;         // compute -> issuer: tiles whose staging buffer has been read (monotonic)
+    unsigned finished;         // compute -> publisher: tiles whose stores are issued (monotonic)
+    unsigned issued;           // issuer -> publisher: tiles handed to the compute warps (monotonic); bit 31: no more will follow
+    unsigned pad_;
+    unsigned *sig[8];          // issuer -> publisher: completion counter of tile (index mod 8)
+};
+
 template <class PH0, class PH1, class PH2>
 struct HsPipeShape {
     static constexpr int NPH = PH2::NT ? 3 : 2;
     static constexpr int cmax(int a, int b) { return a > b ? a : b; }
-    static constexpr int NT = cmax(PH0::NT, cmax(PH1::NT, PH2::NT));
-    static constexpr int SMEM_TILES = cmax(PH0::SMEM, cmax(PH1::SMEM, PH2::SMEM));
-    static constexpr int SMEM = SMEM_TILES + 64; // + the control block below
-    static constexpr int SIG = NT >= 64 ? 32 : 0; // the thread that publishes completions (not in the poller's warp)
-};
-
-// per-CTA control block in shared memory, double buffered by iteration parity
-struct HsPipeCtl {
-    unsigned long long tk[2];  // ticket of the iteration
-    unsigned *sig[2];          // counter of the previous iteration's tile, still to be published (or null)
-    unsigned rdy[2];           // the ticket's dependencies were seen complete when peeked
+    static constexpr int NT = cmax(PH0::NT, cmax(PH1::NT, PH2::NT)); // compute threads
+    static_assert(PH0::NT == NT && PH1::NT == NT && (PH2::NT == NT || PH2::NT == 0), "every phase uses all compute warps");
+    static constexpr int NTHREADS = NT + 64;                         // + the producer warps (issuer, publisher)
+    static constexpr int EXCH = cmax(PH0::SMEM, cmax(PH1::SMEM, PH2::SMEM));
+    static constexpr int STAGE_ELEMS = cmax(PH0::STAGE_ELEMS, cmax(PH1::STAGE_ELEMS, PH2::STAGE_ELEMS));
+    static constexpr int SMEM = 2 * STAGE_ELEMS * 16 + EXCH + 128;   // staging buffers first (TMA destinations), the queue last
+    // two CTAs per SM where they fit: their load / exchange / arithmetic phases then overlap on the SM's pipes
+    static constexpr int MINB = (2 * (SMEM + 1024) <= 227 * 1024 && NTHREADS <= 256) ? 2 : 1;
 };
 
 struct HsPipeItem {
@@ -138,111 +150,161 @@ HS_DEVICE HsPipeItem hs_pipe_decode(const hs_pipe_args &a, const unsigned long l
     it.valid = it.grp >= 0 && it.grp < a.ngroups;
     return it;
 }
+// where a tile sits: transform x, ring index r, tile number inside the transform
+struct HsPipeWhere { long long x, r; int tile; };
+HS_DEVICE HsPipeWhere hs_pipe_where(const hs_pipe_args &a, const HsPipeItem &it)
+{
+    const unsigned tiles = (unsigned)a.ph[it.j].tiles;
+    const int xl = (int)(it.q / tiles);
+    return HsPipeWhere{it.grp * a.G + xl, (it.grp % a.nslot) * a.G + xl, (int)(it.q % tiles)};
+}
 // the two counters a ticket depends on: its producer phase (same group) and the consumer phase of the group
 // that held its ring slot before.  need == 0: no such dependency.
-struct HsPipeDeps {
-    const unsigned *up, *dn;
-    unsigned need_up, need_dn;
-};
 template <int NPH>
-HS_DEVICE HsPipeDeps hs_pipe_deps(const hs_pipe_args &a, const HsPipeItem &it)
+HS_DEVICE bool hs_pipe_deps_ready(const hs_pipe_args &a, const HsPipeItem &it)
 {
     const unsigned *done = (const unsigned *)((const char *)a.ctl + 128);
-    HsPipeDeps d{done, done, 0u, 0u};
-    if (!it.valid) return d;
-    if (it.j > 0) { d.up = done + (long long)(it.j - 1) * a.ngroups + it.grp; d.need_up = a.items[it.j - 1]; }
-    if (it.j < NPH - 1 && it.grp >= a.nslot) { d.dn = done + (long long)(it.j + 1) * a.ngroups + (it.grp - a.nslot); d.need_dn = a.items[it.j + 1]; }
-    return d;
+    const bool up = it.j > 0, dn = it.j < NPH - 1 && it.grp >= a.nslot;
+    // both loads are issued before either is looked at (one L2 round trip, not two)
+    const unsigned vu = up ? hs_peek(done + (long long)(it.j - 1) * a.ngroups + it.grp) : 0u;
+    const unsigned vd = dn ? hs_peek(done + (long long)(it.j + 1) * a.ngroups + (it.grp - a.nslot)) : 0u;
+    return (!up || vu >= a.items[it.j - 1]) && (!dn || vd >= a.items[it.j + 1]);
 }
 
-template <int NPH, int SIG>
-struct HsPipeHooks {
-    const hs_pipe_args &a;
-    unsigned *sigp;                // SIG thread: completion still to be published
-    unsigned long long nxt;        // thread 0: the next ticket (its atomic may still be in flight)
-    bool next_ready;               // thread 0: set by before_last_pass
-    bool fired1, fired2;
-    HS_DEVICE void after_first_loads()
+// hooks of the compute warps: barriers among the compute threads only, staging buffer handed back after the first pass
+template <int NT>
+struct HsComputeHooks {
+    HsPipeQ *q;
+    bool released;
+    HS_DEVICE void sync() const { HS_SYNC_COMPUTE(NT); }
+    HS_DEVICE void after_first_loads() const { hs_fence_async_proxy(); } // my reads of the staging buffer precede its asynchronous refill
+    HS_DEVICE void after_first_pass()
     {
-        fired1 = true;
-        if (HS_TID == SIG && sigp) hs_signal_add(sigp);
-        sigp = nullptr;
+        released = true;
+        if (HS_TID == 0) hs_flag_add(&q->consumed); // the pass's trailing barrier is behind us: everybody has read the buffer
     }
-    HS_DEVICE void after_first_pass() const {}
-    HS_DEVICE void before_last_pass()
-    {
-        fired2 = true;
-        if (HS_TID == 0) {
-            bool ok = true;
-            if (nxt < a.total) {
-                const HsPipeDeps d = hs_pipe_deps<NPH>(a, hs_pipe_decode(a, nxt));
-                const unsigned vu = d.need_up ? hs_peek(d.up) : 0u, vd = d.need_dn ? hs_peek(d.dn) : 0u;
-                ok = vu >= d.need_up && vd >= d.need_dn;
-            }
-            next_ready = ok;
-        }
-    }
-    HS_DEVICE void flush() // a ticket without a transform inside (padding), or a phase without passes
-    {
-        if (!fired1) after_first_loads();
-        if (!fired2) before_last_pass();
-    }
+    HS_DEVICE void before_last_pass() const {}
 };
 
-template <class PH, int J, int NPH, int KNT, class HK>
-HS_PIPE_TILE_FN void hs_pipe_tile(const hs_pipe_args &a, const long long grp, const unsigned q, cplx *smem, HK &hk)
+template <class PH, int J, int NPH, class HK>
+HS_DEVICE void hs_pipe_tile(const hs_pipe_args &a, const HsPipeItem &it, const cplx *stage, cplx *exch, HK &hk)
 {
     const hs_phase_args &pa = a.ph[J];
-    const int xl = (int)(q / (unsigned)pa.tiles), tile = (int)(q % (unsigned)pa.tiles);
-    const long long x = grp * a.G + xl;
-    if (x >= a.howmany) return; // padding of the last group
-    const long long r = (grp % a.nslot) * a.G + xl;
-    const cplx *in_x = (J == 0) ? (const cplx *)a.in + x * pa.g.in_xf : (const cplx *)a.ring[J ? J - 1 : 0] + r * pa.g.in_xf;
-    cplx *out_x = (J == NPH - 1) ? (cplx *)a.out + x * pa.g.out_xf : (cplx *)a.ring[J < NPH - 1 ? J : 0] + r * pa.g.out_xf;
-    PH::template run<KNT>(pa, in_x, out_x, x, tile, smem, hk);
+    const HsPipeWhere w = hs_pipe_where(a, it);
+    const cplx *src = PH::STAGED ? stage
+                                 : ((J == 0) ? (const cplx *)a.in + w.x * pa.g.in_xf : (const cplx *)a.ring[J ? J - 1 : 0] + w.r * pa.g.in_xf);
+    cplx *out_x = (J == NPH - 1) ? (cplx *)a.out + w.x * pa.g.out_xf : (cplx *)a.ring[J < NPH - 1 ? J : 0] + w.r * pa.g.out_xf;
+    PH::run(pa, src, out_x, w.x, w.tile, exch, hk);
 }
 
-template <class PH0, class PH1, class PH2, int MINB>
-HS_GLOBAL void HS_LAUNCH_BOUNDS((HsPipeShape<PH0, PH1, PH2>::NT), MINB)
-hs_pipe_kernel(const HS_GRID_CONSTANT hs_pipe_args a)
+// producer: make the tile of `it` available in slot b (stage it through the TMA engine, or just release the slot)
+template <class PH, int J>
+HS_DEVICE void hs_pipe_issue(const hs_pipe_args &a, const HsTmap *tm, const HsPipeItem &it, cplx *stage, HsMbar *bar)
+{
+    if constexpr (PH::STAGED) {
+        constexpr int BOXR = PH::ROWS < 256 ? PH::ROWS : 256; // rows per TMA box (hardware limit 256 per dimension)
+        const HsPipeWhere w = hs_pipe_where(a, it);
+        hs_fence_proxy_async_all(); // the counters were read through the generic proxy; the tile is read through the asynchronous one
+        hs_mbar_expect(bar, (unsigned)(PH::STAGE_ELEMS * 16));
+        for (int r0 = 0; r0 < PH::ROWS; r0 += BOXR)
+            hs_tma_load_3d_mp<(J == 0 ? 2 : 1)>(stage + r0 * PH::C, tm, 2 * w.tile * PH::C, r0, J == 0 ? w.x : w.r, BOXR, PH::C * 16, bar);
+    } else {
+        hs_mbar_arrive(bar);
+    }
+}
+
+template <class PH0, class PH1, class PH2>
+HS_GLOBAL void HS_LAUNCH_BOUNDS((HsPipeShape<PH0, PH1, PH2>::NTHREADS), (HsPipeShape<PH0, PH1, PH2>::MINB))
+hs_pipe_kernel(const HS_GRID_CONSTANT hs_pipe_args a, const HS_GRID_CONSTANT HsTmap tm0, const HS_GRID_CONSTANT HsTmap tm1,
+               const HS_GRID_CONSTANT HsTmap tm2)
 {
     using SH = HsPipeShape<PH0, PH1, PH2>;
-    constexpr int NPH = SH::NPH;
+    constexpr int NPH = SH::NPH, NT = SH::NT;
     HS_DYN_SMEM(cplx, smem);
-    HsPipeCtl *const ctl = reinterpret_cast<HsPipeCtl *>(smem + SH::SMEM_TILES / 16);
-    unsigned long long *const ticket = (unsigned long long *)a.ctl;
-    unsigned *const done = (unsigned *)((char *)a.ctl + 128);
+    cplx *const stage0 = smem, *const exch = smem + 2 * SH::STAGE_ELEMS;
+    HsPipeQ *const q = reinterpret_cast<HsPipeQ *>(exch + SH::EXCH / 16);
 
-    if (HS_TID == 0) { ctl->tk[0] = hs_ticket_take(ticket); ctl->sig[0] = nullptr; ctl->rdy[0] = 0u; }
+    if (HS_TID == 0) {
+        hs_mbar_init(&q->full[0]); hs_mbar_init(&q->full[1]);
+        q->consumed = 0; q->finished = 0; q->issued = 0;
+    }
+    hs_fence_async_proxy();
     HS_SYNC();
-    for (int it = 0;; ++it) {
-        const int cur = it & 1;
-        const unsigned long long tk = ctl->tk[cur];
-        HsPipeHooks<NPH, SH::SIG> hk{a, ctl->sig[cur], 0ULL, true, false, false};
-        if (tk >= a.total) { hk.after_first_loads(); break; }
-        if (HS_TID == 0) hk.nxt = hs_ticket_take(ticket); // in flight while this tile runs
-        const HsPipeItem item = hs_pipe_decode(a, tk);
-        if (item.valid) {
-            if (!ctl->rdy[cur]) { // rare: the peek found a counter short.  Publish our own completion first (it may be the
-                hk.after_first_loads(); // one we are waiting for), then poll.
-                hk.fired1 = false;
-                if (HS_TID == 0) {
-                    const HsPipeDeps d = hs_pipe_deps<NPH>(a, item);
-                    if (d.need_up) hs_wait_geq(d.up, d.need_up);
-                    if (d.need_dn) hs_wait_geq(d.dn, d.need_dn);
+
+    if (HS_TID < NT) {
+        // ------------------------------------------------------------------ compute warps
+        for (unsigned i = 0;; ++i) {
+            const int b = (int)(i & 1u);
+            hs_mbar_wait(&q->full[b], (i >> 1) & 1u);
+            const unsigned long long tk = q->tk[b];
+            if (tk >= a.total) break;
+            const HsPipeItem it = hs_pipe_decode(a, tk);
+            const cplx *stage = stage0 + b * SH::STAGE_ELEMS;
+            HsComputeHooks<NT> hk{q, false};
+            if (it.j == 0) hs_pipe_tile<PH0, 0, NPH>(a, it, stage, exch, hk);
+            else if (it.j == 1) hs_pipe_tile<PH1, 1, NPH>(a, it, stage, exch, hk);
+            else if constexpr (NPH == 3) hs_pipe_tile<PH2, 2, NPH>(a, it, stage, exch, hk);
+            if (!hk.released) { hs_fence_async_proxy(); HS_SYNC_COMPUTE(NT); hk.after_first_pass(); } // a phase without passes
+            HS_SYNC_COMPUTE(NT); // every compute thread's stores are issued; the exchange buffer is free
+            if (HS_TID == 0) hs_flag_add(&q->finished);
+        }
+    } else if (HS_TID == NT) {
+        // ------------------------------------------------------------------ issuer (one lane of the first producer warp)
+        unsigned long long *const ticket = (unsigned long long *)a.ctl;
+        unsigned *const done = (unsigned *)((char *)a.ctl + 128);
+        unsigned issued = 0;
+        unsigned long long tk = hs_ticket_take(ticket);
+        for (unsigned idle = 0;;) {
+            bool progress = false;
+            // slot free: its previous tile has left the staging buffer, and the publisher's ring of 8 has room
+            if ((issued < 2 || hs_flag_read(&q->consumed) + 1 >= issued) && issued < hs_flag_read(&q->finished) + 6) {
+                const int b = (int)(issued & 1u);
+                if (tk >= a.total) {
+                    q->tk[b] = tk;
+                    hs_mbar_arrive(&q->full[b]);
+                    hs_flag_set(&q->issued, issued | 0x80000000u);
+                    break;
                 }
-                HS_SYNC();
+                const HsPipeItem it = hs_pipe_decode(a, tk);
+                bool skip = !it.valid;
+                if (it.valid && hs_pipe_where(a, it).x >= a.howmany) { // padding of the last group: nothing to compute, still counted
+                    hs_signal_add(done + (long long)it.j * a.ngroups + it.grp);
+                    skip = true;
+                }
+                if (skip) {
+                    tk = hs_ticket_take(ticket);
+                    progress = true;
+                } else if (hs_pipe_deps_ready<NPH>(a, it)) {
+                    cplx *stage = stage0 + b * SH::STAGE_ELEMS;
+                    q->tk[b] = tk;
+                    q->sig[issued & 7u] = done + (long long)it.j * a.ngroups + it.grp;
+                    if (it.j == 0) hs_pipe_issue<PH0, 0>(a, &tm0, it, stage, &q->full[b]);
+                    else if (it.j == 1) hs_pipe_issue<PH1, 1>(a, &tm1, it, stage, &q->full[b]);
+                    else hs_pipe_issue<PH2, 2>(a, &tm2, it, stage, &q->full[b]);
+                    ++issued;
+                    hs_flag_set(&q->issued, issued);
+                    tk = hs_ticket_take(ticket);
+                    progress = true;
+                }
             }
-            if (item.j == 0) hs_pipe_tile<PH0, 0, NPH, SH::NT>(a, item.grp, item.q, smem, hk);
-            else if (item.j == 1) hs_pipe_tile<PH1, 1, NPH, SH::NT>(a, item.grp, item.q, smem, hk);
-            else if constexpr (NPH == 3) hs_pipe_tile<PH2, 2, NPH, SH::NT>(a, item.grp, item.q, smem, hk);
+            if (progress) idle = 0;
+            else { hs_backoff(); if (++idle > (1u << 25)) HS_TRAP(); } // seconds without progress: fail loudly instead of hanging the GPU
         }
-        hk.flush();
-        if (HS_TID == 0) {
-            ctl->tk[cur ^ 1] = hk.nxt;
-            ctl->rdy[cur ^ 1] = hk.next_ready ? 1u : 0u;
-            ctl->sig[cur ^ 1] = item.valid ? done + (long long)item.j * a.ngroups + item.grp : nullptr;
+    } else if (HS_TID == NT + 32) {
+        // ------------------------------------------------------------------ publisher (one lane of the second producer warp)
+        unsigned published = 0;
+        for (unsigned idle = 0;;) {
+            const unsigned iss = hs_flag_read(&q->issued);
+            if (published < (iss & 0x7fffffffu) && hs_flag_read(&q->finished) > published) {
+                hs_signal_add(q->sig[published & 7u]); // fence (cumulative over the compute warps' stores), then count the tile
+                ++published;
+                idle = 0;
+            } else if ((iss & 0x80000000u) && published == (iss & 0x7fffffffu)) {
+                break;
+            } else {
+                hs_backoff();
+                if (++idle > (1u << 25)) HS_TRAP();
+            }
         }
-        HS_SYNC(); // every thread's stores of this tile are issued; the tile buffers and the control block are handed over
     }
 }

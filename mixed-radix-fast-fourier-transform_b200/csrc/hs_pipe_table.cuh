@@ -1,7 +1,7 @@
 // hs_pipe_table.cuh -- which persistent pipelines (hs_pipe.cuh) exist and how they are dispatched.
 // Included by hs_pipe_inst.cu (one translation unit per two-pass size, -DHS_PIPE_ID=<CT_Txx>) and by
 // tests/emu/hs_device_emu.cpp; the including file provides
-//     template <class PH0, class PH1, class PH2, int MINB> void launch_pipe(hs_pipe_args &a, hs_stream_t st);
+//     template <class PH0, class PH1, class PH2> void launch_pipe(hs_pipe_args &a, hs_stream_t st);
 #pragma once
 #include <cstdio>
 #include <cstdlib>
@@ -10,8 +10,8 @@
 #include "hs_plans.cuh"
 
 // per two-pass size: the sub-plans, their inverse-order partners (Bluestein middle) and the CTA size.
-// V selects the CTA shape: 0 = 256-thread CTAs (512 for 2^18), 1 = half of that (smaller tiles, more independent
-// CTAs per SM whose load / compute / store phases overlap); chosen at run time by HSFFT_PIPE_SHAPE.
+// V selects the CTA shape: 0 = 256 compute threads (512 for 2^18), 1 = half of that (smaller tiles, more CTAs per SM);
+// chosen at run time by HSFFT_PIPE_SHAPE.
 template <int ID> struct HsPipeSubs;
 template <> struct HsPipeSubs<CT_T14> { using P1 = S128;  using P2 = S128;  using P2i = S128i;  static constexpr int NT0 = 256; };
 template <> struct HsPipeSubs<CT_T15> { using P1 = S128;  using P2 = S256;  using P2i = S256i;  static constexpr int NT0 = 256; };
@@ -22,8 +22,7 @@ template <> struct HsPipeSubs<CT_T19> { using P1 = S512;  using P2 = S1024; usin
 template <> struct HsPipeSubs<CT_T20> { using P1 = S1024; using P2 = S1024; using P2i = S1024i; static constexpr int NT0 = 256; };
 template <int ID, int V>
 struct HsPipeCfg : HsPipeSubs<ID> {
-    static constexpr int NT = HsPipeSubs<ID>::NT0 >> V;
-    static constexpr int MINB = NT >= 512 ? 1 : (NT == 256 ? 2 : 4);
+    static constexpr int NT = HsPipeSubs<ID>::NT0 >> V; // compute threads (the producer warp comes on top)
 };
 
 // residency classes: 2 = streamed from / to HBM once (L2 evict_first), 1 = ring slot kept in L2 (evict_last, coherent loads)
@@ -44,7 +43,7 @@ struct HsPipeR2C { // half-length transform, then the split (reference src/real.
     using K = HsPipeCfg<ID, V>;
     using A = HsPhTiled<typename K::P1, SGN, K::NT, 0, false, 0, 1, 2, 1>;
     using B = HsPhTiled<typename K::P2, SGN, K::NT, 1, true, 0, 1, 1, 1>;
-    using C = HsPhR2CSplit<K::NT, 4, 1, 2>;
+    using C = HsPhR2CSplit<K::NT, 16, 1, 2>;
 };
 template <int ID, int V, int CS>
 struct HsPipeBlu { // chirp+pad+forward pass 1 | forward pass 2, *Hk, inverse pass 1 | inverse pass 2, chirp, crop
@@ -79,20 +78,20 @@ static int pipe_dispatch_v(int variant, int sgn, hs_pipe_args &a, hs_stream_t st
     using K = HsPipeCfg<ID, V>;
     switch (variant) {
     case HS_PIPE_C2C:
-        if (sgn == 1) { using W = HsPipeC2C<ID, V, 1>; pipe_fill_tiles<typename W::A, typename W::B, HsPhNone>(a, 0); if (!query) launch_pipe<typename W::A, typename W::B, HsPhNone, K::MINB>(a, st); }
-        else { using W = HsPipeC2C<ID, V, -1>; pipe_fill_tiles<typename W::A, typename W::B, HsPhNone>(a, 0); if (!query) launch_pipe<typename W::A, typename W::B, HsPhNone, K::MINB>(a, st); }
+        if (sgn == 1) { using W = HsPipeC2C<ID, V, 1>; pipe_fill_tiles<typename W::A, typename W::B, HsPhNone>(a, 0); if (!query) launch_pipe<typename W::A, typename W::B, HsPhNone>(a, st); }
+        else { using W = HsPipeC2C<ID, V, -1>; pipe_fill_tiles<typename W::A, typename W::B, HsPhNone>(a, 0); if (!query) launch_pipe<typename W::A, typename W::B, HsPhNone>(a, st); }
         return 1;
     case HS_PIPE_C2R:
         if (sgn != -1) return 0;
-        { using W = HsPipeC2R<ID, V, -1>; pipe_fill_tiles<typename W::A, typename W::B, HsPhNone>(a, 0); if (!query) launch_pipe<typename W::A, typename W::B, HsPhNone, K::MINB>(a, st); }
+        { using W = HsPipeC2R<ID, V, -1>; pipe_fill_tiles<typename W::A, typename W::B, HsPhNone>(a, 0); if (!query) launch_pipe<typename W::A, typename W::B, HsPhNone>(a, st); }
         return 1;
     case HS_PIPE_R2C:
         if (sgn != 1) return 0;
-        { using W = HsPipeR2C<ID, V, 1>; pipe_fill_tiles<typename W::A, typename W::B, typename W::C>(a, W::C::KT); if (!query) launch_pipe<typename W::A, typename W::B, typename W::C, K::MINB>(a, st); }
+        { using W = HsPipeR2C<ID, V, 1>; pipe_fill_tiles<typename W::A, typename W::B, typename W::C>(a, W::C::KT); if (!query) launch_pipe<typename W::A, typename W::B, typename W::C>(a, st); }
         return 1;
     case HS_PIPE_BLU: // sgn = the chirp direction (the plan's sgn)
-        if (sgn == 1) { using W = HsPipeBlu<ID, V, 1>; pipe_fill_tiles<typename W::A, typename W::B, typename W::C>(a, 0); if (!query) launch_pipe<typename W::A, typename W::B, typename W::C, K::MINB>(a, st); }
-        else { using W = HsPipeBlu<ID, V, -1>; pipe_fill_tiles<typename W::A, typename W::B, typename W::C>(a, 0); if (!query) launch_pipe<typename W::A, typename W::B, typename W::C, K::MINB>(a, st); }
+        if (sgn == 1) { using W = HsPipeBlu<ID, V, 1>; pipe_fill_tiles<typename W::A, typename W::B, typename W::C>(a, 0); if (!query) launch_pipe<typename W::A, typename W::B, typename W::C>(a, st); }
+        else { using W = HsPipeBlu<ID, V, -1>; pipe_fill_tiles<typename W::A, typename W::B, typename W::C>(a, 0); if (!query) launch_pipe<typename W::A, typename W::B, typename W::C>(a, st); }
         return 1;
     }
     return 0;

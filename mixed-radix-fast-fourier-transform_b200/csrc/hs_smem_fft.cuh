@@ -98,6 +98,7 @@ struct HsLane {
 // has consumed the input) and before the last pass (one shared-memory exchange and the global stores still to
 // come).  The persistent pipeline kernels (hs_pipe.cuh) run their dataflow protocol there.
 struct HsNoHooks {
+    HS_DEVICE void sync() const { HS_SYNC(); } // the barrier between passes: the whole CTA, unless the caller's warps have roles
     HS_DEVICE void after_first_loads() const {}
     HS_DEVICE void after_first_pass() const {}
     HS_DEVICE void before_last_pass() const {}
@@ -192,7 +193,7 @@ HS_DEVICE void hs_stage(LD &ld, ST &st, const HsLane &ln, const cplx *HS_RESTRIC
             hs_bfly<R, SGN, P::EXACT>(v[u]);
         }
     }
-    if (!FIRST && !LAST) HS_SYNC(); // every thread has read its inputs; the buffer may be overwritten
+    if (!FIRST && !LAST) hk.sync(); // every thread has read its inputs; the buffer may be overwritten
     HS_UNROLL
     for (int u = 0; u < B; ++u) {
         const int b = t + P::T * u;
@@ -204,7 +205,7 @@ HS_DEVICE void hs_stage(LD &ld, ST &st, const HsLane &ln, const cplx *HS_RESTRIC
             }
         }
     }
-    if (!LAST) HS_SYNC();
+    if (!LAST) hk.sync();
 }
 
 // ------------------------------------------------------------- two consecutive stages, fused
@@ -280,7 +281,7 @@ HS_DEVICE void hs_stage2(LD &ld, ST &st, const HsLane &ln, const cplx *HS_RESTRI
             }
         }
     }
-    if (!FIRST && !LAST) HS_SYNC();
+    if (!FIRST && !LAST) hk.sync();
     HS_UNROLL
     for (int u = 0; u < B; ++u) {
         const int b = t + P::T * u;
@@ -296,7 +297,7 @@ HS_DEVICE void hs_stage2(LD &ld, ST &st, const HsLane &ln, const cplx *HS_RESTRI
             }
         }
     }
-    if (!LAST) HS_SYNC();
+    if (!LAST) hk.sync();
 }
 
 template <class P, int SGN, int PASS, class LD, class ST, class HK>
@@ -394,6 +395,7 @@ struct HsPersistSmem {
 };
 // re-arms the staging buffer: every thread's reads of it are ordered before the asynchronous refill
 struct HsPrefetchHook {
+    HS_DEVICE void sync() const { HS_SYNC(); }
     cplx *stage;
     const cplx *next_src; // null: nothing left to prefetch
     unsigned next_bytes;
@@ -430,11 +432,9 @@ hs_c2c_persist_kernel(const cplx *HS_RESTRICT in, cplx *HS_RESTRICT out, const c
         hs_mbar_expect(bar, step_bytes(HS_BID));
         hs_bulk_g2s(stage, in + HS_BID * P::X * P::N, step_bytes(HS_BID), bar);
     }
-    long long arrived = 0; // bytes the barrier has been credited with (emulation bookkeeping)
     unsigned j = 0;
     for (long long s = HS_BID; s < nstep; s += HS_NBLOCKS, ++j) {
-        arrived += step_bytes(s);
-        hs_mbar_wait(bar, j & 1u, 0, arrived);
+        hs_mbar_wait(bar, j & 1u);
         const long long xf = s * P::X + team, next = s + HS_NBLOCKS;
         const bool active = xf < howmany;
         HsLoadStaged ld{stage + team * P::N};

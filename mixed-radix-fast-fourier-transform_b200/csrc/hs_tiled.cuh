@@ -149,6 +149,26 @@ struct HsLoadColC2RPre {
     }
 };
 
+// loaders for a tile the copy engine staged in shared memory, layout [row][C] (dense): with lane = column a
+// quarter-warp reads adjacent 16-byte slots -- conflict free
+struct HsLoadTile {
+    static constexpr bool kPost = false;
+    const cplx *tile; // staged [row][C], already offset by the column
+    int C;
+    HS_DEVICE cplx operator()(int, int, int n) const { return tile[n * C]; }
+};
+struct HsLoadTileTw : HsLoadTile {
+    static constexpr bool kPost = true;
+    const cplx *HS_RESTRICT twb;
+    int tw_ld;
+    cplx step;
+    template <int R>
+    HS_DEVICE void post(int b, cplx *v) const
+    {
+        hs_interpass_twiddle<R>(hs_ld_tab(twb + (long long)b * tw_ld), step, v);
+    }
+};
+
 // One tile: C adjacent columns c0..c0+C-1 of one outer item, whose input / output start at in_x / out_x.
 // P: plan of the sub-transform (P::X is ignored); C: columns per CTA; TW: inter-pass twiddle on load
 // (0 none, 1 keyed by the column, 2 keyed by the outer item xf); STCOL: stores keep lane = column
@@ -156,7 +176,8 @@ struct HsLoadColC2RPre {
 // IO: 0 plain; 1 chirp-and-pad load (CS = chirp direction); 2 chirp-and-crop store; 3 c2r merge on load.
 // tid: thread index in the tile's team of P::T*C threads; on: false for threads (or whole CTAs) that only
 // take part in the barriers.
-template <class P, int SGN, int C, int TW, bool STCOL, int IO, int CS, int LDP, int STP, class HK>
+// STG: the input tile was staged in shared memory by the copy engine ([row][C] at in_x); IO 0 and 2 only.
+template <class P, int SGN, int C, int TW, bool STCOL, int IO, int CS, int LDP, int STP, bool STG = false, class HK>
 HS_DEVICE void hs_tile_run(const cplx *HS_RESTRICT in_x, cplx *HS_RESTRICT out_x, const cplx *HS_RESTRICT tw, const HsTileGeom &g,
                            const long long xf, const int c0, cplx *smem, const int tid, const bool on, HK &hk)
 {
@@ -166,6 +187,7 @@ HS_DEVICE void hs_tile_run(const cplx *HS_RESTRICT in_x, cplx *HS_RESTRICT out_x
     const HsLane first{smem + colA * NPADC, tA, on};
     const HsLane rest = STCOL ? first : HsLane{smem + colB * NPADC, tB, on};
     const int colS = STCOL ? colA : colB;
+    static_assert(!STG || IO == 0 || IO == 2, "only plain tile loads can be staged");
     if constexpr (IO == 1) { // forward pass 1 of the long Bluestein
         HsStoreCol<STP> st{out_x + (long long)(c0 + colS) * g.out_c, g.out_e};
         HsLoadColChirp<CS, LDP> ld{in_x, (const cplx *)g.chirp, g.nlog, (long long)(c0 + colA) * g.in_c, g.in_e};
@@ -178,25 +200,45 @@ HS_DEVICE void hs_tile_run(const cplx *HS_RESTRICT in_x, cplx *HS_RESTRICT out_x
         static_assert(TW != 0, "the chirp-and-crop store belongs to a second pass");
         HsStoreColChirpCrop<CS, STP> st{out_x, (const cplx *)g.chirp, g.nlog, (long long)(c0 + colS) * g.out_c, g.out_e};
         const long long k = (TW == 1) ? (long long)(c0 + colA) : xf;
-        HsLoadColTw<LDP> ld;
-        ld.base = in_x; ld.off0 = (long long)(c0 + colA) * g.in_c; ld.es = g.in_e;
-        ld.blk_log = g.blk_log; ld.blk_stride = g.blk_stride;
-        ld.twb = (const cplx *)g.twb + k; ld.tw_ld = g.tw_ld; ld.step = on ? hs_ld_tab((const cplx *)g.tws + k) : hs_c(0.0, 0.0);
-        hs_fft_team2<P, SGN>(ld, st, first, rest, tw, hk);
+        if constexpr (STG) {
+            HsLoadTileTw ld;
+            ld.tile = in_x + colA; ld.C = C;
+            ld.twb = (const cplx *)g.twb + k; ld.tw_ld = g.tw_ld; ld.step = on ? hs_ld_tab((const cplx *)g.tws + k) : hs_c(0.0, 0.0);
+            hs_fft_team2<P, SGN>(ld, st, first, rest, tw, hk);
+        } else {
+            HsLoadColTw<LDP> ld;
+            ld.base = in_x; ld.off0 = (long long)(c0 + colA) * g.in_c; ld.es = g.in_e;
+            ld.blk_log = g.blk_log; ld.blk_stride = g.blk_stride;
+            ld.twb = (const cplx *)g.twb + k; ld.tw_ld = g.tw_ld; ld.step = on ? hs_ld_tab((const cplx *)g.tws + k) : hs_c(0.0, 0.0);
+            hs_fft_team2<P, SGN>(ld, st, first, rest, tw, hk);
+        }
     } else if constexpr (TW != 0) {
         HsStoreCol<STP> st{out_x + (long long)(c0 + colS) * g.out_c, g.out_e};
         const long long k = (TW == 1) ? (long long)(c0 + colA) : xf;
-        HsLoadColTw<LDP> ld;
-        ld.base = in_x; ld.off0 = (long long)(c0 + colA) * g.in_c; ld.es = g.in_e;
-        ld.blk_log = g.blk_log; ld.blk_stride = g.blk_stride;
-        ld.twb = (const cplx *)g.twb + k; ld.tw_ld = g.tw_ld; ld.step = on ? hs_ld_tab((const cplx *)g.tws + k) : hs_c(0.0, 0.0);
-        hs_fft_team2<P, SGN>(ld, st, first, rest, tw, hk);
+        if constexpr (STG) {
+            HsLoadTileTw ld;
+            ld.tile = in_x + colA; ld.C = C;
+            ld.twb = (const cplx *)g.twb + k; ld.tw_ld = g.tw_ld; ld.step = on ? hs_ld_tab((const cplx *)g.tws + k) : hs_c(0.0, 0.0);
+            hs_fft_team2<P, SGN>(ld, st, first, rest, tw, hk);
+        } else {
+            HsLoadColTw<LDP> ld;
+            ld.base = in_x; ld.off0 = (long long)(c0 + colA) * g.in_c; ld.es = g.in_e;
+            ld.blk_log = g.blk_log; ld.blk_stride = g.blk_stride;
+            ld.twb = (const cplx *)g.twb + k; ld.tw_ld = g.tw_ld; ld.step = on ? hs_ld_tab((const cplx *)g.tws + k) : hs_c(0.0, 0.0);
+            hs_fft_team2<P, SGN>(ld, st, first, rest, tw, hk);
+        }
     } else {
         HsStoreCol<STP> st{out_x + (long long)(c0 + colS) * g.out_c, g.out_e};
-        HsLoadCol<LDP> ld;
-        ld.base = in_x; ld.off0 = (long long)(c0 + colA) * g.in_c; ld.es = g.in_e;
-        ld.blk_log = g.blk_log; ld.blk_stride = g.blk_stride;
-        hs_fft_team2<P, SGN>(ld, st, first, rest, tw, hk);
+        if constexpr (STG) {
+            HsLoadTile ld;
+            ld.tile = in_x + colA; ld.C = C;
+            hs_fft_team2<P, SGN>(ld, st, first, rest, tw, hk);
+        } else {
+            HsLoadCol<LDP> ld;
+            ld.base = in_x; ld.off0 = (long long)(c0 + colA) * g.in_c; ld.es = g.in_e;
+            ld.blk_log = g.blk_log; ld.blk_stride = g.blk_stride;
+            hs_fft_team2<P, SGN>(ld, st, first, rest, tw, hk);
+        }
     }
 }
 
@@ -221,24 +263,6 @@ hs_tiled_kernel(const cplx *HS_RESTRICT in, cplx *HS_RESTRICT out, const cplx *H
 // exposes once per CTA (ncu: 25-30 % of its stall samples) disappears behind the previous tile's work.
 // Staging layout [row][column] (dense): with lane = column, a quarter-warp reads 8 adjacent 16-byte
 // slots -- conflict free.  Requires in_c == 1 and no remap; other geometries use hs_tiled_kernel.
-struct HsLoadTile {
-    static constexpr bool kPost = false;
-    const cplx *tile; // staged [row][C], already offset by the column
-    int C;
-    HS_DEVICE cplx operator()(int, int, int n) const { return tile[n * C]; }
-};
-struct HsLoadTileTw : HsLoadTile {
-    static constexpr bool kPost = true;
-    const cplx *HS_RESTRICT twb;
-    int tw_ld;
-    cplx step;
-    template <int R>
-    HS_DEVICE void post(int b, cplx *v) const
-    {
-        hs_interpass_twiddle<R>(hs_ld_tab(twb + (long long)b * tw_ld), step, v);
-    }
-};
-
 template <class P, int C>
 struct HsTmaTileSmem {
     static constexpr int NPADC = hs_col_stride(P::NPAD, C);
@@ -284,7 +308,7 @@ hs_tiled_tma_kernel(const HS_GRID_CONSTANT HsTmap tmap, cplx *HS_RESTRICT out, c
         const int buf = (int)(j & 1);
         const long long next = tile_id + HS_NBLOCKS;
         if (next < total) issue(next, buf ^ 1); // the other buffer was drained before the last barrier of tile j-1
-        hs_mbar_wait(&bar[buf], (unsigned)((j >> 1) & 1), j >> 1, (long long)TE * 16);
+        hs_mbar_wait(&bar[buf], (unsigned)((j >> 1) & 1));
         const long long xf = tile_id / tiles;
         const int c0 = (int)(tile_id % tiles) * C;
         const cplx *stage = buf ? stage1 : stage0;
@@ -325,13 +349,15 @@ struct HsStoreRegsMulCol {
 template <class HK>
 struct HsFirstHook {
     HK &h;
+    HS_DEVICE void sync() { h.sync(); }
     HS_DEVICE void after_first_loads() { h.after_first_loads(); }
-    HS_DEVICE void after_first_pass() {}
+    HS_DEVICE void after_first_pass() { h.after_first_pass(); }
     HS_DEVICE void before_last_pass() {}
 };
 template <class HK>
 struct HsLastHook {
     HK &h;
+    HS_DEVICE void sync() { h.sync(); }
     HS_DEVICE void after_first_loads() {}
     HS_DEVICE void after_first_pass() {}
     HS_DEVICE void before_last_pass() { h.before_last_pass(); }
@@ -343,7 +369,8 @@ struct HsLoadRegsCol {
     HS_DEVICE cplx operator()(int u, int i, int) const { return y[u][i]; }
 };
 
-template <class PF, class PI, int CS, int C, int LDP, int STP, class HK>
+// STG: the tile's input was staged in shared memory by the copy engine ([row][C] at in_x) instead of being read from global memory
+template <class PF, class PI, int CS, int C, int LDP, int STP, bool STG = false, class HK>
 HS_DEVICE void hs_blu_mid_run(const cplx *HS_RESTRICT in_x, cplx *HS_RESTRICT out_x, const cplx *HS_RESTRICT twf, const cplx *HS_RESTRICT twi,
                               const HsTileGeom &g, const cplx *HS_RESTRICT hk, const int c0, cplx *smem, const int tid, const bool on, HK &hooks)
 {
@@ -358,13 +385,20 @@ HS_DEVICE void hs_blu_mid_run(const cplx *HS_RESTRICT in_x, cplx *HS_RESTRICT ou
     cplx y[B][RL];
 
     const long long k = c0 + colA;
-    HsLoadColTw<LDP> ld;
-    ld.base = in_x; ld.off0 = k * g.in_c; ld.es = g.in_e; ld.blk_log = 0; ld.blk_stride = 0;
-    ld.twb = (const cplx *)g.twb + k; ld.tw_ld = g.tw_ld; ld.step = on ? hs_ld_tab((const cplx *)g.tws + k) : hs_c(0.0, 0.0);
     HsStoreRegsMulCol<CS, RL> st{y, hk + k, (long long)g.ncols}; // Hk[k + n1 j]
     HsFirstHook<HK> h1{hooks}; // the forward transform loads from memory, the inverse one stores to it
-    hs_fft_team2<PF, 1>(ld, st, laneA, laneA, twf, h1);
-    HS_SYNC();
+    if constexpr (STG) {
+        HsLoadTileTw ld;
+        ld.tile = in_x + colA; ld.C = C;
+        ld.twb = (const cplx *)g.twb + k; ld.tw_ld = g.tw_ld; ld.step = on ? hs_ld_tab((const cplx *)g.tws + k) : hs_c(0.0, 0.0);
+        hs_fft_team2<PF, 1>(ld, st, laneA, laneA, twf, h1);
+    } else {
+        HsLoadColTw<LDP> ld;
+        ld.base = in_x; ld.off0 = k * g.in_c; ld.es = g.in_e; ld.blk_log = 0; ld.blk_stride = 0;
+        ld.twb = (const cplx *)g.twb + k; ld.tw_ld = g.tw_ld; ld.step = on ? hs_ld_tab((const cplx *)g.tws + k) : hs_c(0.0, 0.0);
+        hs_fft_team2<PF, 1>(ld, st, laneA, laneA, twf, h1);
+    }
+    hooks.sync();
     HsLoadRegsCol<RL> ld2{y};
     HsStoreCol<STP> st2{out_x + (long long)(c0 + colB) * g.out_c, g.out_e};
     HsLastHook<HK> h2{hooks};

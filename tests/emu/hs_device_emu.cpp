@@ -95,14 +95,20 @@ static void launch_tiled(const void *in, void *out, const void *tw, const HsTile
 #include "hs_ct_table.cuh"
 
 // persistent pipelines: CTAs run one after another here, so the first one drains the ticket counter; the
-// emulation checks the ticket order (a dependency that is not met aborts), the geometry and the numerics
-template <class PH0, class PH1, class PH2, int MINB>
+// emulation checks the ticket order, the producer / compute hand-over, the geometry and the numerics
+template <class PH>
+static HsTmap phase_tmap(const hs_pipe_args &a, int j)
+{
+    HsTmap m{nullptr, 0, 0};
+    if (PH::STAGED) m = HsTmap{(const unsigned char *)(j == 0 ? a.in : a.ring[j - 1]), (long long)a.ph[j].g.in_e * 16, (long long)a.ph[j].g.in_xf * 16};
+    return m;
+}
+template <class PH0, class PH1, class PH2>
 static void launch_pipe(hs_pipe_args &a, hs_stream_t)
 {
     using SH = HsPipeShape<PH0, PH1, PH2>;
-    const long long ngroups = (a.howmany + a.G - 1) / a.G;
-    memset(a.ctl, 0, HS_PIPE_CTL_BYTES(ngroups));
-    hs_emu_launch(hs_pipe_kernel<PH0, PH1, PH2, MINB>, 2, SH::NT, SH::SMEM, a);
+    memset(a.ctl, 0, HS_PIPE_CTL_BYTES(a.ngroups));
+    hs_emu_launch(hs_pipe_kernel<PH0, PH1, PH2>, 2, SH::NTHREADS, SH::SMEM, a, phase_tmap<PH0>(a, 0), phase_tmap<PH1>(a, 1), phase_tmap<PH2>(a, 2));
     ++g_launches;
 }
 #include "hs_pipe_table.cuh"

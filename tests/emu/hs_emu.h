@@ -11,7 +11,7 @@
 #include <vector>
 #include "hs_common.cuh"
 
-extern std::barrier<> *hs_emu_bar;
+extern std::barrier<> *hs_emu_bar, *hs_emu_bar2;
 
 template <class K, class... Args>
 void hs_emu_launch(K kernel, long long grid, int block, size_t smem_bytes, Args... args)
@@ -20,8 +20,9 @@ void hs_emu_launch(K kernel, long long grid, int block, size_t smem_bytes, Args.
     hs_emu_gridDim.x = (unsigned)grid;
     std::vector<unsigned char> smem(smem_bytes + 64);
     for (long long bid = 0; bid < grid; ++bid) {
-        std::barrier<> bar(block);
+        std::barrier<> bar(block), bar2(block > 64 ? block - 64 : block); // bar2: the compute warps of a warp-specialised kernel (two producer warps on top)
         hs_emu_bar = &bar;
+        hs_emu_bar2 = &bar2;
         std::vector<std::thread> th;
         th.reserve(block);
         for (int t = 0; t < block; ++t)
