@@ -129,6 +129,9 @@ struct HsPipeShape {
     static constexpr int SMEM = 2 * STAGE_ELEMS * 16 + EXCH + 128;   // staging buffers first (TMA destinations), the queue last
     // two CTAs per SM where they fit: their load / exchange / arithmetic phases then overlap on the SM's pipes
     static constexpr int MINB = (2 * (SMEM + 1024) <= 227 * 1024 && NTHREADS <= 256) ? 2 : 1;
+    // Registers are handed out per warp in blocks of 512: 168 per thread (what ptxas picks for 2 x 192 threads) rounds
+    // up to 176 and the second CTA no longer fits.  Declaring a slightly larger CTA caps ptxas at 160.
+    static constexpr int BOUND = (MINB == 2 && NTHREADS == 192) ? 204 : NTHREADS;
 };
 
 struct HsPipeItem {
@@ -214,7 +217,7 @@ HS_DEVICE void hs_pipe_issue(const hs_pipe_args &a, const HsTmap *tm, const HsPi
 }
 
 template <class PH0, class PH1, class PH2>
-HS_GLOBAL void HS_LAUNCH_BOUNDS((HsPipeShape<PH0, PH1, PH2>::NTHREADS), (HsPipeShape<PH0, PH1, PH2>::MINB))
+HS_GLOBAL void HS_LAUNCH_BOUNDS((HsPipeShape<PH0, PH1, PH2>::BOUND), (HsPipeShape<PH0, PH1, PH2>::MINB))
 hs_pipe_kernel(const HS_GRID_CONSTANT hs_pipe_args a, const HS_GRID_CONSTANT HsTmap tm0, const HS_GRID_CONSTANT HsTmap tm1,
                const HS_GRID_CONSTANT HsTmap tm2)
 {
