@@ -62,6 +62,17 @@ void hsfft_dist_cols_dev(hsfft_dist_object d, const fft_data *d_a, fft_data *d_b
 /* phase B: out[k1l][k2] = FFT_N2 over n2 of r[n2 / Cw][k1l][n2 % Cw] (r as received from the all-to-all) */
 void hsfft_dist_rows_dev(hsfft_dist_object d, const fft_data *d_r, fft_data *d_out, fft_data *d_ws, void *stream);
 long long hsfft_dist_slab_elems(hsfft_dist_object d);
+/* Exchange fused into phase A (no all-to-all): every rank allocates its receive buffer with hsfft_malloc_device,
+ * publishes hsfft_ipc_get_handle()'s 64 bytes to the others (any transport), and passes all ranks' handles, ordered by
+ * rank, to hsfft_dist_set_peers.  hsfft_dist_cols_exchange_dev then stores each output row, already multiplied by
+ * the exchange twiddle, straight into the receive buffer of the rank that owns it (NVLink peer stores issued by the
+ * transform kernel itself).  The caller barriers the ranks before hsfft_dist_rows_dev reads the buffer, and alternates
+ * two receive buffers (set_peers once per buffer, on two plans or between calls) if transforms follow back to back.
+ * hsfft_dist_set_peer_pointers: same for buffers already addressable from this process. */
+void hsfft_ipc_get_handle(void *d_buf, void *handle64);
+void hsfft_dist_set_peers(hsfft_dist_object d, void *d_own_r, const void *handles64, int nhandles);
+void hsfft_dist_set_peer_pointers(hsfft_dist_object d, void *const *peer_r, int npeers);
+void hsfft_dist_cols_exchange_dev(hsfft_dist_object d, const fft_data *d_a, fft_data *d_ws, void *stream);
 void hsfft_dist_free(hsfft_dist_object d);
 
 /* ---- 4. device helpers ---- */

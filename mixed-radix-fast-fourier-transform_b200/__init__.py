@@ -50,6 +50,7 @@ EXPORTS = [
     "hsfft_malloc_host", "hsfft_free_host", "hsfft_copy_h2d", "hsfft_copy_d2h", "hsfft_sync", "hsfft_launch_count",
     "hsfft_plan_describe", "hsfft_version",
     "hsfft_dist_init", "hsfft_dist_cols_dev", "hsfft_dist_rows_dev", "hsfft_dist_slab_elems", "hsfft_dist_free",
+    "hsfft_ipc_get_handle", "hsfft_dist_set_peers", "hsfft_dist_set_peer_pointers", "hsfft_dist_cols_exchange_dev",
 ]
 
 
@@ -78,6 +79,8 @@ def _bind(L):
         "hsfft_launch_count": (ll, []), "hsfft_plan_describe": (cp, [P]), "hsfft_version": (cp, []),
         "hsfft_dist_init": (vp, [i, i, i, i, i]), "hsfft_dist_cols_dev": (None, [vp, vp, vp, vp, vp]),
         "hsfft_dist_rows_dev": (None, [vp, vp, vp, vp, vp]), "hsfft_dist_slab_elems": (ll, [vp]), "hsfft_dist_free": (None, [vp]),
+        "hsfft_ipc_get_handle": (None, [vp, vp]), "hsfft_dist_set_peers": (None, [vp, vp, vp, i]),
+        "hsfft_dist_set_peer_pointers": (None, [vp, vp, i]), "hsfft_dist_cols_exchange_dev": (None, [vp, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)

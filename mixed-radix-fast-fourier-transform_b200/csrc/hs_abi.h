@@ -98,6 +98,19 @@ typedef struct hs_tile_geom {
     int nlog;
 } hs_tile_geom;
 
+/* Four-step exchange fused into phase A's last pass (io_mode 7 of hs_cu_launch_tiled_io): every output row k1 of the
+ * rank's column slab is multiplied by the exchange twiddle W_N^(n2 k1) and stored straight into the receive buffer of
+ * the rank that owns row k1 -- peer memory mapped through CUDA IPC, the stores travel over NVLink while the
+ * pass computes.  One such struct per plan lives in device memory (hs_tile_geom.chirp points to it). */
+#define HS_DIST_MAX_RANKS 16
+typedef struct hs_dist_store {
+    void *peer[HS_DIST_MAX_RANKS]; /* peer[g']: rank g''s receive buffer r[g][k1l][c] (own buffer for g' = rank) */
+    const void *hi, *lo;           /* W_N^e = hi[e >> logS] * lo[e & (2^logS - 1)] */
+    long long Cw, Kw;              /* columns / rows per rank */
+    long long row_mul;             /* global row of output element k of outer item x: x + row_mul * k */
+    int logKw, logN, logS, rank;
+} hs_dist_store;
+
 /* ---- persistent pipeline kernels (hs_pipe.cuh): a chain of up to HS_PIPE_MAX_PHASE tile phases whose
  * intermediates live in rings of workspace slots small enough to stay in L2 ---- */
 #define HS_PIPE_MAX_PHASE 3
@@ -153,6 +166,10 @@ float hs_cu_event_elapsed_ms(void *start, void *stop);
 void  hs_cu_event_sync(void *ev);
 int   hs_cu_sm_count(void);
 long long hs_cu_launch_count(void);          /* kernels launched by this library so far */
+/* CUDA IPC: a 64-byte handle of a hs_cu_malloc'ed buffer, and its mapping in another process on the same node */
+void  hs_cu_ipc_get(void *d, void *handle64);
+void *hs_cu_ipc_open(const void *handle64);
+void  hs_cu_ipc_close(void *mapped);
 
 /* ---- compile-time kernels ---- */
 int   hs_cu_ct_count(void);

@@ -130,6 +130,25 @@ struct HsStoreColChirpCrop {
     }
 };
 
+// Four-step exchange fused into the last pass of phase A (north_star config 5; see hs_dist_store in hs_abi.h): output
+// element k of column c of outer item x is row k1 = x + row_mul k of the rank's slab b[k1][c]; it is multiplied by
+// W_N^((rank Cw + c) k1) and stored into the receive buffer of rank k1 / Kw at r[rank][k1 mod Kw][c].  With lane =
+// column a warp writes runs of C*16 contiguous bytes per row, which is what NVLink wants.
+struct HsStoreColDist {
+    const hs_dist_store *HS_RESTRICT ds;
+    long long x; // outer item
+    int c;       // column inside the slab
+    HS_DEVICE void operator()(int, int, int k, cplx v) const
+    {
+        const unsigned long long k1 = (unsigned long long)(x + ds->row_mul * k);
+        const unsigned long long n2 = (unsigned long long)(ds->rank * ds->Cw + c);
+        const unsigned long long e = (k1 * n2) & ((1ULL << ds->logN) - 1);
+        const cplx w = hs_mul(hs_ld_tab((const cplx *)ds->hi + (e >> ds->logS)), hs_ld_tab((const cplx *)ds->lo + (e & ((1ULL << ds->logS) - 1))));
+        cplx *dst = (cplx *)ds->peer[k1 >> ds->logKw] + ((ds->rank * ds->Kw + (long long)(k1 & (unsigned long long)(ds->Kw - 1))) * ds->Cw + c);
+        *dst = hs_mul(v, w); // plain store: peer memory (or the own buffer), visible system-wide when the kernel ends
+    }
+};
+
 // c2r merge (reference src/real.c:171-179) fused into pass 1 of the half-length transform: element k of the
 // packed signal is built from bins k and H-k of the Hermitian input on the fly, so the merged signal is
 // never written to HBM.
@@ -173,7 +192,8 @@ struct HsLoadTileTw : HsLoadTile {
 // P: plan of the sub-transform (P::X is ignored); C: columns per CTA; TW: inter-pass twiddle on load
 // (0 none, 1 keyed by the column, 2 keyed by the outer item xf); STCOL: stores keep lane = column
 // instead of switching to lane = thread of a team (contiguous output rows).
-// IO: 0 plain; 1 chirp-and-pad load (CS = chirp direction); 2 chirp-and-crop store; 3 c2r merge on load.
+// IO: 0 plain; 1 chirp-and-pad load (CS = chirp direction); 2 chirp-and-crop store; 3 c2r merge on load;
+// 7 four-step exchange on store (g.chirp = the plan's hs_dist_store in device memory).
 // tid: thread index in the tile's team of P::T*C threads; on: false for threads (or whole CTAs) that only
 // take part in the barriers.
 // STG: the input tile was staged in shared memory by the copy engine ([row][C] at in_x); IO 0 and 2 only.
@@ -196,6 +216,21 @@ HS_DEVICE void hs_tile_run(const cplx *HS_RESTRICT in_x, cplx *HS_RESTRICT out_x
         HsStoreCol<STP> st{out_x + (long long)(c0 + colS) * g.out_c, g.out_e};
         HsLoadColC2RPre<LDP> ld{in_x, (const cplx *)g.chirp, g.nlog, (long long)(c0 + colA) * g.in_c, g.in_e};
         hs_fft_team2<P, SGN>(ld, st, first, rest, tw, hk);
+    } else if constexpr (IO == 7) { // last pass of phase A of the distributed transform: twiddle and store to the owning rank
+        static_assert(STCOL && TW != 1, "the exchange store keeps lane = column");
+        HsStoreColDist st{(const hs_dist_store *)g.chirp, xf, c0 + colS};
+        if constexpr (TW == 2) {
+            HsLoadColTw<LDP> ld;
+            ld.base = in_x; ld.off0 = (long long)(c0 + colA) * g.in_c; ld.es = g.in_e;
+            ld.blk_log = g.blk_log; ld.blk_stride = g.blk_stride;
+            ld.twb = (const cplx *)g.twb + xf; ld.tw_ld = g.tw_ld; ld.step = on ? hs_ld_tab((const cplx *)g.tws + xf) : hs_c(0.0, 0.0);
+            hs_fft_team2<P, SGN>(ld, st, first, rest, tw, hk);
+        } else {
+            HsLoadCol<LDP> ld;
+            ld.base = in_x; ld.off0 = (long long)(c0 + colA) * g.in_c; ld.es = g.in_e;
+            ld.blk_log = g.blk_log; ld.blk_stride = g.blk_stride;
+            hs_fft_team2<P, SGN>(ld, st, first, rest, tw, hk);
+        }
     } else if constexpr (IO == 2) { // inverse last pass of the long Bluestein
         static_assert(TW != 0, "the chirp-and-crop store belongs to a second pass");
         HsStoreColChirpCrop<CS, STP> st{out_x, (const cplx *)g.chirp, g.nlog, (long long)(c0 + colS) * g.out_c, g.out_e};

@@ -34,6 +34,8 @@ struct hsfft_dist_set {
     int logN, logS, logCw;
     hs_axis ax1, ax2;
     void *d_hi, *d_lo;
+    void *d_store;          /* hs_dist_store in device memory once the peers' receive buffers are known */
+    void *mapped[HS_DIST_MAX_RANKS]; /* IPC mappings this plan opened (closed by hsfft_dist_free) */
 };
 
 static int ilog2_exact(long long v)
@@ -153,8 +155,85 @@ void hsfft_dist_free(hsfft_dist_object d)
 {
     if (!d) return;
     axis_free(&d->ax1); axis_free(&d->ax2);
-    hs_cu_free(d->d_hi); hs_cu_free(d->d_lo);
+    hs_cu_free(d->d_hi); hs_cu_free(d->d_lo); hs_cu_free(d->d_store);
+    for (int g = 0; g < HS_DIST_MAX_RANKS; ++g) hs_cu_ipc_close(d->mapped[g]);
     free(d);
+}
+
+/* ---- exchange fused into phase A: every rank's receive buffer is mapped into every other rank (CUDA IPC over
+ * NVLink peer access) and phase A's last pass stores each twiddled row straight into its owner's buffer ---- */
+
+void hsfft_ipc_get_handle(void *d_buf, void *handle64) { hs_cu_require_device(); hs_cu_ipc_get(d_buf, handle64); }
+
+void hsfft_dist_set_peers(hsfft_dist_object d, void *d_own_r, const void *handles64, int nhandles)
+{
+    /* handles64: nranks handles of 64 bytes, ordered by rank (the own slot is ignored: d_own_r is used);
+     * handles64 == NULL: every "peer" is d_own_r's process -- pointers are passed instead (tests, one process) */
+    if (!d || !d_own_r || nhandles != d->nranks || d->nranks > HS_DIST_MAX_RANKS) {
+        fprintf(stderr, "Error: Invalid inputs for hsfft_dist_set_peers\n");
+        exit(EXIT_FAILURE);
+    }
+    hs_dist_store st;
+    memset(&st, 0, sizeof st);
+    for (int g = 0; g < d->nranks; ++g) {
+        if (g == d->rank) { st.peer[g] = d_own_r; continue; }
+        hs_cu_ipc_close(d->mapped[g]);
+        d->mapped[g] = hs_cu_ipc_open((const char *)handles64 + 64 * (size_t)g);
+        st.peer[g] = d->mapped[g];
+    }
+    st.hi = d->d_hi; st.lo = d->d_lo;
+    st.Cw = d->Cw; st.Kw = d->Kw;
+    st.row_mul = d->ax1.two ? d->ax1.n1 : 1;
+    st.logKw = ilog2_exact(d->Kw); st.logN = d->logN; st.logS = d->logS; st.rank = d->rank;
+    if (!d->d_store) d->d_store = hs_cu_malloc(sizeof st);
+    hs_cu_h2d(d->d_store, &st, sizeof st, NULL);
+    hs_cu_stream_sync(NULL);
+}
+
+void hsfft_dist_set_peer_pointers(hsfft_dist_object d, void *const *peer_r, int npeers)
+{
+    /* same, for peers whose buffers are already addressable from this process (one process driving several plans) */
+    if (!d || !peer_r || npeers != d->nranks || d->nranks > HS_DIST_MAX_RANKS) {
+        fprintf(stderr, "Error: Invalid inputs for hsfft_dist_set_peer_pointers\n");
+        exit(EXIT_FAILURE);
+    }
+    hs_dist_store st;
+    memset(&st, 0, sizeof st);
+    for (int g = 0; g < d->nranks; ++g) st.peer[g] = peer_r[g];
+    st.hi = d->d_hi; st.lo = d->d_lo;
+    st.Cw = d->Cw; st.Kw = d->Kw;
+    st.row_mul = d->ax1.two ? d->ax1.n1 : 1;
+    st.logKw = ilog2_exact(d->Kw); st.logN = d->logN; st.logS = d->logS; st.rank = d->rank;
+    if (!d->d_store) d->d_store = hs_cu_malloc(sizeof st);
+    hs_cu_h2d(d->d_store, &st, sizeof st, NULL);
+    hs_cu_stream_sync(NULL);
+}
+
+void hsfft_dist_cols_exchange_dev(hsfft_dist_object d, const fft_data *d_a, fft_data *d_ws, void *stream)
+{
+    /* phase A and the exchange in one: b is never materialised, its rows go to their owners as they are produced.
+     * The caller synchronises the ranks afterwards (all stores have landed when every rank's kernel has ended). */
+    if (!d || !d_a || !d_ws || !d->d_store) { fprintf(stderr, "Error: Invalid distributed plan, data pointers or peers not set\n"); exit(EXIT_FAILURE); }
+    const hs_axis *ax = &d->ax1;
+    const long long W = d->Cw;
+    hs_tile_geom g;
+    memset(&g, 0, sizeof g);
+    g.ncols = (int)W;
+    g.in_c = 1; g.out_c = 1;
+    g.chirp = d->d_store;
+    if (!ax->two) {
+        g.in_e = W; g.out_e = W;
+        hs_cu_launch_tiled_io(ax->sub1, d->sgn, 0, 1, 7, 1, d_a, NULL, ax->d_tw1, &g, 1, stream);
+        return;
+    }
+    const long long L1 = ax->n1, L2 = ax->n2;
+    g.chirp = NULL;
+    g.in_xf = W; g.in_e = W * L2; g.out_xf = L1 * W; g.out_e = W;
+    hs_cu_launch_tiled(ax->sub1, d->sgn, 0, 1, d_a, d_ws, ax->d_tw1, &g, L2, stream);
+    g.in_xf = W; g.in_e = L1 * W; g.out_xf = W; g.out_e = L1 * W;
+    g.twb = ax->d_twb; g.tws = ax->d_tws; g.tw_ld = (int)L1;
+    g.chirp = d->d_store;
+    hs_cu_launch_tiled_io(ax->sub2, d->sgn, 2, 1, 7, 1, d_ws, NULL, ax->d_tw2, &g, L1, stream);
 }
 
 long long hsfft_dist_slab_elems(hsfft_dist_object d) { return (long long)d->N1 * d->Cw; }

@@ -77,3 +77,14 @@ def test_four_step_layout_helpers():
     # out[k1l][k2] on rank g is X[(g Kw + k1l) + N1 k2]
     parts = [np.array([[(g * 2 + k1l) + N1 * k2 for k2 in range(N2)] for k1l in range(2)]) for g in range(G)]
     assert np.array_equal(dmod.gather_output(parts, N1, N2), np.arange(N1 * N2))
+
+
+@pytest.mark.parametrize("N1,N2,world,sgn", [(128, 256, 2, 1), (256, 128, 4, -1), (16384, 128, 2, 1)])
+def test_four_step_exchange_fused_into_phase_a(hs, emu_lib, oracle, N1, N2, world, sgn):
+    """Peer-store path: phase A's last pass (one-pass and two-pass axis) twiddles and stores every row into the
+    owning rank's receive buffer; all ranks are driven by one process here (same address space)."""
+    import oracle_lib as ol
+    dmod = importlib.import_module("mixed-radix-fast-fourier-transform_b200.dist")
+    x = ol.rand_cplx(1, N1 * N2, seed=N1 + N2 + world)[0]
+    X = dmod.local_group_forward(hs, x, N1, N2, sgn, world, lib=emu_lib)
+    assert ol.rel_rms(X, oracle.c2c(x, sgn)) <= ol.tol(N1 * N2)

@@ -19,11 +19,17 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+def plan_ptr(t):
+    import ctypes
+    return ctypes.c_void_p(t.data_ptr())
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--log2n", type=int, default=30)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--bins", type=int, default=64)
+    ap.add_argument("--p2p", action="store_true", help="exchange fused into phase A (peer stores over NVLink) instead of an NCCL all-to-all")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -49,13 +55,29 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    plan.forward(a, out)  # warm-up (NCCL channels, kernels)
+    if args.p2p:
+        plan.enable_p2p()
+    fwd = plan.forward_p2p if args.p2p else plan.forward
+    fwd(a, out)  # warm-up (NCCL channels, kernels)
+    fwd(a, out)
     sync()
     tA = tX = tB = 0.0
     for _ in range(args.steps):
         e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         sync()
-        e[0].record(); plan.cols(a); e[1].record(); plan.exchange(); e[2].record(); plan.rows(out); e[3].record()
+        if args.p2p:  # phase A includes the exchange; "exchange" is what is left of it: the barrier
+            par = plan.calls & 1
+            plan.calls += 1
+            e[0].record()
+            plan.L.hsfft_dist_cols_exchange_dev(plan.pp[par], plan_ptr(a), plan_ptr(plan.ws), plan._stream())
+            e[1].record()
+            if world > 1:
+                dist.all_reduce(plan._flag)
+            e[2].record()
+            plan.L.hsfft_dist_rows_dev(plan.pp[par], plan.rbuf[par], plan_ptr(out), plan_ptr(plan.ws), plan._stream())
+            e[3].record()
+        else:
+            e[0].record(); plan.cols(a); e[1].record(); plan.exchange(); e[2].record(); plan.rows(out); e[3].record()
         sync()
         t = torch.tensor([e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2]), e[2].elapsed_time(e[3])], device=dev, dtype=torch.float64)
         if world > 1:
@@ -98,10 +120,12 @@ def main():
         passes_a = 2 * (2 if N1 > 1024 else 1) + 2  # tiled passes (read+write each) + twiddle pass
         passes_b = 2 * (2 if N2 > 1024 else 1)
         line = {"workload": "single c2c N=2^%d fp64, four-step %dx%d on %d GPUs" % (args.log2n, N1, N2, world),
+                "exchange": "fused into phase A: peer stores over NVLink from the transform kernel, all-reduce barrier" if args.p2p
+                            else "NCCL all_to_all_single between the phases",
                 "ms_total": total, "ms_cols": tA, "ms_exchange": tX, "ms_rows": tB,
                 "gflops": 5.0 * N * args.log2n / (total * 1e-3) / 1e9,
                 "local_hbm_gbs_per_gpu": {"cols": passes_a * slab / (tA * 1e-3) / 1e9, "rows": passes_b * slab / (tB * 1e-3) / 1e9},
-                "exchange_gbs_per_gpu_per_direction": slab * (world - 1) / world / (tX * 1e-3) / 1e9 if world > 1 else None,
+                "exchange_gbs_per_gpu_per_direction": (slab * (world - 1) / world / ((tA if args.p2p else tX) * 1e-3) / 1e9) if world > 1 else None,
                 "nvlink_peak_gbs": 900, "nvlink_measured_gbs": 770,
                 "sampled_bins": args.bins, "rel_rms_err_sampled": err, "tolerance": 1e-12 * args.log2n, "parseval_rel": parseval,
                 "ok": bool(err <= 1e-12 * args.log2n and parseval < 1e-12)}
