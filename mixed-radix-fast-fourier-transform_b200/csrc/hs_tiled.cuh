@@ -218,7 +218,7 @@ HS_DEVICE void hs_tile_run(const cplx *HS_RESTRICT in_x, cplx *HS_RESTRICT out_x
         hs_fft_team2<P, SGN>(ld, st, first, rest, tw, hk);
     } else if constexpr (IO == 7) { // last pass of phase A of the distributed transform: twiddle and store to the owning rank
         static_assert(STCOL && TW != 1, "the exchange store keeps lane = column");
-        HsStoreColDist st{(const hs_dist_store *)g.chirp, xf, c0 + colS};
+        HsStoreColDist st{(const hs_dist_store *)g.chirp, xf, g.nlog + c0 + colS}; // g.nlog: first slab column of this launch's chunk
         if constexpr (TW == 2) {
             HsLoadColTw<LDP> ld;
             ld.base = in_x; ld.off0 = (long long)(c0 + colA) * g.in_c; ld.es = g.in_e;

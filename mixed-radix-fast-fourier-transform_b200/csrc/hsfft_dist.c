@@ -35,6 +35,7 @@ struct hsfft_dist_set {
     hs_axis ax1, ax2;
     void *d_hi, *d_lo;
     void *d_store;          /* hs_dist_store in device memory once the peers' receive buffers are known */
+    void *s1, *s2, *ev_fork, *ev_join1, *ev_join2, *ev_chunk[16]; /* two internal streams: pass 1 of chunk i+1 runs under pass 2 of chunk i */
     void *mapped[HS_DIST_MAX_RANKS]; /* IPC mappings this plan opened (closed by hsfft_dist_free) */
 };
 
@@ -157,6 +158,11 @@ void hsfft_dist_free(hsfft_dist_object d)
     axis_free(&d->ax1); axis_free(&d->ax2);
     hs_cu_free(d->d_hi); hs_cu_free(d->d_lo); hs_cu_free(d->d_store);
     for (int g = 0; g < HS_DIST_MAX_RANKS; ++g) hs_cu_ipc_close(d->mapped[g]);
+    if (d->s1) {
+        hs_cu_stream_destroy(d->s1); hs_cu_stream_destroy(d->s2);
+        hs_cu_event_destroy(d->ev_fork); hs_cu_event_destroy(d->ev_join1); hs_cu_event_destroy(d->ev_join2);
+        for (int i = 0; i < 16; ++i) hs_cu_event_destroy(d->ev_chunk[i]);
+    }
     free(d);
 }
 
@@ -226,14 +232,46 @@ void hsfft_dist_cols_exchange_dev(hsfft_dist_object d, const fft_data *d_a, fft_
         hs_cu_launch_tiled_io(ax->sub1, d->sgn, 0, 1, 7, 1, d_a, NULL, ax->d_tw1, &g, 1, stream);
         return;
     }
+    /* Two passes.  Only the second one talks to the peers; HSFFT_DIST_CHUNKS=k cuts the slab into k column chunks and
+     * runs pass 1 of chunk i+1 (on a second stream) under pass 2 of chunk i so that the NVLink stores start earlier.
+     * Measured at 2^30 on 8 GPUs: 4.65 ms with 1 chunk, 4.68 with 2, 4.73 with 4 -- pass 2's CTAs, stalled on their
+     * peer stores, hold the SMs and the next chunk's pass 1 does not get in; so the default is one chunk. */
     const long long L1 = ax->n1, L2 = ax->n2;
-    g.chirp = NULL;
-    g.in_xf = W; g.in_e = W * L2; g.out_xf = L1 * W; g.out_e = W;
-    hs_cu_launch_tiled(ax->sub1, d->sgn, 0, 1, d_a, d_ws, ax->d_tw1, &g, L2, stream);
-    g.in_xf = W; g.in_e = L1 * W; g.out_xf = W; g.out_e = L1 * W;
-    g.twb = ax->d_twb; g.tws = ax->d_tws; g.tw_ld = (int)L1;
-    g.chirp = d->d_store;
-    hs_cu_launch_tiled_io(ax->sub2, d->sgn, 2, 1, 7, 1, d_ws, NULL, ax->d_tw2, &g, L1, stream);
+    int chunks = 1;
+    if (getenv("HSFFT_DIST_CHUNKS")) chunks = atoi(getenv("HSFFT_DIST_CHUNKS"));
+    if (chunks > 16) chunks = 16;
+    while (chunks > 1 && (W % chunks != 0 || (W / chunks) % 64 != 0)) chunks /= 2;
+    if (chunks < 1) chunks = 1;
+    const long long Wc = W / chunks;
+    if (chunks > 1 && !d->s1) {
+        d->s1 = hs_cu_stream_create(); d->s2 = hs_cu_stream_create();
+        d->ev_fork = hs_cu_event_create(); d->ev_join1 = hs_cu_event_create(); d->ev_join2 = hs_cu_event_create();
+        for (int i = 0; i < 16; ++i) d->ev_chunk[i] = hs_cu_event_create();
+    }
+    void *sa = chunks > 1 ? d->s1 : stream, *sb = chunks > 1 ? d->s2 : stream;
+    if (chunks > 1) {
+        hs_cu_event_record(d->ev_fork, stream);
+        hs_cu_stream_wait_event(sa, d->ev_fork);
+        hs_cu_stream_wait_event(sb, d->ev_fork);
+    }
+    for (int i = 0; i < chunks; ++i) {
+        const fft_data *src = d_a + i * Wc;
+        fft_data *mid = d_ws + i * Wc;
+        memset(&g, 0, sizeof g);
+        g.ncols = (int)Wc; g.in_c = 1; g.out_c = 1;
+        g.in_xf = W; g.in_e = W * L2; g.out_xf = L1 * W; g.out_e = W;
+        hs_cu_launch_tiled(ax->sub1, d->sgn, 0, 1, src, mid, ax->d_tw1, &g, L2, sa);
+        if (chunks > 1) { hs_cu_event_record(d->ev_chunk[i], sa); hs_cu_stream_wait_event(sb, d->ev_chunk[i]); }
+        g.in_xf = W; g.in_e = L1 * W; g.out_xf = W; g.out_e = L1 * W;
+        g.twb = ax->d_twb; g.tws = ax->d_tws; g.tw_ld = (int)L1;
+        g.chirp = d->d_store; g.nlog = (int)(i * Wc);
+        hs_cu_launch_tiled_io(ax->sub2, d->sgn, 2, 1, 7, 1, mid, NULL, ax->d_tw2, &g, L1, sb);
+    }
+    if (chunks > 1) {
+        hs_cu_event_record(d->ev_join1, sa); hs_cu_event_record(d->ev_join2, sb);
+        hs_cu_stream_wait_event(stream, d->ev_join1);
+        hs_cu_stream_wait_event(stream, d->ev_join2);
+    }
 }
 
 long long hsfft_dist_slab_elems(hsfft_dist_object d) { return (long long)d->N1 * d->Cw; }
