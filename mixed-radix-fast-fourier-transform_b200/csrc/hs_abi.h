@@ -96,6 +96,13 @@ typedef struct hs_tile_geom {
     /* Bluestein fusions (io_mode of hs_cu_launch_tiled_io): the chirp h[n] and the logical length */
     const void *chirp;
     int nlog;
+    /* convolution fusions: io_mode 4 = rows of nlog reals, zero padded on load (in_xf must be 0);
+     * io_mode 5 = c2r merge of the product aux[k]*in[k]*scale (aux: second spectrum, same row stride as in);
+     * io_mode 6 = store only reals [sl_start, sl_start+sl_len) of every row, to rows of aux_xf reals (out_xf must be 0) */
+    const void *aux;
+    long long aux_xf;
+    double scale;
+    int sl_start, sl_len;
 } hs_tile_geom;
 
 /* Four-step exchange fused into phase A's last pass (io_mode 7 of hs_cu_launch_tiled_io): every output row k1 of the
@@ -184,7 +191,7 @@ void  hs_cu_launch_ct_twopass(int id, int pass, int sgn, const void *d_in, void 
  * the tiled kernel with explicit geometry */
 void  hs_cu_launch_tiled(int sub_id, int sgn, int tw_mode, int stcol, const void *d_in, void *d_out, const void *d_tw,
                          const hs_tile_geom *g, long long howmany, void *stream);
-/* same with a fused Bluestein end: io_mode 1 = load x[n]*conj(h[n]) (chirp_sgn=+1; *h[n] for -1) for n < nlog
+/* same with a fused end (see hs_tile_geom for io_mode 3..7): io_mode 1 = load x[n]*conj(h[n]) (chirp_sgn=+1; *h[n] for -1) for n < nlog
  * and zero beyond (input rows are nlog long); io_mode 2 = store y[n]*conj(h[n]) (resp. *h[n]) for n < nlog only */
 void  hs_cu_launch_tiled_io(int sub_id, int sgn, int tw_mode, int stcol, int io_mode, int chirp_sgn, const void *d_in, void *d_out,
                             const void *d_tw, const hs_tile_geom *g, long long howmany, void *stream);

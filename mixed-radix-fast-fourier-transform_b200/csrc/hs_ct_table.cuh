@@ -233,6 +233,11 @@ static void launch_sub_io(int sgn, int tw_mode, int stcol, int io_mode, int cs, 
     } else if (io_mode == 3 && tw_mode == 0 && !stcol) {
         if (sgn == 1) launch_tiled<P, 1, C, 0, false, 3, 1>(in, out, tw, g, howmany, st);
         else launch_tiled<P, -1, C, 0, false, 3, 1>(in, out, tw, g, howmany, st);
+    } else if ((io_mode == 4 || io_mode == 5) && tw_mode == 0 && !stcol) {
+        if (io_mode == 4) { if (sgn == 1) launch_tiled<P, 1, C, 0, false, 4, 1>(in, out, tw, g, howmany, st); else launch_tiled<P, -1, C, 0, false, 4, 1>(in, out, tw, g, howmany, st); }
+        else { if (sgn == 1) launch_tiled<P, 1, C, 0, false, 5, 1>(in, out, tw, g, howmany, st); else launch_tiled<P, -1, C, 0, false, 5, 1>(in, out, tw, g, howmany, st); }
+    } else if (io_mode == 6 && tw_mode == 1 && stcol) {
+        if (sgn == 1) launch_tiled<P, 1, C, 1, true, 6, 1>(in, out, tw, g, howmany, st); else launch_tiled<P, -1, C, 1, true, 6, 1>(in, out, tw, g, howmany, st);
     } else if (io_mode == 7 && stcol && (tw_mode == 0 || tw_mode == 2)) {
         if (tw_mode == 2) { if (sgn == 1) launch_tiled<P, 1, C, 2, true, 7, 1>(in, out, tw, g, howmany, st); else launch_tiled<P, -1, C, 2, true, 7, 1>(in, out, tw, g, howmany, st); }
         else { if (sgn == 1) launch_tiled<P, 1, C, 0, true, 7, 1>(in, out, tw, g, howmany, st); else launch_tiled<P, -1, C, 0, true, 7, 1>(in, out, tw, g, howmany, st); }

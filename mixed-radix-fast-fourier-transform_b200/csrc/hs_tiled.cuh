@@ -188,11 +188,54 @@ struct HsLoadTileTw : HsLoadTile {
     }
 };
 
+// Convolution fusions (reference src/convolve.c:117-200): the zero padding rides on the first pass's loads of the
+// forward transforms, the spectrum product and the 1/P scale on the merge loads of the inverse one, the output
+// slice on its last pass's stores -- the padded inputs, the product and the full-length result never exist in HBM.
+struct HsLoadColPadReal { // rows of len reals read as rows of complex pairs, zero beyond len (8-byte loads: rows may be 8-byte aligned only)
+    static constexpr bool kPost = false;
+    const double *HS_RESTRICT row;
+    int len;
+    long long off0, es;
+    HS_DEVICE cplx operator()(int, int, int n_) const
+    {
+        const long long r = 2 * (off0 + n_ * es);
+        return hs_c(r < len ? hs_ld_stream_d(row + r) : 0.0, r + 1 < len ? hs_ld_stream_d(row + r + 1) : 0.0);
+    }
+};
+struct HsLoadColC2RMul { // element k of the packed signal from bins k and H-k of the product of two spectra
+    static constexpr bool kPost = false;
+    const cplx *HS_RESTRICT xa, *HS_RESTRICT xb; // bins 0..H of the two spectra
+    const cplx *HS_RESTRICT tw2;
+    int H;
+    double scale;
+    long long off0, es;
+    HS_DEVICE cplx operator()(int, int, int n_) const
+    {
+        const long long k = off0 + n_ * es;
+        const cplx pa = hs_mul(hs_ld_stream(xa + k), hs_ld_stream(xb + k)), pc = hs_mul(hs_ld_stream(xa + (H - k)), hs_ld_stream(xb + (H - k)));
+        const cplx a = hs_c(pa.x * scale, pa.y * scale), c = hs_c(pc.x * scale, pc.y * scale), w = hs_ld_tab(tw2 + k); // reference :147-160
+        const double t1 = -a.y - c.y, t2 = -c.x + a.x;
+        return hs_c(a.x + c.x + (t1 * w.x) - (t2 * w.y), a.y - c.y + (t2 * w.x) + (t1 * w.y));
+    }
+};
+struct HsStoreColSlice { // complex element k of the row = reals 2k, 2k+1; keep [start, start+len)
+    double *HS_RESTRICT row; // destination row (already at its first kept real)
+    int start, len;
+    long long off0, es;
+    HS_DEVICE void operator()(int, int, int k_, cplx v) const
+    {
+        const long long r = 2 * (off0 + k_ * es) - start;
+        if (r >= 0 && r < len) hs_st_stream_d(row + r, v.x);
+        if (r + 1 >= 0 && r + 1 < len) hs_st_stream_d(row + r + 1, v.y);
+    }
+};
+
 // One tile: C adjacent columns c0..c0+C-1 of one outer item, whose input / output start at in_x / out_x.
 // P: plan of the sub-transform (P::X is ignored); C: columns per CTA; TW: inter-pass twiddle on load
 // (0 none, 1 keyed by the column, 2 keyed by the outer item xf); STCOL: stores keep lane = column
 // instead of switching to lane = thread of a team (contiguous output rows).
 // IO: 0 plain; 1 chirp-and-pad load (CS = chirp direction); 2 chirp-and-crop store; 3 c2r merge on load;
+// 4 zero padding on load, 5 spectrum product on merge load, 6 slice on store (convolution);
 // 7 four-step exchange on store (g.chirp = the plan's hs_dist_store in device memory).
 // tid: thread index in the tile's team of P::T*C threads; on: false for threads (or whole CTAs) that only
 // take part in the barriers.
@@ -215,6 +258,22 @@ HS_DEVICE void hs_tile_run(const cplx *HS_RESTRICT in_x, cplx *HS_RESTRICT out_x
     } else if constexpr (IO == 3) { // c2r: merge fused into pass 1 (g.chirp = twiddle2, g.nlog = H)
         HsStoreCol<STP> st{out_x + (long long)(c0 + colS) * g.out_c, g.out_e};
         HsLoadColC2RPre<LDP> ld{in_x, (const cplx *)g.chirp, g.nlog, (long long)(c0 + colA) * g.in_c, g.in_e};
+        hs_fft_team2<P, SGN>(ld, st, first, rest, tw, hk);
+    } else if constexpr (IO == 4) { // convolution: zero padding on load (g.nlog reals per row, rows back to back)
+        HsStoreCol<STP> st{out_x + (long long)(c0 + colS) * g.out_c, g.out_e};
+        HsLoadColPadReal ld{(const double *)in_x + xf * g.nlog, g.nlog, (long long)(c0 + colA) * g.in_c, g.in_e};
+        hs_fft_team2<P, SGN>(ld, st, first, rest, tw, hk);
+    } else if constexpr (IO == 5) { // convolution: product of two spectra, scaled, merged (g.chirp = twiddle2, g.nlog = H)
+        HsStoreCol<STP> st{out_x + (long long)(c0 + colS) * g.out_c, g.out_e};
+        HsLoadColC2RMul ld{in_x, (const cplx *)g.aux + xf * g.in_xf, (const cplx *)g.chirp, g.nlog, g.scale, (long long)(c0 + colA) * g.in_c, g.in_e};
+        hs_fft_team2<P, SGN>(ld, st, first, rest, tw, hk);
+    } else if constexpr (IO == 6) { // convolution: slice on store (rows of g.aux_xf reals)
+        static_assert(TW == 1 && STCOL, "the slice store belongs to a second pass");
+        HsStoreColSlice st{(double *)out_x + xf * g.aux_xf, g.sl_start, g.sl_len, (long long)(c0 + colS) * g.out_c, g.out_e};
+        HsLoadColTw<LDP> ld;
+        ld.base = in_x; ld.off0 = (long long)(c0 + colA) * g.in_c; ld.es = g.in_e;
+        ld.blk_log = g.blk_log; ld.blk_stride = g.blk_stride;
+        ld.twb = (const cplx *)g.twb + (c0 + colA); ld.tw_ld = g.tw_ld; ld.step = on ? hs_ld_tab((const cplx *)g.tws + (c0 + colA)) : hs_c(0.0, 0.0);
         hs_fft_team2<P, SGN>(ld, st, first, rest, tw, hk);
     } else if constexpr (IO == 7) { // last pass of phase A of the distributed transform: twiddle and store to the owning rank
         static_assert(STCOL && TW != 1, "the exchange store keeps lane = column");

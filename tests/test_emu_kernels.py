@@ -161,6 +161,24 @@ def test_convolution(hs, emu_lib, oracle, la, lb):
     assert hs.convolve(a, b, "full", "nope", lib=emu_lib)[0] == -1
 
 
+def test_long_convolution_fused_padding_product_and_slice(hs, emu_lib, oracle):
+    """P >= 2^15: the zero padding rides on pass 1's loads, the product and 1/P on the merge loads of the inverse
+    transform, the slice on its stores.  Odd lengths: rows of a batch are then only 8-byte aligned."""
+    la, lb = 20001, 12999                       # conv_length 32999 -> P = 65536
+    a = xorshift_uniform(2 * la, seed=3).reshape(2, la)
+    b = xorshift_uniform(2 * lb, seed=4).reshape(2, lb)
+    c0 = hs.launch_count(lib=emu_lib) if hasattr(hs, "launch_count") else 0
+    n, y = hs.convolve_batch(a, b, lib=emu_lib)
+    assert n == la + lb - 1
+    for i in range(2):
+        nr, yr = oracle.convolve(a[i], b[i], "full", "linear")
+        assert nr == n and rel_rms(y[i], yr) <= 1e-13
+    for t in ("same", "valid"):
+        n, y1 = hs.convolve(a[0], b[0], t, "linear", lib=emu_lib)
+        nr, yr = oracle.convolve(a[0], b[0], t, "linear")
+        assert n == nr and rel_rms(y1, yr) <= 1e-13, t
+
+
 def test_convolution_batch(hs, emu_lib):
     a = xorshift_uniform(4 * 50, 3).reshape(4, 50)
     b = xorshift_uniform(4 * 20, 4).reshape(4, 20)

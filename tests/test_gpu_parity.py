@@ -120,7 +120,7 @@ def test_real_r2c_c2r(hs, product_lib, oracle, n):
         assert rel_rms(y / n, x) <= tol(n)
 
 
-@pytest.mark.parametrize("la,lb", [(5, 3), (100, 37), (512, 512), (1000, 24), (4096, 4096)])
+@pytest.mark.parametrize("la,lb", [(5, 3), (100, 37), (512, 512), (1000, 24), (4096, 4096), (20001, 12999), (300000, 200001), (524288, 524288)])
 @pytest.mark.parametrize("type_", ["full", "same", "valid"])
 def test_convolve_linear(hs, product_lib, oracle, la, lb, type_):
     a = xorshift_uniform(la, seed=la)
@@ -129,6 +129,31 @@ def test_convolve_linear(hs, product_lib, oracle, la, lb, type_):
     nr, yr = oracle.convolve(a, b, type_, "linear")
     assert n == nr
     assert rel_rms(y, yr) <= 1e-12 * math.log2(max(la + lb, 4))
+
+
+def test_convolve_batch_fused_path_matches_unfused(hs, product_lib):
+    """Batched long convolution (BASELINE config 4): the fused path (padding / product / slice on the transforms' own
+    loads and stores) against the unfused kernel sequence, odd lengths so that rows are only 8-byte aligned."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import importlib,sys,numpy as np;sys.path.insert(0,%r);sys.path.insert(0,%r+'/tests');"
+            "hs=importlib.import_module('mixed-radix-fast-fourier-transform_b200');from oracle_lib import xorshift_uniform as xu;"
+            "a=xu(5*70001,1).reshape(5,70001);b=xu(5*33333,2).reshape(5,33333);n,y=hs.convolve_batch(a,b);"
+            "np.save(sys.argv[1],y);print(n)") % (root, root)
+    outs = []
+    for fuse in ("1", "0"):
+        env = dict(os.environ)
+        if fuse == "0":
+            env["HSFFT_NO_CONV_FUSE"] = "1"
+        f = "/tmp/hsfft_conv_%s.npy" % fuse
+        r = subprocess.run([sys.executable, "-c", code, f], capture_output=True, text=True, env=env, timeout=300)
+        assert r.returncode == 0 and r.stdout.strip() == str(70001 + 33333 - 1), r.stdout + r.stderr[-800:]
+        outs.append(np.load(f))
+    assert rel_rms(outs[0], outs[1]) <= 1e-14
+    a = xorshift_uniform(70001, 1)
+    b = xorshift_uniform(5 * 33333, 2).reshape(5, 33333)[0]
+    assert rel_rms(outs[0][0], np.convolve(a, b)) <= 1e-12
 
 
 def test_convolve_circular_and_errors(hs, product_lib, oracle):
