@@ -151,9 +151,10 @@ def test_convolve_batch_fused_path_matches_unfused(hs, product_lib):
         assert r.returncode == 0 and r.stdout.strip() == str(70001 + 33333 - 1), r.stdout + r.stderr[-800:]
         outs.append(np.load(f))
     assert rel_rms(outs[0], outs[1]) <= 1e-14
-    a = xorshift_uniform(70001, 1)
-    b = xorshift_uniform(5 * 33333, 2).reshape(5, 33333)[0]
-    assert rel_rms(outs[0][0], np.convolve(a, b)) <= 1e-12
+    a = xorshift_uniform(5 * 70001, 1).reshape(5, 70001)
+    b = xorshift_uniform(5 * 33333, 2).reshape(5, 33333)
+    for i in (0, 4):
+        assert rel_rms(outs[0][i], np.convolve(a[i], b[i])) <= 1e-12
 
 
 def test_convolve_circular_and_errors(hs, product_lib, oracle):
