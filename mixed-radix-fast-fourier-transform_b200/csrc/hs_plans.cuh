@@ -11,18 +11,28 @@
 //                      N     T   X  LOGPAD SPLIT GROUPS radices...
 using P4096a = HsPlan<4096, 256, 1, 4, -1, 0, 16, 16, 16>;       // reference factors [8,8,8,8]
 using P4096b = HsPlan<4096, 512, 1, 3, -1, 0, 8, 8, 8, 8>;
-using P3000  = HsPlan<3000, 200, 1, 3, -1, 221, 3, 5, 5, 5, 8>; // reference factors [8,5,5,5,3] verbatim; passes {3,5}{5,5}{8}
+// Twiddle mode of the plans that are bound by the L1/LSU pipe plus FP64 rather than by HBM (measured on B200, fraction of
+// the HBM peak with SPLIT 0 / -1 / -2 = load every row / rows 1,2,4,8 / row 1 only and form the rest by products):
+// N = 3000 61.4 / 75.6 / 78.4 %, fused Bluestein N = 1009 23.8 / 26.1 / 26.9 %, long Bluestein N = 10007 (sub-plans)
+// 11.6 / 12.5 / 13.0 %; the two-pass c2c sizes do not care.  Fewer loads win even at the price of more multiplies.
+#ifndef HS_3000_SPLIT
+#define HS_3000_SPLIT -2
+#endif
+#ifndef HS_B2048_SPLIT
+#define HS_B2048_SPLIT -2
+#endif
+using P3000  = HsPlan<3000, 200, 1, 3, HS_3000_SPLIT, 221, 3, 5, 5, 5, 8>; // reference factors [8,5,5,5,3] verbatim; passes {3,5}{5,5}{8}
 using P1024  = HsPlan<1024, 64, 4, 3, -1, 0, 16, 8, 8>;          // reference factors [8,8,8,2]
 using P2048  = HsPlan<2048, 128, 2, 3, -1, 0, 16, 16, 8>;        // reference factors [8,8,8,4]
 using P512   = HsPlan<512, 64, 4, 3, -1, 0, 8, 8, 8>;
 using P256   = HsPlan<256, 16, 16, 4, -1, 0, 16, 16>;
 using P8192  = HsPlan<8192, 512, 1, 4, -1, 0, 8, 8, 8, 16>;
 // fused Bluestein, M = 2048 (N = 513..1024, e.g. the N = 1009 config): forward / inverse pair
-using PB2048f = HsPlan<2048, 128, 2, 4, -1, 0, 8, 16, 16>;
-using PB2048i = HsPlan<2048, 128, 2, 4, -1, 0, 16, 16, 8>;
+using PB2048f = HsPlan<2048, 128, 2, 4, HS_B2048_SPLIT, 0, 8, 16, 16>;
+using PB2048i = HsPlan<2048, 128, 2, 4, HS_B2048_SPLIT, 0, 16, 16, 8>;
 // sub-plans of the two-pass transforms (N = n1 * n2 > 8192); X is unused there
 #ifndef HS_SUB_SPLIT
-#define HS_SUB_SPLIT -1
+#define HS_SUB_SPLIT -2
 #endif
 using S128  = HsPlan<128, 8, 1, 4, HS_SUB_SPLIT, 0, 8, 16>;
 using S256  = HsPlan<256, 16, 1, 4, HS_SUB_SPLIT, 0, 16, 16>;
