@@ -107,20 +107,13 @@ static void launch_c2c_sgn(int sgn, const void *in, void *out, const void *tw, l
     else launch_c2c<P, -1, MINB, PFW>(in, out, tw, howmany, st);
 }
 
-template <class P, int MINB>
-static void launch_c2c_persist_sgn(int sgn, const void *in, void *out, const void *tw, long long howmany, hs_stream_t st)
-{
-    if (sgn == 1) launch_c2c_persist<P, 1, MINB>(in, out, tw, howmany, st);
-    else launch_c2c_persist<P, -1, MINB>(in, out, tw, howmany, st);
-}
-
 extern "C" void hs_cu_launch_ct_c2c(int id, int sgn, const void *d_in, void *d_out, const void *d_tw, long long howmany, void *stream)
 {
     hs_stream_t st = (hs_stream_t)stream;
     switch (id) {
     case CT_4096A: launch_c2c_sgn<P4096a, 2>(sgn, d_in, d_out, d_tw, howmany, st); break;
     case CT_4096B: launch_c2c_sgn<P4096b, 2>(sgn, d_in, d_out, d_tw, howmany, st); break;
-    case CT_3000: launch_c2c_persist_sgn<P3000, 2>(sgn, d_in, d_out, d_tw, howmany, st); break;
+    case CT_3000: launch_c2c_sgn<P3000, 2>(sgn, d_in, d_out, d_tw, howmany, st); break;
     case CT_1024: launch_c2c_sgn<P1024, 2>(sgn, d_in, d_out, d_tw, howmany, st); break;
     case CT_2048: launch_c2c_sgn<P2048, 2>(sgn, d_in, d_out, d_tw, howmany, st); break;
     case CT_512: launch_c2c_sgn<P512, 3, 1>(sgn, d_in, d_out, d_tw, howmany, st); break;
@@ -141,8 +134,8 @@ extern "C" void hs_cu_launch_ct_bluestein(int id, int sgn, int N, const void *d_
     hs_stream_t st = (hs_stream_t)stream;
     switch (id) {
     case CT_B2048:
-        if (sgn == 1) launch_blu_persist<PB2048f, PB2048i, 1, 2>(N, d_in, d_out, d_tw_f, d_tw_i, d_chirp, d_hk, howmany, st);
-        else launch_blu_persist<PB2048f, PB2048i, -1, 2>(N, d_in, d_out, d_tw_f, d_tw_i, d_chirp, d_hk, howmany, st);
+        if (sgn == 1) launch_blu<PB2048f, PB2048i, 1, 2>(N, d_in, d_out, d_tw_f, d_tw_i, d_chirp, d_hk, howmany, st);
+        else launch_blu<PB2048f, PB2048i, -1, 2>(N, d_in, d_out, d_tw_f, d_tw_i, d_chirp, d_hk, howmany, st);
         break;
     default: fprintf(stderr, "Error: unknown fused Bluestein kernel id %d\n", id); exit(EXIT_FAILURE);
     }

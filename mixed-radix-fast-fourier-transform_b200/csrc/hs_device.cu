@@ -171,37 +171,6 @@ static void launch_c2c(const void *in, void *out, const void *tw, long long howm
     ++g_launches;
 }
 
-// persistent, prefetching variant (hs_c2c_persist_kernel): HSFFT_PERSIST=0 falls back to one CTA per X transforms
-static bool persist_enabled()
-{
-    static int v = -1;
-    if (v < 0) { const char *e = getenv("HSFFT_PERSIST"); v = e ? atoi(e) : 0; }
-    return v != 0;
-}
-
-template <class P, int SGN, int MINB>
-static void launch_c2c_persist(const void *in, void *out, const void *tw, long long howmany, cudaStream_t st)
-{
-    if (!persist_enabled()) { launch_c2c<P, SGN, MINB>(in, out, tw, howmany, st); return; }
-    constexpr int smem = HsPersistSmem<P>::bytes;
-    static_assert(smem * MINB <= 227 * 1024, "staging + exchange buffers of MINB CTAs do not fit one SM");
-    auto kern = hs_c2c_persist_kernel<P, SGN, MINB>;
-    static int per_sm = 0;
-    if (!per_sm) {
-        HS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        HS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        HS_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, P::threads, smem));
-        if (getenv("HSFFT_VERBOSE")) fprintf(stderr, "hsfft: persistent c2c N=%d: %d CTAs/SM, %d bytes smem\n", P::N, per_sm, smem);
-        if (per_sm < 1) per_sm = 1;
-    }
-    const long long nstep = (howmany + P::X - 1) / P::X;
-    long long blocks = (long long)hs_cu_sm_count() * per_sm;
-    if (blocks > nstep) blocks = nstep;
-    kern<<<(unsigned)blocks, P::threads, smem, st>>>((const cplx *)in, (cplx *)out, (const cplx *)tw, howmany);
-    HS_CUDA_CHECK(cudaGetLastError());
-    ++g_launches;
-}
-
 template <class PF, class PI, int SGN, int MINB>
 static void launch_blu(int N, const void *in, void *out, const void *twf, const void *twi, const void *chirp, const void *hk,
                        long long howmany, cudaStream_t st)
@@ -217,31 +186,6 @@ static void launch_blu(int N, const void *in, void *out, const void *twf, const 
     check_grid(blocks);
     kern<<<(unsigned)blocks, PF::threads, PF::smem_bytes, st>>>((const cplx *)in, (cplx *)out, (const cplx *)twf, (const cplx *)twi,
                                                                  (const cplx *)chirp, (const cplx *)hk, N, howmany, prefetch_dist(MINB));
-    HS_CUDA_CHECK(cudaGetLastError());
-    ++g_launches;
-}
-
-template <class PF, class PI, int SGN, int MINB>
-static void launch_blu_persist(int N, const void *in, void *out, const void *twf, const void *twi, const void *chirp, const void *hk,
-                               long long howmany, cudaStream_t st)
-{
-    if (!persist_enabled() || N > PF::N / 2 + 1) { launch_blu<PF, PI, SGN, MINB>(N, in, out, twf, twi, chirp, hk, howmany, st); return; }
-    constexpr int smem = HsBluPersistSmem<PF>::bytes;
-    static_assert(smem * MINB <= 227 * 1024, "staging + exchange buffers of MINB CTAs do not fit one SM");
-    auto kern = hs_bluestein_persist_kernel<PF, PI, SGN, MINB>;
-    static int per_sm = 0;
-    if (!per_sm) {
-        HS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        HS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        HS_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PF::threads, smem));
-        if (getenv("HSFFT_VERBOSE")) fprintf(stderr, "hsfft: persistent Bluestein M=%d: %d CTAs/SM, %d bytes smem\n", PF::N, per_sm, smem);
-        if (per_sm < 1) per_sm = 1;
-    }
-    const long long nstep = (howmany + PF::X - 1) / PF::X;
-    long long blocks = (long long)hs_cu_sm_count() * per_sm;
-    if (blocks > nstep) blocks = nstep;
-    kern<<<(unsigned)blocks, PF::threads, smem, st>>>((const cplx *)in, (cplx *)out, (const cplx *)twf, (const cplx *)twi, (const cplx *)chirp,
-                                                      (const cplx *)hk, N, howmany);
     HS_CUDA_CHECK(cudaGetLastError());
     ++g_launches;
 }

@@ -88,67 +88,3 @@ hs_bluestein_kernel(const cplx *HS_RESTRICT in, cplx *HS_RESTRICT out, const cpl
     HsStoreChirpCrop<SGN> st2{out + (active ? xf : 0) * N, chirp, N};
     hs_fft_team<PI, -1>(ld2, st2, sm, twi, t, active);
 }
-
-// Persistent, prefetching variant (see hs_c2c_persist_kernel): the next step's X*N samples arrive in a staging
-// buffer while this step's two M-point transforms run.  N <= M/2 + 1 logical samples per transform.
-template <int SGN>
-struct HsLoadChirpStaged {
-    static constexpr bool kPost = false;
-    const cplx *stage; // this team's N staged samples
-    const cplx *HS_RESTRICT h;
-    int N;
-    HS_DEVICE cplx operator()(int, int, int n) const
-    {
-        if (n >= N) return hs_c(0.0, 0.0);
-        const cplx xv = stage[n], hv = hs_ld_tab(h + n);
-        return (SGN == 1) ? hs_mulc(xv, hv) : hs_mul(xv, hv);
-    }
-};
-template <class P>
-struct HsBluPersistSmem {
-    static constexpr int exch_elems = P::X * P::NPAD;
-    static constexpr int stage_elems = P::X * (P::N / 2 + 1);
-    static constexpr int bytes = (exch_elems + stage_elems) * 16 + 16;
-};
-
-template <class PF, class PI, int SGN, int MINB>
-HS_GLOBAL void HS_LAUNCH_BOUNDS(PF::threads, MINB)
-hs_bluestein_persist_kernel(const cplx *HS_RESTRICT in, cplx *HS_RESTRICT out, const cplx *HS_RESTRICT twf, const cplx *HS_RESTRICT twi,
-                            const cplx *HS_RESTRICT chirp, const cplx *HS_RESTRICT hk, int N, long long howmany)
-{
-    static_assert(PF::N == PI::N && PF::T == PI::T && PF::X == PI::X && PF::NPAD == PI::NPAD, "plans must pair");
-    constexpr int RL = PF::radix(PF::NST - 1);
-    static_assert(PI::radix(0) == RL, "register hand-over needs matching radices");
-    constexpr int NB = PF::N / RL, B = (NB + PF::T - 1) / PF::T;
-    HS_DYN_SMEM(cplx, smem);
-    cplx *const exch = smem, *const stage = smem + HsBluPersistSmem<PF>::exch_elems;
-    HsMbar *const bar = reinterpret_cast<HsMbar *>(stage + HsBluPersistSmem<PF>::stage_elems);
-    const int team = HS_TID / PF::T, t = HS_TID % PF::T;
-    const long long nstep = (howmany + PF::X - 1) / PF::X;
-    auto step_bytes = [&](long long s) { const long long left = howmany - s * PF::X; return (unsigned)((left < PF::X ? left : PF::X) * N * 16); };
-
-    if (HS_TID == 0) hs_mbar_init(bar);
-    hs_fence_async_proxy();
-    HS_SYNC();
-    if (HS_TID == 0 && HS_BID < nstep) {
-        hs_mbar_expect(bar, step_bytes(HS_BID));
-        hs_bulk_g2s(stage, in + HS_BID * PF::X * N, step_bytes(HS_BID), bar);
-    }
-    unsigned j = 0;
-    for (long long s = HS_BID; s < nstep; s += HS_NBLOCKS, ++j) {
-        hs_mbar_wait(bar, j & 1u);
-        const long long xf = s * PF::X + team, next = s + HS_NBLOCKS;
-        const bool active = xf < howmany;
-        cplx *sm = exch + team * PF::NPAD;
-        cplx y[B][RL];
-        HsLoadChirpStaged<SGN> ld{stage + team * N, chirp, N};
-        HsStoreRegsMul<SGN, RL> st{y, hk};
-        HsPrefetchHook hook{stage, next < nstep ? in + next * PF::X * N : nullptr, next < nstep ? step_bytes(next) : 0u, bar};
-        hs_fft_team_h<PF, 1>(ld, st, sm, twf, t, active, hook);
-        HS_SYNC(); // the forward transform's last reads of sm precede the inverse transform's first writes
-        HsLoadRegs<RL> ld2{y};
-        HsStoreChirpCrop<SGN> st2{out + (active ? xf : 0) * N, chirp, N};
-        hs_fft_team<PI, -1>(ld2, st2, sm, twi, t, active);
-        HS_SYNC();
-    }
-}

@@ -374,73 +374,3 @@ hs_c2c_smem_kernel(const cplx *HS_RESTRICT in, cplx *HS_RESTRICT out, const cplx
     HsStoreGlobal st{out + (active ? xf : 0) * P::N};
     hs_fft_team<P, SGN>(ld, st, smem + team * P::NPAD, tw, t, active);
 }
-
-// ------------------------------------------------------------------- persistent, prefetching variant
-// One CTA per resident slot walks the batch; while the teams transform the X transforms of one step, the
-// bulk-copy engine (cp.async.bulk, UBLKCP) brings the next step's X*N contiguous samples into a staging
-// buffer.  The copy is issued right after the first pass has consumed the staging buffer, so it overlaps every
-// later pass and the stores; the load latency that the one-shot kernel exposes at the start of every CTA (ncu:
-// 23 % of the stall samples at N = 3000, 26 % for the fused Bluestein) and the drain at its end disappear.
-// Costs X*N*16 bytes of shared memory on top of the exchange buffer, so it is used where two CTAs still fit.
-struct HsLoadStaged {
-    static constexpr bool kPost = false;
-    const cplx *stage; // this team's N staged samples
-    HS_DEVICE cplx operator()(int, int, int n) const { return stage[n]; }
-};
-template <class P>
-struct HsPersistSmem {
-    static constexpr int exch_elems = P::X * P::NPAD;
-    static constexpr int stage_elems = P::X * P::N;
-    static constexpr int bytes = (exch_elems + stage_elems) * 16 + 16;
-};
-// re-arms the staging buffer: every thread's reads of it are ordered before the asynchronous refill
-struct HsPrefetchHook {
-    HS_DEVICE void sync() const { HS_SYNC(); }
-    cplx *stage;
-    const cplx *next_src; // null: nothing left to prefetch
-    unsigned next_bytes;
-    HsMbar *bar;
-    HS_DEVICE void after_first_loads() const {}
-    HS_DEVICE void before_last_pass() const {}
-    HS_DEVICE void after_first_pass() const
-    {
-        hs_fence_async_proxy();
-        HS_SYNC();
-        if (HS_TID == 0 && next_src) {
-            hs_mbar_expect(bar, next_bytes);
-            hs_bulk_g2s(stage, next_src, next_bytes, bar);
-        }
-    }
-};
-
-template <class P, int SGN, int MINB>
-HS_GLOBAL void HS_LAUNCH_BOUNDS(P::threads, MINB)
-hs_c2c_persist_kernel(const cplx *HS_RESTRICT in, cplx *HS_RESTRICT out, const cplx *HS_RESTRICT tw, long long howmany)
-{
-    static_assert(P::NPASS > 1, "a one-pass plan has no later pass to hide the copy behind");
-    HS_DYN_SMEM(cplx, smem);
-    cplx *const exch = smem, *const stage = smem + HsPersistSmem<P>::exch_elems;
-    HsMbar *const bar = reinterpret_cast<HsMbar *>(stage + HsPersistSmem<P>::stage_elems);
-    const int team = HS_TID / P::T, t = HS_TID % P::T;
-    const long long nstep = (howmany + P::X - 1) / P::X;
-    auto step_bytes = [&](long long s) { const long long left = howmany - s * P::X; return (unsigned)((left < P::X ? left : P::X) * P::N * 16); };
-
-    if (HS_TID == 0) hs_mbar_init(bar);
-    hs_fence_async_proxy();
-    HS_SYNC();
-    if (HS_TID == 0 && HS_BID < nstep) {
-        hs_mbar_expect(bar, step_bytes(HS_BID));
-        hs_bulk_g2s(stage, in + HS_BID * P::X * P::N, step_bytes(HS_BID), bar);
-    }
-    unsigned j = 0;
-    for (long long s = HS_BID; s < nstep; s += HS_NBLOCKS, ++j) {
-        hs_mbar_wait(bar, j & 1u);
-        const long long xf = s * P::X + team, next = s + HS_NBLOCKS;
-        const bool active = xf < howmany;
-        HsLoadStaged ld{stage + team * P::N};
-        HsStoreGlobal st{out + (active ? xf : 0) * P::N};
-        HsPrefetchHook hk{stage, next < nstep ? in + next * P::X * P::N : nullptr, next < nstep ? step_bytes(next) : 0u, bar};
-        hs_fft_team_h<P, SGN>(ld, st, exch + team * P::NPAD, tw, t, active, hk);
-        HS_SYNC(); // the last pass's reads of the exchange buffer precede the next step's first writes
-    }
-}

@@ -32,15 +32,6 @@ static void launch_c2c(const void *in, void *out, const void *tw, long long howm
     ++g_launches;
 }
 
-template <class P, int SGN, int MINB>
-static void launch_c2c_persist(const void *in, void *out, const void *tw, long long howmany, hs_stream_t)
-{
-    const long long nstep = (howmany + P::X - 1) / P::X; // two "SMs": the second CTA's steps interleave with the first's
-    hs_emu_launch(hs_c2c_persist_kernel<P, SGN, MINB>, nstep < 2 ? nstep : 2, P::threads, HsPersistSmem<P>::bytes, (const cplx *)in, (cplx *)out,
-                  (const cplx *)tw, howmany);
-    ++g_launches;
-}
-
 template <class PF, class PI, int SGN, int MINB>
 static void launch_blu(int N, const void *in, void *out, const void *twf, const void *twi, const void *chirp, const void *hk,
                        long long howmany, hs_stream_t)
@@ -48,16 +39,6 @@ static void launch_blu(int N, const void *in, void *out, const void *twf, const 
     const long long blocks = (howmany + PF::X - 1) / PF::X;
     hs_emu_launch(hs_bluestein_kernel<PF, PI, SGN, MINB>, blocks, PF::threads, PF::smem_bytes, (const cplx *)in, (cplx *)out,
                   (const cplx *)twf, (const cplx *)twi, (const cplx *)chirp, (const cplx *)hk, N, howmany, 2);
-    ++g_launches;
-}
-
-template <class PF, class PI, int SGN, int MINB>
-static void launch_blu_persist(int N, const void *in, void *out, const void *twf, const void *twi, const void *chirp, const void *hk,
-                               long long howmany, hs_stream_t)
-{
-    const long long nstep = (howmany + PF::X - 1) / PF::X;
-    hs_emu_launch(hs_bluestein_persist_kernel<PF, PI, SGN, MINB>, nstep < 2 ? nstep : 2, PF::threads, HsBluPersistSmem<PF>::bytes, (const cplx *)in,
-                  (cplx *)out, (const cplx *)twf, (const cplx *)twi, (const cplx *)chirp, (const cplx *)hk, N, howmany);
     ++g_launches;
 }
 

@@ -65,15 +65,6 @@ def test_long_bluestein_three_fused_kernels(hs, emu_lib, oracle, n):
         assert "3 fused tiled kernels" in desc and err <= tol(n), (n, sgn, err, desc)
 
 
-@pytest.mark.parametrize("n,howmany", [(3000, 5), (1009, 7), (600, 3)])
-def test_persistent_prefetching_kernels_walk_several_steps(hs, emu_lib, oracle, n, howmany):
-    """hs_c2c_persist_kernel / hs_bluestein_persist_kernel: each CTA takes several steps (two CTAs in the
-    emulation), the staging buffer is refilled behind the first pass, the last step is partial."""
-    for sgn in (1, -1):
-        err, desc = run_c2c(hs, emu_lib, oracle, n, sgn, howmany=howmany, seed=howmany)
-        assert err <= tol(n), (n, sgn, err, desc)
-
-
 def test_persistent_pipeline_groups_rings_and_tail(hs, emu_lib, oracle, monkeypatch):
     """Two-pass transforms as one persistent kernel (hs_pipe.cuh): several groups, a partial last group, ring
     slots re-used (more groups than slots), lag 1 and 2.  The emulation aborts if a ticket's dependency is not
