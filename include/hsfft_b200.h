@@ -52,6 +52,13 @@ int fft_convolve_batch_dev(const char *type, const char *conv_type, const fft_ty
                            const fft_type *d_in2, int length2, fft_type *d_out, long out_stride, long howmany,
                            void *stream);
 
+/* ---- 3a. overlap-save streaming convolution: y = x (*) h for a long signal and a short filter ("full" linear
+ *          convolution, Lx + Lh - 1 samples).  Windows of P samples (a power of two 2^15..2^21, at least 2*Lh; P <= 0
+ *          picks one) are transformed in batches; they are read in place, never copied.  Returns the number of
+ *          samples written or -1. ---- */
+long fft_convolve_stream(fft_type *x, long Lx, fft_type *h, int Lh, fft_type *y, int P);
+long fft_convolve_stream_dev(const fft_type *d_x, long Lx, const fft_type *d_h, int Lh, fft_type *d_y, int P, void *stream);
+
 /* ---- 3b. distributed four-step transform: local phases (the exchange between them is the caller's
  *          all-to-all, e.g. torch.distributed / NCCL; see csrc/hsfft_dist.c for the data layout) ----
  * N = N1*N2 (powers of two), `nranks` devices; rank g holds a[N1][N2/nranks] = x[N2 n1 + g N2/nranks + c]. */

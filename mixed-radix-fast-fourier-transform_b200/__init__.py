@@ -46,6 +46,7 @@ EXPORTS = [
     "next_power_of_two", "find_optimal_fft_length", "fft_convolve",
     "fft_exec_batch", "fft_r2c_exec_batch", "fft_c2r_exec_batch", "fft_convolve_batch",
     "fft_exec_batch_dev", "fft_r2c_exec_batch_dev", "fft_c2r_exec_batch_dev", "fft_convolve_batch_dev",
+    "fft_convolve_stream", "fft_convolve_stream_dev",
     "hsfft_device_count", "hsfft_set_device", "hsfft_get_device", "hsfft_malloc_device", "hsfft_free_device",
     "hsfft_malloc_host", "hsfft_free_host", "hsfft_copy_h2d", "hsfft_copy_d2h", "hsfft_sync", "hsfft_launch_count",
     "hsfft_plan_describe", "hsfft_version",
@@ -72,6 +73,7 @@ def _bind(L):
         "fft_r2c_exec_batch_dev": (None, [RP, vp, vp, l, i, l, vp]),
         "fft_c2r_exec_batch_dev": (None, [RP, vp, l, vp, l, vp]),
         "fft_convolve_batch_dev": (i, [cp, cp, vp, i, vp, i, vp, l, l, vp]),
+        "fft_convolve_stream": (l, [vp, l, vp, i, vp, i]), "fft_convolve_stream_dev": (l, [vp, l, vp, i, vp, i, vp]),
         "hsfft_device_count": (i, []), "hsfft_set_device": (None, [i]), "hsfft_get_device": (i, []),
         "hsfft_malloc_device": (vp, [sz]), "hsfft_free_device": (None, [vp]),
         "hsfft_malloc_host": (vp, [sz]), "hsfft_free_host": (None, [vp]),
@@ -250,6 +252,16 @@ def convolve_batch(a, b, type_="full", conv_type="linear", lib=None):
     out = np.zeros((howmany, stride), dtype=np.float64)
     n = L.fft_convolve_batch(type_.encode(), conv_type.encode(), _vp(a), la, _vp(b), lb, _vp(out), stride, howmany)
     return n, out[:, : max(n, 0)].copy()
+
+
+def convolve_stream(x, h, P=0, lib=None):
+    """fft_convolve_stream: overlap-save convolution of a long signal with a short filter ("full")."""
+    L = lib or load()
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    h = np.ascontiguousarray(h, dtype=np.float64)
+    y = np.zeros(x.size + h.size - 1, dtype=np.float64)
+    n = L.fft_convolve_stream(_vp(x), x.size, _vp(h), h.size, _vp(y), P)
+    return n, y[: max(n, 0)]
 
 
 def dividebyN(n, lib=None):

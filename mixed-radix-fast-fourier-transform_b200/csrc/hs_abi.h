@@ -96,13 +96,18 @@ typedef struct hs_tile_geom {
     /* Bluestein fusions (io_mode of hs_cu_launch_tiled_io): the chirp h[n] and the logical length */
     const void *chirp;
     int nlog;
-    /* convolution fusions: io_mode 4 = rows of nlog reals, zero padded on load (in_xf must be 0);
-     * io_mode 5 = c2r merge of the product aux[k]*in[k]*scale (aux: second spectrum, same row stride as in);
-     * io_mode 6 = store only reals [sl_start, sl_start+sl_len) of every row, to rows of aux_xf reals (out_xf must be 0) */
+    /* convolution fusions (in_xf / out_xf must be 0 where a row stride in REALS applies):
+     * io_mode 4 = row x is the nlog reals starting at real index x*pad_stride + pad_off of one long array of pad_total reals;
+     *             reals outside [0, pad_total) and beyond the row's nlog read as zero (plain zero padding: pad_stride = nlog,
+     *             pad_off = 0, pad_total = rows*nlog; overlap-save blocks: pad_stride = hop, pad_off = -(filter-1));
+     * io_mode 5 = c2r merge of the product aux[k]*in[k]*scale, aux = second spectrum with row stride aux_xf (0: one shared row);
+     * io_mode 6 = store only reals [sl_start, sl_start+sl_len) of every row, to index x*aux_xf + (r - sl_start) of one
+     *             output array of sl_total reals (later indices are dropped) */
     const void *aux;
     long long aux_xf;
     double scale;
     int sl_start, sl_len;
+    long long pad_stride, pad_off, pad_total, sl_total;
 } hs_tile_geom;
 
 /* Four-step exchange fused into phase A's last pass (io_mode 7 of hs_cu_launch_tiled_io): every output row k1 of the

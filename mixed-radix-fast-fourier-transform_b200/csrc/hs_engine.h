@@ -90,13 +90,18 @@ int     hs_dev_exec_c2r_fused(hs_dev_obj *d, const void *d_spec, long long in_st
 /* convolution fusions over a two-pass half-length plan (return 0 when the plan has none):
  * rows of len reals zero padded on pass 1's loads -> half-length spectrum d_z (the caller splits it);
  * inverse real transform of scale*A*B with the product on pass 1's merge loads and the output slice on pass 2's stores */
-int     hs_dev_exec_padded_real(hs_dev_obj *d, const void *d_rows, int len, void *d_z, void *d_ws, long long howmany, void *stream);
-int     hs_dev_exec_c2r_mul_slice(hs_dev_obj *d, const void *d_A, const void *d_B, long long in_stride, double scale, const void *d_tw2,
-                                  void *d_out, long long out_stride, int start, int len, void *d_ws, long long howmany, void *stream);
-/* hsfft_real.c internals used by hsfft_convolve.c: padded r2c to a half spectrum, c2r of a product with slice */
-int     hs_real_r2c_padded_dev(fft_real_object obj, const fft_type *d_rows, int len, fft_data *d_out, long out_stride, long howmany, void *stream);
-int     hs_real_c2r_mul_slice_dev(fft_real_object obj, const fft_data *d_A, const fft_data *d_B, long in_stride, double scale, fft_type *d_out,
-                                  long out_stride, int start, int len, long howmany, void *stream);
+int     hs_dev_exec_padded_real(hs_dev_obj *d, const void *d_rows, int len, long long row_stride, long long row_off, long long total, void *d_z,
+                                void *d_ws, long long howmany, void *stream);
+int     hs_dev_exec_c2r_mul_slice(hs_dev_obj *d, const void *d_A, const void *d_B, long long in_stride, long long b_stride, double scale,
+                                  const void *d_tw2, void *d_out, long long out_stride, long long out_total, int start, int len, void *d_ws,
+                                  long long howmany, void *stream);
+/* hsfft_real.c internals used by hsfft_convolve.c: r2c of zero-padded windows of a real array to half spectra (window x
+ * = len reals from index x*row_stride + row_off, zero outside [0, total)); c2r of scale*A*B (B row stride b_stride, 0 = one
+ * shared spectrum) keeping reals [start, start+len) of every row at output index x*out_stride.., clipped to out_total */
+int     hs_real_r2c_padded_dev(fft_real_object obj, const fft_type *d_rows, int len, long long row_stride, long long row_off, long long total,
+                               fft_data *d_out, long out_stride, long howmany, void *stream);
+int     hs_real_c2r_mul_slice_dev(fft_real_object obj, const fft_data *d_A, const fft_data *d_B, long in_stride, long b_stride, double scale,
+                                  fft_type *d_out, long long out_stride, long long out_total, int start, int len, long howmany, void *stream);
 
 /* registry */
 hs_dev_obj *hs_dev_get(fft_object plan);      /* find or build; exits when no CUDA device */

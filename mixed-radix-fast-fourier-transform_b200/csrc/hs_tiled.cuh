@@ -191,15 +191,21 @@ struct HsLoadTileTw : HsLoadTile {
 // Convolution fusions (reference src/convolve.c:117-200): the zero padding rides on the first pass's loads of the
 // forward transforms, the spectrum product and the 1/P scale on the merge loads of the inverse one, the output
 // slice on its last pass's stores -- the padded inputs, the product and the full-length result never exist in HBM.
-struct HsLoadColPadReal { // rows of len reals read as rows of complex pairs, zero beyond len (8-byte loads: rows may be 8-byte aligned only)
-    static constexpr bool kPost = false;
-    const double *HS_RESTRICT row;
+struct HsLoadColPadReal { // a window of a long real array read as a row of complex pairs, zero outside the row's len reals and
+    static constexpr bool kPost = false; // outside the array (8-byte loads: windows may be 8-byte aligned only)
+    const double *HS_RESTRICT x;
+    long long first, total; // the window's first real (may be negative), reals in the array
     int len;
     long long off0, es;
+    HS_DEVICE double at(long long r) const
+    {
+        const long long gidx = first + r;
+        return (r < len && gidx >= 0 && gidx < total) ? hs_ld_stream_d(x + gidx) : 0.0;
+    }
     HS_DEVICE cplx operator()(int, int, int n_) const
     {
         const long long r = 2 * (off0 + n_ * es);
-        return hs_c(r < len ? hs_ld_stream_d(row + r) : 0.0, r + 1 < len ? hs_ld_stream_d(row + r + 1) : 0.0);
+        return hs_c(at(r), at(r + 1));
     }
 };
 struct HsLoadColC2RMul { // element k of the packed signal from bins k and H-k of the product of two spectra
@@ -218,15 +224,20 @@ struct HsLoadColC2RMul { // element k of the packed signal from bins k and H-k o
         return hs_c(a.x + c.x + (t1 * w.x) - (t2 * w.y), a.y - c.y + (t2 * w.x) + (t1 * w.y));
     }
 };
-struct HsStoreColSlice { // complex element k of the row = reals 2k, 2k+1; keep [start, start+len)
-    double *HS_RESTRICT row; // destination row (already at its first kept real)
+struct HsStoreColSlice { // complex element k of the row = reals 2k, 2k+1; keep [start, start+len), clipped to the output array
+    double *HS_RESTRICT y;
+    long long first, total; // output index of the row's first kept real, reals in the output array
     int start, len;
     long long off0, es;
+    HS_DEVICE void put(long long r, double v) const
+    {
+        if (r >= 0 && r < len && first + r < total) hs_st_stream_d(y + first + r, v);
+    }
     HS_DEVICE void operator()(int, int, int k_, cplx v) const
     {
         const long long r = 2 * (off0 + k_ * es) - start;
-        if (r >= 0 && r < len) hs_st_stream_d(row + r, v.x);
-        if (r + 1 >= 0 && r + 1 < len) hs_st_stream_d(row + r + 1, v.y);
+        put(r, v.x);
+        put(r + 1, v.y);
     }
 };
 
@@ -259,17 +270,17 @@ HS_DEVICE void hs_tile_run(const cplx *HS_RESTRICT in_x, cplx *HS_RESTRICT out_x
         HsStoreCol<STP> st{out_x + (long long)(c0 + colS) * g.out_c, g.out_e};
         HsLoadColC2RPre<LDP> ld{in_x, (const cplx *)g.chirp, g.nlog, (long long)(c0 + colA) * g.in_c, g.in_e};
         hs_fft_team2<P, SGN>(ld, st, first, rest, tw, hk);
-    } else if constexpr (IO == 4) { // convolution: zero padding on load (g.nlog reals per row, rows back to back)
+    } else if constexpr (IO == 4) { // convolution: zero padding on load (windows of g.nlog reals of one long array)
         HsStoreCol<STP> st{out_x + (long long)(c0 + colS) * g.out_c, g.out_e};
-        HsLoadColPadReal ld{(const double *)in_x + xf * g.nlog, g.nlog, (long long)(c0 + colA) * g.in_c, g.in_e};
+        HsLoadColPadReal ld{(const double *)in_x, xf * g.pad_stride + g.pad_off, g.pad_total, g.nlog, (long long)(c0 + colA) * g.in_c, g.in_e};
         hs_fft_team2<P, SGN>(ld, st, first, rest, tw, hk);
     } else if constexpr (IO == 5) { // convolution: product of two spectra, scaled, merged (g.chirp = twiddle2, g.nlog = H)
         HsStoreCol<STP> st{out_x + (long long)(c0 + colS) * g.out_c, g.out_e};
-        HsLoadColC2RMul ld{in_x, (const cplx *)g.aux + xf * g.in_xf, (const cplx *)g.chirp, g.nlog, g.scale, (long long)(c0 + colA) * g.in_c, g.in_e};
+        HsLoadColC2RMul ld{in_x, (const cplx *)g.aux + xf * g.aux_xf, (const cplx *)g.chirp, g.nlog, g.scale, (long long)(c0 + colA) * g.in_c, g.in_e};
         hs_fft_team2<P, SGN>(ld, st, first, rest, tw, hk);
     } else if constexpr (IO == 6) { // convolution: slice on store (rows of g.aux_xf reals)
         static_assert(TW == 1 && STCOL, "the slice store belongs to a second pass");
-        HsStoreColSlice st{(double *)out_x + xf * g.aux_xf, g.sl_start, g.sl_len, (long long)(c0 + colS) * g.out_c, g.out_e};
+        HsStoreColSlice st{(double *)out_x, xf * g.aux_xf, g.sl_total, g.sl_start, g.sl_len, (long long)(c0 + colS) * g.out_c, g.out_e};
         HsLoadColTw<LDP> ld;
         ld.base = in_x; ld.off0 = (long long)(c0 + colA) * g.in_c; ld.es = g.in_e;
         ld.blk_log = g.blk_log; ld.blk_stride = g.blk_stride;

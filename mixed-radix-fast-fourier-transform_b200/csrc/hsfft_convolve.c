@@ -134,10 +134,11 @@ int fft_convolve_batch_dev(const char *type, const char *conv_type, const fft_ty
     }
     /* long convolutions: padding, product, scale and slice ride on the transforms' own loads and stores (8 launches,
      * about two thirds of the HBM traffic of the unfused sequence below) */
-    if (hs_real_r2c_padded_dev(c->fwd, d_in1, length1, (fft_data *)c->d_A, (long)H1, howmany, stream)) {
-        if (!hs_real_r2c_padded_dev(c->fwd, d_in2, length2, (fft_data *)c->d_B, (long)H1, howmany, stream) ||
-            !hs_real_c2r_mul_slice_dev(c->inv, (const fft_data *)c->d_A, (const fft_data *)c->d_B, (long)H1, 1.0 / P, d_out, out_stride, start, n,
-                                       howmany, stream)) {
+    if (hs_real_r2c_padded_dev(c->fwd, d_in1, length1, length1, 0, (long long)length1 * howmany, (fft_data *)c->d_A, (long)H1, howmany, stream)) {
+        if (!hs_real_r2c_padded_dev(c->fwd, d_in2, length2, length2, 0, (long long)length2 * howmany, (fft_data *)c->d_B, (long)H1, howmany,
+                                    stream) ||
+            !hs_real_c2r_mul_slice_dev(c->inv, (const fft_data *)c->d_A, (const fft_data *)c->d_B, (long)H1, (long)H1, 1.0 / P, d_out, out_stride,
+                                       (long long)out_stride * (howmany - 1) + n, start, n, howmany, stream)) {
             fprintf(stderr, "Error: fused convolution path became unavailable\n");
             exit(EXIT_FAILURE);
         }
@@ -204,4 +205,70 @@ int fft_convolve(const char *type, const char *conv_type, fft_type *input1, int 
     const int n = conv_setup(type, conv_type, input1, length1, input2, length2, output, &P, &start, &linear);
     if (n <= 0) return n;
     return fft_convolve_batch(type, conv_type, input1, length1, input2, length2, output, n, 1);
+}
+
+
+/* ------------------------------------------------------------ overlap-save streaming convolution (additive)
+ * y = x (*) h, a long signal and a short filter, "full" linear convolution of Lx + Lh - 1 samples.  The signal is cut into
+ * windows of P samples that overlap by Lh - 1 (hop S = P - Lh + 1); every window is circularly convolved with the filter
+ * through the batched real transforms and only its last S samples -- the ones free of wrap-around -- are kept.  The
+ * windows are never copied: window b is read in place by the forward transform's first pass (zero outside the signal),
+ * the filter's spectrum is one shared row of the product, and each block's S samples go straight to y. */
+long fft_convolve_stream_dev(const fft_type *d_x, long Lx, const fft_type *d_h, int Lh, fft_type *d_y, int P, void *stream)
+{
+    if (!d_x || !d_h || !d_y || Lx <= 0 || Lh <= 0) {
+        fprintf(stderr, "Error: Invalid inputs for fft_convolve_stream\n");
+        return -1;
+    }
+    if (P <= 0) { /* 8 filter lengths per window keeps the overlap at 1/8; at least 2^15 (the fused two-pass path), at most 2^20 */
+        P = 1 << 15;
+        while (P < 8 * Lh && P < (1 << 20)) P *= 2;
+    }
+    if (P < (1 << 15) || P > (1 << 21) || (P & (P - 1)) || Lh > P / 2) {
+        fprintf(stderr, "Error: fft_convolve_stream needs a power-of-two window 2^15..2^21 of at least twice the filter (P = %d, filter %d)\n", P, Lh);
+        return -1;
+    }
+    const long total = Lx + Lh - 1, S = P - Lh + 1, nblocks = (total + S - 1) / S;
+    conv_plans *c = plans_for(P);
+    const size_t H1 = (size_t)P / 2 + 1;
+    long chunk = (long)(((size_t)512 << 20) / (sizeof(fft_data) * H1)); /* spectra of a chunk of windows: at most 512 MiB */
+    if (chunk < 1) chunk = 1;
+    if (chunk > nblocks) chunk = nblocks;
+    if (c->cap_AB < sizeof(fft_data) * H1 * (size_t)chunk) {
+        hs_cu_free(c->d_A); hs_cu_free(c->d_B);
+        c->cap_AB = sizeof(fft_data) * H1 * (size_t)chunk;
+        c->d_A = hs_cu_malloc(c->cap_AB);
+        c->d_B = hs_cu_malloc(c->cap_AB);
+    }
+    if (!hs_real_r2c_padded_dev(c->fwd, d_h, Lh, Lh, 0, Lh, (fft_data *)c->d_B, (long)H1, 1, stream)) {
+        fprintf(stderr, "Error: fft_convolve_stream: no fused transform for P = %d\n", P);
+        return -1;
+    }
+    for (long b0 = 0; b0 < nblocks; b0 += chunk) {
+        const long cnt = (b0 + chunk <= nblocks) ? chunk : nblocks - b0;
+        /* window b0 + i starts at signal index (b0 + i) * S - (Lh - 1) */
+        hs_real_r2c_padded_dev(c->fwd, d_x, P, S, b0 * S - (Lh - 1), Lx, (fft_data *)c->d_A, (long)H1, cnt, stream);
+        hs_real_c2r_mul_slice_dev(c->inv, (const fft_data *)c->d_A, (const fft_data *)c->d_B, (long)H1, 0, 1.0 / P, d_y + b0 * S, S, total - b0 * S,
+                                  Lh - 1, (int)S, cnt, stream);
+    }
+    return total;
+}
+
+long fft_convolve_stream(fft_type *x, long Lx, fft_type *h, int Lh, fft_type *y, int P)
+{
+    if (!x || !h || !y || Lx <= 0 || Lh <= 0) {
+        fprintf(stderr, "Error: Invalid inputs for fft_convolve_stream\n");
+        return -1;
+    }
+    hs_cu_require_device();
+    const long total = Lx + Lh - 1;
+    void *dx = hs_cu_malloc(sizeof(fft_type) * (size_t)Lx), *dh = hs_cu_malloc(sizeof(fft_type) * (size_t)Lh);
+    void *dy = hs_cu_malloc(sizeof(fft_type) * (size_t)total);
+    hs_cu_h2d(dx, x, sizeof(fft_type) * (size_t)Lx, NULL);
+    hs_cu_h2d(dh, h, sizeof(fft_type) * (size_t)Lh, NULL);
+    const long n = fft_convolve_stream_dev((const fft_type *)dx, Lx, (const fft_type *)dh, Lh, (fft_type *)dy, P, NULL);
+    if (n > 0) hs_cu_d2h(y, dy, sizeof(fft_type) * (size_t)n, NULL);
+    hs_cu_stream_sync(NULL);
+    hs_cu_free(dx); hs_cu_free(dh); hs_cu_free(dy);
+    return n;
 }

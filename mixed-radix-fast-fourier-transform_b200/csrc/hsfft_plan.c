@@ -827,9 +827,11 @@ static int twopass_subs(const hs_c2c *p, const hs_ct_desc **tp, const hs_ct_desc
     return *tp && *s1 && *s2;
 }
 
-int hs_dev_exec_padded_real(hs_dev_obj *d, const void *d_rows, int len, void *d_z, void *d_ws, long long howmany, void *stream)
+int hs_dev_exec_padded_real(hs_dev_obj *d, const void *d_rows, int len, long long row_stride, long long row_off, long long total, void *d_z,
+                            void *d_ws, long long howmany, void *stream)
 {
-    /* rows of len reals, zero padded to 2*n reals on the fly, through the half-length plan: the padding rides on pass 1's loads */
+    /* windows of len reals (window x starts at real x*row_stride + row_off of an array of `total` reals), zero padded to
+     * 2*n reals on the fly, through the half-length plan: the padding rides on pass 1's loads */
     if (d->lt != 0 || !d->direct || d->direct->tp_id < 0 || getenv("HSFFT_NO_CONV_FUSE")) return 0;
     const hs_c2c *p = d->direct;
     const hs_ct_desc *tp, *s1, *s2;
@@ -837,14 +839,15 @@ int hs_dev_exec_padded_real(hs_dev_obj *d, const void *d_rows, int len, void *d_
     hs_tile_geom g;
     memset(&g, 0, sizeof g);
     g.ncols = tp->n2; g.in_xf = 0; g.in_c = 1; g.in_e = tp->n2; g.out_xf = p->n; g.out_c = tp->n1; g.out_e = 1;
-    g.nlog = len;
+    g.nlog = len; g.pad_stride = row_stride; g.pad_off = row_off; g.pad_total = total;
     hs_cu_launch_tiled_io(s1->id, p->sgn, 0, 0, 4, 1, d_rows, d_ws, p->d_tw, &g, howmany, stream);
     hs_cu_launch_ct_twopass(p->tp_id, 2, p->sgn, d_ws, d_z, p->d_tw2, p->d_twb, p->d_tws, howmany, stream);
     return 1;
 }
 
-int hs_dev_exec_c2r_mul_slice(hs_dev_obj *d, const void *d_A, const void *d_B, long long in_stride, double scale, const void *d_tw2,
-                              void *d_out, long long out_stride, int start, int len, void *d_ws, long long howmany, void *stream)
+int hs_dev_exec_c2r_mul_slice(hs_dev_obj *d, const void *d_A, const void *d_B, long long in_stride, long long b_stride, double scale,
+                              const void *d_tw2, void *d_out, long long out_stride, long long out_total, int start, int len, void *d_ws,
+                              long long howmany, void *stream)
 {
     /* inverse real transform of scale * A * B, keeping reals [start, start+len) of every row: the product rides on the
      * merge loads of pass 1, the slice on the stores of pass 2 */
@@ -855,12 +858,12 @@ int hs_dev_exec_c2r_mul_slice(hs_dev_obj *d, const void *d_A, const void *d_B, l
     hs_tile_geom g;
     memset(&g, 0, sizeof g);
     g.ncols = tp->n2; g.in_xf = in_stride; g.in_c = 1; g.in_e = tp->n2; g.out_xf = p->n; g.out_c = tp->n1; g.out_e = 1;
-    g.chirp = d_tw2; g.nlog = p->n; g.aux = d_B; g.scale = scale;
+    g.chirp = d_tw2; g.nlog = p->n; g.aux = d_B; g.aux_xf = b_stride; g.scale = scale;
     hs_cu_launch_tiled_io(s1->id, p->sgn, 0, 0, 5, 1, d_A, d_ws, p->d_tw, &g, howmany, stream);
     memset(&g, 0, sizeof g);
     g.ncols = tp->n1; g.in_xf = p->n; g.in_c = 1; g.in_e = tp->n1; g.out_xf = 0; g.out_c = 1; g.out_e = tp->n1;
     g.twb = p->d_twb; g.tws = p->d_tws; g.tw_ld = tp->n1;
-    g.aux_xf = out_stride; g.sl_start = start; g.sl_len = len;
+    g.aux_xf = out_stride; g.sl_start = start; g.sl_len = len; g.sl_total = out_total;
     hs_cu_launch_tiled_io(s2->id, p->sgn, 1, 1, 6, 1, d_ws, d_out, p->d_tw2, &g, howmany, stream);
     return 1;
 }

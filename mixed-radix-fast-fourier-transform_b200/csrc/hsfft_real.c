@@ -181,7 +181,8 @@ void fft_c2r_exec_batch_dev(fft_real_object obj, const fft_data *d_in, long in_s
     c2r_dev(obj, r, d_in, in_stride, d_out, r->d_z[0], r->d_ws[0], howmany, stream);
 }
 
-int hs_real_r2c_padded_dev(fft_real_object obj, const fft_type *d_rows, int len, fft_data *d_out, long out_stride, long howmany, void *stream)
+int hs_real_r2c_padded_dev(fft_real_object obj, const fft_type *d_rows, int len, long long row_stride, long long row_off, long long total,
+                           fft_data *d_out, long out_stride, long howmany, void *stream)
 {
     check_real_args(obj, d_rows, d_out);
     hs_real_dev *r = real_dev_get(obj);
@@ -189,20 +190,21 @@ int hs_real_r2c_padded_dev(fft_real_object obj, const fft_type *d_rows, int len,
     if (c->lt != 0 || !c->direct || c->direct->tp_id < 0 || c->direct->pipe) return 0;
     grow(&r->d_z[0], &r->cap_z[0], sizeof(fft_data) * (size_t)howmany * r->H);
     grow(&r->d_ws[0], &r->cap_ws[0], sizeof(fft_data) * (size_t)howmany * r->H);
-    if (!hs_dev_exec_padded_real(c, d_rows, len, r->d_z[0], r->d_ws[0], howmany, stream)) return 0;
+    if (!hs_dev_exec_padded_real(c, d_rows, len, row_stride, row_off, total, r->d_z[0], r->d_ws[0], howmany, stream)) return 0;
     hs_cu_launch_r2c_post(r->d_z[0], d_out, r->d_tw2, r->H, out_stride, 0, howmany, stream);
     return 1;
 }
 
-int hs_real_c2r_mul_slice_dev(fft_real_object obj, const fft_data *d_A, const fft_data *d_B, long in_stride, double scale, fft_type *d_out,
-                              long out_stride, int start, int len, long howmany, void *stream)
+int hs_real_c2r_mul_slice_dev(fft_real_object obj, const fft_data *d_A, const fft_data *d_B, long in_stride, long b_stride, double scale,
+                              fft_type *d_out, long long out_stride, long long out_total, int start, int len, long howmany, void *stream)
 {
     check_real_args(obj, d_A, d_out);
     hs_real_dev *r = real_dev_get(obj);
     hs_dev_obj *c = hs_dev_get(obj->cobj);
     if (c->lt != 0 || !c->direct || c->direct->tp_id < 0 || c->direct->pipe) return 0;
     grow(&r->d_ws[0], &r->cap_ws[0], sizeof(fft_data) * (size_t)howmany * r->H);
-    return hs_dev_exec_c2r_mul_slice(c, d_A, d_B, in_stride, scale, r->d_tw2, d_out, out_stride, start, len, r->d_ws[0], howmany, stream);
+    return hs_dev_exec_c2r_mul_slice(c, d_A, d_B, in_stride, b_stride, scale, r->d_tw2, d_out, out_stride, out_total, start, len, r->d_ws[0],
+                                     howmany, stream);
 }
 
 static long real_chunk(long howmany, size_t row_bytes)

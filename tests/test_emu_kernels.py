@@ -170,6 +170,16 @@ def test_long_convolution_fused_padding_product_and_slice(hs, emu_lib, oracle):
         assert n == nr and rel_rms(y1, yr) <= 1e-13, t
 
 
+@pytest.mark.parametrize("Lx,Lh,P", [(100000, 1001, 32768), (70001, 333, 0), (40000, 16000, 32768)])
+def test_overlap_save_streaming_convolution(hs, emu_lib, Lx, Lh, P):
+    """fft_convolve_stream: windows read in place (zero outside the signal), one shared filter spectrum, each block's
+    valid samples stored straight into y; the last block is clipped."""
+    x, h = xorshift_uniform(Lx, seed=Lx), xorshift_uniform(Lh, seed=Lh)
+    n, y = hs.convolve_stream(x, h, P, lib=emu_lib)
+    assert n == Lx + Lh - 1 and rel_rms(y, np.convolve(x, h)) <= 1e-13
+    assert hs.convolve_stream(x, xorshift_uniform(20000, 1), 32768, lib=emu_lib)[0] == -1   # filter longer than half a window
+
+
 def test_convolution_batch(hs, emu_lib):
     a = xorshift_uniform(4 * 50, 3).reshape(4, 50)
     b = xorshift_uniform(4 * 20, 4).reshape(4, 20)

@@ -157,6 +157,16 @@ def test_convolve_batch_fused_path_matches_unfused(hs, product_lib):
         assert rel_rms(outs[0][i], np.convolve(a[i], b[i])) <= 1e-12
 
 
+@pytest.mark.parametrize("Lx,Lh,P", [(3000001, 4097, 0), (1 << 22, 12345, 65536), (500000, 40000, 1 << 17)])
+def test_overlap_save_streaming_convolution(hs, product_lib, Lx, Lh, P):
+    """Additive API: long signal, short filter, checked against numpy's FFT convolution."""
+    x, h = xorshift_uniform(Lx, seed=Lx), xorshift_uniform(Lh, seed=Lh)
+    n, y = hs.convolve_stream(x, h, P)
+    nfft = 1 << int(np.ceil(np.log2(Lx + Lh - 1)))
+    ref = np.fft.irfft(np.fft.rfft(x, nfft) * np.fft.rfft(h, nfft), nfft)[: Lx + Lh - 1]
+    assert n == Lx + Lh - 1 and rel_rms(y, ref) <= 1e-12
+
+
 def test_convolve_circular_and_errors(hs, product_lib, oracle):
     a = xorshift_uniform(100, seed=1)
     b = xorshift_uniform(37, seed=2)

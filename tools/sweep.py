@@ -73,6 +73,20 @@ def main():
                                                    C.c_void_p(y.data_ptr()), 2 * n, batch, None)
             P = 2 * n
             nbytes, flops = (16.0 * n + 8.0 * (2 * n - 1)) * batch, 3 * 2.5 * P * math.log2(P) * batch
+        elif kind == "convs":    # overlap-save: one signal of n samples, filter of `batch` taps ("convs:<Lx>:<Lh>")
+            import ctypes as C
+            lh = batch
+            x = torch.rand((n,), device=dev, dtype=torch.float64) * 2 - 1
+            x2 = torch.rand((lh,), device=dev, dtype=torch.float64) * 2 - 1
+            y = torch.empty((n + lh,), device=dev, dtype=torch.float64)
+            L = hs.load()
+            p = None
+            run = lambda: L.fft_convolve_stream_dev(C.c_void_p(x.data_ptr()), n, C.c_void_p(x2.data_ptr()), lh, C.c_void_p(y.data_ptr()), 0, None)
+            Pw = 1 << 15
+            while Pw < 8 * lh and Pw < (1 << 20):
+                Pw *= 2
+            nblk = (n + lh - 1 + (Pw - lh)) // (Pw - lh + 1)
+            nbytes, flops = 16.0 * n, 2 * 2.5 * Pw * math.log2(Pw) * nblk
         desc = p.describe() if kind == "c2c" else kind
         for _ in range(3):
             run()
