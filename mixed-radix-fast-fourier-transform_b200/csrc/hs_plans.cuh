@@ -30,6 +30,13 @@ using P8192  = HsPlan<8192, 512, 1, 4, -1, 0, 8, 8, 8, 16>;
 // fused Bluestein, M = 2048 (N = 513..1024, e.g. the N = 1009 config): forward / inverse pair
 using PB2048f = HsPlan<2048, 128, 2, 4, HS_B2048_SPLIT, 0, 8, 16, 16>;
 using PB2048i = HsPlan<2048, 128, 2, 4, HS_B2048_SPLIT, 0, 16, 16, 8>;
+// the same fused kernel for the other pad lengths one SM can hold (N = 65..2048 all run as one kernel); the radix lists
+// are palindromes, so the inverse plan is the forward plan and the spectrum is handed over in registers
+// (all conflict free, tests/emu/bank_check.py)
+using PB256  = HsPlan<256, 16, 16, 4, HS_B2048_SPLIT, 0, 16, 16>;
+using PB512  = HsPlan<512, 64, 4, 3, HS_B2048_SPLIT, 0, 8, 8, 8>;
+using PB1024 = HsPlan<1024, 64, 4, 3, HS_B2048_SPLIT, 0, 8, 16, 8>;
+using PB4096 = HsPlan<4096, 256, 1, 4, HS_B2048_SPLIT, 0, 16, 16, 16>;
 // sub-plans of the two-pass transforms (N = n1 * n2 > 8192); X is unused there
 #ifndef HS_SUB_SPLIT
 #define HS_SUB_SPLIT -2
@@ -59,4 +66,5 @@ using S160xi = HsExact<HsPlan<160, 20, 1, 3, HS_SUB_SPLIT, 0, 8, 4, 5>>;
 enum { CT_4096A = 0, CT_4096B, CT_3000, CT_1024, CT_2048, CT_512, CT_256, CT_8192, CT_B2048, CT_4096X, CT_3000X, CT_4096Y, CT_3000Y, CT_3000Z,
        CT_T14, CT_T15, CT_T16, CT_T17, CT_T18, CT_T19, CT_T20,
        CT_S128, CT_S256, CT_S512, CT_S1024,
-       CT_TX20480, CT_TX40960, CT_TX81920, CT_TX163840, CT_S160X, CT_COUNT };
+       CT_TX20480, CT_TX40960, CT_TX81920, CT_TX163840, CT_S160X,
+       CT_B256, CT_B512, CT_B1024, CT_B4096, CT_COUNT };
