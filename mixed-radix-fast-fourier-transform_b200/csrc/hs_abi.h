@@ -9,7 +9,9 @@
  */
 #ifndef HS_ABI_H_
 #define HS_ABI_H_
+#ifndef __CUDACC_RTC__
 #include <stddef.h>
+#endif
 
 #ifdef __cplusplus
 extern "C" {
@@ -217,6 +219,14 @@ void  hs_cu_launch_ct_bluestein(int id, int sgn, int N, const void *d_in, void *
  * the callee fills ph[].tiles.  query != 0: only fill tiles and report availability.  Returns 0 when this
  * (size, variant, sgn) has no pipeline (the caller then runs the multi-launch path). */
 int   hs_cu_launch_pipe(int tp_id, int variant, int sgn, hs_pipe_args *a, void *stream, int query);
+
+/* ---- plan-time specialisation (hs_jit.cu): a compile-time kernel for any length whose stages fit one SM, compiled with
+ * NVRTC when the plan is created.  radix_exec: stage radices in execution order (2,3,4,5,7,8,16 only).  create returns a
+ * handle >= 0 and fills desc (radices, twiddle mode) or -1 (NVRTC missing, HSFFT_JIT=0, length unsuitable): the caller
+ * then falls back to the run-time planned engine.  hs_cu_jit_source: the generated translation unit (tests). ---- */
+int   hs_cu_jit_c2c_create(int n, int sgn, const int *radix_exec, int nst, hs_ct_desc *desc);
+void  hs_cu_jit_c2c_launch(int handle, const void *d_in, void *d_out, const void *d_tw, long long howmany, void *stream);
+int   hs_cu_jit_source(int n, int sgn, const int *radix_exec, int nst, char *out, int cap);
 
 /* ---- run-time planned pass and element-wise helpers ---- */
 void  hs_cu_launch_generic(int sgn, const void *d_in, void *d_out, const hs_gen_params *p, void *stream);

@@ -94,8 +94,10 @@ void hs_emu_barrier2();
 #define HS_GRID_CONSTANT
 #else
 // ---------------------------------------------------------------------------- CUDA (product)
+#ifndef __CUDACC_RTC__ // the plan-time JIT (hs_jit.cu) compiles these headers with NVRTC, which has its own built-ins
 #include <cuda_runtime.h>
 #include <cstdint>
+#endif
 #define HS_GLOBAL __global__
 #define HS_DEVICE __device__ __forceinline__
 #define HS_NOINLINE __device__ __noinline__
@@ -263,8 +265,12 @@ HS_DEVICE void hs_mbar_wait(HsMbar *m, unsigned parity)
 }
 // 2-D tile of a 3-D tensor [z][row][x] described by a CUtensorMap (cuTensorMapEncodeTiled on the host): one
 // instruction moves box_rows x box_x elements, the TMA engine walks the strides (UTMALDG in SASS)
+#ifndef __CUDACC_RTC__
 #include <cuda.h>
 typedef CUtensorMap HsTmap;
+#else
+struct alignas(64) HsTmap { unsigned long long opaque[16]; };
+#endif
 #define HS_GRID_CONSTANT __grid_constant__
 HS_DEVICE void hs_tma_load_3d(void *dst_smem, const HsTmap *t, int x_dbl, int row0, long long z, int /*rows*/, int /*row_bytes*/, HsMbar *m)
 {

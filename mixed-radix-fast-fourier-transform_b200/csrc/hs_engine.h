@@ -26,6 +26,7 @@ typedef struct hs_c2c {
     int n, sgn;
     int ct_id;          /* >= 0: one compile-time kernel does the whole transform */
     void *d_tw;         /* its stage twiddles in HBM */
+    int jit_id;         /* >= 0: a kernel compiled for this length when the plan was created (hs_jit.cu) */
     int tp_id;          /* >= 0: compile-time two-pass transform (n = n1 * n2) */
     int n1, n2;
     int pipe;           /* the two passes run as one persistent pipeline kernel (hs_pipe.cuh) */

@@ -1,0 +1,324 @@
+// hs_jit.cu -- plan-time specialisation: any length whose stages fit one SM gets its own compile-time kernel.
+//
+// The compile-time plans of hs_plans.cuh cover the sizes BASELINE.json names; every other length used to run
+// through the run-time planned engine (hs_generic.cuh: radices, strides and table offsets as kernel arguments,
+// ~10 % of the HBM roofline).  The kernels of hs_smem_fft.cuh are templates over (N, threads per transform,
+// transforms per CTA, padding, stage radices, pass fusion), so here the plan builder picks those parameters for the
+// length at hand, writes a five-line translation unit that instantiates hs_c2c_smem_body for them and compiles it
+// with NVRTC for sm_100a when the plan is created (about a second, once per (N, direction) and process).  The
+// headers NVRTC needs are embedded in the library (build/hs_jit_sources.inc, written by build.py from csrc/*.cuh),
+// NVRTC itself is dlopen'ed: where libnvrtc.so is missing, or HSFFT_JIT=0, the run-time engine still serves the
+// length.  Stage order, butterflies, literals and twiddle values are exactly those of the static plans, so parity
+// with the reference is unchanged.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <dlfcn.h>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "hs_abi.h"
+#include "hs_cuda_util.h"
+#include "hs_jit_sources.inc" // hs_jit_src_names[], hs_jit_src_texts[], hs_jit_src_count
+
+// ------------------------------------------------------------------------------------------------ NVRTC, dlopen'ed
+typedef struct _nvrtcProgram *nvrtcProgram;
+typedef int nvrtcResult;
+struct Nvrtc {
+    nvrtcResult (*CreateProgram)(nvrtcProgram *, const char *, const char *, int, const char *const *, const char *const *);
+    nvrtcResult (*CompileProgram)(nvrtcProgram, int, const char *const *);
+    nvrtcResult (*GetCUBINSize)(nvrtcProgram, size_t *);
+    nvrtcResult (*GetCUBIN)(nvrtcProgram, char *);
+    nvrtcResult (*GetProgramLogSize)(nvrtcProgram, size_t *);
+    nvrtcResult (*GetProgramLog)(nvrtcProgram, char *);
+    nvrtcResult (*DestroyProgram)(nvrtcProgram *);
+    bool ok;
+};
+static Nvrtc *nvrtc()
+{
+    static Nvrtc n;
+    static bool tried = false;
+    if (tried) return n.ok ? &n : nullptr;
+    tried = true;
+    const char *names[] = {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so"};
+    void *h = nullptr;
+    for (const char *nm : names) if ((h = dlopen(nm, RTLD_NOW | RTLD_LOCAL))) break;
+    if (!h) return nullptr;
+#define HS_SYM(field, sym) *(void **)(&n.field) = dlsym(h, sym); if (!n.field) return nullptr
+    HS_SYM(CreateProgram, "nvrtcCreateProgram");
+    HS_SYM(CompileProgram, "nvrtcCompileProgram");
+    HS_SYM(GetCUBINSize, "nvrtcGetCUBINSize");
+    HS_SYM(GetCUBIN, "nvrtcGetCUBIN");
+    HS_SYM(GetProgramLogSize, "nvrtcGetProgramLogSize");
+    HS_SYM(GetProgramLog, "nvrtcGetProgramLog");
+    HS_SYM(DestroyProgram, "nvrtcDestroyProgram");
+#undef HS_SYM
+    n.ok = true;
+    return &n;
+}
+
+// ------------------------------------------------------------------------------------------------ driver entry points
+typedef CUresult (*fn_cuModuleLoadData)(CUmodule *, const void *);
+typedef CUresult (*fn_cuModuleGetFunction)(CUfunction *, CUmodule, const char *);
+typedef CUresult (*fn_cuFuncSetAttribute)(CUfunction, CUfunction_attribute, int);
+typedef CUresult (*fn_cuLaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void **, void **);
+typedef CUresult (*fn_cuModuleUnload)(CUmodule);
+struct Driver {
+    fn_cuModuleLoadData ModuleLoadData;
+    fn_cuModuleGetFunction ModuleGetFunction;
+    fn_cuFuncSetAttribute FuncSetAttribute;
+    fn_cuLaunchKernel LaunchKernel;
+    fn_cuModuleUnload ModuleUnload;
+    bool ok;
+};
+static Driver *driver()
+{
+    static Driver d;
+    static bool tried = false;
+    if (tried) return d.ok ? &d : nullptr;
+    tried = true;
+    cudaDriverEntryPointQueryResult q;
+#define HS_DRV(field, sym)                                                                                             \
+    { void *p = nullptr; if (cudaGetDriverEntryPoint(sym, &p, cudaEnableDefault, &q) != cudaSuccess || !p) return nullptr; \
+      *(void **)(&d.field) = p; }
+    HS_DRV(ModuleLoadData, "cuModuleLoadData");
+    HS_DRV(ModuleGetFunction, "cuModuleGetFunction");
+    HS_DRV(FuncSetAttribute, "cuFuncSetAttribute");
+    HS_DRV(LaunchKernel, "cuLaunchKernel");
+    HS_DRV(ModuleUnload, "cuModuleUnload");
+#undef HS_DRV
+    d.ok = true;
+    return &d;
+}
+
+// ------------------------------------------------------------------------------------------------ choosing the plan
+static int pad_of(int p, int logpad) { return logpad ? p + (p >> logpad) : p; }
+
+// shared-memory wavefronts per ideal wavefront over all exchanges (1.0 = conflict free); same model as tests/emu/bank_check.py:
+// a fused pass looks like one stage of radix RA*RB to shared memory
+static double conflict_ratio(int N, int T, int logpad, const std::vector<int> &pass_radix)
+{
+    long long total = 0, ideal = 0;
+    int m = 1;
+    const int np = (int)pass_radix.size();
+    for (int s = 0; s < np; ++s) {
+        const int R = pass_radix[s], QP = N / (m * R), NB = N / R, B = (NB + T - 1) / T;
+        for (int w0 = 0; w0 < T; w0 += 32) {
+            for (int u = 0; u < B; ++u) {
+                for (int dir = 0; dir < 2; ++dir) { // 0: reads of this pass (s > 0), 1: writes (s < np-1)
+                    if ((dir == 0 && s == 0) || (dir == 1 && s == np - 1)) continue;
+                    for (int i = 0; i < R; ++i) {
+                        for (int q0 = w0; q0 < w0 + 32 && q0 < T; q0 += 8) {
+                            int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, seen[8][8], lanes = 0;
+                            for (int t = q0; t < q0 + 8 && t < T && t < w0 + 32; ++t) {
+                                const int b = t + T * u;
+                                if (b >= NB) continue;
+                                const int q = b % QP, k = b / QP;
+                                const int a = dir == 0 ? pad_of(q + QP * i + QP * R * k, logpad) : pad_of(b + NB * i, logpad);
+                                const int g = a & 7;
+                                bool dup = false;
+                                for (int z = 0; z < cnt[g]; ++z) dup = dup || seen[g][z] == a;
+                                if (!dup && cnt[g] < 8) seen[g][cnt[g]++] = a;
+                                ++lanes;
+                            }
+                            if (!lanes) continue;
+                            int worst = 1;
+                            for (int g = 0; g < 8; ++g) worst = cnt[g] > worst ? cnt[g] : worst;
+                            total += worst;
+                            ideal += 1;
+                        }
+                    }
+                }
+            }
+        }
+        m *= R;
+    }
+    return ideal ? (double)total / (double)ideal : 1.0;
+}
+
+struct JitChoice {
+    int T, X, logpad, groups, minb, npass;
+    std::vector<int> pass_radix;
+};
+
+static bool choose(int n, const int *rx, int nst, JitChoice &c)
+{
+    if (nst < 2 || nst > 8 || n > 8192 || n < 16) return false;
+    for (int s = 0; s < nst; ++s) {
+        const int r = rx[s];
+        if (!(r == 2 || r == 3 || r == 4 || r == 5 || r == 7 || r == 8 || r == 16)) return false;
+    }
+    // fuse neighbouring stages while the pair stays within 16 points per butterfly (one exchange less each)
+    c.pass_radix.clear();
+    c.groups = 0;
+    int maxpp = 1;
+    for (int s = 0; s < nst;) {
+        int pp = rx[s], sz = 1;
+        if (s + 1 < nst && rx[s] * rx[s + 1] <= 16) { pp = rx[s] * rx[s + 1]; sz = 2; }
+        c.pass_radix.push_back(pp);
+        c.groups = c.groups * 10 + sz;
+        maxpp = pp > maxpp ? pp : maxpp;
+        s += sz;
+    }
+    c.npass = (int)c.pass_radix.size();
+    if (c.npass < 2) { // everything fused into one pass would leave no exchange to switch buffers on: keep the stages apart
+        c.pass_radix.assign(rx, rx + nst);
+        c.groups = 0;
+        c.npass = nst;
+        maxpp = 1;
+        for (int s = 0; s < nst; ++s) maxpp = rx[s] > maxpp ? rx[s] : maxpp;
+    }
+    c.T = n / maxpp; // the widest pass has exactly one butterfly per thread ...
+    int per = 1;
+    if (maxpp <= 8 && c.T > 512 && c.T % 2 == 0) { c.T /= 2; per = 2; } // ... or two, when that keeps a long transform within one CTA
+    if (c.T < 1 || c.T > 1024) return false;
+    const int pts = maxpp * per;
+    int best = 0;
+    double best_ratio = 1e30;
+    const int cand[5] = {3, 4, 2, 5, 0};
+    for (int i = 0; i < 5; ++i) {
+        const double r = conflict_ratio(n, c.T, cand[i], c.pass_radix);
+        if (r < best_ratio - 1e-9) { best_ratio = r; best = cand[i]; }
+    }
+    c.logpad = best;
+    const int npad = best ? n + (n >> best) + 1 : n;
+    int X = 256 / c.T;
+    if (X < 1) X = 1;
+    while (X > 1 && (long long)X * npad * 16 > 100 * 1024) --X;
+    if ((long long)X * npad * 16 > 200 * 1024) return false;
+    c.X = X;
+    const int threads = c.T * X, smem = X * npad * 16;
+    // CTAs per SM: bounded by shared memory, by 2048 threads and by the registers the butterflies need (16 points per
+    // thread want 128, 8 points run well in 80)
+    const int regs = pts > 8 ? 128 : 80, warps32 = (threads + 31) / 32 * 32;
+    if ((long long)warps32 * regs > 65536) return false;
+    int minb = pts > 8 ? 2 : 3;
+    while (minb > 1 && ((long long)minb * (smem + 1024) > 227 * 1024 || minb * threads > 2048 || (long long)minb * warps32 * regs > 65536)) --minb;
+    c.minb = minb;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------ the plans
+struct JitPlan {
+    int n, sgn;
+    hs_ct_desc desc;
+    CUmodule mod;
+    CUfunction fn;
+    int threads, smem, X, minb;
+    std::string text;
+};
+static std::mutex g_mu;
+static std::vector<JitPlan *> g_plans;
+
+static std::string make_source(int n, int sgn, const int *rx, int nst, const JitChoice &c)
+{
+    char buf[1024];
+    std::string rad;
+    for (int s = 0; s < nst; ++s) { snprintf(buf, sizeof buf, ", %d", rx[s]); rad += buf; }
+    snprintf(buf, sizeof buf,
+             "#include \"hs_smem_fft.cuh\"\n"
+             "using PJ = HsPlan<%d, %d, %d, %d, -2, %d%s>;\n"
+             "extern \"C\" __global__ void __launch_bounds__(PJ::threads, %d)\n"
+             "hs_jit_c2c(const cplx *__restrict__ in, cplx *__restrict__ out, const cplx *__restrict__ tw, long long howmany, int pf_dist)\n"
+             "{\n    hs_c2c_smem_body<PJ, %d>(in, out, tw, howmany, pf_dist);\n}\n",
+             n, c.T, c.X, c.logpad, c.groups, rad.c_str(), c.minb, sgn);
+    return std::string(buf);
+}
+
+static bool jit_enabled()
+{
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("HSFFT_JIT"); v = e ? atoi(e) : 1; }
+    return v != 0;
+}
+
+// the generated translation unit for (n, sgn, radices in execution order), without compiling it (tests; returns its length or 0)
+extern "C" int hs_cu_jit_source(int n, int sgn, const int *rx, int nst, char *out, int cap)
+{
+    JitChoice c;
+    if (!choose(n, rx, nst, c)) return 0;
+    const std::string s = make_source(n, sgn, rx, nst, c);
+    if ((int)s.size() + 1 > cap) return 0;
+    memcpy(out, s.c_str(), s.size() + 1);
+    return (int)s.size();
+}
+
+// compile (or find) the kernel for (n, sgn, radices in execution order); returns a handle >= 0 and fills desc, or -1
+extern "C" int hs_cu_jit_c2c_create(int n, int sgn, const int *rx, int nst, hs_ct_desc *desc)
+{
+    if (!jit_enabled()) return -1;
+    std::lock_guard<std::mutex> lock(g_mu);
+    for (size_t i = 0; i < g_plans.size(); ++i)
+        if (g_plans[i]->n == n && g_plans[i]->sgn == sgn) { *desc = g_plans[i]->desc; return (int)i; }
+    JitChoice c;
+    if (!choose(n, rx, nst, c)) return -1;
+    Nvrtc *rt = nvrtc();
+    Driver *drv = driver();
+    if (!rt || !drv) return -1;
+    const std::string src = make_source(n, sgn, rx, nst, c);
+    nvrtcProgram prog = nullptr;
+    if (rt->CreateProgram(&prog, src.c_str(), "hs_jit_plan.cu", hs_jit_src_count, hs_jit_src_texts, hs_jit_src_names) != 0) return -1;
+    const char *opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-default-device", "-DHS_JIT=1"};
+    const nvrtcResult rc = rt->CompileProgram(prog, 4, opts);
+    if (rc != 0) {
+        size_t ls = 0;
+        rt->GetProgramLogSize(prog, &ls);
+        std::string log(ls + 1, '\0');
+        if (ls) rt->GetProgramLog(prog, &log[0]);
+        fprintf(stderr, "hsfft: plan-time compilation for N=%d failed (falling back to the run-time engine):\n%s\n", n, log.c_str());
+        rt->DestroyProgram(&prog);
+        return -1;
+    }
+    size_t cs = 0;
+    rt->GetCUBINSize(prog, &cs);
+    std::vector<char> cubin(cs);
+    rt->GetCUBIN(prog, cubin.data());
+    rt->DestroyProgram(&prog);
+
+    JitPlan *p = new JitPlan();
+    p->n = n; p->sgn = sgn; p->text = src;
+    HS_CUDA_CHECK(cudaFree(0)); // make sure the primary context is current
+    if (drv->ModuleLoadData(&p->mod, cubin.data()) != CUDA_SUCCESS || drv->ModuleGetFunction(&p->fn, p->mod, "hs_jit_c2c") != CUDA_SUCCESS) {
+        fprintf(stderr, "hsfft: loading the plan-time kernel for N=%d failed (falling back to the run-time engine)\n", n);
+        delete p;
+        return -1;
+    }
+    const int npad = c.logpad ? n + (n >> c.logpad) + 1 : n;
+    p->threads = c.T * c.X; p->X = c.X; p->smem = c.X * npad * 16; p->minb = c.minb;
+    drv->FuncSetAttribute(p->fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, p->smem);
+    int pct = (int)(((long long)(p->smem + 1024) * c.minb * 100 + 228 * 1024 - 1) / (228 * 1024));
+    drv->FuncSetAttribute(p->fn, CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT, pct > 100 ? 100 : pct);
+    memset(&p->desc, 0, sizeof p->desc);
+    p->desc.id = (int)g_plans.size();
+    p->desc.family = HS_CT_C2C;
+    p->desc.n = n;
+    p->desc.nst = nst;
+    for (int s = 0; s < 8 && s < nst; ++s) p->desc.radix[s] = rx[s];
+    p->desc.split_min = -2;
+    p->desc.threads = p->threads;
+    p->desc.smem_bytes = p->smem;
+    if (getenv("HSFFT_VERBOSE"))
+        fprintf(stderr, "hsfft: plan-time kernel N=%d: T=%d X=%d LOGPAD=%d GROUPS=%d, %d threads, %d bytes smem, %d CTAs/SM asked\n", n, c.T, c.X, c.logpad,
+                c.groups, p->threads, p->smem, c.minb);
+    g_plans.push_back(p);
+    *desc = p->desc;
+    return p->desc.id;
+}
+
+extern "C" void hs_cu_jit_c2c_launch(int handle, const void *d_in, void *d_out, const void *d_tw, long long howmany, void *stream)
+{
+    JitPlan *p;
+    {
+        std::lock_guard<std::mutex> lock(g_mu);
+        if (handle < 0 || handle >= (int)g_plans.size()) { fprintf(stderr, "Error: unknown plan-time kernel %d\n", handle); exit(EXIT_FAILURE); }
+        p = g_plans[handle];
+    }
+    const long long blocks = (howmany + p->X - 1) / p->X;
+    if (blocks <= 0 || blocks > 2147483647LL) { fprintf(stderr, "Error: batch too large for one launch (%lld CTAs)\n", blocks); exit(EXIT_FAILURE); }
+    int pf = 0;
+    void *args[] = {(void *)&d_in, (void *)&d_out, (void *)&d_tw, (void *)&howmany, (void *)&pf};
+    const CUresult r = driver()->LaunchKernel(p->fn, (unsigned)blocks, 1, 1, (unsigned)p->threads, 1, 1, (unsigned)p->smem, (CUstream)stream, args, nullptr);
+    if (r != CUDA_SUCCESS) { fprintf(stderr, "Error: CUDA failure %d launching the plan-time kernel for N=%d\n", (int)r, p->n); exit(EXIT_FAILURE); }
+    hs_cu_count_launch();
+}

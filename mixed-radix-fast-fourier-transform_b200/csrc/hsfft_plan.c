@@ -323,6 +323,7 @@ static hs_c2c *c2c_create(int n, int sgn, int allow_exact)
     p->sgn = sgn;
     p->ct_id = -1;
     p->tp_id = -1;
+    p->jit_id = -1;
     const hs_ct_desc *ct = find_ct(HS_CT_C2C, n);
     if (ct) {
         p->ct_id = ct->id;
@@ -361,6 +362,16 @@ static hs_c2c *c2c_create(int n, int sgn, int allow_exact)
         if (rx[s] > 8 && (rx[s] % 2 == 0 || rx[s] >= HS_MAX_GENERIC_RADIX)) {
             fprintf(stderr, "Error: unsupported radix %d in the factor list of N=%d\n", rx[s], n);
             exit(EXIT_FAILURE);
+        }
+    }
+    /* a length without a static plan whose stages fit one SM gets its own kernel, compiled now (hs_jit.cu) */
+    {
+        hs_ct_desc jd;
+        const int id = hs_cu_jit_c2c_create(n, sgn, rx, lf, &jd);
+        if (id >= 0) {
+            p->jit_id = id;
+            p->d_tw = upload_stage_twiddles(jd.radix, jd.nst, sgn, jd.split_min);
+            return p;
         }
     }
     /* cos/sin half tables of the generic odd radices (reference :1533-1543) */
@@ -499,6 +510,7 @@ void hs_c2c_exec(const hs_c2c *p, const void *d_in, void *d_out, void *d_ws, lon
 {
     if (howmany <= 0) return;
     if (p->ct_id >= 0) { hs_cu_launch_ct_c2c(p->ct_id, p->sgn, d_in, d_out, p->d_tw, howmany, stream); return; }
+    if (p->jit_id >= 0) { hs_cu_jit_c2c_launch(p->jit_id, d_in, d_out, p->d_tw, howmany, stream); return; }
     if (p->tp_id >= 0 && p->pipe) {
         hs_pipe_args a;
         memset(&a, 0, sizeof a);
@@ -991,6 +1003,7 @@ const char *hsfft_plan_describe(fft_object obj)
     if (d->lt == 0) {
         const hs_c2c *p = d->direct;
         if (p->ct_id >= 0) n = snprintf(buf, sizeof buf, "mixed-radix N=%d: compile-time smem kernel #%d", d->N, p->ct_id);
+        else if (p->jit_id >= 0) n = snprintf(buf, sizeof buf, "mixed-radix N=%d: smem kernel compiled for this plan (NVRTC) #%d", d->N, p->jit_id);
         else if (p->tp_id >= 0)
             n = snprintf(buf, sizeof buf, "mixed-radix N=%d: compile-time two-pass kernels #%d%s", d->N, p->tp_id,
                          p->pipe ? " as one persistent L2-resident pipeline" : "");

@@ -121,6 +121,9 @@ long long hs_cu_launch_count(void) { return g_launches.load(); }
 void hs_cu_ipc_get(void *d, void *handle64) { memset(handle64, 0, 64); memcpy(handle64, &d, sizeof d); } // one address space here
 void *hs_cu_ipc_open(const void *handle64) { void *p; memcpy(&p, handle64, sizeof p); return p; }
 void hs_cu_ipc_close(void *) {}
+int hs_cu_jit_c2c_create(int, int, const int *, int, hs_ct_desc *) { return -1; } // no NVRTC here: the run-time engine serves these lengths
+void hs_cu_jit_c2c_launch(int, const void *, void *, const void *, long long, void *) {}
+int hs_cu_jit_source(int, int, const int *, int, char *, int) { return 0; }
 
 int hs_cu_launch_pipe(int tp_id, int variant, int sgn, hs_pipe_args *a, void *stream, int query)
 {

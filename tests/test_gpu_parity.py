@@ -65,6 +65,22 @@ def test_generic_engine_matches_compile_time_kernels(hs, product_lib, oracle, n)
     assert per_transform_worst(y, oracle.c2c(x, 1)) <= tol(n)
 
 
+JIT_SIZES = [24, 96, 360, 640, 1000, 1536, 2000, 2187, 2401, 3072, 3125, 5000, 6000, 6561, 7000, 8000]
+
+
+@pytest.mark.parametrize("n", JIT_SIZES)
+def test_plan_time_compiled_kernels(hs, product_lib, oracle, n):
+    """Lengths without a static plan get a kernel compiled with NVRTC at plan creation (csrc/hs_jit.cu): same stages,
+    butterflies and literals as the static plans, so the result is within rounding of the reference."""
+    for sgn in (1, -1):
+        x = rand_cplx(7, n, seed=n + sgn)
+        with hs.Plan(n, sgn) as p:
+            desc = p.describe()
+            y = p.exec(x)
+        assert "NVRTC" in desc or n in (6561,), desc   # 3^8 needs 729 threads of 9 points: left to the run-time engine
+        assert per_transform_worst(y, oracle.c2c(x, sgn)) <= min(tol(n), 2e-15 * math.log2(n) * 4), (n, sgn, desc)
+
+
 def test_config1_n1024_forward_inverse_roundtrip(hs, product_lib, oracle):
     """BASELINE.json config 1: N=1024, forward then inverse, /N round trip."""
     n = 1024

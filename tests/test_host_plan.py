@@ -139,3 +139,35 @@ def test_product_does_not_link_or_import_the_oracle():
                 assert "hsfft_oracle" not in txt and "liboracle" not in txt and "oracle_lib" not in txt, f
     ldd = subprocess.run(["ldd", os.path.join(pkg, "libhsfft_b200.so")], capture_output=True, text=True).stdout
     assert "oracle" not in ldd and "cufft" not in ldd.lower()
+
+
+def test_plan_time_kernel_source_is_generated_and_compiles_with_nvrtc(hs, product_lib):
+    """csrc/hs_jit.cu: the translation unit generated for a length without a static plan, and -- NVRTC needs no GPU --
+    its compilation for sm_100a from the library's own headers."""
+    import ctypes as C
+    L = product_lib
+    L.hs_cu_jit_source.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int, C.c_char_p, C.c_int]
+    L.hs_cu_jit_source.restype = C.c_int
+    buf = C.create_string_buffer(4096)
+    rx = (C.c_int * 4)(5, 5, 5, 8)                      # N = 1000: the reference's factor list [8,5,5,5] reversed
+    assert L.hs_cu_jit_source(1000, 1, rx, 4, buf, 4096) > 0
+    src = buf.value.decode()
+    assert "HsPlan<1000, 125, 2, 3, -2, 1111, 5, 5, 5, 8>" in src and "hs_c2c_smem_body<PJ, 1>" in src
+    assert L.hs_cu_jit_source(1001, 1, (C.c_int * 3)(7, 11, 13), 3, buf, 4096) == 0      # radix 11, 13: not a template radix
+    try:
+        rt = C.CDLL("libnvrtc.so.12")
+    except OSError:
+        try:
+            rt = C.CDLL("/usr/local/cuda/lib64/libnvrtc.so.12")
+        except OSError:
+            pytest.skip("no NVRTC in this environment")
+    csrc = os.path.join(ROOT, "mixed-radix-fast-fourier-transform_b200", "csrc")
+    names = ["hs_common.cuh", "hs_abi.h", "hs_butterflies.cuh", "hs_smem_fft.cuh"]
+    texts = [open(os.path.join(csrc, n), "rb").read() for n in names]
+    prog = C.c_void_p()
+    assert rt.nvrtcCreateProgram(C.byref(prog), src.encode(), b"p.cu", 4, (C.c_char_p * 4)(*texts), (C.c_char_p * 4)(*[n.encode() for n in names])) == 0
+    opts = (C.c_char_p * 4)(b"--gpu-architecture=sm_100a", b"-std=c++17", b"-default-device", b"-DHS_JIT=1")
+    rc = rt.nvrtcCompileProgram(prog, 4, opts)
+    size = C.c_size_t()
+    rt.nvrtcGetCUBINSize(prog, C.byref(size))
+    assert rc == 0 and size.value > 1000
