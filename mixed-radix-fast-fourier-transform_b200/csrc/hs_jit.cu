@@ -142,6 +142,12 @@ struct JitChoice {
     std::vector<int> pass_radix;
 };
 
+static int env_or(const char *name, int dflt)
+{
+    const char *e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
 static bool choose(int n, const int *rx, int nst, JitChoice &c)
 {
     if (nst < 2 || nst > 8 || n > 8192 || n < 16) return false;
@@ -150,12 +156,14 @@ static bool choose(int n, const int *rx, int nst, JitChoice &c)
         if (!(r == 2 || r == 3 || r == 4 || r == 5 || r == 7 || r == 8 || r == 16)) return false;
     }
     // fuse neighbouring stages while the pair stays within 16 points per butterfly (one exchange less each)
+    // (HSFFT_JIT_FUSE / _T / _X / _MINB / _LOGPAD override the choices below: tuning aids)
+    const int fuse_max = env_or("HSFFT_JIT_FUSE", 16);
     c.pass_radix.clear();
     c.groups = 0;
     int maxpp = 1;
     for (int s = 0; s < nst;) {
         int pp = rx[s], sz = 1;
-        if (s + 1 < nst && rx[s] * rx[s + 1] <= 16) { pp = rx[s] * rx[s + 1]; sz = 2; }
+        if (s + 1 < nst && rx[s] * rx[s + 1] <= fuse_max) { pp = rx[s] * rx[s + 1]; sz = 2; }
         c.pass_radix.push_back(pp);
         c.groups = c.groups * 10 + sz;
         maxpp = pp > maxpp ? pp : maxpp;
@@ -169,11 +177,14 @@ static bool choose(int n, const int *rx, int nst, JitChoice &c)
         maxpp = 1;
         for (int s = 0; s < nst; ++s) maxpp = rx[s] > maxpp ? rx[s] : maxpp;
     }
-    c.T = n / maxpp; // the widest pass has exactly one butterfly per thread ...
-    int per = 1;
-    if (maxpp <= 8 && c.T > 512 && c.T % 2 == 0) { c.T /= 2; per = 2; } // ... or two, when that keeps a long transform within one CTA
+    // Threads per transform: the widest pass has exactly one butterfly per thread; two when the transform would otherwise
+    // not fit the register file of one SM.  Registers: up to 10 points per thread run without spills in 80, 16 want 128.
+    c.T = n / maxpp;
+    int pts = maxpp;
+    if (((c.T + 31) / 32 * 32) * (pts <= 10 ? 80 : 128) > 65536 && maxpp <= 8) { c.T = (c.T + 1) / 2; pts *= 2; }
+    while (pts * 2 <= 10 && c.T > 128) { c.T = (c.T + 1) / 2; pts *= 2; } // radix 2..5 only: too little work per thread otherwise
+    if (env_or("HSFFT_JIT_T", 0) > 0) { c.T = env_or("HSFFT_JIT_T", 0); pts = maxpp * ((n / maxpp + c.T - 1) / c.T); }
     if (c.T < 1 || c.T > 1024) return false;
-    const int pts = maxpp * per;
     int best = 0;
     double best_ratio = 1e30;
     const int cand[5] = {3, 4, 2, 5, 0};
@@ -181,21 +192,25 @@ static bool choose(int n, const int *rx, int nst, JitChoice &c)
         const double r = conflict_ratio(n, c.T, cand[i], c.pass_radix);
         if (r < best_ratio - 1e-9) { best_ratio = r; best = cand[i]; }
     }
-    c.logpad = best;
+    c.logpad = env_or("HSFFT_JIT_LOGPAD", best);
+    best = c.logpad;
     const int npad = best ? n + (n >> best) + 1 : n;
-    int X = 256 / c.T;
+    // Small CTAs, many of them: independent CTAs are in different phases (load / exchange / arithmetic), which is what keeps
+    // the SM's pipes busy at once (measured: N=1000 68 % of the HBM peak with 2 x 125 threads x 3 CTAs, 81 % with 125 x 6).
+    int X = env_or("HSFFT_JIT_THREADS", 128) / c.T;
+    if (env_or("HSFFT_JIT_X", 0) > 0) X = env_or("HSFFT_JIT_X", 0);
     if (X < 1) X = 1;
     while (X > 1 && (long long)X * npad * 16 > 100 * 1024) --X;
     if ((long long)X * npad * 16 > 200 * 1024) return false;
     c.X = X;
     const int threads = c.T * X, smem = X * npad * 16;
-    // CTAs per SM: bounded by shared memory, by 2048 threads and by the registers the butterflies need (16 points per
-    // thread want 128, 8 points run well in 80)
-    const int regs = pts > 8 ? 128 : 80, warps32 = (threads + 31) / 32 * 32;
+    // CTAs per SM: as many as the registers (see above), shared memory and 2048 threads allow, at most 8
+    const int regs = pts <= 10 ? 80 : 128, warps32 = (threads + 31) / 32 * 32;
     if ((long long)warps32 * regs > 65536) return false;
-    int minb = pts > 8 ? 2 : 3;
-    while (minb > 1 && ((long long)minb * (smem + 1024) > 227 * 1024 || minb * threads > 2048 || (long long)minb * warps32 * regs > 65536)) --minb;
-    c.minb = minb;
+    int minb = (int)(65536 / ((long long)warps32 * regs));
+    if (minb > 8) minb = 8;
+    while (minb > 1 && ((long long)minb * (smem + 1024) > 227 * 1024 || minb * threads > 2048)) --minb;
+    c.minb = env_or("HSFFT_JIT_MINB", minb);
     return true;
 }
 
