@@ -4,7 +4,7 @@
 // through the run-time planned engine (hs_generic.cuh: radices, strides and table offsets as kernel arguments,
 // ~10 % of the HBM roofline).  The kernels of hs_smem_fft.cuh are templates over (N, threads per transform,
 // transforms per CTA, padding, stage radices, pass fusion), so here the plan builder picks those parameters for the
-// length at hand, writes a five-line translation unit that instantiates hs_c2c_smem_body for them and compiles it
+// length at hand, writes a ten-line translation unit that instantiates the transform for them and compiles it
 // with NVRTC for sm_100a when the plan is created (about a second, once per (N, direction) and process).  The
 // headers NVRTC needs are embedded in the library (build/hs_jit_sources.inc, written by build.py from csrc/*.cuh),
 // NVRTC itself is dlopen'ed: where libnvrtc.so is missing, or HSFFT_JIT=0, the run-time engine still serves the
@@ -228,7 +228,7 @@ static std::vector<JitPlan *> g_plans;
 
 static std::string make_source(int n, int sgn, const int *rx, int nst, const JitChoice &c)
 {
-    char buf[1024];
+    char buf[2048];
     std::string rad;
     for (int s = 0; s < nst; ++s) { snprintf(buf, sizeof buf, ", %d", rx[s]); rad += buf; }
     snprintf(buf, sizeof buf,
@@ -236,7 +236,16 @@ static std::string make_source(int n, int sgn, const int *rx, int nst, const Jit
              "using PJ = HsPlan<%d, %d, %d, %d, -2, %d%s>;\n"
              "extern \"C\" __global__ void __launch_bounds__(PJ::threads, %d)\n"
              "hs_jit_c2c(const cplx *__restrict__ in, cplx *__restrict__ out, const cplx *__restrict__ tw, long long howmany, int pf_dist)\n"
-             "{\n    hs_c2c_smem_body<PJ, %d>(in, out, tw, howmany, pf_dist);\n}\n",
+             "{\n" // the body of hs_c2c_smem_kernel, spelled out: wrapped in a device function the same code ran at 43 % instead of
+                   // 78 % of the HBM peak for N = 3000 (measured), so the kernel keeps its loads and stores in its own scope
+             "    HS_DYN_SMEM(cplx, smem);\n"
+             "    const int team = HS_TID / PJ::T, t = HS_TID %% PJ::T;\n"
+             "    const long long xf = HS_BID * PJ::X + team;\n"
+             "    const bool active = xf < howmany;\n"
+             "    HsLoadGlobal ld{in + (active ? xf : 0) * PJ::N};\n"
+             "    HsStoreGlobal st{out + (active ? xf : 0) * PJ::N};\n"
+             "    hs_fft_team<PJ, %d>(ld, st, smem + team * PJ::NPAD, tw, t, active);\n"
+             "}\n",
              n, c.T, c.X, c.logpad, c.groups, rad.c_str(), c.minb, sgn);
     return std::string(buf);
 }

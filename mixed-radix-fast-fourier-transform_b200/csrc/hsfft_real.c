@@ -187,7 +187,7 @@ int hs_real_r2c_padded_dev(fft_real_object obj, const fft_type *d_rows, int len,
     check_real_args(obj, d_rows, d_out);
     hs_real_dev *r = real_dev_get(obj);
     hs_dev_obj *c = hs_dev_get(obj->cobj);
-    if (c->lt != 0 || !c->direct || c->direct->tp_id < 0 || c->direct->pipe) return 0;
+    if (c->lt != 0 || !c->direct || c->direct->tp_id < 0) return 0;
     grow(&r->d_z[0], &r->cap_z[0], sizeof(fft_data) * (size_t)howmany * r->H);
     grow(&r->d_ws[0], &r->cap_ws[0], sizeof(fft_data) * (size_t)howmany * r->H);
     if (!hs_dev_exec_padded_real(c, d_rows, len, row_stride, row_off, total, r->d_z[0], r->d_ws[0], howmany, stream)) return 0;
@@ -201,7 +201,7 @@ int hs_real_c2r_mul_slice_dev(fft_real_object obj, const fft_data *d_A, const ff
     check_real_args(obj, d_A, d_out);
     hs_real_dev *r = real_dev_get(obj);
     hs_dev_obj *c = hs_dev_get(obj->cobj);
-    if (c->lt != 0 || !c->direct || c->direct->tp_id < 0 || c->direct->pipe) return 0;
+    if (c->lt != 0 || !c->direct || c->direct->tp_id < 0) return 0;
     grow(&r->d_ws[0], &r->cap_ws[0], sizeof(fft_data) * (size_t)howmany * r->H);
     return hs_dev_exec_c2r_mul_slice(c, d_A, d_B, in_stride, b_stride, scale, r->d_tw2, d_out, out_stride, out_total, start, len, r->d_ws[0],
                                      howmany, stream);

@@ -152,7 +152,7 @@ def test_plan_time_kernel_source_is_generated_and_compiles_with_nvrtc(hs, produc
     rx = (C.c_int * 4)(5, 5, 5, 8)                      # N = 1000: the reference's factor list [8,5,5,5] reversed
     assert L.hs_cu_jit_source(1000, 1, rx, 4, buf, 4096) > 0
     src = buf.value.decode()
-    assert "HsPlan<1000, 125, 1, 3, -2, 1111, 5, 5, 5, 8>" in src and "hs_c2c_smem_body<PJ, 1>" in src
+    assert "HsPlan<1000, 125, 1, 3, -2, 1111, 5, 5, 5, 8>" in src and "hs_fft_team<PJ, 1>" in src
     assert L.hs_cu_jit_source(1001, 1, (C.c_int * 3)(7, 11, 13), 3, buf, 4096) == 0      # radix 11, 13: not a template radix
     try:
         rt = C.CDLL("libnvrtc.so.12")
