@@ -216,7 +216,7 @@ static bool choose(int n, const int *rx, int nst, JitChoice &c)
 
 // ------------------------------------------------------------------------------------------------ the plans
 struct JitPlan {
-    int n, sgn;
+    int n, sgn, dev; // a module belongs to the context of the device that was current when it was loaded
     hs_ct_desc desc;
     CUmodule mod;
     CUfunction fn;
@@ -273,8 +273,10 @@ extern "C" int hs_cu_jit_c2c_create(int n, int sgn, const int *rx, int nst, hs_c
 {
     if (!jit_enabled()) return -1;
     std::lock_guard<std::mutex> lock(g_mu);
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
     for (size_t i = 0; i < g_plans.size(); ++i)
-        if (g_plans[i]->n == n && g_plans[i]->sgn == sgn) { *desc = g_plans[i]->desc; return (int)i; }
+        if (g_plans[i]->n == n && g_plans[i]->sgn == sgn && g_plans[i]->dev == dev) { *desc = g_plans[i]->desc; return (int)i; }
     JitChoice c;
     if (!choose(n, rx, nst, c)) return -1;
     Nvrtc *rt = nvrtc();
@@ -301,7 +303,7 @@ extern "C" int hs_cu_jit_c2c_create(int n, int sgn, const int *rx, int nst, hs_c
     rt->DestroyProgram(&prog);
 
     JitPlan *p = new JitPlan();
-    p->n = n; p->sgn = sgn; p->text = src;
+    p->n = n; p->sgn = sgn; p->dev = dev; p->text = src;
     HS_CUDA_CHECK(cudaFree(0)); // make sure the primary context is current
     if (drv->ModuleLoadData(&p->mod, cubin.data()) != CUDA_SUCCESS || drv->ModuleGetFunction(&p->fn, p->mod, "hs_jit_c2c") != CUDA_SUCCESS) {
         fprintf(stderr, "hsfft: loading the plan-time kernel for N=%d failed (falling back to the run-time engine)\n", n);
