@@ -59,6 +59,17 @@ int fft_convolve_batch_dev(const char *type, const char *conv_type, const fft_ty
 long fft_convolve_stream(fft_type *x, long Lx, fft_type *h, int Lh, fft_type *y, int P);
 long fft_convolve_stream_dev(const fft_type *d_x, long Lx, const fft_type *d_h, int Lh, fft_type *d_y, int P, void *stream);
 
+/* ---- 3c. two-dimensional complex transforms (row-major n0 x n1, unnormalised, same sign convention as fft_exec):
+ *          rows as batched 1-D transforms, columns by a strided pass (n0 = 128, 256, 512, 1024 and n1 a multiple of 16)
+ *          or through a transpose.  Device-pointer calls are out of place; in and out must not overlap. ---- */
+typedef struct fft2_set *fft2_object;
+fft2_object fft2_init(int n0, int n1, int sgn);
+void fft2_exec(fft2_object p, fft_data *inp, fft_data *oup);
+void fft2_exec_batch(fft2_object p, fft_data *inp, fft_data *oup, long howmany);
+void fft2_exec_batch_dev(fft2_object p, const fft_data *d_in, fft_data *d_out, long howmany, void *stream);
+const char *fft2_describe(fft2_object p);
+void free_fft2(fft2_object p);
+
 /* ---- 3b. distributed four-step transform: local phases (the exchange between them is the caller's
  *          all-to-all, e.g. torch.distributed / NCCL; see csrc/hsfft_dist.c for the data layout) ----
  * N = N1*N2 (powers of two), `nranks` devices; rank g holds a[N1][N2/nranks] = x[N2 n1 + g N2/nranks + c]. */

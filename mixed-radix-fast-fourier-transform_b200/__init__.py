@@ -47,6 +47,7 @@ EXPORTS = [
     "fft_exec_batch", "fft_r2c_exec_batch", "fft_c2r_exec_batch", "fft_convolve_batch",
     "fft_exec_batch_dev", "fft_r2c_exec_batch_dev", "fft_c2r_exec_batch_dev", "fft_convolve_batch_dev",
     "fft_convolve_stream", "fft_convolve_stream_dev",
+    "fft2_init", "fft2_exec", "fft2_exec_batch", "fft2_exec_batch_dev", "fft2_describe", "free_fft2",
     "hsfft_device_count", "hsfft_set_device", "hsfft_get_device", "hsfft_malloc_device", "hsfft_free_device",
     "hsfft_malloc_host", "hsfft_free_host", "hsfft_copy_h2d", "hsfft_copy_d2h", "hsfft_sync", "hsfft_launch_count",
     "hsfft_plan_describe", "hsfft_version",
@@ -73,6 +74,8 @@ def _bind(L):
         "fft_r2c_exec_batch_dev": (None, [RP, vp, vp, l, i, l, vp]),
         "fft_c2r_exec_batch_dev": (None, [RP, vp, l, vp, l, vp]),
         "fft_convolve_batch_dev": (i, [cp, cp, vp, i, vp, i, vp, l, l, vp]),
+        "fft2_init": (vp, [i, i, i]), "fft2_exec": (None, [vp, vp, vp]), "fft2_exec_batch": (None, [vp, vp, vp, l]),
+        "fft2_exec_batch_dev": (None, [vp, vp, vp, l, vp]), "fft2_describe": (cp, [vp]), "free_fft2": (None, [vp]),
         "fft_convolve_stream": (l, [vp, l, vp, i, vp, i]), "fft_convolve_stream_dev": (l, [vp, l, vp, i, vp, i, vp]),
         "hsfft_device_count": (i, []), "hsfft_set_device": (None, [i]), "hsfft_get_device": (i, []),
         "hsfft_malloc_device": (vp, [sz]), "hsfft_free_device": (None, [vp]),
@@ -252,6 +255,40 @@ def convolve_batch(a, b, type_="full", conv_type="linear", lib=None):
     out = np.zeros((howmany, stride), dtype=np.float64)
     n = L.fft_convolve_batch(type_.encode(), conv_type.encode(), _vp(a), la, _vp(b), lb, _vp(out), stride, howmany)
     return n, out[:, : max(n, 0)].copy()
+
+
+class Plan2D:
+    """fft2_init / fft2_exec_batch / free_fft2: row-major n0 x n1 complex transforms (additive API)."""
+
+    def __init__(self, n0, n1, sgn, lib=None):
+        self.L = lib or load()
+        self.n0, self.n1 = n0, n1
+        self.p = self.L.fft2_init(n0, n1, sgn)
+
+    def exec(self, x):
+        x = np.ascontiguousarray(x, dtype=np.complex128)
+        howmany = x.size // (self.n0 * self.n1)
+        y = np.empty_like(x)
+        self.L.fft2_exec_batch(self.p, _vp(x), _vp(y), howmany)
+        return y
+
+    def exec_dev(self, x, y, howmany):
+        import torch
+        self.L.fft2_exec_batch_dev(self.p, _dev_ptr(x), _dev_ptr(y), howmany, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+
+    def describe(self):
+        return self.L.fft2_describe(self.p).decode()
+
+    def close(self):
+        if self.p:
+            self.L.free_fft2(self.p)
+            self.p = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
 
 
 def convolve_stream(x, h, P=0, lib=None):

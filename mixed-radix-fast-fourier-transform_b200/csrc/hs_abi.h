@@ -239,6 +239,8 @@ void  hs_cu_launch_c2r_pre(const void *in, void *z, const void *tw2, int H, long
 void  hs_cu_launch_conv_mul(const void *A, const void *B, void *C, long long total, double scale, void *stream);
 /* rows of len reals -> rows of P reals, zero padded; rows of P reals -> rows [start, start+len) */
 void  hs_cu_launch_pad_rows(const void *src, int len, void *dst, int P, long long howmany, void *stream);
+/* out[img][c][r] = in[img][r][c] for howmany rows x cols complex matrices */
+void  hs_cu_launch_transpose(const void *in, void *out, int rows, int cols, long long howmany, void *stream);
 void  hs_cu_launch_slice_rows(const void *src, int P, int start, int len, void *dst, long long dst_stride, long long howmany,
                               void *stream);
 

@@ -364,6 +364,15 @@ extern "C" void hs_cu_launch_slice_rows(const void *src, int P, int start, int l
     HS_CUDA_CHECK(cudaGetLastError());
     ++g_launches;
 }
+extern "C" void hs_cu_launch_transpose(const void *in, void *out, int rows, int cols, long long howmany, void *stream)
+{
+    const long long tiles = (long long)((rows + 31) / 32) * ((cols + 31) / 32) * howmany;
+    long long blocks = tiles < 148LL * 16 ? tiles : 148LL * 16;
+    if (blocks < 1) blocks = 1;
+    hs_transpose_kernel<<<(unsigned)blocks, 256, 32 * 33 * sizeof(cplx), (cudaStream_t)stream>>>((const cplx *)in, (cplx *)out, rows, cols, howmany);
+    HS_CUDA_CHECK(cudaGetLastError());
+    ++g_launches;
+}
 extern "C" void hs_cu_launch_dist_twiddle(void *b, const void *hi, const void *lo, long long rows, long long cols, long long c0, int logN,
                                           int logS, void *stream)
 {

@@ -244,3 +244,24 @@ HS_GLOBAL void hs_slice_rows_kernel(const double *HS_RESTRICT src, int P, int st
         hs_st_stream_d(dst + b * dst_stride + i, src[b * P + start + i]);
     }
 }
+
+// batched out-of-place transpose of rows x cols complex matrices (2-D transforms whose column length has no strided
+// tiled plan): 32 x 32 tiles through shared memory, rows of 33 slots so that the transposed reads hit different banks
+HS_GLOBAL void hs_transpose_kernel(const cplx *HS_RESTRICT in, cplx *HS_RESTRICT out, int rows, int cols, long long howmany)
+{
+    HS_DYN_SMEM(cplx, tile);
+    const int tx = HS_TID % 32, ty = HS_TID / 32, ny = HS_NTHREADS / 32;
+    const long long tiles_c = (cols + 31) / 32, tiles_r = (rows + 31) / 32, per = tiles_c * tiles_r;
+    for (long long b = HS_BID; b < howmany * per; b += HS_NBLOCKS) {
+        const long long img = b / per, t = b % per;
+        const int r0 = (int)(t / tiles_c) * 32, c0 = (int)(t % tiles_c) * 32;
+        const cplx *src = in + img * rows * cols;
+        cplx *dst = out + img * rows * cols;
+        for (int j = ty; j < 32; j += ny)
+            if (r0 + j < rows && c0 + tx < cols) tile[j * 33 + tx] = hs_ld_stream(src + (long long)(r0 + j) * cols + c0 + tx);
+        HS_SYNC();
+        for (int j = ty; j < 32; j += ny)
+            if (c0 + j < cols && r0 + tx < rows) hs_st_stream(dst + (long long)(c0 + j) * rows + r0 + tx, tile[tx * 33 + j]);
+        HS_SYNC();
+    }
+}

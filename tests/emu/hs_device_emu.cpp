@@ -198,6 +198,11 @@ void hs_cu_launch_dist_twiddle(void *b, const void *hi, const void *lo, long lon
                   logS);
     ++g_launches;
 }
+void hs_cu_launch_transpose(const void *in, void *out, int rows, int cols, long long howmany, void *)
+{
+    hs_emu_launch(hs_transpose_kernel, 3, 64, 32 * 33 * sizeof(cplx), (const cplx *)in, (cplx *)out, rows, cols, howmany);
+    ++g_launches;
+}
 void hs_cu_launch_slice_rows(const void *src, int P, int start, int len, void *dst, long long dst_stride, long long howmany, void *)
 {
     hs_emu_launch(hs_slice_rows_kernel, ew_blocks(howmany * len), 64, 0, (const double *)src, P, start, len, (double *)dst, dst_stride, howmany);

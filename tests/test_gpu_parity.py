@@ -183,6 +183,19 @@ def test_overlap_save_streaming_convolution(hs, product_lib, Lx, Lh, P):
     assert n == Lx + Lh - 1 and rel_rms(y, ref) <= 1e-12
 
 
+@pytest.mark.parametrize("n0,n1", [(128, 64), (256, 3000), (1024, 1024), (100, 36), (1009, 250), (512, 1000)])
+def test_two_dimensional_transforms(hs, product_lib, oracle, n0, n1):
+    """Additive API: 2-D transforms against the reference's 1-D transform along both axes."""
+    b = 2
+    for sgn in (1, -1):
+        x = rand_cplx(b, n0 * n1, seed=n0 + n1 + sgn).reshape(b, n0, n1)
+        with hs.Plan2D(n0, n1, sgn) as p:
+            y = p.exec(x)
+        r1 = oracle.c2c(np.ascontiguousarray(x.reshape(b * n0, n1)), sgn).reshape(b, n0, n1)
+        r2 = oracle.c2c(np.ascontiguousarray(r1.transpose(0, 2, 1).reshape(b * n1, n0)), sgn).reshape(b, n1, n0)
+        assert rel_rms(y, r2.transpose(0, 2, 1)) <= tol(n0 * n1), (n0, n1, sgn)
+
+
 def test_convolve_circular_and_errors(hs, product_lib, oracle):
     a = xorshift_uniform(100, seed=1)
     b = xorshift_uniform(37, seed=2)

@@ -28,7 +28,10 @@ def main():
             steps = int(args.pop(0))
         else:
             f = a.split(":")
-            if len(f) == 2:
+            if f[0] == "fft2":           # fft2:<n0>x<n1>:<batch>
+                n0, n1 = (int(v) for v in f[1].split("x"))
+                cases.append(("fft2", (n0, n1), int(f[2])))
+            elif len(f) == 2:
                 cases.append(("c2c", int(f[0]), int(f[1])))
             else:
                 cases.append((f[0], int(f[1]), int(f[2])))
@@ -38,7 +41,17 @@ def main():
         peak = 6650.0
     dev = torch.device("cuda", 0)
     for kind, n, batch in cases:
-        if kind == "c2c":
+        if kind == "fft2":
+            n0, n1 = n
+            x = torch.rand((batch, n0, n1, 2), device=dev, dtype=torch.float64) * 2 - 1
+            y = torch.empty_like(x)
+            p2 = hs.Plan2D(n0, n1, 1)
+            p = None
+            run = lambda: p2.exec_dev(x, y, batch)
+            n = n0 * n1
+            nbytes, flops = 32.0 * n * batch, 5.0 * n * math.log2(n) * batch
+            kind = "fft2 " + p2.describe()[4:40]
+        elif kind == "c2c":
             x = torch.rand((batch, n, 2), device=dev, dtype=torch.float64) * 2 - 1
             y = torch.empty_like(x)
             p = hs.Plan(n, 1)
