@@ -61,6 +61,7 @@ static void ct_init()
     fill_desc<PB512>(g_ct[CT_B512], CT_B512, HS_CT_BLUESTEIN);
     fill_desc<PB1024>(g_ct[CT_B1024], CT_B1024, HS_CT_BLUESTEIN);
     fill_desc<PB4096>(g_ct[CT_B4096], CT_B4096, HS_CT_BLUESTEIN);
+    fill_desc<PB8192f>(g_ct[CT_B8192], CT_B8192, HS_CT_BLUESTEIN);
     fill_desc<P4096x>(g_ct[CT_4096X], CT_4096X, HS_CT_C2C);
     fill_desc<P3000x>(g_ct[CT_3000X], CT_3000X, HS_CT_C2C);
     fill_desc<P4096y>(g_ct[CT_4096Y], CT_4096Y, HS_CT_C2C);
@@ -156,6 +157,10 @@ extern "C" void hs_cu_launch_ct_bluestein(int id, int sgn, int N, const void *d_
     case CT_B4096:
         if (sgn == 1) launch_blu<PB4096, PB4096, 1, 2>(N, d_in, d_out, d_tw_f, d_tw_i, d_chirp, d_hk, howmany, st);
         else launch_blu<PB4096, PB4096, -1, 2>(N, d_in, d_out, d_tw_f, d_tw_i, d_chirp, d_hk, howmany, st);
+        break;
+    case CT_B8192:
+        if (sgn == 1) launch_blu<PB8192f, PB8192i, 1, 1>(N, d_in, d_out, d_tw_f, d_tw_i, d_chirp, d_hk, howmany, st);
+        else launch_blu<PB8192f, PB8192i, -1, 1>(N, d_in, d_out, d_tw_f, d_tw_i, d_chirp, d_hk, howmany, st);
         break;
     default: fprintf(stderr, "Error: unknown fused Bluestein kernel id %d\n", id); exit(EXIT_FAILURE);
     }

@@ -37,6 +37,8 @@ using PB256  = HsPlan<256, 16, 16, 4, HS_B2048_SPLIT, 0, 16, 16>;
 using PB512  = HsPlan<512, 64, 4, 3, HS_B2048_SPLIT, 0, 8, 8, 8>;
 using PB1024 = HsPlan<1024, 64, 4, 3, HS_B2048_SPLIT, 0, 8, 16, 8>;
 using PB4096 = HsPlan<4096, 256, 1, 4, HS_B2048_SPLIT, 0, 16, 16, 16>;
+using PB8192f = HsPlan<8192, 512, 1, 3, HS_B2048_SPLIT, 0, 8, 16, 8, 8>; // one CTA per SM (147 KB); N = 2049..4096
+using PB8192i = HsPlan<8192, 512, 1, 3, HS_B2048_SPLIT, 0, 8, 8, 16, 8>;
 // sub-plans of the two-pass transforms (N = n1 * n2 > 8192); X is unused there
 #ifndef HS_SUB_SPLIT
 #define HS_SUB_SPLIT -2
@@ -67,4 +69,4 @@ enum { CT_4096A = 0, CT_4096B, CT_3000, CT_1024, CT_2048, CT_512, CT_256, CT_819
        CT_T14, CT_T15, CT_T16, CT_T17, CT_T18, CT_T19, CT_T20,
        CT_S128, CT_S256, CT_S512, CT_S1024,
        CT_TX20480, CT_TX40960, CT_TX81920, CT_TX163840, CT_S160X,
-       CT_B256, CT_B512, CT_B1024, CT_B4096, CT_COUNT };
+       CT_B256, CT_B512, CT_B1024, CT_B4096, CT_B8192, CT_COUNT };

@@ -32,9 +32,9 @@ def test_n3000_is_within_rounding_of_the_reference_not_just_tolerance(hs, emu_li
     assert err <= 1e-15
 
 
-@pytest.mark.parametrize("n", [67, 131, 257, 509, 1031, 2039])
+@pytest.mark.parametrize("n", [67, 131, 257, 509, 1031, 2039, 4093])
 def test_fused_bluestein_every_pad_length_one_sm_holds(hs, emu_lib, oracle, n):
-    """M = 256, 512, 1024, 4096 (palindromic radix lists: the inverse plan is the forward plan)."""
+    """M = 256, 512, 1024, 4096 (palindromic radix lists: the inverse plan is the forward plan) and 8192."""
     for sgn in (1, -1):
         err, desc = run_c2c(hs, emu_lib, oracle, n, sgn, howmany=5)
         assert "fused compile-time" in desc and err <= tol(n), (n, sgn, err, desc)

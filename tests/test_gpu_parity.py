@@ -21,7 +21,7 @@ def per_transform_worst(y, r):
 # BASELINE.json config sizes + the reference's own self-test sizes (src/real.c:278,360) + edge sizes
 C2C_SIZES = [2, 3, 4, 5, 7, 8, 15, 16, 20, 64, 100, 128, 256, 512, 1000, 1024, 2048, 3000, 4096, 8192,
              11, 13, 26, 143, 1001, 53 * 8, 17 * 29, 6561, 10000, 16384, 32768, 1 << 17, 1 << 19, 1 << 20, 3 << 14]
-BLUESTEIN_SIZES = [19, 59, 67, 131, 257, 509, 513, 1009, 1031, 2018, 2039, 4099, 8209, 10007, 10239, 40009, 100003, 300007]
+BLUESTEIN_SIZES = [19, 59, 67, 131, 257, 509, 513, 1009, 1031, 2018, 2039, 2053, 4093, 4099, 8209, 10007, 10239, 40009, 100003, 300007]
 
 
 @pytest.mark.parametrize("n", C2C_SIZES)
