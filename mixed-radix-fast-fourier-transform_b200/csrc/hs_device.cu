@@ -232,7 +232,8 @@ static void launch_tiled(const void *in, void *out, const void *tw, const HsTile
     if constexpr (IO == 0) {
         // (half as many columns per tile and two CTAs per SM -- independent phase streams -- measured slower: 2^20 34.3 % vs
         // 39.3 %, 2^18 35.6 % vs 40.3 % of the HBM peak; 32-byte runs cost more than the overlap gains)
-        if (tma_enabled(P::N) && g.in_c == 1 && g.blk_log == 0) { launch_tiled_tma<P, SGN, C, TW, STCOL>(in, out, tw, g, howmany, st); return; }
+        constexpr int CT = HsTileColsTma<P, C>::value;
+        if (tma_enabled(P::N) && g.in_c == 1 && g.blk_log == 0 && g.ncols % CT == 0) { launch_tiled_tma<P, SGN, CT, TW, STCOL>(in, out, tw, g, howmany, st); return; }
     }
     constexpr int MINB = (P::T * C <= 256 || (P::T * C <= 320 && P::N / P::T <= 10)) ? 2 : 1; // 320 threads of 8-10 points fit 100 registers
     constexpr int smem = C * hs_col_stride(P::NPAD, C) * (int)sizeof(cplx);

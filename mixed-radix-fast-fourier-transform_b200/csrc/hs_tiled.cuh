@@ -34,7 +34,11 @@ constexpr int hs_col_stride(int npad, int C)
 
 // columns per CTA: as many as shared memory and the register file allow (longer contiguous runs on the
 // strided side), 128..512 threads per CTA
-template <class P> struct HsTileCols { static constexpr int C = P::T >= 64 ? (P::N <= 512 ? 8 : 4) : 16; }; // measured: 512-pt 4/8/16 -> 35/40/31 %, 1024-pt 4/8 -> 36/30 % (two-pass, 2^18 / 2^20)
+// 512-point sub-plans: 4 columns (two 256-thread CTAs per SM) for the one-CTA-per-tile kernel, 8 for the persistent TMA-staged
+// one (measured after the bank-conflict fix, fraction of the HBM peak at 2^18 / 2^19: plain kernel 29.9 / 32.8 % with 8
+// columns, 41.2 / 40.8 % with 4; TMA kernel 41.1 / 39.7 % with 8, 41.6 / 38.2 % with 4; c2r 2^20 28.7 -> 31.4 %)
+template <class P> struct HsTileCols { static constexpr int C = P::T >= 64 ? 4 : 16; };
+template <class P, int C> struct HsTileColsTma { static constexpr int value = (P::N == 512 && C == 4) ? 8 : C; };
 
 // LDP / STP: residency class of the loads / stores (hs_ld_mp / hs_st_mp in hs_common.cuh): 0 for the stand-alone
 // passes, 1 / 2 inside the persistent pipeline kernels of hs_pipe.cuh.
