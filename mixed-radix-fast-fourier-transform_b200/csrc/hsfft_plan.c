@@ -921,7 +921,8 @@ fft_object fft_init(int N, int sgn)
 
 static long long chunk_len(long long howmany, size_t bytes_per_xf)
 {
-    const size_t target = (size_t)64 << 20;
+    static size_t target = 0; /* bytes per chunk of the host-pointer pipeline (HSFFT_CHUNK_MB, default 64) */
+    if (!target) target = (size_t)env_int("HSFFT_CHUNK_MB", 64) << 20;
     long long c = (long long)(target / (bytes_per_xf ? bytes_per_xf : 1));
     if (c < 1) c = 1;
     if (c > howmany) c = howmany;
