@@ -75,5 +75,10 @@ def product_lib(hs):
 def emu_lib(hs):
     """CPU emulation of the kernels (tests/emu): the product's kernel source run on OS threads."""
     d = os.path.join(ROOT, "tests", "emu")
+    if os.environ.get("HSFFT_EMU_ASAN"):
+        # AddressSanitizer build of the emulation: run as
+        #   HSFFT_EMU_ASAN=1 LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0 pytest tests/test_emu_kernels.py
+        subprocess.run(["make", "-s", "-C", d, "SAN=1"], check=True, capture_output=True)
+        return hs.load(os.path.join(d, "_build_asan", "libhsfft_emu.so"))
     subprocess.run(["make", "-s", "-C", d], check=True, capture_output=True)
     return hs.load(os.path.join(d, "_build", "libhsfft_emu.so"))
