@@ -292,6 +292,28 @@ def main():
     ms_per_step = total_ms / args.steps
     value = world * batch * flops_per_transform(kind, n) / (ms_per_step * 1e-3) / 1e9
 
+    # a prime N that runs as Rader's cyclic convolution: also time the reference's own route (padded chirp-z) so the line
+    # carries both numbers; the plan reads HSFFT_NO_RADER when it is first executed
+    alt_route = None
+    if kind == "c2c" and "rader" in describe:
+        os.environ["HSFFT_NO_RADER"] = "1"
+        try:
+            plan_b = hs.Plan(n, 1)
+            for _ in range(max(args.warmup, 1)):
+                plan_b.exec_dev(x, y, batch)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(args.steps):
+                plan_b.exec_dev(x, y, batch)
+            e1.record()
+            torch.cuda.synchronize()
+            ms_b = e0.elapsed_time(e1) / args.steps
+            alt_route = {"plan": plan_b.describe(), "ms_per_step": ms_b,
+                         "hbm_frac": batch * bytes_per_transform(kind, n) / (ms_b * 1e-3) / 1e9 / measured_peak()[0]}
+        finally:
+            del os.environ["HSFFT_NO_RADER"]
+
     # ---------------- roofline of the dominant kernel (the whole step when it is one launch)
     peak, peak_src = measured_peak()
     kernel_ms = ms_per_step if launches == args.steps else (total_ms / max(launches, 1)) * (launches / args.steps)
@@ -364,6 +386,8 @@ def main():
             "hbm_gbs": achieved * world, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(launches), "clocks": clocks,
         }
+        if alt_route:
+            line["config"]["chirp_z_route"] = alt_route
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

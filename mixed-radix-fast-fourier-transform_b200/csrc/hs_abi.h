@@ -46,7 +46,7 @@ HS_RULE int hs_stage_tw_entries(int r, int m, int split_min)
 }
 
 /* compile-time kernel families */
-enum { HS_CT_C2C = 0, HS_CT_BLUESTEIN = 1, HS_CT_TWOPASS = 2, HS_CT_SUB = 3 };
+enum { HS_CT_C2C = 0, HS_CT_BLUESTEIN = 1, HS_CT_TWOPASS = 2, HS_CT_SUB = 3, HS_CT_RADER = 4 };
 
 /* one compile-time specialised shared-memory transform the CUDA side offers */
 typedef struct hs_ct_desc {
@@ -211,6 +211,10 @@ void  hs_cu_launch_blu_mid(int sub_id, int chirp_sgn, const void *d_in, void *d_
 void  hs_cu_launch_dist_twiddle(void *b, const void *hi, const void *lo, long long rows, long long cols, long long c0, int logN,
                                 int logS, void *stream);
 /* fused Bluestein: d_tw_f / d_tw_i are the forward-order / inverse-order stage tables of length M */
+/* Rader kernel for prime N = n + 1 (descriptor family HS_CT_RADER, length n): d_perm[q] = g^q mod N (n ints),
+ * d_bk = FFT_n(b) / n with b[m] = exp(-sgn 2 pi i g^-m / N); d_tw_i belongs to the reversed radix list */
+void  hs_cu_launch_ct_rader(int id, const void *d_in, void *d_out, const void *d_tw_f, const void *d_tw_i, const void *d_perm,
+                            const void *d_bk, long long howmany, void *stream);
 void  hs_cu_launch_ct_bluestein(int id, int sgn, int N, const void *d_in, void *d_out, const void *d_tw_f, const void *d_tw_i,
                                 const void *d_chirp, const void *d_hk, long long howmany, void *stream);
 

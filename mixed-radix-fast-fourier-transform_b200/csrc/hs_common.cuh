@@ -38,6 +38,8 @@ static inline double2 hs_ld_stream(const double2 *p) { return *p; }
 static inline void hs_st_stream(double2 *p, double2 v) { *p = v; }
 static inline double2 hs_ld_tab(const double2 *p) { return *p; }
 static inline double hs_ld_stream_d(const double *p) { return *p; }
+static inline int hs_ld_idx(const int *p) { return *p; }
+static inline double2 hs_ld_gather(const double2 *p) { return *p; }
 static inline void hs_st_stream_d(double *p, double v) { *p = v; }
 template <int MP> static inline double2 hs_ld_mp(const double2 *p) { return *p; }
 template <int MP> static inline void hs_st_mp(double2 *p, double2 v) { *p = v; }
@@ -132,6 +134,10 @@ HS_DEVICE double2 hs_ld_tab(const double2 *p)
     return v;
 }
 HS_DEVICE double hs_ld_stream_d(const double *p) { return __ldcs(p); }
+// index tables (re-read by every CTA) and samples gathered through them (the other half of each 32-byte sector is
+// some other lane's sample a moment later: let L1 keep the line)
+HS_DEVICE int hs_ld_idx(const int *p) { return __ldg(p); }
+HS_DEVICE double2 hs_ld_gather(const double2 *p) { return __ldg(p); }
 HS_DEVICE void hs_st_stream_d(double *p, double v) { __stcs(p, v); }
 
 // ---- L2 residency classes for the persistent pipeline kernels (hs_pipe.cuh).  Intermediates that one

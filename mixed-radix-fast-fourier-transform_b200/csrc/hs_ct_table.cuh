@@ -62,6 +62,12 @@ static void ct_init()
     fill_desc<PB1024>(g_ct[CT_B1024], CT_B1024, HS_CT_BLUESTEIN);
     fill_desc<PB4096>(g_ct[CT_B4096], CT_B4096, HS_CT_BLUESTEIN);
     fill_desc<PB8192f>(g_ct[CT_B8192], CT_B8192, HS_CT_BLUESTEIN);
+    fill_desc<PR1008f>(g_ct[CT_R1008], CT_R1008, HS_CT_RADER);
+    fill_desc<PR1008af>(g_ct[CT_R1008A], CT_R1008A, HS_CT_RADER);
+    fill_desc<PR1008gf>(g_ct[CT_R1008G], CT_R1008G, HS_CT_RADER);
+    fill_desc<PB256>(g_ct[CT_R256], CT_R256, HS_CT_RADER);
+    fill_desc<PB2048x2f>(g_ct[CT_B2048X2], CT_B2048X2, HS_CT_BLUESTEIN);
+    fill_desc<PB256x16>(g_ct[CT_B256X16], CT_B256X16, HS_CT_BLUESTEIN);
     fill_desc<P4096x>(g_ct[CT_4096X], CT_4096X, HS_CT_C2C);
     fill_desc<P3000x>(g_ct[CT_3000X], CT_3000X, HS_CT_C2C);
     fill_desc<P4096y>(g_ct[CT_4096Y], CT_4096Y, HS_CT_C2C);
@@ -133,26 +139,48 @@ extern "C" void hs_cu_launch_ct_c2c(int id, int sgn, const void *d_in, void *d_o
     }
 }
 
+extern "C" void hs_cu_launch_ct_rader(int id, const void *d_in, void *d_out, const void *d_tw_f, const void *d_tw_i, const void *d_perm,
+                                      const void *d_bk, long long howmany, void *stream)
+{
+    hs_stream_t st = (hs_stream_t)stream;
+    switch (id) {
+    case CT_R1008: launch_rader<PR1008f, PR1008i, 5>(d_in, d_out, d_tw_f, d_tw_i, d_perm, d_bk, howmany, st); break;
+    case CT_R1008A: launch_rader<PR1008af, PR1008ai, 8>(d_in, d_out, d_tw_f, d_tw_i, d_perm, d_bk, howmany, st); break;
+    case CT_R1008G: launch_rader<PR1008gf, PR1008gi, 6>(d_in, d_out, d_tw_f, d_tw_i, d_perm, d_bk, howmany, st); break;
+    case CT_R256: launch_rader<PB256, PB256, 8>(d_in, d_out, d_tw_f, d_tw_i, d_perm, d_bk, howmany, st); break;
+    default: fprintf(stderr, "Error: unknown Rader kernel id %d\n", id); exit(EXIT_FAILURE);
+    }
+}
+
+
+#define HS_BLU_CASE(ID, PF, PI, MINB)                                                                                     \
+    case ID:                                                                                                              \
+        if (sgn == 1) launch_blu<PF, PI, 1, MINB>(N, d_in, d_out, d_tw_f, d_tw_i, d_chirp, d_hk, howmany, st);            \
+        else launch_blu<PF, PI, -1, MINB>(N, d_in, d_out, d_tw_f, d_tw_i, d_chirp, d_hk, howmany, st);                    \
+        break;
+
 extern "C" void hs_cu_launch_ct_bluestein(int id, int sgn, int N, const void *d_in, void *d_out, const void *d_tw_f, const void *d_tw_i,
                                           const void *d_chirp, const void *d_hk, long long howmany, void *stream)
 {
     hs_stream_t st = (hs_stream_t)stream;
     switch (id) {
+    HS_BLU_CASE(CT_B2048X2, PB2048x2f, PB2048x2i, 2)
+    HS_BLU_CASE(CT_B256X16, PB256x16, PB256x16, 2)
     case CT_B2048:
-        if (sgn == 1) launch_blu<PB2048f, PB2048i, 1, 2>(N, d_in, d_out, d_tw_f, d_tw_i, d_chirp, d_hk, howmany, st);
-        else launch_blu<PB2048f, PB2048i, -1, 2>(N, d_in, d_out, d_tw_f, d_tw_i, d_chirp, d_hk, howmany, st);
+        if (sgn == 1) launch_blu<PB2048f, PB2048i, 1, 4>(N, d_in, d_out, d_tw_f, d_tw_i, d_chirp, d_hk, howmany, st);
+        else launch_blu<PB2048f, PB2048i, -1, 4>(N, d_in, d_out, d_tw_f, d_tw_i, d_chirp, d_hk, howmany, st);
         break;
     case CT_B256:
-        if (sgn == 1) launch_blu<PB256, PB256, 1, 2>(N, d_in, d_out, d_tw_f, d_tw_i, d_chirp, d_hk, howmany, st);
-        else launch_blu<PB256, PB256, -1, 2>(N, d_in, d_out, d_tw_f, d_tw_i, d_chirp, d_hk, howmany, st);
+        if (sgn == 1) launch_blu<PB256, PB256, 1, 8>(N, d_in, d_out, d_tw_f, d_tw_i, d_chirp, d_hk, howmany, st);
+        else launch_blu<PB256, PB256, -1, 8>(N, d_in, d_out, d_tw_f, d_tw_i, d_chirp, d_hk, howmany, st);
         break;
     case CT_B512:
-        if (sgn == 1) launch_blu<PB512, PB512, 1, 3>(N, d_in, d_out, d_tw_f, d_tw_i, d_chirp, d_hk, howmany, st);
-        else launch_blu<PB512, PB512, -1, 3>(N, d_in, d_out, d_tw_f, d_tw_i, d_chirp, d_hk, howmany, st);
+        if (sgn == 1) launch_blu<PB512, PB512, 1, 12>(N, d_in, d_out, d_tw_f, d_tw_i, d_chirp, d_hk, howmany, st);
+        else launch_blu<PB512, PB512, -1, 12>(N, d_in, d_out, d_tw_f, d_tw_i, d_chirp, d_hk, howmany, st);
         break;
     case CT_B1024:
-        if (sgn == 1) launch_blu<PB1024, PB1024, 1, 2>(N, d_in, d_out, d_tw_f, d_tw_i, d_chirp, d_hk, howmany, st);
-        else launch_blu<PB1024, PB1024, -1, 2>(N, d_in, d_out, d_tw_f, d_tw_i, d_chirp, d_hk, howmany, st);
+        if (sgn == 1) launch_blu<PB1024, PB1024, 1, 8>(N, d_in, d_out, d_tw_f, d_tw_i, d_chirp, d_hk, howmany, st);
+        else launch_blu<PB1024, PB1024, -1, 8>(N, d_in, d_out, d_tw_f, d_tw_i, d_chirp, d_hk, howmany, st);
         break;
     case CT_B4096:
         if (sgn == 1) launch_blu<PB4096, PB4096, 1, 2>(N, d_in, d_out, d_tw_f, d_tw_i, d_chirp, d_hk, howmany, st);

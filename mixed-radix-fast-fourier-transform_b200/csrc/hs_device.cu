@@ -190,6 +190,42 @@ static void launch_blu(int N, const void *in, void *out, const void *twf, const 
     ++g_launches;
 }
 
+#ifndef HS_RADER_STAGE_DEFAULT
+#define HS_RADER_STAGE_DEFAULT 2
+#endif
+template <class PF, class PI, int MINB, int STG>
+static void launch_rader_v(const void *in, void *out, const void *twf, const void *twi, const void *perm, const void *bk, long long howmany,
+                           cudaStream_t st)
+{
+    constexpr int smem = HsRaderSmem<PF, PI>::bytes;
+    auto kern = hs_rader_kernel<PF, PI, MINB, STG>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        HS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        set_carveout((const void *)kern, smem, MINB);
+        attr_done = true;
+    }
+    const long long blocks = (howmany + PF::X - 1) / PF::X;
+    check_grid(blocks);
+    kern<<<(unsigned)blocks, PF::threads, smem, st>>>((const cplx *)in, (cplx *)out, (const cplx *)twf, (const cplx *)twi, (const int *)perm,
+                                                      (const cplx *)bk, howmany, prefetch_dist(MINB));
+    HS_CUDA_CHECK(cudaGetLastError());
+    ++g_launches;
+}
+
+// HSFFT_RADER_STAGE=0 / 2: scatter the outputs straight to HBM / through shared memory (default; measured on B200 at
+// N = 1009: 0.238 -> 0.228 ms, N = 257: 0.173 -> 0.161 ms).  Staging the gather as well (bit 0 of the kernel's STG)
+// costs a barrier before the first pass and was slower everywhere (0.250 ms), so it is not instantiated here.
+template <class PF, class PI, int MINB>
+static void launch_rader(const void *in, void *out, const void *twf, const void *twi, const void *perm, const void *bk, long long howmany,
+                         cudaStream_t st)
+{
+    static int stg = -1;
+    if (stg < 0) { const char *e = getenv("HSFFT_RADER_STAGE"); stg = e ? atoi(e) & 3 : HS_RADER_STAGE_DEFAULT; }
+    if (stg & 2) launch_rader_v<PF, PI, MINB, 2>(in, out, twf, twi, perm, bk, howmany, st);
+    else launch_rader_v<PF, PI, MINB, 0>(in, out, twf, twi, perm, bk, howmany, st);
+}
+
 // persistent, TMA-staged variant (hs_tiled_tma_kernel).  Measured on B200 (two-pass c2c, same box, TMA vs plain):
 // 2^17 43.8 vs 38.8 %, 2^18 40.5 vs 29.6 %, 2^19 36.4 vs 32.3 %, 2^20 35.9 vs 35.6 % of the HBM peak, but
 // 2^14..2^16 (128/256-point sub-plans, already at the two-pass cap) 45-49 vs 52-54 %.  So it is the default for

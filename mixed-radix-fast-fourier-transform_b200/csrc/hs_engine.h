@@ -46,6 +46,7 @@ typedef struct hs_dev_obj {
     hs_c2c *fwdM, *invM;
     void *d_chirp, *d_hk;
     int blu_ct_id;
+    int rader_ct_id; /* >= 0: prime N run as a cyclic convolution of length N-1 (d_chirp = int perm[N-1], d_hk = Bk) */
     void *d_blu_twf, *d_blu_twi;
     /* long Bluestein (M = n1*n2 two-pass): three fused kernels, see hs_tiled.cuh */
     int big, big_n1, big_n2, big_sub1, big_sub2;

@@ -88,3 +88,125 @@ hs_bluestein_kernel(const cplx *HS_RESTRICT in, cplx *HS_RESTRICT out, const cpl
     HsStoreChirpCrop<SGN> st2{out + (active ? xf : 0) * N, chirp, N};
     hs_fft_team<PI, -1>(ld2, st2, sm, twi, t, active);
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Rader's algorithm for a prime length N whose N-1 has a shared-memory plan (N = 1009: N-1 = 1008 = 16*9*7).  The
+// reference sends every prime to Bluestein with a power-of-two pad M >= 2N-1 (two 2048-point transforms for N = 1009);
+// for such a prime the DFT is also a CYCLIC convolution of length L = N-1 exactly, with no padding:
+//     X[0]      = sum_n x[n]
+//     X[g^-p]   = x[0] + sum_q x[g^q] * W^(g^(q-p))   = x[0] + (a (*) b)[p],    a[q] = x[g^q],  b[m] = W^(g^-m)
+// (g a primitive root mod N, W = exp(-sgn 2 pi i / N)).  So one kernel does
+//     gather a through perm[q] = g^q mod N -> FFT_L -> * Bk (+ x[0] on the DC bin) -> IFFT_L -> scatter to perm[L - p]
+// with Bk = FFT_L(b) / L a plan-time table.  Two facts keep it to the Bluestein kernel's shape: A[0] = sum_{n>0} x[n],
+// so X[0] = x[0] + A[0] is written by the thread that holds bin 0; and adding x[0] to bin 0 of the product adds x[0] to
+// every output of the unnormalised inverse transform.  Half the arithmetic of the padded chirp-z, same single HBM
+// read and write; the result is the same DFT to rounding (full-precision radix-3/7 constants: HsExact plans).
+struct HsLoadRader {
+    static constexpr bool kPost = false;
+    const cplx *HS_RESTRICT x;
+    const int *HS_RESTRICT perm;
+    HS_DEVICE cplx operator()(int, int, int n) const { return hs_ld_gather(x + hs_ld_idx(perm + n)); }
+};
+// staged forms: the row is copied into the team's buffer with coalesced loads first and gathered from there (the index
+// loads then overlap the row's HBM latency instead of preceding it, and the LSU sees 16-byte shared accesses instead of
+// one 32-byte sector per lane); the outputs are scattered into the buffer and leave it with coalesced stores
+struct HsLoadRaderSm {
+    static constexpr bool kPost = false, kFromSmem = true;
+    const cplx *sm;
+    const int *HS_RESTRICT perm;
+    HS_DEVICE cplx operator()(int, int, int n) const { return sm[hs_ld_idx(perm + n)]; }
+};
+struct HsStoreRaderSm {
+    static constexpr bool kToSmem = true;
+    cplx *sm;
+    const int *HS_RESTRICT perm;
+    int L;
+    HS_DEVICE void operator()(int, int, int p, cplx v) const { sm[hs_ld_idx(perm + (p ? L - p : 0))] = v; }
+};
+template <int RL>
+struct HsStoreRegsMulRader {
+    cplx (*y)[RL];
+    const cplx *HS_RESTRICT bk;
+    const cplx *HS_RESTRICT x;
+    cplx *HS_RESTRICT out;
+    HS_DEVICE void operator()(int u, int j, int k, cplx v) const
+    {
+        cplx r = hs_mul(v, hs_ld_tab(bk + k));
+        if (k == 0) {
+            const cplx x0 = hs_ld_gather(x);
+            hs_st_stream(out, hs_c(x0.x + v.x, x0.y + v.y));
+            r.x += x0.x;
+            r.y += x0.y;
+        }
+        y[u][j] = r;
+    }
+};
+struct HsStoreRader {
+    cplx *HS_RESTRICT out;
+    const int *HS_RESTRICT perm;
+    int L;
+    HS_DEVICE void operator()(int, int, int p, cplx v) const { hs_st_stream(out + hs_ld_idx(perm + (p ? L - p : 0)), v); }
+};
+template <class P>
+struct HsPassPoints {
+    static constexpr int first = P::pass_size(0) == 2 ? P::radix(0) * P::radix(1) : P::radix(0);
+    static constexpr int last = P::pass_size(P::NPASS - 1) == 2 ? P::radix(P::NST - 1) * P::radix(P::NST - 2) : P::radix(P::NST - 1);
+};
+
+template <class PF, class PI>
+struct HsRaderSmem {
+    static constexpr int npad0 = PF::NPAD > PI::NPAD ? PF::NPAD : PI::NPAD;
+    static constexpr int npad = npad0 > PF::N + 1 ? npad0 : PF::N + 2; // room for the N = L+1 staged outputs
+    static constexpr int bytes = npad * PF::X * 16;
+};
+
+// PF / PI: forward / inverse plans of length L = N-1, PI's first pass as wide as PF's last (register hand-over).
+// bk already carries the plan direction, so one instantiation serves both.  STG bit 0: gather through the shared-memory
+// buffer, bit 1: scatter through it.
+template <class PF, class PI, int MINB, int STG>
+HS_GLOBAL void HS_LAUNCH_BOUNDS(PF::threads, MINB)
+hs_rader_kernel(const cplx *HS_RESTRICT in, cplx *HS_RESTRICT out, const cplx *HS_RESTRICT twf, const cplx *HS_RESTRICT twi,
+                const int *HS_RESTRICT perm, const cplx *HS_RESTRICT bk, long long howmany, int pf_dist)
+{
+    static_assert(PF::N == PI::N && PF::T == PI::T && PF::X == PI::X, "plans must pair");
+    constexpr int RL = HsPassPoints<PF>::last;
+    static_assert(HsPassPoints<PI>::first == RL, "register hand-over needs passes of the same width");
+    constexpr int L = PF::N, N = L + 1;
+    constexpr int NB = L / RL, B = (NB + PF::T - 1) / PF::T;
+    HS_DYN_SMEM(cplx, smem);
+    const int team = HS_TID / PF::T, t = HS_TID % PF::T;
+    const long long xf = HS_BID * PF::X + team;
+    const bool active = xf < howmany;
+    cplx *sm = smem + team * HsRaderSmem<PF, PI>::npad;
+    cplx y[B][RL];
+    if (pf_dist > 0 && HS_TID == 0) {
+        const long long pf = (HS_BID + pf_dist) * PF::X, left = howmany - pf;
+        if (left > 0) hs_prefetch_l2(in + pf * N, (unsigned)((left < PF::X ? left : PF::X) * N * 16));
+    }
+    const cplx *x = in + (active ? xf : 0) * N;
+    cplx *o = out + (active ? xf : 0) * N;
+    static_assert(HsRaderSmem<PF, PI>::npad >= N, "the staged row must fit the team's buffer");
+    HsStoreRegsMulRader<RL> st{y, bk, x, o};
+    if constexpr (STG & 1) {
+        if (active)
+            for (int i = t; i < N; i += PF::T) sm[i] = hs_ld_stream(x + i);
+        HS_SYNC();
+        HsLoadRaderSm ld{sm, perm};
+        hs_fft_team<PF, 1>(ld, st, sm, twf, t, active);
+    } else {
+        HsLoadRader ld{x, perm};
+        hs_fft_team<PF, 1>(ld, st, sm, twf, t, active);
+    }
+    HS_SYNC();
+    HsLoadRegs<RL> ld2{y};
+    if constexpr (STG & 2) {
+        HsStoreRaderSm st2{sm, perm, L};
+        hs_fft_team<PI, -1>(ld2, st2, sm, twi, t, active);
+        HS_SYNC();
+        if (active)
+            for (int i = 1 + t; i < N; i += PF::T) hs_st_stream(o + i, sm[i]);
+    } else {
+        HsStoreRader st2{o, perm, L};
+        hs_fft_team<PI, -1>(ld2, st2, sm, twi, t, active);
+    }
+}

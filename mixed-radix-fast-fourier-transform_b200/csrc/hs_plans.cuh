@@ -28,14 +28,16 @@ using P512   = HsPlan<512, 64, 4, 3, -1, 0, 8, 8, 8>;
 using P256   = HsPlan<256, 16, 16, 4, -1, 0, 16, 16>;
 using P8192  = HsPlan<8192, 512, 1, 4, -1, 0, 8, 8, 8, 16>;
 // fused Bluestein, M = 2048 (N = 513..1024, e.g. the N = 1009 config): forward / inverse pair
-using PB2048f = HsPlan<2048, 128, 2, 4, HS_B2048_SPLIT, 0, 8, 16, 16>;
-using PB2048i = HsPlan<2048, 128, 2, 4, HS_B2048_SPLIT, 0, 16, 16, 8>;
+using PB2048f = HsPlan<2048, 128, 1, 4, HS_B2048_SPLIT, 0, 8, 16, 16>;
+using PB2048i = HsPlan<2048, 128, 1, 4, HS_B2048_SPLIT, 0, 16, 16, 8>;
 // the same fused kernel for the other pad lengths one SM can hold (N = 65..2048 all run as one kernel); the radix lists
 // are palindromes, so the inverse plan is the forward plan and the spectrum is handed over in registers
-// (all conflict free, tests/emu/bank_check.py)
-using PB256  = HsPlan<256, 16, 16, 4, HS_B2048_SPLIT, 0, 16, 16>;
-using PB512  = HsPlan<512, 64, 4, 3, HS_B2048_SPLIT, 0, 8, 8, 8>;
-using PB1024 = HsPlan<1024, 64, 4, 3, HS_B2048_SPLIT, 0, 8, 16, 8>;
+// (all conflict free, tests/emu/bank_check.py).  One transform per CTA (four for M = 256) and many CTAs per SM: measured
+// against 2-4 transforms per CTA, M = 2048 0.300 -> 0.267 ms, 1024 0.283 -> 0.235, 512 0.237 -> 0.208, 256 0.183 -> 0.162
+// (profiles/r1b_small_cta_variants.txt)
+using PB256  = HsPlan<256, 16, 4, 4, HS_B2048_SPLIT, 0, 16, 16>;
+using PB512  = HsPlan<512, 64, 1, 3, HS_B2048_SPLIT, 0, 8, 8, 8>;
+using PB1024 = HsPlan<1024, 64, 1, 3, HS_B2048_SPLIT, 0, 8, 16, 8>;
 using PB4096 = HsPlan<4096, 256, 1, 4, HS_B2048_SPLIT, 0, 16, 16, 16>;
 using PB8192f = HsPlan<8192, 512, 1, 3, HS_B2048_SPLIT, 0, 8, 16, 8, 8>; // one CTA per SM (147 KB); N = 2049..4096
 using PB8192i = HsPlan<8192, 512, 1, 3, HS_B2048_SPLIT, 0, 8, 8, 16, 8>;
@@ -65,8 +67,27 @@ using S1024i = HsPlan<1024, 64, 1, 3, HS_SUB_SPLIT, 0, 8, 8, 16>;
 using S160x  = HsExact<HsPlan<160, 20, 1, 3, HS_SUB_SPLIT, 0, 5, 4, 8>>;
 using S160xi = HsExact<HsPlan<160, 20, 1, 3, HS_SUB_SPLIT, 0, 8, 4, 5>>;
 
+// Rader (prime N, cyclic convolution of length N-1 held in shared memory; hs_rader_kernel): N = 1009 -> 1008 = 7*9*16,
+// full-precision radix-3/7 constants.  The forward plan ends and the inverse plan starts with the same pass, so the
+// spectrum is handed over in registers; pads differ because the strided reads of the two directions differ
+// (forward: last pass reads stride 16 -> one pad per 16; inverse: last pass reads stride 7, conflict free unpadded).
+// Measured on B200, 16384 transforms (profiles/r1b_rader_variants.txt): one transform per CTA and 5-6 CTAs per SM
+// 0.194-0.200 ms whatever the pass split (T = 112 / 63 / 126); two or four per CTA 0.22-0.25 ms; the reference's
+// chirp-z route (two 2048-point transforms) 0.300 ms.
+using PR1008f  = HsExact<HsPlan<1008, 112, 1, 4, HS_B2048_SPLIT, 121, 7, 3, 3, 16>>;
+using PR1008i  = HsExact<HsPlan<1008, 112, 1, 0, HS_B2048_SPLIT, 121, 16, 3, 3, 7>>;
+using PR1008af = HsExact<HsPlan<1008, 63, 1, 4, HS_B2048_SPLIT, 121, 7, 3, 3, 16>>;      // 3 | 2 | 1 butterflies per thread
+using PR1008ai = HsExact<HsPlan<1008, 63, 1, 0, HS_B2048_SPLIT, 121, 16, 3, 3, 7>>;
+using PR1008gf = HsExact<HsPlan<1008, 112, 1, 0, HS_B2048_SPLIT, 112, 7, 16, 3, 3>>;     // 9-point hand-over: 36 registers instead of 64
+using PR1008gi = HsExact<HsPlan<1008, 112, 1, 0, HS_B2048_SPLIT, 211, 3, 3, 16, 7>>;
+// the round-1 forms with several transforms per CTA, kept for A/B runs (HSFFT_PREFER_CT)
+using PB256x16 = HsPlan<256, 16, 16, 4, HS_B2048_SPLIT, 0, 16, 16>;
+using PB2048x2f = HsPlan<2048, 128, 2, 4, HS_B2048_SPLIT, 0, 8, 16, 16>;
+using PB2048x2i = HsPlan<2048, 128, 2, 4, HS_B2048_SPLIT, 0, 16, 16, 8>;
+
 enum { CT_4096A = 0, CT_4096B, CT_3000, CT_1024, CT_2048, CT_512, CT_256, CT_8192, CT_B2048, CT_4096X, CT_3000X, CT_4096Y, CT_3000Y, CT_3000Z,
        CT_T14, CT_T15, CT_T16, CT_T17, CT_T18, CT_T19, CT_T20,
        CT_S128, CT_S256, CT_S512, CT_S1024,
        CT_TX20480, CT_TX40960, CT_TX81920, CT_TX163840, CT_S160X,
-       CT_B256, CT_B512, CT_B1024, CT_B4096, CT_B8192, CT_COUNT };
+       CT_B256, CT_B512, CT_B1024, CT_B4096, CT_B8192,
+       CT_R1008, CT_R1008A, CT_R1008G, CT_R256, CT_B2048X2, CT_B256X16, CT_COUNT };

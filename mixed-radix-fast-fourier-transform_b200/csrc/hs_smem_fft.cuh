@@ -104,6 +104,18 @@ struct HsNoHooks {
     HS_DEVICE void before_last_pass() const {}
 };
 
+// A loader / storer may itself work on the team's shared-memory buffer (a staged gather or scatter, hs_fused.cuh): it
+// says so with `static constexpr bool kFromSmem / kToSmem = true`, and the pass then keeps the read-before-overwrite
+// barrier it would otherwise drop for a first / last pass.
+template <class T, class = void>
+struct HsLdFromSmem { static constexpr bool value = false; };
+template <class T>
+struct HsLdFromSmem<T, decltype((void)T::kFromSmem)> { static constexpr bool value = T::kFromSmem; };
+template <class T, class = void>
+struct HsStToSmem { static constexpr bool value = false; };
+template <class T>
+struct HsStToSmem<T, decltype((void)T::kToSmem)> { static constexpr bool value = T::kToSmem; };
+
 // ---------------------------------------------------------------------------- stage twiddles
 // wv[1..R) <- W_{M R}^{i k}, i = 1..R-1, for flat stage S (radix R on sub-transforms of length M).
 template <class P, int S>
@@ -193,7 +205,7 @@ HS_DEVICE void hs_stage(LD &ld, ST &st, const HsLane &ln, const cplx *HS_RESTRIC
             hs_bfly<R, SGN, P::EXACT>(v[u]);
         }
     }
-    if (!FIRST && !LAST) hk.sync(); // every thread has read its inputs; the buffer may be overwritten
+    if ((!FIRST || HsLdFromSmem<LD>::value) && (!LAST || HsStToSmem<ST>::value)) hk.sync(); // every thread has read its inputs; the buffer may be overwritten
     HS_UNROLL
     for (int u = 0; u < B; ++u) {
         const int b = t + P::T * u;
@@ -281,7 +293,7 @@ HS_DEVICE void hs_stage2(LD &ld, ST &st, const HsLane &ln, const cplx *HS_RESTRI
             }
         }
     }
-    if (!FIRST && !LAST) hk.sync();
+    if ((!FIRST || HsLdFromSmem<LD>::value) && (!LAST || HsStToSmem<ST>::value)) hk.sync();
     HS_UNROLL
     for (int u = 0; u < B; ++u) {
         const int b = t + P::T * u;

@@ -566,6 +566,70 @@ static void dev_free_contents(hs_dev_obj *d)
     }
 }
 
+/* Rader's algorithm (hs_fused.cuh): a prime N whose N-1 has a shared-memory kernel of the HS_CT_RADER family becomes one
+ * cyclic convolution of length L = N-1, half the points of Bluestein's padded one.  Builds perm[q] = g^q mod N and
+ * Bk = FFT_L(b) / L, b[m] = exp(-sgn 2 pi i g^(-m) / N), the latter as a direct sum in long double (plan time, L^2). */
+static int rader_setup(hs_dev_obj *d)
+{
+    const int N = d->N, L = N - 1;
+    if (N < 5 || getenv("HSFFT_NO_RADER")) return 0;
+    const hs_ct_desc *ct = find_ct_ex(HS_CT_RADER, L, 1);
+    if (!ct) return 0;
+    for (int f = 2; (long long)f * f <= N; ++f)
+        if (N % f == 0) return 0;
+    /* smallest primitive root: g^(L/p) != 1 for every prime p | L */
+    int pf[16], npf = 0, m = L;
+    for (int f = 2; (long long)f * f <= m; ++f)
+        if (m % f == 0) { pf[npf++] = f; while (m % f == 0) m /= f; }
+    if (m > 1) pf[npf++] = m;
+    int g = 0;
+    for (int c = 2; c < N && !g; ++c) {
+        int ok = 1;
+        for (int i = 0; i < npf && ok; ++i) {
+            long long r = 1, b = c;
+            for (int e = L / pf[i]; e; e >>= 1, b = b * b % N)
+                if (e & 1) r = r * b % N;
+            if (r == 1) ok = 0;
+        }
+        if (ok) g = c;
+    }
+    if (!g) return 0;
+    int *perm = (int *)malloc(sizeof(int) * L);
+    fft_data *bk = (fft_data *)malloc(sizeof(fft_data) * L);
+    long double *wr = (long double *)malloc(sizeof(long double) * 2 * L), *br = (long double *)malloc(sizeof(long double) * 2 * L);
+    if (!perm || !bk || !wr || !br) { fprintf(stderr, "Error: Memory allocation failed for Rader's tables\n"); exit(EXIT_FAILURE); }
+    long long v = 1;
+    for (int q = 0; q < L; ++q) { perm[q] = (int)v; v = v * g % N; }
+    const long double pi2 = 6.283185307179586476925286766559005768L;
+    for (int q = 0; q < L; ++q) { /* b[q] = W^(g^-q) = W^perm[(L-q) % L];  w[q] = exp(-2 pi i q / L) */
+        const long double a = -(long double)d->sgn * pi2 * (long double)perm[(L - q) % L] / (long double)N;
+        br[2 * q] = cosl(a); br[2 * q + 1] = sinl(a);
+        const long double t = -pi2 * (long double)q / (long double)L;
+        wr[2 * q] = cosl(t); wr[2 * q + 1] = sinl(t);
+    }
+    for (int k = 0; k < L; ++k) {
+        long double sr = 0, si = 0;
+        int j = 0;
+        for (int q = 0; q < L; ++q) {
+            sr += br[2 * q] * wr[2 * j] - br[2 * q + 1] * wr[2 * j + 1];
+            si += br[2 * q] * wr[2 * j + 1] + br[2 * q + 1] * wr[2 * j];
+            j += k; if (j >= L) j -= L;
+        }
+        bk[k].re = (fft_type)(sr / L); bk[k].im = (fft_type)(si / L);
+    }
+    int inv[8];
+    for (int s = 0; s < ct->nst; ++s) inv[s] = ct->radix[ct->nst - 1 - s];
+    d->rader_ct_id = ct->id;
+    d->M = L;
+    d->d_chirp = upload(perm, sizeof(int) * L);
+    d->d_hk = upload(bk, sizeof(fft_data) * L);
+    d->d_blu_twf = upload_stage_twiddles(ct->radix, ct->nst, 1, ct->split_min);
+    d->d_blu_twi = upload_stage_twiddles(inv, ct->nst, -1, ct->split_min);
+    hs_cu_stream_sync(NULL);
+    free(perm); free(bk); free(wr); free(br);
+    return 1;
+}
+
 static void dev_build(hs_dev_obj *d, fft_object plan)
 {
     d->key = plan;
@@ -573,12 +637,14 @@ static void dev_build(hs_dev_obj *d, fft_object plan)
     d->sgn = plan->sgn;
     d->lt = plan->lt;
     d->blu_ct_id = -1;
+    d->rader_ct_id = -1;
     if (d->N < 2 || (d->sgn != 1 && d->sgn != -1)) {
         fprintf(stderr, "Error: Invalid FFT object (N = %d, sgn = %d)\n", d->N, d->sgn);
         exit(EXIT_FAILURE);
     }
     for (int s = 0; s < HS_NSLOT; ++s) d->stream[s] = hs_cu_stream_create();
     if (d->lt == 0) { d->direct = hs_c2c_create(d->N, d->sgn); return; }
+    if (rader_setup(d)) return;
 
     /* Bluestein: chirp h and Hk = FFT_M(h padded and mirrored, scaled 1/M) live in HBM */
     const int N = d->N, M = bluestein_device_pad(N);
@@ -716,7 +782,7 @@ void hs_dev_reserve(hs_dev_obj *d, int slot, size_t in_bytes, size_t out_bytes, 
 size_t hs_dev_ws_bytes(const hs_dev_obj *d, long long howmany)
 {
     if (d->lt == 0) return hs_c2c_ws_elems(d->direct, howmany) * sizeof(fft_data);
-    if (d->blu_ct_id >= 0) return 0;
+    if (d->blu_ct_id >= 0 || d->rader_ct_id >= 0) return 0;
     if (d->big && d->big_pipe) return hs_pipe_ws_bytes(d->M, 2, howmany);
     if (d->big) return (size_t)2 * (howmany < d->big_chunk ? howmany : d->big_chunk) * d->M * sizeof(fft_data);
     return ((size_t)2 * howmany * d->M + hs_c2c_ws_elems(d->fwdM, howmany)) * sizeof(fft_data);
@@ -726,6 +792,10 @@ void hs_dev_exec(hs_dev_obj *d, const void *d_in, void *d_out, void *d_ws, long 
 {
     if (howmany <= 0) return;
     if (d->lt == 0) { hs_c2c_exec(d->direct, d_in, d_out, d_ws, howmany, stream); return; }
+    if (d->rader_ct_id >= 0) {
+        hs_cu_launch_ct_rader(d->rader_ct_id, d_in, d_out, d->d_blu_twf, d->d_blu_twi, d->d_chirp, d->d_hk, howmany, stream);
+        return;
+    }
     if (d->blu_ct_id >= 0) {
         hs_cu_launch_ct_bluestein(d->blu_ct_id, d->sgn, d->N, d_in, d_out, d->d_blu_twf, d->d_blu_twi, d->d_chirp, d->d_hk, howmany,
                                   stream);
@@ -1016,6 +1086,9 @@ const char *hsfft_plan_describe(fft_object obj)
     } else if (d->big)
         n = snprintf(buf, sizeof buf, "bluestein N=%d M=%d=%dx%d: 3 fused tiled kernels%s", d->N, d->M, d->big_n1, d->big_n2,
                      d->big_pipe ? " as one persistent L2-resident pipeline" : "");
+    else if (d->rader_ct_id >= 0)
+        n = snprintf(buf, sizeof buf, "rader N=%d (prime), cyclic convolution of length %d: fused compile-time kernel #%d", d->N, d->M,
+                     d->rader_ct_id);
     else if (d->blu_ct_id >= 0)
         n = snprintf(buf, sizeof buf, "bluestein N=%d M=%d: fused compile-time kernel #%d", d->N, d->M, d->blu_ct_id);
     else

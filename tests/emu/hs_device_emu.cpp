@@ -42,6 +42,22 @@ static void launch_blu(int N, const void *in, void *out, const void *twf, const 
     ++g_launches;
 }
 
+template <class PF, class PI, int MINB>
+static void launch_rader(const void *in, void *out, const void *twf, const void *twi, const void *perm, const void *bk, long long howmany,
+                         hs_stream_t)
+{
+    const long long blocks = (howmany + PF::X - 1) / PF::X;
+    const char *e = getenv("HSFFT_RADER_STAGE");
+    const int stg = e ? atoi(e) & 3 : 2;
+    auto k0 = hs_rader_kernel<PF, PI, MINB, 0>;
+    auto k1 = hs_rader_kernel<PF, PI, MINB, 1>;
+    auto k2 = hs_rader_kernel<PF, PI, MINB, 2>;
+    auto k3 = hs_rader_kernel<PF, PI, MINB, 3>;
+    hs_emu_launch(stg == 0 ? k0 : stg == 1 ? k1 : stg == 2 ? k2 : k3, blocks, PF::threads, HsRaderSmem<PF, PI>::bytes, (const cplx *)in,
+                  (cplx *)out, (const cplx *)twf, (const cplx *)twi, (const int *)perm, (const cplx *)bk, howmany, 2);
+    ++g_launches;
+}
+
 template <class PF, class PI, int CS>
 static void launch_blu_mid(const void *in, void *out, const void *twf, const void *twi, const HsTileGeom &g, const void *hk,
                            long long howmany, hs_stream_t)

@@ -33,15 +33,34 @@ def test_n3000_is_within_rounding_of_the_reference_not_just_tolerance(hs, emu_li
 
 
 @pytest.mark.parametrize("n", [67, 131, 257, 509, 1031, 2039, 4093])
-def test_fused_bluestein_every_pad_length_one_sm_holds(hs, emu_lib, oracle, n):
+def test_fused_bluestein_every_pad_length_one_sm_holds(hs, emu_lib, oracle, n, monkeypatch):
     """M = 256, 512, 1024, 4096 (palindromic radix lists: the inverse plan is the forward plan) and 8192."""
+    monkeypatch.setenv("HSFFT_NO_RADER", "1")  # N = 257 would otherwise run as a 256-point cyclic convolution
     for sgn in (1, -1):
         err, desc = run_c2c(hs, emu_lib, oracle, n, sgn, howmany=5)
-        assert "fused compile-time" in desc and err <= tol(n), (n, sgn, err, desc)
+        assert "bluestein" in desc and "fused compile-time" in desc and err <= tol(n), (n, sgn, err, desc)
+
+
+@pytest.mark.parametrize("n", [1009, 257])
+@pytest.mark.parametrize("stage", ["0", "2"])
+def test_rader_prime_lengths_with_a_smooth_predecessor(hs, emu_lib, oracle, n, stage, monkeypatch):
+    """N prime, N-1 = 1008 / 256 held in shared memory: gather by g^q, FFT, * Bk, IFFT, scatter by g^-p (hs_fused.cuh).
+    Odd batch: the last CTA has idle teams.  Same DFT as the reference's Bluestein route, to rounding."""
+    monkeypatch.setenv("HSFFT_RADER_STAGE", stage)
+    for sgn in (1, -1):
+        err, desc = run_c2c(hs, emu_lib, oracle, n, sgn, howmany=7)
+        assert "rader" in desc and err <= tol(n) and err < 5e-15, (n, sgn, err, desc)
+
+
+def test_rader_is_only_taken_for_primes_with_a_kernel(hs, emu_lib, oracle):
+    for n in (1008 + 1 + 1008, 1021, 769):  # 2017 = prime but 2016 has no kernel; 1021, 769: primes, N-1 without a kernel
+        with hs.Plan(n, 1, lib=emu_lib) as p:
+            assert "rader" not in p.describe(), (n, p.describe())
 
 
 @pytest.mark.parametrize("n", [1009, 513, 600, 1000])
-def test_fused_bluestein_and_neighbours(hs, emu_lib, oracle, n):
+def test_fused_bluestein_and_neighbours(hs, emu_lib, oracle, n, monkeypatch):
+    monkeypatch.setenv("HSFFT_NO_RADER", "1")
     for sgn in (1, -1):
         err, desc = run_c2c(hs, emu_lib, oracle, n, sgn)
         assert err <= tol(n), (n, sgn, err, desc)

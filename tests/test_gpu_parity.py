@@ -50,6 +50,26 @@ def test_c2c_bluestein(hs, product_lib, oracle, n, sgn):
     assert per_transform_worst(y, r) <= tol(n)
 
 
+@pytest.mark.parametrize("n", [1009, 257])
+@pytest.mark.parametrize("sgn", [1, -1])
+def test_c2c_prime_rader_and_bluestein_routes_agree(hs, product_lib, oracle, n, sgn):
+    """N = 1009 / 257 run as a cyclic convolution of length N-1 (Rader) by default and as the reference's padded chirp-z
+    with HSFFT_NO_RADER=1 (read at plan build); both must match the reference, and each other far inside the tolerance."""
+    x = rand_cplx(37, n, seed=7 + n)
+    with hs.Plan(n, sgn) as p:
+        d1, y1 = p.describe(), p.exec(x)
+    os.environ["HSFFT_NO_RADER"] = "1"
+    try:
+        with hs.Plan(n, sgn) as p:
+            d2, y2 = p.describe(), p.exec(x)
+    finally:
+        del os.environ["HSFFT_NO_RADER"]
+    assert "rader" in d1 and "bluestein" in d2, (d1, d2)
+    r = oracle.c2c(x, sgn)
+    assert per_transform_worst(y1, r) <= tol(n) and per_transform_worst(y2, r) <= tol(n)
+    assert per_transform_worst(y1, y2) <= 1e-14
+
+
 @pytest.mark.parametrize("n", [1024, 3000, 4096, 1009])
 def test_generic_engine_matches_compile_time_kernels(hs, product_lib, oracle, n):
     """Same sizes through the run-time planned engine (HSFFT_NO_CT=1 is read at plan build)."""
