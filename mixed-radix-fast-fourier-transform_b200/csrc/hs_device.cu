@@ -262,6 +262,9 @@ static void launch_tiled_tma(const void *in, void *out, const void *tw, const Hs
     ++g_launches;
 }
 
+#ifndef HS_TILED_MINB_SMALL
+#define HS_TILED_MINB_SMALL 2
+#endif
 template <class P, int SGN, int C, int TW, bool STCOL, int IO = 0, int CS = 1>
 static void launch_tiled(const void *in, void *out, const void *tw, const HsTileGeom &g, long long howmany, cudaStream_t st)
 {
@@ -271,7 +274,7 @@ static void launch_tiled(const void *in, void *out, const void *tw, const HsTile
         constexpr int CT = HsTileColsTma<P, C>::value;
         if (tma_enabled(P::N) && g.in_c == 1 && g.blk_log == 0 && g.ncols % CT == 0) { launch_tiled_tma<P, SGN, CT, TW, STCOL>(in, out, tw, g, howmany, st); return; }
     }
-    constexpr int MINB = (P::T * C <= 256 || (P::T * C <= 320 && P::N / P::T <= 10)) ? 2 : 1; // 320 threads of 8-10 points fit 100 registers
+    constexpr int MINB = (P::T * C <= 160) ? HS_TILED_MINB_SMALL : (P::T * C <= 256 || (P::T * C <= 320 && P::N / P::T <= 10)) ? 2 : 1; // 320 threads of 8-10 points fit 100 registers
     constexpr int smem = C * hs_col_stride(P::NPAD, C) * (int)sizeof(cplx);
     auto kern = hs_tiled_kernel<P, SGN, C, TW, STCOL, MINB, IO, CS>;
     static bool attr_done = false;
@@ -291,7 +294,7 @@ static void launch_blu_mid(const void *in, void *out, const void *twf, const voi
                            long long howmany, cudaStream_t st)
 {
     constexpr int C = HsTileCols<PF>::C;
-    constexpr int MINB = (PF::T * C <= 256) ? 2 : 1;
+    constexpr int MINB = (PF::T * C <= 160) ? HS_TILED_MINB_SMALL : (PF::T * C <= 256) ? 2 : 1;
     constexpr int smem = C * hs_col_stride(PF::NPAD, C) * (int)sizeof(cplx);
     auto kern = hs_blu_mid_kernel<PF, PI, CS, C, MINB>;
     static bool attr_done = false;

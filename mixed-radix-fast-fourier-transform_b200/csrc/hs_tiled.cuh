@@ -37,7 +37,14 @@ constexpr int hs_col_stride(int npad, int C)
 // 512-point sub-plans: 4 columns (two 256-thread CTAs per SM) for the one-CTA-per-tile kernel, 8 for the persistent TMA-staged
 // one (measured after the bank-conflict fix, fraction of the HBM peak at 2^18 / 2^19: plain kernel 29.9 / 32.8 % with 8
 // columns, 41.2 / 40.8 % with 4; TMA kernel 41.1 / 39.7 % with 8, 41.6 / 38.2 % with 4; c2r 2^20 28.7 -> 31.4 %)
-template <class P> struct HsTileCols { static constexpr int C = P::T >= 64 ? 4 : 16; };
+// columns per tile of the plain tiled kernels (CTA = T * C threads).  Measured on B200 (profiles/r1b_tile_width_ab.txt):
+// 8 instead of 16 columns for the 160- and 256-point plans (320 / 256 -> 160 / 128 threads, more CTAs per SM) takes
+// Bluestein N = 10007 from 6.21 to 5.57 ms and 2^16..2^17 up by 1-3 %; the 128-point plan (T = 8) loses 4 % with 64-thread
+// CTAs and keeps 16.
+#ifndef HS_TILE_C_SMALL
+#define HS_TILE_C_SMALL (P::T <= 8 ? 16 : 8)
+#endif
+template <class P> struct HsTileCols { static constexpr int C = P::T >= 64 ? 4 : HS_TILE_C_SMALL; };
 template <class P, int C> struct HsTileColsTma { static constexpr int value = (P::N == 512 && C == 4) ? 8 : C; };
 
 // LDP / STP: residency class of the loads / stores (hs_ld_mp / hs_st_mp in hs_common.cuh): 0 for the stand-alone
