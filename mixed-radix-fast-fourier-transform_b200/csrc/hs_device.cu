@@ -230,11 +230,14 @@ static void launch_rader(const void *in, void *out, const void *twf, const void 
 // 2^17 43.8 vs 38.8 %, 2^18 40.5 vs 29.6 %, 2^19 36.4 vs 32.3 %, 2^20 35.9 vs 35.6 % of the HBM peak, but
 // 2^14..2^16 (128/256-point sub-plans, already at the two-pass cap) 45-49 vs 52-54 %.  So it is the default for
 // sub-plans of 512 points and more; HSFFT_TMA=0 / 1 forces it off / on everywhere.
-static bool tma_enabled(int sub_len)
+// (later: the plain kernel at three CTAs per SM -- 80 registers, no spill -- beats the persistent one for the 512-point
+// sub-plan: 2^18 44.9 vs 41.1 %, 2^17 47.2 vs 46.5 %; the 1024-point one would spill there and keeps TMA for the first pass,
+// but its second pass (inter-pass twiddle) is faster plain: 2^19 40.3 vs 38.7 %.  profiles/r1b_tiled_occupancy_ab.txt)
+static bool tma_enabled(int sub_len, int tw)
 {
     static int v = -1;
     if (v < 0) { const char *e = getenv("HSFFT_TMA"); v = e ? atoi(e) : 2; }
-    return v == 1 || (v == 2 && sub_len >= 512);
+    return v == 1 || (v == 2 && sub_len >= 1024 && tw == 0);
 }
 
 template <class P, int SGN, int C, int TW, bool STCOL>
@@ -265,6 +268,9 @@ static void launch_tiled_tma(const void *in, void *out, const void *tw, const Hs
 #ifndef HS_TILED_MINB_SMALL
 #define HS_TILED_MINB_SMALL 2
 #endif
+#ifndef HS_TILED_MINB_MID
+#define HS_TILED_MINB_MID (P::N == 512 ? 3 : 2) /* 512-point tiles need 80 registers: three 256-thread CTAs per SM without a spill */
+#endif
 template <class P, int SGN, int C, int TW, bool STCOL, int IO = 0, int CS = 1>
 static void launch_tiled(const void *in, void *out, const void *tw, const HsTileGeom &g, long long howmany, cudaStream_t st)
 {
@@ -272,9 +278,9 @@ static void launch_tiled(const void *in, void *out, const void *tw, const HsTile
         // (half as many columns per tile and two CTAs per SM -- independent phase streams -- measured slower: 2^20 34.3 % vs
         // 39.3 %, 2^18 35.6 % vs 40.3 % of the HBM peak; 32-byte runs cost more than the overlap gains)
         constexpr int CT = HsTileColsTma<P, C>::value;
-        if (tma_enabled(P::N) && g.in_c == 1 && g.blk_log == 0 && g.ncols % CT == 0) { launch_tiled_tma<P, SGN, CT, TW, STCOL>(in, out, tw, g, howmany, st); return; }
+        if (tma_enabled(P::N, TW) && g.in_c == 1 && g.blk_log == 0 && g.ncols % CT == 0) { launch_tiled_tma<P, SGN, CT, TW, STCOL>(in, out, tw, g, howmany, st); return; }
     }
-    constexpr int MINB = (P::T * C <= 160) ? HS_TILED_MINB_SMALL : (P::T * C <= 256 || (P::T * C <= 320 && P::N / P::T <= 10)) ? 2 : 1; // 320 threads of 8-10 points fit 100 registers
+    constexpr int MINB = (P::T * C <= 160) ? HS_TILED_MINB_SMALL : (P::T * C <= 256 || (P::T * C <= 320 && P::N / P::T <= 10)) ? HS_TILED_MINB_MID : 1; // 320 threads of 8-10 points fit 100 registers
     constexpr int smem = C * hs_col_stride(P::NPAD, C) * (int)sizeof(cplx);
     auto kern = hs_tiled_kernel<P, SGN, C, TW, STCOL, MINB, IO, CS>;
     static bool attr_done = false;
