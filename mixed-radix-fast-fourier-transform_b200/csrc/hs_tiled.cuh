@@ -44,7 +44,11 @@ constexpr int hs_col_stride(int npad, int C)
 #ifndef HS_TILE_C_SMALL
 #define HS_TILE_C_SMALL (P::T <= 8 ? 16 : 8)
 #endif
-template <class P> struct HsTileCols { static constexpr int C = P::T >= 64 ? 4 : HS_TILE_C_SMALL; };
+// (2 columns for the 1024-point plan -- four 128-thread CTAs per SM -- measured slower: 2^20 31.3 vs 40.9 %; 32-byte rows)
+#ifndef HS_TILE_C_BIG
+#define HS_TILE_C_BIG 4
+#endif
+template <class P> struct HsTileCols { static constexpr int C = P::T >= 64 ? HS_TILE_C_BIG : HS_TILE_C_SMALL; };
 template <class P, int C> struct HsTileColsTma { static constexpr int value = (P::N == 512 && C == 4) ? 8 : C; };
 
 // LDP / STP: residency class of the loads / stores (hs_ld_mp / hs_st_mp in hs_common.cuh): 0 for the stand-alone
