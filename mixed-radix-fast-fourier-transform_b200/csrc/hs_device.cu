@@ -266,7 +266,10 @@ static void launch_tiled_tma(const void *in, void *out, const void *tw, const Hs
 }
 
 #ifndef HS_TILED_MINB_SMALL
-#define HS_TILED_MINB_SMALL 2
+#define HS_TILED_MINB_SMALL (P::N == 160 ? 5 : 2) /* the 160-point plan fits 72 registers: five 160-thread CTAs per SM (N = 10007: 5.70 -> 5.45 ms) */
+#endif
+#ifndef HS_BLUMID_MINB
+#define HS_BLUMID_MINB ((PF::N == 128 || PF::N == 512) ? 4 : (PF::T * C <= 256) ? 2 : 1) /* 128 / 512 points: no spill at 4 CTAs per SM, +2-3 %; 256 loses 3 %, 1024 spills */
 #endif
 #ifndef HS_TILED_MINB_MID
 #define HS_TILED_MINB_MID (P::N == 512 ? 3 : 2) /* 512-point tiles need 80 registers: three 256-thread CTAs per SM without a spill */
@@ -300,7 +303,7 @@ static void launch_blu_mid(const void *in, void *out, const void *twf, const voi
                            long long howmany, cudaStream_t st)
 {
     constexpr int C = HsTileCols<PF>::C;
-    constexpr int MINB = (PF::T * C <= 160) ? HS_TILED_MINB_SMALL : (PF::T * C <= 256) ? 2 : 1;
+    constexpr int MINB = HS_BLUMID_MINB;
     constexpr int smem = C * hs_col_stride(PF::NPAD, C) * (int)sizeof(cplx);
     auto kern = hs_blu_mid_kernel<PF, PI, CS, C, MINB>;
     static bool attr_done = false;
