@@ -107,9 +107,10 @@ struct HsLoadRader {
     const int *HS_RESTRICT perm;
     HS_DEVICE cplx operator()(int, int, int n) const { return hs_ld_gather(x + hs_ld_idx(perm + n)); }
 };
-// staged forms: the row is copied into the team's buffer with coalesced loads first and gathered from there (the index
-// loads then overlap the row's HBM latency instead of preceding it, and the LSU sees 16-byte shared accesses instead of
-// one 32-byte sector per lane); the outputs are scattered into the buffer and leave it with coalesced stores
+// staged forms: the outputs are scattered into the team's buffer and leave it with coalesced stores (measured faster on
+// B200: the default); the inputs can likewise be copied in with coalesced loads and gathered from shared memory, but the
+// barrier that needs before the first pass costs more than the uncoalesced gather (measured slower: kept for the
+// emulation tests and A/B builds, not instantiated by hs_device.cu)
 struct HsLoadRaderSm {
     static constexpr bool kPost = false, kFromSmem = true;
     const cplx *sm;
