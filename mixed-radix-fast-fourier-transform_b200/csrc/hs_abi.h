@@ -46,7 +46,7 @@ HS_RULE int hs_stage_tw_entries(int r, int m, int split_min)
 }
 
 /* compile-time kernel families */
-enum { HS_CT_C2C = 0, HS_CT_BLUESTEIN = 1, HS_CT_TWOPASS = 2, HS_CT_SUB = 3, HS_CT_RADER = 4 };
+enum { HS_CT_C2C = 0, HS_CT_BLUESTEIN = 1, HS_CT_TWOPASS = 2, HS_CT_SUB = 3, HS_CT_RADER = 4, HS_CT_BLUESTEIN_SPLIT = 5, HS_CT_CONV_SPLIT = 6 };
 
 /* one compile-time specialised shared-memory transform the CUDA side offers */
 typedef struct hs_ct_desc {
@@ -125,37 +125,6 @@ typedef struct hs_dist_store {
     int logKw, logN, logS, rank;
 } hs_dist_store;
 
-/* ---- persistent pipeline kernels (hs_pipe.cuh): a chain of up to HS_PIPE_MAX_PHASE tile phases whose
- * intermediates live in rings of workspace slots small enough to stay in L2 ---- */
-#define HS_PIPE_MAX_PHASE 3
-typedef struct hs_phase_args {
-    hs_tile_geom g;       /* in_xf / out_xf: per-transform stride of this phase's source / destination */
-    const void *tw;       /* stage twiddles of the phase's sub-plan */
-    const void *tw_b;     /* second sub-plan of a fused phase (Bluestein middle: inverse pass 1) */
-    const void *aux;      /* Bluestein middle: Hk */
-    int tiles;            /* tiles per transform */
-    int flags;            /* r2c split: 1 = write the mirrored upper half too */
-} hs_phase_args;
-typedef struct hs_pipe_args {
-    int nphase;
-    hs_phase_args ph[HS_PIPE_MAX_PHASE];
-    const void *in;       /* phase 0 reads transform x at in + x*ph[0].g.in_xf */
-    void *out;            /* the last phase writes transform x at out + x*ph[last].g.out_xf */
-    void *ring[HS_PIPE_MAX_PHASE - 1]; /* ring[j]: nslot*G transforms, written by phase j, read by phase j+1 */
-    long long howmany;
-    int G;                /* transforms per group (the unit of dependency tracking) */
-    int lag;              /* phase j+1 of group g is issued `lag` rounds after phase j of group g */
-    int nslot;            /* ring slots (groups); >= lag + 1 */
-    void *ctl;            /* zeroed by the launcher: u64 ticket, then u32 done[phase][group] from byte 128 */
-    /* derived by the launcher (hs_pipe_finalize) */
-    long long ngroups;
-    unsigned items[HS_PIPE_MAX_PHASE]; /* tickets per group of each phase = G * tiles */
-    unsigned round_items;              /* sum of items[] */
-    unsigned long long total;          /* tickets of the whole launch = (ngroups + (nphase-1)*lag) * round_items */
-} hs_pipe_args;
-/* bytes of control words hs_cu_launch_pipe needs behind hs_pipe_args.ctl */
-#define HS_PIPE_CTL_BYTES(ngroups) ((size_t)128 + (size_t)HS_PIPE_MAX_PHASE * (size_t)(ngroups) * 4)
-
 /* ---- device / memory / streams ---- */
 int   hs_cu_device_count(void);
 void  hs_cu_require_device(void);            /* exits with a message when no CUDA device is usable */
@@ -218,11 +187,16 @@ void  hs_cu_launch_ct_rader(int id, const void *d_in, void *d_out, const void *d
 void  hs_cu_launch_ct_bluestein(int id, int sgn, int N, const void *d_in, void *d_out, const void *d_tw_f, const void *d_tw_i,
                                 const void *d_chirp, const void *d_hk, long long howmany, void *stream);
 
-/* persistent pipeline of the two-pass size tp_id.  variant: 0 c2c, 1 c2r (merge on load), 2 r2c (split as third phase),
- * 3 long Bluestein (sgn = chirp direction).  The caller fills geometry, tables, in/out/ring/ctl, howmany, G, lag, nslot;
- * the callee fills ph[].tiles.  query != 0: only fill tiles and report availability.  Returns 0 when this
- * (size, variant, sgn) has no pipeline (the caller then runs the multi-launch path). */
-int   hs_cu_launch_pipe(int tp_id, int variant, int sgn, hs_pipe_args *a, void *stream, int query);
+/* split chirp-z (descriptor family HS_CT_BLUESTEIN_SPLIT, length M' >= N): two cyclic convolutions of length M' per transform in
+ * one kernel.  d_chirp3 = h | h*conj(w) | h*w (N entries each, w[n] = exp(-2 pi i n / 2M')), d_hk2 = Hk[even] | Hk[odd] of
+ * Hk = FFT_2M'(padded mirrored chirp / 2M') (M' entries each) */
+void  hs_cu_launch_ct_bluestein_split(int id, int sgn, int N, const void *d_in, void *d_out, const void *d_tw_f, const void *d_tw_i,
+                                      const void *d_chirp3, const void *d_hk2, long long howmany, void *stream);
+
+/* the same on the in-place transforms of hs_conv_fft.cuh (descriptor family HS_CT_CONV_SPLIT): d_tw = the DIF stage table
+ * of hs_build_conv_twiddles, d_hkt2 = Hk[even] | Hk[odd] each permuted by hs_conv_permute_hk */
+void  hs_cu_launch_ct_conv_split(int id, int sgn, int N, const void *d_in, void *d_out, const void *d_tw, const void *d_chirp3,
+                                 const void *d_hkt2, long long howmany, void *stream);
 
 /* ---- plan-time specialisation (hs_jit.cu): a compile-time kernel for any length whose stages fit one SM, compiled with
  * NVRTC when the plan is created.  radix_exec: stage radices in execution order (2,3,4,5,7,8,16 only).  create returns a

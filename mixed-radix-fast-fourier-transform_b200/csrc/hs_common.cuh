@@ -41,6 +41,9 @@ static inline double hs_ld_stream_d(const double *p) { return *p; }
 static inline int hs_ld_idx(const int *p) { return *p; }
 static inline double2 hs_ld_gather(const double2 *p) { return *p; }
 static inline void hs_st_stream_d(double *p, double v) { *p = v; }
+// coherent (non read-only path) global load: data this same thread stored earlier in the launch
+static inline double2 hs_ld_coherent(const double2 *p) { return *p; }
+static inline void hs_st_keep(double2 *p, double2 v) { *p = v; }
 template <int MP> static inline double2 hs_ld_mp(const double2 *p) { return *p; }
 template <int MP> static inline void hs_st_mp(double2 *p, double2 v) { *p = v; }
 // grid-level dataflow (persistent pipeline kernels): tickets and completion counters
@@ -132,6 +135,19 @@ HS_DEVICE double2 hs_ld_tab(const double2 *p)
     double2 v;
     asm volatile("ld.global.nc.L1::evict_last.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
     return v;
+}
+// A value this same thread stored earlier in the launch and reads back (the first half-convolution of the split
+// Bluestein kernel parks its result in the output row): the load must not take the read-only (.nc) path, the store
+// asks the L2 to keep the line until it is read back.
+HS_DEVICE double2 hs_ld_coherent(const double2 *p)
+{
+    double2 v;
+    asm volatile("ld.global.cg.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
+    return v;
+}
+HS_DEVICE void hs_st_keep(double2 *p, double2 v)
+{
+    asm volatile("st.global.cg.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
 }
 HS_DEVICE double hs_ld_stream_d(const double *p) { return __ldcs(p); }
 // index tables (re-read by every CTA) and samples gathered through them (the other half of each 32-byte sector is

@@ -12,6 +12,11 @@
 
 #include "hs_plans.cuh"
 
+#ifndef HS_PART
+#define HS_PART(n) 1
+#endif
+
+#if HS_PART(1)
 template <class P>
 static void fill_desc(hs_ct_desc &d, int id, int family)
 {
@@ -68,6 +73,15 @@ static void ct_init()
     fill_desc<PB256>(g_ct[CT_R256], CT_R256, HS_CT_RADER);
     fill_desc<PB2048x2f>(g_ct[CT_B2048X2], CT_B2048X2, HS_CT_BLUESTEIN);
     fill_desc<PB256x16>(g_ct[CT_B256X16], CT_B256X16, HS_CT_BLUESTEIN);
+    fill_desc<PB4096>(g_ct[CT_H4096], CT_H4096, HS_CT_BLUESTEIN_SPLIT);
+    fill_desc<PB8192f>(g_ct[CT_H8192], CT_H8192, HS_CT_BLUESTEIN_SPLIT);
+    fill_desc<PB10240f>(g_ct[CT_H10240], CT_H10240, HS_CT_BLUESTEIN_SPLIT);
+    fill_desc<PC4096>(g_ct[CT_C4096], CT_C4096, HS_CT_CONV_SPLIT);
+    fill_desc<PC8192>(g_ct[CT_C8192], CT_C8192, HS_CT_CONV_SPLIT);
+    fill_desc<PC10240>(g_ct[CT_C10240], CT_C10240, HS_CT_CONV_SPLIT);
+    fill_desc<PC10240s>(g_ct[CT_C10240S], CT_C10240S, HS_CT_CONV_SPLIT);
+    fill_desc<PC10240l>(g_ct[CT_C10240L], CT_C10240L, HS_CT_CONV_SPLIT);
+    fill_desc<PC10240h>(g_ct[CT_C10240H], CT_C10240H, HS_CT_CONV_SPLIT);
     fill_desc<P4096x>(g_ct[CT_4096X], CT_4096X, HS_CT_C2C);
     fill_desc<P3000x>(g_ct[CT_3000X], CT_3000X, HS_CT_C2C);
     fill_desc<P4096y>(g_ct[CT_4096Y], CT_4096Y, HS_CT_C2C);
@@ -195,6 +209,48 @@ extern "C" void hs_cu_launch_ct_bluestein(int id, int sgn, int N, const void *d_
 }
 
 
+#define HS_BLUSPLIT_CASE(ID, PF, PI, MINB)                                                                                 \
+    case ID:                                                                                                              \
+        if (sgn == 1) launch_blu_split<PF, PI, 1, MINB>(N, d_in, d_out, d_tw_f, d_tw_i, d_chirp3, d_hk2, howmany, st);    \
+        else launch_blu_split<PF, PI, -1, MINB>(N, d_in, d_out, d_tw_f, d_tw_i, d_chirp3, d_hk2, howmany, st);            \
+        break;
+
+extern "C" void hs_cu_launch_ct_bluestein_split(int id, int sgn, int N, const void *d_in, void *d_out, const void *d_tw_f, const void *d_tw_i,
+                                                const void *d_chirp3, const void *d_hk2, long long howmany, void *stream)
+{
+    hs_stream_t st = (hs_stream_t)stream;
+    switch (id) {
+    HS_BLUSPLIT_CASE(CT_H4096, PB4096, PB4096, 2)
+    HS_BLUSPLIT_CASE(CT_H8192, PB8192f, PB8192i, 1)
+    HS_BLUSPLIT_CASE(CT_H10240, PB10240f, PB10240i, 1)
+    default: fprintf(stderr, "Error: unknown split Bluestein kernel id %d\n", id); exit(EXIT_FAILURE);
+    }
+}
+
+#define HS_CONVSPLIT_CASE(ID, P, MINB)                                                                      \
+    case ID:                                                                                               \
+        if (sgn == 1) launch_conv_split<P, 1, MINB>(N, d_in, d_out, d_tw, d_chirp3, d_hkt2, howmany, st);  \
+        else launch_conv_split<P, -1, MINB>(N, d_in, d_out, d_tw, d_chirp3, d_hkt2, howmany, st);          \
+        break;
+
+extern "C" void hs_cu_launch_ct_conv_split(int id, int sgn, int N, const void *d_in, void *d_out, const void *d_tw, const void *d_chirp3,
+                                           const void *d_hkt2, long long howmany, void *stream)
+{
+    hs_stream_t st = (hs_stream_t)stream;
+    switch (id) {
+    HS_CONVSPLIT_CASE(CT_C4096, PC4096, 3)
+    HS_CONVSPLIT_CASE(CT_C8192, PC8192, 1)
+    HS_CONVSPLIT_CASE(CT_C10240, PC10240, 1)
+    HS_CONVSPLIT_CASE(CT_C10240S, PC10240s, 1)
+    HS_CONVSPLIT_CASE(CT_C10240L, PC10240l, 1)
+    HS_CONVSPLIT_CASE(CT_C10240H, PC10240h, 1)
+    default: fprintf(stderr, "Error: unknown split Bluestein kernel id %d\n", id); exit(EXIT_FAILURE);
+    }
+}
+
+#endif // HS_PART(1)
+
+#if HS_PART(2)
 // ---- two-pass transforms: C columns per CTA, chosen so that a CTA has 128..512 threads
 
 template <class P1, class P2>
@@ -263,6 +319,9 @@ extern "C" void hs_cu_launch_tiled(int sub_id, int sgn, int tw_mode, int stcol, 
     }
 }
 
+#endif // HS_PART(2)
+
+#if HS_PART(3)
 // ---- long Bluestein (padded length 2^14..2^20): fused ends and the middle kernel
 template <class P>
 static void launch_sub_io(int sgn, int tw_mode, int stcol, int io_mode, int cs, const void *in, void *out, const void *tw,
@@ -317,3 +376,4 @@ extern "C" void hs_cu_launch_blu_mid(int sub_id, int chirp_sgn, const void *d_in
     default: fprintf(stderr, "Error: unknown sub-plan id %d\n", sub_id); exit(EXIT_FAILURE);
     }
 }
+#endif // HS_PART(3)

@@ -7,15 +7,30 @@
 
 #include "hs_abi.h"
 #include "hs_cuda_util.h"
+#include "hs_conv_fft.cuh"
 #include "hs_fused.cuh"
-#include "hs_generic.cuh"
 #include "hs_smem_fft.cuh"
 #include "hs_tiled.cuh"
 
-static std::atomic<long long> g_launches{0};
+// The launchers are compiled as three translation units (build.py: -DHS_TU_PART=1,2,3) so that nvcc works on them in
+// parallel: 1 = this file's plain functions plus the one-kernel families, 2 = the tiled passes, 3 = the tiled passes
+// with fused ends and the long-Bluestein middle kernel.  HS_TU_PART undefined = everything in one unit.
+#ifndef HS_TU_PART
+#define HS_TU_PART 0
+#endif
+#define HS_PART(n) (HS_TU_PART == 0 || HS_TU_PART == (n))
+#if HS_PART(1)
+#include "hs_generic.cuh" // plain (non-template) kernels: defined in one unit only
+#endif
+#if HS_PART(1)
+std::atomic<long long> g_launches{0};
+#else
+extern std::atomic<long long> g_launches;
+#endif
 
 typedef cudaStream_t hs_stream_t;
 
+#if HS_PART(1)
 // ----------------------------------------------------------------------------- device management
 static int g_dev_count = -2;
 
@@ -121,8 +136,33 @@ extern "C" void *hs_cu_ipc_open(const void *handle64)
 extern "C" void hs_cu_ipc_close(void *mapped) { if (mapped) HS_CUDA_CHECK(cudaIpcCloseMemHandle(mapped)); }
 extern "C" long long hs_cu_launch_count(void) { return g_launches.load(); }
 extern "C" void hs_cu_count_launch(void) { ++g_launches; }
+#else
+extern "C" int hs_cu_sm_count(void);
+#endif
 
 // --------------------------------------------------------------------------------------- launchers
+// Function attributes (dynamic shared memory limit, carve-out) belong to a (function, device) pair, so "done" is one bit
+// per device ordinal: a process that drives several GPUs sets them once on each.
+static int cur_device()
+{
+    int dev = 0;
+    HS_CUDA_CHECK(cudaGetDevice(&dev));
+    return dev;
+}
+static bool attr_todo(const std::atomic<unsigned long long> &mask) { return !((mask.load(std::memory_order_acquire) >> (cur_device() & 63)) & 1ULL); }
+static void attr_mark(std::atomic<unsigned long long> &mask) { mask.fetch_or(1ULL << (cur_device() & 63), std::memory_order_release); }
+static void set_carveout(const void *kern, int smem_per_cta, int ctas_per_sm);
+// the usual pair for a kernel with `smem` bytes of dynamic shared memory meant to run `ctas_per_sm` CTAs per SM
+#define hs_func_attr_once(kern, smem, ctas_per_sm)                                                                          \
+    do {                                                                                                                    \
+        static std::atomic<unsigned long long> attr_done_{0};                                                               \
+        if (attr_todo(attr_done_)) {                                                                                        \
+            HS_CUDA_CHECK(cudaFuncSetAttribute((kern), cudaFuncAttributeMaxDynamicSharedMemorySize, (smem)));               \
+            set_carveout((kern), (smem), (ctas_per_sm));                                                                    \
+            attr_mark(attr_done_);                                                                                          \
+        }                                                                                                                   \
+    } while (0)
+
 static void check_grid(long long blocks)
 {
     if (blocks <= 0 || blocks > 2147483647LL) {
@@ -158,11 +198,11 @@ template <class P, int SGN, int MINB, int PFW = 0> // PFW: L2 prefetch distance 
 static void launch_c2c(const void *in, void *out, const void *tw, long long howmany, cudaStream_t st)
 {
     auto kern = hs_c2c_smem_kernel<P, SGN, MINB>;
-    static bool attr_done = false; // per instantiation
-    if (!attr_done) {
+    static std::atomic<unsigned long long> attr_done{0}; // one bit per device: function attributes are per device
+    if (attr_todo(attr_done)) {
         HS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P::smem_bytes));
         set_carveout((const void *)kern, P::smem_bytes, MINB);
-        attr_done = true;
+        attr_mark(attr_done);
     }
     const long long blocks = (howmany + P::X - 1) / P::X;
     check_grid(blocks);
@@ -176,16 +216,42 @@ static void launch_blu(int N, const void *in, void *out, const void *twf, const 
                        long long howmany, cudaStream_t st)
 {
     auto kern = hs_bluestein_kernel<PF, PI, SGN, MINB>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static std::atomic<unsigned long long> attr_done{0}; // one bit per device: function attributes are per device
+    if (attr_todo(attr_done)) {
         HS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PF::smem_bytes));
         set_carveout((const void *)kern, PF::smem_bytes, MINB);
-        attr_done = true;
+        attr_mark(attr_done);
     }
     const long long blocks = (howmany + PF::X - 1) / PF::X;
     check_grid(blocks);
     kern<<<(unsigned)blocks, PF::threads, PF::smem_bytes, st>>>((const cplx *)in, (cplx *)out, (const cplx *)twf, (const cplx *)twi,
                                                                  (const cplx *)chirp, (const cplx *)hk, N, howmany, prefetch_dist(MINB));
+    HS_CUDA_CHECK(cudaGetLastError());
+    ++g_launches;
+}
+
+template <class PF, class PI, int SGN, int MINB>
+static void launch_blu_split(int N, const void *in, void *out, const void *twf, const void *twi, const void *chirp3, const void *hk2,
+                             long long howmany, cudaStream_t st)
+{
+    auto kern = hs_bluestein_split_kernel<PF, PI, SGN, MINB>;
+    hs_func_attr_once((const void *)kern, PF::smem_bytes, MINB);
+    check_grid(howmany);
+    kern<<<(unsigned)howmany, PF::threads, PF::smem_bytes, st>>>((const cplx *)in, (cplx *)out, (const cplx *)twf, (const cplx *)twi,
+                                                                  (const cplx *)chirp3, (const cplx *)hk2, N, howmany, prefetch_dist(MINB));
+    HS_CUDA_CHECK(cudaGetLastError());
+    ++g_launches;
+}
+
+template <class P, int SGN, int MINB>
+static void launch_conv_split(int N, const void *in, void *out, const void *tw, const void *chirp3, const void *hkt2, long long howmany,
+                              cudaStream_t st)
+{
+    auto kern = hs_conv_bluestein_split_kernel<P, SGN, MINB>;
+    hs_func_attr_once((const void *)kern, P::smem_bytes, MINB);
+    check_grid(howmany);
+    kern<<<(unsigned)howmany, P::threads, P::smem_bytes, st>>>((const cplx *)in, (cplx *)out, (const cplx *)tw, (const cplx *)chirp3,
+                                                                (const cplx *)hkt2, N, howmany, prefetch_dist(MINB));
     HS_CUDA_CHECK(cudaGetLastError());
     ++g_launches;
 }
@@ -199,11 +265,11 @@ static void launch_rader_v(const void *in, void *out, const void *twf, const voi
 {
     constexpr int smem = HsRaderSmem<PF, PI>::bytes;
     auto kern = hs_rader_kernel<PF, PI, MINB, STG>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static std::atomic<unsigned long long> attr_done{0}; // one bit per device: function attributes are per device
+    if (attr_todo(attr_done)) {
         HS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         set_carveout((const void *)kern, smem, MINB);
-        attr_done = true;
+        attr_mark(attr_done);
     }
     const long long blocks = (howmany + PF::X - 1) / PF::X;
     check_grid(blocks);
@@ -246,14 +312,14 @@ static void launch_tiled_tma(const void *in, void *out, const void *tw, const Hs
     constexpr int smem = HsTmaTileSmem<P, C>::bytes;
     static_assert(smem <= 227 * 1024, "staging buffers do not fit");
     auto kern = hs_tiled_tma_kernel<P, SGN, C, TW, STCOL>;
-    static bool attr_done = false;
+    static std::atomic<unsigned long long> attr_done{0}; // one bit per device: function attributes are per device
     static int per_sm = 1;
-    if (!attr_done) {
+    if (attr_todo(attr_done)) {
         HS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         HS_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, P::T * C, smem));
         if (per_sm < 1) per_sm = 1;
         if (getenv("HSFFT_VERBOSE")) fprintf(stderr, "hsfft: TMA tiled pass n=%d C=%d: %d CTAs/SM, %d bytes smem\n", P::N, C, per_sm, smem);
-        attr_done = true;
+        attr_mark(attr_done);
     }
     const long long total = howmany * (g.ncols / C);
     long long blocks = (long long)hs_cu_sm_count() * per_sm;
@@ -286,10 +352,10 @@ static void launch_tiled(const void *in, void *out, const void *tw, const HsTile
     constexpr int MINB = (P::T * C <= 160) ? HS_TILED_MINB_SMALL : (P::T * C <= 256 || (P::T * C <= 320 && P::N / P::T <= 10)) ? HS_TILED_MINB_MID : 1; // 320 threads of 8-10 points fit 100 registers
     constexpr int smem = C * hs_col_stride(P::NPAD, C) * (int)sizeof(cplx);
     auto kern = hs_tiled_kernel<P, SGN, C, TW, STCOL, MINB, IO, CS>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static std::atomic<unsigned long long> attr_done{0}; // one bit per device: function attributes are per device
+    if (attr_todo(attr_done)) {
         HS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_done = true;
+        attr_mark(attr_done);
     }
     const long long blocks = howmany * (g.ncols / C);
     check_grid(blocks);
@@ -306,10 +372,10 @@ static void launch_blu_mid(const void *in, void *out, const void *twf, const voi
     constexpr int MINB = HS_BLUMID_MINB;
     constexpr int smem = C * hs_col_stride(PF::NPAD, C) * (int)sizeof(cplx);
     auto kern = hs_blu_mid_kernel<PF, PI, CS, C, MINB>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static std::atomic<unsigned long long> attr_done{0}; // one bit per device: function attributes are per device
+    if (attr_todo(attr_done)) {
         HS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_done = true;
+        attr_mark(attr_done);
     }
     if (g.ncols % C != 0) { fprintf(stderr, "Error: tiled pass needs a multiple of %d columns\n", C); exit(EXIT_FAILURE); }
     const long long blocks = howmany * (g.ncols / C);
@@ -322,6 +388,7 @@ static void launch_blu_mid(const void *in, void *out, const void *twf, const voi
 
 #include "hs_ct_table.cuh"
 
+#if HS_PART(1)
 extern "C" void hs_cu_launch_generic(int sgn, const void *d_in, void *d_out, const hs_gen_params *p, void *stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
@@ -329,11 +396,11 @@ extern "C" void hs_cu_launch_generic(int sgn, const void *d_in, void *d_out, con
     const long long blocks = ntile * p->n_o * p->n_batch;
     check_grid(blocks);
     const size_t smem = (size_t)2 * p->C * p->npad * sizeof(cplx);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static std::atomic<unsigned long long> attr_done{0}; // one bit per device: function attributes are per device
+    if (attr_todo(attr_done)) {
         HS_CUDA_CHECK(cudaFuncSetAttribute(hs_generic_pass_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         HS_CUDA_CHECK(cudaFuncSetAttribute(hs_generic_pass_kernel<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_done = true;
+        attr_mark(attr_done);
     }
     if (smem > 227 * 1024) { fprintf(stderr, "Error: pass needs %zu bytes of shared memory\n", smem); exit(EXIT_FAILURE); }
     if (sgn == 1) hs_generic_pass_kernel<1><<<(unsigned)blocks, 256, smem, st>>>((const cplx *)d_in, (cplx *)d_out, *p);
@@ -430,27 +497,4 @@ extern "C" void hs_cu_launch_dist_twiddle(void *b, const void *hi, const void *l
     HS_CUDA_CHECK(cudaGetLastError());
     ++g_launches;
 }
-
-// ---- persistent pipelines (hs_pipe.cuh): one translation unit per two-pass size, see hs_pipe_inst.cu
-extern "C" {
-int hs_cu_pipe_14(int, int, hs_pipe_args *, void *, int);
-int hs_cu_pipe_15(int, int, hs_pipe_args *, void *, int);
-int hs_cu_pipe_16(int, int, hs_pipe_args *, void *, int);
-int hs_cu_pipe_17(int, int, hs_pipe_args *, void *, int);
-int hs_cu_pipe_18(int, int, hs_pipe_args *, void *, int);
-int hs_cu_pipe_19(int, int, hs_pipe_args *, void *, int);
-int hs_cu_pipe_20(int, int, hs_pipe_args *, void *, int);
-}
-extern "C" int hs_cu_launch_pipe(int tp_id, int variant, int sgn, hs_pipe_args *a, void *stream, int query)
-{
-    switch (tp_id) {
-    case CT_T14: return hs_cu_pipe_14(variant, sgn, a, stream, query);
-    case CT_T15: return hs_cu_pipe_15(variant, sgn, a, stream, query);
-    case CT_T16: return hs_cu_pipe_16(variant, sgn, a, stream, query);
-    case CT_T17: return hs_cu_pipe_17(variant, sgn, a, stream, query);
-    case CT_T18: return hs_cu_pipe_18(variant, sgn, a, stream, query);
-    case CT_T19: return hs_cu_pipe_19(variant, sgn, a, stream, query);
-    case CT_T20: return hs_cu_pipe_20(variant, sgn, a, stream, query);
-    }
-    return 0;
-}
+#endif // HS_PART(1)

@@ -29,7 +29,6 @@ typedef struct hs_c2c {
     int jit_id;         /* >= 0: a kernel compiled for this length when the plan was created (hs_jit.cu) */
     int tp_id;          /* >= 0: compile-time two-pass transform (n = n1 * n2) */
     int n1, n2;
-    int pipe;           /* the two passes run as one persistent pipeline kernel (hs_pipe.cuh) */
     void *d_tw2, *d_twb, *d_tws; /* pass-2 stage twiddles and the inter-pass tables W_n^{k b}, W_n^{k NB} */
     int npass;          /* otherwise: run-time planned passes */
     hs_gen_params pass[HS_MAX_PASS];
@@ -47,10 +46,13 @@ typedef struct hs_dev_obj {
     void *d_chirp, *d_hk;
     int blu_ct_id;
     int rader_ct_id; /* >= 0: prime N run as a cyclic convolution of length N-1 (d_chirp = int perm[N-1], d_hk = Bk) */
+    int split_conv;  /* the split kernel runs on the in-place transforms of hs_conv_fft.cuh (d_blu_twf = their stage table) */
+    int split_ct_id; /* >= 0: split chirp-z, two convolutions of length M/2 >= N in one kernel (d_chirp = h | h conj(w) | h w,
+                      * d_hk = Hk[even] | Hk[odd]) */
     void *d_blu_twf, *d_blu_twi;
     /* long Bluestein (M = n1*n2 two-pass): three fused kernels, see hs_tiled.cuh */
     int big, big_n1, big_n2, big_sub1, big_sub2;
-    int big_tp_id, big_pipe; /* the three kernels as one persistent pipeline */
+    int big_tp_id;
     void *d_big_f1, *d_big_f2, *d_big_i1, *d_big_i2, *d_big_fb, *d_big_fs, *d_big_ib, *d_big_is;
     long long big_chunk;
     /* pipeline slots for host-pointer calls */
@@ -71,18 +73,6 @@ hs_c2c *hs_c2c_create(int n, int sgn);
 void    hs_c2c_destroy(hs_c2c *p);
 size_t  hs_c2c_ws_elems(const hs_c2c *p, long long howmany); /* workspace (complex elements) exec needs */
 void    hs_c2c_exec(const hs_c2c *p, const void *d_in, void *d_out, void *d_ws, long long howmany, void *stream);
-
-/* persistent pipelines (hs_pipe.cuh).  Ring sizing: slots of about HSFFT_PIPE_SLOT_KB (default 16 MiB) hold G
- * transforms of `len` points each; nrings rings of nslot slots plus the control words live in the workspace. */
-void    hs_pipe_shape(long long len, long long howmany, int *G, int *lag, int *nslot);
-size_t  hs_pipe_ws_bytes(long long len, int nrings, long long howmany);
-/* real transforms riding on a pipelined half-length plan; return 0 when this plan has no such pipeline.
- * r2c: rows of 2H reals -> bins 0..H (and the mirrored half when full); c2r: bins 0..H -> rows of 2H reals */
-int     hs_dev_exec_r2c_pipe(hs_dev_obj *d, const void *d_in, void *d_out, long long out_stride, int full, const void *d_tw2, void *d_ws,
-                             long long howmany, void *stream);
-int     hs_dev_exec_c2r_pipe(hs_dev_obj *d, const void *d_spec, long long in_stride, const void *d_tw2, void *d_out, void *d_ws,
-                             long long howmany, void *stream);
-int     hs_dev_has_pipe(const hs_dev_obj *d, int variant);
 
 /* c2r with the merge pass fused into the first pass of the half-length transform; returns 0 when this plan
  * has no such fusion (the caller then runs the separate merge kernel) */

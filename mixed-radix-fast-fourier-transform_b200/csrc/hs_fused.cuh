@@ -90,6 +90,84 @@ hs_bluestein_kernel(const cplx *HS_RESTRICT in, cplx *HS_RESTRICT out, const cpl
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Split chirp-z: lengths whose padded convolution (M >= 2N-1 points) does not fit one SM, but whose N points do.
+// With M = 2 M' and M' >= N the zero-padded input occupies only the first half of the M-point buffer, and only the
+// first N <= M' outputs are wanted, so one radix-2 step of the M-point convolution is trivial on both ends
+// (reference bluestein_fft, src/highSpeedFFT.c:1735-1907, computes the same y = IFFT_M(FFT_M(a) * Hk)):
+//     A[2k']   = FFT_M'(a)[k']                 A[2k'+1] = FFT_M'(a * w)[k'],      w[n] = exp(-2 pi i n / M)
+//     y[n]     = IFFT_M'(A_even * Hk_even)[n] + conj(w[n]) * IFFT_M'(A_odd * Hk_odd)[n],     n < M'
+// i.e. two cyclic convolutions of length M', each of which one CTA holds in shared memory (M' = 10240: 174 KB).
+// One kernel, one CTA per transform, does both halves back to back:
+//     half 0: load x * conj(h) -> FFT_M' -> * Hk_even (registers) -> IFFT_M' -> park y0 in the output row
+//     half 1: load x * conj(h w~) -> FFT_M' -> * Hk_odd -> IFFT_M' -> out = y0 * conj(h) + y1 * conj(h w)
+// HBM sees x once and the result once (the second read of x and the parked y0 are served by the L2: the same
+// thread that parked y0[n] reads it back).  The w factors are folded into two more chirp tables,
+// gA = h * conj(w) and gB = h * w, so each half costs exactly what the one-kernel chirp-z costs per point.
+// For the inverse plan direction the chirp roles flip as in the reference (:1811-1815, :1846-1854, :1879-1885).
+template <int SGN>
+struct HsStoreParkCrop { // half 0: keep y0[n], n < N, where half 1 finds it again
+    cplx *HS_RESTRICT out;
+    int N;
+    HS_DEVICE void operator()(int, int, int k, cplx v) const
+    {
+        if (k < N) hs_st_keep(out + k, v);
+    }
+};
+template <int SGN>
+struct HsStoreCombineChirpCrop { // half 1: out[n] = y0[n] * c0[n] + y1[n] * c1[n]  (conjugated tables for SGN = +1)
+    cplx *HS_RESTRICT out;
+    const cplx *HS_RESTRICT c0, *HS_RESTRICT c1;
+    int N;
+    HS_DEVICE void operator()(int, int, int k, cplx v) const
+    {
+        if (k < N) {
+            const cplx y0 = hs_ld_coherent(out + k), h0 = hs_ld_tab(c0 + k), h1 = hs_ld_tab(c1 + k);
+            const cplx a = (SGN == 1) ? hs_mulc(y0, h0) : hs_mul(y0, h0), b = (SGN == 1) ? hs_mulc(v, h1) : hs_mul(v, h1);
+            hs_st_stream(out + k, hs_add(a, b));
+        }
+    }
+};
+
+// chirp3: the three tables h | gA | gB, N entries each; hk2: Hk_even | Hk_odd, PF::N entries each
+template <class PF, class PI, int SGN, int MINB>
+HS_GLOBAL void HS_LAUNCH_BOUNDS(PF::threads, MINB)
+hs_bluestein_split_kernel(const cplx *HS_RESTRICT in, cplx *HS_RESTRICT out, const cplx *HS_RESTRICT twf, const cplx *HS_RESTRICT twi,
+                          const cplx *HS_RESTRICT chirp3, const cplx *HS_RESTRICT hk2, int N, long long howmany, int pf_dist)
+{
+    static_assert(PF::N == PI::N && PF::T == PI::T && PF::X == 1 && PI::X == 1 && PF::NPAD == PI::NPAD, "plans must pair");
+    constexpr int RL = PF::radix(PF::NST - 1);
+    static_assert(PI::radix(0) == RL, "register hand-over needs matching radices");
+    constexpr int NB = PF::N / RL, B = (NB + PF::T - 1) / PF::T;
+    HS_DYN_SMEM(cplx, sm);
+    const int t = HS_TID;
+    const long long xf = HS_BID;
+    cplx y[B][RL];
+    if (pf_dist > 0 && t == 0 && xf + pf_dist < howmany) hs_prefetch_l2(in + (xf + pf_dist) * N, (unsigned)(N * 16));
+    const cplx *x = in + xf * N;
+    cplx *o = out + xf * N;
+    const cplx *h = chirp3, *gA = chirp3 + N, *gB = chirp3 + 2 * (long long)N;
+    {
+        HsLoadChirp<SGN> ld{x, h, N};
+        HsStoreRegsMul<SGN, RL> st{y, hk2};
+        hs_fft_team<PF, 1>(ld, st, sm, twf, t, true);
+        HS_SYNC();
+        HsLoadRegs<RL> ld2{y};
+        HsStoreParkCrop<SGN> st2{o, N};
+        hs_fft_team<PI, -1>(ld2, st2, sm, twi, t, true);
+    }
+    HS_SYNC(); // the inverse transform's last reads of sm precede the next forward transform's first writes
+    {
+        HsLoadChirp<SGN> ld{x, SGN == 1 ? gA : gB, N};
+        HsStoreRegsMul<SGN, RL> st{y, hk2 + PF::N};
+        hs_fft_team<PF, 1>(ld, st, sm, twf, t, true);
+        HS_SYNC();
+        HsLoadRegs<RL> ld2{y};
+        HsStoreCombineChirpCrop<SGN> st2{o, h, SGN == 1 ? gB : gA, N};
+        hs_fft_team<PI, -1>(ld2, st2, sm, twi, t, true);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Rader's algorithm for a prime length N whose N-1 has a shared-memory plan (N = 1009: N-1 = 1008 = 16*9*7).  The
 // reference sends every prime to Bluestein with a power-of-two pad M >= 2N-1 (two 2048-point transforms for N = 1009);
 // for such a prime the DFT is also a CYCLIC convolution of length L = N-1 exactly, with no padding:

@@ -3,6 +3,7 @@
 // (persistent pipelines).
 #pragma once
 #include "hs_smem_fft.cuh"
+#include "hs_conv_fft.cuh"
 
 // ------------------------------------------------------------------------ compile-time plan table
 // Stage radices in execution order (the reference's factor list reversed; runs of power-of-two
@@ -41,6 +42,27 @@ using PB1024 = HsPlan<1024, 64, 1, 3, HS_B2048_SPLIT, 0, 8, 16, 8>;
 using PB4096 = HsPlan<4096, 256, 1, 4, HS_B2048_SPLIT, 0, 16, 16, 16>;
 using PB8192f = HsPlan<8192, 512, 1, 3, HS_B2048_SPLIT, 0, 8, 16, 8, 8>; // one CTA per SM (147 KB); N = 2049..4096
 using PB8192i = HsPlan<8192, 512, 1, 3, HS_B2048_SPLIT, 0, 8, 8, 16, 8>;
+// split chirp-z (hs_bluestein_split_kernel): two cyclic convolutions of length M' >= N per transform, M' = the plan length.
+// 10240 = 16*8*5*16 with 640 threads: every radix-16 stage has exactly one butterfly per thread, the radix-8 stage two,
+// the radix-5 stage 3.2 (four rounds); both orders are conflict free with one pad slot per 16 points (bank_check.py).
+// Exact radix-5 constants: the reference runs this convolution with power-of-two stages only.
+using PB10240f = HsExact<HsPlan<10240, 640, 1, 4, HS_B2048_SPLIT, 0, 16, 8, 5, 16>>;
+using PB10240i = HsExact<HsPlan<10240, 640, 1, 4, HS_B2048_SPLIT, 0, 16, 5, 8, 16>>;
+// the same split chirp-z on the in-place transforms of hs_conv_fft.cuh (digit-reversed spectrum, one butterfly at a time
+// per thread): 16 points in registers instead of the 16-20 of a whole pass, so 640 threads fit 96 registers without a spill
+// (the auto-sort pair above: 2 KB of spill stores per thread).  All conflict free with one pad slot per 16 points
+// (tests/emu/bank_check.py inplace ...).
+// Twiddle mode -3 (row 1 and successive powers, two live twiddles): 96 registers, 160 B of spill stores per thread; the
+// product tree (-2) spills 380 B, loading rows 1,2,4,8 (-1) 400 B (ptxas -v).
+#ifndef HS_CONV_TWM
+#define HS_CONV_TWM -3
+#endif
+using PC10240  = HsConvPlan<10240, 640, 4, HS_CONV_TWM, 16, 8, 5, 16>;
+using PC10240s = HsConvPlan<10240, 640, 4, -2, 16, 8, 5, 16>;   // A/B: product tree
+using PC10240l = HsConvPlan<10240, 640, 4, -1, 16, 8, 5, 16>;   // A/B: rows 1,2,4,8 loaded
+using PC10240h = HsConvPlan<10240, 320, 4, -2, 16, 8, 5, 16>;   // A/B: 320 threads, twice the butterflies each, no spill at 168 registers
+using PC8192   = HsConvPlan<8192, 512, 4, HS_CONV_TWM, 16, 8, 4, 16>;
+using PC4096   = HsConvPlan<4096, 256, 4, HS_CONV_TWM, 16, 16, 16>;
 // sub-plans of the two-pass transforms (N = n1 * n2 > 8192); X is unused there
 #ifndef HS_SUB_SPLIT
 #define HS_SUB_SPLIT -2
@@ -90,4 +112,6 @@ enum { CT_4096A = 0, CT_4096B, CT_3000, CT_1024, CT_2048, CT_512, CT_256, CT_819
        CT_S128, CT_S256, CT_S512, CT_S1024,
        CT_TX20480, CT_TX40960, CT_TX81920, CT_TX163840, CT_S160X,
        CT_B256, CT_B512, CT_B1024, CT_B4096, CT_B8192,
-       CT_R1008, CT_R1008A, CT_R1008G, CT_R256, CT_B2048X2, CT_B256X16, CT_COUNT };
+       CT_R1008, CT_R1008A, CT_R1008G, CT_R256, CT_B2048X2, CT_B256X16,
+       CT_H4096, CT_H8192, CT_H10240,
+       CT_C4096, CT_C8192, CT_C10240, CT_C10240S, CT_C10240L, CT_C10240H, CT_COUNT };

@@ -156,6 +156,35 @@ HS_DEVICE void hs_twiddles(const cplx *HS_RESTRICT tw, const int k, cplx *wv)
     }
 }
 
+// SPLIT = -3: one table load (row 1) per butterfly, the powers w^2, w^3, ... formed one after the other and applied at
+// once, so that only two twiddles are ever live (a radix-16 stage otherwise holds up to 7 of them next to its 16 points:
+// with 640 threads per CTA -- 96 registers -- that spills).  R = 16 applies w^i to points i and 8+i and w^8 to 8..15:
+// 29 complex products like the tree of SPLIT = -2, but a chain 8 deep; rounding grows with the chain, so this mode is
+// for the convolutions inside Bluestein / Rader only (never for a transform whose result the reference defines bit-wise).
+template <class P, int S>
+HS_DEVICE void hs_twiddle_apply_seq(const cplx *HS_RESTRICT tw, const int k, cplx *v)
+{
+    constexpr int R = P::radix(S);
+    const cplx w1 = hs_ld_tab(tw + P::tw_off(S) + k);
+    cplx w = w1;
+    if (R == 16) {
+        HS_UNROLL
+        for (int i = 1; i < 8; ++i) {
+            v[i] = hs_mul(v[i], w);
+            v[8 + i] = hs_mul(v[8 + i], w);
+            w = hs_mul(w, w1);
+        }
+        HS_UNROLL
+        for (int i = 8; i < 16; ++i) v[i] = hs_mul(v[i], w);
+    } else {
+        HS_UNROLL
+        for (int i = 1; i < R; ++i) {
+            v[i] = hs_mul(v[i], w);
+            if (i + 1 < R) w = hs_mul(w, w1);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------- one stage
 // LD(u, i, n)       -> cplx   : element n of the input signal   (first pass only)
 // ST(u, j, k, v)              : element k of the output spectrum (last pass only)
@@ -179,7 +208,7 @@ HS_DEVICE void hs_stage(LD &ld, ST &st, const HsLane &ln, const cplx *HS_RESTRIC
     HS_UNROLL
     for (int u = 0; u < B; ++u) {
         const int b = t + P::T * u;
-        if (active && (NB % P::T == 0 || b < NB)) {
+        if (active && (NB % P::T == 0 || u < NB / P::T || b < NB)) {
             const int q = b % QP, k = b / QP;
             HS_UNROLL
             for (int i = 0; i < R; ++i) {
@@ -193,8 +222,10 @@ HS_DEVICE void hs_stage(LD &ld, ST &st, const HsLane &ln, const cplx *HS_RESTRIC
     HS_UNROLL
     for (int u = 0; u < B; ++u) {
         const int b = t + P::T * u;
-        if (active && (NB % P::T == 0 || b < NB)) {
-            if (!FIRST) {
+        if (active && (NB % P::T == 0 || u < NB / P::T || b < NB)) {
+            if (!FIRST && P::SPLIT == -3) {
+                hs_twiddle_apply_seq<P, S>(tw, b / QP, v[u]);
+            } else if (!FIRST) {
                 cplx wv[R];
                 hs_twiddles<P, S>(tw, b / QP, wv);
                 HS_UNROLL
@@ -209,7 +240,7 @@ HS_DEVICE void hs_stage(LD &ld, ST &st, const HsLane &ln, const cplx *HS_RESTRIC
     HS_UNROLL
     for (int u = 0; u < B; ++u) {
         const int b = t + P::T * u;
-        if (active && (NB % P::T == 0 || b < NB)) {
+        if (active && (NB % P::T == 0 || u < NB / P::T || b < NB)) {
             HS_UNROLL
             for (int j = 0; j < R; ++j) {
                 if (LAST) st(u, j, b + NB * j, v[u][j]);
@@ -246,7 +277,7 @@ HS_DEVICE void hs_stage2(LD &ld, ST &st, const HsLane &ln, const cplx *HS_RESTRI
     HS_UNROLL
     for (int u = 0; u < B; ++u) {
         const int b = t + P::T * u;
-        if (active && (NB % P::T == 0 || b < NB)) {
+        if (active && (NB % P::T == 0 || u < NB / P::T || b < NB)) {
             const int q = b % QB, k0 = b / QB;
             HS_UNROLL
             for (int ia = 0; ia < RA; ++ia) {
@@ -263,7 +294,7 @@ HS_DEVICE void hs_stage2(LD &ld, ST &st, const HsLane &ln, const cplx *HS_RESTRI
     HS_UNROLL
     for (int u = 0; u < B; ++u) {
         const int b = t + P::T * u;
-        if (active && (NB % P::T == 0 || b < NB)) {
+        if (active && (NB % P::T == 0 || u < NB / P::T || b < NB)) {
             const int k0 = b / QB;
             if (!FIRST) {
                 cplx wa[RA];
@@ -297,7 +328,7 @@ HS_DEVICE void hs_stage2(LD &ld, ST &st, const HsLane &ln, const cplx *HS_RESTRI
     HS_UNROLL
     for (int u = 0; u < B; ++u) {
         const int b = t + P::T * u;
-        if (active && (NB % P::T == 0 || b < NB)) {
+        if (active && (NB % P::T == 0 || u < NB / P::T || b < NB)) {
             HS_UNROLL
             for (int jb = 0; jb < RB; ++jb) {
                 HS_UNROLL

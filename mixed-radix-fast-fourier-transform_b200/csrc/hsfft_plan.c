@@ -185,12 +185,79 @@ int hs_bluestein_exec_pad(int N)
 }
 
 static const hs_ct_desc *find_ct_ex(int family, int n, int allow_exact);
+static void *upload(const void *h, size_t bytes);
 
 /* The pad length the device runs with.  Any M >= 2N-1 gives the same convolution (SURVEY.md section 8c "may
  * differ"); between two powers of two the engine also offers 5/8 of the upper one where a compile-time plan with
  * full-precision radix-5 stages exists (N = 10007: 20480 instead of 32768).  HSFFT_BLU_POW2=1 keeps the power of two. */
+/* Split chirp-z (hs_fused.cuh, hs_bluestein_split_kernel): the smallest compile-time plan of length M' >= N that one SM
+ * holds; the convolution then runs at M = 2 M'.  Used above the lengths the plain one-kernel chirp-z covers (N > 4096:
+ * M >= 16384 does not fit one SM); HSFFT_BLU_SPLIT=0 turns it off, =2 prefers it wherever a plan exists. */
+static const hs_ct_desc *bluestein_split_plan(int N)
+{
+    const int mode = getenv("HSFFT_BLU_SPLIT") ? atoi(getenv("HSFFT_BLU_SPLIT")) : 1;
+    if (mode == 0 || (mode == 1 && N <= 4096)) return NULL;
+    /* two kernel families offer such plans: the in-place transforms of hs_conv_fft.cuh (default) and the auto-sort ones of
+     * hs_fused.cuh (HSFFT_SPLIT_AUTOSORT=1); among equals the first listed wins (HSFFT_PREFER_CT lists its choice first) */
+    const int want = getenv("HSFFT_SPLIT_AUTOSORT") ? HS_CT_BLUESTEIN_SPLIT : HS_CT_CONV_SPLIT;
+    const hs_ct_desc *best = NULL;
+    const int cnt = hs_cu_ct_count();
+    for (int pass = 0; pass < 2 && !best; ++pass)
+        for (int i = 0; i < cnt; ++i) {
+            const hs_ct_desc *d = hs_cu_ct_get(i);
+            const int fam_ok = pass == 0 ? (d->family == want) : (d->family == HS_CT_BLUESTEIN_SPLIT || d->family == HS_CT_CONV_SPLIT);
+            if (fam_ok && d->n >= N && (!best || d->n < best->n)) best = d;
+        }
+    return best;
+}
+
+/* tables of the in-place convolution transforms (hs_conv_fft.cuh): forward stage s < nst-1 works on blocks of length L,
+ * m = L / r, and multiplies output j of the butterfly at in-block position p by W_L^(p j); layout [j-1][p] per stage */
+static int conv_twiddle_count(const int *rx, int nst, int n)
+{
+    int L = n, cnt = 0;
+    for (int s = 0; s + 1 < nst; ++s) { cnt += (rx[s] - 1) * (L / rx[s]); L /= rx[s]; }
+    return cnt;
+}
+static void *upload_conv_twiddles(const int *rx, int nst, int n)
+{
+    const int cnt = conv_twiddle_count(rx, nst, n);
+    fft_data *t = (fft_data *)malloc(sizeof(fft_data) * (cnt > 0 ? cnt : 1));
+    if (!t) { fprintf(stderr, "Error: Memory allocation failed for twiddle table\n"); exit(EXIT_FAILURE); }
+    int L = n, off = 0;
+    for (int s = 0; s + 1 < nst; ++s) {
+        const int r = rx[s], m = L / r;
+        const fft_type theta = -PI2 / (fft_type)L;
+        for (int j = 1; j < r; ++j)
+            for (int p = 0; p < m; ++p) put_twiddle(&t[off + (j - 1) * m + p], p * j, theta, 1);
+        off += (r - 1) * m;
+        L = m;
+    }
+    void *d = upload(t, sizeof(fft_data) * cnt);
+    hs_cu_stream_sync(NULL);
+    free(t);
+    return d;
+}
+/* spectrum table in the order the forward stages leave the spectrum in: position pos = sum_s j_s m_s holds bin
+ * j_0 + r_0 (j_1 + r_1 (...)); stored as [i][beta] for pos = r_last beta + i (coalesced across the threads) */
+static void conv_permute_hk(fft_data *dst, const fft_data *hk, const int *rx, int nst, int n)
+{
+    const int rl = rx[nst - 1], nb = n / rl;
+    for (int pos = 0; pos < n; ++pos) {
+        int m = n, k = 0, w = 1;
+        for (int s = 0; s < nst; ++s) {
+            m /= rx[s];
+            k += ((pos / m) % rx[s]) * w;
+            w *= rx[s];
+        }
+        dst[(size_t)(pos % rl) * nb + pos / rl] = hk[k];
+    }
+}
+
 static int bluestein_device_pad(int N)
 {
+    const hs_ct_desc *sp = bluestein_split_plan(N);
+    if (sp) return 2 * sp->n;
     const int m = hs_bluestein_exec_pad(N);
     const int alt = m / 8 * 5;
     if (m >= 8 && alt >= 2 * N - 1 && !getenv("HSFFT_BLU_POW2") && find_ct_ex(HS_CT_TWOPASS, alt, 1) &&
@@ -235,81 +302,10 @@ static void *upload_stage_twiddles(const int *rx, int nst, int sgn, int split_mi
     return d;
 }
 
-/* ------------------------------------------------------------------------- persistent pipelines */
-
-enum { HS_PIPE_V_C2C = 0, HS_PIPE_V_C2R = 1, HS_PIPE_V_R2C = 2, HS_PIPE_V_BLU = 3 };
-
-static int pipe_enabled(void)
-{
-    /* opt-in (HSFFT_PIPE=1): on B200 the tiled passes are bound by the SMs' FP64 pipe and latency, not by HBM, so
-     * taking the intermediate's HBM round trip away does not pay yet (DESIGN.md, round-1 measurements) */
-    const char *e = getenv("HSFFT_PIPE");
-    return e && atoi(e) != 0;
-}
-
-static int pipe_available(int tp_id, int variant, int sgn)
-{
-    hs_pipe_args a;
-    memset(&a, 0, sizeof a);
-    a.nphase = (variant == HS_PIPE_V_C2C || variant == HS_PIPE_V_C2R) ? 2 : 3;
-    for (int j = 0; j < HS_PIPE_MAX_PHASE; ++j) a.ph[j].g.ncols = 1 << 20;
-    return hs_cu_launch_pipe(tp_id, variant, sgn, &a, NULL, 1);
-}
-
 static int env_int(const char *name, int dflt)
 {
     const char *e = getenv(name);
     return e ? atoi(e) : dflt;
-}
-
-void hs_pipe_shape(long long len, long long howmany, int *G, int *lag, int *nslot)
-{
-    /* A slot holds the tiles that are in flight between two phases (resident CTAs x 64 KiB tiles, about 16 MiB);
-     * lag 1 and three slots keep every dependency one full round (two slots' worth of tickets) behind the
-     * tile that needs it, so the acquire polls of hs_pipe_kernel find their counters already full. */
-    const long long slot_bytes = (long long)env_int("HSFFT_PIPE_SLOT_KB", 16384) << 10;
-    long long g = slot_bytes / (len * (long long)sizeof(fft_data));
-    if (g < 1) g = 1;
-    if (g > howmany) g = howmany;
-    *G = (int)g;
-    *lag = env_int("HSFFT_PIPE_LAG", 1);
-    if (*lag < 1) *lag = 1;
-    *nslot = env_int("HSFFT_PIPE_NSLOT", *lag + 2);
-    if (*nslot < *lag + 1) *nslot = *lag + 1;
-}
-
-static size_t pipe_ctl_bytes(long long howmany, int G)
-{
-    const long long ngroups = (howmany + G - 1) / G;
-    return (HS_PIPE_CTL_BYTES(ngroups) + 255) & ~(size_t)255;
-}
-
-size_t hs_pipe_ws_bytes(long long len, int nrings, long long howmany)
-{
-    int G, lag, nslot;
-    hs_pipe_shape(len, howmany, &G, &lag, &nslot);
-    return pipe_ctl_bytes(howmany, G) + (size_t)nrings * nslot * G * len * sizeof(fft_data);
-}
-
-/* ctl words and rings carved out of the workspace */
-static void pipe_layout(hs_pipe_args *a, void *ws, long long len, int nrings, long long howmany)
-{
-    hs_pipe_shape(len, howmany, &a->G, &a->lag, &a->nslot);
-    a->howmany = howmany;
-    a->ctl = ws;
-    char *ring = (char *)ws + pipe_ctl_bytes(howmany, a->G);
-    for (int r = 0; r < nrings; ++r) a->ring[r] = ring + (size_t)r * a->nslot * a->G * len * sizeof(fft_data);
-}
-
-/* the two passes of a compile-time two-pass plan as phases 0 and 1 */
-static void pipe_twopass_phases(const hs_c2c *p, hs_pipe_args *a)
-{
-    hs_tile_geom *g0 = &a->ph[0].g, *g1 = &a->ph[1].g;
-    g0->ncols = p->n2; g0->in_c = 1; g0->in_e = p->n2; g0->out_c = p->n1; g0->out_e = 1; g0->in_xf = p->n; g0->out_xf = p->n;
-    a->ph[0].tw = p->d_tw;
-    g1->ncols = p->n1; g1->in_c = 1; g1->in_e = p->n1; g1->out_c = 1; g1->out_e = p->n1; g1->in_xf = p->n; g1->out_xf = p->n;
-    g1->twb = p->d_twb; g1->tws = p->d_tws; g1->tw_ld = p->n1;
-    a->ph[1].tw = p->d_tw2;
 }
 
 static hs_c2c *c2c_create(int n, int sgn, int allow_exact);
@@ -337,7 +333,6 @@ static hs_c2c *c2c_create(int n, int sgn, int allow_exact)
         p->tp_id = ct->id;
         p->n1 = ct->n1;
         p->n2 = ct->n2;
-        p->pipe = pipe_enabled() && pipe_available(ct->id, HS_PIPE_V_C2C, sgn);
         p->d_tw = upload_stage_twiddles(ct->radix, ct->nst, sgn, ct->split_min);
         p->d_tw2 = upload_stage_twiddles(ct->radix2, ct->nst2, sgn, ct->split_min2);
         const int NB = ct->n2 / ct->radix2[0], K = ct->n1;
@@ -501,7 +496,6 @@ void hs_c2c_destroy(hs_c2c *p)
 
 size_t hs_c2c_ws_elems(const hs_c2c *p, long long howmany)
 {
-    if (p->tp_id >= 0 && p->pipe) return (hs_pipe_ws_bytes(p->n, 2, howmany) + sizeof(fft_data) - 1) / sizeof(fft_data);
     if (p->tp_id >= 0) return (size_t)howmany * p->n;
     return (p->ct_id < 0 && p->npass > 1) ? (size_t)howmany * p->n : 0;
 }
@@ -511,16 +505,6 @@ void hs_c2c_exec(const hs_c2c *p, const void *d_in, void *d_out, void *d_ws, lon
     if (howmany <= 0) return;
     if (p->ct_id >= 0) { hs_cu_launch_ct_c2c(p->ct_id, p->sgn, d_in, d_out, p->d_tw, howmany, stream); return; }
     if (p->jit_id >= 0) { hs_cu_jit_c2c_launch(p->jit_id, d_in, d_out, p->d_tw, howmany, stream); return; }
-    if (p->tp_id >= 0 && p->pipe) {
-        hs_pipe_args a;
-        memset(&a, 0, sizeof a);
-        a.nphase = 2;
-        pipe_twopass_phases(p, &a);
-        pipe_layout(&a, d_ws, p->n, 1, howmany);
-        a.in = d_in; a.out = d_out;
-        hs_cu_launch_pipe(p->tp_id, HS_PIPE_V_C2C, p->sgn, &a, stream, 0);
-        return;
-    }
     if (p->tp_id >= 0) {
         hs_cu_launch_ct_twopass(p->tp_id, 1, p->sgn, d_in, d_ws, p->d_tw, NULL, NULL, howmany, stream);
         hs_cu_launch_ct_twopass(p->tp_id, 2, p->sgn, d_ws, d_out, p->d_tw2, p->d_twb, p->d_tws, howmany, stream);
@@ -638,6 +622,7 @@ static void dev_build(hs_dev_obj *d, fft_object plan)
     d->lt = plan->lt;
     d->blu_ct_id = -1;
     d->rader_ct_id = -1;
+    d->split_ct_id = -1;
     if (d->N < 2 || (d->sgn != 1 && d->sgn != -1)) {
         fprintf(stderr, "Error: Invalid FFT object (N = %d, sgn = %d)\n", d->N, d->sgn);
         exit(EXIT_FAILURE);
@@ -666,6 +651,43 @@ static void dev_build(hs_dev_obj *d, fft_object plan)
     hs_cu_stream_sync(NULL);
     hs_cu_free(ws);
     hs_cu_free(d_hp);
+    const hs_ct_desc *sp = bluestein_split_plan(N);
+    if (sp && 2 * sp->n == M) {
+        /* tables of the split kernel: h | gA = h conj(w) | gB = h w with w[n] = exp(-2 pi i n / M), and Hk de-interleaved */
+        const int Mh = sp->n;
+        fft_data *c3 = (fft_data *)malloc(sizeof(fft_data) * 3 * (size_t)N), *hk = (fft_data *)malloc(sizeof(fft_data) * (size_t)M);
+        if (!c3 || !hk) { fprintf(stderr, "Error: Memory allocation failed for Bluestein's FFT arrays\n"); exit(EXIT_FAILURE); }
+        hs_cu_d2h(hk, d->d_hk, sizeof(fft_data) * (size_t)M, NULL);
+        hs_cu_stream_sync(NULL);
+        for (int k = 0; k < Mh; ++k) { hp[k] = hk[2 * k]; hp[Mh + k] = hk[2 * k + 1]; }
+        if (sp->family == HS_CT_CONV_SPLIT) { /* both halves in the digit-reversed order of the in-place transforms */
+            memcpy(hk, hp, sizeof(fft_data) * (size_t)M);
+            conv_permute_hk(hp, hk, sp->radix, sp->nst, Mh);
+            conv_permute_hk(hp + Mh, hk + Mh, sp->radix, sp->nst, Mh);
+        }
+        hs_cu_h2d(d->d_hk, hp, sizeof(fft_data) * (size_t)M, NULL);
+        for (int n = 0; n < N; ++n) {
+            const fft_type a = -PI2 * (fft_type)n / (fft_type)M, wr = cos(a), wi = sin(a);
+            c3[n] = h[n];
+            c3[N + n].re = h[n].re * wr + h[n].im * wi;     c3[N + n].im = h[n].im * wr - h[n].re * wi;     /* h * conj(w) */
+            c3[2 * N + n].re = h[n].re * wr - h[n].im * wi; c3[2 * N + n].im = h[n].im * wr + h[n].re * wi; /* h * w */
+        }
+        hs_cu_free(d->d_chirp);
+        d->d_chirp = upload(c3, sizeof(fft_data) * 3 * (size_t)N);
+        int inv[8];
+        for (int s = 0; s < sp->nst; ++s) inv[s] = sp->radix[sp->nst - 1 - s];
+        d->split_ct_id = sp->id;
+        d->split_conv = sp->family == HS_CT_CONV_SPLIT;
+        if (d->split_conv) d->d_blu_twf = upload_conv_twiddles(sp->radix, sp->nst, Mh);
+        else {
+            d->d_blu_twf = upload_stage_twiddles(sp->radix, sp->nst, 1, sp->split_min);
+            d->d_blu_twi = upload_stage_twiddles(inv, sp->nst, -1, sp->split_min);
+        }
+        hs_cu_stream_sync(NULL);
+        free(c3); free(hk); free(h); free(hp);
+        hs_c2c_destroy(f);
+        return;
+    }
     free(h);
     free(hp);
 
@@ -679,7 +701,6 @@ static void dev_build(hs_dev_obj *d, fft_object plan)
         for (int s = 0; s < s2->nst; ++s) inv2[s] = s2->radix[s2->nst - 1 - s];
         d->big = 1; d->big_n1 = n1; d->big_n2 = n2; d->big_sub1 = s1->id; d->big_sub2 = s2->id;
         d->big_tp_id = tp->id;
-        d->big_pipe = pipe_enabled() && pipe_available(tp->id, HS_PIPE_V_BLU, d->sgn);
         d->d_big_f1 = upload_stage_twiddles(s1->radix, s1->nst, 1, s1->split_min);
         d->d_big_f2 = upload_stage_twiddles(s2->radix, s2->nst, 1, s2->split_min);
         d->d_big_i1 = upload_stage_twiddles(inv2, s2->nst, -1, s2->split_min);
@@ -782,8 +803,7 @@ void hs_dev_reserve(hs_dev_obj *d, int slot, size_t in_bytes, size_t out_bytes, 
 size_t hs_dev_ws_bytes(const hs_dev_obj *d, long long howmany)
 {
     if (d->lt == 0) return hs_c2c_ws_elems(d->direct, howmany) * sizeof(fft_data);
-    if (d->blu_ct_id >= 0 || d->rader_ct_id >= 0) return 0;
-    if (d->big && d->big_pipe) return hs_pipe_ws_bytes(d->M, 2, howmany);
+    if (d->blu_ct_id >= 0 || d->rader_ct_id >= 0 || d->split_ct_id >= 0) return 0;
     if (d->big) return (size_t)2 * (howmany < d->big_chunk ? howmany : d->big_chunk) * d->M * sizeof(fft_data);
     return ((size_t)2 * howmany * d->M + hs_c2c_ws_elems(d->fwdM, howmany)) * sizeof(fft_data);
 }
@@ -794,6 +814,15 @@ void hs_dev_exec(hs_dev_obj *d, const void *d_in, void *d_out, void *d_ws, long 
     if (d->lt == 0) { hs_c2c_exec(d->direct, d_in, d_out, d_ws, howmany, stream); return; }
     if (d->rader_ct_id >= 0) {
         hs_cu_launch_ct_rader(d->rader_ct_id, d_in, d_out, d->d_blu_twf, d->d_blu_twi, d->d_chirp, d->d_hk, howmany, stream);
+        return;
+    }
+    if (d->split_ct_id >= 0 && d->split_conv) {
+        hs_cu_launch_ct_conv_split(d->split_ct_id, d->sgn, d->N, d_in, d_out, d->d_blu_twf, d->d_chirp, d->d_hk, howmany, stream);
+        return;
+    }
+    if (d->split_ct_id >= 0) {
+        hs_cu_launch_ct_bluestein_split(d->split_ct_id, d->sgn, d->N, d_in, d_out, d->d_blu_twf, d->d_blu_twi, d->d_chirp, d->d_hk, howmany,
+                                        stream);
         return;
     }
     if (d->blu_ct_id >= 0) {
@@ -813,18 +842,6 @@ void hs_dev_exec(hs_dev_obj *d, const void *d_in, void *d_out, void *d_ws, long 
         gb.twb = d->d_big_fb; gb.tws = d->d_big_fs; gb.tw_ld = (int)n1;
         gc.ncols = (int)n2; gc.in_xf = M; gc.in_c = 1; gc.in_e = n2; gc.out_xf = N; gc.out_c = 1; gc.out_e = n2;
         gc.twb = d->d_big_ib; gc.tws = d->d_big_is; gc.tw_ld = (int)n2; gc.chirp = d->d_chirp; gc.nlog = (int)N;
-        if (d->big_pipe) { /* one persistent kernel, both M-point intermediates stay in L2 */
-            hs_pipe_args a;
-            memset(&a, 0, sizeof a);
-            a.nphase = 3;
-            a.ph[0].g = ga; a.ph[0].tw = d->d_big_f1;
-            a.ph[1].g = gb; a.ph[1].tw = d->d_big_f2; a.ph[1].tw_b = d->d_big_i1; a.ph[1].aux = d->d_hk;
-            a.ph[2].g = gc; a.ph[2].tw = d->d_big_i2;
-            pipe_layout(&a, d_ws, M, 2, howmany);
-            a.in = d_in; a.out = d_out;
-            hs_cu_launch_pipe(d->big_tp_id, HS_PIPE_V_BLU, d->sgn, &a, stream, 0);
-            return;
-        }
         for (long long first = 0; first < howmany; first += chunk) {
             const long long cnt = (first + chunk <= howmany) ? chunk : howmany - first;
             const fft_data *x = (const fft_data *)d_in + first * N;
@@ -842,43 +859,6 @@ void hs_dev_exec(hs_dev_obj *d, const void *d_in, void *d_out, void *d_ws, long 
     hs_cu_launch_spectrum_mul(d->sgn, b, d->d_hk, d->M, howmany, stream);
     hs_c2c_exec(d->invM, b, a, c, howmany, stream);
     hs_cu_launch_chirp_crop(d->sgn, a, d_out, d->d_chirp, d->N, d->M, howmany, stream);
-}
-
-int hs_dev_has_pipe(const hs_dev_obj *d, int variant)
-{
-    if (d->lt != 0 || !d->direct || d->direct->tp_id < 0 || !d->direct->pipe) return 0;
-    return pipe_available(d->direct->tp_id, variant, d->direct->sgn);
-}
-
-int hs_dev_exec_r2c_pipe(hs_dev_obj *d, const void *d_in, void *d_out, long long out_stride, int full, const void *d_tw2, void *d_ws,
-                         long long howmany, void *stream)
-{
-    if (!hs_dev_has_pipe(d, HS_PIPE_V_R2C)) return 0;
-    const hs_c2c *p = d->direct;
-    hs_pipe_args a;
-    memset(&a, 0, sizeof a);
-    a.nphase = 3;
-    pipe_twopass_phases(p, &a);
-    a.ph[2].g.ncols = 1; a.ph[2].g.in_xf = p->n; a.ph[2].g.out_xf = out_stride; a.ph[2].g.chirp = d_tw2; a.ph[2].g.nlog = p->n;
-    a.ph[2].flags = full ? 1 : 0;
-    pipe_layout(&a, d_ws, p->n, 2, howmany);
-    a.in = d_in; a.out = d_out;
-    return hs_cu_launch_pipe(p->tp_id, HS_PIPE_V_R2C, p->sgn, &a, stream, 0);
-}
-
-int hs_dev_exec_c2r_pipe(hs_dev_obj *d, const void *d_spec, long long in_stride, const void *d_tw2, void *d_out, void *d_ws,
-                         long long howmany, void *stream)
-{
-    if (!hs_dev_has_pipe(d, HS_PIPE_V_C2R)) return 0;
-    const hs_c2c *p = d->direct;
-    hs_pipe_args a;
-    memset(&a, 0, sizeof a);
-    a.nphase = 2;
-    pipe_twopass_phases(p, &a);
-    a.ph[0].g.in_xf = in_stride; a.ph[0].g.chirp = d_tw2; a.ph[0].g.nlog = p->n;
-    pipe_layout(&a, d_ws, p->n, 1, howmany);
-    a.in = d_spec; a.out = d_out;
-    return hs_cu_launch_pipe(p->tp_id, HS_PIPE_V_C2R, p->sgn, &a, stream, 0);
 }
 
 int hs_dev_exec_c2r_fused(hs_dev_obj *d, const void *d_spec, long long in_stride, const void *d_tw2, void *d_out, void *d_ws,
@@ -1076,19 +1056,20 @@ const char *hsfft_plan_describe(fft_object obj)
         if (p->ct_id >= 0) n = snprintf(buf, sizeof buf, "mixed-radix N=%d: compile-time smem kernel #%d", d->N, p->ct_id);
         else if (p->jit_id >= 0) n = snprintf(buf, sizeof buf, "mixed-radix N=%d: smem kernel compiled for this plan (NVRTC) #%d", d->N, p->jit_id);
         else if (p->tp_id >= 0)
-            n = snprintf(buf, sizeof buf, "mixed-radix N=%d: compile-time two-pass kernels #%d%s", d->N, p->tp_id,
-                         p->pipe ? " as one persistent L2-resident pipeline" : "");
+            n = snprintf(buf, sizeof buf, "mixed-radix N=%d: compile-time two-pass kernels #%d", d->N, p->tp_id);
         else {
             n = snprintf(buf, sizeof buf, "mixed-radix N=%d: %d run-time pass(es):", d->N, p->npass);
             for (int g = 0; g < p->npass && n < (int)sizeof buf - 32; ++g)
                 n += snprintf(buf + n, sizeof buf - n, " [n=%d C=%d]", p->pass[g].n, p->pass[g].C);
         }
     } else if (d->big)
-        n = snprintf(buf, sizeof buf, "bluestein N=%d M=%d=%dx%d: 3 fused tiled kernels%s", d->N, d->M, d->big_n1, d->big_n2,
-                     d->big_pipe ? " as one persistent L2-resident pipeline" : "");
+        n = snprintf(buf, sizeof buf, "bluestein N=%d M=%d=%dx%d: 3 fused tiled kernels", d->N, d->M, d->big_n1, d->big_n2);
     else if (d->rader_ct_id >= 0)
         n = snprintf(buf, sizeof buf, "rader N=%d (prime), cyclic convolution of length %d: fused compile-time kernel #%d", d->N, d->M,
                      d->rader_ct_id);
+    else if (d->split_ct_id >= 0)
+        n = snprintf(buf, sizeof buf, "bluestein N=%d M=%d: one kernel, two convolutions of length %d (split chirp-z, %s transforms) #%d", d->N, d->M,
+                     d->M / 2, d->split_conv ? "in-place" : "auto-sort", d->split_ct_id);
     else if (d->blu_ct_id >= 0)
         n = snprintf(buf, sizeof buf, "bluestein N=%d M=%d: fused compile-time kernel #%d", d->N, d->M, d->blu_ct_id);
     else

@@ -132,8 +132,6 @@ static void r2c_dev(fft_real_object obj, hs_real_dev *r, const fft_type *d_in, f
                     void *d_ws, long howmany, void *stream)
 {
     hs_dev_obj *c = hs_dev_get(obj->cobj);
-    /* long transforms: both passes and the split as one persistent kernel, intermediates held in L2 (d_z unused) */
-    if (hs_dev_exec_r2c_pipe(c, d_in, d_out, out_stride, full, r->d_tw2, d_ws, howmany, stream)) return;
     hs_dev_exec(c, d_in, d_z, d_ws, howmany, stream); /* rows of N reals == rows of H complex */
     hs_cu_launch_r2c_post(d_z, d_out, r->d_tw2, r->H, out_stride, full, howmany, stream);
 }
@@ -142,9 +140,7 @@ static void c2r_dev(fft_real_object obj, hs_real_dev *r, const fft_data *d_in, l
                     long howmany, void *stream)
 {
     hs_dev_obj *c = hs_dev_get(obj->cobj);
-    /* long transforms: the merge rides on pass 1's loads; as one persistent kernel where the plan has a pipeline
-     * (d_z unused), else as two launches (d_z then serves as the pass workspace) */
-    if (hs_dev_exec_c2r_pipe(c, d_in, in_stride, r->d_tw2, d_out, d_ws, howmany, stream)) return;
+    /* long transforms: the merge rides on pass 1's loads (d_z then serves as the pass workspace) */
     if (hs_dev_exec_c2r_fused(c, d_in, in_stride, r->d_tw2, d_out, d_z, howmany, stream)) return;
     hs_cu_launch_c2r_pre(d_in, d_z, r->d_tw2, r->H, in_stride, howmany, stream);
     hs_dev_exec(c, d_z, d_out, d_ws, howmany, stream);
@@ -161,7 +157,7 @@ void fft_r2c_exec_batch_dev(fft_real_object obj, const fft_type *d_in, fft_data 
         exit(EXIT_FAILURE);
     }
     hs_dev_obj *c = hs_dev_get(obj->cobj);
-    if (!hs_dev_has_pipe(c, 2)) grow(&r->d_z[0], &r->cap_z[0], sizeof(fft_data) * (size_t)howmany * r->H);
+    grow(&r->d_z[0], &r->cap_z[0], sizeof(fft_data) * (size_t)howmany * r->H);
     grow(&r->d_ws[0], &r->cap_ws[0], hs_dev_ws_bytes(c, howmany));
     r2c_dev(obj, r, d_in, d_out, out_stride, full, r->d_z[0], r->d_ws[0], howmany, stream);
 }
@@ -176,7 +172,7 @@ void fft_c2r_exec_batch_dev(fft_real_object obj, const fft_data *d_in, long in_s
         exit(EXIT_FAILURE);
     }
     hs_dev_obj *c = hs_dev_get(obj->cobj);
-    if (!hs_dev_has_pipe(c, 1)) grow(&r->d_z[0], &r->cap_z[0], sizeof(fft_data) * (size_t)howmany * r->H);
+    grow(&r->d_z[0], &r->cap_z[0], sizeof(fft_data) * (size_t)howmany * r->H);
     grow(&r->d_ws[0], &r->cap_ws[0], hs_dev_ws_bytes(c, howmany));
     c2r_dev(obj, r, d_in, in_stride, d_out, r->d_z[0], r->d_ws[0], howmany, stream);
 }
@@ -228,7 +224,7 @@ void fft_r2c_exec_batch(fft_real_object obj, fft_type *inp, fft_data *oup, long 
         if (i < HS_NSLOT) {
             grow(&r->d_in[s], &r->cap_in[s], in_row * chunk);
             grow(&r->d_out[s], &r->cap_out[s], out_row * chunk);
-            if (!hs_dev_has_pipe(c, 2)) grow(&r->d_z[s], &r->cap_z[s], sizeof(fft_data) * (size_t)chunk * r->H);
+            grow(&r->d_z[s], &r->cap_z[s], sizeof(fft_data) * (size_t)chunk * r->H);
             grow(&r->d_ws[s], &r->cap_ws[s], hs_dev_ws_bytes(c, chunk));
         }
         hs_cu_h2d(r->d_in[s], inp + first * N, in_row * cnt, r->stream[s]);
@@ -252,7 +248,7 @@ void fft_c2r_exec_batch(fft_real_object obj, fft_data *inp, fft_type *oup, long 
         if (i < HS_NSLOT) {
             grow(&r->d_in[s], &r->cap_in[s], in_row * chunk);
             grow(&r->d_out[s], &r->cap_out[s], out_row * chunk);
-            if (!hs_dev_has_pipe(c, 1)) grow(&r->d_z[s], &r->cap_z[s], sizeof(fft_data) * (size_t)chunk * r->H);
+            grow(&r->d_z[s], &r->cap_z[s], sizeof(fft_data) * (size_t)chunk * r->H);
             grow(&r->d_ws[s], &r->cap_ws[s], hs_dev_ws_bytes(c, chunk));
         }
         /* a single transform is given as N/2+1 bins by reference-style callers; rows of a batch are N bins apart */

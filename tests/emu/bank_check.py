@@ -73,7 +73,42 @@ def check(N, T, logpad, radices, verbose=True):
     return worst
 
 
+def check_inplace(N, T, logpad, radices, verbose=True):
+    """In-place DIF/DIT stages of csrc/hs_conv_fft.cuh: butterfly beta of stage s touches base + m*i,
+    base = (beta // m) * L + beta % m; reads and writes hit the same addresses."""
+    L = N
+    worst = 1.0
+    for s, R in enumerate(radices):
+        m = L // R
+        NB = N // R
+        B = -(-NB // T)
+        tot = [0, 0]
+        for w0 in range(0, T, 32):
+            lanes = list(range(w0, min(w0 + 32, T)))
+            for u in range(B):
+                for i in range(R):
+                    ad = []
+                    for t in lanes:
+                        beta = t + T * u
+                        ad.append(pad((beta // m) * L + beta % m + m * i, logpad) if beta < NB else None)
+                    a, b_ = wavefronts(ad)
+                    tot[0] += a
+                    tot[1] += b_
+        r = tot[0] / tot[1] if tot[1] else 1.0
+        worst = max(worst, r)
+        if verbose:
+            print("  stage %d radix %2d L=%5d m=%5d: x%.2f" % (s, R, L, m, r))
+        L = m
+    return worst
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "inplace":
+        N, T = int(sys.argv[2]), int(sys.argv[3])
+        rad = [int(x) for x in sys.argv[4:]]
+        for lp in (0, 2, 3, 4, 5, 6):
+            print("N=%d T=%d radices=%s LOGPAD=%d: worst x%.2f" % (N, T, rad, lp, check_inplace(N, T, lp, rad, verbose=False)))
+        sys.exit(0)
     plans = [
         (4096, 256, [16, 16, 16]), (4096, 512, [8, 8, 8, 8]), (3000, 200, [3, 5, 5, 5, 8]),
         (1024, 64, [16, 8, 8]), (1024, 64, [8, 8, 16]), (1024, 128, [8, 16, 8]), (2048, 128, [8, 16, 16]), (2048, 128, [16, 16, 8]),

@@ -14,11 +14,11 @@
 #include <cstring>
 
 #include "hs_abi.h"
+#include "hs_conv_fft.cuh"
 #include "hs_fused.cuh"
 #include "hs_generic.cuh"
 #include "hs_smem_fft.cuh"
 #include "hs_tiled.cuh"
-#include "hs_pipe.cuh"
 
 typedef void *hs_stream_t;
 static std::atomic<long long> g_launches{0};
@@ -39,6 +39,24 @@ static void launch_blu(int N, const void *in, void *out, const void *twf, const 
     const long long blocks = (howmany + PF::X - 1) / PF::X;
     hs_emu_launch(hs_bluestein_kernel<PF, PI, SGN, MINB>, blocks, PF::threads, PF::smem_bytes, (const cplx *)in, (cplx *)out,
                   (const cplx *)twf, (const cplx *)twi, (const cplx *)chirp, (const cplx *)hk, N, howmany, 2);
+    ++g_launches;
+}
+
+template <class PF, class PI, int SGN, int MINB>
+static void launch_blu_split(int N, const void *in, void *out, const void *twf, const void *twi, const void *chirp3, const void *hk2,
+                             long long howmany, hs_stream_t)
+{
+    hs_emu_launch(hs_bluestein_split_kernel<PF, PI, SGN, MINB>, howmany, PF::threads, PF::smem_bytes, (const cplx *)in, (cplx *)out,
+                  (const cplx *)twf, (const cplx *)twi, (const cplx *)chirp3, (const cplx *)hk2, N, howmany, 2);
+    ++g_launches;
+}
+
+template <class P, int SGN, int MINB>
+static void launch_conv_split(int N, const void *in, void *out, const void *tw, const void *chirp3, const void *hkt2, long long howmany,
+                              hs_stream_t)
+{
+    hs_emu_launch(hs_conv_bluestein_split_kernel<P, SGN, MINB>, howmany, P::threads, P::smem_bytes, (const cplx *)in, (cplx *)out,
+                  (const cplx *)tw, (const cplx *)chirp3, (const cplx *)hkt2, N, howmany, 2);
     ++g_launches;
 }
 
@@ -91,25 +109,6 @@ static void launch_tiled(const void *in, void *out, const void *tw, const HsTile
 
 #include "hs_ct_table.cuh"
 
-// persistent pipelines: CTAs run one after another here, so the first one drains the ticket counter; the
-// emulation checks the ticket order, the producer / compute hand-over, the geometry and the numerics
-template <class PH>
-static HsTmap phase_tmap(const hs_pipe_args &a, int j)
-{
-    HsTmap m{nullptr, 0, 0};
-    if (PH::STAGED) m = HsTmap{(const unsigned char *)(j == 0 ? a.in : a.ring[j - 1]), (long long)a.ph[j].g.in_e * 16, (long long)a.ph[j].g.in_xf * 16};
-    return m;
-}
-template <class PH0, class PH1, class PH2>
-static void launch_pipe(hs_pipe_args &a, hs_stream_t)
-{
-    using SH = HsPipeShape<PH0, PH1, PH2>;
-    memset(a.ctl, 0, HS_PIPE_CTL_BYTES(a.ngroups));
-    hs_emu_launch(hs_pipe_kernel<PH0, PH1, PH2>, 2, SH::NTHREADS, SH::SMEM, a, phase_tmap<PH0>(a, 0), phase_tmap<PH1>(a, 1), phase_tmap<PH2>(a, 2));
-    ++g_launches;
-}
-#include "hs_pipe_table.cuh"
-
 extern "C" {
 int hs_cu_device_count(void) { return 1; }
 void hs_cu_require_device(void) {}
@@ -140,20 +139,6 @@ void hs_cu_ipc_close(void *) {}
 int hs_cu_jit_c2c_create(int, int, const int *, int, hs_ct_desc *) { return -1; } // no NVRTC here: the run-time engine serves these lengths
 void hs_cu_jit_c2c_launch(int, const void *, void *, const void *, long long, void *) {}
 int hs_cu_jit_source(int, int, const int *, int, char *, int) { return 0; }
-
-int hs_cu_launch_pipe(int tp_id, int variant, int sgn, hs_pipe_args *a, void *stream, int query)
-{
-    switch (tp_id) {
-    case CT_T14: return pipe_dispatch<CT_T14>(variant, sgn, *a, stream, query != 0);
-    case CT_T15: return pipe_dispatch<CT_T15>(variant, sgn, *a, stream, query != 0);
-    case CT_T16: return pipe_dispatch<CT_T16>(variant, sgn, *a, stream, query != 0);
-    case CT_T17: return pipe_dispatch<CT_T17>(variant, sgn, *a, stream, query != 0);
-    case CT_T18: return pipe_dispatch<CT_T18>(variant, sgn, *a, stream, query != 0);
-    case CT_T19: return pipe_dispatch<CT_T19>(variant, sgn, *a, stream, query != 0);
-    case CT_T20: return pipe_dispatch<CT_T20>(variant, sgn, *a, stream, query != 0);
-    }
-    return 0;
-}
 
 void hs_cu_launch_generic(int sgn, const void *d_in, void *d_out, const hs_gen_params *p, void *)
 {

@@ -85,56 +85,46 @@ def test_compile_time_two_pass(hs, emu_lib, oracle, n):
     assert "two-pass" in desc and err <= tol(n), (err, desc)
 
 
-@pytest.mark.parametrize("n", [4099, 10007])
+@pytest.mark.parametrize("n", [20011, 40009])
 def test_long_bluestein_three_fused_kernels(hs, emu_lib, oracle, n):
+    """Lengths above the split chirp-z kernels (N > 10240): chirp + pass 1, pass 2 * Hk + inverse pass 1, inverse pass 2 + chirp."""
     for sgn in (1, -1):
         err, desc = run_c2c(hs, emu_lib, oracle, n, sgn, howmany=2)
         assert "3 fused tiled kernels" in desc and err <= tol(n), (n, sgn, err, desc)
 
 
-def test_persistent_pipeline_groups_rings_and_tail(hs, emu_lib, oracle, monkeypatch):
-    """Two-pass transforms as one persistent kernel (hs_pipe.cuh): several groups, a partial last group, ring
-    slots re-used (more groups than slots), lag 1 and 2.  The emulation aborts if a ticket's dependency is not
-    produced by a smaller ticket."""
-    n = 16384
-    monkeypatch.setenv("HSFFT_PIPE", "1")
-    for slot_kb, lag, howmany in ((512, 1, 7), (256, 2, 6), (1 << 14, 1, 3)):
-        monkeypatch.setenv("HSFFT_PIPE_SLOT_KB", str(slot_kb))
-        monkeypatch.setenv("HSFFT_PIPE_LAG", str(lag))
-        err, desc = run_c2c(hs, emu_lib, oracle, n, 1, howmany=howmany, seed=slot_kb)
-        assert "persistent" in desc and err <= tol(n), (slot_kb, lag, err, desc)
-    monkeypatch.setenv("HSFFT_PIPE", "0")
-    err, desc = run_c2c(hs, emu_lib, oracle, n, 1, howmany=2)
-    assert "persistent" not in desc and err <= tol(n)
+def test_long_bluestein_route_still_serves_mid_lengths_when_split_is_off(hs, emu_lib, oracle, monkeypatch):
+    monkeypatch.setenv("HSFFT_BLU_SPLIT", "0")
+    for n in (4099, 10007):
+        err, desc = run_c2c(hs, emu_lib, oracle, n, 1, howmany=2)
+        assert "3 fused tiled kernels" in desc and err <= tol(n), (n, err, desc)
 
 
-def test_persistent_pipeline_real_transforms(hs, emu_lib, oracle, monkeypatch):
-    """r2c (split as third phase) and c2r (merge on pass 1's loads) over a pipelined half-length plan."""
-    n = 32768
-    monkeypatch.setenv("HSFFT_PIPE", "1")
-    monkeypatch.setenv("HSFFT_PIPE_SLOT_KB", "512")
-    x = xorshift_uniform(5 * n, seed=11).reshape(5, n)
-    with hs.RealPlan(n, 1, lib=emu_lib) as f, hs.RealPlan(n, -1, lib=emu_lib) as g:
-        X = f.r2c(x)
-        Xr = oracle.r2c(x)
-        assert rel_rms(X, Xr) <= tol(n)
-        assert np.array_equal(X[:, n - 1: n // 2: -1], np.conj(X[:, 1: n // 2]))
-        y = g.c2r(X)
-        assert rel_rms(y, oracle.c2r(Xr, n)) <= tol(n)
-        assert rel_rms(y / n, x) <= tol(n)
+@pytest.mark.parametrize("n", [4099, 8191, 8209, 10007, 10239])
+@pytest.mark.parametrize("family", ["in-place", "auto-sort"])
+def test_split_chirp_z_one_kernel_two_half_length_convolutions(hs, emu_lib, oracle, n, family, monkeypatch):
+    """N <= M' = 8192 / 10240: the padded convolution of length 2M' as two convolutions of length M' inside one CTA
+    (hs_conv_fft.cuh: in-place transforms, digit-reversed spectrum; hs_fused.cuh: the auto-sort pair), odd batch."""
+    if family == "auto-sort":
+        monkeypatch.setenv("HSFFT_SPLIT_AUTOSORT", "1")
+    for sgn in (1, -1):
+        err, desc = run_c2c(hs, emu_lib, oracle, n, sgn, howmany=3)
+        assert "split chirp-z" in desc and family in desc and err <= tol(n) and err < 5e-15, (n, sgn, err, desc)
 
 
-def test_persistent_pipeline_long_bluestein_groups(hs, emu_lib, oracle, monkeypatch):
-    monkeypatch.setenv("HSFFT_PIPE", "1")
-    monkeypatch.setenv("HSFFT_BLU_POW2", "1")   # the pipelines exist for the power-of-two pad lengths
-    monkeypatch.setenv("HSFFT_PIPE_SLOT_KB", "512")
-    err, desc = run_c2c(hs, emu_lib, oracle, 10007, 1, howmany=5)
-    assert "persistent" in desc and err <= tol(10007), (err, desc)
+def test_split_chirp_z_variants_and_small_lengths(hs, emu_lib, oracle, monkeypatch):
+    """HSFFT_BLU_SPLIT=2 takes the split kernel for N <= 4096 as well (M' = 4096); HSFFT_PREFER_CT is read when the
+    library loads, so the A/B variants of the 10240-point plan are exercised on the GPU box only."""
+    monkeypatch.setenv("HSFFT_BLU_SPLIT", "2")
+    for n in (2053, 4093):
+        err, desc = run_c2c(hs, emu_lib, oracle, n, -1, howmany=2)
+        assert "length 4096" in desc and err <= tol(n), (n, err, desc)
 
 
 def test_smooth_bluestein_pad_uses_exact_radix5_and_stays_bluestein_only(hs, emu_lib, oracle, monkeypatch):
-    """N in 8193..10240: the device pads to 20480 = 128 x 160 (full-precision radix-5 stages) instead of 32768.
-    A user-facing N = 20480 transform must NOT take that plan: the reference's own radix-5 literals apply there."""
+    """N in 8193..10240 without the split kernel: the device pads to 20480 = 128 x 160 (full-precision radix-5 stages)
+    instead of 32768.  A user-facing N = 20480 transform must NOT take that plan: the reference's own radix-5 literals apply there."""
+    monkeypatch.setenv("HSFFT_BLU_SPLIT", "0")
     for n in (8209, 10239):
         err, desc = run_c2c(hs, emu_lib, oracle, n, 1, howmany=2)
         assert "M=20480=160x128" in desc and err <= 1e-14, (n, err, desc)
