@@ -159,6 +159,12 @@ int   hs_cu_ct_count(void);
 const hs_ct_desc *hs_cu_ct_get(int idx);
 /* batched contiguous c2c, transform b at in + b*n */
 void  hs_cu_launch_ct_c2c(int id, int sgn, const void *d_in, void *d_out, const void *d_tw, long long howmany, void *stream);
+/* real transforms riding on the one-kernel complex plan `id` of length H = N/2 (hs_smem_fft.cuh):
+ * mode 1 = r2c: d_in rows of N reals (contiguous), d_out rows of `stride` bins, bins 0..H and, when full, the mirrored N-k;
+ * mode 2 = c2r: d_in rows of `stride` bins (0..H are read), d_out rows of N reals.  d_tw2 = exp(+2 pi i k / N), k < H. */
+void  hs_cu_launch_ct_real(int id, int mode, int sgn, const void *d_in, void *d_out, const void *d_tw, const void *d_tw2, long long stride,
+                           int full, long long howmany, void *stream);
+int   hs_cu_ct_has_real(int id);
 /* one pass (1 or 2) of a two-pass transform; d_tw: that pass's sub-plan twiddles; d_twb/d_tws: the
  * inter-pass twiddle tables (pass 2 only) */
 void  hs_cu_launch_ct_twopass(int id, int pass, int sgn, const void *d_in, void *d_out, const void *d_tw, const void *d_twb,
@@ -205,6 +211,10 @@ void  hs_cu_launch_ct_conv_split(int id, int sgn, int N, const void *d_in, void 
 int   hs_cu_jit_c2c_create(int n, int sgn, const int *radix_exec, int nst, hs_ct_desc *desc);
 void  hs_cu_jit_c2c_launch(int handle, const void *d_in, void *d_out, const void *d_tw, long long howmany, void *stream);
 int   hs_cu_jit_source(int n, int sgn, const int *radix_exec, int nst, char *out, int cap);
+/* the real transforms of hs_cu_launch_ct_real on a plan-time kernel (same module, entry points hs_jit_r2c / hs_jit_c2r) */
+int   hs_cu_jit_has_real(int handle);
+void  hs_cu_jit_real_launch(int handle, int mode, const void *d_in, void *d_out, const void *d_tw, const void *d_tw2, long long stride,
+                            int full, long long howmany, void *stream);
 
 /* ---- run-time planned pass and element-wise helpers ---- */
 void  hs_cu_launch_generic(int sgn, const void *d_in, void *d_out, const hs_gen_params *p, void *stream);

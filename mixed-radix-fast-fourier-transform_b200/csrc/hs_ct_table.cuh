@@ -73,6 +73,8 @@ static void ct_init()
     fill_desc<PB256>(g_ct[CT_R256], CT_R256, HS_CT_RADER);
     fill_desc<PB2048x2f>(g_ct[CT_B2048X2], CT_B2048X2, HS_CT_BLUESTEIN);
     fill_desc<PB256x16>(g_ct[CT_B256X16], CT_B256X16, HS_CT_BLUESTEIN);
+    fill_desc<PB1024>(g_ct[CT_H1024], CT_H1024, HS_CT_BLUESTEIN_SPLIT);
+    fill_desc<PB2048f>(g_ct[CT_H2048], CT_H2048, HS_CT_BLUESTEIN_SPLIT);
     fill_desc<PB4096>(g_ct[CT_H4096], CT_H4096, HS_CT_BLUESTEIN_SPLIT);
     fill_desc<PB8192f>(g_ct[CT_H8192], CT_H8192, HS_CT_BLUESTEIN_SPLIT);
     fill_desc<PB10240f>(g_ct[CT_H10240], CT_H10240, HS_CT_BLUESTEIN_SPLIT);
@@ -153,6 +155,35 @@ extern "C" void hs_cu_launch_ct_c2c(int id, int sgn, const void *d_in, void *d_o
     }
 }
 
+template <class P, int MINB>
+static void launch_real_sgn(int mode, int sgn, const void *in, void *out, const void *tw, const void *tw2, long long stride, int full,
+                            long long howmany, hs_stream_t st)
+{
+    if (mode == 1) { if (sgn == 1) launch_r2c<P, 1, MINB>(in, out, tw, tw2, stride, full, howmany, st); else launch_r2c<P, -1, MINB>(in, out, tw, tw2, stride, full, howmany, st); }
+    else           { if (sgn == 1) launch_c2r<P, 1, MINB>(in, out, tw, tw2, stride, howmany, st); else launch_c2r<P, -1, MINB>(in, out, tw, tw2, stride, howmany, st); }
+}
+
+extern "C" void hs_cu_launch_ct_real(int id, int mode, int sgn, const void *d_in, void *d_out, const void *d_tw, const void *d_tw2, long long stride,
+                                     int full, long long howmany, void *stream)
+{
+    hs_stream_t st = (hs_stream_t)stream;
+    switch (id) {
+    case CT_4096A: launch_real_sgn<P4096a, 2>(mode, sgn, d_in, d_out, d_tw, d_tw2, stride, full, howmany, st); break;
+    case CT_3000: launch_real_sgn<P3000, 2>(mode, sgn, d_in, d_out, d_tw, d_tw2, stride, full, howmany, st); break;
+    case CT_1024: launch_real_sgn<P1024, 2>(mode, sgn, d_in, d_out, d_tw, d_tw2, stride, full, howmany, st); break;
+    case CT_2048: launch_real_sgn<P2048, 2>(mode, sgn, d_in, d_out, d_tw, d_tw2, stride, full, howmany, st); break;
+    case CT_512: launch_real_sgn<P512, 3>(mode, sgn, d_in, d_out, d_tw, d_tw2, stride, full, howmany, st); break;
+    case CT_256: launch_real_sgn<P256, 3>(mode, sgn, d_in, d_out, d_tw, d_tw2, stride, full, howmany, st); break;
+    case CT_8192: launch_real_sgn<P8192, 1>(mode, sgn, d_in, d_out, d_tw, d_tw2, stride, full, howmany, st); break;
+    default: fprintf(stderr, "Error: compile-time kernel %d has no real-transform form\n", id); exit(EXIT_FAILURE);
+    }
+}
+/* which one-kernel plans hs_cu_launch_ct_real serves */
+extern "C" int hs_cu_ct_has_real(int id)
+{
+    return id == CT_4096A || id == CT_3000 || id == CT_1024 || id == CT_2048 || id == CT_512 || id == CT_256 || id == CT_8192;
+}
+
 extern "C" void hs_cu_launch_ct_rader(int id, const void *d_in, void *d_out, const void *d_tw_f, const void *d_tw_i, const void *d_perm,
                                       const void *d_bk, long long howmany, void *stream)
 {
@@ -220,6 +251,8 @@ extern "C" void hs_cu_launch_ct_bluestein_split(int id, int sgn, int N, const vo
 {
     hs_stream_t st = (hs_stream_t)stream;
     switch (id) {
+    HS_BLUSPLIT_CASE(CT_H1024, PB1024, PB1024, 8)
+    HS_BLUSPLIT_CASE(CT_H2048, PB2048f, PB2048i, 4)
     HS_BLUSPLIT_CASE(CT_H4096, PB4096, PB4096, 2)
     HS_BLUSPLIT_CASE(CT_H8192, PB8192f, PB8192i, 1)
     HS_BLUSPLIT_CASE(CT_H10240, PB10240f, PB10240i, 1)
@@ -328,8 +361,12 @@ static void launch_sub_io(int sgn, int tw_mode, int stcol, int io_mode, int cs, 
                           const hs_tile_geom &g, long long howmany, hs_stream_t st)
 {
     constexpr int C = HsTileCols<P>::C;
-    if (g.ncols % C != 0) { fprintf(stderr, "Error: tiled pass needs a multiple of %d columns (got %d)\n", C, g.ncols); exit(EXIT_FAILURE); }
-    if (io_mode == 1 && sgn == 1 && tw_mode == 0 && !stcol) {
+    if (g.ncols % C != 0 && io_mode != 9) { fprintf(stderr, "Error: tiled pass needs a multiple of %d columns (got %d)\n", C, g.ncols); exit(EXIT_FAILURE); }
+    if (io_mode == 8 && tw_mode == 0 && !stcol) {
+        if (sgn == 1) launch_tiled<P, 1, C, 0, false, 8, 1>(in, out, tw, g, howmany, st); else launch_tiled<P, -1, C, 0, false, 8, 1>(in, out, tw, g, howmany, st);
+    } else if (io_mode == 9 && tw_mode == 1 && stcol) {
+        if (sgn == 1) launch_tiled<P, 1, C, 1, true, 9, 1>(in, out, tw, g, howmany, st); else launch_tiled<P, -1, C, 1, true, 9, 1>(in, out, tw, g, howmany, st);
+    } else if (io_mode == 1 && sgn == 1 && tw_mode == 0 && !stcol) {
         if (cs == 1) launch_tiled<P, 1, C, 0, false, 1, 1>(in, out, tw, g, howmany, st);
         else launch_tiled<P, 1, C, 0, false, 1, -1>(in, out, tw, g, howmany, st);
     } else if (io_mode == 2 && sgn == -1 && tw_mode == 1 && stcol) {

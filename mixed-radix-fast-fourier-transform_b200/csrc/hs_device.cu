@@ -211,6 +211,29 @@ static void launch_c2c(const void *in, void *out, const void *tw, long long howm
     ++g_launches;
 }
 
+template <class P, int SGN, int MINB>
+static void launch_r2c(const void *in, void *out, const void *tw, const void *tw2, long long out_stride, int full, long long howmany, cudaStream_t st)
+{
+    auto kern = hs_r2c_smem_kernel<P, SGN, MINB>;
+    hs_func_attr_once((const void *)kern, P::smem_bytes, MINB);
+    const long long blocks = (howmany + P::X - 1) / P::X;
+    check_grid(blocks);
+    kern<<<(unsigned)blocks, P::threads, P::smem_bytes, st>>>((const cplx *)in, (cplx *)out, (const cplx *)tw, (const cplx *)tw2, out_stride, full, howmany);
+    HS_CUDA_CHECK(cudaGetLastError());
+    ++g_launches;
+}
+template <class P, int SGN, int MINB>
+static void launch_c2r(const void *in, void *out, const void *tw, const void *tw2, long long in_stride, long long howmany, cudaStream_t st)
+{
+    auto kern = hs_c2r_smem_kernel<P, SGN, MINB>;
+    hs_func_attr_once((const void *)kern, P::smem_bytes, MINB);
+    const long long blocks = (howmany + P::X - 1) / P::X;
+    check_grid(blocks);
+    kern<<<(unsigned)blocks, P::threads, P::smem_bytes, st>>>((const cplx *)in, (cplx *)out, (const cplx *)tw, (const cplx *)tw2, in_stride, howmany);
+    HS_CUDA_CHECK(cudaGetLastError());
+    ++g_launches;
+}
+
 template <class PF, class PI, int SGN, int MINB>
 static void launch_blu(int N, const void *in, void *out, const void *twf, const void *twi, const void *chirp, const void *hk,
                        long long howmany, cudaStream_t st)
@@ -357,7 +380,7 @@ static void launch_tiled(const void *in, void *out, const void *tw, const HsTile
         HS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_mark(attr_done);
     }
-    const long long blocks = howmany * (g.ncols / C);
+    const long long blocks = howmany * ((g.ncols + C - 1) / C);
     check_grid(blocks);
     kern<<<(unsigned)blocks, P::T * C, smem, st>>>((const cplx *)in, (cplx *)out, (const cplx *)tw, g, howmany);
     HS_CUDA_CHECK(cudaGetLastError());

@@ -68,12 +68,20 @@ int  hs_stage_twiddle_count(const int *radix_exec, int nst, int split_min);
 void hs_build_chirp(fft_data *h, int N);                                              /* exp(+i pi n^2/N) */
 int  hs_bluestein_exec_pad(int N);                                                    /* 2^ceil(log2(2N-1)) */
 
+/* plan-building helpers (hsfft_plan.c) */
+const hs_ct_desc *hs_find_ct(int family, int n, int allow_exact);
+void *hs_upload_stage_twiddles(const int *radix_exec, int nst, int sgn, int split_min);
+void *hs_upload_interpass_tables(long long n, int sgn, int nb, int K, int kvalid, void **d_tws);
+
 /* c2c sub-plans */
 hs_c2c *hs_c2c_create(int n, int sgn);
 void    hs_c2c_destroy(hs_c2c *p);
 size_t  hs_c2c_ws_elems(const hs_c2c *p, long long howmany); /* workspace (complex elements) exec needs */
 void    hs_c2c_exec(const hs_c2c *p, const void *d_in, void *d_out, void *d_ws, long long howmany, void *stream);
 
+/* r2c with the split fused into the (one-kernel) complex transform; returns 0 when this plan has no such form */
+int     hs_dev_exec_r2c_fused(hs_dev_obj *d, const void *d_in, void *d_out, long long out_stride, int full, const void *d_tw2, long long howmany,
+                              void *stream);
 /* c2r with the merge pass fused into the first pass of the half-length transform; returns 0 when this plan
  * has no such fusion (the caller then runs the separate merge kernel) */
 int     hs_dev_exec_c2r_fused(hs_dev_obj *d, const void *d_spec, long long in_stride, const void *d_tw2, void *d_out, void *d_ws,

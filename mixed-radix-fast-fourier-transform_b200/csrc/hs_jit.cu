@@ -219,7 +219,7 @@ struct JitPlan {
     int n, sgn, dev; // a module belongs to the context of the device that was current when it was loaded
     hs_ct_desc desc;
     CUmodule mod;
-    CUfunction fn;
+    CUfunction fn, fn_r2c, fn_c2r;
     int threads, smem, X, minb;
     std::string text;
 };
@@ -228,16 +228,19 @@ static std::vector<JitPlan *> g_plans;
 
 static std::string make_source(int n, int sgn, const int *rx, int nst, const JitChoice &c)
 {
-    char buf[2048];
+    char buf[4096];
     std::string rad;
     for (int s = 0; s < nst; ++s) { snprintf(buf, sizeof buf, ", %d", rx[s]); rad += buf; }
+    // three entry points over one plan: the complex transform and the two real transforms that ride on it (the bodies of
+    // hs_c2c_smem_kernel / hs_r2c_smem_kernel / hs_c2r_smem_kernel, spelled out: wrapped in a device function the same
+    // code ran at 43 % instead of 78 % of the HBM peak for N = 3000 (measured), so each kernel keeps its loads and stores
+    // in its own scope)
     snprintf(buf, sizeof buf,
              "#include \"hs_smem_fft.cuh\"\n"
              "using PJ = HsPlan<%d, %d, %d, %d, -2, %d%s>;\n"
              "extern \"C\" __global__ void __launch_bounds__(PJ::threads, %d)\n"
              "hs_jit_c2c(const cplx *__restrict__ in, cplx *__restrict__ out, const cplx *__restrict__ tw, long long howmany, int pf_dist)\n"
-             "{\n" // the body of hs_c2c_smem_kernel, spelled out: wrapped in a device function the same code ran at 43 % instead of
-                   // 78 % of the HBM peak for N = 3000 (measured), so the kernel keeps its loads and stores in its own scope
+             "{\n"
              "    HS_DYN_SMEM(cplx, smem);\n"
              "    const int team = HS_TID / PJ::T, t = HS_TID %% PJ::T;\n"
              "    const long long xf = HS_BID * PJ::X + team;\n"
@@ -245,8 +248,35 @@ static std::string make_source(int n, int sgn, const int *rx, int nst, const Jit
              "    HsLoadGlobal ld{in + (active ? xf : 0) * PJ::N};\n"
              "    HsStoreGlobal st{out + (active ? xf : 0) * PJ::N};\n"
              "    hs_fft_team<PJ, %d>(ld, st, smem + team * PJ::NPAD, tw, t, active);\n"
+             "}\n"
+             "extern \"C\" __global__ void __launch_bounds__(PJ::threads, %d)\n"
+             "hs_jit_r2c(const cplx *__restrict__ in, cplx *__restrict__ out, const cplx *__restrict__ tw, const cplx *__restrict__ tw2,\n"
+             "           long long out_stride, int full, long long howmany)\n"
+             "{\n"
+             "    HS_DYN_SMEM(cplx, smem);\n"
+             "    const int team = HS_TID / PJ::T, t = HS_TID %% PJ::T;\n"
+             "    const long long xf = HS_BID * PJ::X + team;\n"
+             "    const bool active = xf < howmany;\n"
+             "    cplx *sm = smem + team * PJ::NPAD;\n"
+             "    HsLoadGlobal ld{in + (active ? xf : 0) * PJ::N};\n"
+             "    HsStoreSmemNatural<PJ> st{sm};\n"
+             "    hs_fft_team<PJ, %d>(ld, st, sm, tw, t, active);\n"
+             "    HS_SYNC();\n"
+             "    if (active) hs_r2c_split_rows<PJ>(sm, out + xf * out_stride, tw2, full, t);\n"
+             "}\n"
+             "extern \"C\" __global__ void __launch_bounds__(PJ::threads, %d)\n"
+             "hs_jit_c2r(const cplx *__restrict__ in, cplx *__restrict__ out, const cplx *__restrict__ tw, const cplx *__restrict__ tw2,\n"
+             "           long long in_stride, long long howmany)\n"
+             "{\n"
+             "    HS_DYN_SMEM(cplx, smem);\n"
+             "    const int team = HS_TID / PJ::T, t = HS_TID %% PJ::T;\n"
+             "    const long long xf = HS_BID * PJ::X + team;\n"
+             "    const bool active = xf < howmany;\n"
+             "    HsLoadC2RMerge ld{in + (active ? xf : 0) * in_stride, tw2, PJ::N};\n"
+             "    HsStoreGlobal st{out + (active ? xf : 0) * PJ::N};\n"
+             "    hs_fft_team<PJ, %d>(ld, st, smem + team * PJ::NPAD, tw, t, active);\n"
              "}\n",
-             n, c.T, c.X, c.logpad, c.groups, rad.c_str(), c.minb, sgn);
+             n, c.T, c.X, c.logpad, c.groups, rad.c_str(), c.minb, sgn, c.minb, sgn, c.minb, sgn);
     return std::string(buf);
 }
 
@@ -315,6 +345,13 @@ extern "C" int hs_cu_jit_c2c_create(int n, int sgn, const int *rx, int nst, hs_c
     drv->FuncSetAttribute(p->fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, p->smem);
     int pct = (int)(((long long)(p->smem + 1024) * c.minb * 100 + 228 * 1024 - 1) / (228 * 1024));
     drv->FuncSetAttribute(p->fn, CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT, pct > 100 ? 100 : pct);
+    p->fn_r2c = p->fn_c2r = nullptr;
+    if (drv->ModuleGetFunction(&p->fn_r2c, p->mod, "hs_jit_r2c") == CUDA_SUCCESS && drv->ModuleGetFunction(&p->fn_c2r, p->mod, "hs_jit_c2r") == CUDA_SUCCESS) {
+        for (CUfunction f : {p->fn_r2c, p->fn_c2r}) {
+            drv->FuncSetAttribute(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, p->smem);
+            drv->FuncSetAttribute(f, CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT, pct > 100 ? 100 : pct);
+        }
+    } else p->fn_r2c = p->fn_c2r = nullptr;
     memset(&p->desc, 0, sizeof p->desc);
     p->desc.id = (int)g_plans.size();
     p->desc.family = HS_CT_C2C;
@@ -347,4 +384,34 @@ extern "C" void hs_cu_jit_c2c_launch(int handle, const void *d_in, void *d_out, 
     const CUresult r = driver()->LaunchKernel(p->fn, (unsigned)blocks, 1, 1, (unsigned)p->threads, 1, 1, (unsigned)p->smem, (CUstream)stream, args, nullptr);
     if (r != CUDA_SUCCESS) { fprintf(stderr, "Error: CUDA failure %d launching the plan-time kernel for N=%d\n", (int)r, p->n); exit(EXIT_FAILURE); }
     hs_cu_count_launch();
+}
+
+extern "C" void hs_cu_jit_real_launch(int handle, int mode, const void *d_in, void *d_out, const void *d_tw, const void *d_tw2, long long stride,
+                                      int full, long long howmany, void *stream)
+{
+    JitPlan *p;
+    {
+        std::lock_guard<std::mutex> lock(g_mu);
+        if (handle < 0 || handle >= (int)g_plans.size()) { fprintf(stderr, "Error: unknown plan-time kernel %d\n", handle); exit(EXIT_FAILURE); }
+        p = g_plans[handle];
+    }
+    if (!p->fn_r2c) { fprintf(stderr, "Error: the plan-time kernel for N=%d has no real-transform entry points\n", p->n); exit(EXIT_FAILURE); }
+    const long long blocks = (howmany + p->X - 1) / p->X;
+    if (blocks <= 0 || blocks > 2147483647LL) { fprintf(stderr, "Error: batch too large for one launch (%lld CTAs)\n", blocks); exit(EXIT_FAILURE); }
+    CUresult r;
+    if (mode == 1) {
+        void *args[] = {(void *)&d_in, (void *)&d_out, (void *)&d_tw, (void *)&d_tw2, (void *)&stride, (void *)&full, (void *)&howmany};
+        r = driver()->LaunchKernel(p->fn_r2c, (unsigned)blocks, 1, 1, (unsigned)p->threads, 1, 1, (unsigned)p->smem, (CUstream)stream, args, nullptr);
+    } else {
+        void *args[] = {(void *)&d_in, (void *)&d_out, (void *)&d_tw, (void *)&d_tw2, (void *)&stride, (void *)&howmany};
+        r = driver()->LaunchKernel(p->fn_c2r, (unsigned)blocks, 1, 1, (unsigned)p->threads, 1, 1, (unsigned)p->smem, (CUstream)stream, args, nullptr);
+    }
+    if (r != CUDA_SUCCESS) { fprintf(stderr, "Error: CUDA failure %d launching the plan-time real kernel for N=%d\n", (int)r, 2 * p->n); exit(EXIT_FAILURE); }
+    hs_cu_count_launch();
+}
+
+extern "C" int hs_cu_jit_has_real(int handle)
+{
+    std::lock_guard<std::mutex> lock(g_mu);
+    return handle >= 0 && handle < (int)g_plans.size() && g_plans[handle]->fn_r2c != nullptr;
 }

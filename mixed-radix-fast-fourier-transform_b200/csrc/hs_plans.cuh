@@ -113,5 +113,5 @@ enum { CT_4096A = 0, CT_4096B, CT_3000, CT_1024, CT_2048, CT_512, CT_256, CT_819
        CT_TX20480, CT_TX40960, CT_TX81920, CT_TX163840, CT_S160X,
        CT_B256, CT_B512, CT_B1024, CT_B4096, CT_B8192,
        CT_R1008, CT_R1008A, CT_R1008G, CT_R256, CT_B2048X2, CT_B256X16,
-       CT_H4096, CT_H8192, CT_H10240,
+       CT_H1024, CT_H2048, CT_H4096, CT_H8192, CT_H10240,
        CT_C4096, CT_C8192, CT_C10240, CT_C10240S, CT_C10240L, CT_C10240H, CT_COUNT };

@@ -419,3 +419,87 @@ hs_c2c_smem_kernel(const cplx *HS_RESTRICT in, cplx *HS_RESTRICT out, const cplx
     HsStoreGlobal st{out + (active ? xf : 0) * P::N};
     hs_fft_team<P, SGN>(ld, st, smem + team * P::NPAD, tw, t, active);
 }
+
+// ------------------------------------------------------------------ real transforms, one kernel
+// reference src/real.c packs N reals as H = N/2 complex samples, runs the half-length complex plan and splits (r2c,
+// :109-132) or merges (c2r, :171-179) with twiddle2[k] = exp(+2 pi i k / N).  Here both ride on the complex kernel:
+//   c2r: the first pass builds element k of the packed signal from bins k and H-k of the Hermitian input as it loads it;
+//   r2c: the last pass leaves the half-length spectrum Z in the team's shared-memory buffer (natural order), and after
+//        one barrier every thread turns pairs (Z[k], Z[H-k]) into bins k and H-k -- and their mirrors N-k, H+k when the
+//        caller wants the reference's full N-bin spectrum -- with coalesced stores.
+// The merged signal / the half-length spectrum never exist in HBM.
+struct HsLoadC2RMerge {
+    static constexpr bool kPost = false;
+    const cplx *HS_RESTRICT x;   // this transform's bins 0..H
+    const cplx *HS_RESTRICT tw2; // exp(+2 pi i k / N)
+    int H;
+    HS_DEVICE cplx operator()(int, int, int k) const
+    {
+        const cplx a = hs_ld_stream(x + k), c = hs_ld_stream(x + (H - k)), w = hs_ld_tab(tw2 + k);
+        const double t1 = -a.y - c.y, t2 = -c.x + a.x; // reference :171-179
+        return hs_c(a.x + c.x + (t1 * w.x) - (t2 * w.y), a.y - c.y + (t2 * w.x) + (t1 * w.y));
+    }
+};
+template <class P>
+struct HsStoreSmemNatural {
+    static constexpr bool kToSmem = true;
+    cplx *sm;
+    HS_DEVICE void operator()(int, int, int k, cplx v) const { sm[P::pad(k)] = v; }
+};
+// bins k and H-k (and their mirrors) from the half-length spectrum Z held in sm; pairs k = t, t + T, ... <= H/2
+template <class P>
+HS_DEVICE void hs_r2c_split_rows(const cplx *sm, cplx *HS_RESTRICT o, const cplx *HS_RESTRICT tw2, const int full, const int t)
+{
+    constexpr int H = P::N;
+    for (int k = t; k <= H / 2; k += P::T) {
+        if (k == 0) {
+            const cplx z0 = sm[0];
+            hs_st_stream(o, hs_c(z0.x + z0.y, 0.0));
+            hs_st_stream(o + H, hs_c(z0.x - z0.y, 0.0));
+        } else {
+            const cplx a = sm[P::pad(k)], c = sm[P::pad(H - k)];
+            const cplx r = hs_r2c_bin(a, c, hs_ld_tab(tw2 + k));
+            hs_st_stream(o + k, r);
+            if (full) hs_st_stream(o + (2 * H - k), hs_c(r.x, -r.y));
+            if (2 * k != H) {
+                const cplx r2 = hs_r2c_bin(c, a, hs_ld_tab(tw2 + (H - k)));
+                hs_st_stream(o + (H - k), r2);
+                if (full) hs_st_stream(o + (H + k), hs_c(r2.x, -r2.y));
+            }
+        }
+    }
+}
+
+// in: rows of 2H reals read as H complex samples (contiguous); out: rows of out_stride bins
+template <class P, int SGN, int MINB>
+HS_GLOBAL void HS_LAUNCH_BOUNDS(P::threads, MINB)
+hs_r2c_smem_kernel(const cplx *HS_RESTRICT in, cplx *HS_RESTRICT out, const cplx *HS_RESTRICT tw, const cplx *HS_RESTRICT tw2, long long out_stride,
+                   int full, long long howmany)
+{
+    static_assert(P::NPASS > 1, "the split works on the shared-memory buffer");
+    HS_DYN_SMEM(cplx, smem);
+    const int team = HS_TID / P::T, t = HS_TID % P::T;
+    const long long xf = HS_BID * P::X + team;
+    const bool active = xf < howmany;
+    cplx *sm = smem + team * P::NPAD;
+    HsLoadGlobal ld{in + (active ? xf : 0) * P::N};
+    HsStoreSmemNatural<P> st{sm};
+    hs_fft_team<P, SGN>(ld, st, sm, tw, t, active);
+    HS_SYNC();
+    if (active) hs_r2c_split_rows<P>(sm, out + xf * out_stride, tw2, full, t);
+}
+
+// in: rows of in_stride bins (0..H are read); out: rows of 2H reals written as H complex samples (contiguous)
+template <class P, int SGN, int MINB>
+HS_GLOBAL void HS_LAUNCH_BOUNDS(P::threads, MINB)
+hs_c2r_smem_kernel(const cplx *HS_RESTRICT in, cplx *HS_RESTRICT out, const cplx *HS_RESTRICT tw, const cplx *HS_RESTRICT tw2, long long in_stride,
+                   long long howmany)
+{
+    HS_DYN_SMEM(cplx, smem);
+    const int team = HS_TID / P::T, t = HS_TID % P::T;
+    const long long xf = HS_BID * P::X + team;
+    const bool active = xf < howmany;
+    HsLoadC2RMerge ld{in + (active ? xf : 0) * in_stride, tw2, P::N};
+    HsStoreGlobal st{out + (active ? xf : 0) * P::N};
+    hs_fft_team<P, SGN>(ld, st, smem + team * P::NPAD, tw, t, active);
+}

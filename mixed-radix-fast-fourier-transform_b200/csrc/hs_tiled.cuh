@@ -256,13 +256,48 @@ struct HsStoreColSlice { // complex element k of the row = reals 2k, 2k+1; keep 
     }
 };
 
+// Real four-step (r2c of N = n1 n2 reals, reference src/real.c:78-136 computes the same bins through a half-length complex
+// transform and a split pass).  The packed signal z[m] = x[2m] + i x[2m+1] is an n1 x n2/2 complex matrix whose complex
+// column q' carries the REAL columns 2q' and 2q'+1 of the n1 x n2 real matrix.  Pass 1 transforms the complex columns and
+// separates the two real columns' spectra where both partners Z[k1], Z[n1-k1] sit in the same column buffer:
+//     A_2q'[k1] = (Z[k1] + conj Z[n1-k1]) / 2,     A_2q'+1[k1] = (Z[k1] - conj Z[n1-k1]) / 2i,      k1 = 0 .. n1/2
+// (Hermitian: the other rows are their conjugates and are never stored).  Pass 2 runs the n1/2+1 rows:
+//     X[k1 + n1 k2] = sum_q W_N^(q k1) A_q[k1] W_n2^(q k2)
+// and writes every bin together with its conjugate mirror X[N-k].  The split costs one shared-memory round trip in the
+// pass that has HBM bandwidth to spare; no separate split kernel, no half-length spectrum in HBM.
+template <class P>
+struct HsStoreSmemCol { // last pass of a column transform: leave the spectrum in the column's buffer, natural order
+    static constexpr bool kToSmem = true;
+    cplx *sm;
+    HS_DEVICE void operator()(int, int, int k, cplx v) const { sm[P::pad(k)] = v; }
+};
+template <int STP = 0>
+struct HsStoreColR2CMirror { // element k2 of row k1: bin k = k1 + n1 k2 and its mirror N - k
+    cplx *HS_RESTRICT out; // this transform's output row
+    int k1, n1, full;
+    long long H;
+    HS_DEVICE void operator()(int, int, int k2, cplx v) const
+    {
+        const long long k = k1 + (long long)n1 * k2;
+        const bool selfrow = (k1 == 0) || (2 * k1 == n1); // rows whose mirror bins lie in the row itself
+        if (k <= H) {
+            hs_st_mp<STP>(out + k, v);
+            if (full && k != 0 && k != H) hs_st_mp<STP>(out + (2 * H - k), hs_conj(v));
+        } else if (!selfrow) {
+            hs_st_mp<STP>(out + (2 * H - k), hs_conj(v));
+            if (full) hs_st_mp<STP>(out + k, v);
+        }
+    }
+};
+
 // One tile: C adjacent columns c0..c0+C-1 of one outer item, whose input / output start at in_x / out_x.
 // P: plan of the sub-transform (P::X is ignored); C: columns per CTA; TW: inter-pass twiddle on load
 // (0 none, 1 keyed by the column, 2 keyed by the outer item xf); STCOL: stores keep lane = column
 // instead of switching to lane = thread of a team (contiguous output rows).
 // IO: 0 plain; 1 chirp-and-pad load (CS = chirp direction); 2 chirp-and-crop store; 3 c2r merge on load;
 // 4 zero padding on load, 5 spectrum product on merge load, 6 slice on store (convolution);
-// 7 four-step exchange on store (g.chirp = the plan's hs_dist_store in device memory).
+// 7 four-step exchange on store (g.chirp = the plan's hs_dist_store in device memory);
+// 8 / 9 the two passes of the real four-step (g.out_c = two workspace rows; g.nlog = n1, g.sl_start = full spectrum).
 // tid: thread index in the tile's team of P::T*C threads; on: false for threads (or whole CTAs) that only
 // take part in the barriers.
 // STG: the input tile was staged in shared memory by the copy engine ([row][C] at in_x); IO 0 and 2 only.
@@ -316,6 +351,31 @@ HS_DEVICE void hs_tile_run(const cplx *HS_RESTRICT in_x, cplx *HS_RESTRICT out_x
             ld.blk_log = g.blk_log; ld.blk_stride = g.blk_stride;
             hs_fft_team2<P, SGN>(ld, st, first, rest, tw, hk);
         }
+    } else if constexpr (IO == 8) { // real four-step, pass 1: transform the complex columns, split into the two real columns' rows 0..n1/2
+        static_assert(TW == 0 && !STCOL && !STG, "the split belongs to a first pass with contiguous output rows");
+        HsStoreSmemCol<P> st{rest.sm};
+        HsLoadCol<LDP> ld;
+        ld.base = in_x; ld.off0 = (long long)(c0 + colA) * g.in_c; ld.es = g.in_e;
+        ld.blk_log = g.blk_log; ld.blk_stride = g.blk_stride;
+        hs_fft_team2<P, SGN>(ld, st, first, rest, tw, hk);
+        hk.sync();
+        if (on) {
+            const cplx *z = rest.sm;
+            cplx *oe = out_x + (long long)(c0 + colB) * g.out_c, *oo = oe + g.out_c / 2; // g.out_c = two rows of the workspace
+            for (int k1 = tB; k1 <= P::N / 2; k1 += P::T) {
+                const cplx a = z[P::pad(k1)], c = z[P::pad(k1 ? P::N - k1 : 0)];
+                hs_st_mp<STP>(oe + k1, hs_c((a.x + c.x) * 0.5, (a.y - c.y) * 0.5));
+                hs_st_mp<STP>(oo + k1, hs_c((a.y + c.y) * 0.5, (c.x - a.x) * 0.5));
+            }
+        }
+    } else if constexpr (IO == 9) { // real four-step, pass 2: rows k1 = 0..n1/2, every bin stored with its mirror
+        static_assert(TW == 1 && STCOL && !STG, "the mirrored store belongs to a second pass");
+        HsStoreColR2CMirror<STP> st{out_x, c0 + colS, g.nlog, g.sl_start, (long long)g.nlog * P::N / 2};
+        HsLoadColTw<LDP> ld;
+        ld.base = in_x; ld.off0 = (long long)(c0 + colA) * g.in_c; ld.es = g.in_e;
+        ld.blk_log = g.blk_log; ld.blk_stride = g.blk_stride;
+        ld.twb = (const cplx *)g.twb + (c0 + colA); ld.tw_ld = g.tw_ld; ld.step = on ? hs_ld_tab((const cplx *)g.tws + (c0 + colA)) : hs_c(0.0, 0.0);
+        hs_fft_team2<P, SGN>(ld, st, first, rest, tw, hk);
     } else if constexpr (IO == 2) { // inverse last pass of the long Bluestein
         static_assert(TW != 0, "the chirp-and-crop store belongs to a second pass");
         HsStoreColChirpCrop<CS, STP> st{out_x, (const cplx *)g.chirp, g.nlog, (long long)(c0 + colS) * g.out_c, g.out_e};
@@ -368,11 +428,12 @@ HS_GLOBAL void HS_LAUNCH_BOUNDS(P::T *C, MINB)
 hs_tiled_kernel(const cplx *HS_RESTRICT in, cplx *HS_RESTRICT out, const cplx *HS_RESTRICT tw, const HsTileGeom g, long long howmany)
 {
     HS_DYN_SMEM(cplx, smem);
-    const int tiles = g.ncols / C;
+    const int tiles = (g.ncols + C - 1) / C; // a partial last tile only where the columns keep their lane (IO 9: n1/2+1 rows)
     const long long xf = HS_BID / tiles;
     const int c0 = (int)(HS_BID % tiles) * C;
+    const bool on = !STCOL || c0 + HS_TID % C < g.ncols;
     HsNoHooks hk;
-    hs_tile_run<P, SGN, C, TW, STCOL, IO, CS, 0, 0>(in + xf * g.in_xf, out + xf * g.out_xf, tw, g, xf, c0, smem, HS_TID, true, hk);
+    hs_tile_run<P, SGN, C, TW, STCOL, IO, CS, 0, 0>(in + xf * g.in_xf, out + xf * g.out_xf, tw, g, xf, c0, smem, HS_TID, on, hk);
 }
 
 // ----------------------------------------------------------------------------------------------

@@ -195,19 +195,23 @@ static void *upload(const void *h, size_t bytes);
  * M >= 16384 does not fit one SM); HSFFT_BLU_SPLIT=0 turns it off, =2 prefers it wherever a plan exists. */
 static const hs_ct_desc *bluestein_split_plan(int N)
 {
+    /* HSFFT_BLU_SPLIT: 0 off; 1 (default) where it measured faster than the plain one-kernel chirp-z / the three-kernel
+     * route (N > 2048: M' = 4096, 8192, 10240); 2 wherever a plan exists.  Two kernel families offer such plans: the
+     * auto-sort pair of hs_fused.cuh (faster up to M' = 8192: N = 4093 1.61 ms per 16384 transforms against 1.82 ms plain,
+     * N = 8191 4.10 against 4.28 ms for the three kernels) and the in-place transforms of hs_conv_fft.cuh (the only one
+     * that fits M' = 10240 without spilling: 5.0 against 8.7 ms); HSFFT_SPLIT_FAMILY=5 / 6 forces one. */
     const int mode = getenv("HSFFT_BLU_SPLIT") ? atoi(getenv("HSFFT_BLU_SPLIT")) : 1;
-    if (mode == 0 || (mode == 1 && N <= 4096)) return NULL;
-    /* two kernel families offer such plans: the in-place transforms of hs_conv_fft.cuh (default) and the auto-sort ones of
-     * hs_fused.cuh (HSFFT_SPLIT_AUTOSORT=1); among equals the first listed wins (HSFFT_PREFER_CT lists its choice first) */
-    const int want = getenv("HSFFT_SPLIT_AUTOSORT") ? HS_CT_BLUESTEIN_SPLIT : HS_CT_CONV_SPLIT;
+    if (mode == 0 || (mode == 1 && N <= 2048)) return NULL;
+    const int force = getenv("HSFFT_SPLIT_FAMILY") ? atoi(getenv("HSFFT_SPLIT_FAMILY")) : 0;
     const hs_ct_desc *best = NULL;
     const int cnt = hs_cu_ct_count();
-    for (int pass = 0; pass < 2 && !best; ++pass)
-        for (int i = 0; i < cnt; ++i) {
-            const hs_ct_desc *d = hs_cu_ct_get(i);
-            const int fam_ok = pass == 0 ? (d->family == want) : (d->family == HS_CT_BLUESTEIN_SPLIT || d->family == HS_CT_CONV_SPLIT);
-            if (fam_ok && d->n >= N && (!best || d->n < best->n)) best = d;
-        }
+    for (int i = 0; i < cnt; ++i) {
+        const hs_ct_desc *d = hs_cu_ct_get(i);
+        if ((d->family != HS_CT_BLUESTEIN_SPLIT && d->family != HS_CT_CONV_SPLIT) || d->n < N) continue;
+        if (force && d->family != force) continue;
+        const int want = d->n <= 8192 ? HS_CT_BLUESTEIN_SPLIT : HS_CT_CONV_SPLIT;
+        if (!best || d->n < best->n || (d->n == best->n && best->family != want && d->family == want && !getenv("HSFFT_PREFER_CT"))) best = d;
+    }
     return best;
 }
 
@@ -481,6 +485,25 @@ static hs_c2c *c2c_create(int n, int sgn, int allow_exact)
         m *= Rg;
     }
     return p;
+}
+
+/* plan-building helpers shared with hsfft_real.c */
+const hs_ct_desc *hs_find_ct(int family, int n, int allow_exact) { return find_ct_ex(family, n, allow_exact); }
+void *hs_upload_stage_twiddles(const int *rx, int nst, int sgn, int split_min) { return upload_stage_twiddles(rx, nst, sgn, split_min); }
+void *hs_upload_interpass_tables(long long n, int sgn, int nb, int K, int kvalid, void **d_tws)
+{
+    /* twb[b][k] = W_n^(k b), b < nb, and tws[k] = W_n^(k nb), k < kvalid (entries kvalid..K-1 are padding) */
+    fft_data *tb = (fft_data *)calloc((size_t)nb * K, sizeof(fft_data)), *ts = (fft_data *)calloc((size_t)K, sizeof(fft_data));
+    if (!tb || !ts) { fprintf(stderr, "Error: Memory allocation failed for twiddle table\n"); exit(EXIT_FAILURE); }
+    const fft_type theta = -PI2 / (fft_type)n;
+    for (int b = 0; b < nb; ++b)
+        for (int k = 0; k < kvalid; ++k) put_twiddle(&tb[(size_t)b * K + k], k * b, theta, sgn);
+    for (int k = 0; k < kvalid; ++k) put_twiddle(&ts[k], k * nb, theta, sgn);
+    void *d_twb = upload(tb, sizeof(fft_data) * (size_t)nb * K);
+    *d_tws = upload(ts, sizeof(fft_data) * (size_t)K);
+    hs_cu_stream_sync(NULL);
+    free(tb); free(ts);
+    return d_twb;
 }
 
 void hs_c2c_destroy(hs_c2c *p)
@@ -861,10 +884,37 @@ void hs_dev_exec(hs_dev_obj *d, const void *d_in, void *d_out, void *d_ws, long 
     hs_cu_launch_chirp_crop(d->sgn, a, d_out, d->d_chirp, d->N, d->M, howmany, stream);
 }
 
+/* r2c with the split fused into the complex kernel (one launch, no half-length spectrum in HBM): one-kernel plans,
+ * static or compiled for this plan; returns 0 when this plan has no such form (the caller runs transform + split kernel) */
+int hs_dev_exec_r2c_fused(hs_dev_obj *d, const void *d_in, void *d_out, long long out_stride, int full, const void *d_tw2, long long howmany,
+                          void *stream)
+{
+    if (d->lt != 0 || !d->direct || getenv("HSFFT_NO_R2C_FUSE")) return 0;
+    const hs_c2c *p = d->direct;
+    if (p->ct_id >= 0 && hs_cu_ct_has_real(p->ct_id)) {
+        hs_cu_launch_ct_real(p->ct_id, 1, p->sgn, d_in, d_out, p->d_tw, d_tw2, out_stride, full, howmany, stream);
+        return 1;
+    }
+    if (p->jit_id >= 0 && hs_cu_jit_has_real(p->jit_id)) {
+        hs_cu_jit_real_launch(p->jit_id, 1, d_in, d_out, p->d_tw, d_tw2, out_stride, full, howmany, stream);
+        return 1;
+    }
+    return 0;
+}
+
 int hs_dev_exec_c2r_fused(hs_dev_obj *d, const void *d_spec, long long in_stride, const void *d_tw2, void *d_out, void *d_ws,
                           long long howmany, void *stream)
 {
-    if (d->lt != 0 || !d->direct || d->direct->tp_id < 0 || getenv("HSFFT_NO_C2R_FUSE")) return 0;
+    if (d->lt != 0 || !d->direct || getenv("HSFFT_NO_C2R_FUSE")) return 0;
+    if (d->direct->ct_id >= 0 && hs_cu_ct_has_real(d->direct->ct_id)) { /* one kernel: the merge rides on the first pass's loads */
+        hs_cu_launch_ct_real(d->direct->ct_id, 2, d->direct->sgn, d_spec, d_out, d->direct->d_tw, d_tw2, in_stride, 0, howmany, stream);
+        return 1;
+    }
+    if (d->direct->jit_id >= 0 && hs_cu_jit_has_real(d->direct->jit_id)) {
+        hs_cu_jit_real_launch(d->direct->jit_id, 2, d_spec, d_out, d->direct->d_tw, d_tw2, in_stride, 0, howmany, stream);
+        return 1;
+    }
+    if (d->direct->tp_id < 0) return 0;
     const hs_c2c *p = d->direct;
     const hs_ct_desc *tp = NULL;
     for (int i = 0; i < hs_cu_ct_count(); ++i) if (hs_cu_ct_get(i)->id == p->tp_id) tp = hs_cu_ct_get(i);

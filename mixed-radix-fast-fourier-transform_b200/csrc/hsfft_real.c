@@ -20,6 +20,9 @@ typedef struct hs_real_dev {
     const void *key;
     int H;
     void *d_tw2;
+    /* real four-step (N = n1 n2, both with a tiled sub-plan; forward plans): see hs_tiled.cuh */
+    int r4, r4_n1, r4_n2, r4_sub1, r4_sub2, r4_ld;
+    void *d_r4_tw1, *d_r4_tw2, *d_r4_twb, *d_r4_tws;
     void *stream[HS_NSLOT];
     void *d_in[HS_NSLOT], *d_out[HS_NSLOT], *d_z[HS_NSLOT], *d_ws[HS_NSLOT];
     size_t cap_in[HS_NSLOT], cap_out[HS_NSLOT], cap_z[HS_NSLOT], cap_ws[HS_NSLOT];
@@ -32,11 +35,39 @@ static hs_real_dev *r_head = NULL;
 static void real_dev_clear(hs_real_dev *r)
 {
     hs_cu_free(r->d_tw2);
+    hs_cu_free(r->d_r4_tw1); hs_cu_free(r->d_r4_tw2); hs_cu_free(r->d_r4_twb); hs_cu_free(r->d_r4_tws);
     for (int s = 0; s < HS_NSLOT; ++s) {
         hs_cu_free(r->d_in[s]); hs_cu_free(r->d_out[s]); hs_cu_free(r->d_z[s]); hs_cu_free(r->d_ws[s]);
         if (r->stream[s]) hs_cu_stream_destroy(r->stream[s]);
     }
 }
+
+/* Real four-step for long forward transforms: N = n1 * n2 with a tiled sub-plan for both lengths (2^15 .. 2^20).
+ * HSFFT_NO_R2C_FUSE=1 keeps the half-length complex transform followed by the split kernel. */
+static void real_fourstep_setup(fft_real_object obj, hs_real_dev *r)
+{
+    r->r4 = 0;
+    const long long N = 2LL * r->H;
+    if (obj->cobj->sgn != 1 || obj->cobj->lt != 0 || N < (1 << 15) || getenv("HSFFT_NO_R2C_FUSE")) return;
+    static const int lens[4] = {128, 256, 512, 1024};
+    int n1 = 0, n2 = 0;
+    for (int i = 0; i < 4 && !n1; ++i)          /* n1 <= n2, as balanced as the sub-plans allow */
+        for (int j = i; j < 4; ++j)
+            if ((long long)lens[i] * lens[j] == N && (!n1 || lens[j] - lens[i] < n2 - n1)) { n1 = lens[i]; n2 = lens[j]; }
+    if (!n1) return;
+    if (getenv("HSFFT_R4_SWAP")) { const int t = n1; n1 = n2; n2 = t; }
+    const hs_ct_desc *s1 = hs_find_ct(HS_CT_SUB, n1, 0), *s2 = hs_find_ct(HS_CT_SUB, n2, 0);
+    if (!s1 || !s2) return;
+    r->r4_n1 = n1; r->r4_n2 = n2; r->r4_sub1 = s1->id; r->r4_sub2 = s2->id;
+    r->r4_ld = n1 / 2 + 2; /* rows k1 = 0..n1/2 of every real column, padded to an even count (32-byte aligned rows) */
+    r->d_r4_tw1 = hs_upload_stage_twiddles(s1->radix, s1->nst, 1, s1->split_min);
+    r->d_r4_tw2 = hs_upload_stage_twiddles(s2->radix, s2->nst, 1, s2->split_min);
+    r->d_r4_twb = hs_upload_interpass_tables(N, 1, n2 / s2->radix[0], r->r4_ld, n1 / 2 + 1, &r->d_r4_tws);
+    r->r4 = 1;
+}
+
+/* complex elements of the per-transform intermediate (half-length spectrum, or the four-step's padded rows) */
+static size_t real_z_elems(const hs_real_dev *r) { return r->r4 ? (size_t)r->r4_n2 * r->r4_ld : (size_t)r->H; }
 
 static hs_real_dev *real_dev_get(fft_real_object obj)
 {
@@ -64,6 +95,7 @@ static hs_real_dev *real_dev_get(fft_real_object obj)
         r->d_tw2 = hs_cu_malloc(sizeof(fft_data) * (size_t)H);
         hs_cu_h2d(r->d_tw2, obj->twiddle2, sizeof(fft_data) * (size_t)H, NULL);
         for (int s = 0; s < HS_NSLOT; ++s) r->stream[s] = hs_cu_stream_create();
+        real_fourstep_setup(obj, r);
     }
     pthread_mutex_unlock(&r_lock);
     return r;
@@ -132,6 +164,20 @@ static void r2c_dev(fft_real_object obj, hs_real_dev *r, const fft_type *d_in, f
                     void *d_ws, long howmany, void *stream)
 {
     hs_dev_obj *c = hs_dev_get(obj->cobj);
+    if (r->r4) { /* long transforms: real four-step, the split rides on pass 1, the mirror on pass 2's stores (d_z = workspace) */
+        const long long n1 = r->r4_n1, n2 = r->r4_n2, ld = r->r4_ld;
+        hs_tile_geom g;
+        memset(&g, 0, sizeof g);
+        g.ncols = (int)(n2 / 2); g.in_xf = r->H; g.in_c = 1; g.in_e = n2 / 2; g.out_xf = n2 * ld; g.out_c = 2 * ld; g.out_e = 1;
+        hs_cu_launch_tiled_io(r->r4_sub1, 1, 0, 0, 8, 1, d_in, d_z, r->d_r4_tw1, &g, howmany, stream);
+        memset(&g, 0, sizeof g);
+        g.ncols = (int)(n1 / 2 + 1); g.in_xf = n2 * ld; g.in_c = 1; g.in_e = ld; g.out_xf = out_stride;
+        g.twb = r->d_r4_twb; g.tws = r->d_r4_tws; g.tw_ld = (int)ld; g.nlog = (int)n1; g.sl_start = full;
+        hs_cu_launch_tiled_io(r->r4_sub2, 1, 1, 1, 9, 1, d_z, d_out, r->d_r4_tw2, &g, howmany, stream);
+        return;
+    }
+    /* short transforms: the split rides on the one-kernel complex transform (the spectrum is split in shared memory) */
+    if (hs_dev_exec_r2c_fused(c, d_in, d_out, out_stride, full, r->d_tw2, howmany, stream)) return;
     hs_dev_exec(c, d_in, d_z, d_ws, howmany, stream); /* rows of N reals == rows of H complex */
     hs_cu_launch_r2c_post(d_z, d_out, r->d_tw2, r->H, out_stride, full, howmany, stream);
 }
@@ -157,7 +203,7 @@ void fft_r2c_exec_batch_dev(fft_real_object obj, const fft_type *d_in, fft_data 
         exit(EXIT_FAILURE);
     }
     hs_dev_obj *c = hs_dev_get(obj->cobj);
-    grow(&r->d_z[0], &r->cap_z[0], sizeof(fft_data) * (size_t)howmany * r->H);
+    grow(&r->d_z[0], &r->cap_z[0], sizeof(fft_data) * (size_t)howmany * real_z_elems(r));
     grow(&r->d_ws[0], &r->cap_ws[0], hs_dev_ws_bytes(c, howmany));
     r2c_dev(obj, r, d_in, d_out, out_stride, full, r->d_z[0], r->d_ws[0], howmany, stream);
 }
@@ -172,7 +218,7 @@ void fft_c2r_exec_batch_dev(fft_real_object obj, const fft_data *d_in, long in_s
         exit(EXIT_FAILURE);
     }
     hs_dev_obj *c = hs_dev_get(obj->cobj);
-    grow(&r->d_z[0], &r->cap_z[0], sizeof(fft_data) * (size_t)howmany * r->H);
+    grow(&r->d_z[0], &r->cap_z[0], sizeof(fft_data) * (size_t)howmany * real_z_elems(r));
     grow(&r->d_ws[0], &r->cap_ws[0], hs_dev_ws_bytes(c, howmany));
     c2r_dev(obj, r, d_in, in_stride, d_out, r->d_z[0], r->d_ws[0], howmany, stream);
 }
@@ -184,8 +230,8 @@ int hs_real_r2c_padded_dev(fft_real_object obj, const fft_type *d_rows, int len,
     hs_real_dev *r = real_dev_get(obj);
     hs_dev_obj *c = hs_dev_get(obj->cobj);
     if (c->lt != 0 || !c->direct || c->direct->tp_id < 0) return 0;
-    grow(&r->d_z[0], &r->cap_z[0], sizeof(fft_data) * (size_t)howmany * r->H);
-    grow(&r->d_ws[0], &r->cap_ws[0], sizeof(fft_data) * (size_t)howmany * r->H);
+    grow(&r->d_z[0], &r->cap_z[0], sizeof(fft_data) * (size_t)howmany * real_z_elems(r));
+    grow(&r->d_ws[0], &r->cap_ws[0], sizeof(fft_data) * (size_t)howmany * real_z_elems(r));
     if (!hs_dev_exec_padded_real(c, d_rows, len, row_stride, row_off, total, r->d_z[0], r->d_ws[0], howmany, stream)) return 0;
     hs_cu_launch_r2c_post(r->d_z[0], d_out, r->d_tw2, r->H, out_stride, 0, howmany, stream);
     return 1;
@@ -198,7 +244,7 @@ int hs_real_c2r_mul_slice_dev(fft_real_object obj, const fft_data *d_A, const ff
     hs_real_dev *r = real_dev_get(obj);
     hs_dev_obj *c = hs_dev_get(obj->cobj);
     if (c->lt != 0 || !c->direct || c->direct->tp_id < 0) return 0;
-    grow(&r->d_ws[0], &r->cap_ws[0], sizeof(fft_data) * (size_t)howmany * r->H);
+    grow(&r->d_ws[0], &r->cap_ws[0], sizeof(fft_data) * (size_t)howmany * real_z_elems(r));
     return hs_dev_exec_c2r_mul_slice(c, d_A, d_B, in_stride, b_stride, scale, r->d_tw2, d_out, out_stride, out_total, start, len, r->d_ws[0],
                                      howmany, stream);
 }
@@ -224,7 +270,7 @@ void fft_r2c_exec_batch(fft_real_object obj, fft_type *inp, fft_data *oup, long 
         if (i < HS_NSLOT) {
             grow(&r->d_in[s], &r->cap_in[s], in_row * chunk);
             grow(&r->d_out[s], &r->cap_out[s], out_row * chunk);
-            grow(&r->d_z[s], &r->cap_z[s], sizeof(fft_data) * (size_t)chunk * r->H);
+            grow(&r->d_z[s], &r->cap_z[s], sizeof(fft_data) * (size_t)chunk * real_z_elems(r));
             grow(&r->d_ws[s], &r->cap_ws[s], hs_dev_ws_bytes(c, chunk));
         }
         hs_cu_h2d(r->d_in[s], inp + first * N, in_row * cnt, r->stream[s]);
@@ -248,7 +294,7 @@ void fft_c2r_exec_batch(fft_real_object obj, fft_data *inp, fft_type *oup, long 
         if (i < HS_NSLOT) {
             grow(&r->d_in[s], &r->cap_in[s], in_row * chunk);
             grow(&r->d_out[s], &r->cap_out[s], out_row * chunk);
-            grow(&r->d_z[s], &r->cap_z[s], sizeof(fft_data) * (size_t)chunk * r->H);
+            grow(&r->d_z[s], &r->cap_z[s], sizeof(fft_data) * (size_t)chunk * real_z_elems(r));
             grow(&r->d_ws[s], &r->cap_ws[s], hs_dev_ws_bytes(c, chunk));
         }
         /* a single transform is given as N/2+1 bins by reference-style callers; rows of a batch are N bins apart */

@@ -32,6 +32,21 @@ static void launch_c2c(const void *in, void *out, const void *tw, long long howm
     ++g_launches;
 }
 
+template <class P, int SGN, int MINB>
+static void launch_r2c(const void *in, void *out, const void *tw, const void *tw2, long long out_stride, int full, long long howmany, hs_stream_t)
+{
+    hs_emu_launch(hs_r2c_smem_kernel<P, SGN, MINB>, (howmany + P::X - 1) / P::X, P::threads, P::smem_bytes, (const cplx *)in, (cplx *)out,
+                  (const cplx *)tw, (const cplx *)tw2, out_stride, full, howmany);
+    ++g_launches;
+}
+template <class P, int SGN, int MINB>
+static void launch_c2r(const void *in, void *out, const void *tw, const void *tw2, long long in_stride, long long howmany, hs_stream_t)
+{
+    hs_emu_launch(hs_c2r_smem_kernel<P, SGN, MINB>, (howmany + P::X - 1) / P::X, P::threads, P::smem_bytes, (const cplx *)in, (cplx *)out,
+                  (const cplx *)tw, (const cplx *)tw2, in_stride, howmany);
+    ++g_launches;
+}
+
 template <class PF, class PI, int SGN, int MINB>
 static void launch_blu(int N, const void *in, void *out, const void *twf, const void *twi, const void *chirp, const void *hk,
                        long long howmany, hs_stream_t)
@@ -102,7 +117,7 @@ static void launch_tiled(const void *in, void *out, const void *tw, const HsTile
         }
     }
     constexpr int smem = C * hs_col_stride(P::NPAD, C) * (int)sizeof(cplx);
-    hs_emu_launch(hs_tiled_kernel<P, SGN, C, TW, STCOL, 1, IO, CS>, howmany * (g.ncols / C), P::T * C, smem, (const cplx *)in, (cplx *)out,
+    hs_emu_launch(hs_tiled_kernel<P, SGN, C, TW, STCOL, 1, IO, CS>, howmany * ((g.ncols + C - 1) / C), P::T * C, smem, (const cplx *)in, (cplx *)out,
                   (const cplx *)tw, g, howmany);
     ++g_launches;
 }
@@ -139,6 +154,8 @@ void hs_cu_ipc_close(void *) {}
 int hs_cu_jit_c2c_create(int, int, const int *, int, hs_ct_desc *) { return -1; } // no NVRTC here: the run-time engine serves these lengths
 void hs_cu_jit_c2c_launch(int, const void *, void *, const void *, long long, void *) {}
 int hs_cu_jit_source(int, int, const int *, int, char *, int) { return 0; }
+int hs_cu_jit_has_real(int) { return 0; }
+void hs_cu_jit_real_launch(int, int, const void *, void *, const void *, const void *, long long, int, long long, void *) {}
 
 void hs_cu_launch_generic(int sgn, const void *d_in, void *d_out, const hs_gen_params *p, void *)
 {

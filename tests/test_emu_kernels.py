@@ -36,6 +36,7 @@ def test_n3000_is_within_rounding_of_the_reference_not_just_tolerance(hs, emu_li
 def test_fused_bluestein_every_pad_length_one_sm_holds(hs, emu_lib, oracle, n, monkeypatch):
     """M = 256, 512, 1024, 4096 (palindromic radix lists: the inverse plan is the forward plan) and 8192."""
     monkeypatch.setenv("HSFFT_NO_RADER", "1")  # N = 257 would otherwise run as a 256-point cyclic convolution
+    monkeypatch.setenv("HSFFT_BLU_SPLIT", "0")  # N = 4093 would otherwise run as two 4096-point convolutions
     for sgn in (1, -1):
         err, desc = run_c2c(hs, emu_lib, oracle, n, sgn, howmany=5)
         assert "bluestein" in desc and "fused compile-time" in desc and err <= tol(n), (n, sgn, err, desc)
@@ -105,20 +106,24 @@ def test_long_bluestein_route_still_serves_mid_lengths_when_split_is_off(hs, emu
 def test_split_chirp_z_one_kernel_two_half_length_convolutions(hs, emu_lib, oracle, n, family, monkeypatch):
     """N <= M' = 8192 / 10240: the padded convolution of length 2M' as two convolutions of length M' inside one CTA
     (hs_conv_fft.cuh: in-place transforms, digit-reversed spectrum; hs_fused.cuh: the auto-sort pair), odd batch."""
-    if family == "auto-sort":
-        monkeypatch.setenv("HSFFT_SPLIT_AUTOSORT", "1")
+    monkeypatch.setenv("HSFFT_SPLIT_FAMILY", "5" if family == "auto-sort" else "6")
     for sgn in (1, -1):
         err, desc = run_c2c(hs, emu_lib, oracle, n, sgn, howmany=3)
         assert "split chirp-z" in desc and family in desc and err <= tol(n) and err < 5e-15, (n, sgn, err, desc)
 
 
 def test_split_chirp_z_variants_and_small_lengths(hs, emu_lib, oracle, monkeypatch):
-    """HSFFT_BLU_SPLIT=2 takes the split kernel for N <= 4096 as well (M' = 4096); HSFFT_PREFER_CT is read when the
-    library loads, so the A/B variants of the 10240-point plan are exercised on the GPU box only."""
-    monkeypatch.setenv("HSFFT_BLU_SPLIT", "2")
-    for n in (2053, 4093):
+    """Defaults: N = 2049..8192 the auto-sort pair (M' = 4096 / 8192), N = 8193..10240 the in-place transforms; below,
+    the plain one-kernel chirp-z unless HSFFT_BLU_SPLIT=2 asks for the split kernel (M' = 1024 / 2048).  HSFFT_PREFER_CT
+    is read when the library loads, so the A/B variants of the 10240-point plan are exercised on the GPU box only."""
+    for n, want in ((2053, "length 4096 (split chirp-z, auto-sort"), (4093, "length 4096 (split chirp-z, auto-sort"),
+                    (4099, "length 8192 (split chirp-z, auto-sort"), (10007, "length 10240 (split chirp-z, in-place")):
         err, desc = run_c2c(hs, emu_lib, oracle, n, -1, howmany=2)
-        assert "length 4096" in desc and err <= tol(n), (n, err, desc)
+        assert want in desc and err <= tol(n), (n, err, desc)
+    monkeypatch.setenv("HSFFT_BLU_SPLIT", "2")
+    for n, m in ((1031, 2048), (2039, 2048), (521, 1024)):
+        err, desc = run_c2c(hs, emu_lib, oracle, n, 1, howmany=3)
+        assert ("length %d (split" % m) in desc and err <= tol(n), (n, err, desc)
 
 
 def test_smooth_bluestein_pad_uses_exact_radix5_and_stays_bluestein_only(hs, emu_lib, oracle, monkeypatch):
@@ -153,6 +158,49 @@ def test_real_transforms(hs, emu_lib, oracle, n):
         assert rel_rms(y, oracle.c2r(Xr, n)) <= tol(n)
         assert rel_rms(y / n, x) <= tol(n)
         assert rel_rms(g.c2r(f.r2c(x[0])) / n, x[0]) <= tol(n)                   # single-transform entry points
+
+
+@pytest.mark.parametrize("n", [512, 1024, 2048, 4096, 6000, 8192, 16384])
+def test_real_transforms_ride_on_the_one_kernel_complex_plan(hs, emu_lib, oracle, n):
+    """H = N/2 with a one-kernel plan: r2c splits the spectrum in shared memory after the last pass, c2r merges on the first
+    pass's loads -- ONE launch each, no half-length spectrum / merged signal in HBM (reference src/real.c:109-132, :171-179).
+    Batch 5: the last CTA of the plans that hold several transforms per CTA has idle teams."""
+    x = xorshift_uniform(5 * n, seed=9 + n).reshape(5, n)
+    with hs.RealPlan(n, 1, lib=emu_lib) as f, hs.RealPlan(n, -1, lib=emu_lib) as g:
+        f.r2c(x[:2]); g.c2r(oracle.r2c(x[:2]))          # plans built
+        l0 = emu_lib.hsfft_launch_count()
+        X = f.r2c(x)
+        l1 = emu_lib.hsfft_launch_count()
+        Xr = oracle.r2c(x)
+        y = g.c2r(Xr)
+        l2 = emu_lib.hsfft_launch_count()
+        assert (l1 - l0, l2 - l1) == (1, 1), (l1 - l0, l2 - l1)
+        assert max(rel_rms(X[i], Xr[i]) for i in range(5)) <= min(tol(n), 5e-15)
+        assert np.array_equal(X[:, n - 1: n // 2: -1], np.conj(X[:, 1: n // 2]))
+        assert max(rel_rms(y[i], oracle.c2r(Xr, n)[i]) for i in range(5)) <= min(tol(n), 5e-15)
+
+
+@pytest.mark.parametrize("n,swap", [(1 << 15, 0), (1 << 16, 0), (1 << 17, 0), (1 << 17, 1), (1 << 18, 0), (1 << 20, 0)])
+def test_real_four_step_split_on_pass_1_mirror_on_pass_2(hs, emu_lib, oracle, n, swap, monkeypatch):
+    """Long forward real transforms (hs_tiled.cuh IO 8 / 9): two launches, no split kernel; full spectrum with an exact
+    Hermitian mirror, and the half spectrum (bins 0..N/2) with a row stride larger than N/2+1 straight through the
+    device-pointer entry point (host arrays stand in for device memory under the emulation)."""
+    import ctypes as C
+    if swap:
+        monkeypatch.setenv("HSFFT_R4_SWAP", "1")
+    b = 2 if n <= (1 << 17) else 1
+    x = xorshift_uniform(b * n, seed=3 + n).reshape(b, n)
+    Xr = oracle.r2c(x)
+    with hs.RealPlan(n, 1, lib=emu_lib) as f:
+        l0 = emu_lib.hsfft_launch_count()
+        X = f.r2c(x)
+        assert emu_lib.hsfft_launch_count() - l0 == 2
+        assert max(rel_rms(X[i], Xr[i]) for i in range(b)) <= min(tol(n), 5e-15)
+        assert np.array_equal(X[:, n - 1: n // 2: -1], np.conj(X[:, 1: n // 2]))
+        stride = n // 2 + 5
+        half = np.full((b, stride), np.nan + 0j)
+        emu_lib.fft_r2c_exec_batch_dev(f.p, x.ctypes.data_as(C.c_void_p), half.ctypes.data_as(C.c_void_p), stride, 0, b, None)
+        assert np.array_equal(half[:, : n // 2 + 1], X[:, : n // 2 + 1]) and np.isnan(half[:, n // 2 + 1:]).all()
 
 
 @pytest.mark.parametrize("la,lb", [(5, 3), (100, 37), (512, 512), (1000, 24)])
