@@ -105,6 +105,10 @@ void  hsfft_copy_h2d(void *d, const void *h, size_t bytes);
 void  hsfft_copy_d2h(void *h, const void *d, size_t bytes);
 void  hsfft_sync(void);
 long long hsfft_launch_count(void);      /* kernels this library has launched in this process */
+/* per-launch device timing (CUDA events on the launching stream, for roofline records): hsfft_timing_begin(stream), run
+ * any calls, then hsfft_timing_report writes "kernel tag:launches:total ms;..." and returns its length (-1: buffer too small) */
+void  hsfft_timing_begin(void *stream);
+int   hsfft_timing_report(char *out, int cap);
 /* human-readable description of how a plan will execute (kernel family, passes); static buffer */
 const char *hsfft_plan_describe(fft_object obj);
 const char *hsfft_version(void);

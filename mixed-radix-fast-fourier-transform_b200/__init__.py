@@ -50,7 +50,7 @@ EXPORTS = [
     "fft2_init", "fft2_exec", "fft2_exec_batch", "fft2_exec_batch_dev", "fft2_describe", "free_fft2",
     "hsfft_device_count", "hsfft_set_device", "hsfft_get_device", "hsfft_malloc_device", "hsfft_free_device",
     "hsfft_malloc_host", "hsfft_free_host", "hsfft_copy_h2d", "hsfft_copy_d2h", "hsfft_sync", "hsfft_launch_count",
-    "hsfft_plan_describe", "hsfft_version",
+    "hsfft_plan_describe", "hsfft_version", "hsfft_timing_begin", "hsfft_timing_report",
     "hsfft_dist_init", "hsfft_dist_cols_dev", "hsfft_dist_rows_dev", "hsfft_dist_slab_elems", "hsfft_dist_free",
     "hsfft_ipc_get_handle", "hsfft_dist_set_peers", "hsfft_dist_set_peer_pointers", "hsfft_dist_cols_exchange_dev",
 ]
@@ -81,7 +81,7 @@ def _bind(L):
         "hsfft_malloc_device": (vp, [sz]), "hsfft_free_device": (None, [vp]),
         "hsfft_malloc_host": (vp, [sz]), "hsfft_free_host": (None, [vp]),
         "hsfft_copy_h2d": (None, [vp, vp, sz]), "hsfft_copy_d2h": (None, [vp, vp, sz]), "hsfft_sync": (None, []),
-        "hsfft_launch_count": (ll, []), "hsfft_plan_describe": (cp, [P]), "hsfft_version": (cp, []),
+        "hsfft_launch_count": (ll, []), "hsfft_timing_begin": (None, [vp]), "hsfft_timing_report": (i, [cp, i]), "hsfft_plan_describe": (cp, [P]), "hsfft_version": (cp, []),
         "hsfft_dist_init": (vp, [i, i, i, i, i]), "hsfft_dist_cols_dev": (None, [vp, vp, vp, vp, vp]),
         "hsfft_dist_rows_dev": (None, [vp, vp, vp, vp, vp]), "hsfft_dist_slab_elems": (ll, [vp]), "hsfft_dist_free": (None, [vp]),
         "hsfft_ipc_get_handle": (None, [vp, vp]), "hsfft_dist_set_peers": (None, [vp, vp, vp, i]),
@@ -317,3 +317,23 @@ def device_count(lib=None):
 
 def launch_count(lib=None):
     return (lib or load()).hsfft_launch_count()
+
+
+class launch_timing:
+    """with launch_timing(stream) as t: ... ; t.kernels -> [(tag, launches, total_ms)] in launch order (CUDA events on the stream)."""
+
+    def __init__(self, stream=0, lib=None):
+        self.L, self.stream, self.kernels = lib or load(), stream, []
+
+    def __enter__(self):
+        self.L.hsfft_timing_begin(C.c_void_p(self.stream))
+        return self
+
+    def __exit__(self, *a):
+        buf = C.create_string_buffer(1 << 16)
+        n = self.L.hsfft_timing_report(buf, len(buf))
+        self.kernels = []
+        if n > 0:
+            for f in buf.value.decode().split(";"):
+                tag, cnt, ms = f.rsplit(":", 2)
+                self.kernels.append((tag, int(cnt), float(ms)))

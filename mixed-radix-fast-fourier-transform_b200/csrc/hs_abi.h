@@ -149,6 +149,9 @@ float hs_cu_event_elapsed_ms(void *start, void *stop);
 void  hs_cu_event_sync(void *ev);
 int   hs_cu_sm_count(void);
 long long hs_cu_launch_count(void);          /* kernels launched by this library so far */
+/* per-launch device timing (CUDA events on the launching stream): begin, run calls, then report "tag:count:total_ms;..." */
+void  hs_cu_timing_begin(void *stream);
+int   hs_cu_timing_report(char *out, int cap);
 /* CUDA IPC: a 64-byte handle of a hs_cu_malloc'ed buffer, and its mapping in another process on the same node */
 void  hs_cu_ipc_get(void *d, void *handle64);
 void *hs_cu_ipc_open(const void *handle64);

@@ -16,6 +16,7 @@
         }                                                                                              \
     } while (0)
 
+extern "C" void hs_cu_timing_mark(const char *tag, void *stream); // per-launch timing hook (no-op unless bench.py turned it on)
 extern "C" void hs_cu_count_launch(void); // bumps the library's kernel-launch counter (hs_device.cu)
 
 // ---- tensor maps for the TMA-staged tiles (cuTensorMapEncodeTiled through the runtime's driver entry point)

@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <atomic>
+#include <string>
 
 #include "hs_abi.h"
 #include "hs_cuda_util.h"
@@ -136,10 +137,79 @@ extern "C" void *hs_cu_ipc_open(const void *handle64)
 extern "C" void hs_cu_ipc_close(void *mapped) { if (mapped) HS_CUDA_CHECK(cudaIpcCloseMemHandle(mapped)); }
 extern "C" long long hs_cu_launch_count(void) { return g_launches.load(); }
 extern "C" void hs_cu_count_launch(void) { ++g_launches; }
+
+// Per-launch timing for bench.py's roofline record (hsfft_timing_begin / hsfft_timing_report in include/hsfft_b200.h): while it
+// is on, every launcher records a CUDA event on its stream right after its kernel; the time between consecutive events
+// of a stream is that kernel's duration (launches of one call run back to back).  Off (the default) it costs a branch.
+#include <mutex>
+#include <string>
+#include <vector>
+static std::atomic<int> g_timing{0};
+static std::mutex g_timing_mu;
+struct HsTimedLaunch { const char *tag; cudaStream_t st; cudaEvent_t ev; };
+static std::vector<HsTimedLaunch> g_timed;
+extern "C" void hs_cu_timing_mark(const char *tag, void *stream)
+{
+    if (!g_timing.load(std::memory_order_relaxed)) return;
+    cudaEvent_t e;
+    HS_CUDA_CHECK(cudaEventCreate(&e));
+    HS_CUDA_CHECK(cudaEventRecord(e, (cudaStream_t)stream));
+    std::lock_guard<std::mutex> lk(g_timing_mu);
+    g_timed.push_back({tag, (cudaStream_t)stream, e});
+}
+extern "C" void hs_cu_timing_begin(void *stream)
+{
+    {
+        std::lock_guard<std::mutex> lk(g_timing_mu);
+        for (auto &t : g_timed) cudaEventDestroy(t.ev);
+        g_timed.clear();
+    }
+    g_timing.store(1);
+    hs_cu_timing_mark("", stream); // origin of the first launch on this stream
+}
+// stops the recording, waits for the events and writes "tag:count:total_ms;..." (launch order of first appearance)
+extern "C" int hs_cu_timing_report(char *out, int cap)
+{
+    g_timing.store(0);
+    std::lock_guard<std::mutex> lk(g_timing_mu);
+    std::vector<std::string> tags;
+    std::vector<double> ms;
+    std::vector<long long> cnt;
+    for (size_t i = 0; i < g_timed.size(); ++i) {
+        HS_CUDA_CHECK(cudaEventSynchronize(g_timed[i].ev));
+        if (!g_timed[i].tag[0]) continue;
+        long long j = (long long)i - 1;
+        while (j >= 0 && g_timed[j].st != g_timed[i].st) --j; // previous event of the same stream
+        if (j < 0) continue;
+        float t = 0.f;
+        HS_CUDA_CHECK(cudaEventElapsedTime(&t, g_timed[j].ev, g_timed[i].ev));
+        size_t k = 0;
+        while (k < tags.size() && tags[k] != g_timed[i].tag) ++k;
+        if (k == tags.size()) { tags.push_back(g_timed[i].tag); ms.push_back(0.0); cnt.push_back(0); }
+        ms[k] += t; cnt[k] += 1;
+    }
+    std::string r;
+    for (size_t k = 0; k < tags.size(); ++k) {
+        char b[160];
+        snprintf(b, sizeof b, "%s%s:%lld:%.6f", k ? ";" : "", tags[k].c_str(), cnt[k], ms[k]);
+        r += b;
+    }
+    for (auto &t : g_timed) cudaEventDestroy(t.ev);
+    g_timed.clear();
+    if ((int)r.size() + 1 > cap) return -1;
+    memcpy(out, r.c_str(), r.size() + 1);
+    return (int)r.size();
+}
 #else
 extern "C" int hs_cu_sm_count(void);
 #endif
 
+extern "C" void hs_cu_timing_mark(const char *tag, void *stream);
+static inline void hs_launched(const char *tag, cudaStream_t st)
+{
+    ++g_launches;
+    hs_cu_timing_mark(tag, (void *)st);
+}
 // --------------------------------------------------------------------------------------- launchers
 // Function attributes (dynamic shared memory limit, carve-out) belong to a (function, device) pair, so "done" is one bit
 // per device ordinal: a process that drives several GPUs sets them once on each.
@@ -208,7 +278,7 @@ static void launch_c2c(const void *in, void *out, const void *tw, long long howm
     check_grid(blocks);
     kern<<<(unsigned)blocks, P::threads, P::smem_bytes, st>>>((const cplx *)in, (cplx *)out, (const cplx *)tw, howmany, PFW ? prefetch_dist(MINB) : 0);
     HS_CUDA_CHECK(cudaGetLastError());
-    ++g_launches;
+    hs_launched("c2c", st);
 }
 
 template <class P, int SGN, int MINB>
@@ -220,7 +290,7 @@ static void launch_r2c(const void *in, void *out, const void *tw, const void *tw
     check_grid(blocks);
     kern<<<(unsigned)blocks, P::threads, P::smem_bytes, st>>>((const cplx *)in, (cplx *)out, (const cplx *)tw, (const cplx *)tw2, out_stride, full, howmany);
     HS_CUDA_CHECK(cudaGetLastError());
-    ++g_launches;
+    hs_launched("r2c", st);
 }
 template <class P, int SGN, int MINB>
 static void launch_c2r(const void *in, void *out, const void *tw, const void *tw2, long long in_stride, long long howmany, cudaStream_t st)
@@ -231,7 +301,7 @@ static void launch_c2r(const void *in, void *out, const void *tw, const void *tw
     check_grid(blocks);
     kern<<<(unsigned)blocks, P::threads, P::smem_bytes, st>>>((const cplx *)in, (cplx *)out, (const cplx *)tw, (const cplx *)tw2, in_stride, howmany);
     HS_CUDA_CHECK(cudaGetLastError());
-    ++g_launches;
+    hs_launched("c2r", st);
 }
 
 template <class PF, class PI, int SGN, int MINB>
@@ -250,7 +320,7 @@ static void launch_blu(int N, const void *in, void *out, const void *twf, const 
     kern<<<(unsigned)blocks, PF::threads, PF::smem_bytes, st>>>((const cplx *)in, (cplx *)out, (const cplx *)twf, (const cplx *)twi,
                                                                  (const cplx *)chirp, (const cplx *)hk, N, howmany, prefetch_dist(MINB));
     HS_CUDA_CHECK(cudaGetLastError());
-    ++g_launches;
+    hs_launched("blu", st);
 }
 
 template <class PF, class PI, int SGN, int MINB>
@@ -263,7 +333,7 @@ static void launch_blu_split(int N, const void *in, void *out, const void *twf, 
     kern<<<(unsigned)howmany, PF::threads, PF::smem_bytes, st>>>((const cplx *)in, (cplx *)out, (const cplx *)twf, (const cplx *)twi,
                                                                   (const cplx *)chirp3, (const cplx *)hk2, N, howmany, prefetch_dist(MINB));
     HS_CUDA_CHECK(cudaGetLastError());
-    ++g_launches;
+    hs_launched("blu_split", st);
 }
 
 template <class P, int SGN, int MINB>
@@ -276,7 +346,7 @@ static void launch_conv_split(int N, const void *in, void *out, const void *tw, 
     kern<<<(unsigned)howmany, P::threads, P::smem_bytes, st>>>((const cplx *)in, (cplx *)out, (const cplx *)tw, (const cplx *)chirp3,
                                                                 (const cplx *)hkt2, N, howmany, prefetch_dist(MINB));
     HS_CUDA_CHECK(cudaGetLastError());
-    ++g_launches;
+    hs_launched("conv_split", st);
 }
 
 #ifndef HS_RADER_STAGE_DEFAULT
@@ -299,7 +369,7 @@ static void launch_rader_v(const void *in, void *out, const void *twf, const voi
     kern<<<(unsigned)blocks, PF::threads, smem, st>>>((const cplx *)in, (cplx *)out, (const cplx *)twf, (const cplx *)twi, (const int *)perm,
                                                       (const cplx *)bk, howmany, prefetch_dist(MINB));
     HS_CUDA_CHECK(cudaGetLastError());
-    ++g_launches;
+    hs_launched("rader_v", st);
 }
 
 // HSFFT_RADER_STAGE=0 / 2: scatter the outputs straight to HBM / through shared memory (default; measured on B200 at
@@ -351,7 +421,8 @@ static void launch_tiled_tma(const void *in, void *out, const void *tw, const Hs
     const CUtensorMap tm = make_tmap(in, g, P::N, C, howmany);
     kern<<<(unsigned)blocks, P::T * C, smem, st>>>(tm, (cplx *)out, (const cplx *)tw, g, howmany);
     HS_CUDA_CHECK(cudaGetLastError());
-    ++g_launches;
+    static const std::string tag = "tiled_tma n=" + std::to_string(P::N) + (TW ? " pass2" : " pass1");
+    hs_launched(tag.c_str(), st);
 }
 
 #ifndef HS_TILED_MINB_SMALL
@@ -384,7 +455,8 @@ static void launch_tiled(const void *in, void *out, const void *tw, const HsTile
     check_grid(blocks);
     kern<<<(unsigned)blocks, P::T * C, smem, st>>>((const cplx *)in, (cplx *)out, (const cplx *)tw, g, howmany);
     HS_CUDA_CHECK(cudaGetLastError());
-    ++g_launches;
+    static const std::string tag = "tiled n=" + std::to_string(P::N) + (TW ? " pass2" : " pass1") + (IO ? " io" + std::to_string(IO) : std::string());
+    hs_launched(tag.c_str(), st);
 }
 
 template <class PF, class PI, int CS>
@@ -406,7 +478,8 @@ static void launch_blu_mid(const void *in, void *out, const void *twf, const voi
     kern<<<(unsigned)blocks, PF::T * C, smem, st>>>((const cplx *)in, (cplx *)out, (const cplx *)twf, (const cplx *)twi, g, (const cplx *)hk,
                                                     howmany);
     HS_CUDA_CHECK(cudaGetLastError());
-    ++g_launches;
+    static const std::string tag = "blu_mid n=" + std::to_string(PF::N);
+    hs_launched(tag.c_str(), st);
 }
 
 #include "hs_ct_table.cuh"
@@ -429,7 +502,7 @@ extern "C" void hs_cu_launch_generic(int sgn, const void *d_in, void *d_out, con
     if (sgn == 1) hs_generic_pass_kernel<1><<<(unsigned)blocks, 256, smem, st>>>((const cplx *)d_in, (cplx *)d_out, *p);
     else hs_generic_pass_kernel<-1><<<(unsigned)blocks, 256, smem, st>>>((const cplx *)d_in, (cplx *)d_out, *p);
     HS_CUDA_CHECK(cudaGetLastError());
-    ++g_launches;
+    hs_launched("generic", st);
 }
 
 static unsigned ew_grid(long long total)
@@ -448,7 +521,7 @@ extern "C" void hs_cu_launch_chirp_pad(int sgn, const void *x, void *a, const vo
     if (sgn == 1) hs_chirp_pad_kernel<1><<<g, 256, 0, st>>>((const cplx *)x, (cplx *)a, (const cplx *)h, N, M, howmany);
     else hs_chirp_pad_kernel<-1><<<g, 256, 0, st>>>((const cplx *)x, (cplx *)a, (const cplx *)h, N, M, howmany);
     HS_CUDA_CHECK(cudaGetLastError());
-    ++g_launches;
+    hs_launched("chirp_pad", st);
 }
 extern "C" void hs_cu_launch_spectrum_mul(int sgn, void *A, const void *Hk, int M, long long howmany, void *stream)
 {
@@ -457,7 +530,7 @@ extern "C" void hs_cu_launch_spectrum_mul(int sgn, void *A, const void *Hk, int 
     if (sgn == 1) hs_spectrum_mul_kernel<1><<<g, 256, 0, st>>>((cplx *)A, (const cplx *)Hk, M, howmany);
     else hs_spectrum_mul_kernel<-1><<<g, 256, 0, st>>>((cplx *)A, (const cplx *)Hk, M, howmany);
     HS_CUDA_CHECK(cudaGetLastError());
-    ++g_launches;
+    hs_launched("spectrum_mul", st);
 }
 extern "C" void hs_cu_launch_chirp_crop(int sgn, const void *y, void *out, const void *h, int N, int M, long long howmany, void *stream)
 {
@@ -466,7 +539,7 @@ extern "C" void hs_cu_launch_chirp_crop(int sgn, const void *y, void *out, const
     if (sgn == 1) hs_chirp_crop_kernel<1><<<g, 256, 0, st>>>((const cplx *)y, (cplx *)out, (const cplx *)h, N, M, howmany);
     else hs_chirp_crop_kernel<-1><<<g, 256, 0, st>>>((const cplx *)y, (cplx *)out, (const cplx *)h, N, M, howmany);
     HS_CUDA_CHECK(cudaGetLastError());
-    ++g_launches;
+    hs_launched("chirp_crop", st);
 }
 extern "C" void hs_cu_launch_r2c_post(const void *Z, void *out, const void *tw2, int H, long long out_stride, int full, long long howmany,
                                       void *stream)
@@ -474,26 +547,26 @@ extern "C" void hs_cu_launch_r2c_post(const void *Z, void *out, const void *tw2,
     hs_r2c_post_kernel<<<ew_grid(howmany * (H / 2 + 1)), 256, 0, (cudaStream_t)stream>>>((const cplx *)Z, (cplx *)out, (const cplx *)tw2, H,
                                                                                       out_stride, full, howmany);
     HS_CUDA_CHECK(cudaGetLastError());
-    ++g_launches;
+    hs_launched("r2c_post", (cudaStream_t)stream);
 }
 extern "C" void hs_cu_launch_c2r_pre(const void *in, void *z, const void *tw2, int H, long long in_stride, long long howmany, void *stream)
 {
     hs_c2r_pre_kernel<<<ew_grid(howmany * H), 256, 0, (cudaStream_t)stream>>>((const cplx *)in, (cplx *)z, (const cplx *)tw2, H, in_stride,
                                                                                howmany);
     HS_CUDA_CHECK(cudaGetLastError());
-    ++g_launches;
+    hs_launched("c2r_pre", (cudaStream_t)stream);
 }
 extern "C" void hs_cu_launch_conv_mul(const void *A, const void *B, void *C, long long total, double scale, void *stream)
 {
     hs_conv_mul_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>((const cplx *)A, (const cplx *)B, (cplx *)C, total, scale);
     HS_CUDA_CHECK(cudaGetLastError());
-    ++g_launches;
+    hs_launched("conv_mul", (cudaStream_t)stream);
 }
 extern "C" void hs_cu_launch_pad_rows(const void *src, int len, void *dst, int P, long long howmany, void *stream)
 {
     hs_pad_rows_kernel<<<ew_grid(howmany * P), 256, 0, (cudaStream_t)stream>>>((const double *)src, len, (double *)dst, P, howmany);
     HS_CUDA_CHECK(cudaGetLastError());
-    ++g_launches;
+    hs_launched("pad_rows", (cudaStream_t)stream);
 }
 extern "C" void hs_cu_launch_slice_rows(const void *src, int P, int start, int len, void *dst, long long dst_stride, long long howmany,
                                         void *stream)
@@ -501,7 +574,7 @@ extern "C" void hs_cu_launch_slice_rows(const void *src, int P, int start, int l
     hs_slice_rows_kernel<<<ew_grid(howmany * len), 256, 0, (cudaStream_t)stream>>>((const double *)src, P, start, len, (double *)dst,
                                                                                     dst_stride, howmany);
     HS_CUDA_CHECK(cudaGetLastError());
-    ++g_launches;
+    hs_launched("slice_rows", (cudaStream_t)stream);
 }
 extern "C" void hs_cu_launch_transpose(const void *in, void *out, int rows, int cols, long long howmany, void *stream)
 {
@@ -510,7 +583,7 @@ extern "C" void hs_cu_launch_transpose(const void *in, void *out, int rows, int 
     if (blocks < 1) blocks = 1;
     hs_transpose_kernel<<<(unsigned)blocks, 256, 32 * 33 * sizeof(cplx), (cudaStream_t)stream>>>((const cplx *)in, (cplx *)out, rows, cols, howmany);
     HS_CUDA_CHECK(cudaGetLastError());
-    ++g_launches;
+    hs_launched("transpose", (cudaStream_t)stream);
 }
 extern "C" void hs_cu_launch_dist_twiddle(void *b, const void *hi, const void *lo, long long rows, long long cols, long long c0, int logN,
                                           int logS, void *stream)
@@ -518,6 +591,6 @@ extern "C" void hs_cu_launch_dist_twiddle(void *b, const void *hi, const void *l
     hs_dist_twiddle_kernel<0><<<ew_grid(rows * cols), 256, 0, (cudaStream_t)stream>>>((cplx *)b, (const cplx *)hi, (const cplx *)lo, rows, cols,
                                                                                        c0, logN, logS);
     HS_CUDA_CHECK(cudaGetLastError());
-    ++g_launches;
+    hs_launched("dist_twiddle", (cudaStream_t)stream);
 }
 #endif // HS_PART(1)

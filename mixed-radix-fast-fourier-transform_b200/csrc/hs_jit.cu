@@ -384,6 +384,7 @@ extern "C" void hs_cu_jit_c2c_launch(int handle, const void *d_in, void *d_out, 
     const CUresult r = driver()->LaunchKernel(p->fn, (unsigned)blocks, 1, 1, (unsigned)p->threads, 1, 1, (unsigned)p->smem, (CUstream)stream, args, nullptr);
     if (r != CUDA_SUCCESS) { fprintf(stderr, "Error: CUDA failure %d launching the plan-time kernel for N=%d\n", (int)r, p->n); exit(EXIT_FAILURE); }
     hs_cu_count_launch();
+    hs_cu_timing_mark("c2c (plan-time kernel)", stream);
 }
 
 extern "C" void hs_cu_jit_real_launch(int handle, int mode, const void *d_in, void *d_out, const void *d_tw, const void *d_tw2, long long stride,
@@ -408,6 +409,7 @@ extern "C" void hs_cu_jit_real_launch(int handle, int mode, const void *d_in, vo
     }
     if (r != CUDA_SUCCESS) { fprintf(stderr, "Error: CUDA failure %d launching the plan-time real kernel for N=%d\n", (int)r, 2 * p->n); exit(EXIT_FAILURE); }
     hs_cu_count_launch();
+    hs_cu_timing_mark(mode == 1 ? "r2c (plan-time kernel)" : "c2r (plan-time kernel)", stream);
 }
 
 extern "C" int hs_cu_jit_has_real(int handle)

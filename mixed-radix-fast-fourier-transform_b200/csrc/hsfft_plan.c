@@ -1093,6 +1093,8 @@ void hsfft_copy_h2d(void *d, const void *h, size_t bytes) { hs_cu_h2d(d, h, byte
 void hsfft_copy_d2h(void *h, const void *d, size_t bytes) { hs_cu_d2h(h, d, bytes, NULL); hs_cu_stream_sync(NULL); }
 void hsfft_sync(void) { hs_cu_stream_sync(NULL); }
 long long hsfft_launch_count(void) { return hs_cu_launch_count(); }
+void hsfft_timing_begin(void *stream) { hs_cu_timing_begin(stream); }
+int hsfft_timing_report(char *out, int cap) { return hs_cu_timing_report(out, cap); }
 const char *hsfft_version(void) { return "hsfft-b200 0.1 (sm_100a)"; }
 
 const char *hsfft_plan_describe(fft_object obj)

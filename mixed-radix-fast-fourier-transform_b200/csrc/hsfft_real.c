@@ -51,10 +51,14 @@ static void real_fourstep_setup(fft_real_object obj, hs_real_dev *r)
     if (obj->cobj->sgn != 1 || obj->cobj->lt != 0 || N < (1 << 15) || getenv("HSFFT_NO_R2C_FUSE")) return;
     static const int lens[4] = {128, 256, 512, 1024};
     int n1 = 0, n2 = 0;
-    for (int i = 0; i < 4 && !n1; ++i)          /* n1 <= n2, as balanced as the sub-plans allow */
+    for (int i = 0; i < 4 && !n1; ++i)          /* as balanced as the sub-plans allow */
         for (int j = i; j < 4; ++j)
             if ((long long)lens[i] * lens[j] == N && (!n1 || lens[j] - lens[i] < n2 - n1)) { n1 = lens[i]; n2 = lens[j]; }
     if (!n1) return;
+    /* the longer sub-transform goes first (pass 1 has bandwidth to spare, pass 2 writes twice the bytes), unless it is the
+     * 1024-point plan, whose split epilogue at two CTAs per SM is the slower choice.  Measured on B200, n1 x n2:
+     * 2^15 256x128 1.89 ms vs 128x256 2.34; 2^17 512x256 2.13 vs 256x512 2.61; 2^19 512x1024 2.41 vs 1024x512 2.81 */
+    if (n2 != 1024 && n2 > n1) { const int t = n1; n1 = n2; n2 = t; }
     if (getenv("HSFFT_R4_SWAP")) { const int t = n1; n1 = n2; n2 = t; }
     const hs_ct_desc *s1 = hs_find_ct(HS_CT_SUB, n1, 0), *s2 = hs_find_ct(HS_CT_SUB, n2, 0);
     if (!s1 || !s2) return;

@@ -152,3 +152,110 @@ def gather_output(parts, N1, N2):
     """Per-rank out[Kw][N2] (list ordered by rank) -> natural-order X[k1 + N1*k2] (numpy)."""
     full = np.concatenate([np.asarray(p) for p in parts], axis=0)  # [k1][k2]
     return np.ascontiguousarray(full.T).reshape(-1)               # index k2*N1 + k1
+
+
+def bench_four_step(hs, log2n, steps, p2p, rank, world, dev, bins=64):
+    """Device-timed phases (max over ranks) of one c2c of N = 2^log2n points over `world` ranks (torch.distributed already
+    initialised when world > 1), verified on `bins` sampled output bins against direct O(N) DFT sums (fp64, exact integer
+    phase reduction) plus Parseval -- SURVEY.md section 8d's check for sizes no CPU oracle can hold.  Returns a dict."""
+    import math
+    import torch
+    import torch.distributed as dist
+    l1 = log2n // 2
+    N1, N2 = 1 << l1, 1 << (log2n - l1)
+    N = N1 * N2
+    Cw, Kw = N2 // world, N1 // world
+    plan = DistPlan(hs, N1, N2, 1, rank=rank, world=world, device=dev)
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + rank)
+    a = torch.rand((N1 * Cw, 2), generator=g, device=dev, dtype=torch.float64) * 2 - 1
+    out = torch.empty((Kw * N2, 2), device=dev, dtype=torch.float64)
+    ptr = lambda t: C.c_void_p(t.data_ptr())
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    if p2p:
+        plan.enable_p2p()
+    fwd = plan.forward_p2p if p2p else plan.forward
+    for _ in range(3):
+        fwd(a, out)  # warm-up (NCCL channels, kernels, both receive buffers)
+    sync()
+    tA = tX = tB = 0.0
+    for _ in range(steps):
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        sync()
+        if p2p:  # phase A includes the exchange; what is left of "exchange" is the barrier
+            par = plan.calls & 1
+            plan.calls += 1
+            e[0].record()
+            plan.L.hsfft_dist_cols_exchange_dev(plan.pp[par], ptr(a), ptr(plan.ws), plan._stream())
+            e[1].record()
+            if world > 1:
+                dist.all_reduce(plan._flag)
+            e[2].record()
+            plan.L.hsfft_dist_rows_dev(plan.pp[par], plan.rbuf[par], ptr(out), ptr(plan.ws), plan._stream())
+            e[3].record()
+        else:
+            e[0].record(); plan.cols(a); e[1].record(); plan.exchange(); e[2].record(); plan.rows(out); e[3].record()
+        sync()
+        t = torch.tensor([e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2]), e[2].elapsed_time(e[3])], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        tA += t[0].item(); tX += t[1].item(); tB += t[2].item()
+    tA, tX, tB = tA / steps, tX / steps, tB / steps
+
+    # verification: sampled bins + Parseval
+    xa = torch.view_as_complex(a).reshape(N1, Cw)
+    n1 = torch.arange(N1, device=dev, dtype=torch.int64).reshape(N1, 1)
+    c = torch.arange(Cw, device=dev, dtype=torch.int64).reshape(1, Cw)
+    nidx = N2 * n1 + (rank * Cw + c)                       # natural index of every local sample
+    gen = torch.Generator()
+    gen.manual_seed(7)
+    ks = torch.randint(0, N, (bins,), generator=gen, dtype=torch.int64).tolist()
+    ks[0], ks[1] = 0, N - 1
+    want = torch.zeros(bins, dtype=torch.complex128, device=dev)
+    for i, k in enumerate(ks):
+        ph = (nidx * k) % N                                # exact: < 2^60
+        ang = ph.to(torch.float64) * (-2.0 * math.pi / N)
+        want[i] = (xa * torch.complex(torch.cos(ang), torch.sin(ang))).sum()
+    energy_in = (xa.abs() ** 2).sum()
+    X = torch.view_as_complex(out).reshape(Kw, N2)
+    energy_out = (X.abs() ** 2).sum()
+    got = torch.zeros(bins, dtype=torch.complex128, device=dev)
+    for i, k in enumerate(ks):
+        k1, k2 = k % N1, k // N1
+        if k1 // Kw == rank:
+            got[i] = X[k1 % Kw, k2]
+    tot = torch.stack([energy_in, energy_out]).to(torch.float64)
+    if world > 1:
+        wr, wi, gr, gi = want.real.contiguous(), want.imag.contiguous(), got.real.contiguous(), got.imag.contiguous()
+        for t in (wr, wi, gr, gi, tot):
+            dist.all_reduce(t)
+        want, got = torch.complex(wr, wi), torch.complex(gr, gi)
+    err = float(((got - want).abs().pow(2).sum() / want.abs().pow(2).sum()).sqrt())
+    parseval = float(abs(tot[1] / N - tot[0]) / tot[0])
+    total = tA + tX + tB
+    slab = N1 * Cw * 16.0
+    passes_a = 2 * (2 if N1 > 1024 else 1) + (0 if p2p else 2)  # tiled passes (read + write each) + the twiddle pass of the NCCL variant
+    passes_b = 2 * (2 if N2 > 1024 else 1)
+    sent = slab * (world - 1) / world
+    rec = {"four_step": "%dx%d" % (N1, N2),
+           "exchange": "fused into phase A: NVLink peer stores from the transform kernel, all-reduce barrier" if p2p
+                       else "NCCL all_to_all_single between the phases",
+           "ms_total": total, "ms_cols": tA, "ms_exchange": tX, "ms_rows": tB,
+           "gflops": 5.0 * N * log2n / (total * 1e-3) / 1e9,
+           "local_hbm_gbs_per_gpu": {"cols": passes_a * slab / (tA * 1e-3) / 1e9, "rows": passes_b * slab / (tB * 1e-3) / 1e9},
+           "exchange_gbs_per_gpu_per_direction": (sent / ((tA if p2p else tX) * 1e-3) / 1e9) if world > 1 else None,
+           "exchange_bytes_sent_per_gpu": sent, "nvlink_peak_gbs": 900, "nvlink_measured_gbs": 770,
+           "sampled_bins": bins, "rel_rms_err_sampled": err, "tolerance": 1e-12 * log2n, "parseval_rel": parseval,
+           "ok": bool(err <= 1e-12 * log2n and parseval < 1e-12)}
+    if world > 1 and rec["exchange_gbs_per_gpu_per_direction"]:
+        rec["exchange_frac_of_measured_nvlink"] = rec["exchange_gbs_per_gpu_per_direction"] / 770.0
+    plan.close()
+    del a, out
+    torch.cuda.empty_cache()
+    return rec
+

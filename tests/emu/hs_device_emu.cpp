@@ -148,6 +148,8 @@ void hs_cu_stream_wait_event(void *, void *) {}
 float hs_cu_event_elapsed_ms(void *, void *) { return 0.f; }
 void hs_cu_event_sync(void *) {}
 long long hs_cu_launch_count(void) { return g_launches.load(); }
+void hs_cu_timing_begin(void *) {}
+int hs_cu_timing_report(char *out, int cap) { if (cap > 0) out[0] = 0; return 0; }
 void hs_cu_ipc_get(void *d, void *handle64) { memset(handle64, 0, 64); memcpy(handle64, &d, sizeof d); } // one address space here
 void *hs_cu_ipc_open(const void *handle64) { void *p; memcpy(&p, handle64, sizeof p); return p; }
 void hs_cu_ipc_close(void *) {}
