@@ -364,6 +364,8 @@ static void launch_sub_io(int sgn, int tw_mode, int stcol, int io_mode, int cs, 
     if (g.ncols % C != 0 && io_mode != 9) { fprintf(stderr, "Error: tiled pass needs a multiple of %d columns (got %d)\n", C, g.ncols); exit(EXIT_FAILURE); }
     if (io_mode == 8 && tw_mode == 0 && !stcol) {
         if (sgn == 1) launch_tiled<P, 1, C, 0, false, 8, 1>(in, out, tw, g, howmany, st); else launch_tiled<P, -1, C, 0, false, 8, 1>(in, out, tw, g, howmany, st);
+    } else if (io_mode == 10 && tw_mode == 0 && !stcol && sgn == 1) {
+        launch_tiled<P, 1, C, 0, false, 10, 1>(in, out, tw, g, howmany, st);
     } else if (io_mode == 9 && tw_mode == 1 && stcol) {
         if (sgn == 1) launch_tiled<P, 1, C, 1, true, 9, 1>(in, out, tw, g, howmany, st); else launch_tiled<P, -1, C, 1, true, 9, 1>(in, out, tw, g, howmany, st);
     } else if (io_mode == 1 && sgn == 1 && tw_mode == 0 && !stcol) {

@@ -297,7 +297,8 @@ struct HsStoreColR2CMirror { // element k2 of row k1: bin k = k1 + n1 k2 and its
 // IO: 0 plain; 1 chirp-and-pad load (CS = chirp direction); 2 chirp-and-crop store; 3 c2r merge on load;
 // 4 zero padding on load, 5 spectrum product on merge load, 6 slice on store (convolution);
 // 7 four-step exchange on store (g.chirp = the plan's hs_dist_store in device memory);
-// 8 / 9 the two passes of the real four-step (g.out_c = two workspace rows; g.nlog = n1, g.sl_start = full spectrum).
+// 8 / 9 the two passes of the real four-step (g.out_c = two workspace rows; g.nlog = n1, g.sl_start = full spectrum);
+// 10 = 8 with the zero padding of 4 on its loads.
 // tid: thread index in the tile's team of P::T*C threads; on: false for threads (or whole CTAs) that only
 // take part in the barriers.
 // STG: the input tile was staged in shared memory by the copy engine ([row][C] at in_x); IO 0 and 2 only.
@@ -351,13 +352,18 @@ HS_DEVICE void hs_tile_run(const cplx *HS_RESTRICT in_x, cplx *HS_RESTRICT out_x
             ld.blk_log = g.blk_log; ld.blk_stride = g.blk_stride;
             hs_fft_team2<P, SGN>(ld, st, first, rest, tw, hk);
         }
-    } else if constexpr (IO == 8) { // real four-step, pass 1: transform the complex columns, split into the two real columns' rows 0..n1/2
+    } else if constexpr (IO == 8 || IO == 10) { // real four-step, pass 1: transform the complex columns, split into the two real columns' rows 0..n1/2
         static_assert(TW == 0 && !STCOL && !STG, "the split belongs to a first pass with contiguous output rows");
         HsStoreSmemCol<P> st{rest.sm};
-        HsLoadCol<LDP> ld;
-        ld.base = in_x; ld.off0 = (long long)(c0 + colA) * g.in_c; ld.es = g.in_e;
-        ld.blk_log = g.blk_log; ld.blk_stride = g.blk_stride;
-        hs_fft_team2<P, SGN>(ld, st, first, rest, tw, hk);
+        if constexpr (IO == 10) { // convolution: the rows are zero-padded windows of a real array (as IO 4)
+            HsLoadColPadReal ld{(const double *)in_x, xf * g.pad_stride + g.pad_off, g.pad_total, g.nlog, (long long)(c0 + colA) * g.in_c, g.in_e};
+            hs_fft_team2<P, SGN>(ld, st, first, rest, tw, hk);
+        } else {
+            HsLoadCol<LDP> ld;
+            ld.base = in_x; ld.off0 = (long long)(c0 + colA) * g.in_c; ld.es = g.in_e;
+            ld.blk_log = g.blk_log; ld.blk_stride = g.blk_stride;
+            hs_fft_team2<P, SGN>(ld, st, first, rest, tw, hk);
+        }
         hk.sync();
         if (on) {
             const cplx *z = rest.sm;

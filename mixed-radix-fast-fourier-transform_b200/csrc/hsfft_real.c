@@ -235,6 +235,19 @@ int hs_real_r2c_padded_dev(fft_real_object obj, const fft_type *d_rows, int len,
     hs_dev_obj *c = hs_dev_get(obj->cobj);
     if (c->lt != 0 || !c->direct || c->direct->tp_id < 0) return 0;
     grow(&r->d_z[0], &r->cap_z[0], sizeof(fft_data) * (size_t)howmany * real_z_elems(r));
+    if (r->r4 && !getenv("HSFFT_NO_CONV_FUSE")) { /* real four-step with the zero padding on pass 1's loads: two launches, no split kernel */
+        const long long n1 = r->r4_n1, n2 = r->r4_n2, ld = r->r4_ld;
+        hs_tile_geom g;
+        memset(&g, 0, sizeof g);
+        g.ncols = (int)(n2 / 2); g.in_xf = 0; g.in_c = 1; g.in_e = n2 / 2; g.out_xf = n2 * ld; g.out_c = 2 * ld; g.out_e = 1;
+        g.nlog = len; g.pad_stride = row_stride; g.pad_off = row_off; g.pad_total = total;
+        hs_cu_launch_tiled_io(r->r4_sub1, 1, 0, 0, 10, 1, d_rows, r->d_z[0], r->d_r4_tw1, &g, howmany, stream);
+        memset(&g, 0, sizeof g);
+        g.ncols = (int)(n1 / 2 + 1); g.in_xf = n2 * ld; g.in_c = 1; g.in_e = ld; g.out_xf = out_stride;
+        g.twb = r->d_r4_twb; g.tws = r->d_r4_tws; g.tw_ld = (int)ld; g.nlog = (int)n1; g.sl_start = 0;
+        hs_cu_launch_tiled_io(r->r4_sub2, 1, 1, 1, 9, 1, r->d_z[0], d_out, r->d_r4_tw2, &g, howmany, stream);
+        return 1;
+    }
     grow(&r->d_ws[0], &r->cap_ws[0], sizeof(fft_data) * (size_t)howmany * real_z_elems(r));
     if (!hs_dev_exec_padded_real(c, d_rows, len, row_stride, row_off, total, r->d_z[0], r->d_ws[0], howmany, stream)) return 0;
     hs_cu_launch_r2c_post(r->d_z[0], d_out, r->d_tw2, r->H, out_stride, 0, howmany, stream);

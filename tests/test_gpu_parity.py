@@ -320,3 +320,171 @@ print("TILED_OK")
 ''' % (root, root)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, HSFFT_TMA=tma), timeout=600)
     assert "TILED_OK" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Parity at the full BASELINE batches (SURVEY.md section 8d "verification at scale"): the whole batch runs device
+# resident through the C ABI; a >= 1 % random sample of the transforms, including the first and the last one (the
+# tail CTA, the last chunk of a chunked plan), is compared with the oracle on the same inputs.
+
+def _sample_indices(batch, frac=0.01, minimum=3, seed=0):
+    rng = np.random.default_rng(seed)
+    k = max(minimum, int(math.ceil(batch * frac)))
+    idx = set(rng.choice(batch, size=min(k, batch), replace=False).tolist()) | {0, batch - 1}
+    return np.array(sorted(idx), dtype=np.int64)
+
+
+def _device_rand(shape, seed):
+    import torch
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed)
+    return torch.rand(shape, generator=g, device="cuda", dtype=torch.float64) * 2 - 1
+
+
+@pytest.mark.parametrize("n,batch", [(3000, 65536), (1009, 16384), (10007, 16384), (4096, 65536)])
+@pytest.mark.parametrize("sgn", [1, -1])
+def test_full_batch_c2c_sample_against_oracle(hs, product_lib, oracle, n, batch, sgn):
+    import torch
+    x = _device_rand((batch, n, 2), seed=n + sgn)
+    y = torch.empty_like(x)
+    with hs.Plan(n, sgn) as p:
+        p.exec_dev(x, y, batch)
+        torch.cuda.synchronize()
+        desc = p.describe()
+    idx = _sample_indices(batch, seed=n)
+    ti = torch.from_numpy(idx).cuda()
+    xs = torch.view_as_complex(x[ti].contiguous()).cpu().numpy()
+    ys = torch.view_as_complex(y[ti].contiguous()).cpu().numpy()
+    r = oracle.c2c(xs, sgn)
+    assert len(idx) >= batch // 100 and idx[0] == 0 and idx[-1] == batch - 1
+    assert per_transform_worst(ys, r) <= tol(n), (n, sgn, desc)
+
+
+@pytest.mark.parametrize("n,batch", [(1 << 20, 256), (8192, 32768), (2048, 131072)])
+def test_full_batch_real_sample_against_oracle(hs, product_lib, oracle, n, batch):
+    import torch
+    x = _device_rand((batch, n), seed=n)
+    X = torch.empty((batch, n, 2), device="cuda", dtype=torch.float64)
+    back = torch.empty((batch, n), device="cuda", dtype=torch.float64)
+    h1 = n // 2 + 1
+    with hs.RealPlan(n, 1) as f, hs.RealPlan(n, -1) as g:
+        f.r2c_dev(x, X, n, 1, batch)
+        Xh = X[:, :h1, :].contiguous()            # rows of N/2+1 bins: the c2r input layout with in_stride = N/2+1
+        g.c2r_dev(Xh, h1, back, batch)
+        torch.cuda.synchronize()
+    idx = _sample_indices(batch, seed=n)
+    ti = torch.from_numpy(idx).cuda()
+    xs = x[ti].cpu().numpy()
+    Xs = torch.view_as_complex(X[ti].contiguous()).cpu().numpy()
+    Xr = oracle.r2c(xs)
+    assert per_transform_worst(Xs, Xr) <= tol(n)
+    assert np.array_equal(Xs[:, n - 1: n // 2: -1], np.conj(Xs[:, 1: n // 2]))
+    bs = back[ti].cpu().numpy()
+    assert per_transform_worst(bs, oracle.c2r(Xs, n)) <= tol(n)
+    # round trip of the WHOLE batch on the device (size-independent property)
+    rt = ((back / n - x).pow(2).sum(dim=1).sqrt() / x.pow(2).sum(dim=1).sqrt()).max()
+    assert float(rt) <= tol(n)
+
+
+def test_full_batch_convolution_sample_against_oracle(hs, product_lib, oracle):
+    """BASELINE config 4: 2^19 (*) 2^19 samples, 64 rows, device resident through fft_convolve_batch_dev."""
+    import ctypes as C
+    import torch
+    L = hs.load()
+    la = lb = 1 << 19
+    batch = 64
+    a, b = _device_rand((batch, la), seed=1), _device_rand((batch, lb), seed=2)
+    y = torch.zeros((batch, la + lb), device="cuda", dtype=torch.float64)
+    n = L.fft_convolve_batch_dev(b"full", b"linear", C.c_void_p(a.data_ptr()), la, C.c_void_p(b.data_ptr()), lb, C.c_void_p(y.data_ptr()),
+                                 la + lb, batch, None)
+    torch.cuda.synchronize()
+    assert n == la + lb - 1
+    for i in (0, 31, batch - 1):
+        nr, yr = oracle.convolve(a[i].cpu().numpy(), b[i].cpu().numpy(), "full", "linear")
+        assert nr == n and rel_rms(y[i, :n].cpu().numpy(), yr) <= 1e-12 * 20
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The CUDA path against the REFERENCE'S OWN CODE, with no port in between: oracle/_ref (the reference's three .c files
+# compiled where they lie; travels to the GPU box as a binary) and the committed outputs of that same build.
+
+@pytest.mark.parametrize("n", [1024, 3000, 4096, 1009, 10007, 2018, 143])
+def test_cuda_path_against_the_compiled_reference(hs, product_lib, ref_repaired, n):
+    x = rand_cplx(3, n, seed=31 + n)
+    for sgn in (1, -1):
+        with hs.Plan(n, sgn) as p:
+            y = p.exec(x)
+        r = ref_repaired.c2c(x, sgn)
+        assert per_transform_worst(y, r) <= tol(n), (n, sgn)
+    if n % 2 == 0:
+        xr = xorshift_uniform(2 * n, seed=n).reshape(2, n)
+        with hs.RealPlan(n, 1) as f, hs.RealPlan(n, -1) as g:
+            X = f.r2c(xr)
+            Xr = ref_repaired.r2c(xr)
+            assert per_transform_worst(X, Xr) <= tol(n)
+            assert per_transform_worst(g.c2r(X), ref_repaired.c2r(Xr, n)) <= tol(n)
+
+
+def test_cuda_path_against_the_committed_reference_outputs(hs, product_lib):
+    """tests/golden/ref_vectors.npz was written by tests/golden/make_golden.py from oracle/_ref in the build container."""
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_vectors.npz"))
+    checked = 0
+    for n in [2, 3, 4, 5, 7, 8, 15, 16, 20, 64, 11, 13, 26, 143, 19, 59, 257, 1009, 1024, 3000, 4096, 10007]:
+        x = rand_cplx(1, n, seed=424242 + n)[0]
+        for sgn, tag in ((1, "f"), (-1, "i")):
+            key = "c2c_%d_%s" % (n, tag)
+            with hs.Plan(n, sgn) as p:
+                y = p.exec(x)
+            if n <= 64:
+                assert rel_rms(y, z[key]) <= tol(n), key
+            else:
+                idx = z[key + "_idx"]
+                scale = np.sqrt(np.mean(np.abs(y) ** 2))
+                assert np.max(np.abs(y[idx] - z[key])) <= 40 * tol(n) * scale, key
+                assert abs(y.sum() - z[key + "_sum"][0]) <= tol(n) * scale * n, key
+            checked += 1
+    for n in [4, 8, 16, 32, 64, 2018, 4096]:
+        x = xorshift_uniform(n, seed=777 + n)
+        with hs.RealPlan(n, 1) as f, hs.RealPlan(n, -1) as g:
+            X = f.r2c(x)
+            y = g.c2r(X)
+        if n <= 64:
+            assert rel_rms(X, z["r2c_%d" % n]) <= tol(n) and rel_rms(y, z["c2r_%d" % n]) <= tol(n)
+        else:
+            idx = z["r2c_%d_idx" % n]
+            sX, sy = np.sqrt(np.mean(np.abs(X) ** 2)), np.sqrt(np.mean(np.abs(y) ** 2))
+            assert np.max(np.abs(X[idx] - z["r2c_%d" % n])) <= 40 * tol(n) * sX
+            assert np.max(np.abs(y[idx] - z["c2r_%d" % n])) <= 40 * tol(n) * sy
+        checked += 1
+    for la, lb in [(5, 3), (100, 37), (512, 512)]:
+        a, b = xorshift_uniform(la, seed=la), xorshift_uniform(lb, seed=lb + 1)
+        for t in ("full", "same", "valid"):
+            _, y = hs.convolve(a, b, t, "linear")
+            assert rel_rms(y, z["conv_%d_%d_%s" % (la, lb, t)]) <= 1e-12 * math.log2(la + lb + 2)
+            checked += 1
+    assert checked >= 60
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Additive layouts (SURVEY.md section 8f item 3), called directly: half spectrum with a row stride, strided c2r input.
+
+@pytest.mark.parametrize("n", [64, 2018, 4096, 6000, 1 << 15, 1 << 17, 1 << 20])
+def test_half_spectrum_and_row_strides_direct(hs, product_lib, oracle, n):
+    import torch
+    b = 3
+    h1 = n // 2 + 1
+    x = _device_rand((b, n), seed=5 + n)
+    Xr = oracle.r2c(x.cpu().numpy())
+    for stride in (h1, h1 + 7):
+        out = torch.full((b, stride, 2), float("nan"), device="cuda", dtype=torch.float64)
+        with hs.RealPlan(n, 1) as f:
+            f.r2c_dev(x, out, stride, 0, b)
+            torch.cuda.synchronize()
+        got = torch.view_as_complex(out).cpu().numpy()
+        assert per_transform_worst(got[:, :h1], Xr[:, :h1]) <= tol(n), (n, stride)
+        assert np.isnan(got[:, h1:]).all()                      # nothing written beyond bin N/2 of a row
+        back = torch.empty((b, n), device="cuda", dtype=torch.float64)
+        with hs.RealPlan(n, -1) as g:
+            g.c2r_dev(out, stride, back, b)                       # in_stride > N/2+1: the NaN padding must never be read
+            torch.cuda.synchronize()
+        assert per_transform_worst(back.cpu().numpy() / n, x.cpu().numpy()) <= tol(n), (n, stride)
