@@ -487,4 +487,6 @@ def test_half_spectrum_and_row_strides_direct(hs, product_lib, oracle, n):
         with hs.RealPlan(n, -1) as g:
             g.c2r_dev(out, stride, back, b)                       # in_stride > N/2+1: the NaN padding must never be read
             torch.cuda.synchronize()
-        assert per_transform_worst(back.cpu().numpy() / n, x.cpu().numpy()) <= tol(n), (n, stride)
+        # against the reference's own c2r of the reference's spectrum (a round trip is NOT the identity to 1e-12 log2 N where the
+        # reference's truncated radix-3/5 constants act twice, e.g. N/2 = 3000)
+        assert per_transform_worst(back.cpu().numpy(), oracle.c2r(Xr, n)) <= tol(n), (n, stride)
