@@ -39,7 +39,10 @@ void fft_c2r_exec_batch(fft_real_object obj, fft_data *inp, fft_type *oup, long 
 int fft_convolve_batch(const char *type, const char *conv_type, fft_type *input1, int length1,
                        fft_type *input2, int length2, fft_type *output, long out_stride, long howmany);
 
-/* ---- 3. batched, device pointers (stream: a cudaStream_t passed as void*, NULL = default) ---- */
+/* ---- 3. batched, device pointers (stream: a cudaStream_t passed as void*, NULL = default).  Out of place, like every
+ *          transform of the reference: input and output must not overlap.  A plan may be executed from several host
+ *          threads and on several streams at once: calls on one (plan, device) serialise on an internal lock while they
+ *          enqueue, and every caller stream has its own intermediates. ---- */
 void fft_exec_batch_dev(fft_object obj, const fft_data *d_in, fft_data *d_out, long howmany, void *stream);
 /* out_stride: complex elements between output rows (>= N/2+1); full != 0 also writes the mirror
  * bins N/2+1..N-1 (needs out_stride >= N), full == 0 writes bins 0..N/2 only. */
@@ -92,10 +95,17 @@ void hsfft_dist_set_peers(hsfft_dist_object d, void *d_own_r, const void *handle
 void hsfft_dist_set_peer_pointers(hsfft_dist_object d, void *const *peer_r, int npeers);
 void hsfft_dist_cols_exchange_dev(hsfft_dist_object d, const fft_data *d_a, fft_data *d_ws, void *stream);
 void hsfft_dist_free(hsfft_dist_object d);
+/* the same four-step from ONE process driving devices 0 .. ndev-1 (peer access instead of IPC handles): host pointers,
+ * natural order in and out, N = N1*N2, unnormalised.  Returns 0, -1 when the devices cannot reach each other's memory. */
+int fft_exec_dist(int N1, int N2, int sgn, const fft_data *inp, fft_data *oup, int ndev);
 
 /* ---- 4. device helpers ---- */
 int   hsfft_device_count(void);          /* 0 when no usable CUDA device */
-void  hsfft_set_device(int dev);         /* plans are bound to the device current at their first execute */
+void  hsfft_set_device(int dev);         /* device state of a plan is kept per (plan, device): a plan may execute on any device */
+/* The host-pointer batch calls (fft_exec_batch, fft_r2c/c2r_exec_batch, fft_convolve_batch) shard their batch over devices
+ * 0 .. n-1 by batch index, one host thread per device, no communication (default n = 1: the current device only). */
+void  hsfft_set_devices(int n);
+int   hsfft_get_devices(void);
 int   hsfft_get_device(void);
 void *hsfft_malloc_device(size_t bytes);
 void  hsfft_free_device(void *d);

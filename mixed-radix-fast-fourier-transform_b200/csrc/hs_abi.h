@@ -132,6 +132,16 @@ int   hs_cu_get_device(void);
 void  hs_cu_set_device(int dev);
 void *hs_cu_malloc(size_t bytes);
 void  hs_cu_free(void *d);
+/* stream-ordered allocation (cudaMallocAsync / cudaFreeAsync): scratch that grows on a caller's stream without a device-wide
+ * synchronisation and without racing the kernels already queued there */
+void *hs_cu_malloc_async(size_t bytes, void *stream);
+void  hs_cu_free_async(void *d, void *stream);
+void  hs_cu_device_sync(void);
+int   hs_cu_can_access_peer(int dev, int peer);
+void  hs_cu_enable_peer_access(int peer);    /* from the current device; already-enabled is not an error */
+/* rows x width_bytes between host and device with pitches (cudaMemcpy2DAsync) */
+void  hs_cu_h2d_2d(void *d, size_t dpitch, const void *h, size_t hpitch, size_t width_bytes, size_t rows, void *stream);
+void  hs_cu_d2h_2d(void *h, size_t hpitch, const void *d, size_t dpitch, size_t width_bytes, size_t rows, void *stream);
 void *hs_cu_malloc_host(size_t bytes);       /* pinned */
 void  hs_cu_free_host(void *h);
 void  hs_cu_h2d(void *d, const void *h, size_t bytes, void *stream);

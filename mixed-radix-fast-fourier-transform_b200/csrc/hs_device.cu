@@ -67,6 +67,34 @@ extern "C" void *hs_cu_malloc(size_t bytes)
     return p;
 }
 extern "C" void hs_cu_free(void *d) { if (d) HS_CUDA_CHECK(cudaFree(d)); }
+extern "C" void *hs_cu_malloc_async(size_t bytes, void *stream)
+{
+    void *p = nullptr;
+    HS_CUDA_CHECK(cudaMallocAsync(&p, bytes ? bytes : 16, (cudaStream_t)stream));
+    return p;
+}
+extern "C" void hs_cu_free_async(void *d, void *stream) { if (d) HS_CUDA_CHECK(cudaFreeAsync(d, (cudaStream_t)stream)); }
+extern "C" void hs_cu_device_sync(void) { HS_CUDA_CHECK(cudaDeviceSynchronize()); }
+extern "C" int hs_cu_can_access_peer(int dev, int peer)
+{
+    int ok = 0;
+    HS_CUDA_CHECK(cudaDeviceCanAccessPeer(&ok, dev, peer));
+    return ok;
+}
+extern "C" void hs_cu_enable_peer_access(int peer)
+{
+    const cudaError_t e = cudaDeviceEnablePeerAccess(peer, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return; }
+    HS_CUDA_CHECK(e);
+}
+extern "C" void hs_cu_h2d_2d(void *d, size_t dpitch, const void *h, size_t hpitch, size_t width_bytes, size_t rows, void *stream)
+{
+    if (width_bytes && rows) HS_CUDA_CHECK(cudaMemcpy2DAsync(d, dpitch, h, hpitch, width_bytes, rows, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+}
+extern "C" void hs_cu_d2h_2d(void *h, size_t hpitch, const void *d, size_t dpitch, size_t width_bytes, size_t rows, void *stream)
+{
+    if (width_bytes && rows) HS_CUDA_CHECK(cudaMemcpy2DAsync(h, hpitch, d, dpitch, width_bytes, rows, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+}
 extern "C" void *hs_cu_malloc_host(size_t bytes)
 {
     void *p = nullptr;

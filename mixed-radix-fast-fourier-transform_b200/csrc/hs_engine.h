@@ -18,8 +18,22 @@
 extern "C" {
 #endif
 
+#include <pthread.h>
+
 #define HS_MAX_PASS 6
 #define HS_NSLOT 3 /* pipeline depth of the host-pointer batch path */
+
+/* Scratch of the device-pointer entry points, one buffer per caller stream: two streams that execute the same plan
+ * never share an intermediate, and a buffer grows with stream-ordered allocation (no device-wide synchronisation, no
+ * race with the kernels already queued on that stream).  Guarded by the owning object's lock. */
+#define HS_SCRATCH_MAX 8
+typedef struct hs_scratch {
+    void *stream[HS_SCRATCH_MAX], *buf[HS_SCRATCH_MAX];
+    size_t cap[HS_SCRATCH_MAX];
+    int used;
+} hs_scratch;
+void *hs_scratch_get(hs_scratch *s, void *stream, size_t bytes);
+void  hs_scratch_free(hs_scratch *s);
 
 /* batched, contiguous, out-of-place c2c of one length and direction */
 typedef struct hs_c2c {
@@ -38,6 +52,9 @@ typedef struct hs_c2c {
 
 typedef struct hs_dev_obj {
     const void *key;    /* plan address */
+    int device;         /* the CUDA device this state lives on: one entry per (plan, device) */
+    pthread_mutex_t lock; /* execute calls on one (plan, device) serialise on it (staging buffers, scratch look-up, launches) */
+    hs_scratch ws_pool; /* device-pointer calls: workspace per caller stream */
     int N, sgn, lt;
     hs_c2c *direct;     /* lt == 0 */
     /* Bluestein (lt == 1) */
@@ -103,8 +120,14 @@ int     hs_real_r2c_padded_dev(fft_real_object obj, const fft_type *d_rows, int 
 int     hs_real_c2r_mul_slice_dev(fft_real_object obj, const fft_data *d_A, const fft_data *d_B, long in_stride, long b_stride, double scale,
                                   fft_type *d_out, long long out_stride, long long out_total, int start, int len, long howmany, void *stream);
 
-/* registry */
-hs_dev_obj *hs_dev_get(fft_object plan);      /* find or build; exits when no CUDA device */
+/* registry, keyed by (plan address, current device) */
+hs_dev_obj *hs_dev_get(fft_object plan);      /* find or build on the current device; exits when no CUDA device */
+void        hs_dev_lock(hs_dev_obj *d);
+void        hs_dev_unlock(hs_dev_obj *d);
+/* batch sharding over the devices chosen with hsfft_set_devices (hsfft_plan.c): fn(ctx, first, count) runs once per
+ * device, each on its own host thread with that device current; a single device (the default) calls fn directly */
+typedef void (*hs_shard_fn)(void *ctx, long first, long count);
+void        hs_shard_run(long howmany, hs_shard_fn fn, void *ctx);
 void        hs_dev_release(const void *key);  /* no-op when absent */
 void        hs_dev_reserve(hs_dev_obj *d, int slot, size_t in_bytes, size_t out_bytes, size_t ws_bytes, size_t ws2_bytes);
 

@@ -216,7 +216,7 @@ HS_GLOBAL void hs_c2r_pre_kernel(const cplx *HS_RESTRICT in, cplx *HS_RESTRICT z
 }
 
 // convolution product (reference src/convolve.c:147-160): C[k] = A[k]*B[k] * scale, bins 0..H
-HS_GLOBAL void hs_conv_mul_kernel(const cplx *HS_RESTRICT A, const cplx *HS_RESTRICT B, cplx *HS_RESTRICT Cc, long long total, double scale)
+HS_GLOBAL void hs_conv_mul_kernel(const cplx *A, const cplx *HS_RESTRICT B, cplx *Cc, long long total, double scale) // Cc may be A (in-place product)
 {
     for (long long idx = HS_BID * HS_NTHREADS + HS_TID; idx < total; idx += HS_NBLOCKS * HS_NTHREADS) {
         const cplx p = hs_mul(A[idx], B[idx]);

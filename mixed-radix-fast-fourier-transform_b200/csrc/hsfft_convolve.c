@@ -37,12 +37,16 @@ int find_optimal_fft_length(int min_length, const char *conv_type, int length1, 
     exit(EXIT_FAILURE);
 }
 
-/* plan cache: one forward and one inverse real plan per padded length */
+/* plan cache: one forward and one inverse real plan per (padded length, device).  Scratch of the device-pointer calls is
+ * kept per caller stream (hs_scratch); the host-pointer batch call stages through three slots on the cache entry's own
+ * streams and holds the entry's lock for the whole call. */
 typedef struct conv_plans {
-    int P;
+    int P, device;
+    pthread_mutex_t lock;
     fft_real_object fwd, inv;
-    void *d_a, *d_b, *d_A, *d_B, *d_res; /* device scratch, grown on demand */
-    size_t cap_ab, cap_AB, cap_res;
+    hs_scratch a, b, A, B, res;
+    void *stream[HS_NSLOT], *d_1[HS_NSLOT], *d_2[HS_NSLOT], *d_o[HS_NSLOT];
+    size_t cap_1[HS_NSLOT], cap_2[HS_NSLOT], cap_o[HS_NSLOT];
     struct conv_plans *next;
 } conv_plans;
 
@@ -51,15 +55,24 @@ static conv_plans *c_head = NULL;
 
 static conv_plans *plans_for(int P)
 {
+    hs_cu_require_device();
+    const int dev = hs_cu_get_device();
     pthread_mutex_lock(&c_lock);
     conv_plans *c = c_head;
-    while (c && c->P != P) c = c->next;
+    while (c && !(c->P == P && c->device == dev)) c = c->next;
     if (!c) {
         c = (conv_plans *)calloc(1, sizeof(*c));
         if (!c) { fprintf(stderr, "Error: Memory allocation failed\n"); exit(EXIT_FAILURE); }
+        pthread_mutexattr_t at;
+        pthread_mutexattr_init(&at);
+        pthread_mutexattr_settype(&at, PTHREAD_MUTEX_RECURSIVE);
+        pthread_mutex_init(&c->lock, &at);
+        pthread_mutexattr_destroy(&at);
         c->P = P;
+        c->device = dev;
         c->fwd = fft_real_init(P, 1);
         c->inv = fft_real_init(P, -1);
+        for (int s = 0; s < HS_NSLOT; ++s) c->stream[s] = hs_cu_stream_create();
         c->next = c_head;
         c_head = c;
     }
@@ -126,47 +139,75 @@ int fft_convolve_batch_dev(const char *type, const char *conv_type, const fft_ty
     if (n <= 0 || howmany <= 0) return n;
     conv_plans *c = plans_for(P);
     const size_t H1 = (size_t)P / 2 + 1;
-    if (c->cap_AB < sizeof(fft_data) * H1 * howmany) {
-        hs_cu_free(c->d_A); hs_cu_free(c->d_B);
-        c->cap_AB = sizeof(fft_data) * H1 * howmany;
-        c->d_A = hs_cu_malloc(c->cap_AB);
-        c->d_B = hs_cu_malloc(c->cap_AB);
-    }
-    /* long convolutions: padding, product, scale and slice ride on the transforms' own loads and stores (8 launches,
+    pthread_mutex_lock(&c->lock);
+    fft_data *dA = (fft_data *)hs_scratch_get(&c->A, stream, sizeof(fft_data) * H1 * howmany);
+    fft_data *dB = (fft_data *)hs_scratch_get(&c->B, stream, sizeof(fft_data) * H1 * howmany);
+    /* long convolutions: padding, product, scale and slice ride on the transforms' own loads and stores (6 launches,
      * about two thirds of the HBM traffic of the unfused sequence below) */
-    if (hs_real_r2c_padded_dev(c->fwd, d_in1, length1, length1, 0, (long long)length1 * howmany, (fft_data *)c->d_A, (long)H1, howmany, stream)) {
-        if (!hs_real_r2c_padded_dev(c->fwd, d_in2, length2, length2, 0, (long long)length2 * howmany, (fft_data *)c->d_B, (long)H1, howmany,
-                                    stream) ||
-            !hs_real_c2r_mul_slice_dev(c->inv, (const fft_data *)c->d_A, (const fft_data *)c->d_B, (long)H1, (long)H1, 1.0 / P, d_out, out_stride,
+    if (hs_real_r2c_padded_dev(c->fwd, d_in1, length1, length1, 0, (long long)length1 * howmany, dA, (long)H1, howmany, stream)) {
+        if (!hs_real_r2c_padded_dev(c->fwd, d_in2, length2, length2, 0, (long long)length2 * howmany, dB, (long)H1, howmany, stream) ||
+            !hs_real_c2r_mul_slice_dev(c->inv, dA, dB, (long)H1, (long)H1, 1.0 / P, d_out, out_stride,
                                        (long long)out_stride * (howmany - 1) + n, start, n, howmany, stream)) {
             fprintf(stderr, "Error: fused convolution path became unavailable\n");
             exit(EXIT_FAILURE);
         }
+        pthread_mutex_unlock(&c->lock);
         return n;
     }
-    if (c->cap_ab < sizeof(fft_type) * (size_t)P * howmany) {
-        hs_cu_free(c->d_a); hs_cu_free(c->d_b);
-        c->cap_ab = sizeof(fft_type) * (size_t)P * howmany;
-        c->d_a = hs_cu_malloc(c->cap_ab);
-        c->d_b = hs_cu_malloc(c->cap_ab);
-    }
-    if (c->cap_AB < sizeof(fft_data) * H1 * howmany) {
-        hs_cu_free(c->d_A); hs_cu_free(c->d_B);
-        c->cap_AB = sizeof(fft_data) * H1 * howmany;
-        c->d_A = hs_cu_malloc(c->cap_AB);
-        c->d_B = hs_cu_malloc(c->cap_AB);
-    }
-    grow(&c->d_res, &c->cap_res, sizeof(fft_type) * (size_t)P * howmany);
+    fft_type *da = (fft_type *)hs_scratch_get(&c->a, stream, sizeof(fft_type) * (size_t)P * howmany);
+    fft_type *db = (fft_type *)hs_scratch_get(&c->b, stream, sizeof(fft_type) * (size_t)P * howmany);
+    fft_type *dres = (fft_type *)hs_scratch_get(&c->res, stream, sizeof(fft_type) * (size_t)P * howmany);
     /* zero-pad -> r2c x2 (half spectra) -> product * 1/P -> c2r -> slice */
-    hs_cu_launch_pad_rows(d_in1, length1, c->d_a, P, howmany, stream);
-    hs_cu_launch_pad_rows(d_in2, length2, c->d_b, P, howmany, stream);
-    fft_r2c_exec_batch_dev(c->fwd, (const fft_type *)c->d_a, (fft_data *)c->d_A, (long)H1, 0, howmany, stream);
-    /* the real plan keeps one scratch set per stream slot; the two transforms share it in order */
-    fft_r2c_exec_batch_dev(c->fwd, (const fft_type *)c->d_b, (fft_data *)c->d_B, (long)H1, 0, howmany, stream);
-    hs_cu_launch_conv_mul(c->d_A, c->d_B, c->d_A, (long long)(H1 * howmany), 1.0 / P, stream);
-    fft_c2r_exec_batch_dev(c->inv, (const fft_data *)c->d_A, (long)H1, (fft_type *)c->d_res, howmany, stream);
-    hs_cu_launch_slice_rows(c->d_res, P, start, n, d_out, out_stride, howmany, stream);
+    hs_cu_launch_pad_rows(d_in1, length1, da, P, howmany, stream);
+    hs_cu_launch_pad_rows(d_in2, length2, db, P, howmany, stream);
+    fft_r2c_exec_batch_dev(c->fwd, da, dA, (long)H1, 0, howmany, stream);
+    fft_r2c_exec_batch_dev(c->fwd, db, dB, (long)H1, 0, howmany, stream);
+    hs_cu_launch_conv_mul(dA, dB, dA, (long long)(H1 * howmany), 1.0 / P, stream);
+    fft_c2r_exec_batch_dev(c->inv, dA, (long)H1, dres, howmany, stream);
+    hs_cu_launch_slice_rows(dres, P, start, n, d_out, out_stride, howmany, stream);
+    pthread_mutex_unlock(&c->lock);
     return n;
+}
+
+typedef struct conv_ctx {
+    const char *type, *conv_type;
+    fft_type *in1, *in2, *out;
+    int length1, length2, P, n;
+    long out_stride;
+} conv_ctx;
+
+/* one device's share of a host-pointer batch: three slots on the cache entry's own streams, so that the copies of chunk
+ * i+1 and i-1 overlap the kernels of chunk i; staging buffers persist across calls (no allocation per call) */
+static void convolve_batch_one_device(void *vctx, long first0, long howmany)
+{
+    conv_ctx *x = (conv_ctx *)vctx;
+    if (howmany <= 0) return;
+    conv_plans *c = plans_for(x->P);
+    pthread_mutex_lock(&c->lock);
+    const int l1 = x->length1, l2 = x->length2, n = x->n;
+    /* chunk so that the device scratch (about 5 P-sized rows per convolution) stays bounded */
+    long chunk = (long)(((size_t)128 << 20) / (sizeof(fft_type) * (size_t)x->P * 5));
+    if (chunk < 1) chunk = 1;
+    if (chunk > howmany) chunk = howmany;
+    const long nchunk = (howmany + chunk - 1) / chunk;
+    fft_type *in1 = x->in1 + (size_t)first0 * l1, *in2 = x->in2 + (size_t)first0 * l2, *out = x->out + (size_t)first0 * x->out_stride;
+    for (long i = 0; i < nchunk; ++i) {
+        const int s = (int)(i % HS_NSLOT);
+        const long first = i * chunk, cnt = (first + chunk <= howmany) ? chunk : howmany - first;
+        if (i < HS_NSLOT) {
+            grow(&c->d_1[s], &c->cap_1[s], sizeof(fft_type) * (size_t)l1 * chunk);
+            grow(&c->d_2[s], &c->cap_2[s], sizeof(fft_type) * (size_t)l2 * chunk);
+            grow(&c->d_o[s], &c->cap_o[s], sizeof(fft_type) * (size_t)n * chunk);
+        }
+        hs_cu_h2d(c->d_1[s], in1 + first * l1, sizeof(fft_type) * (size_t)l1 * cnt, c->stream[s]);
+        hs_cu_h2d(c->d_2[s], in2 + first * l2, sizeof(fft_type) * (size_t)l2 * cnt, c->stream[s]);
+        fft_convolve_batch_dev(x->type, x->conv_type, (const fft_type *)c->d_1[s], l1, (const fft_type *)c->d_2[s], l2, (fft_type *)c->d_o[s], n,
+                               cnt, c->stream[s]);
+        hs_cu_d2h_2d(out + first * x->out_stride, sizeof(fft_type) * (size_t)x->out_stride, c->d_o[s], sizeof(fft_type) * (size_t)n,
+                     sizeof(fft_type) * (size_t)n, (size_t)cnt, c->stream[s]);
+    }
+    for (int s = 0; s < HS_NSLOT; ++s) hs_cu_stream_sync(c->stream[s]);
+    pthread_mutex_unlock(&c->lock);
 }
 
 int fft_convolve_batch(const char *type, const char *conv_type, fft_type *input1, int length1, fft_type *input2, int length2,
@@ -176,26 +217,8 @@ int fft_convolve_batch(const char *type, const char *conv_type, fft_type *input1
     const int n = conv_setup(type, conv_type, input1, length1, input2, length2, output, &P, &start, &linear);
     if (n <= 0 || howmany <= 0) return n;
     hs_cu_require_device();
-    /* chunk so that the device scratch (about 5 P-sized rows per convolution) stays bounded */
-    long chunk = (long)(((size_t)256 << 20) / (sizeof(fft_type) * (size_t)P * 5));
-    if (chunk < 1) chunk = 1;
-    if (chunk > howmany) chunk = howmany;
-    void *d1 = hs_cu_malloc(sizeof(fft_type) * (size_t)length1 * chunk);
-    void *d2 = hs_cu_malloc(sizeof(fft_type) * (size_t)length2 * chunk);
-    void *dout = hs_cu_malloc(sizeof(fft_type) * (size_t)n * chunk);
-    for (long first = 0; first < howmany; first += chunk) {
-        const long cnt = (first + chunk <= howmany) ? chunk : howmany - first;
-        hs_cu_h2d(d1, input1 + first * length1, sizeof(fft_type) * (size_t)length1 * cnt, NULL);
-        hs_cu_h2d(d2, input2 + first * length2, sizeof(fft_type) * (size_t)length2 * cnt, NULL);
-        fft_convolve_batch_dev(type, conv_type, (const fft_type *)d1, length1, (const fft_type *)d2, length2, (fft_type *)dout, n, cnt,
-                               NULL);
-        if (out_stride == n) hs_cu_d2h(output + first * out_stride, dout, sizeof(fft_type) * (size_t)n * cnt, NULL);
-        else
-            for (long i = 0; i < cnt; ++i)
-                hs_cu_d2h(output + (first + i) * out_stride, (fft_type *)dout + i * n, sizeof(fft_type) * (size_t)n, NULL);
-    }
-    hs_cu_stream_sync(NULL);
-    hs_cu_free(d1); hs_cu_free(d2); hs_cu_free(dout);
+    conv_ctx x = {type, conv_type, input1, input2, output, length1, length2, P, n, out_stride};
+    hs_shard_run(howmany, convolve_batch_one_device, &x);
     return n;
 }
 
@@ -234,23 +257,21 @@ long fft_convolve_stream_dev(const fft_type *d_x, long Lx, const fft_type *d_h, 
     long chunk = (long)(((size_t)512 << 20) / (sizeof(fft_data) * H1)); /* spectra of a chunk of windows: at most 512 MiB */
     if (chunk < 1) chunk = 1;
     if (chunk > nblocks) chunk = nblocks;
-    if (c->cap_AB < sizeof(fft_data) * H1 * (size_t)chunk) {
-        hs_cu_free(c->d_A); hs_cu_free(c->d_B);
-        c->cap_AB = sizeof(fft_data) * H1 * (size_t)chunk;
-        c->d_A = hs_cu_malloc(c->cap_AB);
-        c->d_B = hs_cu_malloc(c->cap_AB);
-    }
-    if (!hs_real_r2c_padded_dev(c->fwd, d_h, Lh, Lh, 0, Lh, (fft_data *)c->d_B, (long)H1, 1, stream)) {
+    pthread_mutex_lock(&c->lock);
+    fft_data *dA = (fft_data *)hs_scratch_get(&c->A, stream, sizeof(fft_data) * H1 * (size_t)chunk);
+    fft_data *dB = (fft_data *)hs_scratch_get(&c->B, stream, sizeof(fft_data) * H1);
+    if (!hs_real_r2c_padded_dev(c->fwd, d_h, Lh, Lh, 0, Lh, dB, (long)H1, 1, stream)) {
         fprintf(stderr, "Error: fft_convolve_stream: no fused transform for P = %d\n", P);
+        pthread_mutex_unlock(&c->lock);
         return -1;
     }
     for (long b0 = 0; b0 < nblocks; b0 += chunk) {
         const long cnt = (b0 + chunk <= nblocks) ? chunk : nblocks - b0;
         /* window b0 + i starts at signal index (b0 + i) * S - (Lh - 1) */
-        hs_real_r2c_padded_dev(c->fwd, d_x, P, S, b0 * S - (Lh - 1), Lx, (fft_data *)c->d_A, (long)H1, cnt, stream);
-        hs_real_c2r_mul_slice_dev(c->inv, (const fft_data *)c->d_A, (const fft_data *)c->d_B, (long)H1, 0, 1.0 / P, d_y + b0 * S, S, total - b0 * S,
-                                  Lh - 1, (int)S, cnt, stream);
+        hs_real_r2c_padded_dev(c->fwd, d_x, P, S, b0 * S - (Lh - 1), Lx, dA, (long)H1, cnt, stream);
+        hs_real_c2r_mul_slice_dev(c->inv, dA, dB, (long)H1, 0, 1.0 / P, d_y + b0 * S, S, total - b0 * S, Lh - 1, (int)S, cnt, stream);
     }
+    pthread_mutex_unlock(&c->lock);
     return total;
 }
 

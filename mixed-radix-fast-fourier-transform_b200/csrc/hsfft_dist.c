@@ -91,6 +91,10 @@ static void axis_init(hs_axis *ax, int L, int sgn)
         exit(EXIT_FAILURE);
     }
     const hs_ct_desc *s1 = find_family(HS_CT_SUB, t->n1), *s2 = find_family(HS_CT_SUB, t->n2);
+    if (!s1 || !s2) {
+        fprintf(stderr, "Error: distributed transform: no tiled sub-plan for the factors %d x %d of axis length %d\n", t->n1, t->n2, L);
+        exit(EXIT_FAILURE);
+    }
     ax->two = 1;
     ax->n1 = t->n1; ax->n2 = t->n2;
     ax->sub1 = s1->id; ax->sub2 = s2->id;
@@ -173,9 +177,9 @@ void hsfft_ipc_get_handle(void *d_buf, void *handle64) { hs_cu_require_device();
 
 void hsfft_dist_set_peers(hsfft_dist_object d, void *d_own_r, const void *handles64, int nhandles)
 {
-    /* handles64: nranks handles of 64 bytes, ordered by rank (the own slot is ignored: d_own_r is used);
-     * handles64 == NULL: every "peer" is d_own_r's process -- pointers are passed instead (tests, one process) */
-    if (!d || !d_own_r || nhandles != d->nranks || d->nranks > HS_DIST_MAX_RANKS) {
+    /* handles64: nranks handles of 64 bytes, ordered by rank (the own slot is ignored: d_own_r is used).  Buffers that are
+     * already addressable from this process go through hsfft_dist_set_peer_pointers instead. */
+    if (!d || !d_own_r || !handles64 || nhandles != d->nranks || d->nranks > HS_DIST_MAX_RANKS) {
         fprintf(stderr, "Error: Invalid inputs for hsfft_dist_set_peers\n");
         exit(EXIT_FAILURE);
     }
@@ -326,4 +330,64 @@ void hsfft_dist_rows_dev(hsfft_dist_object d, const fft_data *d_r, fft_data *d_o
     g.ncols = (int)L1; g.in_xf = N2; g.in_c = 1; g.in_e = L1; g.out_xf = N2; g.out_c = 1; g.out_e = L1;
     g.twb = ax->d_twb; g.tws = ax->d_tws; g.tw_ld = (int)L1;
     hs_cu_launch_tiled(ax->sub2, d->sgn, 1, 1, d_ws, d_out, ax->d_tw2, &g, Kw, stream);
+}
+
+/* ---- the whole four-step from ONE process driving `ndev` GPUs (devices 0 .. ndev-1): host pointers, natural order in
+ * and out.  The self-contained C entry for a single huge transform (north_star config 5) -- no launcher, no handle
+ * exchange: the devices map each other's receive buffers through peer access, phase A's transform kernel stores every
+ * twiddled row straight into its owner over NVLink, one synchronisation of the devices is the barrier, phase B runs
+ * the rows.  inp[N1*N2] -> oup[N1*N2], unnormalised, sgn as in fft_init.  Returns 0, or -1 when the devices cannot
+ * reach each other's memory.  (Many processes: hsfft_dist_init .. hsfft_dist_rows_dev above, with the caller's transport.) */
+int fft_exec_dist(int N1, int N2, int sgn, const fft_data *inp, fft_data *oup, int ndev)
+{
+    hs_cu_require_device();
+    if (!inp || !oup || ndev < 1 || ndev > HS_DIST_MAX_RANKS || ndev > hs_cu_device_count()) {
+        fprintf(stderr, "Error: Invalid inputs for fft_exec_dist - devices: %d (of %d)\n", ndev, hs_cu_device_count());
+        exit(EXIT_FAILURE);
+    }
+    for (int g = 0; g < ndev; ++g)
+        for (int p = 0; p < ndev; ++p)
+            if (g != p && !hs_cu_can_access_peer(g, p)) {
+                fprintf(stderr, "Error: fft_exec_dist: device %d cannot access device %d's memory\n", g, p);
+                return -1;
+            }
+    const int home = hs_cu_get_device();
+    hsfft_dist_object plan[HS_DIST_MAX_RANKS];
+    void *a[HS_DIST_MAX_RANKS], *r[HS_DIST_MAX_RANKS], *ws[HS_DIST_MAX_RANKS], *o[HS_DIST_MAX_RANKS], *st[HS_DIST_MAX_RANKS];
+    const long long Cw = N2 / ndev, Kw = N1 / ndev;
+    const size_t slab = sizeof(fft_data) * (size_t)N1 * (size_t)Cw;
+    for (int g = 0; g < ndev; ++g) {
+        hs_cu_set_device(g);
+        for (int p = 0; p < ndev; ++p)
+            if (p != g) hs_cu_enable_peer_access(p);
+        plan[g] = hsfft_dist_init(N1, N2, ndev, g, sgn);
+        a[g] = hs_cu_malloc(slab); r[g] = hs_cu_malloc(slab); ws[g] = hs_cu_malloc(slab); o[g] = hs_cu_malloc(slab);
+        st[g] = hs_cu_stream_create();
+    }
+    for (int g = 0; g < ndev; ++g) {
+        hs_cu_set_device(g);
+        hsfft_dist_set_peer_pointers(plan[g], r, ndev);
+        /* column slab a[n1][c] = x[N2 n1 + g Cw + c] */
+        hs_cu_h2d_2d(a[g], sizeof(fft_data) * (size_t)Cw, inp + (size_t)g * Cw, sizeof(fft_data) * (size_t)N2, sizeof(fft_data) * (size_t)Cw,
+                     (size_t)N1, st[g]);
+        hsfft_dist_cols_exchange_dev(plan[g], (const fft_data *)a[g], (fft_data *)ws[g], st[g]);
+    }
+    for (int g = 0; g < ndev; ++g) { hs_cu_set_device(g); hs_cu_stream_sync(st[g]); } /* every rank's peer stores have landed */
+    for (int g = 0; g < ndev; ++g) {
+        hs_cu_set_device(g);
+        hsfft_dist_rows_dev(plan[g], (const fft_data *)r[g], (fft_data *)o[g], (fft_data *)ws[g], st[g]);
+        /* out[k1l][k2] = X[(g Kw + k1l) + N1 k2]  ->  [k2][k1l], then rows of Kw bins into the natural-order array */
+        hs_cu_launch_transpose(o[g], a[g], (int)Kw, N2, 1, st[g]);
+        hs_cu_d2h_2d(oup + (size_t)g * Kw, sizeof(fft_data) * (size_t)N1, a[g], sizeof(fft_data) * (size_t)Kw, sizeof(fft_data) * (size_t)Kw,
+                     (size_t)N2, st[g]);
+    }
+    for (int g = 0; g < ndev; ++g) {
+        hs_cu_set_device(g);
+        hs_cu_stream_sync(st[g]);
+        hsfft_dist_free(plan[g]);
+        hs_cu_free(a[g]); hs_cu_free(r[g]); hs_cu_free(ws[g]); hs_cu_free(o[g]);
+        hs_cu_stream_destroy(st[g]);
+    }
+    hs_cu_set_device(home);
+    return 0;
 }

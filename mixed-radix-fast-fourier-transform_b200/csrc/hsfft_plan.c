@@ -558,6 +558,7 @@ static hs_dev_obj *g_head = NULL;
 
 static void dev_free_contents(hs_dev_obj *d)
 {
+    hs_scratch_free(&d->ws_pool);
     hs_c2c_destroy(d->direct);
     hs_c2c_destroy(d->fwdM);
     hs_c2c_destroy(d->invM);
@@ -768,23 +769,70 @@ static void dev_build(hs_dev_obj *d, fft_object plan)
     }
 }
 
+void *hs_scratch_get(hs_scratch *s, void *stream, size_t bytes)
+{
+    int k = 0;
+    while (k < s->used && s->stream[k] != stream) ++k;
+    if (k == s->used) {
+        if (s->used == HS_SCRATCH_MAX) { /* more caller streams than slots: quiesce the device and start over */
+            hs_cu_device_sync();
+            hs_scratch_free(s);
+            k = 0;
+        }
+        s->stream[k] = stream; s->buf[k] = NULL; s->cap[k] = 0;
+        s->used = k + 1;
+    }
+    if (bytes > s->cap[k]) {
+        hs_cu_free_async(s->buf[k], stream);
+        s->buf[k] = hs_cu_malloc_async(bytes, stream);
+        s->cap[k] = bytes;
+    }
+    return s->buf[k];
+}
+
+void hs_scratch_free(hs_scratch *s)
+{
+    for (int k = 0; k < s->used; ++k) hs_cu_free(s->buf[k]);
+    memset(s, 0, sizeof *s);
+}
+
+/* a plan that was free()d directly and whose address came back with other fields, or whose public struct was edited:
+ * every device's state under that address is stale */
+static void dev_drop_key_locked(const void *key)
+{
+    hs_dev_obj **pp = &g_head;
+    while (*pp) {
+        hs_dev_obj *d = *pp;
+        if (d->key == key) {
+            *pp = d->next;
+            dev_free_contents(d);
+            pthread_mutex_destroy(&d->lock);
+            free(d);
+        } else pp = &d->next;
+    }
+}
+
 hs_dev_obj *hs_dev_get(fft_object plan)
 {
     if (plan == NULL) { fprintf(stderr, "Error: Invalid FFT object or data pointers\n"); exit(EXIT_FAILURE); }
     hs_cu_require_device();
+    const int dev = hs_cu_get_device();
     pthread_mutex_lock(&g_lock);
     hs_dev_obj *d = g_head;
-    while (d && d->key != plan) d = d->next;
+    while (d && !(d->key == plan && d->device == dev)) d = d->next;
     if (d && (d->N != plan->N || d->sgn != plan->sgn || d->lt != plan->lt)) {
-        /* the block was free()d and re-used, or the caller edited the public struct: rebuild */
-        hs_dev_obj *nx = d->next;
-        dev_free_contents(d);
-        memset(d, 0, sizeof(*d));
-        d->next = nx;
-        dev_build(d, plan);
-    } else if (!d) {
+        dev_drop_key_locked(plan);
+        d = NULL;
+    }
+    if (!d) {
         d = (hs_dev_obj *)calloc(1, sizeof(hs_dev_obj));
         if (!d) { fprintf(stderr, "Error: Memory allocation failed for device plan\n"); exit(EXIT_FAILURE); }
+        pthread_mutexattr_t at;
+        pthread_mutexattr_init(&at);
+        pthread_mutexattr_settype(&at, PTHREAD_MUTEX_RECURSIVE);
+        pthread_mutex_init(&d->lock, &at);
+        pthread_mutexattr_destroy(&at);
+        d->device = dev;
         dev_build(d, plan);
         d->next = g_head;
         g_head = d;
@@ -793,17 +841,13 @@ hs_dev_obj *hs_dev_get(fft_object plan)
     return d;
 }
 
+void hs_dev_lock(hs_dev_obj *d) { pthread_mutex_lock(&d->lock); }
+void hs_dev_unlock(hs_dev_obj *d) { pthread_mutex_unlock(&d->lock); }
+
 void hs_dev_release(const void *key)
 {
     pthread_mutex_lock(&g_lock);
-    hs_dev_obj **pp = &g_head;
-    while (*pp && (*pp)->key != key) pp = &(*pp)->next;
-    if (*pp) {
-        hs_dev_obj *d = *pp;
-        *pp = d->next;
-        dev_free_contents(d);
-        free(d);
-    }
+    dev_drop_key_locked(key);
     pthread_mutex_unlock(&g_lock);
 }
 
@@ -821,6 +865,50 @@ void hs_dev_reserve(hs_dev_obj *d, int slot, size_t in_bytes, size_t out_bytes, 
     grow(&d->d_out[slot], &d->cap_out[slot], out_bytes);
     grow(&d->d_ws[slot], &d->cap_ws[slot], ws_bytes);
     grow(&d->d_ws2[slot], &d->cap_ws2[slot], ws2_bytes);
+}
+
+/* ----------------------------------------------------------------------------- multi-device sharding */
+
+static int g_ndev = 1; /* hsfft_set_devices: the host-pointer batch calls shard their batch over devices 0 .. g_ndev-1 */
+
+void hsfft_set_devices(int n)
+{
+    const int have = hs_cu_device_count();
+    if (n < 1) n = 1;
+    if (n > have) n = have > 0 ? have : 1;
+    g_ndev = n;
+}
+int hsfft_get_devices(void) { return g_ndev; }
+
+typedef struct shard_job { hs_shard_fn fn; void *ctx; long first, count; int dev; } shard_job;
+static void *shard_thread(void *arg)
+{
+    shard_job *j = (shard_job *)arg;
+    hs_cu_set_device(j->dev);
+    j->fn(j->ctx, j->first, j->count);
+    return NULL;
+}
+
+void hs_shard_run(long howmany, hs_shard_fn fn, void *ctx)
+{
+    const int nd = g_ndev;
+    if (nd <= 1 || howmany < 2L * nd) { fn(ctx, 0, howmany); return; }
+    /* contiguous batch ranges, one host thread per device (no communication) */
+    shard_job job[64];
+    pthread_t th[64];
+    const int n = nd > 64 ? 64 : nd;
+    const int home = hs_cu_get_device();
+    long first = 0;
+    for (int g = 0; g < n; ++g) {
+        const long cnt = howmany / n + (g < howmany % n ? 1 : 0);
+        job[g].fn = fn; job[g].ctx = ctx; job[g].first = first; job[g].count = cnt; job[g].dev = g;
+        first += cnt;
+    }
+    for (int g = 1; g < n; ++g)
+        if (pthread_create(&th[g], NULL, shard_thread, &job[g]) != 0) { fprintf(stderr, "Error: cannot start a device thread\n"); exit(EXIT_FAILURE); }
+    shard_thread(&job[0]);
+    for (int g = 1; g < n; ++g) pthread_join(th[g], NULL);
+    hs_cu_set_device(home);
 }
 
 size_t hs_dev_ws_bytes(const hs_dev_obj *d, long long howmany)
@@ -1029,6 +1117,34 @@ static long long chunk_len(long long howmany, size_t bytes_per_xf)
     return c;
 }
 
+typedef struct exec_ctx { fft_object obj; fft_data *inp, *oup; } exec_ctx;
+
+/* one device's share of a host-pointer batch: chunked three-deep pipeline on the plan's own streams, H2D(i+1) and D2H(i-1)
+ * overlap the kernels of chunk i.  The plan's staging buffers are in use until the last copy has landed, so the whole
+ * call holds the (plan, device) lock: concurrent callers of one plan serialise instead of overwriting each other. */
+static void exec_batch_one_device(void *vctx, long first0, long howmany)
+{
+    exec_ctx *c = (exec_ctx *)vctx;
+    if (howmany <= 0) return;
+    hs_dev_obj *d = hs_dev_get(c->obj);
+    hs_dev_lock(d);
+    const size_t row = sizeof(fft_data) * (size_t)d->N;
+    const long long chunk = chunk_len(howmany, row);
+    const long long nchunk = (howmany + chunk - 1) / chunk;
+    const int nslot = nchunk < HS_NSLOT ? (int)nchunk : HS_NSLOT;
+    fft_data *inp = c->inp + (size_t)first0 * d->N, *oup = c->oup + (size_t)first0 * d->N;
+    for (int s = 0; s < nslot; ++s) hs_dev_reserve(d, s, row * chunk, row * chunk, hs_dev_ws_bytes(d, chunk), 0);
+    for (long long i = 0; i < nchunk; ++i) {
+        const int s = (int)(i % HS_NSLOT);
+        const long long first = i * chunk, cnt = (first + chunk <= howmany) ? chunk : howmany - first;
+        hs_cu_h2d(d->d_in[s], inp + first * d->N, row * cnt, d->stream[s]);
+        hs_dev_exec(d, d->d_in[s], d->d_out[s], d->d_ws[s], cnt, d->stream[s]);
+        hs_cu_d2h(oup + first * d->N, d->d_out[s], row * cnt, d->stream[s]);
+    }
+    for (int s = 0; s < nslot; ++s) hs_cu_stream_sync(d->stream[s]);
+    hs_dev_unlock(d);
+}
+
 void fft_exec_batch(fft_object obj, fft_data *inp, fft_data *oup, long howmany)
 {
     if (obj == NULL || inp == NULL || oup == NULL) {
@@ -1040,21 +1156,8 @@ void fft_exec_batch(fft_object obj, fft_data *inp, fft_data *oup, long howmany)
         exit(EXIT_FAILURE);
     }
     if (howmany <= 0) return;
-    hs_dev_obj *d = hs_dev_get(obj);
-    const size_t row = sizeof(fft_data) * (size_t)d->N;
-    const long long chunk = chunk_len(howmany, row);
-    const long long nchunk = (howmany + chunk - 1) / chunk;
-    const int nslot = nchunk < HS_NSLOT ? (int)nchunk : HS_NSLOT;
-    for (int s = 0; s < nslot; ++s) hs_dev_reserve(d, s, row * chunk, row * chunk, hs_dev_ws_bytes(d, chunk), 0);
-    /* chunked three-deep pipeline: H2D(i+1) and D2H(i-1) overlap the kernels of chunk i */
-    for (long long i = 0; i < nchunk; ++i) {
-        const int s = (int)(i % HS_NSLOT);
-        const long long first = i * chunk, cnt = (first + chunk <= howmany) ? chunk : howmany - first;
-        hs_cu_h2d(d->d_in[s], inp + first * d->N, row * cnt, d->stream[s]);
-        hs_dev_exec(d, d->d_in[s], d->d_out[s], d->d_ws[s], cnt, d->stream[s]);
-        hs_cu_d2h(oup + first * d->N, d->d_out[s], row * cnt, d->stream[s]);
-    }
-    for (int s = 0; s < nslot; ++s) hs_cu_stream_sync(d->stream[s]);
+    exec_ctx c = {obj, inp, oup};
+    hs_shard_run(howmany, exec_batch_one_device, &c); /* one device unless hsfft_set_devices(n > 1) */
 }
 
 void fft_exec(fft_object obj, fft_data *inp, fft_data *oup)
@@ -1068,10 +1171,16 @@ void fft_exec_batch_dev(fft_object obj, const fft_data *d_in, fft_data *d_out, l
         fprintf(stderr, "Error: Invalid FFT object or data pointers\n");
         exit(EXIT_FAILURE);
     }
+    if ((const void *)d_in == (const void *)d_out) { /* like the reference, every transform here is out of place */
+        fprintf(stderr, "Error: fft_exec_batch_dev is out of place: input and output must not be the same buffer\n");
+        exit(EXIT_FAILURE);
+    }
     if (howmany <= 0) return;
     hs_dev_obj *d = hs_dev_get(obj);
-    hs_dev_reserve(d, 0, 0, 0, hs_dev_ws_bytes(d, howmany), 0);
-    hs_dev_exec(d, d_in, d_out, d->d_ws[0], howmany, stream);
+    hs_dev_lock(d);
+    void *ws = hs_scratch_get(&d->ws_pool, stream, hs_dev_ws_bytes(d, howmany));
+    hs_dev_exec(d, d_in, d_out, ws, howmany, stream);
+    hs_dev_unlock(d);
 }
 
 void free_fft(fft_object object)
@@ -1099,7 +1208,7 @@ const char *hsfft_version(void) { return "hsfft-b200 0.1 (sm_100a)"; }
 
 const char *hsfft_plan_describe(fft_object obj)
 {
-    static char buf[512];
+    static __thread char buf[512]; /* one buffer per calling thread */
     if (!obj) return "null plan";
     hs_dev_obj *d = hs_dev_get(obj);
     int n = 0;

@@ -18,6 +18,9 @@
 /* device state of a real plan: twiddle2 in HBM, keyed by the real plan's address */
 typedef struct hs_real_dev {
     const void *key;
+    int device;            /* one entry per (real plan, device) */
+    pthread_mutex_t lock;  /* execute calls on one (plan, device) serialise on it */
+    hs_scratch z_pool, ws_pool; /* device-pointer calls: intermediates per caller stream */
     int H;
     void *d_tw2;
     /* real four-step (N = n1 n2, both with a tiled sub-plan; forward plans): see hs_tiled.cuh */
@@ -34,6 +37,7 @@ static hs_real_dev *r_head = NULL;
 
 static void real_dev_clear(hs_real_dev *r)
 {
+    hs_scratch_free(&r->z_pool); hs_scratch_free(&r->ws_pool);
     hs_cu_free(r->d_tw2);
     hs_cu_free(r->d_r4_tw1); hs_cu_free(r->d_r4_tw2); hs_cu_free(r->d_r4_twb); hs_cu_free(r->d_r4_tws);
     for (int s = 0; s < HS_NSLOT; ++s) {
@@ -73,33 +77,48 @@ static void real_fourstep_setup(fft_real_object obj, hs_real_dev *r)
 /* complex elements of the per-transform intermediate (half-length spectrum, or the four-step's padded rows) */
 static size_t real_z_elems(const hs_real_dev *r) { return r->r4 ? (size_t)r->r4_n2 * r->r4_ld : (size_t)r->H; }
 
+static void real_drop_key_locked(const void *key)
+{
+    hs_real_dev **pp = &r_head;
+    while (*pp) {
+        hs_real_dev *r = *pp;
+        if (r->key == key) {
+            *pp = r->next;
+            real_dev_clear(r);
+            pthread_mutex_destroy(&r->lock);
+            free(r);
+        } else pp = &r->next;
+    }
+}
+
 static hs_real_dev *real_dev_get(fft_real_object obj)
 {
     hs_cu_require_device();
-    const int H = obj->cobj->N;
+    const int H = obj->cobj->N, dev = hs_cu_get_device();
     pthread_mutex_lock(&r_lock);
     hs_real_dev *r = r_head;
-    while (r && r->key != obj) r = r->next;
+    while (r && !(r->key == obj && r->device == dev)) r = r->next;
     if (r && r->H != H) { /* address re-used by a different plan */
-        hs_real_dev *nx = r->next;
-        real_dev_clear(r);
-        memset(r, 0, sizeof(*r));
-        r->next = nx;
-        r->key = NULL;
+        real_drop_key_locked(obj);
+        r = NULL;
     }
     if (!r) {
         r = (hs_real_dev *)calloc(1, sizeof(*r));
         if (!r) { fprintf(stderr, "Error: Memory allocation failed for real FFT object\n"); exit(EXIT_FAILURE); }
-        r->next = r_head;
-        r_head = r;
-    }
-    if (r->key == NULL) {
+        pthread_mutexattr_t at;
+        pthread_mutexattr_init(&at);
+        pthread_mutexattr_settype(&at, PTHREAD_MUTEX_RECURSIVE);
+        pthread_mutex_init(&r->lock, &at);
+        pthread_mutexattr_destroy(&at);
         r->key = obj;
+        r->device = dev;
         r->H = H;
         r->d_tw2 = hs_cu_malloc(sizeof(fft_data) * (size_t)H);
         hs_cu_h2d(r->d_tw2, obj->twiddle2, sizeof(fft_data) * (size_t)H, NULL);
         for (int s = 0; s < HS_NSLOT; ++s) r->stream[s] = hs_cu_stream_create();
         real_fourstep_setup(obj, r);
+        r->next = r_head;
+        r_head = r;
     }
     pthread_mutex_unlock(&r_lock);
     return r;
@@ -108,14 +127,7 @@ static hs_real_dev *real_dev_get(fft_real_object obj)
 static void real_dev_release(const void *key)
 {
     pthread_mutex_lock(&r_lock);
-    hs_real_dev **pp = &r_head;
-    while (*pp && (*pp)->key != key) pp = &(*pp)->next;
-    if (*pp) {
-        hs_real_dev *r = *pp;
-        *pp = r->next;
-        real_dev_clear(r);
-        free(r);
-    }
+    real_drop_key_locked(key);
     pthread_mutex_unlock(&r_lock);
 }
 
@@ -206,10 +218,13 @@ void fft_r2c_exec_batch_dev(fft_real_object obj, const fft_type *d_in, fft_data 
         fprintf(stderr, "Error: r2c output stride %ld too small for N = %d\n", out_stride, 2 * r->H);
         exit(EXIT_FAILURE);
     }
+    if ((const void *)d_in == (const void *)d_out) { fprintf(stderr, "Error: fft_r2c_exec_batch_dev is out of place\n"); exit(EXIT_FAILURE); }
     hs_dev_obj *c = hs_dev_get(obj->cobj);
-    grow(&r->d_z[0], &r->cap_z[0], sizeof(fft_data) * (size_t)howmany * real_z_elems(r));
-    grow(&r->d_ws[0], &r->cap_ws[0], hs_dev_ws_bytes(c, howmany));
-    r2c_dev(obj, r, d_in, d_out, out_stride, full, r->d_z[0], r->d_ws[0], howmany, stream);
+    pthread_mutex_lock(&r->lock);
+    void *z = hs_scratch_get(&r->z_pool, stream, sizeof(fft_data) * (size_t)howmany * real_z_elems(r));
+    void *ws = hs_scratch_get(&r->ws_pool, stream, hs_dev_ws_bytes(c, howmany));
+    r2c_dev(obj, r, d_in, d_out, out_stride, full, z, ws, howmany, stream);
+    pthread_mutex_unlock(&r->lock);
 }
 
 void fft_c2r_exec_batch_dev(fft_real_object obj, const fft_data *d_in, long in_stride, fft_type *d_out, long howmany, void *stream)
@@ -221,10 +236,13 @@ void fft_c2r_exec_batch_dev(fft_real_object obj, const fft_data *d_in, long in_s
         fprintf(stderr, "Error: c2r input stride %ld too small for N = %d\n", in_stride, 2 * r->H);
         exit(EXIT_FAILURE);
     }
+    if ((const void *)d_in == (const void *)d_out) { fprintf(stderr, "Error: fft_c2r_exec_batch_dev is out of place\n"); exit(EXIT_FAILURE); }
     hs_dev_obj *c = hs_dev_get(obj->cobj);
-    grow(&r->d_z[0], &r->cap_z[0], sizeof(fft_data) * (size_t)howmany * real_z_elems(r));
-    grow(&r->d_ws[0], &r->cap_ws[0], hs_dev_ws_bytes(c, howmany));
-    c2r_dev(obj, r, d_in, in_stride, d_out, r->d_z[0], r->d_ws[0], howmany, stream);
+    pthread_mutex_lock(&r->lock);
+    void *z = hs_scratch_get(&r->z_pool, stream, sizeof(fft_data) * (size_t)howmany * real_z_elems(r));
+    void *ws = hs_scratch_get(&r->ws_pool, stream, hs_dev_ws_bytes(c, howmany));
+    c2r_dev(obj, r, d_in, in_stride, d_out, z, ws, howmany, stream);
+    pthread_mutex_unlock(&r->lock);
 }
 
 int hs_real_r2c_padded_dev(fft_real_object obj, const fft_type *d_rows, int len, long long row_stride, long long row_off, long long total,
@@ -234,24 +252,27 @@ int hs_real_r2c_padded_dev(fft_real_object obj, const fft_type *d_rows, int len,
     hs_real_dev *r = real_dev_get(obj);
     hs_dev_obj *c = hs_dev_get(obj->cobj);
     if (c->lt != 0 || !c->direct || c->direct->tp_id < 0) return 0;
-    grow(&r->d_z[0], &r->cap_z[0], sizeof(fft_data) * (size_t)howmany * real_z_elems(r));
+    pthread_mutex_lock(&r->lock);
+    void *z = hs_scratch_get(&r->z_pool, stream, sizeof(fft_data) * (size_t)howmany * real_z_elems(r));
     if (r->r4 && !getenv("HSFFT_NO_CONV_FUSE")) { /* real four-step with the zero padding on pass 1's loads: two launches, no split kernel */
         const long long n1 = r->r4_n1, n2 = r->r4_n2, ld = r->r4_ld;
         hs_tile_geom g;
         memset(&g, 0, sizeof g);
         g.ncols = (int)(n2 / 2); g.in_xf = 0; g.in_c = 1; g.in_e = n2 / 2; g.out_xf = n2 * ld; g.out_c = 2 * ld; g.out_e = 1;
         g.nlog = len; g.pad_stride = row_stride; g.pad_off = row_off; g.pad_total = total;
-        hs_cu_launch_tiled_io(r->r4_sub1, 1, 0, 0, 10, 1, d_rows, r->d_z[0], r->d_r4_tw1, &g, howmany, stream);
+        hs_cu_launch_tiled_io(r->r4_sub1, 1, 0, 0, 10, 1, d_rows, z, r->d_r4_tw1, &g, howmany, stream);
         memset(&g, 0, sizeof g);
         g.ncols = (int)(n1 / 2 + 1); g.in_xf = n2 * ld; g.in_c = 1; g.in_e = ld; g.out_xf = out_stride;
         g.twb = r->d_r4_twb; g.tws = r->d_r4_tws; g.tw_ld = (int)ld; g.nlog = (int)n1; g.sl_start = 0;
-        hs_cu_launch_tiled_io(r->r4_sub2, 1, 1, 1, 9, 1, r->d_z[0], d_out, r->d_r4_tw2, &g, howmany, stream);
+        hs_cu_launch_tiled_io(r->r4_sub2, 1, 1, 1, 9, 1, z, d_out, r->d_r4_tw2, &g, howmany, stream);
+        pthread_mutex_unlock(&r->lock);
         return 1;
     }
-    grow(&r->d_ws[0], &r->cap_ws[0], sizeof(fft_data) * (size_t)howmany * real_z_elems(r));
-    if (!hs_dev_exec_padded_real(c, d_rows, len, row_stride, row_off, total, r->d_z[0], r->d_ws[0], howmany, stream)) return 0;
-    hs_cu_launch_r2c_post(r->d_z[0], d_out, r->d_tw2, r->H, out_stride, 0, howmany, stream);
-    return 1;
+    void *ws = hs_scratch_get(&r->ws_pool, stream, sizeof(fft_data) * (size_t)howmany * real_z_elems(r));
+    const int ok = hs_dev_exec_padded_real(c, d_rows, len, row_stride, row_off, total, z, ws, howmany, stream);
+    if (ok) hs_cu_launch_r2c_post(z, d_out, r->d_tw2, r->H, out_stride, 0, howmany, stream);
+    pthread_mutex_unlock(&r->lock);
+    return ok;
 }
 
 int hs_real_c2r_mul_slice_dev(fft_real_object obj, const fft_data *d_A, const fft_data *d_B, long in_stride, long b_stride, double scale,
@@ -261,9 +282,12 @@ int hs_real_c2r_mul_slice_dev(fft_real_object obj, const fft_data *d_A, const ff
     hs_real_dev *r = real_dev_get(obj);
     hs_dev_obj *c = hs_dev_get(obj->cobj);
     if (c->lt != 0 || !c->direct || c->direct->tp_id < 0) return 0;
-    grow(&r->d_ws[0], &r->cap_ws[0], sizeof(fft_data) * (size_t)howmany * real_z_elems(r));
-    return hs_dev_exec_c2r_mul_slice(c, d_A, d_B, in_stride, b_stride, scale, r->d_tw2, d_out, out_stride, out_total, start, len, r->d_ws[0],
-                                     howmany, stream);
+    pthread_mutex_lock(&r->lock);
+    void *ws = hs_scratch_get(&r->ws_pool, stream, sizeof(fft_data) * (size_t)howmany * real_z_elems(r));
+    const int ok = hs_dev_exec_c2r_mul_slice(c, d_A, d_B, in_stride, b_stride, scale, r->d_tw2, d_out, out_stride, out_total, start, len, ws,
+                                             howmany, stream);
+    pthread_mutex_unlock(&r->lock);
+    return ok;
 }
 
 static long real_chunk(long howmany, size_t row_bytes)
@@ -273,13 +297,19 @@ static long real_chunk(long howmany, size_t row_bytes)
     return c > howmany ? howmany : c;
 }
 
-void fft_r2c_exec_batch(fft_real_object obj, fft_type *inp, fft_data *oup, long howmany)
+typedef struct real_ctx { fft_real_object obj; void *inp, *oup; long total; } real_ctx;
+
+static void r2c_batch_one_device(void *vctx, long first0, long howmany)
 {
-    check_real_args(obj, inp, oup);
+    real_ctx *x = (real_ctx *)vctx;
+    fft_real_object obj = x->obj;
     if (howmany <= 0) return;
     hs_real_dev *r = real_dev_get(obj);
     hs_dev_obj *c = hs_dev_get(obj->cobj);
+    pthread_mutex_lock(&r->lock);
     const size_t N = 2 * (size_t)r->H, in_row = sizeof(fft_type) * N, out_row = sizeof(fft_data) * N;
+    fft_type *inp = (fft_type *)x->inp + (size_t)first0 * N;
+    fft_data *oup = (fft_data *)x->oup + (size_t)first0 * N;
     const long chunk = real_chunk(howmany, out_row), nchunk = (howmany + chunk - 1) / chunk;
     for (long i = 0; i < nchunk; ++i) {
         const int s = (int)(i % HS_NSLOT);
@@ -295,15 +325,28 @@ void fft_r2c_exec_batch(fft_real_object obj, fft_type *inp, fft_data *oup, long 
         hs_cu_d2h(oup + first * N, r->d_out[s], out_row * cnt, r->stream[s]);
     }
     for (int s = 0; s < HS_NSLOT; ++s) hs_cu_stream_sync(r->stream[s]);
+    pthread_mutex_unlock(&r->lock);
 }
 
-void fft_c2r_exec_batch(fft_real_object obj, fft_data *inp, fft_type *oup, long howmany)
+void fft_r2c_exec_batch(fft_real_object obj, fft_type *inp, fft_data *oup, long howmany)
 {
     check_real_args(obj, inp, oup);
     if (howmany <= 0) return;
+    real_ctx x = {obj, inp, oup, howmany};
+    hs_shard_run(howmany, r2c_batch_one_device, &x);
+}
+
+static void c2r_batch_one_device(void *vctx, long first0, long howmany)
+{
+    real_ctx *x = (real_ctx *)vctx;
+    fft_real_object obj = x->obj;
+    if (howmany <= 0) return;
     hs_real_dev *r = real_dev_get(obj);
     hs_dev_obj *c = hs_dev_get(obj->cobj);
+    pthread_mutex_lock(&r->lock);
     const size_t N = 2 * (size_t)r->H, in_row = sizeof(fft_data) * N, out_row = sizeof(fft_type) * N;
+    fft_data *inp = (fft_data *)x->inp + (size_t)first0 * N;
+    fft_type *oup = (fft_type *)x->oup + (size_t)first0 * N;
     const long chunk = real_chunk(howmany, in_row), nchunk = (howmany + chunk - 1) / chunk;
     for (long i = 0; i < nchunk; ++i) {
         const int s = (int)(i % HS_NSLOT);
@@ -315,12 +358,21 @@ void fft_c2r_exec_batch(fft_real_object obj, fft_data *inp, fft_type *oup, long 
             grow(&r->d_ws[s], &r->cap_ws[s], hs_dev_ws_bytes(c, chunk));
         }
         /* a single transform is given as N/2+1 bins by reference-style callers; rows of a batch are N bins apart */
-        const size_t bytes = (howmany == 1) ? sizeof(fft_data) * (size_t)(r->H + 1) : in_row * cnt;
+        const size_t bytes = (x->total == 1) ? sizeof(fft_data) * (size_t)(r->H + 1) : in_row * cnt;
         hs_cu_h2d(r->d_in[s], inp + first * N, bytes, r->stream[s]);
         c2r_dev(obj, r, (const fft_data *)r->d_in[s], (long)N, (fft_type *)r->d_out[s], r->d_z[s], r->d_ws[s], cnt, r->stream[s]);
         hs_cu_d2h(oup + first * N, r->d_out[s], out_row * cnt, r->stream[s]);
     }
     for (int s = 0; s < HS_NSLOT; ++s) hs_cu_stream_sync(r->stream[s]);
+    pthread_mutex_unlock(&r->lock);
+}
+
+void fft_c2r_exec_batch(fft_real_object obj, fft_data *inp, fft_type *oup, long howmany)
+{
+    check_real_args(obj, inp, oup);
+    if (howmany <= 0) return;
+    real_ctx x = {obj, inp, oup, howmany};
+    hs_shard_run(howmany, c2r_batch_one_device, &x);
 }
 
 void fft_r2c_exec(fft_real_object real_obj, fft_type *input_data, fft_data *output_data)

@@ -125,13 +125,29 @@ static void launch_tiled(const void *in, void *out, const void *tw, const HsTile
 #include "hs_ct_table.cuh"
 
 extern "C" {
-int hs_cu_device_count(void) { return 1; }
+// HSFFT_EMU_DEVICES=n pretends to have n devices (one address space; the "current device" is per host thread, as in CUDA):
+// exercises the (plan, device) registry and the batch sharding of hsfft_set_devices on a box without a GPU
+static thread_local int t_dev = 0;
+int hs_cu_device_count(void) { const char *e = getenv("HSFFT_EMU_DEVICES"); const int n = e ? atoi(e) : 1; return n > 0 ? n : 1; }
 void hs_cu_require_device(void) {}
-int hs_cu_get_device(void) { return 0; }
-void hs_cu_set_device(int) {}
+int hs_cu_get_device(void) { return t_dev; }
+void hs_cu_set_device(int d) { t_dev = d; }
 int hs_cu_sm_count(void) { return 148; }
 void *hs_cu_malloc(size_t bytes) { return malloc(bytes ? bytes : 16); }
 void hs_cu_free(void *d) { free(d); }
+void *hs_cu_malloc_async(size_t bytes, void *) { return malloc(bytes ? bytes : 16); }
+void hs_cu_free_async(void *d, void *) { free(d); }
+void hs_cu_device_sync(void) {}
+int hs_cu_can_access_peer(int, int) { return 1; }
+void hs_cu_enable_peer_access(int) {}
+void hs_cu_h2d_2d(void *d, size_t dpitch, const void *h, size_t hpitch, size_t width_bytes, size_t rows, void *)
+{
+    for (size_t r = 0; r < rows; ++r) memcpy((char *)d + r * dpitch, (const char *)h + r * hpitch, width_bytes);
+}
+void hs_cu_d2h_2d(void *h, size_t hpitch, const void *d, size_t dpitch, size_t width_bytes, size_t rows, void *)
+{
+    for (size_t r = 0; r < rows; ++r) memcpy((char *)h + r * hpitch, (const char *)d + r * dpitch, width_bytes);
+}
 void *hs_cu_malloc_host(size_t bytes) { return malloc(bytes ? bytes : 16); }
 void hs_cu_free_host(void *h) { free(h); }
 void hs_cu_h2d(void *d, const void *h, size_t bytes, void *) { if (bytes) memcpy(d, h, bytes); }

@@ -13,9 +13,13 @@
 
 extern std::barrier<> *hs_emu_bar, *hs_emu_bar2;
 
+#include <mutex>
+extern std::mutex hs_emu_launch_mu; // the launch state below is global: launches from several host threads take turns
+
 template <class K, class... Args>
 void hs_emu_launch(K kernel, long long grid, int block, size_t smem_bytes, Args... args)
 {
+    std::lock_guard<std::mutex> launch_guard(hs_emu_launch_mu);
     hs_emu_blockDim.x = block;
     hs_emu_gridDim.x = (unsigned)grid;
     std::vector<unsigned char> smem(smem_bytes + 64);

@@ -297,3 +297,59 @@ def test_two_dimensional_transforms(hs, emu_lib, oracle, n0, n1):
             desc = p.describe()
         assert ("no transpose" in desc) == (n0 in (128, 256, 512, 1024) and n1 % {1024: 4, 512: 8}.get(n0, 16) == 0), desc
         assert rel_rms(y, oracle_fft2(oracle, x, sgn)) <= tol(n0 * n1), (n0, n1, sgn, desc)
+
+
+def test_batch_sharding_over_devices_and_plans_shared_between_threads(hs, emu_lib, oracle, monkeypatch):
+    """hsfft_set_devices(n): the host-pointer batch calls cut the batch into n contiguous ranges, one host thread and one
+    (plan, device) state each (the emulation pretends to have 3 devices).  Also several host threads executing ONE plan at
+    once, which the reference allows for mixed-radix plans: calls serialise on the plan's lock instead of sharing staging buffers."""
+    import threading
+    monkeypatch.setenv("HSFFT_EMU_DEVICES", "3")
+    emu_lib.hsfft_set_devices(3)
+    try:
+        assert emu_lib.hsfft_get_devices() == 3
+        n = 1000
+        x = rand_cplx(11, n, seed=4)
+        with hs.Plan(n, 1, lib=emu_lib) as p:
+            y = p.exec(x)                          # 11 transforms over 3 devices: 4 + 4 + 3
+            assert max(rel_rms(y[i], oracle.c2c(x, 1)[i]) for i in range(11)) <= tol(n)
+        nr = 2048
+        xr = xorshift_uniform(7 * nr, seed=8).reshape(7, nr)
+        with hs.RealPlan(nr, 1, lib=emu_lib) as f, hs.RealPlan(nr, -1, lib=emu_lib) as g:
+            X = f.r2c(xr)
+            assert rel_rms(X, oracle.r2c(xr)) <= tol(nr)
+            assert rel_rms(g.c2r(X) / nr, xr) <= tol(nr)
+        a, b = xorshift_uniform(6 * 300, seed=1).reshape(6, 300), xorshift_uniform(6 * 41, seed=2).reshape(6, 41)
+        cnt, yc = hs.convolve_batch(a, b, lib=emu_lib)
+        assert cnt == 340 and all(rel_rms(yc[i], np.convolve(a[i], b[i])) <= 1e-13 for i in range(6))
+    finally:
+        emu_lib.hsfft_set_devices(1)
+    n = 4096
+    x = rand_cplx(4, n, seed=9)
+    ref = oracle.c2c(x, 1)
+    out, errs = [None] * 4, []
+    with hs.Plan(n, 1, lib=emu_lib) as p:
+        def work(i):
+            try:
+                for _ in range(3):
+                    out[i] = p.exec(x[i])
+            except Exception as e:   # pragma: no cover
+                errs.append(e)
+        th = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+    assert not errs and all(rel_rms(out[i], ref[i]) <= tol(n) for i in range(4))
+
+
+@pytest.mark.parametrize("ndev,N1,N2,sgn", [(1, 256, 512, 1), (2, 256, 512, -1), (4, 16384, 128, 1)])
+def test_single_process_four_step_entry(hs, emu_lib, oracle, ndev, N1, N2, sgn, monkeypatch):
+    """fft_exec_dist: host pointers, natural order, one process driving `ndev` devices whose receive buffers are mutually
+    addressable (peer access on the GPU box, one address space here): scatter, phase A with the exchange fused into its
+    stores, barrier, phase B, transpose, gather."""
+    import ctypes as C
+    monkeypatch.setenv("HSFFT_EMU_DEVICES", str(ndev))
+    x = rand_cplx(1, N1 * N2, seed=77 + ndev)[0]
+    y = np.empty_like(x)
+    assert emu_lib.fft_exec_dist(N1, N2, sgn, x.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p), ndev) == 0
+    assert rel_rms(y, oracle.c2c(x, sgn)) <= tol(N1 * N2)
+

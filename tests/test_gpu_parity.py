@@ -490,3 +490,73 @@ def test_half_spectrum_and_row_strides_direct(hs, product_lib, oracle, n):
         # against the reference's own c2r of the reference's spectrum (a round trip is NOT the identity to 1e-12 log2 N where the
         # reference's truncated radix-3/5 constants act twice, e.g. N/2 = 3000)
         assert per_transform_worst(back.cpu().numpy(), oracle.c2r(Xr, n)) <= tol(n), (n, stride)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Re-entrancy and several devices from one process (the reference's mixed-radix fft_exec only reads its plan, so callers
+# may share a plan between threads; kernel attributes and plan state are per device here).
+
+def test_one_plan_two_streams_and_four_threads(hs, product_lib, oracle):
+    import threading
+    import torch
+    n, b = 1 << 16, 4                                 # two-pass plan: needs a workspace, one per caller stream
+    xs = [_device_rand((b, n, 2), seed=s) for s in (1, 2)]
+    ys = [torch.empty_like(x) for x in xs]
+    st = [torch.cuda.Stream(), torch.cuda.Stream()]
+    with hs.Plan(n, 1) as p:
+        for rep in range(5):
+            for i in (0, 1):
+                p.exec_dev(xs[i], ys[i], b, stream=st[i].cuda_stream)
+        torch.cuda.synchronize()
+        for i in (0, 1):
+            got = torch.view_as_complex(ys[i]).cpu().numpy()
+            assert per_transform_worst(got, oracle.c2c(torch.view_as_complex(xs[i]).cpu().numpy(), 1)) <= tol(n)
+    n = 10007
+    x = rand_cplx(8, n, seed=3)
+    ref = oracle.c2c(x, 1)
+    out, errs = [None] * 8, []
+    with hs.Plan(n, 1) as p:
+        def work(i):
+            try:
+                for _ in range(4):
+                    out[i] = p.exec(x[i])
+            except Exception as e:   # pragma: no cover
+                errs.append(e)
+        th = [threading.Thread(target=work, args=(i,)) for i in range(8)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+    assert not errs and all(rel_rms(out[i], ref[i]) <= tol(n) for i in range(8))
+
+
+def test_two_devices_driven_by_one_process(hs, product_lib, oracle):
+    """One process, two GPUs: the same plan executes on device 0 and then on device 1 (kernel attributes and plan state are
+    kept per device), hsfft_set_devices(2) shards host-pointer batches by batch index, and fft_exec_dist runs the four-step
+    with the exchange as NVLink peer stores between the two devices."""
+    import ctypes as C
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    L = hs.load()
+    x = rand_cplx(6, 8192, seed=12)
+    r = oracle.c2c(x, 1)
+    with hs.Plan(8192, 1) as p:                        # 139 KB of dynamic shared memory: the attribute must be set on both devices
+        for dev in (0, 1, 0):
+            L.hsfft_set_device(dev)
+            assert per_transform_worst(p.exec(x), r) <= tol(8192)
+    L.hsfft_set_device(0)
+    L.hsfft_set_devices(2)
+    try:
+        for n, b in ((4096, 37), (10007, 9), (1 << 17, 5)):
+            x = rand_cplx(b, n, seed=n)
+            with hs.Plan(n, -1) as p:
+                assert per_transform_worst(p.exec(x), oracle.c2c(x, -1)) <= tol(n)
+        xr = xorshift_uniform(9 * 8192, seed=4).reshape(9, 8192)
+        with hs.RealPlan(8192, 1) as f:
+            assert per_transform_worst(f.r2c(xr), oracle.r2c(xr)) <= tol(8192)
+    finally:
+        L.hsfft_set_devices(1)
+    for N1, N2, sgn in ((256, 512, 1), (16384, 1024, -1)):
+        x = rand_cplx(1, N1 * N2, seed=N1)[0]
+        y = np.empty_like(x)
+        assert L.fft_exec_dist(N1, N2, sgn, x.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p), 2) == 0
+        assert rel_rms(y, oracle.c2c(x, sgn)) <= tol(N1 * N2)
