@@ -70,6 +70,8 @@ static inline void hs_emu_mbar_complete_tx(HsMbar *m, long long bytes) { std::lo
 static inline bool hs_mbar_test(HsMbar *m, unsigned parity) { std::lock_guard<std::mutex> g(hs_emu_mbar_mu); return (m->phase & 1u) != parity; }
 static inline void hs_mbar_wait(HsMbar *m, unsigned parity) { while (!hs_mbar_test(m, parity)) { } }
 static inline void hs_bulk_g2s(void *dst, const void *src, unsigned bytes, HsMbar *m) { memcpy(dst, src, bytes); hs_emu_mbar_complete_tx(m, bytes); }
+static inline void hs_bulk_s2g(void *dst, const void *src, unsigned bytes) { memcpy(dst, src, bytes); }
+static inline void hs_bulk_commit_wait_read() {}
 static inline void hs_fence_async_proxy() {}
 static inline void hs_fence_proxy_async_all() {}
 static inline void hs_prefetch_l2(const void *, unsigned) {}
@@ -265,6 +267,18 @@ HS_DEVICE void hs_bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes,
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(hs_smem_u32(dst_smem)),
                  "l"(src_gmem), "r"(bytes), "r"(hs_smem_u32(m))
                  : "memory");
+}
+// shared -> global (the destination may be a peer GPU's memory), 16-byte aligned, size a multiple of 16; part of the
+// issuing thread's current bulk group
+HS_DEVICE void hs_bulk_s2g(void *dst_gmem, const void *src_smem, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(hs_smem_u32(src_smem)), "r"(bytes) : "memory");
+}
+// close the thread's bulk group and wait until the copy engine has READ its shared-memory sources (the CTA may then
+// overwrite them or exit; the writes themselves complete like any other store, by the end of the kernel)
+HS_DEVICE void hs_bulk_commit_wait_read()
+{
+    asm volatile("cp.async.bulk.commit_group;\n cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 // ask the copy engine to bring [p, p + bytes) into the L2 (16-byte aligned, a multiple of 16 bytes)
 HS_DEVICE void hs_prefetch_l2(const void *p, unsigned bytes)

@@ -383,8 +383,32 @@ static void launch_sub_io(int sgn, int tw_mode, int stcol, int io_mode, int cs, 
     } else if (io_mode == 6 && tw_mode == 1 && stcol) {
         if (sgn == 1) launch_tiled<P, 1, C, 1, true, 6, 1>(in, out, tw, g, howmany, st); else launch_tiled<P, -1, C, 1, true, 6, 1>(in, out, tw, g, howmany, st);
     } else if (io_mode == 7 && stcol && (tw_mode == 0 || tw_mode == 2)) {
-        if (tw_mode == 2) { if (sgn == 1) launch_tiled<P, 1, C, 2, true, 7, 1>(in, out, tw, g, howmany, st); else launch_tiled<P, -1, C, 2, true, 7, 1>(in, out, tw, g, howmany, st); }
+        // the exchange pass: wider tiles mean longer contiguous runs per peer store (C * 16 bytes per row); HSFFT_DIST_C picks
+        // 8 / 16 / 32 columns for the short sub-plans (default: 16 where the CTA stays within 256 threads)
+        constexpr int CW = (P::T <= 16) ? 16 : C;
+        constexpr int CX = (P::T <= 16) ? 32 : C;
+        static int want = -1;
+        if (want < 0) { const char *e = getenv("HSFFT_DIST_C"); want = e ? atoi(e) : 0; }
+        const int use = (want == 8 || want == C) ? C : (want == 32 ? CX : (want == 16 ? CW : CW));
+        if (tw_mode == 2) {
+            if (use == C || g.ncols % use != 0) { if (sgn == 1) launch_tiled<P, 1, C, 2, true, 7, 1>(in, out, tw, g, howmany, st); else launch_tiled<P, -1, C, 2, true, 7, 1>(in, out, tw, g, howmany, st); }
+            else if (use == CW) { if (sgn == 1) launch_tiled<P, 1, CW, 2, true, 7, 1>(in, out, tw, g, howmany, st); else launch_tiled<P, -1, CW, 2, true, 7, 1>(in, out, tw, g, howmany, st); }
+            else { if (sgn == 1) launch_tiled<P, 1, CX, 2, true, 7, 1>(in, out, tw, g, howmany, st); else launch_tiled<P, -1, CX, 2, true, 7, 1>(in, out, tw, g, howmany, st); }
+        }
         else { if (sgn == 1) launch_tiled<P, 1, C, 0, true, 7, 1>(in, out, tw, g, howmany, st); else launch_tiled<P, -1, C, 0, true, 7, 1>(in, out, tw, g, howmany, st); }
+    } else if (io_mode == 11 && stcol && (tw_mode == 0 || tw_mode == 2)) {
+        // the same with bulk copies (see hs_tiled.cuh IO 11)
+        constexpr int CW = (P::T <= 16) ? 16 : C;
+        constexpr int CX = (P::T <= 16) ? 32 : C;
+        static int want = -1;
+        if (want < 0) { const char *e = getenv("HSFFT_DIST_C"); want = e ? atoi(e) : 0; }
+        const int use = (want == 8 || want == C) ? C : (want == 32 ? CX : (want == 16 ? CW : CW));
+        if (tw_mode == 2) {
+            if (use == C || g.ncols % use != 0) { if (sgn == 1) launch_tiled<P, 1, C, 2, true, 11, 1>(in, out, tw, g, howmany, st); else launch_tiled<P, -1, C, 2, true, 11, 1>(in, out, tw, g, howmany, st); }
+            else if (use == CW) { if (sgn == 1) launch_tiled<P, 1, CW, 2, true, 11, 1>(in, out, tw, g, howmany, st); else launch_tiled<P, -1, CW, 2, true, 11, 1>(in, out, tw, g, howmany, st); }
+            else { if (sgn == 1) launch_tiled<P, 1, CX, 2, true, 11, 1>(in, out, tw, g, howmany, st); else launch_tiled<P, -1, CX, 2, true, 11, 1>(in, out, tw, g, howmany, st); }
+        }
+        else { if (sgn == 1) launch_tiled<P, 1, C, 0, true, 11, 1>(in, out, tw, g, howmany, st); else launch_tiled<P, -1, C, 0, true, 11, 1>(in, out, tw, g, howmany, st); }
     } else { fprintf(stderr, "Error: unsupported fused tiled pass\n"); exit(EXIT_FAILURE); }
 }
 

@@ -164,6 +164,27 @@ struct HsStoreColDist {
     }
 };
 
+// The same exchange with the rows staged in shared memory: the last pass leaves its twiddled outputs as stage[k][c]
+// (C adjacent columns of output row k = C*16 contiguous bytes of the owner's receive buffer), and after one barrier one
+// thread per row hands the run to the copy engine (cp.async.bulk shared -> peer global): the SM's load/store unit issues
+// one instruction per row instead of C stores, and the warps do not sit on NVLink back-pressure.
+struct HsStoreColDistStage {
+    static constexpr bool kToSmem = true;
+    const hs_dist_store *HS_RESTRICT ds;
+    long long x;  // outer item
+    int c;        // column inside the slab
+    cplx *stage;  // [k][C]
+    int cs, C;    // column slot inside the tile
+    HS_DEVICE void operator()(int, int, int k, cplx v) const
+    {
+        const unsigned long long k1 = (unsigned long long)(x + ds->row_mul * k);
+        const unsigned long long n2 = (unsigned long long)(ds->rank * ds->Cw + c);
+        const unsigned long long e = (k1 * n2) & ((1ULL << ds->logN) - 1);
+        const cplx w = hs_mul(hs_ld_tab((const cplx *)ds->hi + (e >> ds->logS)), hs_ld_tab((const cplx *)ds->lo + (e & ((1ULL << ds->logS) - 1))));
+        stage[k * C + cs] = hs_mul(v, w);
+    }
+};
+
 // c2r merge (reference src/real.c:171-179) fused into pass 1 of the half-length transform: element k of the
 // packed signal is built from bins k and H-k of the Hermitian input on the fly, so the merged signal is
 // never written to HBM.
@@ -298,7 +319,7 @@ struct HsStoreColR2CMirror { // element k2 of row k1: bin k = k1 + n1 k2 and its
 // 4 zero padding on load, 5 spectrum product on merge load, 6 slice on store (convolution);
 // 7 four-step exchange on store (g.chirp = the plan's hs_dist_store in device memory);
 // 8 / 9 the two passes of the real four-step (g.out_c = two workspace rows; g.nlog = n1, g.sl_start = full spectrum);
-// 10 = 8 with the zero padding of 4 on its loads.
+// 10 = 8 with the zero padding of 4 on its loads; 11 = 7 with the rows staged in shared memory and sent as bulk copies.
 // tid: thread index in the tile's team of P::T*C threads; on: false for threads (or whole CTAs) that only
 // take part in the barriers.
 // STG: the input tile was staged in shared memory by the copy engine ([row][C] at in_x); IO 0 and 2 only.
@@ -352,6 +373,31 @@ HS_DEVICE void hs_tile_run(const cplx *HS_RESTRICT in_x, cplx *HS_RESTRICT out_x
             ld.blk_log = g.blk_log; ld.blk_stride = g.blk_stride;
             hs_fft_team2<P, SGN>(ld, st, first, rest, tw, hk);
         }
+    } else if constexpr (IO == 11) { // as 7, rows staged in shared memory and sent with bulk copies
+        static_assert(STCOL && TW != 1 && !STG, "the exchange store keeps lane = column");
+        const hs_dist_store *ds = (const hs_dist_store *)g.chirp;
+        HsStoreColDistStage st{ds, xf, g.nlog + c0 + colS, smem, colS, C};
+        if constexpr (TW == 2) {
+            HsLoadColTw<LDP> ld;
+            ld.base = in_x; ld.off0 = (long long)(c0 + colA) * g.in_c; ld.es = g.in_e;
+            ld.blk_log = g.blk_log; ld.blk_stride = g.blk_stride;
+            ld.twb = (const cplx *)g.twb + xf; ld.tw_ld = g.tw_ld; ld.step = on ? hs_ld_tab((const cplx *)g.tws + xf) : hs_c(0.0, 0.0);
+            hs_fft_team2<P, SGN>(ld, st, first, rest, tw, hk);
+        } else {
+            HsLoadCol<LDP> ld;
+            ld.base = in_x; ld.off0 = (long long)(c0 + colA) * g.in_c; ld.es = g.in_e;
+            ld.blk_log = g.blk_log; ld.blk_stride = g.blk_stride;
+            hs_fft_team2<P, SGN>(ld, st, first, rest, tw, hk);
+        }
+        hs_fence_async_proxy(); // this thread's staged outputs become visible to the copy engine ...
+        hk.sync();              // ... and after the barrier so are everybody's
+        for (int k = tid; k < P::N; k += P::T * C) {
+            const unsigned long long k1 = (unsigned long long)(xf + ds->row_mul * k);
+            cplx *dst = (cplx *)ds->peer[k1 >> ds->logKw] +
+                        ((ds->rank * ds->Kw + (long long)(k1 & (unsigned long long)(ds->Kw - 1))) * ds->Cw + (g.nlog + c0));
+            hs_bulk_s2g(dst, smem + k * C, (unsigned)(C * sizeof(cplx)));
+        }
+        hs_bulk_commit_wait_read();
     } else if constexpr (IO == 8 || IO == 10) { // real four-step, pass 1: transform the complex columns, split into the two real columns' rows 0..n1/2
         static_assert(TW == 0 && !STCOL && !STG, "the split belongs to a first pass with contiguous output rows");
         HsStoreSmemCol<P> st{rest.sm};

@@ -23,6 +23,10 @@
 #include "hs_engine.h"
 #include "../../include/hsfft_b200.h"
 
+#ifndef HS_DIST_BULK_DEFAULT
+#define HS_DIST_BULK_DEFAULT 0
+#endif
+
 typedef struct hs_axis { /* transform of length L along one axis, as one or two tiled passes */
     int L, two, sub1, sub2, n1, n2, nb2;
     void *d_tw1, *d_tw2, *d_twb, *d_tws;
@@ -219,6 +223,15 @@ void hsfft_dist_set_peer_pointers(hsfft_dist_object d, void *const *peer_r, int 
     hs_cu_stream_sync(NULL);
 }
 
+/* how phase A's last pass sends its rows: 7 = 16-byte stores from the registers, 11 = rows staged in shared memory and handed
+ * to the copy engine (cp.async.bulk shared -> peer global); HSFFT_DIST_BULK=0 / 1 */
+static int dist_store_mode(void)
+{
+    static int mode = -1;
+    if (mode < 0) { const char *e = getenv("HSFFT_DIST_BULK"); mode = (e ? atoi(e) : HS_DIST_BULK_DEFAULT) ? 11 : 7; }
+    return mode;
+}
+
 void hsfft_dist_cols_exchange_dev(hsfft_dist_object d, const fft_data *d_a, fft_data *d_ws, void *stream)
 {
     /* phase A and the exchange in one: b is never materialised, its rows go to their owners as they are produced.
@@ -233,7 +246,7 @@ void hsfft_dist_cols_exchange_dev(hsfft_dist_object d, const fft_data *d_a, fft_
     g.chirp = d->d_store;
     if (!ax->two) {
         g.in_e = W; g.out_e = W;
-        hs_cu_launch_tiled_io(ax->sub1, d->sgn, 0, 1, 7, 1, d_a, NULL, ax->d_tw1, &g, 1, stream);
+        hs_cu_launch_tiled_io(ax->sub1, d->sgn, 0, 1, dist_store_mode(), 1, d_a, NULL, ax->d_tw1, &g, 1, stream);
         return;
     }
     /* Two passes.  Only the second one talks to the peers; HSFFT_DIST_CHUNKS=k cuts the slab into k column chunks and
@@ -269,7 +282,7 @@ void hsfft_dist_cols_exchange_dev(hsfft_dist_object d, const fft_data *d_a, fft_
         g.in_xf = W; g.in_e = L1 * W; g.out_xf = W; g.out_e = L1 * W;
         g.twb = ax->d_twb; g.tws = ax->d_tws; g.tw_ld = (int)L1;
         g.chirp = d->d_store; g.nlog = (int)(i * Wc);
-        hs_cu_launch_tiled_io(ax->sub2, d->sgn, 2, 1, 7, 1, mid, NULL, ax->d_tw2, &g, L1, sb);
+        hs_cu_launch_tiled_io(ax->sub2, d->sgn, 2, 1, dist_store_mode(), 1, mid, NULL, ax->d_tw2, &g, L1, sb);
     }
     if (chunks > 1) {
         hs_cu_event_record(d->ev_join1, sa); hs_cu_event_record(d->ev_join2, sb);
