@@ -44,6 +44,8 @@ int fft_convolve_batch(const char *type, const char *conv_type, fft_type *input1
  *          threads and on several streams at once: calls on one (plan, device) serialise on an internal lock while they
  *          enqueue, and every caller stream has its own intermediates. ---- */
 void fft_exec_batch_dev(fft_object obj, const fft_data *d_in, fft_data *d_out, long howmany, void *stream);
+/* in place: every transform of d_data is replaced by its spectrum (the one call that may be given a single buffer) */
+void fft_exec_batch_inplace_dev(fft_object obj, fft_data *d_data, long howmany, void *stream);
 /* out_stride: complex elements between output rows (>= N/2+1); full != 0 also writes the mirror
  * bins N/2+1..N-1 (needs out_stride >= N), full == 0 writes bins 0..N/2 only. */
 void fft_r2c_exec_batch_dev(fft_real_object obj, const fft_type *d_in, fft_data *d_out, long out_stride, int full,

@@ -51,7 +51,7 @@ EXPORTS = [
     "hsfft_device_count", "hsfft_set_device", "hsfft_get_device", "hsfft_malloc_device", "hsfft_free_device",
     "hsfft_malloc_host", "hsfft_free_host", "hsfft_copy_h2d", "hsfft_copy_d2h", "hsfft_sync", "hsfft_launch_count",
     "hsfft_plan_describe", "hsfft_version", "hsfft_timing_begin", "hsfft_timing_report",
-    "hsfft_set_devices", "hsfft_get_devices", "fft_exec_dist",
+    "hsfft_set_devices", "hsfft_get_devices", "fft_exec_dist", "fft_exec_batch_inplace_dev",
     "hsfft_dist_init", "hsfft_dist_cols_dev", "hsfft_dist_rows_dev", "hsfft_dist_slab_elems", "hsfft_dist_free",
     "hsfft_ipc_get_handle", "hsfft_dist_set_peers", "hsfft_dist_set_peer_pointers", "hsfft_dist_cols_exchange_dev",
 ]
@@ -83,7 +83,7 @@ def _bind(L):
         "hsfft_malloc_host": (vp, [sz]), "hsfft_free_host": (None, [vp]),
         "hsfft_copy_h2d": (None, [vp, vp, sz]), "hsfft_copy_d2h": (None, [vp, vp, sz]), "hsfft_sync": (None, []),
         "hsfft_launch_count": (ll, []), "hsfft_timing_begin": (None, [vp]), "hsfft_set_devices": (None, [i]), "hsfft_get_devices": (i, []),
-        "fft_exec_dist": (i, [i, i, i, vp, vp, i]), "hsfft_timing_report": (i, [cp, i]), "hsfft_plan_describe": (cp, [P]), "hsfft_version": (cp, []),
+        "fft_exec_dist": (i, [i, i, i, vp, vp, i]), "fft_exec_batch_inplace_dev": (None, [P, vp, l, vp]), "hsfft_timing_report": (i, [cp, i]), "hsfft_plan_describe": (cp, [P]), "hsfft_version": (cp, []),
         "hsfft_dist_init": (vp, [i, i, i, i, i]), "hsfft_dist_cols_dev": (None, [vp, vp, vp, vp, vp]),
         "hsfft_dist_rows_dev": (None, [vp, vp, vp, vp, vp]), "hsfft_dist_slab_elems": (ll, [vp]), "hsfft_dist_free": (None, [vp]),
         "hsfft_ipc_get_handle": (None, [vp, vp]), "hsfft_dist_set_peers": (None, [vp, vp, vp, i]),
@@ -168,6 +168,9 @@ class Plan:
     def exec_dev(self, d_in, d_out, howmany, stream=0):
         """Device-resident batch: d_in/d_out are torch CUDA complex128 tensors (or raw pointers)."""
         self.L.fft_exec_batch_dev(self.p, _dev_ptr(d_in), _dev_ptr(d_out), howmany, C.c_void_p(stream))
+
+    def exec_inplace_dev(self, d_data, howmany, stream=0):
+        self.L.fft_exec_batch_inplace_dev(self.p, _dev_ptr(d_data), howmany, C.c_void_p(stream))
 
     def close(self):
         if self.p:

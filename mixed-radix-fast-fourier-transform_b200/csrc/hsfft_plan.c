@@ -1183,6 +1183,32 @@ void fft_exec_batch_dev(fft_object obj, const fft_data *d_in, fft_data *d_out, l
     hs_dev_unlock(d);
 }
 
+/* In-place execution (additive): the transforms of d_data are replaced by their spectra.
+ * Every plan whose first kernel consumes a whole transform (or the whole batch) before anything is written back is run
+ * directly on the buffer; the few that do not go through a copy of the input. */
+void fft_exec_batch_inplace_dev(fft_object obj, fft_data *d_data, long howmany, void *stream)
+{
+    if (obj == NULL || d_data == NULL) {
+        fprintf(stderr, "Error: Invalid FFT object or data pointers\n");
+        exit(EXIT_FAILURE);
+    }
+    if (howmany <= 0) return;
+    hs_dev_obj *d = hs_dev_get(obj);
+    hs_dev_lock(d);
+    const size_t bytes = sizeof(fft_data) * (size_t)d->N * (size_t)howmany, wsb = hs_dev_ws_bytes(d, howmany);
+    const hs_c2c *p = d->lt == 0 ? d->direct : NULL;
+    /* unsafe on the caller's buffer: the run-time engine's multi-pass plans (pass 1 writes into the output while other CTAs
+     * still read the input) and the split chirp-z kernel (parks its first half-convolution in the output row, then reads
+     * the input row again) */
+    const int copy = (p && p->ct_id < 0 && p->jit_id < 0 && p->tp_id < 0 && p->npass > 1) || (d->lt == 1 && d->split_ct_id >= 0);
+    char *ws = (char *)hs_scratch_get(&d->ws_pool, stream, wsb + (copy ? bytes : 0));
+    if (copy) {
+        hs_cu_d2d(ws + wsb, d_data, bytes, stream);
+        hs_dev_exec(d, ws + wsb, d_data, ws, howmany, stream);
+    } else hs_dev_exec(d, d_data, d_data, ws, howmany, stream);
+    hs_dev_unlock(d);
+}
+
 void free_fft(fft_object object)
 {
     if (object) hs_dev_release(object);

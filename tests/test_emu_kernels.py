@@ -353,3 +353,17 @@ def test_single_process_four_step_entry(hs, emu_lib, oracle, ndev, N1, N2, sgn, 
     assert emu_lib.fft_exec_dist(N1, N2, sgn, x.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p), ndev) == 0
     assert rel_rms(y, oracle.c2c(x, sgn)) <= tol(N1 * N2)
 
+
+@pytest.mark.parametrize("n", [64, 1000, 4096, 1009, 10007, 4099, 16384, 6561, 20011, 3 << 14])
+def test_in_place_execution(hs, emu_lib, oracle, n):
+    """fft_exec_batch_inplace_dev (additive): one buffer in, the same buffer out, for every kernel family -- the plans that
+    cannot run on a single buffer (run-time multi-pass, split chirp-z) go through a copy of the input."""
+    import ctypes as C
+    x = rand_cplx(3, n, seed=n)
+    buf = x.copy()
+    with hs.Plan(n, 1, lib=emu_lib) as p:
+        emu_lib.fft_exec_batch_inplace_dev(p.p, buf.ctypes.data_as(C.c_void_p), 3, None)
+        desc = p.describe()
+    r = oracle.c2c(x, 1)
+    assert max(rel_rms(buf[i], r[i]) for i in range(3)) <= tol(n), (n, desc)
+

@@ -560,3 +560,21 @@ def test_two_devices_driven_by_one_process(hs, product_lib, oracle):
         y = np.empty_like(x)
         assert L.fft_exec_dist(N1, N2, sgn, x.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p), 2) == 0
         assert rel_rms(y, oracle.c2c(x, sgn)) <= tol(N1 * N2)
+
+
+@pytest.mark.parametrize("n", [64, 1000, 3000, 4096, 8192, 1009, 2039, 4099, 10007, 40009, 16384, 1 << 20, 6561, 3 << 14, 1001])
+def test_in_place_execution(hs, product_lib, oracle, n):
+    """fft_exec_batch_inplace_dev: one device buffer in and out, every kernel family."""
+    import torch
+    b = 4 if n <= 16384 else 2
+    x = rand_cplx(b, n, seed=n + 1)
+    buf = torch.view_as_real(torch.from_numpy(x.copy())).cuda()
+    for sgn in (1, -1):
+        buf.copy_(torch.view_as_real(torch.from_numpy(x)))
+        with hs.Plan(n, sgn) as p:
+            p.exec_inplace_dev(buf, b)
+            torch.cuda.synchronize()
+            desc = p.describe()
+        got = torch.view_as_complex(buf).cpu().numpy()
+        assert per_transform_worst(got, oracle.c2c(x, sgn)) <= tol(n), (n, sgn, desc)
+
