@@ -226,6 +226,11 @@ void  hs_cu_jit_c2c_launch(int handle, const void *d_in, void *d_out, const void
 int   hs_cu_jit_source(int n, int sgn, const int *radix_exec, int nst, char *out, int cap);
 /* the real transforms of hs_cu_launch_ct_real on a plan-time kernel (same module, entry points hs_jit_r2c / hs_jit_c2r) */
 int   hs_cu_jit_has_real(int handle);
+/* two tiled passes compiled for this plan (N > 8192, all stages compile-time radices): radix_exec cut after `split` stages;
+ * fills desc like a static HS_CT_TWOPASS descriptor; launch runs pass 1 or 2 over a contiguous batch */
+int   hs_cu_jit_twopass_create(long long n, int sgn, const int *radix_exec, int nst, int split, hs_ct_desc *desc);
+void  hs_cu_jit_twopass_launch(int handle, int pass, const void *d_in, void *d_out, const void *d_tw, const void *d_twb, const void *d_tws,
+                               long long howmany, void *stream);
 void  hs_cu_jit_real_launch(int handle, int mode, const void *d_in, void *d_out, const void *d_tw, const void *d_tw2, long long stride,
                             int full, long long howmany, void *stream);
 

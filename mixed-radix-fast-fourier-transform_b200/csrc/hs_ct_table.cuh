@@ -84,6 +84,9 @@ static void ct_init()
     fill_desc<PC10240s>(g_ct[CT_C10240S], CT_C10240S, HS_CT_CONV_SPLIT);
     fill_desc<PC10240l>(g_ct[CT_C10240L], CT_C10240L, HS_CT_CONV_SPLIT);
     fill_desc<PC10240h>(g_ct[CT_C10240H], CT_C10240H, HS_CT_CONV_SPLIT);
+    fill_desc<P8192c>(g_ct[CT_8192C], CT_8192C, HS_CT_C2C);
+    fill_desc<P8192d>(g_ct[CT_8192D], CT_8192D, HS_CT_C2C);
+    fill_desc<P3000>(g_ct[CT_3000M3], CT_3000M3, HS_CT_C2C);
     fill_desc<P4096x>(g_ct[CT_4096X], CT_4096X, HS_CT_C2C);
     fill_desc<P3000x>(g_ct[CT_3000X], CT_3000X, HS_CT_C2C);
     fill_desc<P4096y>(g_ct[CT_4096Y], CT_4096Y, HS_CT_C2C);
@@ -146,6 +149,9 @@ extern "C" void hs_cu_launch_ct_c2c(int id, int sgn, const void *d_in, void *d_o
     case CT_512: launch_c2c_sgn<P512, 3, 1>(sgn, d_in, d_out, d_tw, howmany, st); break;
     case CT_256: launch_c2c_sgn<P256, 3, 1>(sgn, d_in, d_out, d_tw, howmany, st); break;
     case CT_8192: launch_c2c_sgn<P8192, 1, 1>(sgn, d_in, d_out, d_tw, howmany, st); break;
+    case CT_8192C: launch_c2c_sgn<P8192c, 1, 1>(sgn, d_in, d_out, d_tw, howmany, st); break;
+    case CT_8192D: launch_c2c_sgn<P8192d, 1, 1>(sgn, d_in, d_out, d_tw, howmany, st); break;
+    case CT_3000M3: launch_c2c_sgn<P3000, 3>(sgn, d_in, d_out, d_tw, howmany, st); break;
     case CT_4096X: launch_c2c_sgn<P4096x, 2>(sgn, d_in, d_out, d_tw, howmany, st); break;
     case CT_3000X: launch_c2c_sgn<P3000x, 2>(sgn, d_in, d_out, d_tw, howmany, st); break;
     case CT_4096Y: launch_c2c_sgn<P4096y, 2>(sgn, d_in, d_out, d_tw, howmany, st); break;

@@ -42,6 +42,7 @@ typedef struct hs_c2c {
     void *d_tw;         /* its stage twiddles in HBM */
     int jit_id;         /* >= 0: a kernel compiled for this length when the plan was created (hs_jit.cu) */
     int tp_id;          /* >= 0: compile-time two-pass transform (n = n1 * n2) */
+    int jtp_id;         /* >= 0: the two passes compiled for this length when the plan was created (hs_jit.cu) */
     int n1, n2;
     void *d_tw2, *d_twb, *d_tws; /* pass-2 stage twiddles and the inter-pass tables W_n^{k b}, W_n^{k NB} */
     int npass;          /* otherwise: run-time planned passes */

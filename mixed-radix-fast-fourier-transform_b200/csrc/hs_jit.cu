@@ -417,3 +417,184 @@ extern "C" int hs_cu_jit_has_real(int handle)
     std::lock_guard<std::mutex> lock(g_mu);
     return handle >= 0 && handle < (int)g_plans.size() && g_plans[handle]->fn_r2c != nullptr;
 }
+
+// ------------------------------------------------------------------------------------------------ two tiled passes
+// Lengths above one SM's shared memory whose stages are all compile-time radices (N = 10000, 3*2^14, 6561 ...): the factor
+// list, in execution order, is cut in two; pass 1 runs the first stages as strided sub-transforms of length n1, pass 2 the
+// rest (length n2) with the inter-pass twiddle on its loads -- the kernels of hs_tiled.cuh instantiated for these two
+// sub-plans.  Same stages, butterflies and literals in the same order as the reference's recursion, so parity is unchanged;
+// the run-time engine (hs_generic.cuh) served these lengths at about a tenth of the HBM roofline.
+struct SubChoice { int T, C, logpad, minb, threads, smem; };
+static bool choose_sub(int L, const int *rx, int nst, SubChoice &c)
+{
+    if (nst < 2 || nst > 8 || L < 16 || L > 2048) return false;
+    int maxr = 1;
+    for (int s = 0; s < nst; ++s) {
+        const int r = rx[s];
+        if (!(r == 2 || r == 3 || r == 4 || r == 5 || r == 7 || r == 8 || r == 16)) return false;
+        maxr = r > maxr ? r : maxr;
+    }
+    c.T = L / maxr;                       // one butterfly per thread in the widest stage
+    int pts = maxr;
+    while (c.T > 64 && pts * 2 <= 16) { c.T = (c.T + 1) / 2; pts *= 2; }
+    if (c.T < 1 || c.T > 256) return false;
+    std::vector<int> pr(rx, rx + nst);
+    int best = 0;
+    double best_ratio = 1e30;
+    const int cand[5] = {3, 4, 2, 5, 0};
+    for (int i = 0; i < 5; ++i) {
+        const double r = conflict_ratio(L, c.T, cand[i], pr);
+        if (r < best_ratio - 1e-9) { best_ratio = r; best = cand[i]; }
+    }
+    c.logpad = best;
+    c.C = c.T <= 16 ? 8 : (c.T <= 64 ? 4 : 2);
+    c.threads = c.T * c.C;
+    if (c.threads > 512) return false;
+    const int npad = best ? L + (L >> best) + 1 : L;
+    // same rule as hs_col_stride (hs_tiled.cuh)
+    int stride = npad;
+    const int want = c.C >= 8 ? 1 : (c.C == 4 ? 2 : 4);
+    while (c.C >= 8 ? (stride % 2 == 0) : (stride % (2 * want) != want)) ++stride;
+    c.smem = c.C * stride * 16;
+    if (c.smem > 200 * 1024) return false;
+    const int regs = pts <= 10 ? 80 : 128, w32 = (c.threads + 31) / 32 * 32;
+    int minb = (int)(65536 / ((long long)w32 * regs));
+    if (minb > 6) minb = 6;
+    while (minb > 1 && (long long)minb * (c.smem + 1024) > 227 * 1024) --minb;
+    c.minb = minb < 1 ? 1 : minb;
+    return true;
+}
+
+struct JitTwoPass {
+    long long n;
+    int sgn, dev, n1, n2;
+    hs_ct_desc desc;
+    CUmodule mod;
+    CUfunction fn[2];
+    SubChoice sc[2];
+};
+static std::vector<JitTwoPass *> g_tp;
+
+static std::string radix_list(const int *rx, int nst)
+{
+    std::string r;
+    char b[16];
+    for (int s = 0; s < nst; ++s) { snprintf(b, sizeof b, ", %d", rx[s]); r += b; }
+    return r;
+}
+
+// rx[0..nst): stage radices in execution order; the first `split` stages form pass 1.  Fills desc like a static two-pass
+// descriptor (n1, n2, radix / radix2) and returns a handle >= 0, or -1.
+extern "C" int hs_cu_jit_twopass_create(long long n, int sgn, const int *rx, int nst, int split, hs_ct_desc *desc)
+{
+    if (!jit_enabled() || split < 1 || split >= nst || nst - split > 8 || split > 8) return -1;
+    std::lock_guard<std::mutex> lock(g_mu);
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    long long n1 = 1, n2 = 1;
+    for (int s = 0; s < split; ++s) n1 *= rx[s];
+    for (int s = split; s < nst; ++s) n2 *= rx[s];
+    if (n1 * n2 != n) return -1;
+    for (size_t i = 0; i < g_tp.size(); ++i)
+        if (g_tp[i]->n == n && g_tp[i]->sgn == sgn && g_tp[i]->dev == dev && g_tp[i]->n1 == n1) { *desc = g_tp[i]->desc; return (int)i; }
+    SubChoice c1, c2;
+    if (!choose_sub((int)n1, rx, split, c1) || !choose_sub((int)n2, rx + split, nst - split, c2)) return -1;
+    Nvrtc *rt = nvrtc();
+    Driver *drv = driver();
+    if (!rt || !drv) return -1;
+    char buf[4096];
+    snprintf(buf, sizeof buf,
+             "#include \"hs_tiled.cuh\"\n"
+             "using P1 = HsPlan<%d, %d, 1, %d, -2, 0%s>;\n"
+             "using P2 = HsPlan<%d, %d, 1, %d, -2, 0%s>;\n"
+             "extern \"C\" __global__ void __launch_bounds__(%d, %d)\n"
+             "hs_jit_pass1(const cplx *__restrict__ in, cplx *__restrict__ out, const cplx *__restrict__ tw, const HsTileGeom g, long long howmany)\n"
+             "{\n"
+             "    HS_DYN_SMEM(cplx, smem);\n"
+             "    const int tiles = (g.ncols + %d - 1) / %d;\n"
+             "    const long long xf = HS_BID / tiles;\n"
+             "    const int c0 = (int)(HS_BID %% tiles) * %d;\n"
+             "    HsNoHooks hk;\n"
+             "    hs_tile_run<P1, %d, %d, 0, false, 0, 1, 0, 0>(in + xf * g.in_xf, out + xf * g.out_xf, tw, g, xf, c0, smem, HS_TID, true, hk);\n"
+             "}\n"
+             "extern \"C\" __global__ void __launch_bounds__(%d, %d)\n"
+             "hs_jit_pass2(const cplx *__restrict__ in, cplx *__restrict__ out, const cplx *__restrict__ tw, const HsTileGeom g, long long howmany)\n"
+             "{\n"
+             "    HS_DYN_SMEM(cplx, smem);\n"
+             "    const int tiles = (g.ncols + %d - 1) / %d;\n"
+             "    const long long xf = HS_BID / tiles;\n"
+             "    const int c0 = (int)(HS_BID %% tiles) * %d;\n"
+             "    HsNoHooks hk;\n"
+             "    hs_tile_run<P2, %d, %d, 1, true, 0, 1, 0, 0>(in + xf * g.in_xf, out + xf * g.out_xf, tw, g, xf, c0, smem, HS_TID, true, hk);\n"
+             "}\n",
+             (int)n1, c1.T, c1.logpad, radix_list(rx, split).c_str(), (int)n2, c2.T, c2.logpad, radix_list(rx + split, nst - split).c_str(),
+             c1.threads, c1.minb, c1.C, c1.C, c1.C, sgn, c1.C, c2.threads, c2.minb, c2.C, c2.C, c2.C, sgn, c2.C);
+    nvrtcProgram prog = nullptr;
+    if (rt->CreateProgram(&prog, buf, "hs_jit_twopass.cu", hs_jit_src_count, hs_jit_src_texts, hs_jit_src_names) != 0) return -1;
+    const char *opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-default-device", "-DHS_JIT=1"};
+    if (rt->CompileProgram(prog, 4, opts) != 0) {
+        size_t ls = 0;
+        rt->GetProgramLogSize(prog, &ls);
+        std::string log(ls + 1, '\0');
+        if (ls) rt->GetProgramLog(prog, &log[0]);
+        fprintf(stderr, "hsfft: plan-time compilation of the two passes for N=%lld failed (falling back to the run-time engine):\n%s\n", n, log.c_str());
+        rt->DestroyProgram(&prog);
+        return -1;
+    }
+    size_t cs = 0;
+    rt->GetCUBINSize(prog, &cs);
+    std::vector<char> cubin(cs);
+    rt->GetCUBIN(prog, cubin.data());
+    rt->DestroyProgram(&prog);
+    JitTwoPass *p = new JitTwoPass();
+    p->n = n; p->sgn = sgn; p->dev = dev; p->n1 = (int)n1; p->n2 = (int)n2; p->sc[0] = c1; p->sc[1] = c2;
+    HS_CUDA_CHECK(cudaFree(0));
+    if (drv->ModuleLoadData(&p->mod, cubin.data()) != CUDA_SUCCESS || drv->ModuleGetFunction(&p->fn[0], p->mod, "hs_jit_pass1") != CUDA_SUCCESS ||
+        drv->ModuleGetFunction(&p->fn[1], p->mod, "hs_jit_pass2") != CUDA_SUCCESS) {
+        fprintf(stderr, "hsfft: loading the plan-time passes for N=%lld failed (falling back to the run-time engine)\n", n);
+        delete p;
+        return -1;
+    }
+    for (int k = 0; k < 2; ++k) drv->FuncSetAttribute(p->fn[k], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, p->sc[k].smem);
+    memset(&p->desc, 0, sizeof p->desc);
+    p->desc.id = (int)g_tp.size();
+    p->desc.family = HS_CT_TWOPASS;
+    p->desc.n = (int)n;
+    p->desc.n1 = (int)n1; p->desc.n2 = (int)n2;
+    p->desc.nst = split; p->desc.nst2 = nst - split;
+    for (int s = 0; s < split; ++s) p->desc.radix[s] = rx[s];
+    for (int s = split; s < nst; ++s) p->desc.radix2[s - split] = rx[s];
+    p->desc.split_min = p->desc.split_min2 = -2;
+    p->desc.threads = c1.threads; p->desc.smem_bytes = c1.smem;
+    if (getenv("HSFFT_VERBOSE"))
+        fprintf(stderr, "hsfft: plan-time passes N=%lld = %lld x %lld: pass 1 T=%d C=%d LOGPAD=%d %d CTAs/SM, pass 2 T=%d C=%d LOGPAD=%d %d CTAs/SM\n", n, n1, n2,
+                c1.T, c1.C, c1.logpad, c1.minb, c2.T, c2.C, c2.logpad, c2.minb);
+    g_tp.push_back(p);
+    *desc = p->desc;
+    return p->desc.id;
+}
+
+// pass 1 or 2 with the geometry of a contiguous batch (as launch_twopass in hs_ct_table.cuh)
+extern "C" void hs_cu_jit_twopass_launch(int handle, int pass, const void *d_in, void *d_out, const void *d_tw, const void *d_twb, const void *d_tws,
+                                         long long howmany, void *stream)
+{
+    JitTwoPass *p;
+    {
+        std::lock_guard<std::mutex> lock(g_mu);
+        if (handle < 0 || handle >= (int)g_tp.size()) { fprintf(stderr, "Error: unknown plan-time two-pass plan %d\n", handle); exit(EXIT_FAILURE); }
+        p = g_tp[handle];
+    }
+    hs_tile_geom g;
+    memset(&g, 0, sizeof g);
+    g.in_xf = g.out_xf = p->n;
+    const SubChoice &c = p->sc[pass - 1];
+    if (pass == 1) { g.ncols = p->n2; g.in_c = 1; g.in_e = p->n2; g.out_c = p->n1; g.out_e = 1; }
+    else { g.ncols = p->n1; g.in_c = 1; g.in_e = p->n1; g.out_c = 1; g.out_e = p->n1; g.twb = d_twb; g.tws = d_tws; g.tw_ld = p->n1; }
+    const long long blocks = howmany * ((g.ncols + c.C - 1) / c.C);
+    if (blocks <= 0 || blocks > 2147483647LL) { fprintf(stderr, "Error: batch too large for one launch (%lld CTAs)\n", blocks); exit(EXIT_FAILURE); }
+    void *args[] = {(void *)&d_in, (void *)&d_out, (void *)&d_tw, (void *)&g, (void *)&howmany};
+    const CUresult r = driver()->LaunchKernel(p->fn[pass - 1], (unsigned)blocks, 1, 1, (unsigned)c.threads, 1, 1, (unsigned)c.smem, (CUstream)stream, args, nullptr);
+    if (r != CUDA_SUCCESS) { fprintf(stderr, "Error: CUDA failure %d launching plan-time pass %d for N=%lld\n", (int)r, pass, p->n); exit(EXIT_FAILURE); }
+    hs_cu_count_launch();
+    hs_cu_timing_mark(pass == 1 ? "tiled pass1 (plan-time kernel)" : "tiled pass2 (plan-time kernel)", stream);
+}

@@ -28,6 +28,9 @@ using P2048  = HsPlan<2048, 128, 2, 3, -1, 0, 16, 16, 8>;        // reference fa
 using P512   = HsPlan<512, 64, 4, 3, -1, 0, 8, 8, 8>;
 using P256   = HsPlan<256, 16, 16, 4, -1, 0, 16, 16>;
 using P8192  = HsPlan<8192, 512, 1, 4, -1, 0, 8, 8, 8, 16>;
+// A/B candidates: 8192 points with 1024 threads (8 points per thread, five passes, 64 registers: twice the warps of P8192)
+using P8192c = HsPlan<8192, 1024, 1, 3, -1, 0, 4, 8, 8, 8, 4>;
+using P8192d = HsPlan<8192, 1024, 1, 3, -1, 0, 8, 8, 8, 8, 2>;
 // fused Bluestein, M = 2048 (N = 513..1024, e.g. the N = 1009 config): forward / inverse pair
 using PB2048f = HsPlan<2048, 128, 1, 4, HS_B2048_SPLIT, 0, 8, 16, 16>;
 using PB2048i = HsPlan<2048, 128, 1, 4, HS_B2048_SPLIT, 0, 16, 16, 8>;
@@ -114,4 +117,5 @@ enum { CT_4096A = 0, CT_4096B, CT_3000, CT_1024, CT_2048, CT_512, CT_256, CT_819
        CT_B256, CT_B512, CT_B1024, CT_B4096, CT_B8192,
        CT_R1008, CT_R1008A, CT_R1008G, CT_R256, CT_B2048X2, CT_B256X16,
        CT_H1024, CT_H2048, CT_H4096, CT_H8192, CT_H10240,
-       CT_C4096, CT_C8192, CT_C10240, CT_C10240S, CT_C10240L, CT_C10240H, CT_COUNT };
+       CT_C4096, CT_C8192, CT_C10240, CT_C10240S, CT_C10240L, CT_C10240H,
+       CT_8192C, CT_8192D, CT_3000M3, CT_COUNT };

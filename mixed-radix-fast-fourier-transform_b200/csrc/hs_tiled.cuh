@@ -330,8 +330,9 @@ HS_DEVICE void hs_tile_run(const cplx *HS_RESTRICT in_x, cplx *HS_RESTRICT out_x
     constexpr int NPADC = hs_col_stride(P::NPAD, C);
     const int colA = tid % C, tA = tid / C;       // lane = column
     const int colB = tid / P::T, tB = tid % P::T; // lane = thread of a team
-    const HsLane first{smem + colA * NPADC, tA, on};
-    const HsLane rest = STCOL ? first : HsLane{smem + colB * NPADC, tB, on};
+    // a partial last tile (column count not a multiple of C): columns beyond the end only take part in the barriers
+    const HsLane first{smem + colA * NPADC, tA, on && c0 + colA < g.ncols};
+    const HsLane rest = STCOL ? first : HsLane{smem + colB * NPADC, tB, on && c0 + colB < g.ncols};
     const int colS = STCOL ? colA : colB;
     static_assert(!STG || IO == 0 || IO == 2, "only plain tile loads can be staged");
     if constexpr (IO == 1) { // forward pass 1 of the long Bluestein
@@ -356,7 +357,7 @@ HS_DEVICE void hs_tile_run(const cplx *HS_RESTRICT in_x, cplx *HS_RESTRICT out_x
         HsLoadColTw<LDP> ld;
         ld.base = in_x; ld.off0 = (long long)(c0 + colA) * g.in_c; ld.es = g.in_e;
         ld.blk_log = g.blk_log; ld.blk_stride = g.blk_stride;
-        ld.twb = (const cplx *)g.twb + (c0 + colA); ld.tw_ld = g.tw_ld; ld.step = on ? hs_ld_tab((const cplx *)g.tws + (c0 + colA)) : hs_c(0.0, 0.0);
+        ld.twb = (const cplx *)g.twb + (c0 + colA); ld.tw_ld = g.tw_ld; ld.step = first.active ? hs_ld_tab((const cplx *)g.tws + (c0 + colA)) : hs_c(0.0, 0.0);
         hs_fft_team2<P, SGN>(ld, st, first, rest, tw, hk);
     } else if constexpr (IO == 7) { // last pass of phase A of the distributed transform: twiddle and store to the owning rank
         static_assert(STCOL && TW != 1, "the exchange store keeps lane = column");
@@ -365,7 +366,7 @@ HS_DEVICE void hs_tile_run(const cplx *HS_RESTRICT in_x, cplx *HS_RESTRICT out_x
             HsLoadColTw<LDP> ld;
             ld.base = in_x; ld.off0 = (long long)(c0 + colA) * g.in_c; ld.es = g.in_e;
             ld.blk_log = g.blk_log; ld.blk_stride = g.blk_stride;
-            ld.twb = (const cplx *)g.twb + xf; ld.tw_ld = g.tw_ld; ld.step = on ? hs_ld_tab((const cplx *)g.tws + xf) : hs_c(0.0, 0.0);
+            ld.twb = (const cplx *)g.twb + xf; ld.tw_ld = g.tw_ld; ld.step = first.active ? hs_ld_tab((const cplx *)g.tws + xf) : hs_c(0.0, 0.0);
             hs_fft_team2<P, SGN>(ld, st, first, rest, tw, hk);
         } else {
             HsLoadCol<LDP> ld;
@@ -381,7 +382,7 @@ HS_DEVICE void hs_tile_run(const cplx *HS_RESTRICT in_x, cplx *HS_RESTRICT out_x
             HsLoadColTw<LDP> ld;
             ld.base = in_x; ld.off0 = (long long)(c0 + colA) * g.in_c; ld.es = g.in_e;
             ld.blk_log = g.blk_log; ld.blk_stride = g.blk_stride;
-            ld.twb = (const cplx *)g.twb + xf; ld.tw_ld = g.tw_ld; ld.step = on ? hs_ld_tab((const cplx *)g.tws + xf) : hs_c(0.0, 0.0);
+            ld.twb = (const cplx *)g.twb + xf; ld.tw_ld = g.tw_ld; ld.step = first.active ? hs_ld_tab((const cplx *)g.tws + xf) : hs_c(0.0, 0.0);
             hs_fft_team2<P, SGN>(ld, st, first, rest, tw, hk);
         } else {
             HsLoadCol<LDP> ld;
@@ -411,7 +412,7 @@ HS_DEVICE void hs_tile_run(const cplx *HS_RESTRICT in_x, cplx *HS_RESTRICT out_x
             hs_fft_team2<P, SGN>(ld, st, first, rest, tw, hk);
         }
         hk.sync();
-        if (on) {
+        if (rest.active) {
             const cplx *z = rest.sm;
             cplx *oe = out_x + (long long)(c0 + colB) * g.out_c, *oo = oe + g.out_c / 2; // g.out_c = two rows of the workspace
             for (int k1 = tB; k1 <= P::N / 2; k1 += P::T) {
@@ -426,7 +427,7 @@ HS_DEVICE void hs_tile_run(const cplx *HS_RESTRICT in_x, cplx *HS_RESTRICT out_x
         HsLoadColTw<LDP> ld;
         ld.base = in_x; ld.off0 = (long long)(c0 + colA) * g.in_c; ld.es = g.in_e;
         ld.blk_log = g.blk_log; ld.blk_stride = g.blk_stride;
-        ld.twb = (const cplx *)g.twb + (c0 + colA); ld.tw_ld = g.tw_ld; ld.step = on ? hs_ld_tab((const cplx *)g.tws + (c0 + colA)) : hs_c(0.0, 0.0);
+        ld.twb = (const cplx *)g.twb + (c0 + colA); ld.tw_ld = g.tw_ld; ld.step = first.active ? hs_ld_tab((const cplx *)g.tws + (c0 + colA)) : hs_c(0.0, 0.0);
         hs_fft_team2<P, SGN>(ld, st, first, rest, tw, hk);
     } else if constexpr (IO == 2) { // inverse last pass of the long Bluestein
         static_assert(TW != 0, "the chirp-and-crop store belongs to a second pass");
@@ -435,13 +436,13 @@ HS_DEVICE void hs_tile_run(const cplx *HS_RESTRICT in_x, cplx *HS_RESTRICT out_x
         if constexpr (STG) {
             HsLoadTileTw ld;
             ld.tile = in_x + colA; ld.C = C;
-            ld.twb = (const cplx *)g.twb + k; ld.tw_ld = g.tw_ld; ld.step = on ? hs_ld_tab((const cplx *)g.tws + k) : hs_c(0.0, 0.0);
+            ld.twb = (const cplx *)g.twb + k; ld.tw_ld = g.tw_ld; ld.step = first.active ? hs_ld_tab((const cplx *)g.tws + k) : hs_c(0.0, 0.0);
             hs_fft_team2<P, SGN>(ld, st, first, rest, tw, hk);
         } else {
             HsLoadColTw<LDP> ld;
             ld.base = in_x; ld.off0 = (long long)(c0 + colA) * g.in_c; ld.es = g.in_e;
             ld.blk_log = g.blk_log; ld.blk_stride = g.blk_stride;
-            ld.twb = (const cplx *)g.twb + k; ld.tw_ld = g.tw_ld; ld.step = on ? hs_ld_tab((const cplx *)g.tws + k) : hs_c(0.0, 0.0);
+            ld.twb = (const cplx *)g.twb + k; ld.tw_ld = g.tw_ld; ld.step = first.active ? hs_ld_tab((const cplx *)g.tws + k) : hs_c(0.0, 0.0);
             hs_fft_team2<P, SGN>(ld, st, first, rest, tw, hk);
         }
     } else if constexpr (TW != 0) {
@@ -450,13 +451,13 @@ HS_DEVICE void hs_tile_run(const cplx *HS_RESTRICT in_x, cplx *HS_RESTRICT out_x
         if constexpr (STG) {
             HsLoadTileTw ld;
             ld.tile = in_x + colA; ld.C = C;
-            ld.twb = (const cplx *)g.twb + k; ld.tw_ld = g.tw_ld; ld.step = on ? hs_ld_tab((const cplx *)g.tws + k) : hs_c(0.0, 0.0);
+            ld.twb = (const cplx *)g.twb + k; ld.tw_ld = g.tw_ld; ld.step = first.active ? hs_ld_tab((const cplx *)g.tws + k) : hs_c(0.0, 0.0);
             hs_fft_team2<P, SGN>(ld, st, first, rest, tw, hk);
         } else {
             HsLoadColTw<LDP> ld;
             ld.base = in_x; ld.off0 = (long long)(c0 + colA) * g.in_c; ld.es = g.in_e;
             ld.blk_log = g.blk_log; ld.blk_stride = g.blk_stride;
-            ld.twb = (const cplx *)g.twb + k; ld.tw_ld = g.tw_ld; ld.step = on ? hs_ld_tab((const cplx *)g.tws + k) : hs_c(0.0, 0.0);
+            ld.twb = (const cplx *)g.twb + k; ld.tw_ld = g.tw_ld; ld.step = first.active ? hs_ld_tab((const cplx *)g.tws + k) : hs_c(0.0, 0.0);
             hs_fft_team2<P, SGN>(ld, st, first, rest, tw, hk);
         }
     } else {
@@ -480,10 +481,10 @@ HS_GLOBAL void HS_LAUNCH_BOUNDS(P::T *C, MINB)
 hs_tiled_kernel(const cplx *HS_RESTRICT in, cplx *HS_RESTRICT out, const cplx *HS_RESTRICT tw, const HsTileGeom g, long long howmany)
 {
     HS_DYN_SMEM(cplx, smem);
-    const int tiles = (g.ncols + C - 1) / C; // a partial last tile only where the columns keep their lane (IO 9: n1/2+1 rows)
+    const int tiles = (g.ncols + C - 1) / C; // the last tile may be partial (hs_tile_run masks its missing columns)
     const long long xf = HS_BID / tiles;
     const int c0 = (int)(HS_BID % tiles) * C;
-    const bool on = !STCOL || c0 + HS_TID % C < g.ncols;
+    const bool on = true;
     HsNoHooks hk;
     hs_tile_run<P, SGN, C, TW, STCOL, IO, CS, 0, 0>(in + xf * g.in_xf, out + xf * g.out_xf, tw, g, xf, c0, smem, HS_TID, on, hk);
 }

@@ -324,6 +324,7 @@ static hs_c2c *c2c_create(int n, int sgn, int allow_exact)
     p->ct_id = -1;
     p->tp_id = -1;
     p->jit_id = -1;
+    p->jtp_id = -1;
     const hs_ct_desc *ct = find_ct(HS_CT_C2C, n);
     if (ct) {
         p->ct_id = ct->id;
@@ -370,6 +371,31 @@ static hs_c2c *c2c_create(int n, int sgn, int allow_exact)
         if (id >= 0) {
             p->jit_id = id;
             p->d_tw = upload_stage_twiddles(jd.radix, jd.nst, sgn, jd.split_min);
+            return p;
+        }
+    }
+    /* longer lengths whose stages are all compile-time radices (and shorter ones the one-kernel planner turned down, e.g.
+     * 3^8): two tiled passes compiled now; the factor list (execution order) is cut where the two sub-transform lengths
+     * are closest */
+    if (n >= 1024 && lf >= 4) {
+        int cand[64], nc = 0;
+        for (int a = 2; a <= lf - 2; ++a) cand[nc++] = a;
+        for (int i = 0; i < nc; ++i)       /* order the cuts by |log n1 - log n2| */
+            for (int j = i + 1; j < nc; ++j) {
+                double pi_ = 1, pj = 1;
+                for (int s = 0; s < cand[i]; ++s) pi_ *= rx[s];
+                for (int s = 0; s < cand[j]; ++s) pj *= rx[s];
+                if (fabs(log(pi_ * pi_ / n)) > fabs(log(pj * pj / n))) { const int t = cand[i]; cand[i] = cand[j]; cand[j] = t; }
+            }
+        for (int i = 0; i < nc && i < 3; ++i) {
+            hs_ct_desc jd;
+            const int id = hs_cu_jit_twopass_create(n, sgn, rx, lf, cand[i], &jd);
+            if (id < 0) continue;
+            p->jtp_id = id;
+            p->n1 = jd.n1; p->n2 = jd.n2;
+            p->d_tw = upload_stage_twiddles(jd.radix, jd.nst, sgn, jd.split_min);
+            p->d_tw2 = upload_stage_twiddles(jd.radix2, jd.nst2, sgn, jd.split_min2);
+            p->d_twb = hs_upload_interpass_tables(n, sgn, jd.n2 / jd.radix2[0], jd.n1, jd.n1, &p->d_tws);
             return p;
         }
     }
@@ -519,7 +545,7 @@ void hs_c2c_destroy(hs_c2c *p)
 
 size_t hs_c2c_ws_elems(const hs_c2c *p, long long howmany)
 {
-    if (p->tp_id >= 0) return (size_t)howmany * p->n;
+    if (p->tp_id >= 0 || p->jtp_id >= 0) return (size_t)howmany * p->n;
     return (p->ct_id < 0 && p->npass > 1) ? (size_t)howmany * p->n : 0;
 }
 
@@ -528,6 +554,11 @@ void hs_c2c_exec(const hs_c2c *p, const void *d_in, void *d_out, void *d_ws, lon
     if (howmany <= 0) return;
     if (p->ct_id >= 0) { hs_cu_launch_ct_c2c(p->ct_id, p->sgn, d_in, d_out, p->d_tw, howmany, stream); return; }
     if (p->jit_id >= 0) { hs_cu_jit_c2c_launch(p->jit_id, d_in, d_out, p->d_tw, howmany, stream); return; }
+    if (p->jtp_id >= 0) {
+        hs_cu_jit_twopass_launch(p->jtp_id, 1, d_in, d_ws, p->d_tw, NULL, NULL, howmany, stream);
+        hs_cu_jit_twopass_launch(p->jtp_id, 2, d_ws, d_out, p->d_tw2, p->d_twb, p->d_tws, howmany, stream);
+        return;
+    }
     if (p->tp_id >= 0) {
         hs_cu_launch_ct_twopass(p->tp_id, 1, p->sgn, d_in, d_ws, p->d_tw, NULL, NULL, howmany, stream);
         hs_cu_launch_ct_twopass(p->tp_id, 2, p->sgn, d_ws, d_out, p->d_tw2, p->d_twb, p->d_tws, howmany, stream);
@@ -1200,7 +1231,7 @@ void fft_exec_batch_inplace_dev(fft_object obj, fft_data *d_data, long howmany, 
     /* unsafe on the caller's buffer: the run-time engine's multi-pass plans (pass 1 writes into the output while other CTAs
      * still read the input) and the split chirp-z kernel (parks its first half-convolution in the output row, then reads
      * the input row again) */
-    const int copy = (p && p->ct_id < 0 && p->jit_id < 0 && p->tp_id < 0 && p->npass > 1) || (d->lt == 1 && d->split_ct_id >= 0);
+    const int copy = (p && p->ct_id < 0 && p->jit_id < 0 && p->tp_id < 0 && p->jtp_id < 0 && p->npass > 1) || (d->lt == 1 && d->split_ct_id >= 0);
     char *ws = (char *)hs_scratch_get(&d->ws_pool, stream, wsb + (copy ? bytes : 0));
     if (copy) {
         hs_cu_d2d(ws + wsb, d_data, bytes, stream);
@@ -1242,6 +1273,8 @@ const char *hsfft_plan_describe(fft_object obj)
         const hs_c2c *p = d->direct;
         if (p->ct_id >= 0) n = snprintf(buf, sizeof buf, "mixed-radix N=%d: compile-time smem kernel #%d", d->N, p->ct_id);
         else if (p->jit_id >= 0) n = snprintf(buf, sizeof buf, "mixed-radix N=%d: smem kernel compiled for this plan (NVRTC) #%d", d->N, p->jit_id);
+        else if (p->jtp_id >= 0)
+            n = snprintf(buf, sizeof buf, "mixed-radix N=%d = %d x %d: two tiled passes compiled for this plan (NVRTC) #%d", d->N, p->n1, p->n2, p->jtp_id);
         else if (p->tp_id >= 0)
             n = snprintf(buf, sizeof buf, "mixed-radix N=%d: compile-time two-pass kernels #%d", d->N, p->tp_id);
         else {

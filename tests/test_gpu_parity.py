@@ -578,3 +578,20 @@ def test_in_place_execution(hs, product_lib, oracle, n):
         got = torch.view_as_complex(buf).cpu().numpy()
         assert per_transform_worst(got, oracle.c2c(x, sgn)) <= tol(n), (n, sgn, desc)
 
+
+JIT_TWOPASS_SIZES = [6561, 10000, 12000, 3 << 14, 50000, 100000, 3 << 16, 250000, 1000000]
+
+
+@pytest.mark.parametrize("n", JIT_TWOPASS_SIZES)
+def test_plan_time_compiled_two_pass_kernels(hs, product_lib, oracle, n):
+    """Smooth lengths above one SM's shared memory without a static plan: the factor list is cut in two and both tiled
+    passes are compiled with NVRTC at plan creation (csrc/hs_jit.cu) -- same stages, butterflies and literals in the
+    reference's order, partial last tiles where a sub-length is not a multiple of the tile width."""
+    for sgn in (1, -1):
+        x = rand_cplx(3, n, seed=n + sgn)
+        with hs.Plan(n, sgn) as p:
+            desc = p.describe()
+            y = p.exec(x)
+        assert "two tiled passes compiled" in desc, desc
+        assert per_transform_worst(y, oracle.c2c(x, sgn)) <= tol(n), (n, sgn, desc)
+
