@@ -209,6 +209,54 @@ HS_DEVICE void hs_bfly_generic(cplx *v, int r, const double *cs, const double *s
     }
 }
 
+
+// Odd prime radices 11, 13, 17 with compile-time tables: the reference's generic butterfly (src/highSpeedFFT.c:1475-1628: sums and
+// differences of mirrored inputs, then one cosine and one sine sum per output pair) fully unrolled, so that lengths with
+// these factors get plan-time kernels like every other length (hs_jit.cu).  The reference evaluates cos / sin(i*PI2/r) in double
+// precision; the literals below are those values (no truncation here: only the radix-3/5/7 butterflies carry 11-digit constants).
+template <int R> struct HsOddTab;
+template <> struct HsOddTab<11> {
+    static HS_HD double cs(int i) { constexpr double t[10] = {8.41253532831181168863e-01, 4.15415013001886425489e-01, -1.42314838273285140460e-01, -6.54860733945285064127e-01, -9.59492973614497389901e-01, -9.59492973614497389901e-01, -6.54860733945285064072e-01, -1.42314838273285140243e-01, 4.15415013001886425679e-01, 8.41253532831181168917e-01}; return t[i]; }
+    static HS_HD double sn(int i) { constexpr double t[10] = {5.40640817455597582101e-01, 9.09631995354518371418e-01, 9.89821441880932732359e-01, 7.55749574354258283704e-01, 2.81732556841429697652e-01, -2.81732556841429697734e-01, -7.55749574354258283758e-01, -9.89821441880932732414e-01, -9.09631995354518371364e-01, -5.40640817455597581993e-01}; return t[i]; }
+};
+template <> struct HsOddTab<13> {
+    static HS_HD double cs(int i) { constexpr double t[12] = {8.85456025653209895872e-01, 5.68064746731155802487e-01, 1.20536680255323053250e-01, -3.54604887042535626003e-01, -7.48510748171101098684e-01, -9.70941817426052027193e-01, -9.70941817426052027193e-01, -7.48510748171101098630e-01, -3.54604887042535626003e-01, 1.20536680255323053460e-01, 5.68064746731155802378e-01, 8.85456025653209896089e-01}; return t[i]; }
+    static HS_HD double sn(int i) { constexpr double t[12] = {4.64723172043768545663e-01, 8.22983865893656394580e-01, 9.92708874098053992835e-01, 9.35016242685414823450e-01, 6.63122658240795202322e-01, 2.39315664287557766952e-01, -2.39315664287557767061e-01, -6.63122658240795202430e-01, -9.35016242685414823450e-01, -9.92708874098053992781e-01, -8.22983865893656394688e-01, -4.64723172043768545310e-01}; return t[i]; }
+};
+template <> struct HsOddTab<17> {
+    static HS_HD double cs(int i) { constexpr double t[16] = {9.32472229404355804593e-01, 7.39008917220659115909e-01, 4.45738355776538267358e-01, 9.22683594633019952527e-02, -2.73662990072082863561e-01, -6.02634636379256389269e-01, -8.50217135729614152131e-01, -9.82973099683901778260e-01, -9.82973099683901778260e-01, -8.50217135729614152076e-01, -6.02634636379256389161e-01, -2.73662990072082863371e-01, 9.22683594633019951375e-02, 4.45738355776538267439e-01, 7.39008917220659116072e-01, 9.32472229404355804538e-01}; return t[i]; }
+    static HS_HD double sn(int i) { constexpr double t[16] = {3.61241666187152948744e-01, 6.73695643646557211731e-01, 8.95163291355062322062e-01, 9.95734176295034521895e-01, 9.61825643172819070399e-01, 7.98017227280239503260e-01, 5.26432162877355800247e-01, 1.83749517816570331603e-01, -1.83749517816570331698e-01, -5.26432162877355800301e-01, -7.98017227280239503315e-01, -9.61825643172819070453e-01, -9.95734176295034521895e-01, -8.95163291355062322062e-01, -6.73695643646557211569e-01, -3.61241666187152948798e-01}; return t[i]; }
+};
+template <int R, int SGN>
+HS_HD void hs_bfly_oddct(cplx *v)
+{
+    constexpr int H = (R - 1) / 2;
+    cplx tp[H], tm[H];
+    const cplx y0 = v[0];
+    cplx acc = y0;
+    HS_UNROLL
+    for (int i = 0; i < H; ++i) {
+        tp[i] = hs_add(v[i + 1], v[R - 1 - i]);
+        tm[i] = hs_sub(v[i + 1], v[R - 1 - i]);
+        acc = hs_add(acc, tp[i]);
+    }
+    v[0] = acc;
+    HS_UNROLL
+    for (int u = 0; u < H; ++u) {
+        cplx p = y0, q = hs_c(0.0, 0.0);
+        HS_UNROLL
+        for (int w = 0; w < H; ++w) {
+            const int t = ((u + 1) * (w + 1)) % R;
+            const double c = HsOddTab<R>::cs(t - 1), s = HsOddTab<R>::sn(t - 1);
+            p.x += c * tp[w].x; p.y += c * tp[w].y;
+            q.x -= s * tm[w].x; q.y -= s * tm[w].y;
+        }
+        if (SGN != 1) { q.x = -q.x; q.y = -q.y; }
+        v[u + 1] = hs_c(p.x - q.y, p.y + q.x);
+        v[R - u - 1] = hs_c(p.x + q.y, p.y - q.x);
+    }
+}
+
 // compile-time radix dispatch; EXACT selects the full-precision radix-3/5/7 constants (Bluestein-internal
 // transforms only -- a transform the reference itself runs must keep the reference's literals)
 template <int R, int SGN, bool EXACT = false>
@@ -221,4 +269,5 @@ HS_HD void hs_bfly(cplx *v)
     else if (R == 7) { if (EXACT) hs_bfly7_exact<SGN>(v); else hs_bfly7<SGN>(v); }
     else if (R == 8) hs_bfly8<SGN>(v);
     else if (R == 16) hs_bfly16<SGN>(v);
+    if constexpr (R == 11 || R == 13 || R == 17) hs_bfly_oddct<R, SGN>(v);
 }

@@ -153,7 +153,7 @@ static bool choose(int n, const int *rx, int nst, JitChoice &c)
     if (nst < 2 || nst > 8 || n > 8192 || n < 16) return false;
     for (int s = 0; s < nst; ++s) {
         const int r = rx[s];
-        if (!(r == 2 || r == 3 || r == 4 || r == 5 || r == 7 || r == 8 || r == 16)) return false;
+        if (!(r == 2 || r == 3 || r == 4 || r == 5 || r == 7 || r == 8 || r == 16 || r == 11 || r == 13 || r == 17)) return false;
     }
     // fuse neighbouring stages while the pair stays within 16 points per butterfly (one exchange less each)
     // (HSFFT_JIT_FUSE / _T / _X / _MINB / _LOGPAD override the choices below: tuning aids)
@@ -431,7 +431,7 @@ static bool choose_sub(int L, const int *rx, int nst, SubChoice &c)
     int maxr = 1;
     for (int s = 0; s < nst; ++s) {
         const int r = rx[s];
-        if (!(r == 2 || r == 3 || r == 4 || r == 5 || r == 7 || r == 8 || r == 16)) return false;
+        if (!(r == 2 || r == 3 || r == 4 || r == 5 || r == 7 || r == 8 || r == 16 || r == 11 || r == 13 || r == 17)) return false;
         maxr = r > maxr ? r : maxr;
     }
     c.T = L / maxr;                       // one butterfly per thread in the widest stage

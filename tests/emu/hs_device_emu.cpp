@@ -247,3 +247,15 @@ void hs_cu_launch_slice_rows(const void *src, int P, int start, int len, void *d
     ++g_launches;
 }
 }
+
+// unit hook for tests: one odd-radix butterfly with compile-time tables (hs_butterflies.cuh), v[r] in place
+extern "C" int hs_emu_bfly_odd(int r, int sgn, double *v)
+{
+    cplx *c = reinterpret_cast<cplx *>(v);
+    if (r == 11) { if (sgn == 1) hs_bfly<11, 1>(c); else hs_bfly<11, -1>(c); }
+    else if (r == 13) { if (sgn == 1) hs_bfly<13, 1>(c); else hs_bfly<13, -1>(c); }
+    else if (r == 17) { if (sgn == 1) hs_bfly<17, 1>(c); else hs_bfly<17, -1>(c); }
+    else return -1;
+    return 0;
+}
+

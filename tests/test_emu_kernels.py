@@ -367,3 +367,17 @@ def test_in_place_execution(hs, emu_lib, oracle, n):
     r = oracle.c2c(x, 1)
     assert max(rel_rms(buf[i], r[i]) for i in range(3)) <= tol(n), (n, desc)
 
+
+@pytest.mark.parametrize("r", [11, 13, 17])
+def test_odd_radix_butterflies_with_compile_time_tables(emu_lib, r):
+    """hs_bfly<11 / 13 / 17>: the reference's generic butterfly unrolled with literal cos / sin tables (plan-time kernels
+    for lengths with these factors): a plain r-point DFT to rounding, both directions."""
+    import ctypes as C
+    x = rand_cplx(1, r, seed=r)[0]
+    k = np.arange(r)
+    for sgn in (1, -1):
+        v = x.copy()
+        assert emu_lib.hs_emu_bfly_odd(r, sgn, v.ctypes.data_as(C.c_void_p)) == 0
+        ref = np.exp(-2j * np.pi * sgn * np.outer(k, k) / r) @ x
+        assert rel_rms(v, ref) <= 5e-16 * r
+

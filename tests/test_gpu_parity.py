@@ -85,7 +85,7 @@ def test_generic_engine_matches_compile_time_kernels(hs, product_lib, oracle, n)
     assert per_transform_worst(y, oracle.c2c(x, 1)) <= tol(n)
 
 
-JIT_SIZES = [24, 96, 360, 640, 1000, 1536, 2000, 2187, 2401, 3072, 3125, 5000, 6000, 6561, 7000, 8000]
+JIT_SIZES = [24, 96, 360, 640, 1000, 1001, 1144, 1536, 2000, 2002, 2187, 2401, 3072, 3125, 5632, 5000, 6000, 6561, 7000, 8000]
 
 
 @pytest.mark.parametrize("n", JIT_SIZES)
@@ -579,7 +579,7 @@ def test_in_place_execution(hs, product_lib, oracle, n):
         assert per_transform_worst(got, oracle.c2c(x, sgn)) <= tol(n), (n, sgn, desc)
 
 
-JIT_TWOPASS_SIZES = [10000, 12000, 3 << 14, 50000, 100000, 3 << 16, 250000, 1000000]
+JIT_TWOPASS_SIZES = [11 * 1024, 13 * 4096, 17 * 512, 10000, 12000, 3 << 14, 50000, 100000, 3 << 16, 250000, 1000000]
 
 
 @pytest.mark.parametrize("n", JIT_TWOPASS_SIZES)
