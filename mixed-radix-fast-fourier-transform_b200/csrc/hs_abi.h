@@ -226,6 +226,11 @@ void  hs_cu_jit_c2c_launch(int handle, const void *d_in, void *d_out, const void
 int   hs_cu_jit_source(int n, int sgn, const int *radix_exec, int nst, char *out, int cap);
 /* the real transforms of hs_cu_launch_ct_real on a plan-time kernel (same module, entry points hs_jit_r2c / hs_jit_c2r) */
 int   hs_cu_jit_has_real(int handle);
+/* Rader kernel (hs_fused.cuh) compiled for a prime N = L + 1 whose L is a product of compile-time radices, L <= 4096:
+ * radix_exec = any ordering of L's radices (full-precision constants); launch arguments as hs_cu_launch_ct_rader */
+int   hs_cu_jit_rader_create(int L, const int *radix_exec, int nst, hs_ct_desc *desc);
+void  hs_cu_jit_rader_launch(int handle, const void *d_in, void *d_out, const void *d_tw_f, const void *d_tw_i, const void *d_perm,
+                             const void *d_bk, long long howmany, void *stream);
 /* two tiled passes compiled for this plan (N > 8192, all stages compile-time radices): radix_exec cut after `split` stages;
  * fills desc like a static HS_CT_TWOPASS descriptor; launch runs pass 1 or 2 over a contiguous batch */
 int   hs_cu_jit_twopass_create(long long n, int sgn, const int *radix_exec, int nst, int split, hs_ct_desc *desc);

@@ -63,6 +63,7 @@ typedef struct hs_dev_obj {
     hs_c2c *fwdM, *invM;
     void *d_chirp, *d_hk;
     int blu_ct_id;
+    int rader_jit;   /* rader_ct_id is a handle of hs_cu_jit_rader_create (kernel compiled for this prime) instead of a static kernel id */
     int rader_ct_id; /* >= 0: prime N run as a cyclic convolution of length N-1 (d_chirp = int perm[N-1], d_hk = Bk) */
     int split_conv;  /* the split kernel runs on the in-place transforms of hs_conv_fft.cuh (d_blu_twf = their stage table) */
     int split_ct_id; /* >= 0: split chirp-z, two convolutions of length M/2 >= N in one kernel (d_chirp = h | h conj(w) | h w,

@@ -33,6 +33,8 @@ struct Nvrtc {
     nvrtcResult (*GetProgramLogSize)(nvrtcProgram, size_t *);
     nvrtcResult (*GetProgramLog)(nvrtcProgram, char *);
     nvrtcResult (*DestroyProgram)(nvrtcProgram *);
+    nvrtcResult (*AddNameExpression)(nvrtcProgram, const char *);
+    nvrtcResult (*GetLoweredName)(nvrtcProgram, const char *, const char **);
     bool ok;
 };
 static Nvrtc *nvrtc()
@@ -53,6 +55,8 @@ static Nvrtc *nvrtc()
     HS_SYM(GetProgramLogSize, "nvrtcGetProgramLogSize");
     HS_SYM(GetProgramLog, "nvrtcGetProgramLog");
     HS_SYM(DestroyProgram, "nvrtcDestroyProgram");
+    HS_SYM(AddNameExpression, "nvrtcAddNameExpression");
+    HS_SYM(GetLoweredName, "nvrtcGetLoweredName");
 #undef HS_SYM
     n.ok = true;
     return &n;
@@ -597,4 +601,127 @@ extern "C" void hs_cu_jit_twopass_launch(int handle, int pass, const void *d_in,
     if (r != CUDA_SUCCESS) { fprintf(stderr, "Error: CUDA failure %d launching plan-time pass %d for N=%lld\n", (int)r, pass, p->n); exit(EXIT_FAILURE); }
     hs_cu_count_launch();
     hs_cu_timing_mark(pass == 1 ? "tiled pass1 (plan-time kernel)" : "tiled pass2 (plan-time kernel)", stream);
+}
+
+// ------------------------------------------------------------------------------------------------ Rader kernels
+// A prime N whose N-1 is a product of compile-time radices and fits one SM (N <= 4097): the cyclic convolution of length
+// L = N-1 of hs_fused.cuh's hs_rader_kernel, instantiated for this L (forward plan = the radix list, inverse plan = the
+// list reversed, full-precision constants).  Half the arithmetic of the padded chirp-z the reference's route implies.
+struct JitRader {
+    int L, dev;
+    hs_ct_desc desc;
+    CUmodule mod;
+    CUfunction fn;
+    int threads, smem, minb;
+};
+static std::vector<JitRader *> g_rader;
+
+extern "C" int hs_cu_jit_rader_create(int L, const int *rx, int nst, hs_ct_desc *desc)
+{
+    if (!jit_enabled() || nst < 2 || nst > 8 || L < 16 || L > 4096) return -1;
+    std::lock_guard<std::mutex> lock(g_mu);
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    for (size_t i = 0; i < g_rader.size(); ++i)
+        if (g_rader[i]->L == L && g_rader[i]->dev == dev) { *desc = g_rader[i]->desc; return (int)i; }
+    int maxr = 1, inv[8];
+    for (int s = 0; s < nst; ++s) {
+        const int r = rx[s];
+        if (!(r == 2 || r == 3 || r == 4 || r == 5 || r == 7 || r == 8 || r == 16 || r == 11 || r == 13 || r == 17)) return -1;
+        maxr = r > maxr ? r : maxr;
+        inv[s] = rx[nst - 1 - s];
+    }
+    int T = L / maxr, pts = maxr;
+    while (T > 128 && pts * 2 <= 16) { T = (T + 1) / 2; pts *= 2; }
+    if (T < 1 || T > 512) return -1;
+    std::vector<int> pf(rx, rx + nst), pi(inv, inv + nst);
+    int lpf = 0, lpi = 0;
+    double bf = 1e30, bi = 1e30;
+    const int cand[5] = {3, 4, 2, 5, 0};
+    for (int i = 0; i < 5; ++i) {
+        const double a = conflict_ratio(L, T, cand[i], pf), b = conflict_ratio(L, T, cand[i], pi);
+        if (a < bf - 1e-9) { bf = a; lpf = cand[i]; }
+        if (b < bi - 1e-9) { bi = b; lpi = cand[i]; }
+    }
+    const int npf = lpf ? L + (L >> lpf) + 1 : L, npi = lpi ? L + (L >> lpi) + 1 : L;
+    int npad = npf > npi ? npf : npi;
+    if (npad < L + 2) npad = L + 2;        // HsRaderSmem: room for the N = L+1 staged outputs
+    const int smem = npad * 16;
+    const int regs = pts <= 10 ? 80 : 128, w32 = (T + 31) / 32 * 32;
+    int minb = (int)(65536 / ((long long)w32 * regs));
+    if (minb > 8) minb = 8;
+    while (minb > 1 && ((long long)minb * (smem + 1024) > 227 * 1024 || minb * T > 2048)) --minb;
+    Nvrtc *rt = nvrtc();
+    Driver *drv = driver();
+    if (!rt || !drv) return -1;
+    // the kernel template of hs_fused.cuh itself, instantiated by name (no wrapper around its body)
+    char buf[1024], expr[128];
+    snprintf(buf, sizeof buf,
+             "#include \"hs_fused.cuh\"\n"
+             "using PF = HsExact<HsPlan<%d, %d, 1, %d, -2, 0%s>>;\n"
+             "using PI = HsExact<HsPlan<%d, %d, 1, %d, -2, 0%s>>;\n",
+             L, T, lpf, radix_list(rx, nst).c_str(), L, T, lpi, radix_list(inv, nst).c_str());
+    snprintf(expr, sizeof expr, "hs_rader_kernel<PF, PI, %d, 2>", minb);
+    nvrtcProgram prog = nullptr;
+    if (rt->CreateProgram(&prog, buf, "hs_jit_rader.cu", hs_jit_src_count, hs_jit_src_texts, hs_jit_src_names) != 0) return -1;
+    if (rt->AddNameExpression(prog, expr) != 0) { rt->DestroyProgram(&prog); return -1; }
+    const char *opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-default-device", "-DHS_JIT=1"};
+    if (rt->CompileProgram(prog, 4, opts) != 0) {
+        size_t ls = 0;
+        rt->GetProgramLogSize(prog, &ls);
+        std::string log(ls + 1, '\0');
+        if (ls) rt->GetProgramLog(prog, &log[0]);
+        fprintf(stderr, "hsfft: plan-time compilation of the Rader kernel for N=%d failed (falling back to chirp-z):\n%s\n", L + 1, log.c_str());
+        rt->DestroyProgram(&prog);
+        return -1;
+    }
+    const char *lowered = nullptr;
+    if (rt->GetLoweredName(prog, expr, &lowered) != 0 || !lowered) { rt->DestroyProgram(&prog); return -1; }
+    const std::string kname(lowered);
+    size_t cs = 0;
+    rt->GetCUBINSize(prog, &cs);
+    std::vector<char> cubin(cs);
+    rt->GetCUBIN(prog, cubin.data());
+    rt->DestroyProgram(&prog);
+    JitRader *p = new JitRader();
+    p->L = L; p->dev = dev; p->threads = T; p->smem = smem; p->minb = minb;
+    HS_CUDA_CHECK(cudaFree(0));
+    if (drv->ModuleLoadData(&p->mod, cubin.data()) != CUDA_SUCCESS || drv->ModuleGetFunction(&p->fn, p->mod, kname.c_str()) != CUDA_SUCCESS) {
+        delete p;
+        return -1;
+    }
+    drv->FuncSetAttribute(p->fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, smem);
+    int pct = (int)(((long long)(smem + 1024) * minb * 100 + 228 * 1024 - 1) / (228 * 1024));
+    drv->FuncSetAttribute(p->fn, CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT, pct > 100 ? 100 : pct);
+    memset(&p->desc, 0, sizeof p->desc);
+    p->desc.id = (int)g_rader.size();
+    p->desc.family = HS_CT_RADER;
+    p->desc.n = L;
+    p->desc.nst = nst;
+    for (int s = 0; s < nst; ++s) p->desc.radix[s] = rx[s];
+    p->desc.split_min = -2;
+    p->desc.threads = T; p->desc.smem_bytes = smem; p->desc.exact = 1;
+    if (getenv("HSFFT_VERBOSE"))
+        fprintf(stderr, "hsfft: plan-time Rader kernel N=%d: L=%d T=%d LOGPAD=%d/%d, %d bytes smem, %d CTAs/SM asked\n", L + 1, L, T, lpf, lpi, smem, minb);
+    g_rader.push_back(p);
+    *desc = p->desc;
+    return p->desc.id;
+}
+
+extern "C" void hs_cu_jit_rader_launch(int handle, const void *d_in, void *d_out, const void *d_tw_f, const void *d_tw_i, const void *d_perm,
+                                       const void *d_bk, long long howmany, void *stream)
+{
+    JitRader *p;
+    {
+        std::lock_guard<std::mutex> lock(g_mu);
+        if (handle < 0 || handle >= (int)g_rader.size()) { fprintf(stderr, "Error: unknown plan-time Rader kernel %d\n", handle); exit(EXIT_FAILURE); }
+        p = g_rader[handle];
+    }
+    if (howmany <= 0 || howmany > 2147483647LL) { fprintf(stderr, "Error: batch too large for one launch (%lld CTAs)\n", howmany); exit(EXIT_FAILURE); }
+    int pf = 0;
+    void *args[] = {(void *)&d_in, (void *)&d_out, (void *)&d_tw_f, (void *)&d_tw_i, (void *)&d_perm, (void *)&d_bk, (void *)&howmany, (void *)&pf};
+    const CUresult r = driver()->LaunchKernel(p->fn, (unsigned)howmany, 1, 1, (unsigned)p->threads, 1, 1, (unsigned)p->smem, (CUstream)stream, args, nullptr);
+    if (r != CUDA_SUCCESS) { fprintf(stderr, "Error: CUDA failure %d launching the plan-time Rader kernel for N=%d\n", (int)r, p->L + 1); exit(EXIT_FAILURE); }
+    hs_cu_count_launch();
+    hs_cu_timing_mark("rader (plan-time kernel)", stream);
 }

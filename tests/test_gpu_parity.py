@@ -595,3 +595,28 @@ def test_plan_time_compiled_two_pass_kernels(hs, product_lib, oracle, n):
         assert "two tiled passes compiled" in desc, desc
         assert per_transform_worst(y, oracle.c2c(x, sgn)) <= tol(n), (n, sgn, desc)
 
+
+RADER_JIT_PRIMES = [127, 251, 337, 401, 449, 577, 641, 769, 1153, 1871, 2017, 2521, 3137, 3361, 4001, 4051]
+
+
+@pytest.mark.parametrize("n", RADER_JIT_PRIMES)
+def test_rader_kernels_compiled_for_primes_with_a_smooth_predecessor(hs, product_lib, oracle, n):
+    """Every prime N <= 4097 whose N-1 is a product of compile-time radices runs as ONE cyclic convolution of length N-1
+    (hs_fused.cuh's Rader kernel, compiled for this N at plan creation), not as the padded chirp-z of twice the length."""
+    x = rand_cplx(9, n, seed=n)
+    os.environ["HSFFT_RADER_JIT"] = "2"       # every prime that can have a kernel (the default keeps those that measured faster)
+    try:
+        for sgn in (1, -1):
+            with hs.Plan(n, sgn) as p:
+                desc = p.describe()
+                y = p.exec(x)
+            assert "rader" in desc and "plan-time" in desc, desc
+            assert per_transform_worst(y, oracle.c2c(x, sgn)) <= tol(n), (n, sgn, desc)
+    finally:
+        del os.environ["HSFFT_RADER_JIT"]
+    with hs.Plan(n, 1) as p:
+        desc = p.describe()
+        y = p.exec(x)
+    assert ("rader" in desc) == (n in (401, 449, 577, 641, 769, 1153, 1871, 2521, 3137, 3361, 4001)), desc
+    assert per_transform_worst(y, oracle.c2c(x, 1)) <= tol(n)
+
