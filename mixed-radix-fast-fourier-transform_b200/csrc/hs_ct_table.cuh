@@ -73,20 +73,9 @@ static void ct_init()
     fill_desc<PB256>(g_ct[CT_R256], CT_R256, HS_CT_RADER);
     fill_desc<PB2048x2f>(g_ct[CT_B2048X2], CT_B2048X2, HS_CT_BLUESTEIN);
     fill_desc<PB256x16>(g_ct[CT_B256X16], CT_B256X16, HS_CT_BLUESTEIN);
-    fill_desc<PB1024>(g_ct[CT_H1024], CT_H1024, HS_CT_BLUESTEIN_SPLIT);
-    fill_desc<PB2048f>(g_ct[CT_H2048], CT_H2048, HS_CT_BLUESTEIN_SPLIT);
     fill_desc<PB4096>(g_ct[CT_H4096], CT_H4096, HS_CT_BLUESTEIN_SPLIT);
     fill_desc<PB8192f>(g_ct[CT_H8192], CT_H8192, HS_CT_BLUESTEIN_SPLIT);
-    fill_desc<PB10240f>(g_ct[CT_H10240], CT_H10240, HS_CT_BLUESTEIN_SPLIT);
-    fill_desc<PC4096>(g_ct[CT_C4096], CT_C4096, HS_CT_CONV_SPLIT);
-    fill_desc<PC8192>(g_ct[CT_C8192], CT_C8192, HS_CT_CONV_SPLIT);
     fill_desc<PC10240>(g_ct[CT_C10240], CT_C10240, HS_CT_CONV_SPLIT);
-    fill_desc<PC10240s>(g_ct[CT_C10240S], CT_C10240S, HS_CT_CONV_SPLIT);
-    fill_desc<PC10240l>(g_ct[CT_C10240L], CT_C10240L, HS_CT_CONV_SPLIT);
-    fill_desc<PC10240h>(g_ct[CT_C10240H], CT_C10240H, HS_CT_CONV_SPLIT);
-    fill_desc<P8192c>(g_ct[CT_8192C], CT_8192C, HS_CT_C2C);
-    fill_desc<P8192d>(g_ct[CT_8192D], CT_8192D, HS_CT_C2C);
-    fill_desc<P3000>(g_ct[CT_3000M3], CT_3000M3, HS_CT_C2C);
     fill_desc<P4096x>(g_ct[CT_4096X], CT_4096X, HS_CT_C2C);
     fill_desc<P3000x>(g_ct[CT_3000X], CT_3000X, HS_CT_C2C);
     fill_desc<P4096y>(g_ct[CT_4096Y], CT_4096Y, HS_CT_C2C);
@@ -149,9 +138,6 @@ extern "C" void hs_cu_launch_ct_c2c(int id, int sgn, const void *d_in, void *d_o
     case CT_512: launch_c2c_sgn<P512, 3, 1>(sgn, d_in, d_out, d_tw, howmany, st); break;
     case CT_256: launch_c2c_sgn<P256, 3, 1>(sgn, d_in, d_out, d_tw, howmany, st); break;
     case CT_8192: launch_c2c_sgn<P8192, 1, 1>(sgn, d_in, d_out, d_tw, howmany, st); break;
-    case CT_8192C: launch_c2c_sgn<P8192c, 1, 1>(sgn, d_in, d_out, d_tw, howmany, st); break;
-    case CT_8192D: launch_c2c_sgn<P8192d, 1, 1>(sgn, d_in, d_out, d_tw, howmany, st); break;
-    case CT_3000M3: launch_c2c_sgn<P3000, 3>(sgn, d_in, d_out, d_tw, howmany, st); break;
     case CT_4096X: launch_c2c_sgn<P4096x, 2>(sgn, d_in, d_out, d_tw, howmany, st); break;
     case CT_3000X: launch_c2c_sgn<P3000x, 2>(sgn, d_in, d_out, d_tw, howmany, st); break;
     case CT_4096Y: launch_c2c_sgn<P4096y, 2>(sgn, d_in, d_out, d_tw, howmany, st); break;
@@ -257,11 +243,8 @@ extern "C" void hs_cu_launch_ct_bluestein_split(int id, int sgn, int N, const vo
 {
     hs_stream_t st = (hs_stream_t)stream;
     switch (id) {
-    HS_BLUSPLIT_CASE(CT_H1024, PB1024, PB1024, 8)
-    HS_BLUSPLIT_CASE(CT_H2048, PB2048f, PB2048i, 4)
     HS_BLUSPLIT_CASE(CT_H4096, PB4096, PB4096, 2)
     HS_BLUSPLIT_CASE(CT_H8192, PB8192f, PB8192i, 1)
-    HS_BLUSPLIT_CASE(CT_H10240, PB10240f, PB10240i, 1)
     default: fprintf(stderr, "Error: unknown split Bluestein kernel id %d\n", id); exit(EXIT_FAILURE);
     }
 }
@@ -277,12 +260,7 @@ extern "C" void hs_cu_launch_ct_conv_split(int id, int sgn, int N, const void *d
 {
     hs_stream_t st = (hs_stream_t)stream;
     switch (id) {
-    HS_CONVSPLIT_CASE(CT_C4096, PC4096, 3)
-    HS_CONVSPLIT_CASE(CT_C8192, PC8192, 1)
     HS_CONVSPLIT_CASE(CT_C10240, PC10240, 1)
-    HS_CONVSPLIT_CASE(CT_C10240S, PC10240s, 1)
-    HS_CONVSPLIT_CASE(CT_C10240L, PC10240l, 1)
-    HS_CONVSPLIT_CASE(CT_C10240H, PC10240h, 1)
     default: fprintf(stderr, "Error: unknown split Bluestein kernel id %d\n", id); exit(EXIT_FAILURE);
     }
 }

@@ -28,9 +28,8 @@ using P2048  = HsPlan<2048, 128, 2, 3, -1, 0, 16, 16, 8>;        // reference fa
 using P512   = HsPlan<512, 64, 4, 3, -1, 0, 8, 8, 8>;
 using P256   = HsPlan<256, 16, 16, 4, -1, 0, 16, 16>;
 using P8192  = HsPlan<8192, 512, 1, 4, -1, 0, 8, 8, 8, 16>;
-// A/B candidates: 8192 points with 1024 threads (8 points per thread, five passes, 64 registers: twice the warps of P8192)
-using P8192c = HsPlan<8192, 1024, 1, 3, -1, 0, 4, 8, 8, 8, 4>;
-using P8192d = HsPlan<8192, 1024, 1, 3, -1, 0, 8, 8, 8, 8, 2>;
+// (8192 points with 1024 threads -- 8 points per thread, five passes, 64 registers, twice the warps -- measured slower: 56 % and
+// 53 % of the HBM peak for 4.8.8.8.4 / 8.8.8.8.2 against 65 %; N = 3000 at three CTAs per SM spills and drops from 78 % to 59 %)
 // fused Bluestein, M = 2048 (N = 513..1024, e.g. the N = 1009 config): forward / inverse pair
 using PB2048f = HsPlan<2048, 128, 1, 4, HS_B2048_SPLIT, 0, 8, 16, 16>;
 using PB2048i = HsPlan<2048, 128, 1, 4, HS_B2048_SPLIT, 0, 16, 16, 8>;
@@ -49,8 +48,8 @@ using PB8192i = HsPlan<8192, 512, 1, 3, HS_B2048_SPLIT, 0, 8, 8, 16, 8>;
 // 10240 = 16*8*5*16 with 640 threads: every radix-16 stage has exactly one butterfly per thread, the radix-8 stage two,
 // the radix-5 stage 3.2 (four rounds); both orders are conflict free with one pad slot per 16 points (bank_check.py).
 // Exact radix-5 constants: the reference runs this convolution with power-of-two stages only.
-using PB10240f = HsExact<HsPlan<10240, 640, 1, 4, HS_B2048_SPLIT, 0, 16, 8, 5, 16>>;
-using PB10240i = HsExact<HsPlan<10240, 640, 1, 4, HS_B2048_SPLIT, 0, 16, 5, 8, 16>>;
+// (for 10240 = 16*8*5*16 with 640 threads this pair needs all 16-20 points of a pass in 96 registers: 2 KB of spill stores
+// per thread, 8.7 ms against 5.0 ms for the in-place transforms below, so it is not built)
 // the same split chirp-z on the in-place transforms of hs_conv_fft.cuh (digit-reversed spectrum, one butterfly at a time
 // per thread): 16 points in registers instead of the 16-20 of a whole pass, so 640 threads fit 96 registers without a spill
 // (the auto-sort pair above: 2 KB of spill stores per thread).  All conflict free with one pad slot per 16 points
@@ -60,12 +59,10 @@ using PB10240i = HsExact<HsPlan<10240, 640, 1, 4, HS_B2048_SPLIT, 0, 16, 5, 8, 1
 #ifndef HS_CONV_TWM
 #define HS_CONV_TWM -3
 #endif
+// Measured on B200, N = 10007 x 16384 (profiles/r2_sweep_split_variants.txt): this plan 5.11 ms; product tree 4.96, rows 1,2,4,8
+// loaded 5.07, 320 threads with twice the butterflies each (no spill at 168 registers) 5.00 -- all within run-to-run noise of
+// each other, so only one is built.  For M' = 8192 / 4096 the auto-sort pair above is faster (4.10 vs 4.60 ms, 1.61 vs 4.67 ms).
 using PC10240  = HsConvPlan<10240, 640, 4, HS_CONV_TWM, 16, 8, 5, 16>;
-using PC10240s = HsConvPlan<10240, 640, 4, -2, 16, 8, 5, 16>;   // A/B: product tree
-using PC10240l = HsConvPlan<10240, 640, 4, -1, 16, 8, 5, 16>;   // A/B: rows 1,2,4,8 loaded
-using PC10240h = HsConvPlan<10240, 320, 4, -2, 16, 8, 5, 16>;   // A/B: 320 threads, twice the butterflies each, no spill at 168 registers
-using PC8192   = HsConvPlan<8192, 512, 4, HS_CONV_TWM, 16, 8, 4, 16>;
-using PC4096   = HsConvPlan<4096, 256, 4, HS_CONV_TWM, 16, 16, 16>;
 // sub-plans of the two-pass transforms (N = n1 * n2 > 8192); X is unused there
 #ifndef HS_SUB_SPLIT
 #define HS_SUB_SPLIT -2
@@ -116,6 +113,4 @@ enum { CT_4096A = 0, CT_4096B, CT_3000, CT_1024, CT_2048, CT_512, CT_256, CT_819
        CT_TX20480, CT_TX40960, CT_TX81920, CT_TX163840, CT_S160X,
        CT_B256, CT_B512, CT_B1024, CT_B4096, CT_B8192,
        CT_R1008, CT_R1008A, CT_R1008G, CT_R256, CT_B2048X2, CT_B256X16,
-       CT_H1024, CT_H2048, CT_H4096, CT_H8192, CT_H10240,
-       CT_C4096, CT_C8192, CT_C10240, CT_C10240S, CT_C10240L, CT_C10240H,
-       CT_8192C, CT_8192D, CT_3000M3, CT_COUNT };
+       CT_H4096, CT_H8192, CT_C10240, CT_COUNT };

@@ -101,29 +101,15 @@ def test_long_bluestein_route_still_serves_mid_lengths_when_split_is_off(hs, emu
         assert "3 fused tiled kernels" in desc and err <= tol(n), (n, err, desc)
 
 
-@pytest.mark.parametrize("n", [4099, 8191, 8209, 10007, 10239])
-@pytest.mark.parametrize("family", ["in-place", "auto-sort"])
-def test_split_chirp_z_one_kernel_two_half_length_convolutions(hs, emu_lib, oracle, n, family, monkeypatch):
-    """N <= M' = 8192 / 10240: the padded convolution of length 2M' as two convolutions of length M' inside one CTA
-    (hs_conv_fft.cuh: in-place transforms, digit-reversed spectrum; hs_fused.cuh: the auto-sort pair), odd batch."""
-    monkeypatch.setenv("HSFFT_SPLIT_FAMILY", "5" if family == "auto-sort" else "6")
+@pytest.mark.parametrize("n", [2053, 4093, 4099, 8191, 8209, 10007, 10239])
+def test_split_chirp_z_one_kernel_two_half_length_convolutions(hs, emu_lib, oracle, n):
+    """N <= M' = 4096 / 8192 / 10240: the padded convolution of length 2M' as two convolutions of length M' inside one CTA
+    (hs_fused.cuh: the auto-sort pair, M' <= 8192; hs_conv_fft.cuh: in-place transforms with a digit-reversed spectrum,
+    M' = 10240), odd batch."""
+    want = "in-place" if n > 8192 else "auto-sort"
     for sgn in (1, -1):
         err, desc = run_c2c(hs, emu_lib, oracle, n, sgn, howmany=3)
-        assert "split chirp-z" in desc and family in desc and err <= tol(n) and err < 5e-15, (n, sgn, err, desc)
-
-
-def test_split_chirp_z_variants_and_small_lengths(hs, emu_lib, oracle, monkeypatch):
-    """Defaults: N = 2049..8192 the auto-sort pair (M' = 4096 / 8192), N = 8193..10240 the in-place transforms; below,
-    the plain one-kernel chirp-z unless HSFFT_BLU_SPLIT=2 asks for the split kernel (M' = 1024 / 2048).  HSFFT_PREFER_CT
-    is read when the library loads, so the A/B variants of the 10240-point plan are exercised on the GPU box only."""
-    for n, want in ((2053, "length 4096 (split chirp-z, auto-sort"), (4093, "length 4096 (split chirp-z, auto-sort"),
-                    (4099, "length 8192 (split chirp-z, auto-sort"), (10007, "length 10240 (split chirp-z, in-place")):
-        err, desc = run_c2c(hs, emu_lib, oracle, n, -1, howmany=2)
-        assert want in desc and err <= tol(n), (n, err, desc)
-    monkeypatch.setenv("HSFFT_BLU_SPLIT", "2")
-    for n, m in ((1031, 2048), (2039, 2048), (521, 1024)):
-        err, desc = run_c2c(hs, emu_lib, oracle, n, 1, howmany=3)
-        assert ("length %d (split" % m) in desc and err <= tol(n), (n, err, desc)
+        assert "split chirp-z" in desc and want in desc and err <= tol(n) and err < 5e-15, (n, sgn, err, desc)
 
 
 def test_smooth_bluestein_pad_uses_exact_radix5_and_stays_bluestein_only(hs, emu_lib, oracle, monkeypatch):

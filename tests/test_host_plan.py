@@ -153,7 +153,11 @@ def test_plan_time_kernel_source_is_generated_and_compiles_with_nvrtc(hs, produc
     assert L.hs_cu_jit_source(1000, 1, rx, 4, buf, 4096) > 0
     src = buf.value.decode()
     assert "HsPlan<1000, 125, 1, 3, -2, 1111, 5, 5, 5, 8>" in src and "hs_fft_team<PJ, 1>" in src
-    assert L.hs_cu_jit_source(1001, 1, (C.c_int * 3)(7, 11, 13), 3, buf, 4096) == 0      # radix 11, 13: not a template radix
+    assert L.hs_cu_jit_source(1472, 1, (C.c_int * 3)(8, 8, 23), 3, buf, 4096) == 0       # radix 23: not a template radix
+    buf2 = C.create_string_buffer(4096)
+    assert L.hs_cu_jit_source(1001, 1, (C.c_int * 3)(7, 11, 13), 3, buf2, 4096) > 0      # radix 11, 13, 17: unrolled generic butterflies
+    src2 = buf2.value.decode()
+    assert "7, 11, 13>" in src2 and "hs_jit_r2c" in src2 and "hs_jit_c2r" in src2
     try:
         rt = C.CDLL("libnvrtc.so.12")
     except OSError:
@@ -171,3 +175,6 @@ def test_plan_time_kernel_source_is_generated_and_compiles_with_nvrtc(hs, produc
     size = C.c_size_t()
     rt.nvrtcGetCUBINSize(prog, C.byref(size))
     assert rc == 0 and size.value > 1000
+    prog2 = C.c_void_p()
+    assert rt.nvrtcCreateProgram(C.byref(prog2), src2.encode(), b"p2.cu", 4, (C.c_char_p * 4)(*texts), (C.c_char_p * 4)(*[n.encode() for n in names])) == 0
+    assert rt.nvrtcCompileProgram(prog2, 4, opts) == 0
