@@ -11,7 +11,11 @@
  * N/2+1, its loop at src/real.c:128-132 writes the mirror):
  *   fft_r2c_exec writes ALL N bins (out[N-k] = conj(out[k])): out must hold N fft_data.
  *   fft_c2r_exec reads bins 0..N/2 and returns N unnormalised reals (N*x for a round trip).
- * The split / merge passes are fused into the first / last FFT kernel on the GPU.
+ * Where the half-length complex plan is a one-kernel plan (N/2 <= 8192, static or compiled at plan time) or N = 2^15..2^20,
+ * the split (r2c) and the merge (c2r) are fused into the transform kernels themselves: r2c splits in shared memory after
+ * the last pass (one kernel) or on pass 1 of a real four-step (two kernels), c2r merges on the first pass's loads.  Only
+ * half-lengths that run as Bluestein / Rader / the run-time engine, and r2c on an inverse plan, use the separate
+ * element-wise split / merge kernels (csrc/hs_generic.cuh).
  */
 #ifndef REAL_H_
 #define REAL_H_
