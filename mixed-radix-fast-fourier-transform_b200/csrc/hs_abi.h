@@ -213,9 +213,10 @@ void  hs_cu_launch_ct_bluestein_split(int id, int sgn, int N, const void *d_in, 
                                       const void *d_chirp3, const void *d_hk2, long long howmany, void *stream);
 
 /* the same on the in-place transforms of hs_conv_fft.cuh (descriptor family HS_CT_CONV_SPLIT): d_tw = the DIF stage table
- * of hs_build_conv_twiddles, d_hkt2 = Hk[even] | Hk[odd] each permuted by hs_conv_permute_hk */
+ * of hs_build_conv_twiddles, d_hkt2 = Hk[even] | Hk[odd] each permuted by hs_conv_permute_hk, d_wp[p] = exp(-i pi p / M'),
+ * p < M' / radix[0] (the variant that parks its intermediates in tensor memory rebuilds w from it) */
 void  hs_cu_launch_ct_conv_split(int id, int sgn, int N, const void *d_in, void *d_out, const void *d_tw, const void *d_chirp3,
-                                 const void *d_hkt2, long long howmany, void *stream);
+                                 const void *d_wp, const void *d_hkt2, long long howmany, void *stream);
 
 /* ---- plan-time specialisation (hs_jit.cu): a compile-time kernel for any length whose stages fit one SM, compiled with
  * NVRTC when the plan is created.  radix_exec: stage radices in execution order (2,3,4,5,7,8,16 only).  create returns a

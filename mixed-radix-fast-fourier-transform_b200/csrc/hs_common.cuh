@@ -71,6 +71,18 @@ static inline bool hs_mbar_test(HsMbar *m, unsigned parity) { std::lock_guard<st
 static inline void hs_mbar_wait(HsMbar *m, unsigned parity) { while (!hs_mbar_test(m, parity)) { } }
 static inline void hs_bulk_g2s(void *dst, const void *src, unsigned bytes, HsMbar *m) { memcpy(dst, src, bytes); hs_emu_mbar_complete_tx(m, bytes); }
 static inline void hs_bulk_s2g(void *dst, const void *src, unsigned bytes) { memcpy(dst, src, bytes); }
+// asynchronous 16-byte copy global -> shared (cp.async): done at once here
+static inline void hs_cp_async16(void *dst_smem, const void *src) { memcpy(dst_smem, src, 16); }
+static inline void hs_cp_async_wait_all() {}
+// tensor-memory stand-in: every CUDA thread is one OS thread here, and a thread only ever reads back what it parked itself
+extern thread_local double hs_emu_tmem[128];
+static inline unsigned hs_tmem_alloc(unsigned *) { return 0u; }
+static inline void hs_tmem_free(unsigned) {}
+static inline unsigned hs_tmem_my_addr(unsigned base, int words_per_thread) { (void)words_per_thread; return base; }
+static inline void hs_tmem_st4(unsigned taddr, int chunk, const double2 *v) { memcpy(hs_emu_tmem + 8 * chunk + taddr, v, 64); }
+static inline void hs_tmem_ld4(unsigned taddr, int chunk, double2 *v) { memcpy(v, hs_emu_tmem + 8 * chunk + taddr, 64); }
+static inline void hs_tmem_wait_st() {}
+static inline void hs_tmem_wait_ld() {}
 static inline void hs_bulk_commit_wait_read() {}
 static inline void hs_fence_async_proxy() {}
 static inline void hs_fence_proxy_async_all() {}
@@ -327,6 +339,74 @@ HS_DEVICE void hs_tma_load_3d_mp(void *dst_smem, const HsTmap *t, int x_dbl, int
         "l"(t), "r"(x_dbl), "r"(row0), "r"((int)z), "r"(hs_smem_u32(m)), "l"(pol)
         : "memory");
 }
+
+// asynchronous 16-byte copy global -> shared that bypasses the registers and L1 (LDGSTS): the issuing thread goes on, the data
+// lands later; hs_cp_async_wait_all waits for this thread's copies (other threads need a barrier on top)
+HS_DEVICE void hs_cp_async16(void *dst_smem, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(hs_smem_u32(dst_smem)), "l"(src) : "memory");
+}
+HS_DEVICE void hs_cp_async_wait_all() { asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory"); }
+
+// ---- tensor memory (TMEM, 256 KB per SM: 128 lanes x 512 columns x 32 bit) used as a per-thread parking lot.  The split
+// chirp-z kernel has to keep 160 KB of intermediate results per transform while its shared memory and registers are busy
+// with the next half-convolution; tcgen05.st / tcgen05.ld move registers to and from TMEM without touching L1 / L2.
+// A warp reaches the 32 lanes of its quadrant (warp id mod 4), one lane per thread, and any column.
+HS_DEVICE unsigned hs_tmem_alloc(unsigned *smem_slot) // whole CTA calls; warp 0 allocates all 512 columns
+{
+    if (threadIdx.x < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(hs_smem_u32(smem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    return *(volatile unsigned *)smem_slot;
+}
+HS_DEVICE void hs_tmem_free(unsigned base) // whole CTA calls after its last tcgen05.ld has been waited for
+{
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(512) : "memory");
+}
+// this thread's slot of `words_per_thread` columns: lane quadrant of its warp, columns by the warp's rank inside the quadrant
+HS_DEVICE unsigned hs_tmem_my_addr(unsigned base, int words_per_thread)
+{
+    const unsigned warp = threadIdx.x >> 5;
+    return base + (((warp & 3u) * 32u) << 16) + (warp >> 2) * (unsigned)words_per_thread;
+}
+// four complex doubles (16 words) of chunk `chunk` of the thread's slot
+HS_DEVICE void hs_tmem_st4(unsigned taddr, int chunk, const double2 *v)
+{
+    unsigned r[16];
+    HS_UNROLL
+    for (int i = 0; i < 4; ++i) {
+        r[4 * i + 0] = (unsigned)__double2loint(v[i].x); r[4 * i + 1] = (unsigned)__double2hiint(v[i].x);
+        r[4 * i + 2] = (unsigned)__double2loint(v[i].y); r[4 * i + 3] = (unsigned)__double2hiint(v[i].y);
+    }
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(
+                     taddr + 16u * (unsigned)chunk),
+                 "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+                 "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+                 : "memory");
+}
+HS_DEVICE void hs_tmem_ld4(unsigned taddr, int chunk, double2 *v)
+{
+    unsigned r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr + 16u * (unsigned)chunk)
+                 : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); // the registers are valid from here on
+    HS_UNROLL
+    for (int i = 0; i < 4; ++i) {
+        v[i].x = __hiloint2double((int)r[4 * i + 1], (int)r[4 * i + 0]);
+        v[i].y = __hiloint2double((int)r[4 * i + 3], (int)r[4 * i + 2]);
+    }
+}
+HS_DEVICE void hs_tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+HS_DEVICE void hs_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // order this thread's generic-proxy accesses to shared memory before later asynchronous-proxy ones
 HS_DEVICE void hs_fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // same for every state space: a counter read through the generic proxy gates a TMA load of global data

@@ -97,13 +97,22 @@ HS_DEVICE void hs_conv_twiddle_apply(const cplx *HS_RESTRICT row1, const int M, 
     }
 }
 
+// butterflies of a thread that the compiler may interleave (1: strictly one after the other, fewest registers).  Measured on
+// B200 with the tensor-memory kernel, N = 10007 x 16384 (profiles/r2_split_tmem_variants.txt): 1 -> 4.53 ms, 2 -> 4.33 ms,
+// 4 -> 6.24 ms (1.4 KB of spill stores per thread); 320 threads with 2 / 4 interleaved butterflies 6.2 / 6.4 ms.
+#ifndef HS_CONV_UNROLL
+#define HS_CONV_UNROLL 2
+#endif
+#define HS_PRAGMA_(x) _Pragma(#x)
+#define HS_CONV_UNROLL_PRAGMA(n) HS_PRAGMA_(unroll n)
+
 // Forward stage S (not the last).  FIRST: the inputs come from ld(n) (global memory), else from shared memory.
 template <class P, int S, bool FIRST, class LD>
 HS_DEVICE void hs_dif_stage(LD &ld, cplx *sm, const cplx *HS_RESTRICT tw, const int t)
 {
     constexpr int R = P::radix(S), LB = P::L(S), M = P::m(S), NB = P::N / R;
     constexpr int B = (NB + P::T - 1) / P::T;
-#pragma unroll 1
+HS_CONV_UNROLL_PRAGMA(HS_CONV_UNROLL)
     for (int u = 0; u < B; ++u) {
         const int beta = t + P::T * u;
         if (NB % P::T != 0 && beta >= NB) break;
@@ -131,7 +140,7 @@ HS_DEVICE void hs_dit_stage(ST &st, cplx *sm, const cplx *HS_RESTRICT tw, const 
 {
     constexpr int R = P::radix(S), LB = P::L(S), M = P::m(S), NB = P::N / R;
     constexpr int B = (NB + P::T - 1) / P::T;
-#pragma unroll 1
+HS_CONV_UNROLL_PRAGMA(HS_CONV_UNROLL)
     for (int u = 0; u < B; ++u) {
         const int beta = t + P::T * u;
         if (NB % P::T != 0 && beta >= NB) break;
@@ -157,7 +166,7 @@ HS_DEVICE void hs_conv_middle(cplx *sm, const cplx *HS_RESTRICT hkt, const int t
     constexpr int S = P::NST - 1, R = P::radix(S), NB = P::N / R;
     constexpr int B = (NB + P::T - 1) / P::T;
     static_assert(P::m(S) == 1, "the last stage works on adjacent points");
-#pragma unroll 1
+HS_CONV_UNROLL_PRAGMA(HS_CONV_UNROLL)
     for (int u = 0; u < B; ++u) {
         const int beta = t + P::T * u;
         if (NB % P::T != 0 && beta >= NB) break;
@@ -192,6 +201,17 @@ HS_DEVICE void hs_conv_inverse_from(ST &st, cplx *sm, const cplx *tw, const int 
         HS_SYNC();
         hs_dit_stage<P, S, S == 0>(st, sm, tw, t);
         hs_conv_inverse_from<P, S - 1>(st, sm, tw, t);
+    }
+}
+
+// inverse stages S, S-1, ... LO (each preceded by its barrier); the caller does stages LO-1 .. 0 itself
+template <class P, int S, int LO, class ST>
+HS_DEVICE void hs_conv_inverse_down_to(ST &st, cplx *sm, const cplx *tw, const int t)
+{
+    if constexpr (S >= LO) {
+        HS_SYNC();
+        hs_dit_stage<P, S, false>(st, sm, tw, t);
+        hs_conv_inverse_down_to<P, S - 1, LO>(st, sm, tw, t);
     }
 }
 
@@ -298,3 +318,141 @@ hs_conv_bluestein_kernel(const cplx *HS_RESTRICT in, cplx *HS_RESTRICT out, cons
     HsConvStoreChirpCrop<SGN> st{out + xf * N, chirp, N};
     hs_conv_run<P, SGN != 1>(ld, st, sm, tw, hkt, t);
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// The same split chirp-z with its intermediates parked in TENSOR MEMORY instead of travelling through the L2.
+// ncu on the kernel above (profiles/r2_ncu_blu10007_split_summary.txt, stall timeline): 44 % of its stall samples sit in
+// the phases that move data between the SM and the L2 -- the second read of x with its second chirp table, the parked
+// first half-convolution going out and coming back, three loads per point in the final combine: 1.77 MB per transform
+// through an SM port that sustains about 32 bytes per clock there.  Two observations remove 45 % of it:
+//   * the second convolution's input is a1 = a0 * w with a0 = x * conj(h) already in registers in the first stage of the
+//     first convolution, and w[p + 640 i] = w[p] * exp(-i pi i / 16): one table load per thread and compile-time constants.
+//     a1 is computed there and parked in the thread's TMEM slot (tcgen05.st, 16 points = 64 columns of its lane);
+//   * at the turn between the two convolutions the thread that holds y0[p + 640 i] (last inverse stage of the first) is
+//     the thread that needs a1[p + 640 i] (first forward stage of the second): it swaps them, four points at a time, so
+//     the same 160 KB of TMEM hold a1 during the first convolution and y0 during the second.
+// The final stage reads y0 back, four points at a time, next to y1 in registers:  out = (y0 + conj(w) y1) * conj(h).
+// L2 traffic per transform: x, h (twice), Hk and the result -- no second read of x, no gA / gB tables, no parked row.
+// Needs one radix-16 butterfly per thread on the outer stage (P::N = 16 T) and the whole TMEM of the SM (one CTA per SM).
+template <class P, int SGN, int MINB>
+HS_GLOBAL void HS_LAUNCH_BOUNDS(P::threads, MINB)
+hs_conv_bluestein_split_tmem_kernel(const cplx *HS_RESTRICT in, cplx *HS_RESTRICT out, const cplx *HS_RESTRICT tw, const cplx *HS_RESTRICT h,
+                                    const cplx *HS_RESTRICT wp, const cplx *HS_RESTRICT hkt2, int N, long long howmany, int pf_dist)
+{
+    static_assert(P::radix(0) == 16 && P::N == 16 * P::T && P::NST >= 3, "one radix-16 butterfly per thread on the outer stage");
+    constexpr int M0 = P::m(0);
+    // exp(-i pi i / 16), i < 16
+    constexpr double CR[16] = {1.0, 0.98078528040323044913, 0.92387953251128675613, 0.83146961230254523708, 0.70710678118654752440,
+                               0.55557023301960222474, 0.38268343236508977173, 0.19509032201612826785, 0.0, -0.19509032201612826785,
+                               -0.38268343236508977173, -0.55557023301960222474, -0.70710678118654752440, -0.83146961230254523708,
+                               -0.92387953251128675613, -0.98078528040323044913};
+    constexpr double CI[16] = {-0.0, -0.19509032201612826785, -0.38268343236508977173, -0.55557023301960222474, -0.70710678118654752440,
+                               -0.83146961230254523708, -0.92387953251128675613, -0.98078528040323044913, -1.0, -0.98078528040323044913,
+                               -0.92387953251128675613, -0.83146961230254523708, -0.70710678118654752440, -0.55557023301960222474,
+                               -0.38268343236508977173, -0.19509032201612826785};
+    HS_DYN_SMEM(cplx, sm);
+    unsigned *tm_slot = reinterpret_cast<unsigned *>(sm + P::NPAD); // 16 spare bytes behind the transform buffer
+    const int t = HS_TID;
+    const unsigned tbase = hs_tmem_alloc(tm_slot), taddr = hs_tmem_my_addr(tbase, 64);
+    const cplx *tw0 = tw + P::tw_off(0) + t; // outer-stage twiddles of this thread's butterfly (p = t)
+    HsConvStorePark dummy{out, 0};
+    cplx v[16];
+    (void)pf_dist;
+
+    // Persistent: the CTA walks the transforms xf = bid, bid + grid, ...  The raw samples of a transform are brought into this
+    // thread's own sixteen positions of the buffer with asynchronous copies (cp.async) that the PREVIOUS transform's last stage
+    // issues as soon as it has taken its values out of those positions: the HBM latency of x hides behind the final combine.
+    auto fetch = [&](long long xf) {
+        const cplx *x = in + xf * N;
+        HS_UNROLL
+        for (int i = 0; i < 16; ++i) {
+            const int n = t + M0 * i;
+            if (n < N) hs_cp_async16(&sm[P::pad(n)], x + n);
+            else sm[P::pad(n)] = hs_c(0.0, 0.0);
+        }
+    };
+    if (HS_BID < howmany) fetch(HS_BID);
+    for (long long xf = HS_BID; xf < howmany; xf += HS_NBLOCKS) {
+        cplx *o = out + xf * N;
+        // ---- first convolution, outer forward stage: a0 = x * conj(h); a1 = a0 * w parked in TMEM
+        hs_cp_async_wait_all();
+        HS_UNROLL
+        for (int i = 0; i < 16; ++i) v[i] = sm[P::pad(t + M0 * i)];
+        HS_UNROLL
+        for (int i = 0; i < 16; ++i)
+            if (t + M0 * i < N) {
+                const cplx hv = hs_ld_tab(h + t + M0 * i);
+                v[i] = (SGN == 1) ? hs_mulc(v[i], hv) : hs_mul(v[i], hv);
+            }
+        {
+            const cplx w_p = hs_ld_tab(wp + t); // loaded where it is used (an opaque load): the sixteen products w_p c_i are not kept alive
+            HS_UNROLL
+            for (int c = 0; c < 4; ++c) {
+                cplx a1[4];
+                HS_UNROLL
+                for (int k = 0; k < 4; ++k) a1[k] = hs_mul(hs_mul(v[4 * c + k], hs_c(CR[4 * c + k], CI[4 * c + k])), w_p);
+                hs_tmem_st4(taddr, c, a1);
+            }
+        }
+        hs_bfly<16, 1, P::EXACT>(v);
+        hs_conv_twiddle_apply<16, P::TWM, false>(tw0, M0, v);
+        HS_UNROLL
+        for (int j = 0; j < 16; ++j) sm[P::pad(t + M0 * j)] = v[j];
+        HS_SYNC();
+        hs_conv_forward_from<P, 1>(dummy, sm, tw, t);
+        hs_conv_middle<P, SGN != 1>(sm, hkt2, t);
+        hs_conv_inverse_down_to<P, P::NST - 2, 1>(dummy, sm, tw, t);
+
+        // ---- the turn: last inverse stage of the first convolution, y0 <-> a1 through TMEM, first forward stage of the second
+        HS_SYNC();
+        HS_UNROLL
+        for (int j = 0; j < 16; ++j) v[j] = sm[P::pad(t + M0 * j)];
+        hs_conv_twiddle_apply<16, P::TWM, true>(tw0, M0, v);
+        hs_bfly<16, -1, P::EXACT>(v);
+        hs_tmem_wait_st();
+        HS_UNROLL
+        for (int c = 0; c < 4; ++c) {
+            cplx a1[4];
+            hs_tmem_ld4(taddr, c, a1);
+            hs_tmem_st4(taddr, c, v + 4 * c);
+            HS_UNROLL
+            for (int k = 0; k < 4; ++k) v[4 * c + k] = a1[k];
+        }
+        hs_bfly<16, 1, P::EXACT>(v);
+        hs_conv_twiddle_apply<16, P::TWM, false>(tw0, M0, v);
+        HS_UNROLL
+        for (int j = 0; j < 16; ++j) sm[P::pad(t + M0 * j)] = v[j];
+        HS_SYNC();
+        hs_conv_forward_from<P, 1>(dummy, sm, tw, t);
+        hs_conv_middle<P, SGN != 1>(sm, hkt2 + P::N, t);
+        hs_conv_inverse_down_to<P, P::NST - 2, 1>(dummy, sm, tw, t);
+
+        // ---- last inverse stage of the second convolution and the combine: out = (y0 + conj(w) y1) * conj(h)
+        HS_SYNC();
+        HS_UNROLL
+        for (int j = 0; j < 16; ++j) v[j] = sm[P::pad(t + M0 * j)];
+        hs_conv_twiddle_apply<16, P::TWM, true>(tw0, M0, v);
+        hs_bfly<16, -1, P::EXACT>(v);
+        // this thread's positions of the buffer are free now (every v[j] above went through the butterfly): start the next
+        // transform's samples on their way
+        if (xf + HS_NBLOCKS < howmany) fetch(xf + HS_NBLOCKS);
+        hs_tmem_wait_st();
+        const cplx w_p = hs_ld_tab(wp + t);
+        HS_UNROLL
+        for (int c = 0; c < 4; ++c) {
+            cplx y0[4];
+            hs_tmem_ld4(taddr, c, y0);
+            HS_UNROLL
+            for (int k = 0; k < 4; ++k) {
+                const int i = 4 * c + k, n = t + M0 * i;
+                if (n < N) {
+                    const cplx s = hs_add(y0[k], hs_mulc(hs_mulc(v[i], hs_c(CR[i], CI[i])), w_p));
+                    const cplx hv = hs_ld_tab(h + n);
+                    hs_st_stream(o + n, (SGN == 1) ? hs_mulc(s, hv) : hs_mul(s, hv));
+                }
+            }
+        }
+    }
+    hs_tmem_free(tbase);
+}
+

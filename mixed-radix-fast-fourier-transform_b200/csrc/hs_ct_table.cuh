@@ -249,16 +249,31 @@ extern "C" void hs_cu_launch_ct_bluestein_split(int id, int sgn, int N, const vo
     }
 }
 
-#define HS_CONVSPLIT_CASE(ID, P, MINB)                                                                      \
-    case ID:                                                                                               \
-        if (sgn == 1) launch_conv_split<P, 1, MINB>(N, d_in, d_out, d_tw, d_chirp3, d_hkt2, howmany, st);  \
-        else launch_conv_split<P, -1, MINB>(N, d_in, d_out, d_tw, d_chirp3, d_hkt2, howmany, st);          \
+// intermediates of the split chirp-z kernel in tensor memory (default) or in the L2: N = 10007 x 16384 4.33 vs 5.12 ms
+#ifndef HS_SPLIT_TMEM_DEFAULT
+#define HS_SPLIT_TMEM_DEFAULT 1
+#endif
+template <class P, int SGN, int MINB>
+static void launch_conv_split_any(int tmem, int N, const void *d_in, void *d_out, const void *d_tw, const void *d_chirp3, const void *d_wp,
+                                  const void *d_hkt2, long long howmany, hs_stream_t st)
+{
+    if constexpr (P::N == 16 * P::T && P::radix(0) == 16) { // the tensor-memory variant wants one radix-16 butterfly per thread on the outer stage
+        if (tmem) { launch_conv_split_tmem<P, SGN, MINB>(N, d_in, d_out, d_tw, d_chirp3, d_wp, d_hkt2, howmany, st); return; }
+    }
+    launch_conv_split<P, SGN, MINB>(N, d_in, d_out, d_tw, d_chirp3, d_hkt2, howmany, st);
+}
+#define HS_CONVSPLIT_CASE(ID, P, MINB)                                                                                        \
+    case ID:                                                                                                                 \
+        if (sgn == 1) launch_conv_split_any<P, 1, MINB>(tmem, N, d_in, d_out, d_tw, d_chirp3, d_wp, d_hkt2, howmany, st);   \
+        else launch_conv_split_any<P, -1, MINB>(tmem, N, d_in, d_out, d_tw, d_chirp3, d_wp, d_hkt2, howmany, st);           \
         break;
 
 extern "C" void hs_cu_launch_ct_conv_split(int id, int sgn, int N, const void *d_in, void *d_out, const void *d_tw, const void *d_chirp3,
-                                           const void *d_hkt2, long long howmany, void *stream)
+                                           const void *d_wp, const void *d_hkt2, long long howmany, void *stream)
 {
     hs_stream_t st = (hs_stream_t)stream;
+    static int tmem = -1; // intermediates parked in tensor memory (d_wp = the w[p] table) or in the L2
+    if (tmem < 0) { const char *e = getenv("HSFFT_SPLIT_TMEM"); tmem = e ? atoi(e) : HS_SPLIT_TMEM_DEFAULT; }
     switch (id) {
     HS_CONVSPLIT_CASE(CT_C10240, PC10240, 1)
     default: fprintf(stderr, "Error: unknown split Bluestein kernel id %d\n", id); exit(EXIT_FAILURE);

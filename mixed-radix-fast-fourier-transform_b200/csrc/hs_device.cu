@@ -364,6 +364,24 @@ static void launch_blu_split(int N, const void *in, void *out, const void *twf, 
     hs_launched("blu_split", st);
 }
 
+// HSFFT_SPLIT_TMEM=0 / 1: the split chirp-z kernel with its intermediates in the L2 / in tensor memory (see hs_conv_fft.cuh)
+template <class P, int SGN, int MINB>
+static void launch_conv_split_tmem(int N, const void *in, void *out, const void *tw, const void *h, const void *wp, const void *hkt2,
+                                   long long howmany, cudaStream_t st)
+{
+    auto kern = hs_conv_bluestein_split_tmem_kernel<P, SGN, MINB>;
+    constexpr int smem = P::smem_bytes + 16;
+    hs_func_attr_once((const void *)kern, smem, MINB);
+    // persistent: one CTA per SM (it owns the SM's tensor memory and 175 KB of its shared memory) walks the batch
+    long long blocks = (long long)hs_cu_sm_count() * MINB;
+    if (blocks > howmany) blocks = howmany;
+    check_grid(blocks);
+    kern<<<(unsigned)blocks, P::threads, smem, st>>>((const cplx *)in, (cplx *)out, (const cplx *)tw, (const cplx *)h, (const cplx *)wp,
+                                                     (const cplx *)hkt2, N, howmany, 0);
+    HS_CUDA_CHECK(cudaGetLastError());
+    hs_launched("conv_split_tmem", st);
+}
+
 template <class P, int SGN, int MINB>
 static void launch_conv_split(int N, const void *in, void *out, const void *tw, const void *chirp3, const void *hkt2, long long howmany,
                               cudaStream_t st)

@@ -55,14 +55,18 @@ using PB8192i = HsPlan<8192, 512, 1, 3, HS_B2048_SPLIT, 0, 8, 8, 16, 8>;
 // (the auto-sort pair above: 2 KB of spill stores per thread).  All conflict free with one pad slot per 16 points
 // (tests/emu/bank_check.py inplace ...).
 // Twiddle mode -3 (row 1 and successive powers, two live twiddles): 96 registers, 160 B of spill stores per thread; the
-// product tree (-2) spills 380 B, loading rows 1,2,4,8 (-1) 400 B (ptxas -v).
+// product tree (-2) spills 380 B, loading rows 1,2,4,8 (-1) 400 B (ptxas -v).  With the tensor-memory kernel: -3 4.33 ms,
+// -2 4.59, -1 4.77, all rows loaded 5.77 (N = 10007 x 16384).
 #ifndef HS_CONV_TWM
 #define HS_CONV_TWM -3
 #endif
 // Measured on B200, N = 10007 x 16384 (profiles/r2_sweep_split_variants.txt): this plan 5.11 ms; product tree 4.96, rows 1,2,4,8
 // loaded 5.07, 320 threads with twice the butterflies each (no spill at 168 registers) 5.00 -- all within run-to-run noise of
 // each other, so only one is built.  For M' = 8192 / 4096 the auto-sort pair above is faster (4.10 vs 4.60 ms, 1.61 vs 4.67 ms).
-using PC10240  = HsConvPlan<10240, 640, 4, HS_CONV_TWM, 16, 8, 5, 16>;
+#ifndef HS_CONV_T
+#define HS_CONV_T 640
+#endif
+using PC10240  = HsConvPlan<10240, HS_CONV_T, 4, HS_CONV_TWM, 16, 8, 5, 16>;
 // sub-plans of the two-pass transforms (N = n1 * n2 > 8192); X is unused there
 #ifndef HS_SUB_SPLIT
 #define HS_SUB_SPLIT -2

@@ -772,7 +772,18 @@ static void dev_build(hs_dev_obj *d, fft_object plan)
         for (int s = 0; s < sp->nst; ++s) inv[s] = sp->radix[sp->nst - 1 - s];
         d->split_ct_id = sp->id;
         d->split_conv = sp->family == HS_CT_CONV_SPLIT;
-        if (d->split_conv) d->d_blu_twf = upload_conv_twiddles(sp->radix, sp->nst, Mh);
+        if (d->split_conv) {
+            d->d_blu_twf = upload_conv_twiddles(sp->radix, sp->nst, Mh);
+            /* w[p] = exp(-2 pi i p / M), p < M' / r0: the kernel that parks its intermediates in tensor memory forms every
+             * w[p + (M'/r0) i] from it and compile-time constants */
+            const int m0 = Mh / sp->radix[0];
+            fft_data *wp = (fft_data *)malloc(sizeof(fft_data) * (size_t)m0);
+            if (!wp) { fprintf(stderr, "Error: Memory allocation failed for Bluestein's FFT arrays\n"); exit(EXIT_FAILURE); }
+            for (int q = 0; q < m0; ++q) { const fft_type a = -PI2 * (fft_type)q / (fft_type)M; wp[q].re = cos(a); wp[q].im = sin(a); }
+            d->d_blu_twi = upload(wp, sizeof(fft_data) * (size_t)m0);
+            hs_cu_stream_sync(NULL);
+            free(wp);
+        }
         else {
             d->d_blu_twf = upload_stage_twiddles(sp->radix, sp->nst, 1, sp->split_min);
             d->d_blu_twi = upload_stage_twiddles(inv, sp->nst, -1, sp->split_min);
@@ -1002,7 +1013,7 @@ void hs_dev_exec(hs_dev_obj *d, const void *d_in, void *d_out, void *d_ws, long 
         return;
     }
     if (d->split_ct_id >= 0 && d->split_conv) {
-        hs_cu_launch_ct_conv_split(d->split_ct_id, d->sgn, d->N, d_in, d_out, d->d_blu_twf, d->d_chirp, d->d_hk, howmany, stream);
+        hs_cu_launch_ct_conv_split(d->split_ct_id, d->sgn, d->N, d_in, d_out, d->d_blu_twf, d->d_chirp, d->d_blu_twi, d->d_hk, howmany, stream);
         return;
     }
     if (d->split_ct_id >= 0) {

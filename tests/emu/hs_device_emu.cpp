@@ -75,6 +75,15 @@ static void launch_conv_split(int N, const void *in, void *out, const void *tw, 
     ++g_launches;
 }
 
+template <class P, int SGN, int MINB>
+static void launch_conv_split_tmem(int N, const void *in, void *out, const void *tw, const void *h, const void *wp, const void *hkt2,
+                                   long long howmany, hs_stream_t)
+{
+    hs_emu_launch(hs_conv_bluestein_split_tmem_kernel<P, SGN, MINB>, howmany < 2 ? howmany : 2, P::threads, P::smem_bytes + 16, (const cplx *)in, (cplx *)out,
+                  (const cplx *)tw, (const cplx *)h, (const cplx *)wp, (const cplx *)hkt2, N, howmany, 2);
+    ++g_launches;
+}
+
 template <class PF, class PI, int MINB>
 static void launch_rader(const void *in, void *out, const void *twf, const void *twi, const void *perm, const void *bk, long long howmany,
                          hs_stream_t)

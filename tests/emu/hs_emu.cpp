@@ -9,3 +9,4 @@ std::mutex hs_emu_mbar_mu;
 std::barrier<> *hs_emu_bar2;
 void hs_emu_barrier2() { hs_emu_bar2->arrive_and_wait(); }
 std::mutex hs_emu_launch_mu;
+thread_local double hs_emu_tmem[128];

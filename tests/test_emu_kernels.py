@@ -112,6 +112,23 @@ def test_split_chirp_z_one_kernel_two_half_length_convolutions(hs, emu_lib, orac
         assert "split chirp-z" in desc and want in desc and err <= tol(n) and err < 5e-15, (n, sgn, err, desc)
 
 
+def test_split_chirp_z_with_and_without_tensor_memory_parking(hs, emu_lib, oracle):
+    """M' = 10240: the persistent kernel that parks a1 / y0 in tensor memory and prefetches the next transform with cp.async
+    (five transforms over the emulation's two CTAs: a CTA walks 3 / 2 of them) against the kernel that parks in the L2.
+    HSFFT_SPLIT_TMEM is read once per process, so the L2 variant runs in a child process."""
+    import subprocess
+    import sys
+    err, desc = run_c2c(hs, emu_lib, oracle, 10007, 1, howmany=5)
+    assert err <= tol(10007) and err < 5e-15, (err, desc)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import importlib,sys;sys.path.insert(0,%r);sys.path.insert(0,%r+'/tests');import oracle_lib as ol;"
+            "hs=importlib.import_module('mixed-radix-fast-fourier-transform_b200');L=hs.load(%r+'/tests/emu/_build/libhsfft_emu.so');"
+            "x=ol.rand_cplx(3,10007,seed=1);p=hs.Plan(10007,-1,lib=L);y=p.exec(x);r=ol.Oracle().c2c(x,-1);"
+            "print('ERR',max(ol.rel_rms(y[i],r[i]) for i in range(3)))") % (root, root, root)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, HSFFT_SPLIT_TMEM="0"), timeout=300)
+    assert "ERR" in r.stdout and float(r.stdout.split("ERR")[1]) < 5e-15, r.stdout + r.stderr[-800:]
+
+
 def test_smooth_bluestein_pad_uses_exact_radix5_and_stays_bluestein_only(hs, emu_lib, oracle, monkeypatch):
     """N in 8193..10240 without the split kernel: the device pads to 20480 = 128 x 160 (full-precision radix-5 stages)
     instead of 32768.  A user-facing N = 20480 transform must NOT take that plan: the reference's own radix-5 literals apply there."""

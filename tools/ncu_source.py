@@ -37,3 +37,20 @@ for n, r in sorted(enumerate(body), key=lambda nr: -int(nr[1][ix["# Samples"]] o
     s = int(r[ix["# Samples"]] or 0)
     why = sorted(((int(r[ix[k]] or 0), k[6:]) for k in stalls), reverse=True)[:2]
     print("  #%4d %5.1f%%  %-60s %s" % (n, 100.0 * s / tot, r[ix["Source"]].strip()[:60], " ".join("%s:%d" % (k, v) for v, k in why if v)))
+# timeline: samples per window of 128 instructions, with the window's dominant stall reasons and its memory / barrier instructions
+print("timeline (window of 128 instructions: share of samples, top stall reasons, LDG/STG/LDS/STS/BAR/FP64 instruction counts):")
+W = 128
+for w0 in range(0, len(body), W):
+    win = body[w0:w0 + W]
+    sm = sum(int(r[ix["# Samples"]] or 0) for r in win)
+    why = sorted(((sum(int(r[ix[k]] or 0) for r in win), k[6:]) for k in stalls), reverse=True)[:3]
+    ops = {}
+    for r in win:
+        f = r[ix["Source"]].split()
+        op = (f[1] if f and f[0].startswith("@") and len(f) > 1 else (f[0] if f else "?")).split(".")[0]
+        ops[op] = ops.get(op, 0) + 1
+    fp = ops.get("DFMA", 0) + ops.get("DADD", 0) + ops.get("DMUL", 0)
+    print("  @%5d %5.1f%%  %-44s LDG %2d STG %2d LDS %2d STS %2d BAR %d FP64 %3d LDL/STL %d" % (
+        w0, 100.0 * sm / tot, " ".join("%s:%d" % (k, v) for v, k in why if v), ops.get("LDG", 0), ops.get("STG", 0), ops.get("LDS", 0),
+        ops.get("STS", 0), ops.get("BAR", 0), fp, ops.get("LDL", 0) + ops.get("STL", 0)))
+
