@@ -76,8 +76,8 @@ static inline void hs_cp_async16(void *dst_smem, const void *src) { memcpy(dst_s
 static inline void hs_cp_async_wait_all() {}
 // tensor-memory stand-in: every CUDA thread is one OS thread here, and a thread only ever reads back what it parked itself
 extern thread_local double hs_emu_tmem[128];
-static inline unsigned hs_tmem_alloc(unsigned *) { return 0u; }
-static inline void hs_tmem_free(unsigned) {}
+static inline unsigned hs_tmem_alloc(unsigned *, int) { return 0u; }
+static inline void hs_tmem_free(unsigned, int) {}
 static inline unsigned hs_tmem_my_addr(unsigned base, int words_per_thread) { (void)words_per_thread; return base; }
 static inline void hs_tmem_st4(unsigned taddr, int chunk, const double2 *v) { memcpy(hs_emu_tmem + 8 * chunk + taddr, v, 64); }
 static inline void hs_tmem_ld4(unsigned taddr, int chunk, double2 *v) { memcpy(v, hs_emu_tmem + 8 * chunk + taddr, 64); }
@@ -352,10 +352,10 @@ HS_DEVICE void hs_cp_async_wait_all() { asm volatile("cp.async.commit_group;\n c
 // chirp-z kernel has to keep 160 KB of intermediate results per transform while its shared memory and registers are busy
 // with the next half-convolution; tcgen05.st / tcgen05.ld move registers to and from TMEM without touching L1 / L2.
 // A warp reaches the 32 lanes of its quadrant (warp id mod 4), one lane per thread, and any column.
-HS_DEVICE unsigned hs_tmem_alloc(unsigned *smem_slot) // whole CTA calls; warp 0 allocates all 512 columns
+HS_DEVICE unsigned hs_tmem_alloc(unsigned *smem_slot, int ncols) // whole CTA calls; warp 0 allocates ncols columns (a power of two, 32..512)
 {
     if (threadIdx.x < 32) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(hs_smem_u32(smem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(hs_smem_u32(smem_slot)), "r"(ncols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -363,11 +363,11 @@ HS_DEVICE unsigned hs_tmem_alloc(unsigned *smem_slot) // whole CTA calls; warp 0
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     return *(volatile unsigned *)smem_slot;
 }
-HS_DEVICE void hs_tmem_free(unsigned base) // whole CTA calls after its last tcgen05.ld has been waited for
+HS_DEVICE void hs_tmem_free(unsigned base, int ncols) // whole CTA calls after its last tcgen05.ld has been waited for
 {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(512) : "memory");
+    if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(ncols) : "memory");
 }
 // this thread's slot of `words_per_thread` columns: lane quadrant of its warp, columns by the warp's rank inside the quadrant
 HS_DEVICE unsigned hs_tmem_my_addr(unsigned base, int words_per_thread)

@@ -339,7 +339,7 @@ HS_GLOBAL void HS_LAUNCH_BOUNDS(P::threads, MINB)
 hs_conv_bluestein_split_tmem_kernel(const cplx *HS_RESTRICT in, cplx *HS_RESTRICT out, const cplx *HS_RESTRICT tw, const cplx *HS_RESTRICT h,
                                     const cplx *HS_RESTRICT wp, const cplx *HS_RESTRICT hkt2, int N, long long howmany, int pf_dist)
 {
-    static_assert(P::radix(0) == 16 && P::N == 16 * P::T && P::NST >= 3, "one radix-16 butterfly per thread on the outer stage");
+    static_assert(P::radix(0) == 16 && P::N == 16 * P::T && P::NST >= 3 && P::T % 32 == 0, "one radix-16 butterfly per thread on the outer stage");
     constexpr int M0 = P::m(0);
     // exp(-i pi i / 16), i < 16
     constexpr double CR[16] = {1.0, 0.98078528040323044913, 0.92387953251128675613, 0.83146961230254523708, 0.70710678118654752440,
@@ -353,7 +353,9 @@ hs_conv_bluestein_split_tmem_kernel(const cplx *HS_RESTRICT in, cplx *HS_RESTRIC
     HS_DYN_SMEM(cplx, sm);
     unsigned *tm_slot = reinterpret_cast<unsigned *>(sm + P::NPAD); // 16 spare bytes behind the transform buffer
     const int t = HS_TID;
-    const unsigned tbase = hs_tmem_alloc(tm_slot), taddr = hs_tmem_my_addr(tbase, 64);
+    // 64 columns per thread, the warps of a lane quadrant side by side: a power of two of columns per CTA
+    constexpr int QW = (P::T / 32 + 3) / 4, TCOLS = QW * 64 <= 64 ? 64 : (QW * 64 <= 128 ? 128 : (QW * 64 <= 256 ? 256 : 512));
+    const unsigned tbase = hs_tmem_alloc(tm_slot, TCOLS), taddr = hs_tmem_my_addr(tbase, 64);
     const cplx *tw0 = tw + P::tw_off(0) + t; // outer-stage twiddles of this thread's butterfly (p = t)
     HsConvStorePark dummy{out, 0};
     cplx v[16];
@@ -453,6 +455,6 @@ hs_conv_bluestein_split_tmem_kernel(const cplx *HS_RESTRICT in, cplx *HS_RESTRIC
             }
         }
     }
-    hs_tmem_free(tbase);
+    hs_tmem_free(tbase, TCOLS);
 }
 

@@ -76,6 +76,7 @@ static void ct_init()
     fill_desc<PB4096>(g_ct[CT_H4096], CT_H4096, HS_CT_BLUESTEIN_SPLIT);
     fill_desc<PB8192f>(g_ct[CT_H8192], CT_H8192, HS_CT_BLUESTEIN_SPLIT);
     fill_desc<PC10240>(g_ct[CT_C10240], CT_C10240, HS_CT_CONV_SPLIT);
+    fill_desc<PC8192>(g_ct[CT_C8192], CT_C8192, HS_CT_CONV_SPLIT);
     fill_desc<P4096x>(g_ct[CT_4096X], CT_4096X, HS_CT_C2C);
     fill_desc<P3000x>(g_ct[CT_3000X], CT_3000X, HS_CT_C2C);
     fill_desc<P4096y>(g_ct[CT_4096Y], CT_4096Y, HS_CT_C2C);
@@ -276,6 +277,7 @@ extern "C" void hs_cu_launch_ct_conv_split(int id, int sgn, int N, const void *d
     if (tmem < 0) { const char *e = getenv("HSFFT_SPLIT_TMEM"); tmem = e ? atoi(e) : HS_SPLIT_TMEM_DEFAULT; }
     switch (id) {
     HS_CONVSPLIT_CASE(CT_C10240, PC10240, 1)
+    HS_CONVSPLIT_CASE(CT_C8192, PC8192, 1)
     default: fprintf(stderr, "Error: unknown split Bluestein kernel id %d\n", id); exit(EXIT_FAILURE);
     }
 }

@@ -67,6 +67,10 @@ using PB8192i = HsPlan<8192, 512, 1, 3, HS_B2048_SPLIT, 0, 8, 8, 16, 8>;
 #define HS_CONV_T 640
 #endif
 using PC10240  = HsConvPlan<10240, HS_CONV_T, 4, HS_CONV_TWM, 16, 8, 5, 16>;
+// M' = 8192 the same way: N = 8191 3.81 ms against 4.11 ms for the auto-sort pair, but N = 4099 3.41 against 3.28 ms, so the
+// planner takes it for the upper part of the range only; M' = 4096 in place measured no faster (1.61 ms both, N = 2053 3.02
+// against 2.58 ms) and is not built (profiles/r2_split_inplace_tmem_8192_4096.txt)
+using PC8192   = HsConvPlan<8192, 512, 4, HS_CONV_TWM, 16, 8, 4, 16>;
 // sub-plans of the two-pass transforms (N = n1 * n2 > 8192); X is unused there
 #ifndef HS_SUB_SPLIT
 #define HS_SUB_SPLIT -2
@@ -117,4 +121,4 @@ enum { CT_4096A = 0, CT_4096B, CT_3000, CT_1024, CT_2048, CT_512, CT_256, CT_819
        CT_TX20480, CT_TX40960, CT_TX81920, CT_TX163840, CT_S160X,
        CT_B256, CT_B512, CT_B1024, CT_B4096, CT_B8192,
        CT_R1008, CT_R1008A, CT_R1008G, CT_R256, CT_B2048X2, CT_B256X16,
-       CT_H4096, CT_H8192, CT_C10240, CT_COUNT };
+       CT_H4096, CT_H8192, CT_C10240, CT_C8192, CT_COUNT };

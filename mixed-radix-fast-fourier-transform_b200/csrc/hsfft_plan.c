@@ -197,9 +197,10 @@ static const hs_ct_desc *bluestein_split_plan(int N)
 {
     /* HSFFT_BLU_SPLIT: 0 off; 1 (default) where it measured faster than the plain one-kernel chirp-z / the three-kernel
      * route (N > 2048: M' = 4096, 8192, 10240); 2 wherever a plan exists.  Two kernel families offer such plans: the
-     * auto-sort pair of hs_fused.cuh (faster up to M' = 8192: N = 4093 1.61 ms per 16384 transforms against 1.82 ms plain,
-     * N = 8191 4.10 against 4.28 ms for the three kernels) and the in-place transforms of hs_conv_fft.cuh (the only one
-     * that fits M' = 10240 without spilling: 5.0 against 8.7 ms); HSFFT_SPLIT_FAMILY=5 / 6 forces one. */
+     * auto-sort pair of hs_fused.cuh (N = 4093 1.61 ms per 16384 transforms against 1.82 ms plain, N = 4099 3.28 ms against
+     * 3.96 ms for the three kernels) and the in-place transforms of hs_conv_fft.cuh with their intermediates in tensor
+     * memory (the only one that fits M' = 10240 without spilling: 4.33 against 8.7 ms; M' = 8192: N = 8191 3.81 against
+     * 4.11 ms, but N = 4099 3.41 against 3.28 ms, hence the split of that range); HSFFT_SPLIT_FAMILY=5 / 6 forces one. */
     const int mode = getenv("HSFFT_BLU_SPLIT") ? atoi(getenv("HSFFT_BLU_SPLIT")) : 1;
     if (mode == 0 || (mode == 1 && N <= 2048)) return NULL;
     const int force = getenv("HSFFT_SPLIT_FAMILY") ? atoi(getenv("HSFFT_SPLIT_FAMILY")) : 0;
@@ -209,7 +210,7 @@ static const hs_ct_desc *bluestein_split_plan(int N)
         const hs_ct_desc *d = hs_cu_ct_get(i);
         if ((d->family != HS_CT_BLUESTEIN_SPLIT && d->family != HS_CT_CONV_SPLIT) || d->n < N) continue;
         if (force && d->family != force) continue;
-        const int want = d->n <= 8192 ? HS_CT_BLUESTEIN_SPLIT : HS_CT_CONV_SPLIT;
+        const int want = (d->n > 8192 || (d->n == 8192 && N > 6144)) ? HS_CT_CONV_SPLIT : HS_CT_BLUESTEIN_SPLIT;
         if (!best || d->n < best->n || (d->n == best->n && best->family != want && d->family == want && !getenv("HSFFT_PREFER_CT"))) best = d;
     }
     return best;

@@ -106,7 +106,7 @@ def test_split_chirp_z_one_kernel_two_half_length_convolutions(hs, emu_lib, orac
     """N <= M' = 4096 / 8192 / 10240: the padded convolution of length 2M' as two convolutions of length M' inside one CTA
     (hs_fused.cuh: the auto-sort pair, M' <= 8192; hs_conv_fft.cuh: in-place transforms with a digit-reversed spectrum,
     M' = 10240), odd batch."""
-    want = "in-place" if n > 8192 else "auto-sort"
+    want = "in-place" if n > 6144 else "auto-sort"
     for sgn in (1, -1):
         err, desc = run_c2c(hs, emu_lib, oracle, n, sgn, howmany=3)
         assert "split chirp-z" in desc and want in desc and err <= tol(n) and err < 5e-15, (n, sgn, err, desc)
