@@ -46,7 +46,8 @@ HS_RULE int hs_stage_tw_entries(int r, int m, int split_min)
 }
 
 /* compile-time kernel families */
-enum { HS_CT_C2C = 0, HS_CT_BLUESTEIN = 1, HS_CT_TWOPASS = 2, HS_CT_SUB = 3, HS_CT_RADER = 4, HS_CT_BLUESTEIN_SPLIT = 5, HS_CT_CONV_SPLIT = 6 };
+enum { HS_CT_C2C = 0, HS_CT_BLUESTEIN = 1, HS_CT_TWOPASS = 2, HS_CT_SUB = 3, HS_CT_RADER = 4, HS_CT_BLUESTEIN_SPLIT = 5, HS_CT_CONV_SPLIT = 6,
+       HS_CT_SUB2 = 7 /* sub-plans built for second passes only (strided stores, inter-pass twiddle on load) */ };
 
 /* one compile-time specialised shared-memory transform the CUDA side offers */
 typedef struct hs_ct_desc {

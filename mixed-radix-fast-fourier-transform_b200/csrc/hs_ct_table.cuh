@@ -85,9 +85,9 @@ static void ct_init()
     fill_desc2<S128, S128>(g_ct[CT_T14], CT_T14);
     fill_desc2<S128, S256>(g_ct[CT_T15], CT_T15);
     fill_desc2<S256, S256>(g_ct[CT_T16], CT_T16);
-    fill_desc2<S256, S512>(g_ct[CT_T17], CT_T17);
-    fill_desc2<S512, S512>(g_ct[CT_T18], CT_T18);
-    fill_desc2<S512, S1024>(g_ct[CT_T19], CT_T19);
+    fill_desc2<S256, S512b>(g_ct[CT_T17], CT_T17);
+    fill_desc2<S512, S512b>(g_ct[CT_T18], CT_T18);
+    fill_desc2<S1024, S512b>(g_ct[CT_T19], CT_T19); // (512 x 1024 before: 3.73 ms per 2^19 x 512 against ... with the 1024-point pass staged first)
     fill_desc2<S1024, S1024>(g_ct[CT_T20], CT_T20);
     fill_desc<S128>(g_ct[CT_S128], CT_S128, HS_CT_SUB);
     fill_desc<S256>(g_ct[CT_S256], CT_S256, HS_CT_SUB);
@@ -95,9 +95,10 @@ static void ct_init()
     fill_desc<S1024>(g_ct[CT_S1024], CT_S1024, HS_CT_SUB);
     fill_desc2<S160x, S128>(g_ct[CT_TX20480], CT_TX20480);
     fill_desc2<S160x, S256>(g_ct[CT_TX40960], CT_TX40960);
-    fill_desc2<S160x, S512>(g_ct[CT_TX81920], CT_TX81920);
+    fill_desc2<S160x, S512b>(g_ct[CT_TX81920], CT_TX81920);
     fill_desc2<S160x, S1024>(g_ct[CT_TX163840], CT_TX163840);
     fill_desc<S160x>(g_ct[CT_S160X], CT_S160X, HS_CT_SUB);
+    fill_desc<S512b>(g_ct[CT_S512B], CT_S512B, HS_CT_SUB2);
     for (int i = 0; i < CT_COUNT; ++i) g_ct_order[i] = i;
     // HSFFT_PREFER_CT=<id>: list that instance first (A/B runs of alternative plans for one N)
     if (const char *e = getenv("HSFFT_PREFER_CT")) {
@@ -314,13 +315,13 @@ extern "C" void hs_cu_launch_ct_twopass(int id, int pass, int sgn, const void *d
     case CT_T14: launch_twopass<S128, S128>(pass, sgn, d_in, d_out, d_tw, d_twb, d_tws, howmany, st); break;
     case CT_T15: launch_twopass<S128, S256>(pass, sgn, d_in, d_out, d_tw, d_twb, d_tws, howmany, st); break;
     case CT_T16: launch_twopass<S256, S256>(pass, sgn, d_in, d_out, d_tw, d_twb, d_tws, howmany, st); break;
-    case CT_T17: launch_twopass<S256, S512>(pass, sgn, d_in, d_out, d_tw, d_twb, d_tws, howmany, st); break;
-    case CT_T18: launch_twopass<S512, S512>(pass, sgn, d_in, d_out, d_tw, d_twb, d_tws, howmany, st); break;
-    case CT_T19: launch_twopass<S512, S1024>(pass, sgn, d_in, d_out, d_tw, d_twb, d_tws, howmany, st); break;
+    case CT_T17: launch_twopass<S256, S512b>(pass, sgn, d_in, d_out, d_tw, d_twb, d_tws, howmany, st); break;
+    case CT_T18: launch_twopass<S512, S512b>(pass, sgn, d_in, d_out, d_tw, d_twb, d_tws, howmany, st); break;
+    case CT_T19: launch_twopass<S1024, S512b>(pass, sgn, d_in, d_out, d_tw, d_twb, d_tws, howmany, st); break;
     case CT_T20: launch_twopass<S1024, S1024>(pass, sgn, d_in, d_out, d_tw, d_twb, d_tws, howmany, st); break;
     case CT_TX20480: launch_twopass<S160x, S128>(pass, sgn, d_in, d_out, d_tw, d_twb, d_tws, howmany, st); break;
     case CT_TX40960: launch_twopass<S160x, S256>(pass, sgn, d_in, d_out, d_tw, d_twb, d_tws, howmany, st); break;
-    case CT_TX81920: launch_twopass<S160x, S512>(pass, sgn, d_in, d_out, d_tw, d_twb, d_tws, howmany, st); break;
+    case CT_TX81920: launch_twopass<S160x, S512b>(pass, sgn, d_in, d_out, d_tw, d_twb, d_tws, howmany, st); break;
     case CT_TX163840: launch_twopass<S160x, S1024>(pass, sgn, d_in, d_out, d_tw, d_twb, d_tws, howmany, st); break;
     default: fprintf(stderr, "Error: unknown two-pass kernel id %d\n", id); exit(EXIT_FAILURE);
     }
@@ -339,6 +340,17 @@ static void launch_sub(int sgn, int tw_mode, int stcol, const void *in, void *ou
     else                        { if (sgn == 1) launch_tiled<P, 1, C, 2, true>(in, out, tw, g, howmany, st); else launch_tiled<P, -1, C, 2, true>(in, out, tw, g, howmany, st); }
 }
 
+// second passes only (family HS_CT_SUB2)
+template <class P>
+static void launch_sub2(int sgn, int tw_mode, int stcol, const void *in, void *out, const void *tw, const hs_tile_geom &g, long long howmany,
+                        hs_stream_t st)
+{
+    constexpr int C = HsTileCols<P>::C;
+    if (g.ncols % C != 0 || !stcol || tw_mode == 0) { fprintf(stderr, "Error: this sub-plan runs second passes over a multiple of %d columns only\n", C); exit(EXIT_FAILURE); }
+    if (tw_mode == 1) { if (sgn == 1) launch_tiled<P, 1, C, 1, true>(in, out, tw, g, howmany, st); else launch_tiled<P, -1, C, 1, true>(in, out, tw, g, howmany, st); }
+    else              { if (sgn == 1) launch_tiled<P, 1, C, 2, true>(in, out, tw, g, howmany, st); else launch_tiled<P, -1, C, 2, true>(in, out, tw, g, howmany, st); }
+}
+
 extern "C" void hs_cu_launch_tiled(int sub_id, int sgn, int tw_mode, int stcol, const void *d_in, void *d_out, const void *d_tw,
                                    const hs_tile_geom *g, long long howmany, void *stream)
 {
@@ -349,6 +361,7 @@ extern "C" void hs_cu_launch_tiled(int sub_id, int sgn, int tw_mode, int stcol, 
     case CT_S512: launch_sub<S512>(sgn, tw_mode, stcol, d_in, d_out, d_tw, *g, howmany, st); break;
     case CT_S1024: launch_sub<S1024>(sgn, tw_mode, stcol, d_in, d_out, d_tw, *g, howmany, st); break;
     case CT_S160X: launch_sub<S160x>(sgn, tw_mode, stcol, d_in, d_out, d_tw, *g, howmany, st); break;
+    case CT_S512B: launch_sub2<S512b>(sgn, tw_mode, stcol, d_in, d_out, d_tw, *g, howmany, st); break;
     default: fprintf(stderr, "Error: unknown sub-plan id %d\n", sub_id); exit(EXIT_FAILURE);
     }
 }
@@ -368,7 +381,8 @@ static void launch_sub_io(int sgn, int tw_mode, int stcol, int io_mode, int cs, 
     } else if (io_mode == 10 && tw_mode == 0 && !stcol && sgn == 1) {
         launch_tiled<P, 1, C, 0, false, 10, 1>(in, out, tw, g, howmany, st);
     } else if (io_mode == 9 && tw_mode == 1 && stcol) {
-        if (sgn == 1) launch_tiled<P, 1, C, 1, true, 9, 1>(in, out, tw, g, howmany, st); else launch_tiled<P, -1, C, 1, true, 9, 1>(in, out, tw, g, howmany, st);
+        constexpr int C2 = HsTileColsMirror<P>::C;
+        if (sgn == 1) launch_tiled<P, 1, C2, 1, true, 9, 1>(in, out, tw, g, howmany, st); else launch_tiled<P, -1, C2, 1, true, 9, 1>(in, out, tw, g, howmany, st);
     } else if (io_mode == 1 && sgn == 1 && tw_mode == 0 && !stcol) {
         if (cs == 1) launch_tiled<P, 1, C, 0, false, 1, 1>(in, out, tw, g, howmany, st);
         else launch_tiled<P, 1, C, 0, false, 1, -1>(in, out, tw, g, howmany, st);
@@ -413,6 +427,21 @@ static void launch_sub_io(int sgn, int tw_mode, int stcol, int io_mode, int cs, 
     } else { fprintf(stderr, "Error: unsupported fused tiled pass\n"); exit(EXIT_FAILURE); }
 }
 
+// second passes only (family HS_CT_SUB2): the real four-step's mirrored pass and the convolution's slice
+template <class P>
+static void launch_sub_io2(int sgn, int tw_mode, int stcol, int io_mode, const void *in, void *out, const void *tw, const hs_tile_geom &g,
+                           long long howmany, hs_stream_t st)
+{
+    constexpr int C = HsTileCols<P>::C;
+    if (g.ncols % C != 0 && io_mode != 9) { fprintf(stderr, "Error: tiled pass needs a multiple of %d columns (got %d)\n", C, g.ncols); exit(EXIT_FAILURE); }
+    if (io_mode == 9 && tw_mode == 1 && stcol) {
+        constexpr int C2 = HsTileColsMirror<P>::C;
+        if (sgn == 1) launch_tiled<P, 1, C2, 1, true, 9, 1>(in, out, tw, g, howmany, st); else launch_tiled<P, -1, C2, 1, true, 9, 1>(in, out, tw, g, howmany, st);
+    } else if (io_mode == 6 && tw_mode == 1 && stcol) {
+        if (sgn == 1) launch_tiled<P, 1, C, 1, true, 6, 1>(in, out, tw, g, howmany, st); else launch_tiled<P, -1, C, 1, true, 6, 1>(in, out, tw, g, howmany, st);
+    } else { fprintf(stderr, "Error: unsupported fused tiled pass\n"); exit(EXIT_FAILURE); }
+}
+
 extern "C" void hs_cu_launch_tiled_io(int sub_id, int sgn, int tw_mode, int stcol, int io_mode, int chirp_sgn, const void *d_in, void *d_out,
                                       const void *d_tw, const hs_tile_geom *g, long long howmany, void *stream)
 {
@@ -423,6 +452,7 @@ extern "C" void hs_cu_launch_tiled_io(int sub_id, int sgn, int tw_mode, int stco
     case CT_S512: launch_sub_io<S512>(sgn, tw_mode, stcol, io_mode, chirp_sgn, d_in, d_out, d_tw, *g, howmany, st); break;
     case CT_S1024: launch_sub_io<S1024>(sgn, tw_mode, stcol, io_mode, chirp_sgn, d_in, d_out, d_tw, *g, howmany, st); break;
     case CT_S160X: launch_sub_io<S160x>(sgn, tw_mode, stcol, io_mode, chirp_sgn, d_in, d_out, d_tw, *g, howmany, st); break;
+    case CT_S512B: launch_sub_io2<S512b>(sgn, tw_mode, stcol, io_mode, d_in, d_out, d_tw, *g, howmany, st); break;
     default: fprintf(stderr, "Error: unknown sub-plan id %d\n", sub_id); exit(EXIT_FAILURE);
     }
 }

@@ -442,15 +442,15 @@ static bool tma_enabled(int sub_len, int tw)
 {
     static int v = -1;
     if (v < 0) { const char *e = getenv("HSFFT_TMA"); v = e ? atoi(e) : 2; }
-    return v == 1 || (v == 2 && sub_len >= 1024 && tw == 0);
+    return v == 1 || (v == 2 && sub_len >= 1024 && tw == 0) || (v == 3 && sub_len >= 512 && tw == 0);
 }
 
-template <class P, int SGN, int C, int TW, bool STCOL>
+template <class P, int SGN, int C, int TW, bool STCOL, int IO = 0>
 static void launch_tiled_tma(const void *in, void *out, const void *tw, const HsTileGeom &g, long long howmany, cudaStream_t st)
 {
     constexpr int smem = HsTmaTileSmem<P, C>::bytes;
     static_assert(smem <= 227 * 1024, "staging buffers do not fit");
-    auto kern = hs_tiled_tma_kernel<P, SGN, C, TW, STCOL>;
+    auto kern = hs_tiled_tma_kernel<P, SGN, C, TW, STCOL, IO>;
     static std::atomic<unsigned long long> attr_done{0}; // one bit per device: function attributes are per device
     static int per_sm = 1;
     if (attr_todo(attr_done)) {
@@ -467,22 +467,33 @@ static void launch_tiled_tma(const void *in, void *out, const void *tw, const Hs
     const CUtensorMap tm = make_tmap(in, g, P::N, C, howmany);
     kern<<<(unsigned)blocks, P::T * C, smem, st>>>(tm, (cplx *)out, (const cplx *)tw, g, howmany);
     HS_CUDA_CHECK(cudaGetLastError());
-    static const std::string tag = "tiled_tma n=" + std::to_string(P::N) + (TW ? " pass2" : " pass1");
+    static const std::string tag = "tiled_tma n=" + std::to_string(P::N) + (TW ? " pass2" : " pass1") + (IO ? " io" + std::to_string(IO) : std::string());
     hs_launched(tag.c_str(), st);
 }
 
+#ifndef HS_R4_TMA_DEFAULT
+#define HS_R4_TMA_DEFAULT 2
+#endif
 #ifndef HS_TILED_MINB_SMALL
 #define HS_TILED_MINB_SMALL (P::N == 160 ? 5 : 2) /* the 160-point plan fits 72 registers: five 160-thread CTAs per SM (N = 10007: 5.70 -> 5.45 ms) */
 #endif
 #ifndef HS_BLUMID_MINB
-#define HS_BLUMID_MINB ((PF::N == 128 || PF::N == 512) ? 4 : (PF::T * C <= 256) ? 2 : 1) /* 128 / 512 points: no spill at 4 CTAs per SM, +2-3 %; 256 loses 3 %, 1024 spills */
+#define HS_BLUMID_MINB ((PF::N == 128 || (PF::N == 512 && PF::T == 64)) ? 4 : (PF::T * C <= 256) ? 2 : 1) /* 128 / 512 points: no spill at 4 CTAs per SM, +2-3 %; 256 loses 3 %, 1024 spills */
 #endif
 #ifndef HS_TILED_MINB_MID
-#define HS_TILED_MINB_MID (P::N == 512 ? 3 : 2) /* 512-point tiles need 80 registers: three 256-thread CTAs per SM without a spill */
+#define HS_TILED_MINB_MID (P::N == 512 && P::T == 64 ? 3 : 2) /* 512-point tiles need 80 registers: three 256-thread CTAs per SM without a spill */
 #endif
 template <class P, int SGN, int C, int TW, bool STCOL, int IO = 0, int CS = 1>
 static void launch_tiled(const void *in, void *out, const void *tw, const HsTileGeom &g, long long howmany, cudaStream_t st)
 {
+    if constexpr (IO == 8 && !STCOL && TW == 0) {
+        // the real four-step's first pass: same staging, the split as epilogue.  HSFFT_R4_TMA: 0 off, 1 for 1024 points, 2 (default)
+        // for 512 points as well.  Measured at 2^28 reals: 1024 points 0.84 ms staged vs 1.05 plain, 512 points 0.86 vs 1.29
+        constexpr int CT = HsTileColsTma<P, C>::value;
+        static int r4tma = -1;
+        if (r4tma < 0) { const char *e = getenv("HSFFT_R4_TMA"); r4tma = e ? atoi(e) : HS_R4_TMA_DEFAULT; }
+        if (r4tma && P::N >= (r4tma == 2 ? 512 : 1024) && g.in_c == 1 && g.blk_log == 0 && g.ncols % CT == 0) { launch_tiled_tma<P, SGN, CT, 0, false, 8>(in, out, tw, g, howmany, st); return; }
+    }
     if constexpr (IO == 0) {
         // (half as many columns per tile and two CTAs per SM -- independent phase streams -- measured slower: 2^20 34.3 % vs
         // 39.3 %, 2^18 35.6 % vs 40.3 % of the HBM peak; 32-byte runs cost more than the overlap gains)
@@ -497,6 +508,7 @@ static void launch_tiled(const void *in, void *out, const void *tw, const HsTile
         HS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_mark(attr_done);
     }
+    if (!HS_TILE_PARTIAL(IO) && g.ncols % C != 0) { fprintf(stderr, "hsfft-b200: tiled pass with %d columns in tiles of %d\n", g.ncols, C); exit(EXIT_FAILURE); }
     const long long blocks = howmany * ((g.ncols + C - 1) / C);
     check_grid(blocks);
     kern<<<(unsigned)blocks, P::T * C, smem, st>>>((const cplx *)in, (cplx *)out, (const cplx *)tw, g, howmany);

@@ -89,6 +89,7 @@ int  hs_bluestein_exec_pad(int N);                                              
 
 /* plan-building helpers (hsfft_plan.c) */
 const hs_ct_desc *hs_find_ct(int family, int n, int allow_exact);
+const hs_ct_desc *hs_find_sub_second(int n);
 void *hs_upload_stage_twiddles(const int *radix_exec, int nst, int sgn, int split_min);
 void *hs_upload_interpass_tables(long long n, int sgn, int nb, int K, int kvalid, void **d_tws);
 

@@ -508,6 +508,7 @@ extern "C" int hs_cu_jit_twopass_create(long long n, int sgn, const int *rx, int
     if (!rt || !drv) return -1;
     char buf[4096];
     snprintf(buf, sizeof buf,
+             "#define HS_TILE_PARTIAL(IO) 1\n"
              "#include \"hs_tiled.cuh\"\n"
              "using P1 = HsPlan<%d, %d, 1, %d, -2, 0%s>;\n"
              "using P2 = HsPlan<%d, %d, 1, %d, -2, 0%s>;\n"

@@ -78,7 +78,12 @@ using PC8192   = HsConvPlan<8192, 512, 4, HS_CONV_TWM, 16, 8, 4, 16>;
 using S128  = HsPlan<128, 8, 1, 4, HS_SUB_SPLIT, 0, 8, 16>;
 using S256  = HsPlan<256, 16, 1, 4, HS_SUB_SPLIT, 0, 16, 16>;
 using S512  = HsPlan<512, 64, 1, 3, HS_SUB_SPLIT, 0, 8, 8, 8>;
-using S1024 = HsPlan<1024, 64, 1, 3, HS_SUB_SPLIT, 0, 16, 8, 8>;      // (T=128, 8.8.8.2 measured slower: 29% vs 36% at 2^20)
+using S1024 = HsPlan<1024, 64, 1, 3, HS_SUB_SPLIT, 0, 16, 8, 8>;      // (T=128, 8.8.8.2 measured slower: 29% vs 36% at 2^20;
+                                                                      //  T=128, 8.8.4.4 in round 2: 2^20 29.0 vs 39.0 %)
+// 512 points as a SECOND pass (family HS_CT_SUB2): 32 threads of 16 points, hence 8 columns per tile -- 128-byte instead of
+// 64-byte runs on the strided stores.  Measured on B200 (profiles/r2_subplan_variants.txt): second pass 1.44 vs 1.60 ms at
+// 2^18 x 1024, the real four-step's mirrored pass 1.34 vs 1.83 ms; as a FIRST pass it loses (2.54 vs 1.82 ms), so S512 stays.
+using S512b = HsPlan<512, 32, 1, 3, HS_SUB_SPLIT, 0, 16, 8, 4>;
 // profiling-only ablations (never selected unless HSFFT_PREFER_CT names them)
 using P4096x = HsPlan<4096, 256, 1, 4, 0, 0, 16, 16, 16>;
 using P3000x = HsPlan<3000, 200, 1, 3, -1, 0, 3, 5, 5, 5, 8>;
@@ -121,4 +126,4 @@ enum { CT_4096A = 0, CT_4096B, CT_3000, CT_1024, CT_2048, CT_512, CT_256, CT_819
        CT_TX20480, CT_TX40960, CT_TX81920, CT_TX163840, CT_S160X,
        CT_B256, CT_B512, CT_B1024, CT_B4096, CT_B8192,
        CT_R1008, CT_R1008A, CT_R1008G, CT_R256, CT_B2048X2, CT_B256X16,
-       CT_H4096, CT_H8192, CT_C10240, CT_C8192, CT_COUNT };
+       CT_H4096, CT_H8192, CT_C10240, CT_C8192, CT_S512B, CT_COUNT };

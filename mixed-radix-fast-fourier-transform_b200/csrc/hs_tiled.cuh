@@ -48,7 +48,27 @@ constexpr int hs_col_stride(int npad, int C)
 #ifndef HS_TILE_C_BIG
 #define HS_TILE_C_BIG 4
 #endif
+// passes whose column count need not be a multiple of the tile width: the real four-step's second pass (n1/2 + 1 rows);
+// the plan-time (NVRTC) passes define it as 1 for every pass
+#ifndef HS_TILE_PARTIAL
+#define HS_TILE_PARTIAL(IO) ((IO) == 9)
+#endif
 template <class P> struct HsTileCols { static constexpr int C = P::T >= 64 ? HS_TILE_C_BIG : HS_TILE_C_SMALL; };
+// the real four-step's mirrored second pass (IO 9) stores every run twice, the mirror image 16 bytes off the run's natural
+// alignment: wider tiles pay there.  256 points: 16 instead of 8 columns takes that pass from 1.50 to 1.09 ms per 2^28 reals,
+// while the plain second pass of a complex transform does not care (1.23 vs 1.24-1.26 ms)
+#ifndef HS_TILE_C9_256
+#define HS_TILE_C9_256 16
+#endif
+#ifndef HS_TILE_C9_512
+#define HS_TILE_C9_512 8
+#endif
+#ifndef HS_TILE_C9_1024
+#define HS_TILE_C9_1024 4
+#endif
+template <class P> struct HsTileColsMirror {
+    static constexpr int C = (P::N == 256 && P::T == 16) ? HS_TILE_C9_256 : (P::N == 512 && P::T == 32) ? HS_TILE_C9_512 : (P::N == 1024 && P::T == 64) ? HS_TILE_C9_1024 : HsTileCols<P>::C;
+};
 template <class P, int C> struct HsTileColsTma { static constexpr int value = (P::N == 512 && C == 4) ? 8 : C; };
 
 // LDP / STP: residency class of the loads / stores (hs_ld_mp / hs_st_mp in hs_common.cuh): 0 for the stand-alone
@@ -331,8 +351,10 @@ HS_DEVICE void hs_tile_run(const cplx *HS_RESTRICT in_x, cplx *HS_RESTRICT out_x
     const int colA = tid % C, tA = tid / C;       // lane = column
     const int colB = tid / P::T, tB = tid % P::T; // lane = thread of a team
     // a partial last tile (column count not a multiple of C): columns beyond the end only take part in the barriers
-    const HsLane first{smem + colA * NPADC, tA, on && c0 + colA < g.ncols};
-    const HsLane rest = STCOL ? first : HsLane{smem + colB * NPADC, tB, on && c0 + colB < g.ncols};
+    // (only where the column count need not be a multiple of C: a run-time `active` costs the 512-point passes 8-14 %)
+    constexpr bool PART = HS_TILE_PARTIAL(IO);
+    const HsLane first{smem + colA * NPADC, tA, PART ? (on && c0 + colA < g.ncols) : on};
+    const HsLane rest = STCOL ? first : HsLane{smem + colB * NPADC, tB, PART ? (on && c0 + colB < g.ncols) : on};
     const int colS = STCOL ? colA : colB;
     static_assert(!STG || IO == 0 || IO == 2, "only plain tile loads can be staged");
     if constexpr (IO == 1) { // forward pass 1 of the long Bluestein
@@ -504,10 +526,12 @@ struct HsTmaTileSmem {
     static constexpr int bytes = (2 * tile_elems + C * NPADC) * 16 + 64;
 };
 
-template <class P, int SGN, int C, int TW, bool STCOL>
+// IO: 0 plain stores; 8 the real four-step's first pass (split of the two real columns' spectra after the transform, see IO 8 of hs_tile_run)
+template <class P, int SGN, int C, int TW, bool STCOL, int IO = 0>
 HS_GLOBAL void HS_LAUNCH_BOUNDS(P::T *C, 1)
 hs_tiled_tma_kernel(const HS_GRID_CONSTANT HsTmap tmap, cplx *HS_RESTRICT out, const cplx *HS_RESTRICT tw, const HsTileGeom g, long long howmany)
 {
+    static_assert(IO == 0 || (IO == 8 && TW == 0 && !STCOL), "staged tiles: plain stores, or the real four-step's first pass");
     constexpr int BOXR = P::N < 256 ? P::N : 256; // rows per TMA box (hardware limit 256 per dimension)
     constexpr int NPADC = hs_col_stride(P::NPAD, C);
     constexpr int TE = P::N * C;             // elements of one staged tile
@@ -546,6 +570,20 @@ hs_tiled_tma_kernel(const HS_GRID_CONSTANT HsTmap tmap, cplx *HS_RESTRICT out, c
         const long long xf = tile_id / tiles;
         const int c0 = (int)(tile_id % tiles) * C;
         const cplx *stage = buf ? stage1 : stage0;
+        if constexpr (IO == 8) {
+            HsStoreSmemCol<P> st{rest.sm};
+            HsLoadTile ld;
+            ld.tile = stage + colA; ld.C = C;
+            hs_fft_team2<P, SGN>(ld, st, first, rest, tw);
+            HS_SYNC();
+            const cplx *z = rest.sm;
+            cplx *oe = out + xf * g.out_xf + (long long)(c0 + colB) * g.out_c, *oo = oe + g.out_c / 2;
+            for (int k1 = tB; k1 <= P::N / 2; k1 += P::T) {
+                const cplx a = z[P::pad(k1)], c = z[P::pad(k1 ? P::N - k1 : 0)];
+                hs_st_stream(oe + k1, hs_c((a.x + c.x) * 0.5, (a.y - c.y) * 0.5));
+                hs_st_stream(oo + k1, hs_c((a.y + c.y) * 0.5, (c.x - a.x) * 0.5));
+            }
+        } else {
         HsStoreCol<0> st{out + xf * g.out_xf + (long long)(c0 + colS) * g.out_c, g.out_e};
         if constexpr (TW != 0) {
             const long long k = (TW == 1) ? (long long)(c0 + colA) : xf;
@@ -557,6 +595,7 @@ hs_tiled_tma_kernel(const HS_GRID_CONSTANT HsTmap tmap, cplx *HS_RESTRICT out, c
             HsLoadTile ld;
             ld.tile = stage + colA; ld.C = C;
             hs_fft_team2<P, SGN>(ld, st, first, rest, tw);
+        }
         }
         hs_fence_async_proxy(); // this tile's reads of the staging buffer precede the copy that refills it
         HS_SYNC();              // ... and the exchange buffer is free for the next tile

@@ -287,6 +287,20 @@ static const hs_ct_desc *find_ct_ex(int family, int n, int allow_exact)
     return NULL;
 }
 static const hs_ct_desc *find_ct(int family, int n) { return find_ct_ex(family, n, 0); }
+/* the sub-plan (first- or second-pass family) that runs exactly these stages: the one whose twiddle tables a two-pass
+ * descriptor's radix[] / radix2[] describe */
+static const hs_ct_desc *find_sub_like(int n, const int *radix, int nst)
+{
+    const int cnt = hs_cu_ct_count();
+    for (int i = 0; i < cnt; ++i) {
+        const hs_ct_desc *d = hs_cu_ct_get(i);
+        if ((d->family != HS_CT_SUB && d->family != HS_CT_SUB2) || d->n != n || d->nst != nst) continue;
+        int same = 1;
+        for (int s = 0; s < nst; ++s) same &= d->radix[s] == radix[s];
+        if (same) return d;
+    }
+    return NULL;
+}
 
 static void *upload(const void *h, size_t bytes)
 {
@@ -516,6 +530,12 @@ static hs_c2c *c2c_create(int n, int sgn, int allow_exact)
 
 /* plan-building helpers shared with hsfft_real.c */
 const hs_ct_desc *hs_find_ct(int family, int n, int allow_exact) { return find_ct_ex(family, n, allow_exact); }
+/* sub-plan of length n for a second pass: one built for that role where it exists */
+const hs_ct_desc *hs_find_sub_second(int n)
+{
+    const hs_ct_desc *d = getenv("HSFFT_NO_SUB2") ? NULL : find_ct_ex(HS_CT_SUB2, n, 0);
+    return d ? d : find_ct_ex(HS_CT_SUB, n, 0);
+}
 void *hs_upload_stage_twiddles(const int *rx, int nst, int sgn, int split_min) { return upload_stage_twiddles(rx, nst, sgn, split_min); }
 void *hs_upload_interpass_tables(long long n, int sgn, int nb, int K, int kvalid, void **d_tws)
 {
@@ -1092,7 +1112,7 @@ int hs_dev_exec_c2r_fused(hs_dev_obj *d, const void *d_spec, long long in_stride
     const hs_c2c *p = d->direct;
     const hs_ct_desc *tp = NULL;
     for (int i = 0; i < hs_cu_ct_count(); ++i) if (hs_cu_ct_get(i)->id == p->tp_id) tp = hs_cu_ct_get(i);
-    const hs_ct_desc *s1 = tp ? find_ct(HS_CT_SUB, tp->n1) : NULL;
+    const hs_ct_desc *s1 = tp ? find_sub_like(tp->n1, tp->radix, tp->nst) : NULL;
     if (!tp || !s1) return 0;
     hs_tile_geom g;
     memset(&g, 0, sizeof g);
@@ -1108,8 +1128,8 @@ static int twopass_subs(const hs_c2c *p, const hs_ct_desc **tp, const hs_ct_desc
 {
     *tp = NULL;
     for (int i = 0; i < hs_cu_ct_count(); ++i) if (hs_cu_ct_get(i)->id == p->tp_id) *tp = hs_cu_ct_get(i);
-    *s1 = *tp ? find_ct(HS_CT_SUB, (*tp)->n1) : NULL;
-    *s2 = *tp ? find_ct(HS_CT_SUB, (*tp)->n2) : NULL;
+    *s1 = *tp ? find_sub_like((*tp)->n1, (*tp)->radix, (*tp)->nst) : NULL;
+    *s2 = *tp ? find_sub_like((*tp)->n2, (*tp)->radix2, (*tp)->nst2) : NULL;
     return *tp && *s1 && *s2;
 }
 

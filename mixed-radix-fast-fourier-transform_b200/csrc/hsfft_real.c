@@ -53,18 +53,23 @@ static void real_fourstep_setup(fft_real_object obj, hs_real_dev *r)
     r->r4 = 0;
     const long long N = 2LL * r->H;
     if (obj->cobj->sgn != 1 || obj->cobj->lt != 0 || N < (1 << 15) || getenv("HSFFT_NO_R2C_FUSE")) return;
-    static const int lens[4] = {128, 256, 512, 1024};
+    /* N = n1 * n2, both sub-lengths from 128..1024.  The second pass (mirrored stores, twice the bytes of the first) decides:
+     * measured on B200 per 2^28 reals (profiles/r2_subplan_second_pass_and_r4_splits.txt, r2_r4_mirror_tile_width.txt) it
+     * takes 1.09 ms with n2 = 256 and 1.10-1.14 with 128 (16 columns per tile: 256-byte runs), 1.35 with 512 (the second-pass
+     * plan, 128-byte runs) and 1.57 with 1024 (64-byte runs), while the first pass takes 0.76-0.89 ms whatever n1 is (512 and
+     * 1024 staged by the copy engine).  So: the best n2 whose partner exists -- 2^15 128x256, 2^16 256x256, 2^17 512x256,
+     * 2^18 1024x256 1.88 ms, 2^19 1024x512 2.17, 2^20 1024x1024 2.39 (round 1's choices: 2.31 / 2.41 / 2.62). */
+    static const int order2[4] = {256, 128, 512, 1024};
     int n1 = 0, n2 = 0;
-    for (int i = 0; i < 4 && !n1; ++i)          /* as balanced as the sub-plans allow */
-        for (int j = i; j < 4; ++j)
-            if ((long long)lens[i] * lens[j] == N && (!n1 || lens[j] - lens[i] < n2 - n1)) { n1 = lens[i]; n2 = lens[j]; }
+    for (int i = 0; i < 4 && !n1; ++i)
+        if (N % order2[i] == 0 && N / order2[i] >= 128 && N / order2[i] <= 1024) { n2 = order2[i]; n1 = (int)(N / n2); }
     if (!n1) return;
-    /* the longer sub-transform goes first (pass 1 has bandwidth to spare, pass 2 writes twice the bytes), unless it is the
-     * 1024-point plan, whose split epilogue at two CTAs per SM is the slower choice.  Measured on B200, n1 x n2:
-     * 2^15 256x128 1.89 ms vs 128x256 2.34; 2^17 512x256 2.13 vs 256x512 2.61; 2^19 512x1024 2.41 vs 1024x512 2.81 */
-    if (n2 != 1024 && n2 > n1) { const int t = n1; n1 = n2; n2 = t; }
     if (getenv("HSFFT_R4_SWAP")) { const int t = n1; n1 = n2; n2 = t; }
-    const hs_ct_desc *s1 = hs_find_ct(HS_CT_SUB, n1, 0), *s2 = hs_find_ct(HS_CT_SUB, n2, 0);
+    if (getenv("HSFFT_R4_N1")) { /* experiments: force the first sub-length */
+        const int f = atoi(getenv("HSFFT_R4_N1"));
+        if (f >= 128 && f <= 1024 && N % f == 0 && N / f >= 128 && N / f <= 1024) { n1 = f; n2 = (int)(N / f); }
+    }
+    const hs_ct_desc *s1 = hs_find_ct(HS_CT_SUB, n1, 0), *s2 = hs_find_sub_second(n2);
     if (!s1 || !s2) return;
     r->r4_n1 = n1; r->r4_n2 = n2; r->r4_sub1 = s1->id; r->r4_sub2 = s2->id;
     r->r4_ld = n1 / 2 + 2; /* rows k1 = 0..n1/2 of every real column, padded to an even count (32-byte aligned rows) */

@@ -114,6 +114,17 @@ static void launch_blu_mid(const void *in, void *out, const void *twf, const voi
 template <class P, int SGN, int C, int TW, bool STCOL, int IO = 0, int CS = 1>
 static void launch_tiled(const void *in, void *out, const void *tw, const HsTileGeom &g, long long howmany, hs_stream_t)
 {
+    if constexpr (IO == 8 && !STCOL && TW == 0) {
+        const char *e = getenv("HSFFT_R4_TMA");
+        if (e && atoi(e) != 0 && g.in_c == 1 && g.blk_log == 0 && g.ncols % C == 0) { // persistent TMA-staged kernel with the split epilogue, 3 "SMs"
+            const long long total = howmany * (g.ncols / C);
+            const HsTmap tm{(const unsigned char *)in, (long long)g.in_e * 16, (long long)g.in_xf * 16};
+            hs_emu_launch(hs_tiled_tma_kernel<P, SGN, C, 0, false, 8>, total < 3 ? total : 3, P::T * C, HsTmaTileSmem<P, C>::bytes, tm,
+                          (cplx *)out, (const cplx *)tw, g, howmany);
+            ++g_launches;
+            return;
+        }
+    }
     if constexpr (IO == 0) {
         const char *e = getenv("HSFFT_TMA");
         if ((!e || atoi(e) != 0) && g.in_c == 1 && g.blk_log == 0) { // persistent TMA-staged kernel, 3 "SMs"

@@ -20,12 +20,15 @@ def main():
     import torch
     hs = importlib.import_module("mixed-radix-fast-fourier-transform_b200")
     steps = 10
+    kernels = False
     cases = []
     args = sys.argv[1:]
     while args:
         a = args.pop(0)
         if a == "--steps":
             steps = int(args.pop(0))
+        elif a == "--kernels":       # per-kernel times of one extra pass (CUDA events around every launch)
+            kernels = True
         else:
             f = a.split(":")
             if f[0] == "fft2":           # fft2:<n0>x<n1>:<batch>
@@ -115,6 +118,12 @@ def main():
         gfl = flops / (ms * 1e-3) / 1e9
         print("%-4s N=%-8d batch=%-7d %8.3f ms  %8.1f GB/s  %5.1f%% of %.0f  %9.1f GFLOP/s  [%s]" %
               (kind, n, batch, ms, gbs, 100 * gbs / peak, peak, gfl, desc), flush=True)
+        if kernels:
+            with hs.launch_timing() as t:
+                run()
+                torch.cuda.synchronize()
+            for tag, cnt, kms in t.kernels:
+                print("       %-40s x%-3d %8.3f ms" % (tag, cnt, kms), flush=True)
         if p is not None:
             p.close()
         del x, y
