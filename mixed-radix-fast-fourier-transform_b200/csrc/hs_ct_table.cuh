@@ -346,8 +346,9 @@ static void launch_sub2(int sgn, int tw_mode, int stcol, const void *in, void *o
                         hs_stream_t st)
 {
     constexpr int C = HsTileCols<P>::C;
-    if (g.ncols % C != 0 || !stcol || tw_mode == 0) { fprintf(stderr, "Error: this sub-plan runs second passes over a multiple of %d columns only\n", C); exit(EXIT_FAILURE); }
-    if (tw_mode == 1) { if (sgn == 1) launch_tiled<P, 1, C, 1, true>(in, out, tw, g, howmany, st); else launch_tiled<P, -1, C, 1, true>(in, out, tw, g, howmany, st); }
+    if (g.ncols % C != 0 || !stcol) { fprintf(stderr, "Error: this sub-plan runs passes with strided stores over a multiple of %d columns only\n", C); exit(EXIT_FAILURE); }
+    if (tw_mode == 0) { if (sgn == 1) launch_tiled<P, 1, C, 0, true>(in, out, tw, g, howmany, st); else launch_tiled<P, -1, C, 0, true>(in, out, tw, g, howmany, st); } // column pass of a 2-D transform
+    else if (tw_mode == 1) { if (sgn == 1) launch_tiled<P, 1, C, 1, true>(in, out, tw, g, howmany, st); else launch_tiled<P, -1, C, 1, true>(in, out, tw, g, howmany, st); }
     else              { if (sgn == 1) launch_tiled<P, 1, C, 2, true>(in, out, tw, g, howmany, st); else launch_tiled<P, -1, C, 2, true>(in, out, tw, g, howmany, st); }
 }
 

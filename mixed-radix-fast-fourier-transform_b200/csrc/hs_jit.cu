@@ -508,7 +508,7 @@ extern "C" int hs_cu_jit_twopass_create(long long n, int sgn, const int *rx, int
     if (!rt || !drv) return -1;
     char buf[4096];
     snprintf(buf, sizeof buf,
-             "#define HS_TILE_PARTIAL(IO) 1\n"
+             "#define HS_TILE_PARTIAL(IO) %d\n" // a run-time column mask only where a pass has a ragged last tile (it costs 8-14 %)
              "#include \"hs_tiled.cuh\"\n"
              "using P1 = HsPlan<%d, %d, 1, %d, -2, 0%s>;\n"
              "using P2 = HsPlan<%d, %d, 1, %d, -2, 0%s>;\n"
@@ -532,6 +532,7 @@ extern "C" int hs_cu_jit_twopass_create(long long n, int sgn, const int *rx, int
              "    HsNoHooks hk;\n"
              "    hs_tile_run<P2, %d, %d, 1, true, 0, 1, 0, 0>(in + xf * g.in_xf, out + xf * g.out_xf, tw, g, xf, c0, smem, HS_TID, true, hk);\n"
              "}\n",
+             (n2 % c1.C != 0 || n1 % c2.C != 0) ? 1 : 0,
              (int)n1, c1.T, c1.logpad, radix_list(rx, split).c_str(), (int)n2, c2.T, c2.logpad, radix_list(rx + split, nst - split).c_str(),
              c1.threads, c1.minb, c1.C, c1.C, c1.C, sgn, c1.C, c2.threads, c2.minb, c2.C, c2.C, c2.C, sgn, c2.C);
     nvrtcProgram prog = nullptr;

@@ -46,9 +46,11 @@ static void plan_columns(fft2_object p)
     const int need = p->n0 == 1024 ? 4 : (p->n0 == 512 ? 8 : 16); /* columns per tile of the sub-plan (HsTileCols, hs_tiled.cuh) */
     if (p->n1 % need == 0 && !getenv("HSFFT_2D_TRANSPOSE")) {
         const int cnt = hs_cu_ct_count();
+        /* the column pass stores strided runs like a second pass: a sub-plan built for that role first (HS_CT_SUB2) */
+        for (int fam = getenv("HSFFT_NO_SUB2") ? 1 : 0; fam < 2; ++fam)
         for (int i = 0; i < cnt; ++i) {
             const hs_ct_desc *d = hs_cu_ct_get(i);
-            if (d->family == HS_CT_SUB && d->n == p->n0 && !d->exact) {
+            if (d->family == (fam == 0 ? HS_CT_SUB2 : HS_CT_SUB) && d->n == p->n0 && !d->exact) {
                 const int nt = hs_stage_twiddle_count(d->radix, d->nst, d->split_min);
                 fft_data *t = (fft_data *)malloc(sizeof(fft_data) * (nt > 0 ? nt : 1));
                 if (!t) { fprintf(stderr, "Error: Memory allocation failed for twiddle table\n"); exit(EXIT_FAILURE); }
