@@ -228,6 +228,7 @@ void  hs_cu_jit_c2c_launch(int handle, const void *d_in, void *d_out, const void
 int   hs_cu_jit_source(int n, int sgn, const int *radix_exec, int nst, char *out, int cap);
 /* the real transforms of hs_cu_launch_ct_real on a plan-time kernel (same module, entry points hs_jit_r2c / hs_jit_c2r) */
 int   hs_cu_jit_has_real(int handle);
+int   hs_cu_jit_is_staged(int handle); /* large batches run as persistent CTAs with the next input staged by the copy engine */
 /* Rader kernel (hs_fused.cuh) compiled for a prime N = L + 1 whose L is a product of compile-time radices, L <= 4096:
  * radix_exec = any ordering of L's radices (full-precision constants); launch arguments as hs_cu_launch_ct_rader */
 int   hs_cu_jit_rader_create(int L, const int *radix_exec, int nst, hs_ct_desc *desc);

@@ -68,12 +68,14 @@ typedef CUresult (*fn_cuModuleGetFunction)(CUfunction *, CUmodule, const char *)
 typedef CUresult (*fn_cuFuncSetAttribute)(CUfunction, CUfunction_attribute, int);
 typedef CUresult (*fn_cuLaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void **, void **);
 typedef CUresult (*fn_cuModuleUnload)(CUmodule);
+typedef CUresult (*fn_cuFuncGetAttribute)(int *, CUfunction_attribute, CUfunction);
 struct Driver {
     fn_cuModuleLoadData ModuleLoadData;
     fn_cuModuleGetFunction ModuleGetFunction;
     fn_cuFuncSetAttribute FuncSetAttribute;
     fn_cuLaunchKernel LaunchKernel;
     fn_cuModuleUnload ModuleUnload;
+    fn_cuFuncGetAttribute FuncGetAttribute;
     bool ok;
 };
 static Driver *driver()
@@ -91,6 +93,7 @@ static Driver *driver()
     HS_DRV(FuncSetAttribute, "cuFuncSetAttribute");
     HS_DRV(LaunchKernel, "cuLaunchKernel");
     HS_DRV(ModuleUnload, "cuModuleUnload");
+    HS_DRV(FuncGetAttribute, "cuFuncGetAttribute");
 #undef HS_DRV
     d.ok = true;
     return &d;
@@ -223,8 +226,8 @@ struct JitPlan {
     int n, sgn, dev; // a module belongs to the context of the device that was current when it was loaded
     hs_ct_desc desc;
     CUmodule mod;
-    CUfunction fn, fn_r2c, fn_c2r;
-    int threads, smem, X, minb;
+    CUfunction fn, fn_r2c, fn_c2r, fn_staged;
+    int threads, smem, X, minb, smem_staged;
     std::string text;
 };
 static std::mutex g_mu;
@@ -281,7 +284,35 @@ static std::string make_source(int n, int sgn, const int *rx, int nst, const Jit
              "    hs_fft_team<PJ, %d>(ld, st, smem + team * PJ::NPAD, tw, t, active);\n"
              "}\n",
              n, c.T, c.X, c.logpad, c.groups, rad.c_str(), c.minb, sgn, c.minb, sgn, c.minb, sgn);
-    return std::string(buf);
+    std::string src(buf);
+    if (c.X == 1 && c.npass > 1) { // persistent twin with the next input staged by the copy engine (see HsStageRefill)
+        snprintf(buf, sizeof buf,
+                 "extern \"C\" __global__ void __launch_bounds__(PJ::threads, %d)\n"
+                 "hs_jit_c2c_staged(const cplx *__restrict__ in, cplx *__restrict__ out, const cplx *__restrict__ tw, long long howmany)\n"
+                 "{\n"
+                 "    HS_DYN_SMEM(cplx, smem);\n"
+                 "    cplx *stage = smem + HsStagedSmem<PJ>::stage_off;\n"
+                 "    HsMbar *bar = reinterpret_cast<HsMbar *>(stage + PJ::N);\n"
+                 "    if (HS_TID == 0) hs_mbar_init(bar);\n"
+                 "    hs_fence_async_proxy();\n"
+                 "    HS_SYNC();\n"
+                 "    if (HS_TID == 0 && (long long)HS_BID < howmany) {\n"
+                 "        hs_mbar_expect(bar, (unsigned)(PJ::N * 16));\n"
+                 "        hs_bulk_g2s(stage, in + (long long)HS_BID * PJ::N, (unsigned)(PJ::N * 16), bar);\n"
+                 "    }\n"
+                 "    for (int j = 0; HS_BID + (long long)j * HS_NBLOCKS < howmany; ++j) {\n"
+                 "        hs_mbar_wait(bar, (unsigned)(j & 1));\n"
+                 "        HsStageRefill hk{bar, stage, in, howmany, j, PJ::N};\n"
+                 "        HsLoadStage ld{stage};\n"
+                 "        HsStoreGlobal st{out + (HS_BID + (long long)j * HS_NBLOCKS) * PJ::N};\n"
+                 "        hs_fft_team_h<PJ, %d>(ld, st, smem, tw, HS_TID, true, hk);\n"
+                 "        HS_SYNC();\n"
+                 "    }\n"
+                 "}\n",
+                 c.minb, sgn);
+        src += buf;
+    }
+    return src;
 }
 
 static bool jit_enabled()
@@ -356,6 +387,58 @@ extern "C" int hs_cu_jit_c2c_create(int n, int sgn, const int *rx, int nst, hs_c
             drv->FuncSetAttribute(f, CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT, pct > 100 ? 100 : pct);
         }
     } else p->fn_r2c = p->fn_c2r = nullptr;
+    // HSFFT_JIT_STAGED: 0 never, 1 plans that run one CTA per SM, 2 (default) also two CTAs per SM where both buffers fit -- each
+    // measured against the one-shot kernel when the plan is made; 3 always (no measurement)
+    p->fn_staged = nullptr;
+    p->smem_staged = (((npad + 7) / 8 * 8) + n) * 16 + 16;
+    const int want_staged = env_or("HSFFT_JIT_STAGED", 2);
+    if (c.X == 1 && c.npass > 1 && want_staged > 0 && c.minb <= (want_staged >= 2 ? 2 : 1) && (long long)c.minb * (p->smem_staged + 1024) <= 227 * 1024 &&
+        drv->ModuleGetFunction(&p->fn_staged, p->mod, "hs_jit_c2c_staged") == CUDA_SUCCESS) {
+        drv->FuncSetAttribute(p->fn_staged, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, p->smem_staged);
+        int pcts = (int)(((long long)(p->smem_staged + 1024) * c.minb * 100 + 228 * 1024 - 1) / (228 * 1024));
+        drv->FuncSetAttribute(p->fn_staged, CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT, pcts > 100 ? 100 : pcts);
+    } else p->fn_staged = nullptr;
+    if (p->fn_staged && want_staged < 3) {
+        // Which of the two wins depends on what the persistent loop does to the register allocation (N = 4500: 29.7 -> 52.2 % of
+        // the HBM peak, N = 6000: 46.3 -> 28.6 %; ptxas' local-memory size does not separate the cases), so the plan measures
+        // both once, on zero-filled scratch rows, and keeps the staged kernel only where it is faster.
+        const long long resident = (long long)hs_cu_sm_count() * c.minb, rows = 8 * resident;
+        const size_t bytes = (size_t)rows * n * 16;
+        void *d_a = nullptr, *d_b = nullptr, *d_t = nullptr;
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        float ms_plain = 0.f, ms_staged = 0.f;
+        bool ok = cudaMalloc(&d_a, bytes) == cudaSuccess && cudaMalloc(&d_b, bytes) == cudaSuccess && cudaMalloc(&d_t, (size_t)2 * n * 16) == cudaSuccess &&
+                  cudaMemset(d_a, 0, bytes) == cudaSuccess && cudaMemset(d_t, 0, (size_t)2 * n * 16) == cudaSuccess &&
+                  cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess;
+        if (ok) {
+            long long hm = rows;
+            int pf = 0;
+            void *a_plain[] = {(void *)&d_a, (void *)&d_b, (void *)&d_t, (void *)&hm, (void *)&pf};
+            void *a_staged[] = {(void *)&d_a, (void *)&d_b, (void *)&d_t, (void *)&hm};
+            for (int which = 0; which < 2 && ok; ++which) {
+                float best = 1e30f;
+                for (int rep = 0; rep < 4 && ok; ++rep) { // the first repetition warms up
+                    cudaEventRecord(e0, 0);
+                    const CUresult r = which == 0
+                        ? drv->LaunchKernel(p->fn, (unsigned)rows, 1, 1, (unsigned)p->threads, 1, 1, (unsigned)p->smem, 0, a_plain, nullptr)
+                        : drv->LaunchKernel(p->fn_staged, (unsigned)resident, 1, 1, (unsigned)p->threads, 1, 1, (unsigned)p->smem_staged, 0, a_staged, nullptr);
+                    cudaEventRecord(e1, 0);
+                    float ms = 0.f;
+                    ok = r == CUDA_SUCCESS && cudaEventSynchronize(e1) == cudaSuccess && cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess;
+                    if (rep > 0 && ms < best) best = ms;
+                }
+                (which == 0 ? ms_plain : ms_staged) = best;
+            }
+        }
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+        cudaFree(d_a); cudaFree(d_b); cudaFree(d_t);
+        if (!ok) cudaGetLastError();
+        if (!ok || !(ms_staged < 0.97f * ms_plain)) p->fn_staged = nullptr;
+        if (getenv("HSFFT_VERBOSE"))
+            fprintf(stderr, "hsfft: plan-time kernel N=%d: one-shot %.3f ms, staged %.3f ms per %lld transforms -> %s\n", n, ms_plain, ms_staged, rows,
+                    p->fn_staged ? "staged" : "one-shot");
+    }
     memset(&p->desc, 0, sizeof p->desc);
     p->desc.id = (int)g_plans.size();
     p->desc.family = HS_CT_C2C;
@@ -383,6 +466,15 @@ extern "C" void hs_cu_jit_c2c_launch(int handle, const void *d_in, void *d_out, 
     }
     const long long blocks = (howmany + p->X - 1) / p->X;
     if (blocks <= 0 || blocks > 2147483647LL) { fprintf(stderr, "Error: batch too large for one launch (%lld CTAs)\n", blocks); exit(EXIT_FAILURE); }
+    const long long resident = (long long)hs_cu_sm_count() * p->minb;
+    if (p->fn_staged && howmany >= 4 * resident) { // persistent CTAs, next input staged by the copy engine
+        void *args[] = {(void *)&d_in, (void *)&d_out, (void *)&d_tw, (void *)&howmany};
+        const CUresult r = driver()->LaunchKernel(p->fn_staged, (unsigned)resident, 1, 1, (unsigned)p->threads, 1, 1, (unsigned)p->smem_staged, (CUstream)stream, args, nullptr);
+        if (r != CUDA_SUCCESS) { fprintf(stderr, "Error: CUDA failure %d launching the staged plan-time kernel for N=%d\n", (int)r, p->n); exit(EXIT_FAILURE); }
+        hs_cu_count_launch();
+        hs_cu_timing_mark("c2c (plan-time kernel, staged)", stream);
+        return;
+    }
     int pf = 0;
     void *args[] = {(void *)&d_in, (void *)&d_out, (void *)&d_tw, (void *)&howmany, (void *)&pf};
     const CUresult r = driver()->LaunchKernel(p->fn, (unsigned)blocks, 1, 1, (unsigned)p->threads, 1, 1, (unsigned)p->smem, (CUstream)stream, args, nullptr);
@@ -414,6 +506,12 @@ extern "C" void hs_cu_jit_real_launch(int handle, int mode, const void *d_in, vo
     if (r != CUDA_SUCCESS) { fprintf(stderr, "Error: CUDA failure %d launching the plan-time real kernel for N=%d\n", (int)r, 2 * p->n); exit(EXIT_FAILURE); }
     hs_cu_count_launch();
     hs_cu_timing_mark(mode == 1 ? "r2c (plan-time kernel)" : "c2r (plan-time kernel)", stream);
+}
+
+extern "C" int hs_cu_jit_is_staged(int handle)
+{
+    std::lock_guard<std::mutex> lock(g_mu);
+    return handle >= 0 && handle < (int)g_plans.size() && g_plans[handle]->fn_staged != nullptr;
 }
 
 extern "C" int hs_cu_jit_has_real(int handle)

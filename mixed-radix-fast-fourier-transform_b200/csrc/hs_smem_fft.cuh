@@ -420,6 +420,44 @@ hs_c2c_smem_kernel(const cplx *HS_RESTRICT in, cplx *HS_RESTRICT out, const cplx
     hs_fft_team<P, SGN>(ld, st, smem + team * P::NPAD, tw, t, active);
 }
 
+// Persistent form of the one-kernel transform for plans that run ONE CTA per SM (plan-time kernels for N = 5000...6600:
+// the exchange buffer or the register file leaves room for one).  With a single CTA nothing covers the HBM latency of the
+// first pass's loads, so the NEXT transform's input is staged by the copy engine: one cp.async.bulk of N*16 bytes into a
+// second shared-memory buffer, completion on an mbarrier, issued as soon as the first pass has consumed the buffer, so the
+// copy runs under the remaining passes and the stores.  (At two CTAs per SM the loop does not fit the register cap: N =
+// 3000 spills 500 bytes and runs 1.98 vs 1.23 ms, profiles/r2_n3000_staged_persistent_ab.txt.)
+struct HsStageRefill { // hook: after the first pass's barrier thread 0 starts the copy of the CTA's next transform
+    HsMbar *bar;
+    cplx *stage;
+    const cplx *HS_RESTRICT in;
+    long long howmany;
+    int j, n;
+    HS_DEVICE void sync() { HS_SYNC(); }
+    HS_DEVICE void after_first_loads() {}
+    HS_DEVICE void after_first_pass()
+    {
+        hs_fence_async_proxy(); // this transform's reads of the staging buffer precede the copy that refills it
+        if (HS_TID == 0) {
+            const long long next = HS_BID + (long long)(j + 1) * HS_NBLOCKS;
+            if (next < howmany) {
+                hs_mbar_expect(bar, (unsigned)(n * 16));
+                hs_bulk_g2s(stage, in + next * n, (unsigned)(n * 16), bar);
+            }
+        }
+    }
+    HS_DEVICE void before_last_pass() {}
+};
+struct HsLoadStage {
+    static constexpr bool kPost = false;
+    const cplx *stage;
+    HS_DEVICE cplx operator()(int, int, int n) const { return stage[n]; }
+};
+template <class P>
+struct HsStagedSmem {
+    static constexpr int stage_off = (P::NPAD + 7) / 8 * 8; // 128-byte aligned
+    static constexpr int bytes = (stage_off + P::N) * 16 + 16;
+};
+
 // ------------------------------------------------------------------ real transforms, one kernel
 // reference src/real.c packs N reals as H = N/2 complex samples, runs the half-length complex plan and splits (r2c,
 // :109-132) or merges (c2r, :171-179) with twiddle2[k] = exp(+2 pi i k / N).  Here both ride on the complex kernel:

@@ -1347,7 +1347,9 @@ const char *hsfft_plan_describe(fft_object obj)
     if (d->lt == 0) {
         const hs_c2c *p = d->direct;
         if (p->ct_id >= 0) n = snprintf(buf, sizeof buf, "mixed-radix N=%d: compile-time smem kernel #%d", d->N, p->ct_id);
-        else if (p->jit_id >= 0) n = snprintf(buf, sizeof buf, "mixed-radix N=%d: smem kernel compiled for this plan (NVRTC) #%d", d->N, p->jit_id);
+        else if (p->jit_id >= 0)
+            n = snprintf(buf, sizeof buf, "mixed-radix N=%d: smem kernel compiled for this plan (NVRTC) #%d%s", d->N, p->jit_id,
+                         hs_cu_jit_is_staged(p->jit_id) ? ", persistent with staged input for large batches" : "");
         else if (p->jtp_id >= 0)
             n = snprintf(buf, sizeof buf, "mixed-radix N=%d = %d x %d: two tiled passes compiled for this plan (NVRTC) #%d", d->N, p->n1, p->n2, p->jtp_id);
         else if (p->tp_id >= 0)

@@ -193,6 +193,7 @@ int hs_cu_jit_c2c_create(int, int, const int *, int, hs_ct_desc *) { return -1; 
 void hs_cu_jit_c2c_launch(int, const void *, void *, const void *, long long, void *) {}
 int hs_cu_jit_source(int, int, const int *, int, char *, int) { return 0; }
 int hs_cu_jit_has_real(int) { return 0; }
+int hs_cu_jit_is_staged(int) { return 0; }
 int hs_cu_jit_rader_create(int, const int *, int, hs_ct_desc *) { return -1; }
 void hs_cu_jit_rader_launch(int, const void *, void *, const void *, const void *, const void *, const void *, long long, void *) {}
 int hs_cu_jit_twopass_create(long long, int, const int *, int, int, hs_ct_desc *) { return -1; }

@@ -101,6 +101,29 @@ def test_plan_time_compiled_kernels(hs, product_lib, oracle, n):
         assert per_transform_worst(y, oracle.c2c(x, sgn)) <= min(tol(n), 2e-15 * math.log2(n) * 4), (n, sgn, desc)
 
 
+@pytest.mark.parametrize("n", [2400, 4500, 6250, 6561])
+def test_plan_time_kernels_persistent_staged_form(hs, product_lib, oracle, n, monkeypatch):
+    """Batches of a few waves and more run the plan-time kernel as persistent CTAs whose next input is staged by the copy
+    engine (csrc/hs_smem_fft.cuh HsStageRefill; HSFFT_JIT_STAGED=3 takes that form without the plan-time measurement):
+    first / last transform, the ones around the end of the first wave and the tail against the oracle."""
+    monkeypatch.setenv("HSFFT_JIT_STAGED", "3")
+    b = 2500
+    idx = [0, 1, 147, 148, 149, 295, 296, 297, 1183, 1184, 1185, b // 2, b - 2, b - 1]
+    import torch
+    dev = torch.device("cuda", 0)
+    for sgn in (1, -1):
+        x = rand_cplx(b, n, seed=n - sgn)
+        xd = torch.from_numpy(x).to(dev)
+        yd = torch.empty_like(xd)
+        with hs.Plan(n, sgn) as p:
+            with hs.launch_timing() as t:
+                p.exec_dev(xd, yd, b)
+                torch.cuda.synchronize()
+        assert any("staged" in k[0] for k in t.kernels), t.kernels
+        y = yd.cpu().numpy()
+        assert per_transform_worst(y[idx], oracle.c2c(x[idx], sgn)) <= tol(n), (n, sgn)
+
+
 def test_config1_n1024_forward_inverse_roundtrip(hs, product_lib, oracle):
     """BASELINE.json config 1: N=1024, forward then inverse, /N round trip."""
     n = 1024
