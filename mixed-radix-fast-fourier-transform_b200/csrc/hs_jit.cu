@@ -527,7 +527,7 @@ extern "C" int hs_cu_jit_has_real(int handle)
 // sub-plans.  Same stages, butterflies and literals in the same order as the reference's recursion, so parity is unchanged;
 // the run-time engine (hs_generic.cuh) served these lengths at about a tenth of the HBM roofline.
 struct SubChoice { int T, C, logpad, minb, threads, smem; };
-static bool choose_sub(int L, const int *rx, int nst, SubChoice &c)
+static bool choose_sub(int L, const int *rx, int nst, SubChoice &c, int want_c = 0)
 {
     if (nst < 2 || nst > 8 || L < 16 || L > 2048) return false;
     int maxr = 1;
@@ -550,6 +550,7 @@ static bool choose_sub(int L, const int *rx, int nst, SubChoice &c)
     }
     c.logpad = best;
     c.C = c.T <= 16 ? 8 : (c.T <= 64 ? 4 : 2);
+    if (want_c > 0) c.C = want_c;
     c.threads = c.T * c.C;
     if (c.threads > 512) return false;
     const int npad = best ? L + (L >> best) + 1 : L;
@@ -600,7 +601,11 @@ extern "C" int hs_cu_jit_twopass_create(long long n, int sgn, const int *rx, int
     for (size_t i = 0; i < g_tp.size(); ++i)
         if (g_tp[i]->n == n && g_tp[i]->sgn == sgn && g_tp[i]->dev == dev && g_tp[i]->n1 == n1) { *desc = g_tp[i]->desc; return (int)i; }
     SubChoice c1, c2;
-    if (!choose_sub((int)n1, rx, split, c1) || !choose_sub((int)n2, rx + split, nst - split, c2)) return -1;
+    // HSFFT_JIT_C1 / _C2: columns per tile of the first / second pass (tuning aids)
+    if (!choose_sub((int)n1, rx, split, c1, env_or("HSFFT_JIT_C1", 0)) || !choose_sub((int)n2, rx + split, nst - split, c2, env_or("HSFFT_JIT_C2", 0))) return -1;
+    if (getenv("HSFFT_VERBOSE"))
+        fprintf(stderr, "hsfft: plan-time two-pass N=%lld = %lld x %lld: pass 1 T=%d C=%d (%d threads, %d B, %d CTAs/SM), pass 2 T=%d C=%d (%d threads, %d B, %d CTAs/SM)\n",
+                n, n1, n2, c1.T, c1.C, c1.threads, c1.smem, c1.minb, c2.T, c2.C, c2.threads, c2.smem, c2.minb);
     Nvrtc *rt = nvrtc();
     Driver *drv = driver();
     if (!rt || !drv) return -1;
