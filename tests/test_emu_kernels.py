@@ -183,14 +183,18 @@ def test_real_transforms_ride_on_the_one_kernel_complex_plan(hs, emu_lib, oracle
         assert max(rel_rms(y[i], oracle.c2r(Xr, n)[i]) for i in range(5)) <= min(tol(n), 5e-15)
 
 
-@pytest.mark.parametrize("n,swap", [(1 << 15, 0), (1 << 16, 0), (1 << 17, 0), (1 << 17, 1), (1 << 18, 0), (1 << 20, 0)])
-def test_real_four_step_split_on_pass_1_mirror_on_pass_2(hs, emu_lib, oracle, n, swap, monkeypatch):
+@pytest.mark.parametrize("n,swap,staged", [(1 << 15, 0, 0), (1 << 16, 0, 0), (1 << 17, 0, 0), (1 << 17, 1, 0), (1 << 17, 0, 1), (1 << 18, 0, 0),
+                                           (1 << 19, 0, 0), (1 << 19, 0, 1), (1 << 20, 0, 1)])
+def test_real_four_step_split_on_pass_1_mirror_on_pass_2(hs, emu_lib, oracle, n, swap, staged, monkeypatch):
     """Long forward real transforms (hs_tiled.cuh IO 8 / 9): two launches, no split kernel; full spectrum with an exact
     Hermitian mirror, and the half spectrum (bins 0..N/2) with a row stride larger than N/2+1 straight through the
-    device-pointer entry point (host arrays stand in for device memory under the emulation)."""
+    device-pointer entry point (host arrays stand in for device memory under the emulation).  Every split the planner
+    picks (128 x 256 ... 1024 x 256, 1024 x 512 with the second-pass 512-point plan, 1024 x 1024); `staged`: the first
+    pass on the persistent TMA-staged kernel (what the GPU runs for n1 = 512 / 1024), with the split as its epilogue."""
     import ctypes as C
     if swap:
         monkeypatch.setenv("HSFFT_R4_SWAP", "1")
+    monkeypatch.setenv("HSFFT_R4_TMA", "1" if staged else "0")
     b = 2 if n <= (1 << 17) else 1
     x = xorshift_uniform(b * n, seed=3 + n).reshape(b, n)
     Xr = oracle.r2c(x)
