@@ -45,6 +45,7 @@ typedef struct hs_c2c {
     int jtp_id;         /* >= 0: the two passes compiled for this length when the plan was created (hs_jit.cu) */
     int n1, n2;
     void *d_tw2, *d_twb, *d_tws; /* pass-2 stage twiddles and the inter-pass tables W_n^{k b}, W_n^{k NB} */
+    void *d_mrg_wc, *d_mrg_wr; /* c2r merge on pass 1: exp(2 pi i c / 2n), c < n2, and exp(2 pi i n2 r / 2n), r < n1 (made on first use) */
     int npass;          /* otherwise: run-time planned passes */
     hs_gen_params pass[HS_MAX_PASS];
     void *d_pass_tw[HS_MAX_PASS], *d_pass_lo[HS_MAX_PASS], *d_pass_hi[HS_MAX_PASS];

@@ -223,6 +223,25 @@ struct HsLoadColC2RPre {
         return hs_c(a.x + c.x + (t1 * w.x) - (t2 * w.y), a.y - c.y + (t2 * w.x) + (t1 * w.y));
     }
 };
+// the same with twiddle2[column + n2 row] formed as the product of a per-column factor (held in a register) and a per-row
+// factor (n1 entries, L1 resident) instead of read from the H-entry table: at N = 2^20 that table is 8 MB, read once per
+// transform -- a third of the pass's L2 traffic
+template <int LDP = 0>
+struct HsLoadColC2RPre2 {
+    static constexpr bool kPost = false;
+    const cplx *HS_RESTRICT x;  // this transform's bins 0..H
+    const cplx *HS_RESTRICT wr; // exp(+2 pi i n2 row / N)
+    cplx wc;                    // exp(+2 pi i column / N)
+    int H;
+    long long off0, es;
+    HS_DEVICE cplx operator()(int, int, int n_) const
+    {
+        const long long k = off0 + n_ * es;
+        const cplx a = hs_ld_mp<LDP>(x + k), c = hs_ld_mp<LDP>(x + (H - k)), w = hs_mul(wc, hs_ld_tab(wr + n_));
+        const double t1 = -a.y - c.y, t2 = -c.x + a.x;
+        return hs_c(a.x + c.x + (t1 * w.x) - (t2 * w.y), a.y - c.y + (t2 * w.x) + (t1 * w.y));
+    }
+};
 
 // loaders for a tile the copy engine staged in shared memory, layout [row][C] (dense): with lane = column a
 // quarter-warp reads adjacent 16-byte slots -- conflict free
@@ -363,8 +382,13 @@ HS_DEVICE void hs_tile_run(const cplx *HS_RESTRICT in_x, cplx *HS_RESTRICT out_x
         hs_fft_team2<P, SGN>(ld, st, first, rest, tw, hk);
     } else if constexpr (IO == 3) { // c2r: merge fused into pass 1 (g.chirp = twiddle2, g.nlog = H)
         HsStoreCol<STP> st{out_x + (long long)(c0 + colS) * g.out_c, g.out_e};
-        HsLoadColC2RPre<LDP> ld{in_x, (const cplx *)g.chirp, g.nlog, (long long)(c0 + colA) * g.in_c, g.in_e};
-        hs_fft_team2<P, SGN>(ld, st, first, rest, tw, hk);
+        if (g.twb) { // column / row factors of twiddle2 (in_c == 1: the column index is the offset)
+            HsLoadColC2RPre2<LDP> ld{in_x, (const cplx *)g.tws, hs_ld_tab((const cplx *)g.twb + (c0 + colA)), g.nlog, (long long)(c0 + colA) * g.in_c, g.in_e};
+            hs_fft_team2<P, SGN>(ld, st, first, rest, tw, hk);
+        } else {
+            HsLoadColC2RPre<LDP> ld{in_x, (const cplx *)g.chirp, g.nlog, (long long)(c0 + colA) * g.in_c, g.in_e};
+            hs_fft_team2<P, SGN>(ld, st, first, rest, tw, hk);
+        }
     } else if constexpr (IO == 4) { // convolution: zero padding on load (windows of g.nlog reals of one long array)
         HsStoreCol<STP> st{out_x + (long long)(c0 + colS) * g.out_c, g.out_e};
         HsLoadColPadReal ld{(const double *)in_x, xf * g.pad_stride + g.pad_off, g.pad_total, g.nlog, (long long)(c0 + colA) * g.in_c, g.in_e};

@@ -558,6 +558,7 @@ void hs_c2c_destroy(hs_c2c *p)
     if (!p) return;
     hs_cu_free(p->d_tw);
     hs_cu_free(p->d_tw2); hs_cu_free(p->d_twb); hs_cu_free(p->d_tws);
+    hs_cu_free(p->d_mrg_wc); hs_cu_free(p->d_mrg_wr);
     for (int g = 0; g < HS_MAX_PASS; ++g) { hs_cu_free(p->d_pass_tw[g]); hs_cu_free(p->d_pass_lo[g]); hs_cu_free(p->d_pass_hi[g]); }
     hs_cu_free(p->d_gen_cs);
     hs_cu_free(p->d_gen_sn);
@@ -1118,6 +1119,22 @@ int hs_dev_exec_c2r_fused(hs_dev_obj *d, const void *d_spec, long long in_stride
     memset(&g, 0, sizeof g);
     g.ncols = tp->n2; g.in_xf = in_stride; g.in_c = 1; g.in_e = tp->n2; g.out_xf = p->n; g.out_c = tp->n1; g.out_e = 1;
     g.chirp = d_tw2; g.nlog = p->n;
+    if (!p->d_mrg_wc && p->n >= (1 << 17) && !getenv("HSFFT_C2R_TW2_TABLE")) {
+        /* twiddle2[c + n2 r] = exp(2 pi i (c + n2 r) / 2n) as a product of a column and a row factor (HsLoadColC2RPre2) where
+         * the table no longer sits close to the SMs: measured on B200 per 2^28 reals, merge pass with the product / the table:
+         * N = 2^20 1.11 / 1.17 ms, 2^18 0.87 / 0.97, 2^19 0.98 / 0.98, but 2^16 0.92 / 0.85 and 2^15 0.91 / 0.84 */
+        hs_c2c *pw = (hs_c2c *)p;
+        fft_data *wc = (fft_data *)malloc(sizeof(fft_data) * tp->n2), *wr = (fft_data *)malloc(sizeof(fft_data) * tp->n1);
+        if (!wc || !wr) { fprintf(stderr, "Error: Memory allocation failed for twiddle table\n"); exit(EXIT_FAILURE); }
+        const fft_type theta = PI2 / (fft_type)(2 * (long long)p->n);
+        for (int c = 0; c < tp->n2; ++c) { wc[c].re = cos(theta * c); wc[c].im = sin(theta * c); }
+        for (int r = 0; r < tp->n1; ++r) { wr[r].re = cos(theta * ((fft_type)tp->n2 * r)); wr[r].im = sin(theta * ((fft_type)tp->n2 * r)); }
+        pw->d_mrg_wc = upload(wc, sizeof(fft_data) * tp->n2);
+        pw->d_mrg_wr = upload(wr, sizeof(fft_data) * tp->n1);
+        hs_cu_stream_sync(NULL);
+        free(wc); free(wr);
+    }
+    g.twb = p->d_mrg_wc; g.tws = p->d_mrg_wr;
     hs_cu_launch_tiled_io(s1->id, p->sgn, 0, 0, 3, 1, d_spec, d_ws, p->d_tw, &g, howmany, stream);
     hs_cu_launch_ct_twopass(p->tp_id, 2, p->sgn, d_ws, d_out, p->d_tw2, p->d_twb, p->d_tws, howmany, stream);
     return 1;
