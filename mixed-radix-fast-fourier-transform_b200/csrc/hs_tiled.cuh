@@ -286,7 +286,9 @@ struct HsLoadColPadReal { // a window of a long real array read as a row of comp
 struct HsLoadColC2RMul { // element k of the packed signal from bins k and H-k of the product of two spectra
     static constexpr bool kPost = false;
     const cplx *HS_RESTRICT xa, *HS_RESTRICT xb; // bins 0..H of the two spectra
-    const cplx *HS_RESTRICT tw2;
+    const cplx *HS_RESTRICT tw2;                 // twiddle2, or (wr != nullptr) unused: twiddle2[k] = wc * wr[row]
+    const cplx *HS_RESTRICT wr;
+    cplx wc;
     int H;
     double scale;
     long long off0, es;
@@ -294,7 +296,8 @@ struct HsLoadColC2RMul { // element k of the packed signal from bins k and H-k o
     {
         const long long k = off0 + n_ * es;
         const cplx pa = hs_mul(hs_ld_stream(xa + k), hs_ld_stream(xb + k)), pc = hs_mul(hs_ld_stream(xa + (H - k)), hs_ld_stream(xb + (H - k)));
-        const cplx a = hs_c(pa.x * scale, pa.y * scale), c = hs_c(pc.x * scale, pc.y * scale), w = hs_ld_tab(tw2 + k); // reference :147-160
+        const cplx a = hs_c(pa.x * scale, pa.y * scale), c = hs_c(pc.x * scale, pc.y * scale);
+        const cplx w = wr ? hs_mul(wc, hs_ld_tab(wr + n_)) : hs_ld_tab(tw2 + k); // reference :147-160
         const double t1 = -a.y - c.y, t2 = -c.x + a.x;
         return hs_c(a.x + c.x + (t1 * w.x) - (t2 * w.y), a.y - c.y + (t2 * w.x) + (t1 * w.y));
     }
@@ -395,7 +398,8 @@ HS_DEVICE void hs_tile_run(const cplx *HS_RESTRICT in_x, cplx *HS_RESTRICT out_x
         hs_fft_team2<P, SGN>(ld, st, first, rest, tw, hk);
     } else if constexpr (IO == 5) { // convolution: product of two spectra, scaled, merged (g.chirp = twiddle2, g.nlog = H)
         HsStoreCol<STP> st{out_x + (long long)(c0 + colS) * g.out_c, g.out_e};
-        HsLoadColC2RMul ld{in_x, (const cplx *)g.aux + xf * g.aux_xf, (const cplx *)g.chirp, g.nlog, g.scale, (long long)(c0 + colA) * g.in_c, g.in_e};
+        HsLoadColC2RMul ld{in_x, (const cplx *)g.aux + xf * g.aux_xf, (const cplx *)g.chirp, (const cplx *)g.tws,
+                           g.twb ? hs_ld_tab((const cplx *)g.twb + (c0 + colA)) : hs_c(1.0, 0.0), g.nlog, g.scale, (long long)(c0 + colA) * g.in_c, g.in_e};
         hs_fft_team2<P, SGN>(ld, st, first, rest, tw, hk);
     } else if constexpr (IO == 6) { // convolution: slice on store (rows of g.aux_xf reals)
         static_assert(TW == 1 && STCOL, "the slice store belongs to a second pass");

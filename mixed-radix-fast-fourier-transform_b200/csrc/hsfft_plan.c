@@ -1097,6 +1097,24 @@ int hs_dev_exec_r2c_fused(hs_dev_obj *d, const void *d_in, void *d_out, long lon
     return 0;
 }
 
+/* twiddle2[c + n2 r] = exp(2 pi i (c + n2 r) / 2n) as a product of a column and a row factor (HsLoadColC2RPre2, HsLoadColC2RMul)
+ * where the table no longer sits close to the SMs: measured on B200 per 2^28 reals, merge pass with the product / the table:
+ * N = 2^20 1.11 / 1.17 ms, 2^18 0.87 / 0.97, 2^19 0.98 / 0.98, but 2^16 0.92 / 0.85 and 2^15 0.91 / 0.84 */
+static void c2r_merge_factors(const hs_c2c *p, const hs_ct_desc *tp)
+{
+    if (p->d_mrg_wc || p->n < (1 << 17) || getenv("HSFFT_C2R_TW2_TABLE")) return;
+    hs_c2c *pw = (hs_c2c *)p;
+    fft_data *wc = (fft_data *)malloc(sizeof(fft_data) * tp->n2), *wr = (fft_data *)malloc(sizeof(fft_data) * tp->n1);
+    if (!wc || !wr) { fprintf(stderr, "Error: Memory allocation failed for twiddle table\n"); exit(EXIT_FAILURE); }
+    const fft_type theta = PI2 / (fft_type)(2 * (long long)p->n);
+    for (int c = 0; c < tp->n2; ++c) { wc[c].re = cos(theta * c); wc[c].im = sin(theta * c); }
+    for (int r = 0; r < tp->n1; ++r) { wr[r].re = cos(theta * ((fft_type)tp->n2 * r)); wr[r].im = sin(theta * ((fft_type)tp->n2 * r)); }
+    pw->d_mrg_wc = upload(wc, sizeof(fft_data) * tp->n2);
+    pw->d_mrg_wr = upload(wr, sizeof(fft_data) * tp->n1);
+    hs_cu_stream_sync(NULL);
+    free(wc); free(wr);
+}
+
 int hs_dev_exec_c2r_fused(hs_dev_obj *d, const void *d_spec, long long in_stride, const void *d_tw2, void *d_out, void *d_ws,
                           long long howmany, void *stream)
 {
@@ -1119,21 +1137,7 @@ int hs_dev_exec_c2r_fused(hs_dev_obj *d, const void *d_spec, long long in_stride
     memset(&g, 0, sizeof g);
     g.ncols = tp->n2; g.in_xf = in_stride; g.in_c = 1; g.in_e = tp->n2; g.out_xf = p->n; g.out_c = tp->n1; g.out_e = 1;
     g.chirp = d_tw2; g.nlog = p->n;
-    if (!p->d_mrg_wc && p->n >= (1 << 17) && !getenv("HSFFT_C2R_TW2_TABLE")) {
-        /* twiddle2[c + n2 r] = exp(2 pi i (c + n2 r) / 2n) as a product of a column and a row factor (HsLoadColC2RPre2) where
-         * the table no longer sits close to the SMs: measured on B200 per 2^28 reals, merge pass with the product / the table:
-         * N = 2^20 1.11 / 1.17 ms, 2^18 0.87 / 0.97, 2^19 0.98 / 0.98, but 2^16 0.92 / 0.85 and 2^15 0.91 / 0.84 */
-        hs_c2c *pw = (hs_c2c *)p;
-        fft_data *wc = (fft_data *)malloc(sizeof(fft_data) * tp->n2), *wr = (fft_data *)malloc(sizeof(fft_data) * tp->n1);
-        if (!wc || !wr) { fprintf(stderr, "Error: Memory allocation failed for twiddle table\n"); exit(EXIT_FAILURE); }
-        const fft_type theta = PI2 / (fft_type)(2 * (long long)p->n);
-        for (int c = 0; c < tp->n2; ++c) { wc[c].re = cos(theta * c); wc[c].im = sin(theta * c); }
-        for (int r = 0; r < tp->n1; ++r) { wr[r].re = cos(theta * ((fft_type)tp->n2 * r)); wr[r].im = sin(theta * ((fft_type)tp->n2 * r)); }
-        pw->d_mrg_wc = upload(wc, sizeof(fft_data) * tp->n2);
-        pw->d_mrg_wr = upload(wr, sizeof(fft_data) * tp->n1);
-        hs_cu_stream_sync(NULL);
-        free(wc); free(wr);
-    }
+    c2r_merge_factors(p, tp);
     g.twb = p->d_mrg_wc; g.tws = p->d_mrg_wr;
     hs_cu_launch_tiled_io(s1->id, p->sgn, 0, 0, 3, 1, d_spec, d_ws, p->d_tw, &g, howmany, stream);
     hs_cu_launch_ct_twopass(p->tp_id, 2, p->sgn, d_ws, d_out, p->d_tw2, p->d_twb, p->d_tws, howmany, stream);
@@ -1182,6 +1186,8 @@ int hs_dev_exec_c2r_mul_slice(hs_dev_obj *d, const void *d_A, const void *d_B, l
     memset(&g, 0, sizeof g);
     g.ncols = tp->n2; g.in_xf = in_stride; g.in_c = 1; g.in_e = tp->n2; g.out_xf = p->n; g.out_c = tp->n1; g.out_e = 1;
     g.chirp = d_tw2; g.nlog = p->n; g.aux = d_B; g.aux_xf = b_stride; g.scale = scale;
+    c2r_merge_factors(p, tp);
+    g.twb = p->d_mrg_wc; g.tws = p->d_mrg_wr;
     hs_cu_launch_tiled_io(s1->id, p->sgn, 0, 0, 5, 1, d_A, d_ws, p->d_tw, &g, howmany, stream);
     memset(&g, 0, sizeof g);
     g.ncols = tp->n1; g.in_xf = p->n; g.in_c = 1; g.in_e = tp->n1; g.out_xf = 0; g.out_c = 1; g.out_e = tp->n1;
