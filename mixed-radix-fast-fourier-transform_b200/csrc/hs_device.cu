@@ -320,16 +320,33 @@ static void launch_r2c(const void *in, void *out, const void *tw, const void *tw
     HS_CUDA_CHECK(cudaGetLastError());
     hs_launched("r2c", st);
 }
+#ifndef HS_C2R_STAGE_DEFAULT
+#define HS_C2R_STAGE_DEFAULT 1
+#endif
 template <class P, int SGN, int MINB>
 static void launch_c2r(const void *in, void *out, const void *tw, const void *tw2, long long in_stride, long long howmany, cudaStream_t st)
 {
-    auto kern = hs_c2r_smem_kernel<P, SGN, MINB>;
-    hs_func_attr_once((const void *)kern, P::smem_bytes, MINB);
+    // The merge reads a copy of the row staged in the team's buffer (every bin fetched once, in order) unless HSFFT_C2R_STAGE=0
+    // (every bin loaded twice straight from global memory); =2 stages for every plan.  Measured on B200, fraction of the HBM
+    // peak staged / direct by real length N (plan length H = N/2): N = 512 91 / 60 %, 2048 65 / 46 %, 4096 72 / 70 %, 8192
+    // 72 / 70 %; the two plans that do not gain keep the direct form: N = 1024 (H = 512) 79.5 / 80.8 %, N = 16384 (H = 8192,
+    // one CTA per SM) 45.0 / 46.7 %.  profiles/r2_c2r_staged_merge_one_kernel_ab.txt
+    static int want = -1;
+    if (want < 0) { const char *e = getenv("HSFFT_C2R_STAGE"); want = e ? atoi(e) : HS_C2R_STAGE_DEFAULT; }
+    const int stage = want == 2 || (want == 1 && P::N != 512 && P::N != 8192);
     const long long blocks = (howmany + P::X - 1) / P::X;
     check_grid(blocks);
-    kern<<<(unsigned)blocks, P::threads, P::smem_bytes, st>>>((const cplx *)in, (cplx *)out, (const cplx *)tw, (const cplx *)tw2, in_stride, howmany);
+    if (stage) {
+        auto kern = hs_c2r_smem_kernel<P, SGN, MINB, true>;
+        hs_func_attr_once((const void *)kern, P::smem_bytes, MINB);
+        kern<<<(unsigned)blocks, P::threads, P::smem_bytes, st>>>((const cplx *)in, (cplx *)out, (const cplx *)tw, (const cplx *)tw2, in_stride, howmany);
+    } else {
+        auto kern = hs_c2r_smem_kernel<P, SGN, MINB>;
+        hs_func_attr_once((const void *)kern, P::smem_bytes, MINB);
+        kern<<<(unsigned)blocks, P::threads, P::smem_bytes, st>>>((const cplx *)in, (cplx *)out, (const cplx *)tw, (const cplx *)tw2, in_stride, howmany);
+    }
     HS_CUDA_CHECK(cudaGetLastError());
-    hs_launched("c2r", st);
+    hs_launched(stage ? "c2r (staged merge)" : "c2r", st);
 }
 
 template <class PF, class PI, int SGN, int MINB>

@@ -527,8 +527,25 @@ hs_r2c_smem_kernel(const cplx *HS_RESTRICT in, cplx *HS_RESTRICT out, const cplx
     if (active) hs_r2c_split_rows<P>(sm, out + xf * out_stride, tw2, full, t);
 }
 
+// the merge from a copy of bins 0..H-1 in the team's own buffer (bin H, needed for k = 0 only, comes from global memory):
+// every bin is then read from HBM / L2 once, in order, by asynchronous 16-byte copies, instead of twice (as k and as H-k)
+struct HsLoadC2RMergeSmem {
+    static constexpr bool kPost = false, kFromSmem = true;
+    const cplx *sm;                // bins 0..H-1, natural order
+    const cplx *HS_RESTRICT xh;    // bin H
+    const cplx *HS_RESTRICT tw2;
+    int H;
+    HS_DEVICE cplx operator()(int, int, int k) const
+    {
+        const cplx a = sm[k], c = k ? sm[H - k] : hs_ld_tab(xh), w = hs_ld_tab(tw2 + k);
+        const double t1 = -a.y - c.y, t2 = -c.x + a.x; // reference :171-179
+        return hs_c(a.x + c.x + (t1 * w.x) - (t2 * w.y), a.y - c.y + (t2 * w.x) + (t1 * w.y));
+    }
+};
+
 // in: rows of in_stride bins (0..H are read); out: rows of 2H reals written as H complex samples (contiguous)
-template <class P, int SGN, int MINB>
+// STG: the merge reads a staged copy of the row (HsLoadC2RMergeSmem) instead of loading every bin twice
+template <class P, int SGN, int MINB, bool STG = false>
 HS_GLOBAL void HS_LAUNCH_BOUNDS(P::threads, MINB)
 hs_c2r_smem_kernel(const cplx *HS_RESTRICT in, cplx *HS_RESTRICT out, const cplx *HS_RESTRICT tw, const cplx *HS_RESTRICT tw2, long long in_stride,
                    long long howmany)
@@ -537,7 +554,18 @@ hs_c2r_smem_kernel(const cplx *HS_RESTRICT in, cplx *HS_RESTRICT out, const cplx
     const int team = HS_TID / P::T, t = HS_TID % P::T;
     const long long xf = HS_BID * P::X + team;
     const bool active = xf < howmany;
-    HsLoadC2RMerge ld{in + (active ? xf : 0) * in_stride, tw2, P::N};
     HsStoreGlobal st{out + (active ? xf : 0) * P::N};
-    hs_fft_team<P, SGN>(ld, st, smem + team * P::NPAD, tw, t, active);
+    if constexpr (STG) {
+        cplx *sm = smem + team * P::NPAD;
+        const cplx *x = in + (active ? xf : 0) * in_stride;
+        if (active)
+            for (int k = t; k < P::N; k += P::T) hs_cp_async16(sm + k, x + k);
+        hs_cp_async_wait_all();
+        HS_SYNC();
+        HsLoadC2RMergeSmem ld{sm, x + P::N, tw2, P::N};
+        hs_fft_team<P, SGN>(ld, st, sm, tw, t, active);
+    } else {
+        HsLoadC2RMerge ld{in + (active ? xf : 0) * in_stride, tw2, P::N};
+        hs_fft_team<P, SGN>(ld, st, smem + team * P::NPAD, tw, t, active);
+    }
 }

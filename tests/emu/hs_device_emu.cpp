@@ -42,6 +42,13 @@ static void launch_r2c(const void *in, void *out, const void *tw, const void *tw
 template <class P, int SGN, int MINB>
 static void launch_c2r(const void *in, void *out, const void *tw, const void *tw2, long long in_stride, long long howmany, hs_stream_t)
 {
+    const char *e = getenv("HSFFT_C2R_STAGE");
+    if (e ? atoi(e) != 0 : (P::N != 512 && P::N != 8192)) { // the product's rule (hs_device.cu launch_c2r)
+        hs_emu_launch(hs_c2r_smem_kernel<P, SGN, MINB, true>, (howmany + P::X - 1) / P::X, P::threads, P::smem_bytes, (const cplx *)in, (cplx *)out,
+                      (const cplx *)tw, (const cplx *)tw2, in_stride, howmany);
+        ++g_launches;
+        return;
+    }
     hs_emu_launch(hs_c2r_smem_kernel<P, SGN, MINB>, (howmany + P::X - 1) / P::X, P::threads, P::smem_bytes, (const cplx *)in, (cplx *)out,
                   (const cplx *)tw, (const cplx *)tw2, in_stride, howmany);
     ++g_launches;

@@ -210,6 +210,19 @@ def test_real_four_step_split_on_pass_1_mirror_on_pass_2(hs, emu_lib, oracle, n,
         assert np.array_equal(half[:, : n // 2 + 1], X[:, : n // 2 + 1]) and np.isnan(half[:, n // 2 + 1:]).all()
 
 
+@pytest.mark.parametrize("n,stage", [(1024, "0"), (1024, "2"), (4096, "0"), (4096, "2"), (6000, "2")])
+def test_one_kernel_c2r_merge_direct_and_from_a_staged_row(hs, emu_lib, oracle, n, stage, monkeypatch):
+    """hs_c2r_smem_kernel<..., STG>: the merge either loads bins k and H-k straight from global memory (HSFFT_C2R_STAGE=0)
+    or reads a copy of bins 0..H-1 staged in the team's buffer by asynchronous copies, bin H from global memory (=2: for
+    every plan; the default picks per plan).  Arbitrary complex bins: the reference's merge defines the result."""
+    monkeypatch.setenv("HSFFT_C2R_STAGE", stage)
+    X = rand_cplx(5, n, seed=n + int(stage))
+    with hs.RealPlan(n, -1, lib=emu_lib) as g:
+        y = g.c2r(X)
+    yr = oracle.c2r(X, n)
+    assert max(rel_rms(y[i], yr[i]) for i in range(5)) <= min(tol(n), 5e-15)
+
+
 @pytest.mark.parametrize("la,lb", [(5, 3), (100, 37), (512, 512), (1000, 24)])
 def test_convolution(hs, emu_lib, oracle, la, lb):
     a, b = xorshift_uniform(la, seed=la), xorshift_uniform(lb, seed=lb + 1)
