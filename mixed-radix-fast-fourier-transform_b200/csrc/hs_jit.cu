@@ -235,7 +235,7 @@ static std::vector<JitPlan *> g_plans;
 
 static std::string make_source(int n, int sgn, const int *rx, int nst, const JitChoice &c)
 {
-    char buf[4096];
+    char buf[8192];
     std::string rad;
     for (int s = 0; s < nst; ++s) { snprintf(buf, sizeof buf, ", %d", rx[s]); rad += buf; }
     // three entry points over one plan: the complex transform and the two real transforms that ride on it (the bodies of
@@ -279,11 +279,23 @@ static std::string make_source(int n, int sgn, const int *rx, int nst, const Jit
              "    const int team = HS_TID / PJ::T, t = HS_TID %% PJ::T;\n"
              "    const long long xf = HS_BID * PJ::X + team;\n"
              "    const bool active = xf < howmany;\n"
-             "    HsLoadC2RMerge ld{in + (active ? xf : 0) * in_stride, tw2, PJ::N};\n"
              "    HsStoreGlobal st{out + (active ? xf : 0) * PJ::N};\n"
-             "    hs_fft_team<PJ, %d>(ld, st, smem + team * PJ::NPAD, tw, t, active);\n"
+             "    if (%d) { // merge from a copy of the row staged in the team's buffer (see hs_c2r_smem_kernel)\n"
+             "        cplx *sm = smem + team * PJ::NPAD;\n"
+             "        const cplx *x = in + (active ? xf : 0) * in_stride;\n"
+             "        if (active)\n"
+             "            for (int k = t; k < PJ::N; k += PJ::T) hs_cp_async16(sm + k, x + k);\n"
+             "        hs_cp_async_wait_all();\n"
+             "        HS_SYNC();\n"
+             "        HsLoadC2RMergeSmem ld{sm, x + PJ::N, tw2, PJ::N};\n"
+             "        hs_fft_team<PJ, %d>(ld, st, sm, tw, t, active);\n"
+             "    } else {\n"
+             "        HsLoadC2RMerge ld{in + (active ? xf : 0) * in_stride, tw2, PJ::N};\n"
+             "        hs_fft_team<PJ, %d>(ld, st, smem + team * PJ::NPAD, tw, t, active);\n"
+             "    }\n"
              "}\n",
-             n, c.T, c.X, c.logpad, c.groups, rad.c_str(), c.minb, sgn, c.minb, sgn, c.minb, sgn);
+             n, c.T, c.X, c.logpad, c.groups, rad.c_str(), c.minb, sgn, c.minb, sgn, c.minb,
+             env_or("HSFFT_C2R_STAGE", 1) == 2 ? 1 : 0, sgn, sgn); // plan-time kernels: the staged merge measured 2-6 % slower (N = 2000, 2002, 4000, 4374)
     std::string src(buf);
     if (c.X == 1 && c.npass > 1) { // persistent twin with the next input staged by the copy engine (see HsStageRefill)
         snprintf(buf, sizeof buf,

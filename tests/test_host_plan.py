@@ -148,14 +148,14 @@ def test_plan_time_kernel_source_is_generated_and_compiles_with_nvrtc(hs, produc
     L = product_lib
     L.hs_cu_jit_source.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int, C.c_char_p, C.c_int]
     L.hs_cu_jit_source.restype = C.c_int
-    buf = C.create_string_buffer(4096)
+    buf = C.create_string_buffer(16384)
     rx = (C.c_int * 4)(5, 5, 5, 8)                      # N = 1000: the reference's factor list [8,5,5,5] reversed
-    assert L.hs_cu_jit_source(1000, 1, rx, 4, buf, 4096) > 0
+    assert L.hs_cu_jit_source(1000, 1, rx, 4, buf, 16384) > 0
     src = buf.value.decode()
     assert "HsPlan<1000, 125, 1, 3, -2, 1111, 5, 5, 5, 8>" in src and "hs_fft_team<PJ, 1>" in src
-    assert L.hs_cu_jit_source(1472, 1, (C.c_int * 3)(8, 8, 23), 3, buf, 4096) == 0       # radix 23: not a template radix
-    buf2 = C.create_string_buffer(4096)
-    assert L.hs_cu_jit_source(1001, 1, (C.c_int * 3)(7, 11, 13), 3, buf2, 4096) > 0      # radix 11, 13, 17: unrolled generic butterflies
+    assert L.hs_cu_jit_source(1472, 1, (C.c_int * 3)(8, 8, 23), 3, buf, 16384) == 0       # radix 23: not a template radix
+    buf2 = C.create_string_buffer(16384)
+    assert L.hs_cu_jit_source(1001, 1, (C.c_int * 3)(7, 11, 13), 3, buf2, 16384) > 0      # radix 11, 13, 17: unrolled generic butterflies
     src2 = buf2.value.decode()
     assert "7, 11, 13>" in src2 and "hs_jit_r2c" in src2 and "hs_jit_c2r" in src2
     try:
