@@ -85,8 +85,8 @@ static void ct_init()
     fill_desc2<S128, S128>(g_ct[CT_T14], CT_T14);
     fill_desc2<S128, S256>(g_ct[CT_T15], CT_T15);
     fill_desc2<S256, S256>(g_ct[CT_T16], CT_T16);
-    fill_desc2<S256, S512b>(g_ct[CT_T17], CT_T17);
-    fill_desc2<S512, S512b>(g_ct[CT_T18], CT_T18);
+    fill_desc2<HS_T17_P1, HS_T17_P2>(g_ct[CT_T17], CT_T17);
+    fill_desc2<HS_T18_P1, HS_T18_P2>(g_ct[CT_T18], CT_T18);
     fill_desc2<S1024, S512b>(g_ct[CT_T19], CT_T19); // (512 x 1024 before: 3.73 ms per 2^19 x 512 against ... with the 1024-point pass staged first)
     fill_desc2<S1024, S1024>(g_ct[CT_T20], CT_T20);
     fill_desc<S128>(g_ct[CT_S128], CT_S128, HS_CT_SUB);
@@ -315,8 +315,8 @@ extern "C" void hs_cu_launch_ct_twopass(int id, int pass, int sgn, const void *d
     case CT_T14: launch_twopass<S128, S128>(pass, sgn, d_in, d_out, d_tw, d_twb, d_tws, howmany, st); break;
     case CT_T15: launch_twopass<S128, S256>(pass, sgn, d_in, d_out, d_tw, d_twb, d_tws, howmany, st); break;
     case CT_T16: launch_twopass<S256, S256>(pass, sgn, d_in, d_out, d_tw, d_twb, d_tws, howmany, st); break;
-    case CT_T17: launch_twopass<S256, S512b>(pass, sgn, d_in, d_out, d_tw, d_twb, d_tws, howmany, st); break;
-    case CT_T18: launch_twopass<S512, S512b>(pass, sgn, d_in, d_out, d_tw, d_twb, d_tws, howmany, st); break;
+    case CT_T17: launch_twopass<HS_T17_P1, HS_T17_P2>(pass, sgn, d_in, d_out, d_tw, d_twb, d_tws, howmany, st); break;
+    case CT_T18: launch_twopass<HS_T18_P1, HS_T18_P2>(pass, sgn, d_in, d_out, d_tw, d_twb, d_tws, howmany, st); break;
     case CT_T19: launch_twopass<S1024, S512b>(pass, sgn, d_in, d_out, d_tw, d_twb, d_tws, howmany, st); break;
     case CT_T20: launch_twopass<S1024, S1024>(pass, sgn, d_in, d_out, d_tw, d_twb, d_tws, howmany, st); break;
     case CT_TX20480: launch_twopass<S160x, S128>(pass, sgn, d_in, d_out, d_tw, d_twb, d_tws, howmany, st); break;

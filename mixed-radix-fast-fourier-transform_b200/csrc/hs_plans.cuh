@@ -84,6 +84,18 @@ using S1024 = HsPlan<1024, 64, 1, 3, HS_SUB_SPLIT, 0, 16, 8, 8>;      // (T=128,
 // 64-byte runs on the strided stores.  Measured on B200 (profiles/r2_subplan_variants.txt): second pass 1.44 vs 1.60 ms at
 // 2^18 x 1024, the real four-step's mirrored pass 1.34 vs 1.83 ms; as a FIRST pass it loses (2.54 vs 1.82 ms), so S512 stays.
 using S512b = HsPlan<512, 32, 1, 3, HS_SUB_SPLIT, 0, 16, 8, 4>;
+// Which split a two-pass length takes is decided by its SECOND pass (strided stores): per 8.6 GB moved the 256-point plan
+// needs 1.23 ms, the second-pass 512-point plan 1.54-1.68, the 1024-point plan 1.87, while first passes run at 1.25-1.41 ms
+// whatever their length (profiles/r2_subplan_second_pass_and_r4_splits.txt).  So 2^17 = 512 x 256 and 2^18 = 1024 x 256
+// (before: 256 x 512 and 512 x 512).
+#ifndef HS_T17_P1
+#define HS_T17_P1 S512
+#define HS_T17_P2 S256
+#endif
+#ifndef HS_T18_P1
+#define HS_T18_P1 S1024
+#define HS_T18_P2 S256
+#endif
 // profiling-only ablations (never selected unless HSFFT_PREFER_CT names them)
 using P4096x = HsPlan<4096, 256, 1, 4, 0, 0, 16, 16, 16>;
 using P3000x = HsPlan<3000, 200, 1, 3, -1, 0, 3, 5, 5, 5, 8>;
