@@ -178,3 +178,40 @@ def test_plan_time_kernel_source_is_generated_and_compiles_with_nvrtc(hs, produc
     prog2 = C.c_void_p()
     assert rt.nvrtcCreateProgram(C.byref(prog2), src2.encode(), b"p2.cu", 4, (C.c_char_p * 4)(*texts), (C.c_char_p * 4)(*[n.encode() for n in names])) == 0
     assert rt.nvrtcCompileProgram(prog2, 4, opts) == 0
+
+
+def test_compile_time_kernel_table_is_self_consistent(hs, product_lib):
+    """csrc/hs_ct_table.cuh: every two-pass descriptor factors its length, and both of its stage lists belong to a sub-plan
+    the host side can launch by id (family HS_CT_SUB for first passes, HS_CT_SUB or HS_CT_SUB2 for second passes) -- the
+    fused real / convolution paths pair a descriptor's twiddle tables with those ids (hsfft_plan.c find_sub_like).
+    Host tables only: no GPU needed."""
+    import ctypes as C
+
+    class Desc(C.Structure):
+        _fields_ = [("id", C.c_int), ("family", C.c_int), ("n", C.c_int), ("nst", C.c_int), ("radix", C.c_int * 8), ("split_min", C.c_int),
+                    ("threads", C.c_int), ("smem_bytes", C.c_int), ("n1", C.c_int), ("n2", C.c_int), ("nst2", C.c_int), ("radix2", C.c_int * 8),
+                    ("split_min2", C.c_int), ("exact", C.c_int)]
+
+    L = product_lib
+    L.hs_cu_ct_count.restype = C.c_int
+    L.hs_cu_ct_get.restype = C.POINTER(Desc)
+    L.hs_cu_ct_get.argtypes = [C.c_int]
+    descs = [L.hs_cu_ct_get(i).contents for i in range(L.hs_cu_ct_count())]
+    assert len({d.id for d in descs}) == len(descs)
+    SUB, SUB2, TWOPASS = 3, 7, 2
+    subs = [(d.family, d.n, tuple(d.radix[: d.nst])) for d in descs if d.family in (SUB, SUB2)]
+    two = [d for d in descs if d.family == TWOPASS]
+    assert len(two) >= 7 and any(f == SUB2 for f, _, _ in subs)
+    for d in descs:
+        prod = 1
+        for r in d.radix[: d.nst]:
+            prod *= r
+        assert prod == (d.n1 if d.family == TWOPASS else d.n), (d.id, prod)
+    for d in two:
+        assert d.n1 * d.n2 == d.n
+        prod2 = 1
+        for r in d.radix2[: d.nst2]:
+            prod2 *= r
+        assert prod2 == d.n2
+        assert (SUB, d.n1, tuple(d.radix[: d.nst])) in subs, ("first pass without a sub-plan", d.id)
+        assert any(f in (SUB, SUB2) and n == d.n2 and rx == tuple(d.radix2[: d.nst2]) for f, n, rx in subs), ("second pass without a sub-plan", d.id)
