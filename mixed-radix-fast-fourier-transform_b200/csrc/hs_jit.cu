@@ -268,8 +268,10 @@ static std::string make_source(int n, int sgn, const int *rx, int nst, const Jit
              "    HsLoadGlobal ld{in + (active ? xf : 0) * PJ::N};\n"
              "    HsStoreSmemNatural<PJ> st{sm};\n"
              "    hs_fft_team<PJ, %d>(ld, st, sm, tw, t, active);\n"
+             "    HsR2CSplitTw<PJ> w2;\n"
+             "    w2.load(tw2, t); // in flight across the barrier\n"
              "    HS_SYNC();\n"
-             "    if (active) hs_r2c_split_rows<PJ>(sm, out + xf * out_stride, tw2, full, t);\n"
+             "    if (active) hs_r2c_split_rows_w<PJ>(sm, out + xf * out_stride, w2, full, t);\n"
              "}\n"
              "extern \"C\" __global__ void __launch_bounds__(PJ::threads, %d)\n"
              "hs_jit_c2r(const cplx *__restrict__ in, cplx *__restrict__ out, const cplx *__restrict__ tw, const cplx *__restrict__ tw2,\n"

@@ -484,23 +484,42 @@ struct HsStoreSmemNatural {
     cplx *sm;
     HS_DEVICE void operator()(int, int, int k, cplx v) const { sm[P::pad(k)] = v; }
 };
-// bins k and H-k (and their mirrors) from the half-length spectrum Z held in sm; pairs k = t, t + T, ... <= H/2
+// bins k and H-k (and their mirrors) from the half-length spectrum Z held in sm; pairs k = t, t + T, ... <= H/2.
+// In two steps, so that the twiddle2 loads are in flight while the CTA waits at the barrier that ends the
+// transform (ncu had 29 % of the r2c kernel's stall samples on these two loads: they were issued after the barrier, at the
+// very end of the CTA, where nothing else can cover them).  w[2 i], w[2 i + 1] = twiddle2[k], twiddle2[H - k], k = t + T i.
 template <class P>
-HS_DEVICE void hs_r2c_split_rows(const cplx *sm, cplx *HS_RESTRICT o, const cplx *HS_RESTRICT tw2, const int full, const int t)
+struct HsR2CSplitTw {
+    static constexpr int ITER = (P::N / 2) / P::T + 1;
+    cplx w[2 * ITER];
+    HS_DEVICE void load(const cplx *HS_RESTRICT tw2, const int t)
+    {
+        HS_UNROLL
+        for (int i = 0; i < ITER; ++i) {
+            const int k = t + P::T * i;
+            if (k <= P::N / 2) { w[2 * i] = hs_ld_tab(tw2 + k); w[2 * i + 1] = hs_ld_tab(tw2 + (P::N - k)); }
+        }
+    }
+};
+template <class P>
+HS_DEVICE void hs_r2c_split_rows_w(const cplx *sm, cplx *HS_RESTRICT o, const HsR2CSplitTw<P> &tw, const int full, const int t)
 {
     constexpr int H = P::N;
-    for (int k = t; k <= H / 2; k += P::T) {
+    HS_UNROLL
+    for (int i = 0; i < HsR2CSplitTw<P>::ITER; ++i) {
+        const int k = t + P::T * i;
+        if (k > H / 2) continue;
         if (k == 0) {
             const cplx z0 = sm[0];
             hs_st_stream(o, hs_c(z0.x + z0.y, 0.0));
             hs_st_stream(o + H, hs_c(z0.x - z0.y, 0.0));
         } else {
             const cplx a = sm[P::pad(k)], c = sm[P::pad(H - k)];
-            const cplx r = hs_r2c_bin(a, c, hs_ld_tab(tw2 + k));
+            const cplx r = hs_r2c_bin(a, c, tw.w[2 * i]);
             hs_st_stream(o + k, r);
             if (full) hs_st_stream(o + (2 * H - k), hs_c(r.x, -r.y));
             if (2 * k != H) {
-                const cplx r2 = hs_r2c_bin(c, a, hs_ld_tab(tw2 + (H - k)));
+                const cplx r2 = hs_r2c_bin(c, a, tw.w[2 * i + 1]);
                 hs_st_stream(o + (H - k), r2);
                 if (full) hs_st_stream(o + (H + k), hs_c(r2.x, -r2.y));
             }
@@ -523,8 +542,10 @@ hs_r2c_smem_kernel(const cplx *HS_RESTRICT in, cplx *HS_RESTRICT out, const cplx
     HsLoadGlobal ld{in + (active ? xf : 0) * P::N};
     HsStoreSmemNatural<P> st{sm};
     hs_fft_team<P, SGN>(ld, st, sm, tw, t, active);
+    HsR2CSplitTw<P> w2;
+    w2.load(tw2, t); // in flight across the barrier
     HS_SYNC();
-    if (active) hs_r2c_split_rows<P>(sm, out + xf * out_stride, tw2, full, t);
+    if (active) hs_r2c_split_rows_w<P>(sm, out + xf * out_stride, w2, full, t);
 }
 
 // the merge from a copy of bins 0..H-1 in the team's own buffer (bin H, needed for k = 0 only, comes from global memory):
