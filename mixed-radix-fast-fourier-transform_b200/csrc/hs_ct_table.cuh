@@ -82,6 +82,10 @@ static void ct_init()
     fill_desc<P4096y>(g_ct[CT_4096Y], CT_4096Y, HS_CT_C2C);
     fill_desc<P3000y>(g_ct[CT_3000Y], CT_3000Y, HS_CT_C2C);
     fill_desc<P3000z>(g_ct[CT_3000Z], CT_3000Z, HS_CT_C2C);
+    fill_desc<P3000t>(g_ct[CT_3000T], CT_3000T, HS_CT_C2C);
+    fill_desc<P3000v>(g_ct[CT_3000V], CT_3000V, HS_CT_C2C);
+    fill_desc<P8192q>(g_ct[CT_8192Q], CT_8192Q, HS_CT_C2C);
+    fill_desc<P8192b>(g_ct[CT_8192B], CT_8192B, HS_CT_C2C);
     fill_desc2<S128, S128>(g_ct[CT_T14], CT_T14);
     fill_desc2<S128, S256>(g_ct[CT_T15], CT_T15);
     fill_desc2<S256, S256>(g_ct[CT_T16], CT_T16);
@@ -134,7 +138,7 @@ extern "C" void hs_cu_launch_ct_c2c(int id, int sgn, const void *d_in, void *d_o
     switch (id) {
     case CT_4096A: launch_c2c_sgn<P4096a, 2>(sgn, d_in, d_out, d_tw, howmany, st); break;
     case CT_4096B: launch_c2c_sgn<P4096b, 2>(sgn, d_in, d_out, d_tw, howmany, st); break;
-    case CT_3000: launch_c2c_sgn<P3000, 2>(sgn, d_in, d_out, d_tw, howmany, st); break;
+    case CT_3000: launch_c2c_sgn<P3000, 3>(sgn, d_in, d_out, d_tw, howmany, st); break;
     case CT_1024: launch_c2c_sgn<P1024, 2>(sgn, d_in, d_out, d_tw, howmany, st); break;
     case CT_2048: launch_c2c_sgn<P2048, 2>(sgn, d_in, d_out, d_tw, howmany, st); break;
     case CT_512: launch_c2c_sgn<P512, 3, 1>(sgn, d_in, d_out, d_tw, howmany, st); break;
@@ -145,6 +149,10 @@ extern "C" void hs_cu_launch_ct_c2c(int id, int sgn, const void *d_in, void *d_o
     case CT_4096Y: launch_c2c_sgn<P4096y, 2>(sgn, d_in, d_out, d_tw, howmany, st); break;
     case CT_3000Y: launch_c2c_sgn<P3000y, 3>(sgn, d_in, d_out, d_tw, howmany, st); break;
     case CT_3000Z: launch_c2c_sgn<P3000z, 3>(sgn, d_in, d_out, d_tw, howmany, st); break;
+    case CT_3000T: launch_c2c_sgn<P3000t, 2>(sgn, d_in, d_out, d_tw, howmany, st); break;
+    case CT_3000V: launch_c2c_sgn<P3000v, 3>(sgn, d_in, d_out, d_tw, howmany, st); break;
+    case CT_8192Q: launch_c2c_sgn<P8192q, 1, 1>(sgn, d_in, d_out, d_tw, howmany, st); break;
+    case CT_8192B: launch_c2c_sgn<P8192b, 1, 1>(sgn, d_in, d_out, d_tw, howmany, st); break;
     default: fprintf(stderr, "Error: unknown compile-time kernel id %d\n", id); exit(EXIT_FAILURE);
     }
 }
@@ -163,7 +171,7 @@ extern "C" void hs_cu_launch_ct_real(int id, int mode, int sgn, const void *d_in
     hs_stream_t st = (hs_stream_t)stream;
     switch (id) {
     case CT_4096A: launch_real_sgn<P4096a, 2>(mode, sgn, d_in, d_out, d_tw, d_tw2, stride, full, howmany, st); break;
-    case CT_3000: launch_real_sgn<P3000, 2>(mode, sgn, d_in, d_out, d_tw, d_tw2, stride, full, howmany, st); break;
+    case CT_3000: launch_real_sgn<P3000, 3>(mode, sgn, d_in, d_out, d_tw, d_tw2, stride, full, howmany, st); break;
     case CT_1024: launch_real_sgn<P1024, 2>(mode, sgn, d_in, d_out, d_tw, d_tw2, stride, full, howmany, st); break;
     case CT_2048: launch_real_sgn<P2048, 2>(mode, sgn, d_in, d_out, d_tw, d_tw2, stride, full, howmany, st); break;
     case CT_512: launch_real_sgn<P512, 3>(mode, sgn, d_in, d_out, d_tw, d_tw2, stride, full, howmany, st); break;

@@ -22,12 +22,22 @@ using P4096b = HsPlan<4096, 512, 1, 3, -1, 0, 8, 8, 8, 8>;
 #ifndef HS_B2048_SPLIT
 #define HS_B2048_SPLIT -2
 #endif
-using P3000  = HsPlan<3000, 200, 1, 3, HS_3000_SPLIT, 221, 3, 5, 5, 5, 8>; // reference factors [8,5,5,5,3] verbatim; passes {3,5}{5,5}{8}
+// N = 3000: reference factors [8,5,5,5,3] verbatim, passes {3,5}{5,5}{8}.  Fewer, fatter threads: 125 threads (4 warps) hold
+// 30 / 25 / 24 points each in the three passes, 158 registers without a spill, THREE CTAs per SM.  With 200 threads (15 / 25 /
+// 16 points) a CTA is allocated 8 warps, so two CTAs per SM cap it at 128 registers and a third at 80 (spills, 59 %).
+// Measured on B200, 65536 transforms (profiles/r2_fat_threads_ab.txt): T = 125 x 3 CTAs 1.110 ms = 86.6 % of the HBM peak,
+// T = 200 x 2 CTAs 1.227 ms = 78.3 %, T = 125 x 4 CTAs (128 registers, 192 B of spills) 1.587 ms.
+using P3000  = HsPlan<3000, 125, 1, 3, HS_3000_SPLIT, 221, 3, 5, 5, 5, 8>;
+using P3000t = HsPlan<3000, 200, 1, 3, HS_3000_SPLIT, 221, 3, 5, 5, 5, 8>; // round 1 / early round 2 (A/B: HSFFT_PREFER_CT)
 using P1024  = HsPlan<1024, 64, 4, 3, -1, 0, 16, 8, 8>;          // reference factors [8,8,8,2]
 using P2048  = HsPlan<2048, 128, 2, 3, -1, 0, 16, 16, 8>;        // reference factors [8,8,8,4]
 using P512   = HsPlan<512, 64, 4, 3, -1, 0, 8, 8, 8>;
 using P256   = HsPlan<256, 16, 16, 4, -1, 0, 16, 16>;
-using P8192  = HsPlan<8192, 512, 1, 4, -1, 0, 8, 8, 8, 16>;
+// N = 8192 in THREE passes (two shared-memory exchanges instead of three): 256 threads of 32 points, the first pass a fused
+// {4,8}; 230 registers, no spill, one CTA per SM either way (139 KB).  Measured: 1.820 ms per 32768 transforms = 72.1 % of the
+// HBM peak against 2.026 ms = 64.8 % for 512 threads in four passes 8.8.8.16 (P8192q); {16}{16}{8,4} the same (1.822 ms).
+using P8192  = HsPlan<8192, 256, 1, 4, -1, 211, 4, 8, 16, 16>;
+using P8192q = HsPlan<8192, 512, 1, 4, -1, 0, 8, 8, 8, 16>;
 // (8192 points with 1024 threads -- 8 points per thread, five passes, 64 registers, twice the warps -- measured slower: 56 % and
 // 53 % of the HBM peak for 4.8.8.8.4 / 8.8.8.8.2 against 65 %; N = 3000 at three CTAs per SM spills and drops from 78 % to 59 %)
 // fused Bluestein, M = 2048 (N = 513..1024, e.g. the N = 1009 config): forward / inverse pair
@@ -102,6 +112,8 @@ using P3000x = HsPlan<3000, 200, 1, 3, -1, 0, 3, 5, 5, 5, 8>;
 using P4096y = HsPlan<4096, 256, 1, 4, -2, 0, 16, 16, 16>;
 using P3000y = HsPlan<3000, 200, 1, 3, 0, 0, 3, 5, 5, 5, 8>;       // one stage per pass, load-all twiddles (round-1 first contact)
 using P3000z = HsPlan<3000, 200, 1, 3, -1, 2111, 3, 5, 5, 5, 8>;  // passes {3,5} {5} {5} {8}
+using P3000v = HsPlan<3000, 125, 1, 3, -1, 221, 3, 5, 5, 5, 8>;    // the default plan with rows 1,2,4,8 of the stage twiddles loaded
+using P8192b = HsPlan<8192, 256, 1, 5, -1, 112, 16, 16, 8, 4>;    // the fused 32-point pass last instead of first
 
 // inverse-order partners of the sub-plans (first radix = the forward plan's last radix)
 using S128i  = HsPlan<128, 8, 1, 4, HS_SUB_SPLIT, 0, 16, 8>;
@@ -138,4 +150,4 @@ enum { CT_4096A = 0, CT_4096B, CT_3000, CT_1024, CT_2048, CT_512, CT_256, CT_819
        CT_TX20480, CT_TX40960, CT_TX81920, CT_TX163840, CT_S160X,
        CT_B256, CT_B512, CT_B1024, CT_B4096, CT_B8192,
        CT_R1008, CT_R1008A, CT_R1008G, CT_R256, CT_B2048X2, CT_B256X16,
-       CT_H4096, CT_H8192, CT_C10240, CT_C8192, CT_S512B, CT_COUNT };
+       CT_H4096, CT_H8192, CT_C10240, CT_C8192, CT_S512B, CT_3000T, CT_3000V, CT_8192Q, CT_8192B, CT_COUNT };
