@@ -146,6 +146,7 @@ static double conflict_ratio(int N, int T, int logpad, const std::vector<int> &p
 
 struct JitChoice {
     int T, X, logpad, groups, minb, npass;
+    bool fat;
     std::vector<int> pass_radix;
 };
 
@@ -155,7 +156,7 @@ static int env_or(const char *name, int dflt)
     return e ? atoi(e) : dflt;
 }
 
-static bool choose(int n, const int *rx, int nst, JitChoice &c)
+static bool choose(int n, const int *rx, int nst, JitChoice &c, bool allow_fat = true)
 {
     if (nst < 2 || nst > 8 || n > 8192 || n < 16) return false;
     for (int s = 0; s < nst; ++s) {
@@ -191,6 +192,55 @@ static bool choose(int n, const int *rx, int nst, JitChoice &c)
     if (((c.T + 31) / 32 * 32) * (pts <= 10 ? 80 : 128) > 65536 && maxpp <= 8) { c.T = (c.T + 1) / 2; pts *= 2; }
     while (pts * 2 <= 10 && c.T > 128) { c.T = (c.T + 1) / 2; pts *= 2; } // radix 2..5 only: too little work per thread otherwise
     if (env_or("HSFFT_JIT_T", 0) > 0) { c.T = env_or("HSFFT_JIT_T", 0); pts = maxpp * ((n / maxpp + c.T - 1) / c.T); }
+    // Fewer, fatter threads for the longer lengths (n >= 1536): pairs fused up to 25 points, and a team so small that a thread
+    // carries 16-32 points per pass -- 8-10 warps with that much independent work keep an SM busier than 16-24 warps of 5-10
+    // points, and the smaller lengths fit three CTAs per SM at 168 registers.  Among the team sizes T = ceil(NB_p / k) (NB_p:
+    // butterflies of pass p) with n/26 <= T <= n/15 and at most 32 points per thread, take the one for which the passes with
+    // exactly NB_p = k T (no guard on their loads and stores) carry the most points; none exact -> the rule above stays.
+    // Measured on B200 (profiles/r2_plan_time_fat_threads.txt), % of the HBM peak, rule above -> this one: N = 2000 72.8 -> 79.0,
+    // 2400 64.6 -> 86.3, 3125 54.0 -> 88.4, 4000 51.2 -> 63.3, 4500 52.2 -> 70.6, 5000 43.4 -> 69.6, 5120 51.7 -> 69.9,
+    // 6000 44.5 -> 63.9, 6250 56.5 -> 70.8, 6400 47.5 -> 56.8; N = 1000 (82 %), 1536 (95.7 %, 85.7 with this rule) and 6561 (65 %) keep the rule above.
+    bool fat = false;
+    if (allow_fat && n >= 1800 && !getenv("HSFFT_JIT_T") && !getenv("HSFFT_JIT_FUSE") && env_or("HSFFT_JIT_FAT", 1) != 0) {
+        std::vector<int> pr;
+        int groups = 0;
+        for (int s = 0; s < nst;) {
+            int pp = rx[s], sz = 1;
+            if (s + 1 < nst && rx[s] * rx[s + 1] <= 25) { pp = rx[s] * rx[s + 1]; sz = 2; }
+            pr.push_back(pp);
+            groups = groups * 10 + sz;
+            s += sz;
+        }
+        int bestT = 0, bestW = 0, bestPts = 0;
+        if (pr.size() >= 2)
+            for (size_t p = 0; p < pr.size(); ++p)
+                for (int k = 1; k <= 8; ++k) {
+                    const int T = (n / pr[p] + k - 1) / k;
+                    if (T * 26 < n || T * 15 > n || T > 1024) continue;
+                    int mp = 0, w = 0;
+                    for (size_t q = 0; q < pr.size(); ++q) {
+                        const int nb = n / pr[q], b = (nb + T - 1) / T;
+                        mp = pr[q] * b > mp ? pr[q] * b : mp;
+                        if (nb % T == 0) w += pr[q];
+                    }
+                    if (mp > 32 || w == 0) continue;
+                    // CTAs per SM at 168 registers (registers come in units of four warps) and n + n/8 points of shared memory:
+                    // three of them (T <= 128) beat one (N = 2400, 3000, 3125: 86-88 % against 63-70 % for N = 4000 ... 6250)
+                    const int by_regs = 65536 / ((T + 127) / 128 * 128 * 168), by_smem = 227 * 1024 / ((n + n / 8 + 1) * 16 + 1024);
+                    const int ctas = by_regs < by_smem ? by_regs : by_smem;
+                    if (ctas < 1 || ctas * ((T + 31) / 32) < 7) continue; // fewer than 7 warps per SM: too little to hide anything
+                    w += ctas >= 3 ? 1000 : 0;
+                    if (w > bestW || (w == bestW && T < bestT)) { bestW = w; bestT = T; bestPts = mp; }
+                }
+        if (bestW > 0) {
+            fat = true;
+            c.pass_radix = pr;
+            c.groups = groups;
+            c.npass = (int)pr.size();
+            c.T = bestT;
+            pts = bestPts;
+        }
+    }
     if (c.T < 1 || c.T > 1024) return false;
     int best = 0;
     double best_ratio = 1e30;
@@ -204,7 +254,7 @@ static bool choose(int n, const int *rx, int nst, JitChoice &c)
     const int npad = best ? n + (n >> best) + 1 : n;
     // Small CTAs, many of them: independent CTAs are in different phases (load / exchange / arithmetic), which is what keeps
     // the SM's pipes busy at once (measured: N=1000 68 % of the HBM peak with 2 x 125 threads x 3 CTAs, 81 % with 125 x 6).
-    int X = env_or("HSFFT_JIT_THREADS", 128) / c.T;
+    int X = fat ? 1 : env_or("HSFFT_JIT_THREADS", 128) / c.T;
     if (env_or("HSFFT_JIT_X", 0) > 0) X = env_or("HSFFT_JIT_X", 0);
     if (X < 1) X = 1;
     while (X > 1 && (long long)X * npad * 16 > 100 * 1024) --X;
@@ -212,7 +262,10 @@ static bool choose(int n, const int *rx, int nst, JitChoice &c)
     c.X = X;
     const int threads = c.T * X, smem = X * npad * 16;
     // CTAs per SM: as many as the registers (see above), shared memory and 2048 threads allow, at most 8
-    const int regs = pts <= 10 ? 80 : 128, warps32 = (threads + 31) / 32 * 32;
+    // (a CTA is allocated registers for a multiple of four warps: 200 threads count as 256; up to 20 points per thread run in
+    // 128 registers -- N = 3600 at 240 threads of 18 points: two CTAs per SM 71.8 %, one 66.0 %)
+    const int regs = fat ? (pts <= 20 ? 128 : 168) : pts <= 10 ? 80 : 128, warps32 = fat ? (threads + 127) / 128 * 128 : (threads + 31) / 32 * 32;
+    c.fat = fat;
     if ((long long)warps32 * regs > 65536) return false;
     int minb = (int)(65536 / ((long long)warps32 * regs));
     if (minb > 8) minb = 8;
@@ -228,12 +281,13 @@ struct JitPlan {
     CUmodule mod;
     CUfunction fn, fn_r2c, fn_c2r, fn_staged;
     int threads, smem, X, minb, smem_staged;
+    int threads_c2r, smem_c2r, X_c2r; // hs_jit_c2r may run on its own plan
     std::string text;
 };
 static std::mutex g_mu;
 static std::vector<JitPlan *> g_plans;
 
-static std::string make_source(int n, int sgn, const int *rx, int nst, const JitChoice &c)
+static std::string make_source(int n, int sgn, const int *rx, int nst, const JitChoice &c, const JitChoice &cr)
 {
     char buf[8192];
     std::string rad;
@@ -245,6 +299,7 @@ static std::string make_source(int n, int sgn, const int *rx, int nst, const Jit
     snprintf(buf, sizeof buf,
              "#include \"hs_smem_fft.cuh\"\n"
              "using PJ = HsPlan<%d, %d, %d, %d, -2, %d%s>;\n"
+             "using PR = HsPlan<%d, %d, %d, %d, -2, %d%s>; // the plan of hs_jit_c2r (see hs_cu_jit_c2c_create)\n"
              "extern \"C\" __global__ void __launch_bounds__(PJ::threads, %d)\n"
              "hs_jit_c2c(const cplx *__restrict__ in, cplx *__restrict__ out, const cplx *__restrict__ tw, long long howmany, int pf_dist)\n"
              "{\n"
@@ -273,30 +328,30 @@ static std::string make_source(int n, int sgn, const int *rx, int nst, const Jit
              "    HS_SYNC();\n"
              "    if (active) hs_r2c_split_rows_w<PJ>(sm, out + xf * out_stride, w2, full, t);\n"
              "}\n"
-             "extern \"C\" __global__ void __launch_bounds__(PJ::threads, %d)\n"
+             "extern \"C\" __global__ void __launch_bounds__(PR::threads, %d)\n"
              "hs_jit_c2r(const cplx *__restrict__ in, cplx *__restrict__ out, const cplx *__restrict__ tw, const cplx *__restrict__ tw2,\n"
              "           long long in_stride, long long howmany)\n"
              "{\n"
              "    HS_DYN_SMEM(cplx, smem);\n"
-             "    const int team = HS_TID / PJ::T, t = HS_TID %% PJ::T;\n"
-             "    const long long xf = HS_BID * PJ::X + team;\n"
+             "    const int team = HS_TID / PR::T, t = HS_TID %% PR::T;\n"
+             "    const long long xf = HS_BID * PR::X + team;\n"
              "    const bool active = xf < howmany;\n"
-             "    HsStoreGlobal st{out + (active ? xf : 0) * PJ::N};\n"
+             "    HsStoreGlobal st{out + (active ? xf : 0) * PR::N};\n"
              "    if (%d) { // merge from a copy of the row staged in the team's buffer (see hs_c2r_smem_kernel)\n"
-             "        cplx *sm = smem + team * PJ::NPAD;\n"
+             "        cplx *sm = smem + team * PR::NPAD;\n"
              "        const cplx *x = in + (active ? xf : 0) * in_stride;\n"
              "        if (active)\n"
-             "            for (int k = t; k < PJ::N; k += PJ::T) hs_cp_async16(sm + k, x + k);\n"
+             "            for (int k = t; k < PR::N; k += PR::T) hs_cp_async16(sm + k, x + k);\n"
              "        hs_cp_async_wait_all();\n"
              "        HS_SYNC();\n"
-             "        HsLoadC2RMergeSmem ld{sm, x + PJ::N, tw2, PJ::N};\n"
-             "        hs_fft_team<PJ, %d>(ld, st, sm, tw, t, active);\n"
+             "        HsLoadC2RMergeSmem ld{sm, x + PR::N, tw2, PR::N};\n"
+             "        hs_fft_team<PR, %d>(ld, st, sm, tw, t, active);\n"
              "    } else {\n"
-             "        HsLoadC2RMerge ld{in + (active ? xf : 0) * in_stride, tw2, PJ::N};\n"
-             "        hs_fft_team<PJ, %d>(ld, st, smem + team * PJ::NPAD, tw, t, active);\n"
+             "        HsLoadC2RMerge ld{in + (active ? xf : 0) * in_stride, tw2, PR::N};\n"
+             "        hs_fft_team<PR, %d>(ld, st, smem + team * PR::NPAD, tw, t, active);\n"
              "    }\n"
              "}\n",
-             n, c.T, c.X, c.logpad, c.groups, rad.c_str(), c.minb, sgn, c.minb, sgn, c.minb,
+             n, c.T, c.X, c.logpad, c.groups, rad.c_str(), n, cr.T, cr.X, cr.logpad, cr.groups, rad.c_str(), c.minb, sgn, c.minb, sgn, cr.minb,
              env_or("HSFFT_C2R_STAGE", 1) == 2 ? 1 : 0, sgn, sgn); // plan-time kernels: the staged merge measured 2-6 % slower (N = 2000, 2002, 4000, 4374)
     std::string src(buf);
     if (c.X == 1 && c.npass > 1) { // persistent twin with the next input staged by the copy engine (see HsStageRefill)
@@ -339,9 +394,11 @@ static bool jit_enabled()
 // the generated translation unit for (n, sgn, radices in execution order), without compiling it (tests; returns its length or 0)
 extern "C" int hs_cu_jit_source(int n, int sgn, const int *rx, int nst, char *out, int cap)
 {
-    JitChoice c;
+    JitChoice c, cr;
     if (!choose(n, rx, nst, c)) return 0;
-    const std::string s = make_source(n, sgn, rx, nst, c);
+    cr = c;
+    if (c.fat && c.minb == 1 && !choose(n, rx, nst, cr, false)) cr = c;
+    const std::string s = make_source(n, sgn, rx, nst, c, cr);
     if ((int)s.size() + 1 > cap) return 0;
     memcpy(out, s.c_str(), s.size() + 1);
     return (int)s.size();
@@ -356,12 +413,16 @@ extern "C" int hs_cu_jit_c2c_create(int n, int sgn, const int *rx, int nst, hs_c
     if (cudaGetDevice(&dev) != cudaSuccess) return -1;
     for (size_t i = 0; i < g_plans.size(); ++i)
         if (g_plans[i]->n == n && g_plans[i]->sgn == sgn && g_plans[i]->dev == dev) { *desc = g_plans[i]->desc; return (int)i; }
-    JitChoice c;
+    // The c2r kernel has no persistent twin to make up for a single small CTA per SM, so where the fat-thread rule ends at one
+    // CTA per SM it keeps the thin-thread plan (c2r N = 10000: 35.6 % of the HBM peak against 21.3 %; r2c gains either way)
+    JitChoice c, cr;
     if (!choose(n, rx, nst, c)) return -1;
+    cr = c;
+    if (c.fat && c.minb == 1 && !choose(n, rx, nst, cr, false)) cr = c;
     Nvrtc *rt = nvrtc();
     Driver *drv = driver();
     if (!rt || !drv) return -1;
-    const std::string src = make_source(n, sgn, rx, nst, c);
+    const std::string src = make_source(n, sgn, rx, nst, c, cr);
     nvrtcProgram prog = nullptr;
     if (rt->CreateProgram(&prog, src.c_str(), "hs_jit_plan.cu", hs_jit_src_count, hs_jit_src_texts, hs_jit_src_names) != 0) return -1;
     const char *opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-default-device", "-DHS_JIT=1"};
@@ -391,15 +452,18 @@ extern "C" int hs_cu_jit_c2c_create(int n, int sgn, const int *rx, int nst, hs_c
     }
     const int npad = c.logpad ? n + (n >> c.logpad) + 1 : n;
     p->threads = c.T * c.X; p->X = c.X; p->smem = c.X * npad * 16; p->minb = c.minb;
+    const int npad_r = cr.logpad ? n + (n >> cr.logpad) + 1 : n;
+    p->threads_c2r = cr.T * cr.X; p->X_c2r = cr.X; p->smem_c2r = cr.X * npad_r * 16;
     drv->FuncSetAttribute(p->fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, p->smem);
     int pct = (int)(((long long)(p->smem + 1024) * c.minb * 100 + 228 * 1024 - 1) / (228 * 1024));
     drv->FuncSetAttribute(p->fn, CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT, pct > 100 ? 100 : pct);
     p->fn_r2c = p->fn_c2r = nullptr;
     if (drv->ModuleGetFunction(&p->fn_r2c, p->mod, "hs_jit_r2c") == CUDA_SUCCESS && drv->ModuleGetFunction(&p->fn_c2r, p->mod, "hs_jit_c2r") == CUDA_SUCCESS) {
-        for (CUfunction f : {p->fn_r2c, p->fn_c2r}) {
-            drv->FuncSetAttribute(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, p->smem);
-            drv->FuncSetAttribute(f, CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT, pct > 100 ? 100 : pct);
-        }
+        drv->FuncSetAttribute(p->fn_r2c, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, p->smem);
+        drv->FuncSetAttribute(p->fn_r2c, CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT, pct > 100 ? 100 : pct);
+        const int pctr = (int)(((long long)(p->smem_c2r + 1024) * cr.minb * 100 + 228 * 1024 - 1) / (228 * 1024));
+        drv->FuncSetAttribute(p->fn_c2r, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, p->smem_c2r);
+        drv->FuncSetAttribute(p->fn_c2r, CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT, pctr > 100 ? 100 : pctr);
     } else p->fn_r2c = p->fn_c2r = nullptr;
     // HSFFT_JIT_STAGED: 0 never, 1 plans that run one CTA per SM, 2 (default) also two CTAs per SM where both buffers fit -- each
     // measured against the one-shot kernel when the plan is made; 3 always (no measurement)
@@ -507,7 +571,8 @@ extern "C" void hs_cu_jit_real_launch(int handle, int mode, const void *d_in, vo
         p = g_plans[handle];
     }
     if (!p->fn_r2c) { fprintf(stderr, "Error: the plan-time kernel for N=%d has no real-transform entry points\n", p->n); exit(EXIT_FAILURE); }
-    const long long blocks = (howmany + p->X - 1) / p->X;
+    const int X = mode == 1 ? p->X : p->X_c2r;
+    const long long blocks = (howmany + X - 1) / X;
     if (blocks <= 0 || blocks > 2147483647LL) { fprintf(stderr, "Error: batch too large for one launch (%lld CTAs)\n", blocks); exit(EXIT_FAILURE); }
     CUresult r;
     if (mode == 1) {
@@ -515,7 +580,7 @@ extern "C" void hs_cu_jit_real_launch(int handle, int mode, const void *d_in, vo
         r = driver()->LaunchKernel(p->fn_r2c, (unsigned)blocks, 1, 1, (unsigned)p->threads, 1, 1, (unsigned)p->smem, (CUstream)stream, args, nullptr);
     } else {
         void *args[] = {(void *)&d_in, (void *)&d_out, (void *)&d_tw, (void *)&d_tw2, (void *)&stride, (void *)&howmany};
-        r = driver()->LaunchKernel(p->fn_c2r, (unsigned)blocks, 1, 1, (unsigned)p->threads, 1, 1, (unsigned)p->smem, (CUstream)stream, args, nullptr);
+        r = driver()->LaunchKernel(p->fn_c2r, (unsigned)blocks, 1, 1, (unsigned)p->threads_c2r, 1, 1, (unsigned)p->smem_c2r, (CUstream)stream, args, nullptr);
     }
     if (r != CUDA_SUCCESS) { fprintf(stderr, "Error: CUDA failure %d launching the plan-time real kernel for N=%d\n", (int)r, 2 * p->n); exit(EXIT_FAILURE); }
     hs_cu_count_launch();

@@ -85,7 +85,7 @@ def test_generic_engine_matches_compile_time_kernels(hs, product_lib, oracle, n)
     assert per_transform_worst(y, oracle.c2c(x, 1)) <= tol(n)
 
 
-JIT_SIZES = [24, 96, 360, 640, 1000, 1001, 1144, 1536, 2000, 2002, 2187, 2401, 3072, 3125, 5632, 5000, 6000, 6561, 7000, 8000]
+JIT_SIZES = [24, 96, 360, 640, 1000, 1001, 1144, 1536, 2000, 2002, 2187, 2400, 2401, 2560, 3072, 3125, 3600, 4500, 5120, 5632, 5000, 6000, 6250, 6561, 6912, 7000, 8000]
 
 
 @pytest.mark.parametrize("n", JIT_SIZES)
@@ -101,7 +101,7 @@ def test_plan_time_compiled_kernels(hs, product_lib, oracle, n):
         assert per_transform_worst(y, oracle.c2c(x, sgn)) <= min(tol(n), 2e-15 * math.log2(n) * 4), (n, sgn, desc)
 
 
-@pytest.mark.parametrize("n", [2400, 4500, 6250, 6561])
+@pytest.mark.parametrize("n", [4000, 4500, 6250, 6561])   # (N = 2400 runs three CTAs per SM since the fat-thread rule: no persistent twin)
 def test_plan_time_kernels_persistent_staged_form(hs, product_lib, oracle, n, monkeypatch):
     """Batches of a few waves and more run the plan-time kernel as persistent CTAs whose next input is staged by the copy
     engine (csrc/hs_smem_fft.cuh HsStageRefill; HSFFT_JIT_STAGED=3 takes that form without the plan-time measurement):
@@ -165,7 +165,7 @@ def test_linearity_and_parseval_full_batch(hs, product_lib):
         assert float(rt) < 1e-12 * math.log2(n)
 
 
-@pytest.mark.parametrize("n", [4, 8, 16, 32, 64, 2018, 4096, 8192, 1 << 15, 1 << 20])
+@pytest.mark.parametrize("n", [4, 8, 16, 32, 64, 2018, 4096, 4800, 6000, 8192, 10000, 16384, 1 << 15, 1 << 20])   # 4800 / 10000: plan-time kernels (at 10000 the c2r kernel runs on its own plan)
 def test_real_r2c_c2r(hs, product_lib, oracle, n):
     x = xorshift_uniform(3 * n, seed=n).reshape(3, n)
     with hs.RealPlan(n, 1) as f, hs.RealPlan(n, -1) as g:
@@ -175,8 +175,10 @@ def test_real_r2c_c2r(hs, product_lib, oracle, n):
         # Hermitian mirror written in full (reference src/real.c:128-132)
         assert np.array_equal(X[:, n - 1: n // 2: -1], np.conj(X[:, 1: n // 2]))
         y = g.c2r(X)
-        assert per_transform_worst(y, oracle.c2r(Xr, n)) <= tol(n)
-        assert rel_rms(y / n, x) <= tol(n)
+        yr = oracle.c2r(Xr, n)
+        assert per_transform_worst(y, yr) <= tol(n)
+        # round trip: as good as the reference's own (its 11-digit radix-3/5 constants put N = 4800, 6000, 10000 above tol(n))
+        assert rel_rms(y / n, x) <= max(tol(n), 1.05 * rel_rms(yr / n, x))
 
 
 @pytest.mark.parametrize("la,lb", [(5, 3), (100, 37), (512, 512), (1000, 24), (4096, 4096), (20001, 12999), (300000, 200001), (524288, 524288)])
@@ -491,7 +493,7 @@ def test_cuda_path_against_the_committed_reference_outputs(hs, product_lib):
 # ------------------------------------------------------------------------------------------------------------------
 # Additive layouts, called directly: half spectrum with a row stride, strided c2r input.
 
-@pytest.mark.parametrize("n", [64, 2018, 4096, 6000, 1 << 15, 1 << 17, 1 << 20])
+@pytest.mark.parametrize("n", [64, 2018, 4096, 6000, 10000, 1 << 15, 1 << 17, 1 << 20])
 def test_half_spectrum_and_row_strides_direct(hs, product_lib, oracle, n):
     import torch
     b = 3
