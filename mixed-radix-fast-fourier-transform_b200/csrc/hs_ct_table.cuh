@@ -84,6 +84,7 @@ static void ct_init()
     fill_desc<P3000z>(g_ct[CT_3000Z], CT_3000Z, HS_CT_C2C);
     fill_desc<P3000t>(g_ct[CT_3000T], CT_3000T, HS_CT_C2C);
     fill_desc<P3000v>(g_ct[CT_3000V], CT_3000V, HS_CT_C2C);
+    fill_desc<P3000u>(g_ct[CT_3000U], CT_3000U, HS_CT_C2C);
     fill_desc<P8192q>(g_ct[CT_8192Q], CT_8192Q, HS_CT_C2C);
     fill_desc<P8192b>(g_ct[CT_8192B], CT_8192B, HS_CT_C2C);
     fill_desc2<S128, S128>(g_ct[CT_T14], CT_T14);
@@ -151,6 +152,7 @@ extern "C" void hs_cu_launch_ct_c2c(int id, int sgn, const void *d_in, void *d_o
     case CT_3000Z: launch_c2c_sgn<P3000z, 3>(sgn, d_in, d_out, d_tw, howmany, st); break;
     case CT_3000T: launch_c2c_sgn<P3000t, 2>(sgn, d_in, d_out, d_tw, howmany, st); break;
     case CT_3000V: launch_c2c_sgn<P3000v, 3>(sgn, d_in, d_out, d_tw, howmany, st); break;
+    case CT_3000U: launch_c2c_sgn<P3000u, 3>(sgn, d_in, d_out, d_tw, howmany, st); break;
     case CT_8192Q: launch_c2c_sgn<P8192q, 1, 1>(sgn, d_in, d_out, d_tw, howmany, st); break;
     case CT_8192B: launch_c2c_sgn<P8192b, 1, 1>(sgn, d_in, d_out, d_tw, howmany, st); break;
     default: fprintf(stderr, "Error: unknown compile-time kernel id %d\n", id); exit(EXIT_FAILURE);
@@ -171,7 +173,7 @@ extern "C" void hs_cu_launch_ct_real(int id, int mode, int sgn, const void *d_in
     hs_stream_t st = (hs_stream_t)stream;
     switch (id) {
     case CT_4096A: launch_real_sgn<P4096a, 2>(mode, sgn, d_in, d_out, d_tw, d_tw2, stride, full, howmany, st); break;
-    case CT_3000: // c2r keeps the 200-thread plan (same stages, same tables): N = 6000 59.1 % of the HBM peak against 53.9 %; r2c 74.8 -> 81.0 % at 125
+    case CT_3000: // c2r keeps the 200-thread plan (same stages, same tables): N = 6000 59.1 % of the HBM peak against 53.9 % at 125 threads; r2c 74.8 -> 81.0 %
         if (mode == 1) launch_real_sgn<P3000, 3>(mode, sgn, d_in, d_out, d_tw, d_tw2, stride, full, howmany, st);
         else launch_real_sgn<P3000t, 2>(mode, sgn, d_in, d_out, d_tw, d_tw2, stride, full, howmany, st);
         break;

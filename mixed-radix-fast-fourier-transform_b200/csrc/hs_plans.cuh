@@ -22,12 +22,14 @@ using P4096b = HsPlan<4096, 512, 1, 3, -1, 0, 8, 8, 8, 8>;
 #ifndef HS_B2048_SPLIT
 #define HS_B2048_SPLIT -2
 #endif
-// N = 3000: reference factors [8,5,5,5,3] verbatim, passes {3,5}{5,5}{8}.  Fewer, fatter threads: 125 threads (4 warps) hold
-// 30 / 25 / 24 points each in the three passes, 158 registers without a spill, THREE CTAs per SM.  With 200 threads (15 / 25 /
+// N = 3000: reference factors [8,5,5,5,3] verbatim, passes {3,5}{5,5}{8}.  Fewer, fatter threads: 128 threads (4 whole warps)
+// hold 30 / 25 / 24 points each in the three passes, 158 registers without a spill, THREE CTAs per SM.  With 200 threads (15 / 25 /
 // 16 points) a CTA is allocated 8 warps, so two CTAs per SM cap it at 128 registers and a third at 80 (spills, 59 %).
-// Measured on B200, 65536 transforms (profiles/r2_fat_threads_ab.txt): T = 125 x 3 CTAs 1.110 ms = 86.6 % of the HBM peak,
-// T = 200 x 2 CTAs 1.227 ms = 78.3 %, T = 125 x 4 CTAs (128 registers, 192 B of spills) 1.587 ms.
-using P3000  = HsPlan<3000, 125, 1, 3, HS_3000_SPLIT, 221, 3, 5, 5, 5, 8>;
+// Measured on B200, 65536 transforms (profiles/r2_fat_threads_ab.txt): T = 128 x 3 CTAs 1.092 ms = 88.1 % of the HBM peak; T = 125
+// (the radix-8 pass in exactly three rounds, but the second round of a pass starts at butterfly 125: its 8-lane groups straddle
+// two 128-byte lines, 16 % more shared-memory wavefronts) 1.108 ms = 86.7 %; T = 120 (25-point pass exact) 1.134 ms; T = 200 x 2
+// CTAs 1.227 ms = 78.3 %; T = 125 x 4 CTAs (128 registers, 192 B of spills) 1.587 ms.
+using P3000  = HsPlan<3000, 128, 1, 3, HS_3000_SPLIT, 221, 3, 5, 5, 5, 8>;
 using P3000t = HsPlan<3000, 200, 1, 3, HS_3000_SPLIT, 221, 3, 5, 5, 5, 8>; // round 1 / early round 2 (A/B: HSFFT_PREFER_CT)
 using P1024  = HsPlan<1024, 64, 4, 3, -1, 0, 16, 8, 8>;          // reference factors [8,8,8,2]
 using P2048  = HsPlan<2048, 128, 2, 3, -1, 0, 16, 16, 8>;        // reference factors [8,8,8,4]
@@ -112,7 +114,8 @@ using P3000x = HsPlan<3000, 200, 1, 3, -1, 0, 3, 5, 5, 5, 8>;
 using P4096y = HsPlan<4096, 256, 1, 4, -2, 0, 16, 16, 16>;
 using P3000y = HsPlan<3000, 200, 1, 3, 0, 0, 3, 5, 5, 5, 8>;       // one stage per pass, load-all twiddles (round-1 first contact)
 using P3000z = HsPlan<3000, 200, 1, 3, -1, 2111, 3, 5, 5, 5, 8>;  // passes {3,5} {5} {5} {8}
-using P3000v = HsPlan<3000, 125, 1, 3, -1, 221, 3, 5, 5, 5, 8>;    // the default plan with rows 1,2,4,8 of the stage twiddles loaded
+using P3000v = HsPlan<3000, 125, 1, 3, HS_3000_SPLIT, 221, 3, 5, 5, 5, 8>; // 125 threads: the radix-8 pass exact, rounds not 8-aligned
+using P3000u = HsPlan<3000, 120, 1, 3, HS_3000_SPLIT, 221, 3, 5, 5, 5, 8>; // the 25-point pass exact (120 butterflies), the radix-8 pass in four rounds
 using P8192b = HsPlan<8192, 256, 1, 5, -1, 112, 16, 16, 8, 4>;    // the fused 32-point pass last instead of first
 
 // inverse-order partners of the sub-plans (first radix = the forward plan's last radix)
@@ -150,4 +153,4 @@ enum { CT_4096A = 0, CT_4096B, CT_3000, CT_1024, CT_2048, CT_512, CT_256, CT_819
        CT_TX20480, CT_TX40960, CT_TX81920, CT_TX163840, CT_S160X,
        CT_B256, CT_B512, CT_B1024, CT_B4096, CT_B8192,
        CT_R1008, CT_R1008A, CT_R1008G, CT_R256, CT_B2048X2, CT_B256X16,
-       CT_H4096, CT_H8192, CT_C10240, CT_C8192, CT_S512B, CT_3000T, CT_3000V, CT_8192Q, CT_8192B, CT_COUNT };
+       CT_H4096, CT_H8192, CT_C10240, CT_C8192, CT_S512B, CT_3000T, CT_3000V, CT_8192Q, CT_8192B, CT_3000U, CT_COUNT };
