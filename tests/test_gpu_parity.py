@@ -85,7 +85,7 @@ def test_generic_engine_matches_compile_time_kernels(hs, product_lib, oracle, n)
     assert per_transform_worst(y, oracle.c2c(x, 1)) <= tol(n)
 
 
-JIT_SIZES = [24, 96, 360, 640, 1000, 1001, 1144, 1536, 2000, 2002, 2187, 2400, 2401, 2560, 3072, 3125, 3600, 4500, 5120, 5632, 5000, 6000, 6250, 6561, 6912, 7000, 8000]
+JIT_SIZES = [24, 96, 360, 640, 1000, 1001, 1144, 1536, 1800, 2000, 2002, 2187, 2400, 2401, 2560, 3072, 3125, 3600, 4500, 5120, 5632, 5000, 6000, 6250, 6561, 6912, 7000, 8000]
 
 
 @pytest.mark.parametrize("n", JIT_SIZES)
