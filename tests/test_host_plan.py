@@ -180,6 +180,44 @@ def test_plan_time_kernel_source_is_generated_and_compiles_with_nvrtc(hs, produc
     assert rt.nvrtcCompileProgram(prog2, 4, opts) == 0
 
 
+def test_plan_time_planner_fat_thread_rule(hs, product_lib, monkeypatch):
+    """csrc/hs_jit.cu choose(): lengths from 1800 up get fewer, fatter threads (pairs fused up to 25 points, 16-32 points per
+    thread, three CTAs per SM where they fit, whole warps where a warp would idle); the c2r kernel keeps the thin plan where
+    the fat one runs one CTA per SM; shorter lengths and HSFFT_JIT_FAT=0 keep one butterfly of the widest pass per thread."""
+    import ctypes as C
+    import re
+    L = product_lib
+    L.hs_cu_jit_source.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int, C.c_char_p, C.c_int]
+    L.hs_cu_jit_source.restype = C.c_int
+
+    def plans(n, rx):
+        buf = C.create_string_buffer(32768)
+        assert L.hs_cu_jit_source(n, 1, (C.c_int * len(rx))(*rx), len(rx), buf, 32768) > 0
+        src = buf.value.decode()
+        pj = re.search(r"using PJ = HsPlan<([^>]*)>", src).group(1)
+        pr = re.search(r"using PR = HsPlan<([^>]*)>", src).group(1)
+        minb = int(re.search(r"__launch_bounds__\(PJ::threads, (\d+)\)\s*hs_jit_c2c\(", src).group(1))
+        return pj, pr, minb
+
+    # (length, stage radices in execution order) -> threads, pass grouping, CTAs per SM
+    pj, pr, minb = plans(5000, [5, 5, 5, 5, 8])
+    assert pj.startswith("5000, 200, 1,") and ", 221, 5, 5, 5, 5, 8" in pj and minb == 1
+    assert pr.startswith("5000, 625, 1,") and ", 11111, " in pr              # c2r: the thin plan (no persistent twin)
+    pj, pr, minb = plans(3125, [5, 5, 5, 5, 5])
+    assert pj.startswith("3125, 125, 1,") and ", 221, " in pj and minb == 3 and pr == pj   # every pass exact: stays at 125
+    pj, pr, minb = plans(2400, [3, 4, 5, 5, 8])
+    assert pj.startswith("2400, 128, 1,") and ", 221, " in pj and minb == 3 and pr == pj   # 100 -> whole warps
+    pj, pr, minb = plans(3600, [2, 3, 3, 5, 5, 8])
+    assert pj.startswith("3600, 240, 1,") and minb == 2                       # <= 20 points per thread: 128 registers, two CTAs
+    pj, pr, minb = plans(1536, [3, 8, 8, 8])
+    assert pj.startswith("1536, 192, 1,") and ", 1111, " in pj                # below the threshold: thin threads
+    pj, pr, minb = plans(6561, [3] * 8)
+    assert pj.startswith("6561, 729, 1,")                                     # no team size with an exact pass in range: rule above
+    monkeypatch.setenv("HSFFT_JIT_FAT", "0")
+    pj, pr, minb = plans(5000, [5, 5, 5, 5, 8])
+    assert pj.startswith("5000, 625, 1,") and pr == pj
+
+
 def test_compile_time_kernel_table_is_self_consistent(hs, product_lib):
     """csrc/hs_ct_table.cuh: every two-pass descriptor factors its length, and both of its stage lists belong to a sub-plan
     the host side can launch by id (family HS_CT_SUB for first passes, HS_CT_SUB or HS_CT_SUB2 for second passes) -- the
