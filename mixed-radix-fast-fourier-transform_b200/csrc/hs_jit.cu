@@ -192,7 +192,7 @@ static bool choose(int n, const int *rx, int nst, JitChoice &c, bool allow_fat =
     if (((c.T + 31) / 32 * 32) * (pts <= 10 ? 80 : 128) > 65536 && maxpp <= 8) { c.T = (c.T + 1) / 2; pts *= 2; }
     while (pts * 2 <= 10 && c.T > 128) { c.T = (c.T + 1) / 2; pts *= 2; } // radix 2..5 only: too little work per thread otherwise
     if (env_or("HSFFT_JIT_T", 0) > 0) { c.T = env_or("HSFFT_JIT_T", 0); pts = maxpp * ((n / maxpp + c.T - 1) / c.T); }
-    // Fewer, fatter threads for the longer lengths (n >= 1536): pairs fused up to 25 points, and a team so small that a thread
+    // Fewer, fatter threads for the longer lengths (n >= 1800): pairs fused up to 25 points, and a team so small that a thread
     // carries 16-32 points per pass -- 8-10 warps with that much independent work keep an SM busier than 16-24 warps of 5-10
     // points, and the smaller lengths fit three CTAs per SM at 168 registers.  Among the team sizes T = ceil(NB_p / k) (NB_p:
     // butterflies of pass p) with n/26 <= T <= n/15 and at most 32 points per thread, take the one for which the passes with
